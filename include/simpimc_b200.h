@@ -1,0 +1,215 @@
+/* simpimc_b200 -- C ABI of the B200-native action-evaluation path.
+ *
+ * Drop-in boundary for simpimc's `Action` operator API (src/actions/action_class.h:7-74)
+ * restricted to the pair actions, the Ewald k-space sums, the move action-deltas and the
+ * E / g(r) / S(k) estimator reductions.  Plain C: opaque handles, pointers and sizes, no
+ * exceptions and no torch / C++ types cross this boundary.  Every entry point returns
+ * PIMC_OK (0) or a negative pimc_status; pimc_last_error() gives the message.
+ *
+ * Where the reference holds ONE walker per process (src/framework/framework_class.h:44-53)
+ * a context here holds `n_clones` independent walkers of identical shape on one GPU; every
+ * per-walker scalar of the reference becomes an array of n_clones doubles.  With
+ * n_clones = 1 the calls are one-to-one with the reference's.
+ *
+ * Host layouts are the reference's: positions R[clone][particle][bead][dim]
+ * (species_class.h:66-70, bead_(p,b)).  Device layouts are private to the library.
+ *
+ * OLD/NEW semantics (path_class.h:95, bead_class.h:98): the context keeps the committed
+ * path (the reference's r_c / rho_k_c) plus, per species and clone, at most one pending
+ * proposal written by pimc_propose (the reference's r of the beads a move touched).
+ * mode = PIMC_OLD reads the committed path, PIMC_NEW reads it overlaid with the proposal.
+ * pimc_commit is Move::Accept / Move::Reject (bisect_class.h:24-36,127-139).
+ *
+ * Thread-compatibility: calls on one context must not overlap; different contexts are
+ * independent.  All work of a context is issued on one CUDA stream.
+ */
+#ifndef SIMPIMC_B200_H_
+#define SIMPIMC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    PIMC_OK = 0,
+    PIMC_ERR_INVALID = -1,     /* bad argument (reference: assert / abort, io_xml.h:118) */
+    PIMC_ERR_UNSUPPORTED = -2, /* valid in the reference, outside this path (e.g. max_level > 0) */
+    PIMC_ERR_CUDA = -3,        /* CUDA runtime failure; no CPU fallback exists */
+    PIMC_ERR_TABLE = -4        /* malformed pair-action table (reference: exit(1), david...:241) */
+} pimc_status;
+
+enum { PIMC_OLD = 0, PIMC_NEW = 1 }; /* ModeType, bead_class.h:7-8 */
+
+typedef struct pimc_ctx pimc_ctx;       /* Path + Species[] + KSpace for n_clones walkers */
+typedef struct pimc_action pimc_action; /* one PairAction subclass instance */
+
+/* <System> and <Species> attributes (path_class.h:25-69, species_class.h:48-60). */
+typedef struct {
+    int32_t n_d;           /* spatial dimensions; this build evaluates n_d = 3 */
+    int32_t pbc;           /* periodic box (path_class.h:29) */
+    double L;              /* box side, ignored when pbc = 0 */
+    double beta;           /* inverse temperature; tau = beta / n_bead */
+    int32_t n_bead;        /* M: time slices of the whole path */
+    int32_t n_species;
+    const int32_t *n_part; /* [n_species] */
+    const double *lambda;  /* [n_species] hbar^2/2m */
+    int32_t n_clones;      /* independent walkers batched in this context */
+    int32_t device;        /* CUDA device ordinal */
+    int32_t slice_lo;      /* time-slice shard [slice_lo, slice_hi) owned by this context; */
+    int32_t slice_hi;      /* 0, n_bead for an unsharded path */
+} pimc_config;
+
+/* ---- pair-action tables: the datasets the reference constructors read ------------------ */
+typedef struct {
+    int32_t n;
+    const double *r; /* grid, ascending */
+    const double *f; /* values on the grid */
+} pimc_table_1d;
+
+typedef struct {
+    int32_t n_x, n_y;
+    const double *x, *y;
+    const double *f; /* row-major f[ix*n_y + iy] (ilkka_pair_action_class.h:272-280) */
+} pimc_table_2d;
+
+/* <obj>/diag/{r_long, <obj>_long_r, <obj>_long_r_0, k, <obj>_long_k, <obj>_long_k_0} */
+typedef struct {
+    pimc_table_1d f_r;
+    double f_r_0;
+    int32_t n_k;
+    const double *k;   /* |k| shell list, first entry 0 (Ewald.py:295-318) */
+    const double *f_k; /* value per shell */
+    double f_k_0;
+} pimc_long_range;
+
+typedef struct { /* ilkka_pair_action_class.h:266-418 */
+    pimc_table_2d u_xy, du_xy;
+    pimc_table_1d v_r;
+    pimc_long_range u_long, du_long, v_long; /* read only when use_long_range */
+} pimc_ilkka_tables;
+
+typedef struct { /* bare_pair_action_class.h:38-95 */
+    pimc_table_1d v_r;
+    pimc_long_range v_long;
+    int32_t is_coulomb; /* analytic 1/2r + 1/2r' instead of the v spline (bare...:106-108) */
+} pimc_bare_tables;
+
+enum { PIMC_GRID_GENERAL = 0, PIMC_GRID_LOG = 1, PIMC_GRID_LINEAR = 2 };
+typedef struct { /* david_pair_action_class.h:194-336 */
+    int32_t grid_type;
+    double r_start, r_end;
+    int32_t n_grid;
+    const double *grid_points; /* used when grid_type = GENERAL */
+    int32_t n_order;           /* n_val = 1 + sum_{i=1..n_order}(1+i) */
+    int32_t n_tau;             /* = max_level + 1; this build takes 1 */
+    const double *taus;        /* [n_tau] */
+    const double *u_kj;        /* file order [n_grid][n_val][n_tau] */
+    const double *du_kj_dbeta; /* same shape */
+    const double *potential;   /* [n_grid] */
+    int32_t n_k;               /* long_range/{n_k,k_points,u_k}, squarer/v_image */
+    const double *k_points;
+    const double *u_k;
+    double v_image;
+} pimc_david_tables;
+
+/* ---- context ------------------------------------------------------------------------ */
+const char *pimc_last_error(void);
+int pimc_version(void);
+int pimc_ctx_create(const pimc_config *cfg, pimc_ctx **out);
+int pimc_ctx_destroy(pimc_ctx *ctx);
+int pimc_ctx_sync(pimc_ctx *ctx);           /* wait for the context's stream */
+void *pimc_ctx_stream(pimc_ctx *ctx);       /* the cudaStream_t all kernels run on */
+
+/* KSpace::Setup (k_space_class.h:33-80): grow-only, returns the vector count. */
+int pimc_kspace_setup(pimc_ctx *ctx, double k_cut, int32_t *n_k);
+/* k_index[n_k][n_d] (signed lattice indices, reference order), k_mag[n_k]. */
+int pimc_kspace_get(pimc_ctx *ctx, int32_t *k_index, double *k_mag);
+
+/* Species::InitPaths + InitRhoK (species_class.h:222-403): set r and r_c of clones
+ * [clone_lo, clone_hi) of one species from host memory and rebuild rho_k.
+ * R[clone][particle][bead][dim], bead running over the context's shard
+ * [slice_lo, slice_hi] -- INCLUDING the halo slice slice_hi (mod n_bead) when sharded;
+ * exactly n_bead beads when unsharded. */
+int pimc_positions_upload(pimc_ctx *ctx, int32_t species, int32_t clone_lo, int32_t clone_hi, const double *R);
+int pimc_positions_download(pimc_ctx *ctx, int32_t species, int32_t mode, int32_t clone_lo, int32_t clone_hi, double *R);
+/* Same, from / to DEVICE memory in the library's own layout R[clone][bead][dim][particle]. */
+int pimc_positions_set_device(pimc_ctx *ctx, int32_t species, const double *d_R);
+double *pimc_positions_device_ptr(pimc_ctx *ctx, int32_t species);
+int pimc_rhok_rebuild(pimc_ctx *ctx, int32_t species); /* Species::InitRhoK */
+/* rho_k of one clone, out[bead][n_k][2] (re, im) (Species::GetRhoK, species_class.h:428). */
+int pimc_rhok_download(pimc_ctx *ctx, int32_t species, int32_t mode, int32_t clone, double *out);
+
+/* ---- actions (ActionFactory, actions.h:13-35; PairAction ctor, pair_action_class.h:204-238) */
+int pimc_action_create_ilkka(pimc_ctx *ctx, int32_t species_a, int32_t species_b, const pimc_ilkka_tables *t,
+                             int32_t max_level, int32_t use_long_range, double k_cut, pimc_action **out);
+int pimc_action_create_bare(pimc_ctx *ctx, int32_t species_a, int32_t species_b, const pimc_bare_tables *t,
+                            int32_t max_level, int32_t use_long_range, double k_cut, pimc_action **out);
+int pimc_action_create_david(pimc_ctx *ctx, int32_t species_a, int32_t species_b, const pimc_david_tables *t,
+                             int32_t max_level, int32_t use_long_range, pimc_action **out);
+int pimc_action_destroy(pimc_action *act);
+
+/* Action::DActionDBeta (pair_action_class.h:241-264) and Action::Potential (:369-395),
+ * one double per clone, long-range k-sum and constants included.  `out` is host memory.
+ * For a sharded context the value is this shard's partial sum (constants on the rank
+ * that owns slice 0); the caller all-reduces. */
+int pimc_action_dbeta(pimc_action *act, double *out);
+int pimc_action_potential(pimc_action *act, double *out);
+/* Same, result left in device memory (for NCCL all-reduce without a host round trip). */
+int pimc_action_dbeta_device(pimc_action *act, double *d_out);
+int pimc_action_potential_device(pimc_action *act, double *d_out);
+
+/* Action::GetAction(b0, b1, particles, level) (pair_action_class.h:267-302).
+ *   b0[n_clones]                first slice of each clone's window; b1 = b0 + n_window
+ *   moved_species[n_moved]      species of each moved particle (same for all clones)
+ *   moved_particle[n_clones][n_moved]
+ * Returns 0 for level > max_level or constant actions, as the reference does.  In NEW mode
+ * with use_long_range the first call after pimc_commit / pimc_action_accept refreshes the
+ * proposal's rho_k (Species::UpdateRhoK, species_class.h:406-425). */
+int pimc_action_get(pimc_action *act, int32_t mode, const int32_t *b0, int32_t n_window, int32_t n_moved,
+                    const int32_t *moved_species, const int32_t *moved_particle, int32_t level, double *out);
+/* Whole-path action of every clone: GetAction(0, n_bead, all particles, 0) in OLD mode. */
+int pimc_action_total(pimc_action *act, double *out);
+int pimc_action_total_device(pimc_action *act, double *d_out);
+int pimc_action_accept(pimc_action *act); /* PairAction::Accept, pair_action_class.h:406-411 */
+int pimc_action_reject(pimc_action *act); /* PairAction::Reject, :414-419 */
+
+/* Per-pair kernels on caller-supplied distances (tests; CalcU / CalcdUdBeta / CalcV).
+ * which: 0 = U, 1 = dU/dbeta, 2 = V.  Arrays are host memory of length n. */
+int pimc_action_calc_pair(pimc_action *act, int32_t which, int32_t n, const double *r, const double *r_p,
+                          const double *s, int32_t level, double *out);
+
+/* ---- moves' contract ------------------------------------------------------------------ */
+/* NEW-mode Bead::SetR for one particle per clone (bisect_class.h:89-94,
+ * displace_particle_class.h:40-50): beads b_first[c] .. b_first[c]+n_beads-1 (mod n_bead)
+ * of particle[c] take newR[c][i][dim]. */
+int pimc_propose(pimc_ctx *ctx, int32_t species, const int32_t *particle, const int32_t *b_first, int32_t n_beads,
+                 const double *newR);
+/* Move::Accept (accept[c] != 0) or Move::Reject for the pending proposals of all species:
+ * StoreR/StoreRhoK or RestoreR/RestoreRhoK, then every action's flag is re-armed. */
+int pimc_commit(pimc_ctx *ctx, const int32_t *accept);
+
+/* ---- estimators ------------------------------------------------------------------------ */
+/* PairCorrelation::Accumulate (pair_correlation_class.h:15-28): y[c][i] += cofactor[c] for
+ * every pair and slice, bin i = (uint32)nearbyint((|dr|-r_min)*d_ir - 0.5), i < n_r kept.
+ * y is host memory [n_clones][n_r] and is ADDED to.  cofactor may be NULL (= 1). */
+int pimc_est_gofr(pimc_ctx *ctx, int32_t species_a, int32_t species_b, double r_min, double r_max, int32_t n_r,
+                  const double *cofactor, double *y);
+/* Integer bin counts (bit-exact part): counts[c][i], host memory, overwritten. */
+int pimc_est_gofr_counts(pimc_ctx *ctx, int32_t species_a, int32_t species_b, double r_min, double r_max, int32_t n_r,
+                         uint64_t *counts);
+/* StructureFactor::Accumulate (structure_factor_class.h:15-32): sk[c][k] += cofactor[c] *
+ * sum_b Re(rho_a rho_b^*) for |k| < k_cut.  Host memory [n_clones][n_k], ADDED to. */
+int pimc_est_sofk(pimc_ctx *ctx, int32_t species_a, int32_t species_b, double k_cut, const double *cofactor, double *sk);
+
+/* ---- measurement helpers ------------------------------------------------------------- */
+/* Number of kernels this library launched since the context was created. */
+int64_t pimc_ctx_launch_count(pimc_ctx *ctx);
+/* FP64 FMA micro-benchmark on the context's device: returns achieved TFLOP/s (2 flop/FMA). */
+int pimc_fp64_peak(pimc_ctx *ctx, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMPIMC_B200_H_ */

@@ -1,0 +1,2 @@
+// TEST INFRASTRUCTURE ONLY -- see einspline_shim.h
+#include "einspline_shim.h"

@@ -1,0 +1,131 @@
+"""Host-side description of a path-integral system: the fields the reference reads from its
+XML input (<System>, <Species>, <Action>; src/data_structures/path_class.h:25-69,
+species_class.h:48-60, actions/action_class.h:25-33, pair_action_class.h:208-222) plus the
+synthetic configurations SURVEY.md section 8(d) defines for the BASELINE shapes.
+"""
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from . import tables as T
+
+
+@dataclass
+class SpeciesConfig:
+    name: str
+    n_part: int
+    lam: float  # hbar^2/2m, the XML attribute "lambda"
+
+
+@dataclass
+class ActionConfig:
+    name: str
+    type: str  # "IlkkaPairAction" | "BarePairAction" | "DavidPairAction" | "Kinetic"
+    species_a: str
+    species_b: str = ""
+    table: Optional[dict] = None
+    max_level: int = 0
+    use_long_range: bool = False
+    k_cut: Optional[float] = None
+    n_order: int = 0
+    is_coulomb: bool = False
+    n_images: int = 0
+
+
+@dataclass
+class SystemConfig:
+    n_d: int
+    n_bead: int
+    beta: float
+    L: float
+    pbc: bool = True
+    k_cut: Optional[float] = None  # <System k_cut=...>; default 2*pi/L gives no k vectors
+    species: List[SpeciesConfig] = field(default_factory=list)
+    actions: List[ActionConfig] = field(default_factory=list)
+    moves: List[dict] = field(default_factory=list)
+    observables: List[dict] = field(default_factory=list)
+
+    @property
+    def tau(self):
+        return self.beta / (1.0 * self.n_bead)
+
+    def species_index(self, name):
+        for i, s in enumerate(self.species):
+            if s.name == name:
+                return i
+        raise KeyError(name)
+
+
+def ueg_parameters(N, rs=1.0, theta=1.0, polarized=True):
+    """inputs/e-gas/gen_e_pa.py:14-31: box, k_cut = 14/(L/2) and beta = 1/(theta T_F)."""
+    if polarized:
+        TF = 0.5 * (9.0 * math.pi / 2.0) ** (2.0 / 3.0) / (rs ** 2)
+    else:
+        TF = 0.5 * (9.0 * math.pi / 4.0) ** (2.0 / 3.0) / (rs ** 2)
+    beta = 1.0 / (theta * TF)
+    L = pow(N * (4.0 / 3.0) * math.pi * rs ** 3, 1.0 / 3.0)
+    k_cut = 14.0 / (L / 2.0)
+    return L, k_cut, beta
+
+
+def ueg_config(N=256, M=128, rs=1.0, theta=1.0, action="IlkkaPairAction", use_long_range=True, n_xy=100, n_r_long=1000,
+               with_kinetic=False):
+    """Uniform electron gas, one species "e" (SURVEY.md 8(d), config C3 at the defaults)."""
+    L, k_cut, beta = ueg_parameters(N, rs, theta)
+    tau = beta / M
+    cfg = SystemConfig(n_d=3, n_bead=M, beta=beta, L=L, pbc=True, k_cut=k_cut)
+    cfg.species.append(SpeciesConfig("e", N, 0.5))
+    if with_kinetic:
+        cfg.actions.append(ActionConfig("Kinetic", "Kinetic", "e"))
+    if action == "IlkkaPairAction":
+        tab = T.make_ilkka_table(1.0, tau, L, k_cut, use_long_range=use_long_range, n_xy=n_xy, n_r_long=n_r_long)
+    elif action == "BarePairAction":
+        tab = T.make_bare_table(1.0, L, k_cut, use_long_range=use_long_range, n_r_long=n_r_long)
+    elif action == "DavidPairAction":
+        tab = T.make_david_table(1.0, tau, n_order=2, r_end=0.95 * math.sqrt(3.0) * L / 2.0, L=L, k_cut=k_cut,
+                                 use_long_range=use_long_range)
+    else:
+        raise ValueError(action)
+    cfg.actions.append(ActionConfig("CoulombEE", action, "e", "e", table=tab, max_level=0, use_long_range=use_long_range,
+                                    k_cut=k_cut, n_order=2 if action == "DavidPairAction" else 0))
+    return cfg
+
+
+def plasma_config(Ne=8, Np=8, M=16, rs=1.0, theta=1.0, n_xy=60, n_r_long=400):
+    """Two-species hydrogen-like plasma (config C5 shape at reduced size): e-e, e-p Ilkka
+    actions and a Bare p-p action, all with long range (as inputs/C/c.xml mixes them)."""
+    L, k_cut, beta = ueg_parameters(Ne, rs, theta)
+    tau = beta / M
+    cfg = SystemConfig(n_d=3, n_bead=M, beta=beta, L=L, pbc=True, k_cut=k_cut)
+    cfg.species.append(SpeciesConfig("e", Ne, 0.5))
+    cfg.species.append(SpeciesConfig("p", Np, 0.5 / 1836.15267))
+    cfg.actions.append(ActionConfig("CoulombEE", "IlkkaPairAction", "e", "e", max_level=0, use_long_range=True, k_cut=k_cut,
+                                    table=T.make_ilkka_table(1.0, tau, L, k_cut, n_xy=n_xy, n_r_long=n_r_long)))
+    cfg.actions.append(ActionConfig("CoulombEP", "IlkkaPairAction", "e", "p", max_level=0, use_long_range=True, k_cut=k_cut,
+                                    table=T.make_ilkka_table(-1.0, tau, L, k_cut, n_xy=n_xy, n_r_long=n_r_long, sigma=0.4)))
+    cfg.actions.append(ActionConfig("CoulombPP", "BarePairAction", "p", "p", max_level=0, use_long_range=True, k_cut=k_cut,
+                                    table=T.make_bare_table(1.0, L, k_cut, n_r_long=n_r_long)))
+    return cfg
+
+
+def synthetic_paths(cfg, sp, clone, seed=12345):
+    """Closed Brownian-bridge paths R[particle][bead][dim] for species index `sp` of clone
+    `clone`: centres uniform in [-L/2, L/2)^3, bead b = centre + bridge with
+    variance 2*lambda*tau per link; generator numpy default_rng(seed + clone) advanced per
+    species in order."""
+    rng = np.random.default_rng(seed + clone)
+    out = None
+    for i, s in enumerate(cfg.species):
+        N, M, nd = s.n_part, cfg.n_bead, cfg.n_d
+        half = cfg.L / 2.0 if cfg.pbc else 1.0
+        centres = rng.uniform(-half, half, size=(N, 1, nd))
+        steps = rng.normal(0.0, math.sqrt(2.0 * s.lam * cfg.tau), size=(N, M, nd))
+        walk = np.cumsum(steps, axis=1)
+        frac = (np.arange(1, M + 1) / M).reshape(1, M, 1)
+        bridge = walk - frac * walk[:, -1:, :]
+        R = centres + bridge
+        if i == sp:
+            out = np.ascontiguousarray(R)
+    return out
