@@ -1,0 +1,1189 @@
+// C ABI of the B200-native action-evaluation path: implementation of include/simpimc_b200.h.
+//
+// Host side of the boundary: owns the device buffers of a context (n_clones walkers), builds
+// the spline tables and k-space lists the way the reference's constructors do, and launches
+// the kernels in kernels.cuh on the context's stream.  There is no CPU fallback: every
+// compute entry point fails with PIMC_ERR_CUDA when no device is usable.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/simpimc_b200.h"
+#include "kernels.cuh"
+#include "spline_build.h"
+
+using namespace pimc;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int Fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define PIMC_CUDA(expr)                                                                                   \
+    do {                                                                                                  \
+        cudaError_t e__ = (expr);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return Fail(PIMC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));              \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t Alloc(size_t count) {
+        Free();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void **)&p, count * sizeof(T));
+    }
+    void Free() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { Free(); }
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
+struct SpeciesState {
+    int N = 0, Npad = 0;
+    double lambda = 0.;
+    DevBuf<double> R;        // committed positions [C][Mstore][3][Npad]
+    DevBuf<double2> rho;     // committed rho_k [C][Mloc][n_k]
+    // pending proposal
+    DevBuf<double> P;        // [C][n_prop][3]
+    DevBuf<int32_t> P_particle, P_first;
+    int n_prop = 0;
+    // rho_k increment of the proposal over the window it was computed for
+    DevBuf<double2> drho;
+    DevBuf<int32_t> drho_b0;
+    int drho_window = 0;
+    bool drho_valid = false;
+    bool need_update_rho_k = true;  // Species::need_update_rho_k_ (species_class.h:25)
+};
+
+}  // namespace
+
+struct pimc_ctx {
+    int n_d = 3, pbc = 1, M = 0, C = 0, device = 0;
+    double L = 0, iL = 0, vol = 1, beta = 0, tau = 0;
+    int slice_lo = 0, slice_hi = 0, Mloc = 0, Mstore = 0, sharded = 0;
+    cudaStream_t stream = nullptr;
+    int n_sm = 148;
+    size_t smem_optin = 0;
+    std::vector<std::unique_ptr<SpeciesState>> species;
+    // KSpace (k_space_class.h:6-15)
+    double k_cutoff = 0.;
+    int max_index = 0;
+    std::vector<int32_t> k_index;  // [n_k][3] signed lattice indices
+    std::vector<double> k_mag;
+    DevBuf<int32_t> d_kidx;        // [n_k][3] offset by max_index
+    DevBuf<double> d_kmag;
+    // scratch
+    DevBuf<double> partial, out_dev, lr_dev, stage;
+    DevBuf<int32_t> i32_a, i32_b, i32_c, i32_d;
+    DevBuf<unsigned long long> counts;
+    DevBuf<double> est;
+    std::vector<pimc_action *> actions;
+    int64_t launches = 0;
+
+    int n_k() const { return (int)k_mag.size(); }
+    PathView View() const {
+        PathView v;
+        v.C = C;
+        v.M = M;
+        v.Mloc = Mloc;
+        v.Mstore = Mstore;
+        v.slice_lo = slice_lo;
+        v.sharded = sharded;
+        v.box.L = L;
+        v.box.iL = iL;
+        return v;
+    }
+    SpeciesView SView(int s, bool with_proposal) const {
+        const SpeciesState &st = *species[s];
+        SpeciesView v;
+        v.R = st.R.p;
+        v.N = st.N;
+        v.Npad = st.Npad;
+        v.P = st.P.p;
+        v.P_particle = st.P_particle.p;
+        v.P_first = st.P_first.p;
+        v.n_prop = with_proposal ? st.n_prop : 0;
+        return v;
+    }
+    KSpaceView KView() const {
+        KSpaceView k;
+        k.n_k = n_k();
+        k.max_index = max_index;
+        k.kidx = d_kidx.p;
+        k.kbox = 2. * M_PI / L;
+        return k;
+    }
+};
+
+struct pimc_action {
+    pimc_ctx *ctx = nullptr;
+    int atype = ATYPE_ILKKA;
+    int sa = 0, sb = 0;
+    int max_level = 0;
+    bool use_long_range = false;
+    bool is_constant = false;
+    // table blobs per evaluated quantity (U, dU, V)
+    DevBuf<double> blob[3];
+    PairTable table[3];
+    // long range: weight per k vector and scaled constants
+    DevBuf<double> wk[3];
+    double k0[3] = {0, 0, 0}, r0[3] = {0, 0, 0};
+    double ulong_scale = 1.;  // Bare CalcULong: level_tau
+};
+
+namespace {
+
+// -------------------------------------------------------------------------------- helpers
+int EnsureI32(pimc_ctx *ctx, DevBuf<int32_t> &buf, const int32_t *host, size_t n) {
+    if (buf.n < n) PIMC_CUDA(buf.Alloc(n));
+    PIMC_CUDA(cudaMemcpyAsync(buf.p, host, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    return PIMC_OK;
+}
+
+int GridFor(const pimc_ctx *ctx, int items) { return std::max(1, std::min(items, ctx->n_sm * 8)); }
+
+// KSpace::Setup (k_space_class.h:33-80).  The reference walks GenCombPermK's list
+// (algorithm.h:101-121): sorted index multisets in lexicographic order, each followed by its
+// distinct permutations in lexicographic order.  Equivalent total order: sort all lattice
+// triples by (sorted triple, triple).
+void BuildKSpace(pimc_ctx *ctx, double k_cut) {
+    ctx->k_index.clear();
+    ctx->k_mag.clear();
+    ctx->k_cutoff = k_cut;
+    const double kb = 2. * M_PI / ctx->L;
+    const int m = (int)(uint32_t)std::ceil(1.1 * k_cut / kb);
+    ctx->max_index = m;
+    struct Cand {
+        int s[3], v[3];
+    };
+    std::vector<Cand> cands;
+    for (int i = -m; i <= m; ++i)
+        for (int j = -m; j <= m; ++j)
+            for (int k = -m; k <= m; ++k) {
+                Cand c;
+                c.v[0] = i;
+                c.v[1] = j;
+                c.v[2] = k;
+                c.s[0] = i;
+                c.s[1] = j;
+                c.s[2] = k;
+                std::sort(c.s, c.s + 3);
+                cands.push_back(c);
+            }
+    std::sort(cands.begin(), cands.end(), [](const Cand &a, const Cand &b) {
+        for (int d = 0; d < 3; ++d)
+            if (a.s[d] != b.s[d]) return a.s[d] < b.s[d];
+        for (int d = 0; d < 3; ++d)
+            if (a.v[d] != b.v[d]) return a.v[d] < b.v[d];
+        return false;
+    });
+    for (const Cand &c : cands) {
+        const double k0 = c.v[0] * kb, k1 = c.v[1] * kb, k2 = c.v[2] * kb;
+        // dot(k,k) in the reference's pairing (x0^2 + x2^2) + x1^2; no contraction on the host
+        const double kk = (k0 * k0 + k2 * k2) + k1 * k1;
+        if (!(kk < k_cut * k_cut && kk != 0.)) continue;
+        const bool keep = (k0 > 0.) || (k0 == 0. && k1 > 0.) || (k0 == 0. && k1 == 0. && k2 > 0.);
+        if (!keep) continue;
+        ctx->k_index.push_back(c.v[0]);
+        ctx->k_index.push_back(c.v[1]);
+        ctx->k_index.push_back(c.v[2]);
+        ctx->k_mag.push_back(std::sqrt(kk));
+    }
+}
+
+int UploadKSpace(pimc_ctx *ctx) {
+    const int n_k = ctx->n_k();
+    std::vector<int32_t> off(ctx->k_index);
+    for (auto &v : off) v += ctx->max_index;
+    PIMC_CUDA(ctx->d_kidx.Alloc(std::max(1, n_k * 3)));
+    PIMC_CUDA(ctx->d_kmag.Alloc(std::max(1, n_k)));
+    if (n_k) {
+        PIMC_CUDA(cudaMemcpyAsync(ctx->d_kidx.p, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        PIMC_CUDA(cudaMemcpyAsync(ctx->d_kmag.p, ctx->k_mag.data(), n_k * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    PIMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PIMC_OK;
+}
+
+int RebuildRhoK(pimc_ctx *ctx, int s) {
+    SpeciesState &st = *ctx->species[s];
+    const int n_k = ctx->n_k();
+    st.drho_valid = false;
+    st.need_update_rho_k = true;
+    if (n_k == 0) {
+        st.rho.Free();
+        return PIMC_OK;
+    }
+    const size_t need = (size_t)ctx->C * ctx->Mloc * n_k;
+    if (st.rho.n != need) PIMC_CUDA(st.rho.Alloc(need));
+    const int tl = 2 * ctx->max_index + 1;
+    int chunk = std::max(1, std::min(32, (int)(40000 / (3 * tl * sizeof(double2)))));
+    const size_t smem = (size_t)chunk * 3 * tl * sizeof(double2);
+    const int items = ctx->C * ctx->Mloc;
+    rhok_build_kernel<<<GridFor(ctx, items), 256, smem, ctx->stream>>>(ctx->View(), ctx->SView(s, false), ctx->KView(), chunk, st.rho.p);
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    return PIMC_OK;
+}
+
+// --------------------------------------------------------------------------- table packing
+void Fill1D(Sp1Desc &d, int n, int base, const double *grid) {
+    d.n = n;
+    d.off_t = base;
+    d.off_w = base + (n + 5);
+    d.off_c = base + (n + 5) + 3 * (n + 2);
+    d.n_splines = 1;
+    d.code = GRIDCODE_GENERAL;
+    d.r_min = grid[0];
+    d.r_max = grid[n - 1];
+    d.ainv = 0.;
+    d.startinv = 0.;
+}
+
+void CheckTable1D(const pimc_table_1d &t, const char *what) {
+    if (t.n < 4 || !t.r || !t.f) throw std::invalid_argument(std::string(what) + ": missing or too short");
+}
+
+// ilkka_pair_action_class.h:308-315: weight of each k vector = table value of the shell whose
+// |k| matches within 1e-8 (last match wins), else 0.
+std::vector<double> MatchShells(const pimc_ctx *ctx, const pimc_long_range &lr) {
+    std::vector<double> w(ctx->n_k(), 0.);
+    for (int k_i = 0; k_i < ctx->n_k(); ++k_i)
+        for (int k_t = 0; k_t < lr.n_k; ++k_t)
+            if (std::fabs(ctx->k_mag[k_i] - lr.k[k_t]) < 1.e-8) w[k_i] = lr.f_k[k_t];
+    return w;
+}
+
+// ilkka...:421-431, bare...:89-95, david...:347-358
+void ScaleConstants(const pimc_ctx *ctx, const pimc_action *a, double &k0, double &r0) {
+    const int Na = ctx->species[a->sa]->N, Nb = ctx->species[a->sb]->N;
+    if (a->sa == a->sb) {
+        k0 *= 0.5 * Na * Nb * ctx->M;
+        r0 *= -0.5 * Na * ctx->M;
+    } else {
+        k0 *= Na * Nb * ctx->M;
+        r0 *= 0.;
+    }
+}
+
+int UploadBlob(pimc_ctx *ctx, DevBuf<double> &dst, const std::vector<double> &blob) {
+    PIMC_CUDA(dst.Alloc(blob.size()));
+    PIMC_CUDA(cudaMemcpy(dst.p, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return PIMC_OK;
+}
+int UploadVec(DevBuf<double> &dst, const std::vector<double> &v) {
+    PIMC_CUDA(dst.Alloc(std::max<size_t>(1, v.size())));
+    if (!v.empty()) PIMC_CUDA(cudaMemcpy(dst.p, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return PIMC_OK;
+}
+
+// PairAction constructor (pair_action_class.h:204-238)
+int NewAction(pimc_ctx *ctx, int atype, int sa, int sb, int max_level, int use_lr, double k_cut, pimc_action **out) {
+    if (!ctx || !out) return Fail(PIMC_ERR_INVALID, "null context or output");
+    if (sa < 0 || sb < 0 || sa >= (int)ctx->species.size() || sb >= (int)ctx->species.size())
+        return Fail(PIMC_ERR_INVALID, "species index out of range");
+    if (max_level != 0)
+        return Fail(PIMC_ERR_UNSUPPORTED,
+                    "max_level > 0: the reference's long-range update assumes level 0 (pair_action_class.h:293) and every "
+                    "shipped input uses max_level=0");
+    if (use_lr && !ctx->pbc) return Fail(PIMC_ERR_INVALID, "use_long_range needs a periodic box");
+    pimc_action *a = new pimc_action;
+    a->ctx = ctx;
+    a->atype = atype;
+    a->sa = sa;
+    a->sb = sb;
+    a->max_level = max_level;
+    a->use_long_range = use_lr != 0;
+    if (a->use_long_range && k_cut > ctx->k_cutoff) {
+        int32_t n_k;
+        int rc = pimc_kspace_setup(ctx, k_cut, &n_k);
+        if (rc != PIMC_OK) {
+            delete a;
+            return rc;
+        }
+    }
+    a->is_constant = (sa == sb) && (ctx->species[sa]->N == 1 || ctx->species[sa]->lambda == 0.);
+    *out = a;
+    return PIMC_OK;
+}
+
+int LoadLongRange(pimc_ctx *ctx, pimc_action *a, int which, const pimc_long_range &lr, std::vector<double> &blob, Sp1Desc &desc) {
+    CheckTable1D(lr.f_r, "long-range r table");
+    if (lr.n_k < 1 || !lr.k || !lr.f_k) throw std::invalid_argument("long-range k table missing");
+    const int base = (int)blob.size();
+    std::vector<double> b = BuildBlob1D(lr.f_r.r, lr.f_r.f, lr.f_r.n);
+    blob.insert(blob.end(), b.begin(), b.end());
+    Fill1D(desc, lr.f_r.n, base, lr.f_r.r);
+    int rc = UploadVec(a->wk[which], MatchShells(ctx, lr));
+    if (rc != PIMC_OK) return rc;
+    a->k0[which] = lr.f_k_0;
+    a->r0[which] = lr.f_r_0;
+    return PIMC_OK;
+}
+
+// ------------------------------------------------------------------------------ launchers
+template <int ATYPE, int WHICH>
+int LaunchPairFullT(pimc_ctx *ctx, const PairFullArgs &args, size_t smem, int grid) {
+    PIMC_CUDA(cudaFuncSetAttribute(pair_full_kernel<ATYPE, WHICH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    pair_full_kernel<ATYPE, WHICH><<<grid, kPairThreads, smem, ctx->stream>>>(args);
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    return PIMC_OK;
+}
+
+int LaunchPairFull(pimc_action *a, int which, bool independent_images) {
+    pimc_ctx *ctx = a->ctx;
+    PairFullArgs args;
+    args.pv = ctx->View();
+    args.A = ctx->SView(a->sa, false);
+    args.B = ctx->SView(a->sb, false);
+    args.same = a->sa == a->sb;
+    args.T = a->table[which];
+    args.blob = a->blob[which].p;
+    args.blob_doubles = (int)a->blob[which].n;
+    args.independent_images = independent_images ? 1 : 0;
+    const size_t items = (size_t)ctx->C * ctx->Mloc;
+    if (ctx->partial.n < items) PIMC_CUDA(ctx->partial.Alloc(items));
+    args.partial = ctx->partial.p;
+    const size_t pos_bytes = sizeof(double) * 2 * 3 * (args.A.Npad + (args.same ? 0 : args.B.Npad));
+    const size_t blob_bytes = sizeof(double) * a->blob[which].n;
+    args.stage = (pos_bytes + blob_bytes + 1024 <= ctx->smem_optin) ? 1 : 0;
+    const size_t smem = pos_bytes + (args.stage ? blob_bytes : 0);
+    if (smem > ctx->smem_optin) return Fail(PIMC_ERR_UNSUPPORTED, "species too large for the shared-memory position tile");
+    // persistent CTAs: as many as fit per SM given the staged table, never more than the items
+    int per_sm = std::max(1, (int)(ctx->smem_optin / std::max<size_t>(smem + 1024, 1)));
+    per_sm = std::min(per_sm, 2048 / kPairThreads);
+    const int grid = (int)std::min<size_t>(items, (size_t)ctx->n_sm * per_sm);
+#define PIMC_DISPATCH(AT)                                                                    \
+    switch (which) {                                                                         \
+        case WHICH_U: return LaunchPairFullT<AT, WHICH_U>(ctx, args, smem, grid);            \
+        case WHICH_DU: return LaunchPairFullT<AT, WHICH_DU>(ctx, args, smem, grid);          \
+        default: return LaunchPairFullT<AT, WHICH_V>(ctx, args, smem, grid);                 \
+    }
+    switch (a->atype) {
+        case ATYPE_ILKKA: PIMC_DISPATCH(ATYPE_ILKKA)
+        case ATYPE_BARE: PIMC_DISPATCH(ATYPE_BARE)
+        default: PIMC_DISPATCH(ATYPE_DAVID)
+    }
+#undef PIMC_DISPATCH
+}
+
+/// Long-range k sum over the whole shard (b0 == nullptr) or over a window, into ctx->lr_dev.
+int LaunchKSum(pimc_action *a, int which, const int32_t *d_b0, int n_window, bool use_delta, double scale) {
+    pimc_ctx *ctx = a->ctx;
+    if ((int)ctx->lr_dev.n < ctx->C) PIMC_CUDA(ctx->lr_dev.Alloc(ctx->C));
+    KSumArgs k;
+    k.pv = ctx->View();
+    k.n_k = ctx->n_k();
+    k.rho_a = ctx->species[a->sa]->rho.p;
+    k.rho_b = ctx->species[a->sb]->rho.p;
+    k.drho_a = (use_delta && ctx->species[a->sa]->drho_valid) ? ctx->species[a->sa]->drho.p : nullptr;
+    k.drho_b = (use_delta && ctx->species[a->sb]->drho_valid) ? ctx->species[a->sb]->drho.p : nullptr;
+    k.wk = a->wk[which].p;
+    k.b0 = d_b0;
+    k.n_window = n_window;
+    k.twice = a->sa != a->sb;
+    k.scale = scale;
+    k.out = ctx->lr_dev.p;
+    ksum_kernel<<<ctx->C, 256, 0, ctx->stream>>>(k);
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    return PIMC_OK;
+}
+
+int Finalize(pimc_ctx *ctx, int n_per_clone, bool add_lr, double k0, double r0, bool add_const, double *d_out) {
+    finalize_kernel<<<(ctx->C + 127) / 128, 128, 0, ctx->stream>>>(ctx->partial.p, ctx->C, n_per_clone, ctx->lr_dev.p, add_lr ? 1 : 0, k0,
+                                                                   r0, add_const ? 1 : 0, d_out);
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    return PIMC_OK;
+}
+
+/// DActionDBeta (which = DU), Potential (V) or the whole-path action (U) into device memory.
+int FullEvaluation(pimc_action *a, int which, double *d_out) {
+    pimc_ctx *ctx = a->ctx;
+    if (a->is_constant) {
+        // App. A-1: a constant action has no pairs (one particle) or never changes; the
+        // reference caches its first value.  Only the no-pair case is evaluated here.
+        if (ctx->species[a->sa]->N != 1)
+            return Fail(PIMC_ERR_UNSUPPORTED, "constant action with lambda = 0 and more than one particle");
+    }
+    int rc = LaunchPairFull(a, which, which == WHICH_V);
+    if (rc != PIMC_OK) return rc;
+    if (a->use_long_range) {
+        if (ctx->n_k() > 0) {
+            const double scale = (which == WHICH_U) ? a->ulong_scale : 1.0;
+            rc = LaunchKSum(a, which, nullptr, 0, false, scale);
+            if (rc != PIMC_OK) return rc;
+        } else {  // no k vector inside the cutoff: empty k sum, the constants remain
+            if ((int)ctx->lr_dev.n < ctx->C) PIMC_CUDA(ctx->lr_dev.Alloc(ctx->C));
+            PIMC_CUDA(cudaMemsetAsync(ctx->lr_dev.p, 0, ctx->C * sizeof(double), ctx->stream));
+        }
+    }
+    // constants belong to the rank that owns slice 0 when the path is sharded
+    const bool add_const = (which != WHICH_U) && (!ctx->sharded || ctx->slice_lo == 0);
+    const double k0 = a->k0[which], r0 = a->r0[which];
+    return Finalize(ctx, ctx->Mloc, a->use_long_range, k0, r0, add_const, d_out);
+}
+
+int ToHost(pimc_ctx *ctx, const double *d_src, double *host, size_t n) {
+    PIMC_CUDA(cudaMemcpyAsync(host, d_src, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    PIMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PIMC_OK;
+}
+
+int EnsureOut(pimc_ctx *ctx) {
+    if ((int)ctx->out_dev.n < ctx->C) PIMC_CUDA(ctx->out_dev.Alloc(ctx->C));
+    return PIMC_OK;
+}
+
+}  // namespace
+
+// =========================================================================== C ABI
+extern "C" {
+
+const char *pimc_last_error(void) { return g_last_error.c_str(); }
+int pimc_version(void) { return 100; }
+
+int pimc_ctx_create(const pimc_config *cfg, pimc_ctx **out) {
+    if (!cfg || !out) return Fail(PIMC_ERR_INVALID, "null config or output");
+    if (cfg->n_d != 3) return Fail(PIMC_ERR_UNSUPPORTED, "only n_d = 3 is evaluated on the device");
+    if (cfg->n_bead < 1 || cfg->n_species < 1 || cfg->n_clones < 1) return Fail(PIMC_ERR_INVALID, "n_bead, n_species, n_clones must be >= 1");
+    if (cfg->pbc && !(cfg->L > 0.)) return Fail(PIMC_ERR_INVALID, "periodic box needs L > 0");
+    int lo = cfg->slice_lo, hi = cfg->slice_hi;
+    if (lo == 0 && hi == 0) hi = cfg->n_bead;
+    if (lo < 0 || hi > cfg->n_bead || lo >= hi) return Fail(PIMC_ERR_INVALID, "bad slice shard");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        return Fail(PIMC_ERR_CUDA, "no CUDA device visible; simpimc_b200 has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= n_dev) return Fail(PIMC_ERR_INVALID, "device ordinal out of range");
+    PIMC_CUDA(cudaSetDevice(cfg->device));
+    std::unique_ptr<pimc_ctx> ctx(new pimc_ctx);
+    ctx->n_d = cfg->n_d;
+    ctx->pbc = cfg->pbc != 0;
+    ctx->M = cfg->n_bead;
+    ctx->C = cfg->n_clones;
+    ctx->device = cfg->device;
+    ctx->beta = cfg->beta;
+    ctx->tau = cfg->beta / (1. * cfg->n_bead);
+    if (ctx->pbc) {  // path_class.h:33-42
+        ctx->L = cfg->L;
+        ctx->iL = 1. / cfg->L;
+        ctx->vol = std::pow(cfg->L, cfg->n_d);
+    } else {
+        ctx->L = 0.;
+        ctx->iL = 0.;
+        ctx->vol = 1.;
+    }
+    ctx->slice_lo = lo;
+    ctx->slice_hi = hi;
+    ctx->Mloc = hi - lo;
+    ctx->sharded = (ctx->Mloc != ctx->M);
+    ctx->Mstore = ctx->Mloc + (ctx->sharded ? 1 : 0);
+    PIMC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    cudaDeviceProp prop;
+    PIMC_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    ctx->n_sm = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    for (int s = 0; s < cfg->n_species; ++s) {
+        std::unique_ptr<SpeciesState> st(new SpeciesState);
+        st->N = cfg->n_part[s];
+        if (st->N < 1) return Fail(PIMC_ERR_INVALID, "species without particles");
+        st->Npad = (st->N + 3) & ~3;
+        st->lambda = cfg->lambda[s];
+        const size_t n = (size_t)ctx->C * ctx->Mstore * 3 * st->Npad;
+        PIMC_CUDA(st->R.Alloc(n));
+        PIMC_CUDA(cudaMemsetAsync(st->R.p, 0, n * sizeof(double), ctx->stream));
+        PIMC_CUDA(st->P_particle.Alloc(ctx->C));
+        PIMC_CUDA(st->P_first.Alloc(ctx->C));
+        PIMC_CUDA(st->drho_b0.Alloc(ctx->C));
+        ctx->species.push_back(std::move(st));
+    }
+    PIMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = ctx.release();
+    return PIMC_OK;
+}
+
+int pimc_ctx_destroy(pimc_ctx *ctx) {
+    if (!ctx) return PIMC_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (pimc_action *a : ctx->actions) delete a;
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return PIMC_OK;
+}
+
+int pimc_ctx_sync(pimc_ctx *ctx) {
+    if (!ctx) return Fail(PIMC_ERR_INVALID, "null context");
+    PIMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PIMC_OK;
+}
+void *pimc_ctx_stream(pimc_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int64_t pimc_ctx_launch_count(pimc_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int pimc_kspace_setup(pimc_ctx *ctx, double k_cut, int32_t *n_k) {
+    if (!ctx) return Fail(PIMC_ERR_INVALID, "null context");
+    if (!ctx->pbc) return Fail(PIMC_ERR_INVALID, "k space needs a periodic box");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    if (k_cut > ctx->k_cutoff) {  // grow-only (k_space_class.h:34-41)
+        BuildKSpace(ctx, k_cut);
+        int rc = UploadKSpace(ctx);
+        if (rc != PIMC_OK) return rc;
+        for (size_t s = 0; s < ctx->species.size(); ++s) {
+            rc = RebuildRhoK(ctx, (int)s);
+            if (rc != PIMC_OK) return rc;
+        }
+    }
+    if (n_k) *n_k = ctx->n_k();
+    return PIMC_OK;
+}
+
+int pimc_kspace_get(pimc_ctx *ctx, int32_t *k_index, double *k_mag) {
+    if (!ctx) return Fail(PIMC_ERR_INVALID, "null context");
+    if (k_index) std::memcpy(k_index, ctx->k_index.data(), ctx->k_index.size() * sizeof(int32_t));
+    if (k_mag) std::memcpy(k_mag, ctx->k_mag.data(), ctx->k_mag.size() * sizeof(double));
+    return PIMC_OK;
+}
+
+int pimc_positions_upload(pimc_ctx *ctx, int32_t s, int32_t clone_lo, int32_t clone_hi, const double *R) {
+    if (!ctx || !R) return Fail(PIMC_ERR_INVALID, "null argument");
+    if (s < 0 || s >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
+    if (clone_lo < 0 || clone_hi > ctx->C || clone_lo >= clone_hi) return Fail(PIMC_ERR_INVALID, "bad clone range");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    SpeciesState &st = *ctx->species[s];
+    const int nc = clone_hi - clone_lo;
+    const size_t n_host = (size_t)nc * st.N * ctx->Mstore * 3;
+    if (ctx->stage.n < n_host) PIMC_CUDA(ctx->stage.Alloc(n_host));
+    PIMC_CUDA(cudaMemcpyAsync(ctx->stage.p, R, n_host * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    double *dst = st.R.p + (size_t)clone_lo * ctx->Mstore * 3 * st.Npad;
+    positions_in_kernel<<<ctx->n_sm * 4, 256, 0, ctx->stream>>>(ctx->stage.p, nc, st.N, st.Npad, ctx->Mstore, dst);
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    st.n_prop = 0;
+    if (clone_lo == 0 && clone_hi == ctx->C) return RebuildRhoK(ctx, s);
+    st.need_update_rho_k = true;
+    st.drho_valid = false;
+    return PIMC_OK;  // partial upload: caller finishes with pimc_rhok_rebuild
+}
+
+int pimc_positions_download(pimc_ctx *ctx, int32_t s, int32_t mode, int32_t clone_lo, int32_t clone_hi, double *R) {
+    if (!ctx || !R) return Fail(PIMC_ERR_INVALID, "null argument");
+    if (s < 0 || s >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
+    if (clone_lo < 0 || clone_hi > ctx->C || clone_lo >= clone_hi) return Fail(PIMC_ERR_INVALID, "bad clone range");
+    if (mode != PIMC_OLD) return Fail(PIMC_ERR_UNSUPPORTED, "download returns the committed path; proposals live with the caller");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    SpeciesState &st = *ctx->species[s];
+    const int nc = clone_hi - clone_lo;
+    const size_t n_host = (size_t)nc * st.N * ctx->Mstore * 3;
+    if (ctx->stage.n < n_host) PIMC_CUDA(ctx->stage.Alloc(n_host));
+    const double *src = st.R.p + (size_t)clone_lo * ctx->Mstore * 3 * st.Npad;
+    positions_out_kernel<<<ctx->n_sm * 4, 256, 0, ctx->stream>>>(src, nc, st.N, st.Npad, ctx->Mstore, ctx->stage.p);
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    return ToHost(ctx, ctx->stage.p, R, n_host);
+}
+
+int pimc_positions_set_device(pimc_ctx *ctx, int32_t s, const double *d_R) {
+    if (!ctx || !d_R) return Fail(PIMC_ERR_INVALID, "null argument");
+    if (s < 0 || s >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    SpeciesState &st = *ctx->species[s];
+    PIMC_CUDA(cudaMemcpyAsync(st.R.p, d_R, st.R.n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    st.n_prop = 0;
+    return RebuildRhoK(ctx, s);
+}
+
+double *pimc_positions_device_ptr(pimc_ctx *ctx, int32_t s) {
+    if (!ctx || s < 0 || s >= (int)ctx->species.size()) return nullptr;
+    return ctx->species[s]->R.p;
+}
+
+int pimc_rhok_rebuild(pimc_ctx *ctx, int32_t s) {
+    if (!ctx) return Fail(PIMC_ERR_INVALID, "null context");
+    if (s < 0 || s >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    return RebuildRhoK(ctx, s);
+}
+
+int pimc_rhok_download(pimc_ctx *ctx, int32_t s, int32_t mode, int32_t clone, double *out) {
+    if (!ctx || !out) return Fail(PIMC_ERR_INVALID, "null argument");
+    if (s < 0 || s >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
+    if (clone < 0 || clone >= ctx->C) return Fail(PIMC_ERR_INVALID, "clone out of range");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    SpeciesState &st = *ctx->species[s];
+    const int n_k = ctx->n_k();
+    if (n_k == 0) return PIMC_OK;
+    const size_t n = (size_t)ctx->Mloc * n_k;
+    std::vector<double> host(2 * n);
+    PIMC_CUDA(cudaMemcpyAsync(host.data(), st.rho.p + (size_t)clone * n, n * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+    PIMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (mode == PIMC_NEW && st.drho_valid) {
+        // rho_k (NEW) = committed + increment on the window the increment was computed for
+        std::vector<double> d((size_t)2 * st.drho_window * n_k);
+        int32_t b0;
+        PIMC_CUDA(cudaMemcpy(d.data(), st.drho.p + (size_t)clone * st.drho_window * n_k, d.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        PIMC_CUDA(cudaMemcpy(&b0, st.drho_b0.p + clone, sizeof(int32_t), cudaMemcpyDeviceToHost));
+        for (int j = 0; j < st.drho_window; ++j) {
+            int b = (b0 + j) % ctx->M - ctx->slice_lo;
+            for (int k = 0; k < 2 * n_k; ++k) host[(size_t)b * 2 * n_k + k] += d[(size_t)j * 2 * n_k + k];
+        }
+    }
+    std::memcpy(out, host.data(), host.size() * sizeof(double));
+    return PIMC_OK;
+}
+
+// -------------------------------------------------------------------------------- actions
+int pimc_action_create_ilkka(pimc_ctx *ctx, int32_t sa, int32_t sb, const pimc_ilkka_tables *t, int32_t max_level,
+                             int32_t use_lr, double k_cut, pimc_action **out) {
+    if (!t) return Fail(PIMC_ERR_INVALID, "null tables");
+    pimc_action *a = nullptr;
+    int rc = NewAction(ctx, ATYPE_ILKKA, sa, sb, max_level, use_lr, k_cut, &a);
+    if (rc != PIMC_OK) return rc;
+    std::unique_ptr<pimc_action> guard(a);
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    try {
+        const pimc_table_2d *xy[2] = {&t->u_xy, &t->du_xy};
+        const pimc_long_range *lrs[3] = {&t->u_long, &t->du_long, &t->v_long};
+        for (int which = 0; which < 2; ++which) {
+            const pimc_table_2d &g = *xy[which];
+            if (g.n_x < 4 || g.n_y < 4 || !g.x || !g.y || !g.f) throw std::invalid_argument("off-diagonal table missing");
+            std::vector<double> blob = BuildBlob2D(g.x, g.n_x, g.y, g.n_y, g.f);
+            PairTable &T = a->table[which];
+            std::memset(&T, 0, sizeof(T));
+            T.xy.nx = g.n_x;
+            T.xy.ny = g.n_y;
+            T.xy.off_tx = 0;
+            T.xy.off_wx = g.n_x + 5;
+            T.xy.off_ty = T.xy.off_wx + 3 * (g.n_x + 2);
+            T.xy.off_wy = T.xy.off_ty + g.n_y + 5;
+            T.xy.off_c = T.xy.off_wy + 3 * (g.n_y + 2);
+            T.use_lr = a->use_long_range;
+            if (a->use_long_range) {
+                rc = LoadLongRange(ctx, a, which, *lrs[which], blob, T.lr);
+                if (rc != PIMC_OK) return rc;
+            }
+            rc = UploadBlob(ctx, a->blob[which], blob);
+            if (rc != PIMC_OK) return rc;
+        }
+        {
+            CheckTable1D(t->v_r, "v_r table");
+            std::vector<double> blob = BuildBlob1D(t->v_r.r, t->v_r.f, t->v_r.n);
+            PairTable &T = a->table[WHICH_V];
+            std::memset(&T, 0, sizeof(T));
+            Fill1D(T.a, t->v_r.n, 0, t->v_r.r);
+            T.use_lr = a->use_long_range;
+            if (a->use_long_range) {
+                rc = LoadLongRange(ctx, a, WHICH_V, t->v_long, blob, T.lr);
+                if (rc != PIMC_OK) return rc;
+            }
+            rc = UploadBlob(ctx, a->blob[WHICH_V], blob);
+            if (rc != PIMC_OK) return rc;
+        }
+    } catch (const std::exception &e) {
+        return Fail(PIMC_ERR_TABLE, e.what());
+    }
+    if (a->use_long_range) {
+        // only du and v constants are scaled and used (ilkka...:421-431); u has none in CalcULong
+        ScaleConstants(ctx, a, a->k0[WHICH_DU], a->r0[WHICH_DU]);
+        ScaleConstants(ctx, a, a->k0[WHICH_V], a->r0[WHICH_V]);
+    }
+    ctx->actions.push_back(guard.release());
+    *out = a;
+    return PIMC_OK;
+}
+
+int pimc_action_create_bare(pimc_ctx *ctx, int32_t sa, int32_t sb, const pimc_bare_tables *t, int32_t max_level,
+                            int32_t use_lr, double k_cut, pimc_action **out) {
+    if (!t) return Fail(PIMC_ERR_INVALID, "null tables");
+    pimc_action *a = nullptr;
+    int rc = NewAction(ctx, ATYPE_BARE, sa, sb, max_level, use_lr, k_cut, &a);
+    if (rc != PIMC_OK) return rc;
+    std::unique_ptr<pimc_action> guard(a);
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    try {
+        CheckTable1D(t->v_r, "v_r table");
+        // U, dU/dbeta and V all evaluate CalcV (bare...:146-150,175-182); one blob each keeps
+        // the kernels' addressing uniform
+        for (int which = 0; which < 3; ++which) {
+            std::vector<double> blob = BuildBlob1D(t->v_r.r, t->v_r.f, t->v_r.n);
+            PairTable &T = a->table[which];
+            std::memset(&T, 0, sizeof(T));
+            Fill1D(T.a, t->v_r.n, 0, t->v_r.r);
+            T.use_lr = a->use_long_range;
+            T.is_coulomb = t->is_coulomb != 0;
+            T.u_scale = ctx->tau;  // level 0: (1 >> 0) * tau
+            if (a->use_long_range) {
+                rc = LoadLongRange(ctx, a, which, t->v_long, blob, T.lr);
+                if (rc != PIMC_OK) return rc;
+            }
+            rc = UploadBlob(ctx, a->blob[which], blob);
+            if (rc != PIMC_OK) return rc;
+        }
+    } catch (const std::exception &e) {
+        return Fail(PIMC_ERR_TABLE, e.what());
+    }
+    if (a->use_long_range) {
+        ScaleConstants(ctx, a, a->k0[WHICH_DU], a->r0[WHICH_DU]);
+        ScaleConstants(ctx, a, a->k0[WHICH_V], a->r0[WHICH_V]);
+        a->ulong_scale = ctx->tau;  // bare...:170-171 at level 0
+    }
+    ctx->actions.push_back(guard.release());
+    *out = a;
+    return PIMC_OK;
+}
+
+int pimc_action_create_david(pimc_ctx *ctx, int32_t sa, int32_t sb, const pimc_david_tables *t, int32_t max_level,
+                             int32_t use_lr, pimc_action **out) {
+    if (!t) return Fail(PIMC_ERR_INVALID, "null tables");
+    pimc_action *a = nullptr;
+    int rc = NewAction(ctx, ATYPE_DAVID, sa, sb, max_level, use_lr, ctx ? ctx->k_cutoff : 0., &a);
+    if (rc != PIMC_OK) return rc;
+    std::unique_ptr<pimc_action> guard(a);
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    if (t->n_tau != 1) return Fail(PIMC_ERR_UNSUPPORTED, "DavidPairAction tables with more than one tau (max_level > 0)");
+    // david...:232-245: the path's tau has to be in the table
+    if (!t->taus || std::fabs(t->taus[0] - ctx->tau) >= 1.0e-6) return Fail(PIMC_ERR_TABLE, "tau of the path not found in the table");
+    if (t->n_grid < 4 || !t->u_kj || !t->du_kj_dbeta || !t->potential) return Fail(PIMC_ERR_TABLE, "DavidPairAction table missing");
+    try {
+        const int n = t->n_grid;
+        std::vector<double> grid(n);
+        double ainv = 0., startinv = 0.;
+        int code = GRIDCODE_GENERAL;
+        if (t->grid_type == PIMC_GRID_LOG) {  // einspline create_log_grid
+            const double aa = 1.0 / (double)(n - 1) * std::log(t->r_end / t->r_start);
+            for (int i = 0; i < n; ++i) grid[i] = t->r_start * std::exp(aa * (double)i);
+            ainv = 1.0 / aa;
+            startinv = 1.0 / t->r_start;
+            code = GRIDCODE_LOG;
+        } else if (t->grid_type == PIMC_GRID_LINEAR) {
+            for (int i = 0; i < n; ++i) grid[i] = t->r_start + (t->r_end - t->r_start) * (double)i / (double)(n - 1);
+        } else {
+            if (!t->grid_points) return Fail(PIMC_ERR_TABLE, "general grid without grid_points");
+            std::copy(t->grid_points, t->grid_points + n, grid.begin());
+        }
+        int n_val = 1;  // david...:252-254
+        for (int i = 1; i <= t->n_order; ++i) n_val += 1 + i;
+        for (int which = 0; which < 3; ++which) {
+            const double *data = (which == WHICH_DU) ? t->du_kj_dbeta : t->u_kj;
+            // david...:262-283: value 0 of every knot is the potential; the last grid point of
+            // every value stays 0 (the fill loop stops at n_grid-1)
+            std::vector<std::vector<double>> values(n_val + 1, std::vector<double>(n, 0.));
+            for (int v = 0; v < n_val + 1; ++v)
+                for (int g = 0; g < n - 1; ++g) values[v][g] = (v == 0) ? t->potential[g] : data[(size_t)(v - 1) + (size_t)n_val * g];
+            std::vector<double> blob = BuildBlobMulti(grid.data(), n, values);
+            PairTable &T = a->table[which];
+            std::memset(&T, 0, sizeof(T));
+            Fill1D(T.a, n, 0, grid.data());
+            T.a.n_splines = n_val + 1;
+            T.a.code = code;
+            T.a.ainv = ainv;
+            T.a.startinv = startinv;
+            T.a.r_min = (code == GRIDCODE_LOG) ? t->r_start : grid[0];
+            T.a.r_max = (code == GRIDCODE_LOG) ? t->r_end : grid[n - 1];
+            T.n_order = t->n_order;
+            T.use_lr = 0;  // David subtracts nothing in r space
+            rc = UploadBlob(ctx, a->blob[which], blob);
+            if (rc != PIMC_OK) return rc;
+        }
+    } catch (const std::exception &e) {
+        return Fail(PIMC_ERR_TABLE, e.what());
+    }
+    if (a->use_long_range) {  // david...:311-358
+        if (t->n_k < 1 || !t->k_points || !t->u_k) return Fail(PIMC_ERR_TABLE, "DavidPairAction long_range table missing");
+        const int n_k = ctx->n_k();
+        std::vector<double> u(n_k, 0.), du(n_k, 0.), v(n_k, 0.);
+        double v_long_k_0 = 0.;
+        for (int kv = 0; kv < t->n_k; ++kv) {
+            const double vk = t->u_k[kv] / ctx->vol;
+            if (std::fabs(0. - t->k_points[kv]) < 1.e-8) v_long_k_0 = vk;
+            for (int k_i = 0; k_i < n_k; ++k_i)
+                if (std::fabs(ctx->k_mag[k_i] - t->k_points[kv]) < 1.e-8) {
+                    u[k_i] = vk * ctx->tau;
+                    du[k_i] = vk;
+                    v[k_i] = vk;  // the reference indexes shells by vector index here (UB); see DESIGN.md
+                }
+        }
+        if ((rc = UploadVec(a->wk[WHICH_U], u)) != PIMC_OK) return rc;
+        if ((rc = UploadVec(a->wk[WHICH_DU], du)) != PIMC_OK) return rc;
+        if ((rc = UploadVec(a->wk[WHICH_V], v)) != PIMC_OK) return rc;
+        a->r0[WHICH_DU] = t->v_image;
+        a->r0[WHICH_V] = t->v_image;
+        a->k0[WHICH_DU] = v_long_k_0;
+        a->k0[WHICH_V] = v_long_k_0;
+        ScaleConstants(ctx, a, a->k0[WHICH_DU], a->r0[WHICH_DU]);
+        ScaleConstants(ctx, a, a->k0[WHICH_V], a->r0[WHICH_V]);
+    }
+    ctx->actions.push_back(guard.release());
+    *out = a;
+    return PIMC_OK;
+}
+
+int pimc_action_destroy(pimc_action *act) {
+    if (!act) return PIMC_OK;
+    pimc_ctx *ctx = act->ctx;
+    auto it = std::find(ctx->actions.begin(), ctx->actions.end(), act);
+    if (it != ctx->actions.end()) ctx->actions.erase(it);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    delete act;
+    return PIMC_OK;
+}
+
+int pimc_action_dbeta_device(pimc_action *act, double *d_out) {
+    if (!act || !d_out) return Fail(PIMC_ERR_INVALID, "null argument");
+    PIMC_CUDA(cudaSetDevice(act->ctx->device));
+    return FullEvaluation(act, WHICH_DU, d_out);
+}
+int pimc_action_potential_device(pimc_action *act, double *d_out) {
+    if (!act || !d_out) return Fail(PIMC_ERR_INVALID, "null argument");
+    PIMC_CUDA(cudaSetDevice(act->ctx->device));
+    return FullEvaluation(act, WHICH_V, d_out);
+}
+int pimc_action_total_device(pimc_action *act, double *d_out) {
+    if (!act || !d_out) return Fail(PIMC_ERR_INVALID, "null argument");
+    PIMC_CUDA(cudaSetDevice(act->ctx->device));
+    return FullEvaluation(act, WHICH_U, d_out);
+}
+static int FullToHost(pimc_action *act, int which, double *out) {
+    if (!act || !out) return Fail(PIMC_ERR_INVALID, "null argument");
+    pimc_ctx *ctx = act->ctx;
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    int rc = EnsureOut(ctx);
+    if (rc != PIMC_OK) return rc;
+    rc = FullEvaluation(act, which, ctx->out_dev.p);
+    if (rc != PIMC_OK) return rc;
+    return ToHost(ctx, ctx->out_dev.p, out, ctx->C);
+}
+int pimc_action_dbeta(pimc_action *act, double *out) { return FullToHost(act, WHICH_DU, out); }
+int pimc_action_potential(pimc_action *act, double *out) { return FullToHost(act, WHICH_V, out); }
+int pimc_action_total(pimc_action *act, double *out) { return FullToHost(act, WHICH_U, out); }
+
+int pimc_action_get(pimc_action *act, int32_t mode, const int32_t *b0, int32_t n_window, int32_t n_moved,
+                    const int32_t *moved_species, const int32_t *moved_particle, int32_t level, double *out) {
+    if (!act || !out || !b0 || (n_moved > 0 && (!moved_species || !moved_particle))) return Fail(PIMC_ERR_INVALID, "null argument");
+    pimc_ctx *ctx = act->ctx;
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    // pair_action_class.h:269
+    if (level > act->max_level || act->is_constant) {
+        for (int c = 0; c < ctx->C; ++c) out[c] = 0.;
+        return PIMC_OK;
+    }
+    if (ctx->sharded) return Fail(PIMC_ERR_UNSUPPORTED, "move windows on a slice-sharded context");
+    if (n_window < 1 || n_window > ctx->M) return Fail(PIMC_ERR_INVALID, "window must cover 1..n_bead slices");
+    int ia = -1, ib = -1;
+    for (int i = 0; i < n_moved; ++i) {
+        if (moved_species[i] == act->sa) {
+            if (ia >= 0) return Fail(PIMC_ERR_UNSUPPORTED, "two moved particles of one species (permutation moves are a later row)");
+            ia = i;
+        } else if (moved_species[i] == act->sb) {
+            if (ib >= 0) return Fail(PIMC_ERR_UNSUPPORTED, "two moved particles of one species (permutation moves are a later row)");
+            ib = i;
+        }
+    }
+    if (act->sa == act->sb) ib = -1;
+    if (ia < 0 && ib < 0) {  // pair_action_class.h:77-78
+        for (int c = 0; c < ctx->C; ++c) out[c] = 0.;
+        return PIMC_OK;
+    }
+    std::vector<int32_t> pa(ctx->C, 0), pb(ctx->C, 0);
+    for (int c = 0; c < ctx->C; ++c) {
+        if (ia >= 0) pa[c] = moved_particle[(size_t)c * n_moved + ia];
+        if (ib >= 0) pb[c] = moved_particle[(size_t)c * n_moved + ib];
+        if (b0[c] < 0 || b0[c] >= ctx->M) return Fail(PIMC_ERR_INVALID, "window start out of range");
+        if (ia >= 0 && (pa[c] < 0 || pa[c] >= ctx->species[act->sa]->N)) return Fail(PIMC_ERR_INVALID, "moved particle out of range");
+        if (ib >= 0 && (pb[c] < 0 || pb[c] >= ctx->species[act->sb]->N)) return Fail(PIMC_ERR_INVALID, "moved particle out of range");
+    }
+    int rc;
+    if ((rc = EnsureI32(ctx, ctx->i32_a, pa.data(), ctx->C)) != PIMC_OK) return rc;
+    if ((rc = EnsureI32(ctx, ctx->i32_b, pb.data(), ctx->C)) != PIMC_OK) return rc;
+    if ((rc = EnsureI32(ctx, ctx->i32_c, b0, ctx->C)) != PIMC_OK) return rc;
+    PairWindowArgs w;
+    w.pv = ctx->View();
+    w.A = ctx->SView(act->sa, mode == PIMC_NEW);
+    w.B = ctx->SView(act->sb, mode == PIMC_NEW);
+    w.same = act->sa == act->sb;
+    w.moved_a = ia >= 0;
+    w.moved_b = ib >= 0;
+    w.part_a = ctx->i32_a.p;
+    w.part_b = ctx->i32_b.p;
+    w.b0 = ctx->i32_c.p;
+    w.n_links = n_window;
+    w.mode = mode;
+    w.T = act->table[WHICH_U];
+    w.blob = act->blob[WHICH_U].p;
+    const size_t items = (size_t)ctx->C * n_window;
+    if (ctx->partial.n < items) PIMC_CUDA(ctx->partial.Alloc(items));
+    w.partial = ctx->partial.p;
+    const int grid = (int)std::min<size_t>(items, (size_t)ctx->n_sm * 16);
+    switch (act->atype) {
+        case ATYPE_ILKKA: pair_window_kernel<ATYPE_ILKKA><<<grid, 128, 0, ctx->stream>>>(w); break;
+        case ATYPE_BARE: pair_window_kernel<ATYPE_BARE><<<grid, 128, 0, ctx->stream>>>(w); break;
+        default: pair_window_kernel<ATYPE_DAVID><<<grid, 128, 0, ctx->stream>>>(w); break;
+    }
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    const bool lr = act->use_long_range && ctx->n_k() > 0;
+    if (lr) {
+        // pair_action_class.h:293-299: refresh the proposal's rho_k once per move per species
+        if (mode == PIMC_NEW) {
+            const int sp[2] = {act->sa, act->sb};
+            const int idx[2] = {ia, ib};
+            for (int t = 0; t < (act->sa == act->sb ? 1 : 2); ++t) {
+                SpeciesState &st = *ctx->species[sp[t]];
+                if (!st.need_update_rho_k) continue;
+                st.drho_valid = false;
+                if (idx[t] >= 0 && st.n_prop > 0) {
+                    const size_t need = (size_t)ctx->C * n_window * ctx->n_k();
+                    if (st.drho.n < need) PIMC_CUDA(st.drho.Alloc(need));
+                    PIMC_CUDA(cudaMemcpyAsync(st.drho_b0.p, ctx->i32_c.p, ctx->C * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+                    const int tl = 2 * ctx->max_index + 1;
+                    rhok_delta_kernel<<<GridFor(ctx, ctx->C * n_window), 256, (size_t)6 * tl * sizeof(double2), ctx->stream>>>(
+                        ctx->View(), ctx->SView(sp[t], true), ctx->KView(), st.drho_b0.p, n_window, st.drho.p);
+                    ctx->launches++;
+                    PIMC_CUDA(cudaGetLastError());
+                    st.drho_window = n_window;
+                    st.drho_valid = true;
+                }
+                st.need_update_rho_k = false;
+            }
+            for (int t = 0; t < 2; ++t) {
+                SpeciesState &st = *ctx->species[sp[t]];
+                if (st.drho_valid && st.drho_window != n_window)
+                    return Fail(PIMC_ERR_INVALID, "NEW-mode GetAction window differs from the window rho_k was refreshed for");
+            }
+        }
+        rc = LaunchKSum(act, WHICH_U, ctx->i32_c.p, n_window, mode == PIMC_NEW, act->ulong_scale);
+        if (rc != PIMC_OK) return rc;
+    }
+    if ((rc = EnsureOut(ctx)) != PIMC_OK) return rc;
+    if (act->use_long_range && !lr) {
+        if ((int)ctx->lr_dev.n < ctx->C) PIMC_CUDA(ctx->lr_dev.Alloc(ctx->C));
+        PIMC_CUDA(cudaMemsetAsync(ctx->lr_dev.p, 0, ctx->C * sizeof(double), ctx->stream));
+    }
+    rc = Finalize(ctx, n_window, act->use_long_range, 0., 0., false, ctx->out_dev.p);
+    if (rc != PIMC_OK) return rc;
+    return ToHost(ctx, ctx->out_dev.p, out, ctx->C);
+}
+
+static int ArmFlags(pimc_action *act) {
+    if (!act) return Fail(PIMC_ERR_INVALID, "null action");
+    if (act->use_long_range) {
+        act->ctx->species[act->sa]->need_update_rho_k = true;
+        act->ctx->species[act->sb]->need_update_rho_k = true;
+    }
+    return PIMC_OK;
+}
+int pimc_action_accept(pimc_action *act) { return ArmFlags(act); }
+int pimc_action_reject(pimc_action *act) { return ArmFlags(act); }
+
+int pimc_action_calc_pair(pimc_action *act, int32_t which, int32_t n, const double *r, const double *r_p, const double *s,
+                          int32_t level, double *out) {
+    if (!act || !r || !r_p || !s || !out || n < 0 || which < 0 || which > 2) return Fail(PIMC_ERR_INVALID, "bad argument");
+    if (level != 0) return Fail(PIMC_ERR_UNSUPPORTED, "level > 0");
+    if (n == 0) return PIMC_OK;
+    pimc_ctx *ctx = act->ctx;
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    DevBuf<double> buf;
+    PIMC_CUDA(buf.Alloc((size_t)4 * n));
+    PIMC_CUDA(cudaMemcpyAsync(buf.p, r, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    PIMC_CUDA(cudaMemcpyAsync(buf.p + n, r_p, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    PIMC_CUDA(cudaMemcpyAsync(buf.p + 2 * (size_t)n, s, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const int grid = (n + 127) / 128;
+    const double *blob = act->blob[which].p;
+    const PairTable &T = act->table[which];
+#define PIMC_CP(AT, WH) calc_pair_kernel<AT, WH><<<grid, 128, 0, ctx->stream>>>(blob, T, n, buf.p, buf.p + n, buf.p + 2 * (size_t)n, buf.p + 3 * (size_t)n)
+#define PIMC_CPW(AT)                      \
+    if (which == WHICH_U)                 \
+        PIMC_CP(AT, WHICH_U);             \
+    else if (which == WHICH_DU)           \
+        PIMC_CP(AT, WHICH_DU);            \
+    else                                  \
+        PIMC_CP(AT, WHICH_V);
+    if (act->atype == ATYPE_ILKKA) {
+        PIMC_CPW(ATYPE_ILKKA)
+    } else if (act->atype == ATYPE_BARE) {
+        PIMC_CPW(ATYPE_BARE)
+    } else {
+        PIMC_CPW(ATYPE_DAVID)
+    }
+#undef PIMC_CPW
+#undef PIMC_CP
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    return ToHost(ctx, buf.p + 3 * (size_t)n, out, n);
+}
+
+// ---------------------------------------------------------------------------------- moves
+int pimc_propose(pimc_ctx *ctx, int32_t s, const int32_t *particle, const int32_t *b_first, int32_t n_beads, const double *newR) {
+    if (!ctx || !particle || !b_first || !newR) return Fail(PIMC_ERR_INVALID, "null argument");
+    if (s < 0 || s >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
+    if (n_beads < 1 || n_beads > ctx->M) return Fail(PIMC_ERR_INVALID, "proposal must cover 1..n_bead beads");
+    if (ctx->sharded) return Fail(PIMC_ERR_UNSUPPORTED, "proposals on a slice-sharded context");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    SpeciesState &st = *ctx->species[s];
+    for (int c = 0; c < ctx->C; ++c) {
+        if (particle[c] < 0 || particle[c] >= st.N) return Fail(PIMC_ERR_INVALID, "proposal particle out of range");
+        if (b_first[c] < 0 || b_first[c] >= ctx->M) return Fail(PIMC_ERR_INVALID, "proposal bead out of range");
+    }
+    const size_t n = (size_t)ctx->C * n_beads * 3;
+    if (st.P.n < n) PIMC_CUDA(st.P.Alloc(n));
+    PIMC_CUDA(cudaMemcpyAsync(st.P.p, newR, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    PIMC_CUDA(cudaMemcpyAsync(st.P_particle.p, particle, ctx->C * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    PIMC_CUDA(cudaMemcpyAsync(st.P_first.p, b_first, ctx->C * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    PIMC_CUDA(cudaStreamSynchronize(ctx->stream));  // host buffers may be reused by the caller
+    st.n_prop = n_beads;
+    st.drho_valid = false;
+    return PIMC_OK;
+}
+
+int pimc_commit(pimc_ctx *ctx, const int32_t *accept) {
+    if (!ctx || !accept) return Fail(PIMC_ERR_INVALID, "null argument");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = EnsureI32(ctx, ctx->i32_d, accept, ctx->C)) != PIMC_OK) return rc;
+    for (auto &sp : ctx->species) {
+        SpeciesState &st = *sp;
+        if (st.n_prop > 0) {
+            commit_positions_kernel<<<ctx->C, 64, 0, ctx->stream>>>(ctx->View(), st.Npad, st.P.p, st.P_particle.p, st.P_first.p, st.n_prop,
+                                                                  ctx->i32_d.p, st.R.p);
+            ctx->launches++;
+            PIMC_CUDA(cudaGetLastError());
+            if (st.drho_valid) {
+                const int n_k = ctx->n_k();
+                dim3 grid((st.drho_window * n_k + 255) / 256, ctx->C);
+                commit_rhok_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->View(), n_k, st.drho.p, st.drho_b0.p, st.drho_window, ctx->i32_d.p,
+                                                                  st.rho.p);
+                ctx->launches++;
+                PIMC_CUDA(cudaGetLastError());
+            } else if (ctx->n_k() > 0) {
+                // no action refreshed rho_k for this proposal (no long-range action touched the
+                // species in NEW mode): keep the committed rho_k consistent with the new path
+                bool any = false;
+                for (int c = 0; c < ctx->C; ++c) any = any || accept[c];
+                if (any && (rc = RebuildRhoK(ctx, (int)(&sp - &ctx->species[0]))) != PIMC_OK) return rc;
+            }
+        }
+        st.n_prop = 0;
+        st.drho_valid = false;
+        st.need_update_rho_k = true;  // every action's Accept/Reject re-arms the flag
+    }
+    PIMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PIMC_OK;
+}
+
+// ----------------------------------------------------------------------------- estimators
+int pimc_est_gofr_counts(pimc_ctx *ctx, int32_t sa, int32_t sb, double r_min, double r_max, int32_t n_r, uint64_t *counts) {
+    if (!ctx || !counts) return Fail(PIMC_ERR_INVALID, "null argument");
+    if (sa < 0 || sb < 0 || sa >= (int)ctx->species.size() || sb >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
+    if (n_r < 2 || n_r > 8192) return Fail(PIMC_ERR_INVALID, "n_r must be in 2..8192");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->C * n_r;
+    if (ctx->counts.n < n) PIMC_CUDA(ctx->counts.Alloc(n));
+    PIMC_CUDA(cudaMemsetAsync(ctx->counts.p, 0, n * sizeof(unsigned long long), ctx->stream));
+    GofrArgs g;
+    g.pv = ctx->View();
+    g.A = ctx->SView(sa, false);
+    g.B = ctx->SView(sb, false);
+    g.same = sa == sb;
+    // LinearGrid::CreateGrid (observable_class.h:30-40)
+    const double dr = (r_max - r_min) / (n_r - 1.);
+    g.r_min = r_min;
+    g.d_ir = 1. / dr;
+    g.n_r = n_r;
+    g.counts = ctx->counts.p;
+    const int items = ctx->C * ctx->Mloc;
+    gofr_kernel<<<GridFor(ctx, items), 256, n_r * sizeof(unsigned int), ctx->stream>>>(g);
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    PIMC_CUDA(cudaMemcpyAsync(counts, ctx->counts.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PIMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PIMC_OK;
+}
+
+int pimc_est_gofr(pimc_ctx *ctx, int32_t sa, int32_t sb, double r_min, double r_max, int32_t n_r, const double *cofactor, double *y) {
+    if (!ctx || !y) return Fail(PIMC_ERR_INVALID, "null argument");
+    std::vector<uint64_t> counts((size_t)ctx->C * std::max(n_r, 0));
+    int rc = pimc_est_gofr_counts(ctx, sa, sb, r_min, r_max, n_r, counts.data());
+    if (rc != PIMC_OK) return rc;
+    // gr.y(i) = gr.y(i) + 1.*cofactor, once per counted pair (pair_correlation_class.h:23)
+    for (int c = 0; c < ctx->C; ++c) {
+        const double cf = cofactor ? cofactor[c] : 1.0;
+        for (int i = 0; i < n_r; ++i) y[(size_t)c * n_r + i] += cf * (double)counts[(size_t)c * n_r + i];
+    }
+    return PIMC_OK;
+}
+
+int pimc_est_sofk(pimc_ctx *ctx, int32_t sa, int32_t sb, double k_cut, const double *cofactor, double *sk) {
+    if (!ctx || !sk) return Fail(PIMC_ERR_INVALID, "null argument");
+    if (sa < 0 || sb < 0 || sa >= (int)ctx->species.size() || sb >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    if (k_cut > ctx->k_cutoff) {  // structure_factor_class.h:49-51
+        int32_t n_k;
+        int rc = pimc_kspace_setup(ctx, k_cut, &n_k);
+        if (rc != PIMC_OK) return rc;
+    }
+    const int n_k = ctx->n_k();
+    if (n_k == 0) return PIMC_OK;
+    const size_t n = (size_t)ctx->C * n_k;
+    if (ctx->est.n < n + ctx->C) PIMC_CUDA(ctx->est.Alloc(n + ctx->C));
+    PIMC_CUDA(cudaMemcpyAsync(ctx->est.p, sk, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    double *d_cf = nullptr;
+    if (cofactor) {
+        d_cf = ctx->est.p + n;
+        PIMC_CUDA(cudaMemcpyAsync(d_cf, cofactor, ctx->C * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    dim3 grid((n_k + 127) / 128, ctx->C);
+    sofk_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->View(), n_k, ctx->species[sa]->rho.p, ctx->species[sb]->rho.p, ctx->d_kmag.p, k_cut, d_cf,
+                                               ctx->est.p);
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    return ToHost(ctx, ctx->est.p, sk, n);
+}
+
+int pimc_fp64_peak(pimc_ctx *ctx, double *tflops) {
+    if (!ctx || !tflops) return Fail(PIMC_ERR_INVALID, "null argument");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    const int blocks = ctx->n_sm * 8, threads = 256, iters = 1 << 16;
+    DevBuf<double> buf;
+    PIMC_CUDA(buf.Alloc((size_t)blocks * threads));
+    cudaEvent_t e0, e1;
+    PIMC_CUDA(cudaEventCreate(&e0));
+    PIMC_CUDA(cudaEventCreate(&e1));
+    double best = 0.;
+    for (int rep = 0; rep < 4; ++rep) {
+        PIMC_CUDA(cudaEventRecord(e0, ctx->stream));
+        fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(buf.p, iters);
+        PIMC_CUDA(cudaEventRecord(e1, ctx->stream));
+        PIMC_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        PIMC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    return PIMC_OK;
+}
+
+}  // extern "C"

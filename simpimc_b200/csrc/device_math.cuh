@@ -1,0 +1,270 @@
+// Device-side arithmetic of the pair-action path: minimum-image distance triples and
+// non-uniform cubic B-spline evaluation on tables staged in shared (or left in global) memory.
+//
+// Reference semantics being reproduced (all /root/reference/src):
+//   Path::DrDrpDrrp          data_structures/path_class.h:137-150
+//   Path::Dr / PutInBox      data_structures/path_class.h:108-134
+//   PairAction::SetLimits    actions/pair_action/pair_action_class.h:32-42
+//   Ilkka CalcU/CalcdUdBeta/CalcV   actions/pair_action/ilkka_pair_action_class.h:77-101,125-149,34-54
+//   Bare  CalcV/CalcU               actions/pair_action/bare_pair_action_class.h:99-123,146-150
+//   David CalcU/CalcdUdBeta/CalcV   actions/pair_action/david_pair_action_class.h:63-102,126-168,26-39
+// The spline evaluation follows the published einspline algorithm the reference calls
+// (eval_NUBspline_{1d,2d}_d, eval_multi_NUBspline_1d_d): interval search on the knot grid,
+// Cox-de Boor recursion for the four live basis functions, 4 / 16-tap contraction.
+#ifndef SIMPIMC_B200_DEVICE_MATH_CUH_
+#define SIMPIMC_B200_DEVICE_MATH_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pimc {
+
+enum { ATYPE_ILKKA = 0, ATYPE_BARE = 1, ATYPE_DAVID = 2 };
+enum { WHICH_U = 0, WHICH_DU = 1, WHICH_V = 2 };
+enum { GRIDCODE_GENERAL = 0, GRIDCODE_LOG = 1 };
+
+struct Box {
+    double L, iL;
+};
+
+/// Offsets (in doubles) of one 1-D / multi spline inside a table blob.
+struct Sp1Desc {
+    int n;            // grid points
+    int off_t, off_w, off_c;
+    int n_splines;    // 1 for a plain spline; stride of the multi-spline coefficient rows
+    int code;         // GRIDCODE_*
+    double r_min, r_max;  // grid start / end (SetLimits)
+    double ainv, startinv;  // log grid reverse map
+};
+struct Sp2Desc {
+    int nx, ny;
+    int off_tx, off_wx, off_ty, off_wy, off_c;
+};
+/// Everything a pair kernel needs to evaluate one of U / dU/dbeta / V of one action.
+struct PairTable {
+    int use_lr;
+    int is_coulomb;
+    int n_order;
+    double u_scale;  // Bare CalcU: (1 >> level) * tau
+    Sp2Desc xy;      // Ilkka u_xy / du_xy
+    Sp1Desc a;       // Ilkka/Bare v_r, David multi-spline
+    Sp1Desc lr;      // the long-range r-space spline subtracted from the short-range part
+};
+
+// nearbyint() in the default rounding mode is round-half-even == rint()
+__device__ __forceinline__ double MinImage(double d, const Box &bx) { return d - rint(d * bx.iL) * bx.L; }
+
+// scaffold mag() = arma::norm(v,2) for 3 elements accumulates (x0^2 + x2^2) + x1^2
+__device__ __forceinline__ double Mag3(double x, double y, double z) { return sqrt((x * x + z * z) + y * y); }
+
+// Same without FMA contraction and with correctly rounded sqrt: g(r) bin indices depend on it.
+__device__ __forceinline__ double Mag3Exact(double x, double y, double z) {
+    return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(z, z)), __dmul_rn(y, y)));
+}
+
+/// Path::DrDrpDrrp: r between the two particles at slice b0 (minimum image), r' at slice b1
+/// moved to the SAME image as r, and |r - r'| minimum-imaged.
+__device__ __forceinline__ void DrDrpDrrp(const double a0[3], const double b0[3], const double a1[3], const double b1[3],
+                                          const Box &bx, double &r_mag, double &rp_mag, double &rrp_mag) {
+    double r[3], rp[3], rrp[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        r[d] = b0[d] - a0[d];
+        rp[d] = b1[d] - a1[d];
+        r[d] -= rint(r[d] * bx.iL) * bx.L;
+        rp[d] += rint((r[d] - rp[d]) * bx.iL) * bx.L;
+        rrp[d] = r[d] - rp[d];
+        rrp[d] -= rint(rrp[d] * bx.iL) * bx.L;
+    }
+    r_mag = Mag3(r[0], r[1], r[2]);
+    rp_mag = Mag3(rp[0], rp[1], rp[2]);
+    rrp_mag = Mag3(rrp[0], rrp[1], rrp[2]);
+}
+
+__device__ __forceinline__ void SetLimits(double r_min, double r_max, double &r, double &r_p) {
+    r = r > r_max ? r_max : (r < r_min ? r_min : r);
+    r_p = r_p > r_max ? r_max : (r_p < r_min ? r_min : r_p);
+}
+
+/// Interval index of x on the grid g[0..n) (einspline general_grid_reverse_map): last i with
+/// g[i] <= x, 0 below the grid, n-1 at or above its end.
+__device__ __forceinline__ int GridInterval(const double *__restrict__ g, int n, double x) {
+    if (x <= g[0]) return 0;
+    if (x >= g[n - 1]) return n - 1;
+    int lo = 0, hi = n - 1;
+    while (hi - lo >= 2) {
+        int mid = (hi + lo) >> 1;
+        if (g[mid] > x)
+            hi = mid;
+        else
+            lo = mid;
+    }
+    return lo;
+}
+
+/// Cox-de Boor recursion: the four cubic B-spline basis values alive on interval i at x.
+/// t = knots (grid at t+2), w[3i+j] = 1/(t[i+j+1]-t[i]).
+__device__ __forceinline__ void BasisOnInterval(const double *__restrict__ t, const double *__restrict__ w, int i, double x,
+                                                double b[4]) {
+    const int i2 = i + 2;
+    const double tm2 = t[i2 - 2], tm1 = t[i2 - 1], t0 = t[i2], t1 = t[i2 + 1], t2 = t[i2 + 2], t3 = t[i2 + 3];
+    const double w00 = w[3 * i + 2];
+    const double w11 = w[3 * (i + 1) + 1], w12 = w[3 * (i + 1) + 2];
+    const double w20 = w[3 * (i + 2) + 0], w21 = w[3 * (i + 2) + 1], w22 = w[3 * (i + 2) + 2];
+    const double l0 = (t1 - x) * w20;
+    const double l1 = (x - t0) * w20;
+    const double q0 = (t1 - x) * w11 * l0;
+    const double q1 = ((x - tm1) * w11 * l0 + (t2 - x) * w21 * l1);
+    const double q2 = (x - t0) * w21 * l1;
+    b[0] = (t1 - x) * w00 * q0;
+    b[1] = ((x - tm2) * w00 * q0 + (t2 - x) * w12 * q1);
+    b[2] = ((x - tm1) * w12 * q1 + (t3 - x) * w22 * q2);
+    b[3] = (x - t0) * w22 * q2;
+}
+
+__device__ __forceinline__ int Sp1Interval(const double *__restrict__ blob, const Sp1Desc &s, double x) {
+    if (s.code == GRIDCODE_LOG) {
+        int idx = (int)floor(s.ainv * log(x * s.startinv));
+        idx = idx < 0 ? 0 : idx;
+        return idx > s.n - 1 ? s.n - 1 : idx;
+    }
+    return GridInterval(blob + s.off_t + 2, s.n, x);
+}
+
+__device__ __forceinline__ double Sp1Eval(const double *__restrict__ blob, const Sp1Desc &s, double x) {
+    double b[4];
+    const int i = Sp1Interval(blob, s, x);
+    BasisOnInterval(blob + s.off_t, blob + s.off_w, i, x, b);
+    const double *c = blob + s.off_c + i;
+    return (c[0] * b[0] + c[1] * b[1] + c[2] * b[2] + c[3] * b[3]);
+}
+
+/// One value of a multi-spline (coefficient rows of n_splines doubles).
+__device__ __forceinline__ double MultiTap(const double *__restrict__ blob, const Sp1Desc &s, int i, const double b[4], int v) {
+    const double *c = blob + s.off_c + (size_t)i * s.n_splines + v;
+    const int st = s.n_splines;
+    return c[0] * b[0] + c[st] * b[1] + c[2 * st] * b[2] + c[3 * st] * b[3];
+}
+
+__device__ __forceinline__ double Sp2Eval(const double *__restrict__ blob, const Sp2Desc &s, double x, double y) {
+    double a[4], b[4];
+    const int ix = GridInterval(blob + s.off_tx + 2, s.nx, x);
+    const int iy = GridInterval(blob + s.off_ty + 2, s.ny, y);
+    BasisOnInterval(blob + s.off_tx, blob + s.off_wx, ix, x, a);
+    BasisOnInterval(blob + s.off_ty, blob + s.off_wy, iy, y, b);
+    const int sy = s.ny + 2;
+    const double *c = blob + s.off_c + (size_t)ix * sy + iy;
+    double v = 0.;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const double *cm = c + m * sy;
+        v += a[m] * (cm[0] * b[0] + cm[1] * b[1] + cm[2] * b[2] + cm[3] * b[3]);
+    }
+    return v;
+}
+
+/// CalcV of the three action families.
+template <int ATYPE>
+__device__ __forceinline__ double PairV(const double *__restrict__ blob, const PairTable &T, double r, double r_p) {
+    if (ATYPE == ATYPE_DAVID) {
+        SetLimits(T.a.r_min, T.a.r_max, r, r_p);
+        double b[4];
+        int i = Sp1Interval(blob, T.a, r);
+        BasisOnInterval(blob + T.a.off_t, blob + T.a.off_w, i, r, b);
+        double v0 = MultiTap(blob, T.a, i, b, 0);
+        i = Sp1Interval(blob, T.a, r_p);
+        BasisOnInterval(blob + T.a.off_t, blob + T.a.off_w, i, r_p, b);
+        double v1 = MultiTap(blob, T.a, i, b, 0);
+        return 0.5 * (v0 + v1);
+    }
+    SetLimits(T.a.r_min, T.a.r_max, r, r_p);
+    double v = 0.;
+    if (ATYPE == ATYPE_BARE && T.is_coulomb) {
+        v += (0.5 / r) + (0.5 / r_p);
+    } else {
+        v += 0.5 * Sp1Eval(blob, T.a, r);
+        v += 0.5 * Sp1Eval(blob, T.a, r_p);
+    }
+    if (T.use_lr) {
+        SetLimits(T.lr.r_min, T.lr.r_max, r, r_p);
+        v -= 0.5 * Sp1Eval(blob, T.lr, r);
+        v -= 0.5 * Sp1Eval(blob, T.lr, r_p);
+    }
+    return v;
+}
+
+/// CalcU (WHICH_U) / CalcdUdBeta (WHICH_DU) / CalcV (WHICH_V) for one (r, r', s) triple.
+template <int ATYPE, int WHICH>
+__device__ __forceinline__ double PairEval(const double *__restrict__ blob, const PairTable &T, double r, double r_p, double s) {
+    if (WHICH == WHICH_V) return PairV<ATYPE>(blob, T, r, r_p);
+    if (ATYPE == ATYPE_BARE) {
+        const double v = PairV<ATYPE_BARE>(blob, T, r, r_p);
+        return WHICH == WHICH_U ? T.u_scale * v : v;
+    }
+    if (ATYPE == ATYPE_ILKKA) {
+        const double q = 0.5 * (r + r_p);
+        const double x = q + 0.5 * s;
+        const double y = q - 0.5 * s;
+        double u = Sp2Eval(blob, T.xy, x, y);
+        if (T.use_lr) {
+            SetLimits(T.lr.r_min, T.lr.r_max, r, r_p);
+            u -= 0.5 * Sp1Eval(blob, T.lr, r);
+            u -= 0.5 * Sp1Eval(blob, T.lr, r_p);
+        }
+        return u;
+    }
+    // David: endpoint term plus the off-diagonal polynomial in z^2 and s^2
+    const double q = 0.5 * (r + r_p);
+    const double z = r - r_p;
+    const double r_max = T.a.r_max;
+    SetLimits(T.a.r_min, T.a.r_max, r, r_p);
+    double b[4];
+    int i = Sp1Interval(blob, T.a, r);
+    BasisOnInterval(blob + T.a.off_t, blob + T.a.off_w, i, r, b);
+    double e1 = MultiTap(blob, T.a, i, b, 1);
+    double e0 = (WHICH == WHICH_DU) ? MultiTap(blob, T.a, i, b, 0) : 0.;
+    i = Sp1Interval(blob, T.a, r_p);
+    BasisOnInterval(blob + T.a.off_t, blob + T.a.off_w, i, r_p, b);
+    double f1 = MultiTap(blob, T.a, i, b, 1);
+    double f0 = (WHICH == WHICH_DU) ? MultiTap(blob, T.a, i, b, 0) : 0.;
+    double u = 0.5 * (e1 + f1);
+    if (WHICH == WHICH_DU) u += 0.5 * (e0 + f0);
+    if (s > 0.0 && q < r_max) {
+        i = Sp1Interval(blob, T.a, q);
+        BasisOnInterval(blob + T.a.off_t, blob + T.a.off_w, i, q, b);
+        const double z_2 = z * z, s_2 = s * s, i_s_2 = 1. / s_2;
+        double s_2_k = s_2;
+        for (int k = 1; k <= T.n_order; k++) {
+            double z_2_j = 1, current_s = s_2_k;
+            for (int j = 0; j <= k; j++) {
+                const double cof = MultiTap(blob, T.a, i, b, k * (k + 1) / 2 + (j + 1));
+                u += cof * z_2_j * current_s;
+                z_2_j *= z_2;
+                current_s *= i_s_2;
+            }
+            s_2_k *= s_2;
+        }
+    }
+    return u;
+}
+
+/// Deterministic block-wide sum: warp shuffles, then warp leaders in fixed order.
+template <int NT>
+__device__ __forceinline__ double BlockSum(double v, double *scratch /* NT/32 doubles */) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    double tot = 0.;
+    if (threadIdx.x == 0) {
+#pragma unroll 1
+        for (int i = 0; i < NT / 32; ++i) tot += scratch[i];
+    }
+    return tot;  // valid on thread 0
+}
+
+}  // namespace pimc
+
+#endif  // SIMPIMC_B200_DEVICE_MATH_CUH_

@@ -1,0 +1,325 @@
+"""Host-side mirror of the reference's operator interface for the action-evaluation path,
+bound to the CUDA library through the C ABI (include/simpimc_b200.h).
+
+Names and argument meaning follow the reference so tests read like calls into it:
+
+* `Path`        -- src/data_structures/path_class.h (box, tau, species, KSpace, OLD/NEW mode)
+                   holding `n_clones` walkers instead of one;
+* `PairAction`  -- src/actions/action_class.h:37-73 as implemented by
+                   src/actions/pair_action/{ilkka,bare,david}_pair_action_class.h:
+                   `DActionDBeta()`, `Potential()`, `GetAction(b0, b1, particles, level)`,
+                   `Accept()`, `Reject()`;
+* `PairCorrelation`, `StructureFactor`, `Energy` -- src/events/observables/*_class.h
+                   (`Accumulate()`, and the normalisation of `Write()`).
+
+Every method returns one value per clone (numpy array of length n_clones).
+There is no CPU fallback: constructing a `Path` without the built CUDA library or without a
+GPU raises.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import capi
+
+OLD_MODE, NEW_MODE = capi.PIMC_OLD, capi.PIMC_NEW
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Path:
+    """Path + Species[] + KSpace of `n_clones` independent walkers on one GPU."""
+
+    def __init__(self, cfg, n_clones=1, device=0, slice_lo=0, slice_hi=None):
+        self.L = capi.lib()
+        self.cfg = cfg
+        self.n_clones = n_clones
+        self.n_d = cfg.n_d
+        self.n_bead = cfg.n_bead
+        self.slice_lo = slice_lo
+        self.slice_hi = cfg.n_bead if slice_hi is None else slice_hi
+        self.sharded = (self.slice_hi - self.slice_lo) != cfg.n_bead
+        self.n_store = (self.slice_hi - self.slice_lo) + (1 if self.sharded else 0)
+        c, self._keep = capi.make_config(cfg, n_clones, device, slice_lo, self.slice_hi)
+        h = C.c_void_p()
+        capi.check(self.L.pimc_ctx_create(C.byref(c), C.byref(h)))
+        self.h = h
+        self.mode = NEW_MODE
+        self.n_k = 0
+        if cfg.pbc and cfg.k_cut is not None:
+            self.SetupKSpace(cfg.k_cut)
+        self.actions = []
+        for a in cfg.actions:
+            self.actions.append(None if a.type == "Kinetic" else PairAction(self, a))
+        if any(a is not None and a.use_long_range for a in self.actions):
+            self.n_k = self._n_k()
+
+    def close(self):
+        if self.h:
+            self.L.pimc_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- KSpace (k_space_class.h) -------------------------------------------------------
+    def _n_k(self):
+        if not self.cfg.pbc:
+            return 0
+        n = C.c_int32()
+        capi.check(self.L.pimc_kspace_setup(self.h, 0.0, C.byref(n)))
+        return n.value
+
+    def SetupKSpace(self, k_cut):
+        n = C.c_int32()
+        capi.check(self.L.pimc_kspace_setup(self.h, float(k_cut), C.byref(n)))
+        self.n_k = n.value
+        return self.n_k
+
+    def KSpace(self):
+        n_k = self._n_k()
+        idx = np.zeros((n_k, self.n_d), dtype=np.int32)
+        mags = np.zeros(n_k)
+        capi.check(self.L.pimc_kspace_get(self.h, _vp(idx), _vp(mags)))
+        return idx, mags
+
+    # -- mode flag (path_class.h:95) -----------------------------------------------------
+    def SetMode(self, mode):
+        self.mode = mode
+
+    def GetMode(self):
+        return self.mode
+
+    def GetTau(self):
+        return self.cfg.tau
+
+    # -- positions ----------------------------------------------------------------------
+    def SetPositions(self, species, R, clone_lo=0, clone_hi=None):
+        """R[clone][particle][bead][dim] (host); sets r and r_c and rebuilds rho_k."""
+        clone_hi = self.n_clones if clone_hi is None else clone_hi
+        R = np.ascontiguousarray(R, dtype=np.float64)
+        s = self.cfg.species[species]
+        assert R.shape == (clone_hi - clone_lo, s.n_part, self.n_store, self.n_d), R.shape
+        capi.check(self.L.pimc_positions_upload(self.h, species, clone_lo, clone_hi, _vp(R)))
+        if not (clone_lo == 0 and clone_hi == self.n_clones):
+            capi.check(self.L.pimc_rhok_rebuild(self.h, species))
+
+    def GetPositions(self, species, clone_lo=0, clone_hi=None):
+        clone_hi = self.n_clones if clone_hi is None else clone_hi
+        s = self.cfg.species[species]
+        R = np.zeros((clone_hi - clone_lo, s.n_part, self.n_store, self.n_d))
+        capi.check(self.L.pimc_positions_download(self.h, species, OLD_MODE, clone_lo, clone_hi, _vp(R)))
+        return R
+
+    def GetRhoK(self, species, clone=0, mode=None):
+        mode = self.mode if mode is None else mode
+        n_k = self._n_k()
+        out = np.zeros((self.slice_hi - self.slice_lo, n_k, 2))
+        capi.check(self.L.pimc_rhok_download(self.h, species, mode, clone, _vp(out)))
+        return out[..., 0] + 1j * out[..., 1]
+
+    # -- the moves' side of the contract --------------------------------------------------
+    def Propose(self, species, particle, b_first, newR):
+        """NEW-mode SetR of beads b_first[c]..+n_beads-1 of particle[c]; newR[c][i][dim]."""
+        particle = np.ascontiguousarray(np.broadcast_to(particle, (self.n_clones,)), dtype=np.int32)
+        b_first = np.ascontiguousarray(np.broadcast_to(b_first, (self.n_clones,)), dtype=np.int32)
+        newR = np.ascontiguousarray(newR, dtype=np.float64)
+        assert newR.shape[0] == self.n_clones and newR.shape[2] == self.n_d
+        capi.check(self.L.pimc_propose(self.h, species, _vp(particle), _vp(b_first), newR.shape[1], _vp(newR)))
+
+    def Commit(self, accept):
+        accept = np.ascontiguousarray(np.broadcast_to(accept, (self.n_clones,)), dtype=np.int32)
+        capi.check(self.L.pimc_commit(self.h, _vp(accept)))
+
+    def LaunchCount(self):
+        return int(self.L.pimc_ctx_launch_count(self.h))
+
+    def Sync(self):
+        capi.check(self.L.pimc_ctx_sync(self.h))
+
+    def Fp64Peak(self):
+        t = C.c_double()
+        capi.check(self.L.pimc_fp64_peak(self.h, C.byref(t)))
+        return t.value
+
+
+class PairAction:
+    """One IlkkaPairAction / BarePairAction / DavidPairAction on the device."""
+
+    def __init__(self, path, acfg):
+        self.path = path
+        self.L = path.L
+        self.name = acfg.name
+        self.type = acfg.type
+        self.use_long_range = acfg.use_long_range
+        self.max_level = acfg.max_level
+        cfg = path.cfg
+        sa, sb = cfg.species_index(acfg.species_a), cfg.species_index(acfg.species_b)
+        self.species_a, self.species_b = sa, sb
+        kc = acfg.k_cut if acfg.k_cut is not None else (cfg.k_cut or 0.0)
+        h = C.c_void_p()
+        if acfg.type == "IlkkaPairAction":
+            t, self._keep = capi.pack_ilkka(acfg.table, acfg.use_long_range)
+            capi.check(self.L.pimc_action_create_ilkka(path.h, sa, sb, C.byref(t), acfg.max_level, int(acfg.use_long_range), kc,
+                                                      C.byref(h)))
+        elif acfg.type == "BarePairAction":
+            t, self._keep = capi.pack_bare(acfg.table, acfg.use_long_range, acfg.is_coulomb)
+            capi.check(self.L.pimc_action_create_bare(path.h, sa, sb, C.byref(t), acfg.max_level, int(acfg.use_long_range), kc,
+                                                     C.byref(h)))
+        elif acfg.type == "DavidPairAction":
+            t, self._keep = capi.pack_david(acfg.table, acfg.n_order, acfg.use_long_range)
+            capi.check(self.L.pimc_action_create_david(path.h, sa, sb, C.byref(t), acfg.max_level, int(acfg.use_long_range),
+                                                      C.byref(h)))
+        else:
+            raise ValueError("ERROR: Unrecognized Action, %s" % acfg.type)  # actions.h:32
+        self.h = h
+
+    def _full(self, fn):
+        out = np.zeros(self.path.n_clones)
+        capi.check(fn(self.h, _vp(out)))
+        return out
+
+    def DActionDBeta(self):
+        return self._full(self.L.pimc_action_dbeta)
+
+    def Potential(self):
+        return self._full(self.L.pimc_action_potential)
+
+    def TotalAction(self):
+        return self._full(self.L.pimc_action_total)
+
+    def GetAction(self, b0, b1, particles, level):
+        """particles: list of (species index, particle) with particle an int or an array of
+        one index per clone; b0 an int or per-clone array; b1 - b0 the common window."""
+        C_ = self.path.n_clones
+        b0a = np.ascontiguousarray(np.broadcast_to(b0, (C_,)), dtype=np.int32)
+        n_window = int(np.broadcast_to(b1, (C_,))[0] - b0a[0])
+        sp = np.ascontiguousarray([p[0] for p in particles], dtype=np.int32)
+        pi = np.zeros((C_, len(particles)), dtype=np.int32)
+        for i, p in enumerate(particles):
+            pi[:, i] = np.broadcast_to(p[1], (C_,))
+        out = np.zeros(C_)
+        capi.check(self.L.pimc_action_get(self.h, self.path.mode, _vp(b0a), n_window, len(particles), _vp(sp), _vp(pi), level,
+                                          _vp(out)))
+        return out
+
+    def Accept(self):
+        capi.check(self.L.pimc_action_accept(self.h))
+
+    def Reject(self):
+        capi.check(self.L.pimc_action_reject(self.h))
+
+    def CalcPair(self, which, r, r_p, s, level=0):
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        r_p = np.ascontiguousarray(r_p, dtype=np.float64)
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        out = np.zeros_like(r)
+        capi.check(self.L.pimc_action_calc_pair(self.h, which, len(r), _vp(r), _vp(r_p), _vp(s), level, _vp(out)))
+        return out
+
+
+class PairCorrelation:
+    """src/events/observables/pair_correlation_class.h."""
+
+    def __init__(self, path, species_a, species_b, r_min=0.0, r_max=None, n_r=100):
+        self.path = path
+        self.sa, self.sb = species_a, species_b
+        self.r_min = r_min
+        self.r_max = path.cfg.L / 2.0 if r_max is None else r_max
+        self.n_r = int(n_r)
+        self.Reset()
+
+    def Reset(self):
+        self.n_measure = 0
+        self.y = np.zeros((self.path.n_clones, self.n_r))
+
+    def Accumulate(self, cofactor=None):
+        cf = None if cofactor is None else np.ascontiguousarray(cofactor, dtype=np.float64)
+        capi.check(self.path.L.pimc_est_gofr(self.path.h, self.sa, self.sb, self.r_min, self.r_max, self.n_r,
+                                             None if cf is None else _vp(cf), _vp(self.y)))
+        self.n_measure += 1
+
+    def Counts(self):
+        counts = np.zeros((self.path.n_clones, self.n_r), dtype=np.uint64)
+        capi.check(self.path.L.pimc_est_gofr_counts(self.path.h, self.sa, self.sb, self.r_min, self.r_max, self.n_r, _vp(counts)))
+        return counts
+
+    def Write(self):
+        """Normalised g(r) per clone (pair_correlation_class.h:89-123), then reset."""
+        cfg = self.path.cfg
+        Na, Nb = cfg.species[self.sa].n_part, cfg.species[self.sb].n_part
+        vol = cfg.L ** cfg.n_d if cfg.pbc else 1.0
+        if self.sa == self.sb:
+            norm = 0.5 * self.n_measure * Na * (Nb - 1) * cfg.n_bead / vol
+        else:
+            norm = self.n_measure * Na * Nb * cfg.n_bead / vol
+        dr = (self.r_max - self.r_min) / (self.n_r - 1.0)
+        x = self.r_min + np.arange(self.n_r) * dr
+        r1 = x
+        r2 = np.concatenate([x[1:], [2.0 * x[-1] - x[-2]]])
+        bin_vol = 4.0 * math.pi / 3.0 * (r2 ** 3 - r1 ** 3)
+        g = self.y / (bin_vol * norm)
+        self.Reset()
+        return g
+
+
+class StructureFactor:
+    """src/events/observables/structure_factor_class.h."""
+
+    def __init__(self, path, species_a, species_b, k_cut=None):
+        self.path = path
+        self.sa, self.sb = species_a, species_b
+        self.k_cut = path.cfg.k_cut if k_cut is None else k_cut
+        path.SetupKSpace(self.k_cut)
+        self.Reset()
+
+    def Reset(self):
+        self.n_measure = 0
+        self.sk = np.zeros((self.path.n_clones, self.path._n_k()))
+
+    def Accumulate(self, cofactor=None):
+        cf = None if cofactor is None else np.ascontiguousarray(cofactor, dtype=np.float64)
+        capi.check(self.path.L.pimc_est_sofk(self.path.h, self.sa, self.sb, self.k_cut, None if cf is None else _vp(cf),
+                                             _vp(self.sk)))
+        self.n_measure += 1
+
+    def Write(self):
+        cfg = self.path.cfg
+        norm = self.n_measure * cfg.n_bead * cfg.species[self.sa].n_part * cfg.species[self.sb].n_part
+        out = self.sk / norm
+        self.Reset()
+        return out
+
+
+class Energy:
+    """Thermal and potential estimators of src/events/observables/energy_class.h:22-33,119-161."""
+
+    def __init__(self, path, measure_potential=False):
+        self.path = path
+        self.measure_potential = measure_potential
+        self.actions = [a for a in path.actions if a is not None]
+        self.Reset()
+
+    def Reset(self):
+        self.n_measure = 0
+        self.energies = np.zeros((len(self.actions), self.path.n_clones))
+        self.potentials = np.zeros((len(self.actions), self.path.n_clones))
+
+    def Accumulate(self, cofactor=1.0):
+        for i, a in enumerate(self.actions):
+            self.energies[i] += cofactor * a.DActionDBeta()
+            if self.measure_potential:
+                self.potentials[i] += cofactor * a.Potential()
+        self.n_measure += 1
+
+    def Write(self):
+        norm = self.path.cfg.n_bead * self.n_measure  # energy_class.h:234
+        e, v = self.energies / norm, self.potentials / norm
+        self.Reset()
+        return e, v

@@ -1,0 +1,222 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on
+the same seeded inputs.  Tolerance: |gpu - oracle| <= 1e-10 * |oracle| for floating-point
+results (BASELINE.json north_star), bit-exact for k vectors and histogram bins."""
+import numpy as np
+import pytest
+
+from simpimc_b200 import system as S
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+def rel_ok(got, ref, scale=None, rtol=RTOL):
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    sc = np.abs(ref) if scale is None else np.maximum(np.abs(ref), scale)
+    return np.all(np.abs(got - ref) <= rtol * np.maximum(sc, 1e-300))
+
+
+def make_pair(cfg, n_clones, seed=12345):
+    from simpimc_b200 import host
+    from oracle import oracle as O
+    path = host.Path(cfg, n_clones=n_clones)
+    oracles = []
+    Rs = []
+    for sp in range(len(cfg.species)):
+        R = np.stack([S.synthetic_paths(cfg, sp, c, seed) for c in range(n_clones)])
+        path.SetPositions(sp, R)
+        Rs.append(R)
+    for c in range(n_clones):
+        o = O.Oracle(cfg)
+        for sp in range(len(cfg.species)):
+            o.set_positions(sp, Rs[sp][c])
+        oracles.append(o)
+    return path, oracles, Rs
+
+
+CONFIGS = {
+    "ilkka_lr_n7": lambda: S.ueg_config(N=7, M=8),
+    "ilkka_lr_n33": lambda: S.ueg_config(N=33, M=16),
+    "ilkka_nolr_n8": lambda: S.ueg_config(N=8, M=8, use_long_range=False),
+    "bare_lr_n7": lambda: S.ueg_config(N=7, M=8, action="BarePairAction"),
+    "david_n7": lambda: S.ueg_config(N=7, M=8, action="DavidPairAction", use_long_range=False),
+    "david_lr_n7": lambda: S.ueg_config(N=7, M=8, action="DavidPairAction", use_long_range=True),
+    "plasma": lambda: S.plasma_config(Ne=6, Np=5, M=8),
+    "n2": lambda: S.ueg_config(N=2, M=4),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_full_path_values(name):
+    cfg = CONFIGS[name]()
+    path, oracles, _ = make_pair(cfg, 3)
+    for ai, act in enumerate(path.actions):
+        if act is None:
+            continue
+        du, u = act.DActionDBeta(), act.TotalAction()
+        # GetAction(0, M, every particle, 0) in OLD mode is the whole-path action
+        parts = [(s, p) for s in range(len(cfg.species)) for p in range(cfg.species[s].n_part)]
+        for c, o in enumerate(oracles):
+            assert rel_ok(du[c], o.dbeta(ai)), (name, ai, c, du[c], o.dbeta(ai))
+            ref_u = o.get_action(ai, 0, 0, cfg.n_bead, parts, 0)
+            assert rel_ok(u[c], ref_u), (name, ai, c, u[c], ref_u)
+        if not (cfg.actions[ai].type == "DavidPairAction" and cfg.actions[ai].use_long_range):
+            v = act.Potential()
+            for c, o in enumerate(oracles):
+                assert rel_ok(v[c], o.potential(ai)), (name, ai, c, v[c], o.potential(ai))
+    path.close()
+
+
+@pytest.mark.parametrize("name", ["ilkka_lr_n7", "bare_lr_n7", "david_n7", "plasma"])
+def test_per_pair_kernels(name):
+    cfg = CONFIGS[name]()
+    path, oracles, _ = make_pair(cfg, 1)
+    rng = np.random.default_rng(3)
+    n = 4000
+    rmax = np.sqrt(3) * cfg.L / 2
+    r = rng.uniform(1e-3, rmax, n)
+    rp = np.clip(r + rng.normal(0, 0.1, n), 1e-4, rmax)
+    s = np.abs(r - rp) + np.abs(rng.normal(0, 0.05, n))
+    # edge cases: zero separation change, grid ends, far beyond the long-range grid
+    r[:4] = [1e-5, rmax, 0.3, 2.0]
+    rp[:4] = [1e-5, rmax * 1.5, 0.3, 2.0]
+    s[:4] = [0.0, 0.1, 0.0, 0.0]
+    for ai, act in enumerate(path.actions):
+        if act is None:
+            continue
+        for which in (0, 1, 2):
+            got = act.CalcPair(which, r, rp, s)
+            ref = oracles[0].calc_pair(ai, which, r, rp, s)
+            assert rel_ok(got, ref, scale=1e-6 * np.max(np.abs(ref))), (name, ai, which, np.max(np.abs(got - ref)))
+    path.close()
+
+
+@pytest.mark.parametrize("name", ["ilkka_lr_n7", "ilkka_lr_n33", "plasma"])
+def test_kspace_and_rhok(name):
+    cfg = CONFIGS[name]()
+    path, oracles, _ = make_pair(cfg, 2)
+    idx, mags = path.KSpace()
+    oidx, omags = oracles[0].kspace()
+    assert np.array_equal(idx, oidx)          # integer work: bit-exact, reference order
+    assert np.array_equal(mags, omags)
+    for sp in range(len(cfg.species)):
+        for c, o in enumerate(oracles):
+            got, ref = path.GetRhoK(sp, c), o.rhok(sp)
+            assert np.max(np.abs(got - ref)) <= 1e-12 * cfg.species[sp].n_part
+    path.close()
+
+
+@pytest.mark.parametrize("name", ["ilkka_lr_n7", "ilkka_lr_n33", "bare_lr_n7", "david_n7", "plasma", "ilkka_nolr_n8"])
+def test_move_windows_old_new_commit(name):
+    """Bisect-style windows (incl. wrap-around b1 > n_bead) and a displace-style whole-path
+    move: OLD and NEW GetAction, their difference, and the state after accept / reject."""
+    cfg = CONFIGS[name]()
+    n_clones = 4
+    path, oracles, Rs = make_pair(cfg, n_clones)
+    from simpimc_b200 import host
+    rng = np.random.default_rng(11)
+    M = cfg.n_bead
+    for trial in range(6):
+        sp = trial % len(cfg.species)
+        N = cfg.species[sp].n_part
+        nb = [4, 2, M, 4, 1, M][trial]          # links in the window; M = displace
+        part = rng.integers(0, N, n_clones)
+        b0 = rng.integers(0, M, n_clones)
+        if trial == 3:
+            b0[:] = M - 2                       # forces wrap-around
+        n_beads = nb - 1 if nb < M else M
+        first = (b0 + 1) % M if nb < M else np.zeros(n_clones, dtype=int)
+        if nb == M:
+            b0[:] = 0
+        if n_beads == 0:
+            continue
+        old_pos = np.stack([oracles[c].get_positions(sp, 0)[part[c], (first[c] + np.arange(n_beads)) % M] for c in range(n_clones)])
+        newR = old_pos + 0.08 * rng.standard_normal(old_pos.shape)
+        path.Propose(sp, part, first, newR)
+        accept = rng.integers(0, 2, n_clones)
+        for c, o in enumerate(oracles):
+            o.propose(sp, int(part[c]), int(first[c]), newR[c])
+        sums = {}
+        for ai, act in enumerate(path.actions):
+            if act is None or sp not in (act.species_a, act.species_b):
+                continue
+            path.SetMode(host.OLD_MODE)
+            old = act.GetAction(b0, b0 + nb, [(sp, part)], 0)
+            path.SetMode(host.NEW_MODE)
+            new = act.GetAction(b0, b0 + nb, [(sp, part)], 0)
+            for c, o in enumerate(oracles):
+                ro = o.get_action(ai, 0, int(b0[c]), int(b0[c]) + nb, [(sp, int(part[c]))], 0)
+                rn = o.get_action(ai, 1, int(b0[c]), int(b0[c]) + nb, [(sp, int(part[c]))], 0)
+                assert rel_ok(old[c], ro), (name, trial, ai, c, old[c], ro)
+                assert rel_ok(new[c], rn), (name, trial, ai, c, new[c], rn)
+                # the difference a move tests, relative to the size of the sums it comes from
+                assert abs((new[c] - old[c]) - (rn - ro)) <= RTOL * max(abs(rn - ro), 1e-4 * (abs(rn) + abs(ro)))
+        path.Commit(accept)
+        for c, o in enumerate(oracles):
+            lo = int(b0[c])
+            # bisect commits beads bead0..bead1 and slices [bead0, bead1) (bisect_class.h:24-36);
+            # displace commits every bead and slice (displace_particle_class.h:13-25)
+            o.finish_move(sp, int(part[c]), lo, lo + nb, bool(accept[c]))
+        got = path.GetPositions(sp)
+        for c, o in enumerate(oracles):
+            assert np.array_equal(got[c], o.get_positions(sp, 0)), (name, trial, c)
+            if path._n_k():
+                assert np.max(np.abs(path.GetRhoK(sp, c, host.OLD_MODE) - o.rhok(sp, 0))) <= 1e-11 * N
+    # after the moves the full-path values still agree
+    for ai, act in enumerate(path.actions):
+        if act is None:
+            continue
+        du = act.DActionDBeta()
+        for c, o in enumerate(oracles):
+            assert rel_ok(du[c], o.dbeta(ai)), (name, "post", ai, c)
+    path.close()
+
+
+@pytest.mark.parametrize("name", ["ilkka_lr_n7", "ilkka_lr_n33", "plasma"])
+def test_estimators(name):
+    from simpimc_b200 import host
+    cfg = CONFIGS[name]()
+    path, oracles, _ = make_pair(cfg, 3)
+    ns = len(cfg.species)
+    for sa in range(ns):
+        for sb in range(sa, ns):
+            gr = host.PairCorrelation(path, sa, sb, 0.0, cfg.L / 2, 100)
+            counts = gr.Counts()
+            gr.Accumulate(cofactor=np.array([1.0, -1.0, 1.0]))
+            sk = host.StructureFactor(path, sa, sb, cfg.k_cut)
+            sk.Accumulate()
+            sk.Accumulate(cofactor=np.array([1.0, -1.0, 1.0]))
+            for c, o in enumerate(oracles):
+                y, oc = o.gofr(sa, sb, 0.0, cfg.L / 2, 100, cofactor=[1.0, -1.0, 1.0][c])
+                assert np.array_equal(counts[c], oc)              # bins: bit-exact
+                assert np.array_equal(gr.y[c], y)
+                ref = o.sofk(sa, sb, cfg.k_cut) * (1.0 + [1.0, -1.0, 1.0][c])
+                assert np.max(np.abs(sk.sk[c] - ref)) <= 1e-10 * max(1.0, np.max(np.abs(o.sofk(sa, sb, cfg.k_cut))))
+    path.close()
+
+
+def test_energy_observable_matches_oracle():
+    from simpimc_b200 import host
+    cfg = S.plasma_config(Ne=6, Np=5, M=8)
+    path, oracles, _ = make_pair(cfg, 2)
+    en = host.Energy(path, measure_potential=True)
+    en.Accumulate()
+    e, v = en.Write()
+    for c, o in enumerate(oracles):
+        for i in range(len(cfg.actions)):
+            assert rel_ok(e[i, c] * cfg.n_bead, o.dbeta(i))
+            assert rel_ok(v[i, c] * cfg.n_bead, o.potential(i))
+    path.close()
+
+
+def test_errors_are_loud():
+    from simpimc_b200 import host
+    cfg = S.ueg_config(N=7, M=8)
+    cfg.actions[0].max_level = 1
+    with pytest.raises(RuntimeError):
+        host.Path(cfg, n_clones=1)
+    cfg = S.ueg_config(N=7, M=8)
+    cfg.n_d = 2
+    with pytest.raises(RuntimeError):
+        host.Path(cfg, n_clones=1)
