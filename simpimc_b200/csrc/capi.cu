@@ -343,7 +343,8 @@ int LoadLongRange(pimc_ctx *ctx, pimc_action *a, int which, const pimc_long_rang
 // ------------------------------------------------------------------------------ launchers
 template <int ATYPE, int WHICH>
 int LaunchPairFullT(pimc_ctx *ctx, const PairFullArgs &args, size_t smem, int grid) {
-    PIMC_CUDA(cudaFuncSetAttribute(pair_full_kernel<ATYPE, WHICH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    if (smem > 48 * 1024)
+        PIMC_CUDA(cudaFuncSetAttribute(pair_full_kernel<ATYPE, WHICH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pair_full_kernel<ATYPE, WHICH><<<grid, kPairThreads, smem, ctx->stream>>>(args);
     ctx->launches++;
     PIMC_CUDA(cudaGetLastError());
@@ -1075,13 +1076,10 @@ int pimc_commit(pimc_ctx *ctx, const int32_t *accept) {
                                                                   st.rho.p);
                 ctx->launches++;
                 PIMC_CUDA(cudaGetLastError());
-            } else if (ctx->n_k() > 0) {
-                // no action refreshed rho_k for this proposal (no long-range action touched the
-                // species in NEW mode): keep the committed rho_k consistent with the new path
-                bool any = false;
-                for (int c = 0; c < ctx->C; ++c) any = any || accept[c];
-                if (any && (rc = RebuildRhoK(ctx, (int)(&sp - &ctx->species[0]))) != PIMC_OK) return rc;
             }
+            // If no long-range action evaluated this proposal in NEW mode, rho_k is NOT refreshed:
+            // the reference only updates it inside PairAction::GetAction
+            // (pair_action_class.h:293-299), so StoreRhoK commits the old values there too.
         }
         st.n_prop = 0;
         st.drho_valid = false;
