@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the action-evaluation hot path (BASELINE.json metric: bead-pair action evals/s
++ MC sweeps/s, UEG N=256 M=128, 1024 clones per B200).
+
+    python bench.py --gpus N --steps K --warmup W            our arm (CUDA, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K ...   the reference's CPU implementation
+
+A step = one full energy evaluation of every clone: rebuild rho_k from the positions (K2),
+IlkkaPairAction::DActionDBeta over all pairs and slices with the long-range r-space
+subtraction (K1), the Ewald k-space sum and constants (K3 + finalize).  One bead-pair action
+eval = one DrDrpDrrp + one CalcdUdBeta, 273 flop by the stated convention.
+
+`value`   inputs resident in HBM, K steps timed with CUDA events on the library's stream.
+`e2e`     the same step through the C ABI with HOST buffers: pimc_positions_upload from pinned
+          host memory + pimc_action_dbeta returning host doubles, every step.
+Both arms print one JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_EVAL = 273.0   # Ilkka bead-pair eval with long-range subtraction
+N_PART, N_SLICE = 256, 128
+BISECT_LEVEL = 3
+
+
+def pair_evals_per_clone(N=N_PART, M=N_SLICE):
+    return N * (N - 1) // 2 * M
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks line of B200_PROFILING.md, sampled every 200 ms during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------- CPU baseline
+def _cpu_worker(args):
+    """One process = one walker (the reference's MPI model, framework_class.h:44-53)."""
+    kind, clone, n_eval, N, M = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    import numpy as np
+    from simpimc_b200 import system as S
+    cfg = S.ueg_config(N=N, M=M)
+    R = S.synthetic_paths(cfg, 0, clone)
+    if kind == "reference":
+        from oracle import refsim
+        sim = refsim.RefSim(cfg, fast=refsim.available(fast=True))
+        sim.set_positions(0, R)
+        f = lambda: sim.dbeta(0)
+    else:
+        from oracle import oracle as O
+        sim = O.Oracle(cfg)
+        sim.set_positions(0, R)
+        f = lambda: sim.dbeta(0)
+    f()
+    t0 = time.perf_counter()
+    val = 0.0
+    for _ in range(n_eval):
+        val = f()
+    return time.perf_counter() - t0, val
+
+
+def cpu_baseline(n_eval=1, N=N_PART, M=N_SLICE, cores=None):
+    """DActionDBeta() of the CPU implementation on every host core at once: `cores` independent
+    single-clone processes, each timing n_eval full evaluations after one warm-up."""
+    import multiprocessing as mp
+    from oracle import refsim
+    kind = "reference" if refsim.available() else "port"
+    cores = cores or len(os.sched_getaffinity(0))
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(kind, c, n_eval, N, M) for c in range(cores)])
+    wall = time.perf_counter() - t0
+    slowest = max(r[0] for r in res)
+    evals = cores * n_eval * pair_evals_per_clone(N, M)
+    return {"value": evals / slowest, "unit": "bead-pair action evals/s", "cores": cores, "kind": kind,
+            "sample": "%d clone(s) x %d DActionDBeta() of UEG N=%d M=%d, one process per core, %.1f s wall incl. setup"
+                      % (cores, n_eval, N, M, wall)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps_evals = max(1, args.steps)
+    t0 = time.perf_counter()
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(n_eval=1)
+    base = cpu_baseline(n_eval=steps_evals)
+    ms = 1e3 * (time.perf_counter() - t0) / max(1, args.steps)
+    line = {"impl": "reference", "metric": "bead-pair action evals/s", "value": base["value"], "unit": "bead-pair action evals/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "UEG N=256 M=128 IlkkaPairAction use_long_range=1: DActionDBeta() per clone, one clone per host core",
+                       "step": "one DActionDBeta() per core"},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "bead-pair action evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from simpimc_b200 import host, moves, system as S, capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    C = args.clones
+    cfg = S.ueg_config(N=N_PART, M=N_SLICE)
+    path = host.Path(cfg, n_clones=C, device=local)
+    act = path.actions[0]
+    lib = path.L
+    # synthetic walkers: clone index offset by rank so every GPU holds different walkers
+    R_pinned = torch.empty((C, N_PART, N_SLICE, 3), dtype=torch.float64, pin_memory=True)
+    R = R_pinned.numpy()
+    for c in range(C):
+        R[c] = S.synthetic_paths(cfg, 0, rank * C + c)
+    path.SetPositions(0, R)
+    out_dev = torch.zeros(C, dtype=torch.float64, device="cuda")
+    out_host = np.zeros(C)
+    stream = torch.cuda.ExternalStream(lib.pimc_ctx_stream(path.h), device=torch.device("cuda", local))
+
+    def step_resident():
+        capi.check(lib.pimc_rhok_rebuild(path.h, 0))
+        capi.check(lib.pimc_action_dbeta_device(act.h, out_dev.data_ptr()))
+
+    def step_e2e():
+        capi.check(lib.pimc_positions_upload(path.h, 0, 0, C, R.ctypes.data))
+        capi.check(lib.pimc_action_dbeta(act.h, out_host.ctypes.data))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        path.Sync()
+
+    fp64_peak = path.Fp64Peak()
+    for _ in range(args.warmup):
+        step_resident()
+    path.Sync()
+    # ---- device-resident timing ------------------------------------------------------------
+    path.SetTiming(True)
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    launches0 = path.LaunchCount()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    e1.record(stream)
+    e1.synchronize()
+    barrier()
+    launches = path.LaunchCount() - launches0
+    clk = clocks.stop()
+    ms_total = e0.elapsed_time(e1)
+    k1_ms, k1_n = path.KernelTime(1)
+    k2_ms, k2_n = path.KernelTime(2)
+    k3_ms, k3_n = path.KernelTime(3)
+    path.SetTiming(False)
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    evals_step = C * pair_evals_per_clone()
+    value = world * evals_step * args.steps / (ms_max * 1e-3)
+    # ---- end to end through the C ABI with host buffers -------------------------------------
+    for _ in range(min(2, args.warmup)):
+        step_e2e()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    f1.record(stream)
+    f1.synchronize()
+    w1 = time.perf_counter()
+    barrier()
+    te = torch.tensor([max(f0.elapsed_time(f1), 1e3 * (w1 - w0))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * evals_step * args.steps / (float(te.item()) * 1e-3)
+    # correctness guard for the bench itself: both paths computed the same energies
+    assert np.allclose(out_dev.cpu().numpy(), out_host, rtol=1e-12, atol=0), "resident and e2e energies differ"
+    # ---- MC sweeps: host-driven bisection attempts on all clones ------------------------------
+    rng = np.random.default_rng(1234 + rank)
+    bis = moves.Bisect(path, rng, 0, BISECT_LEVEL)
+    for _ in range(2):
+        bis.DoEvent()
+    barrier()
+    n_att = args.attempts
+    s0 = time.perf_counter()
+    for _ in range(n_att):
+        bis.DoEvent()
+    path.Sync()
+    s1 = time.perf_counter()
+    ts = torch.tensor([s1 - s0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+    attempts_per_sweep = N_PART * N_SLICE // (1 << BISECT_LEVEL)
+    sweeps_per_s = world * C * n_att / attempts_per_sweep / float(ts.item())
+    window_evals_per_s = world * C * n_att * 2 * (N_PART - 1) * (1 << BISECT_LEVEL) / float(ts.item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel (K1) ------------------------------------------------
+    k1_avg_s = (k1_ms / max(1, k1_n)) * 1e-3
+    achieved = evals_step * FLOP_PER_EVAL / k1_avg_s / 1e12
+    traffic = None
+    tf = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(tf):
+        try:
+            traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "fp64", "kernel": "pair_full_kernel<ILKKA,DU>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
+                "peak_source": "DFMA micro-benchmark (pimc_fp64_peak) measured in this run; MEASURED_PEAKS.json holds no FP64 figure",
+                "algorithmic_flop_per_launch": evals_step * FLOP_PER_EVAL,
+                "algorithmic_bytes_per_launch": C * N_SLICE * N_PART * 24,
+                "kernel_ms": {"K1_pair_full": k1_ms / max(1, k1_n), "K2_rhok_build": k2_ms / max(1, k2_n), "K3_ksum": k3_ms / max(1, k3_n)},
+                "kernel_share_of_step": {"K1": k1_ms / ms_total, "K2": k2_ms / ms_total, "K3": k3_ms / ms_total}}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        hbm = peaks.get("hbm_gbs")
+    except Exception:
+        hbm = 6650.0
+    roofline["hbm_gbs_peak"] = hbm
+    roofline["k1_hbm_gbs_algorithmic"] = C * N_SLICE * N_PART * 24 / k1_avg_s / 1e9
+    base = cpu_baseline(n_eval=args.cpu_evals) if args.cpu_evals > 0 else None
+    line = {"metric": "bead-pair action evals/s", "value": value, "unit": "bead-pair action evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "UEG N=256 M=128, IlkkaPairAction use_long_range=1 (n_k=182), %d clones per GPU" % C,
+                       "step": "rho_k rebuild + DActionDBeta (pair action over all pairs x slices + Ewald k-sum + constants)",
+                       "clones_per_gpu": C, "parallelism": "independent clones per GPU, no data-path collective",
+                       "l2": "inputs larger than L2 (positions %.0f MB + rho_k %.0f MB per GPU)" % (R.nbytes / 1e6, C * N_SLICE * 182 * 16 / 1e6),
+                       "bisect_n_level": BISECT_LEVEL},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "bead-pair action evals/s", "h2d_bytes_per_step": int(R.nbytes),
+                    "d2h_bytes_per_step": int(out_host.nbytes)},
+            "gpu_launches": int(launches),
+            "mc_sweeps_per_s": sweeps_per_s,
+            "mc": {"unit": "clone-sweeps/s (one sweep = N*M/2^n_level bisection attempts)", "attempts_timed": n_att,
+                   "accept_ratio": bis.accept_ratio(), "window_pair_evals_per_s": window_evals_per_s,
+                   "driver": "host-driven Bisect (simpimc_b200.moves) calling GetAction OLD/NEW + commit through the C ABI"},
+            "roofline": roofline}
+    if base:
+        line["cpu_baseline"] = base
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clones", type=int, default=int(os.environ.get("BENCH_CLONES", "1024")))
+    ap.add_argument("--attempts", type=int, default=24, help="bisection attempts timed for the MC-sweep figure")
+    ap.add_argument("--cpu-evals", type=int, default=2, help="DActionDBeta() calls per core for cpu_baseline (0 = skip)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -186,6 +186,11 @@ int pimc_action_calc_pair(pimc_action *act, int32_t which, int32_t n, const doub
  * of particle[c] take newR[c][i][dim]. */
 int pimc_propose(pimc_ctx *ctx, int32_t species, const int32_t *particle, const int32_t *b_first, int32_t n_beads,
                  const double *newR);
+/* Committed positions of beads b_first[c] .. b_first[c]+n_beads-1 (mod n_bead) of
+ * particle[c], out[c][i][dim] (what Bisect::Attempt reads through GetBead / GetNextBead,
+ * bisect_class.h:51-58). */
+int pimc_beads_download(pimc_ctx *ctx, int32_t species, const int32_t *particle, const int32_t *b_first, int32_t n_beads,
+                        double *out);
 /* Move::Accept (accept[c] != 0) or Move::Reject for the pending proposals of all species:
  * StoreR/StoreRhoK or RestoreR/RestoreRhoK, then every action's flag is re-armed. */
 int pimc_commit(pimc_ctx *ctx, const int32_t *accept);
@@ -206,6 +211,18 @@ int pimc_est_sofk(pimc_ctx *ctx, int32_t species_a, int32_t species_b, double k_
 /* ---- measurement helpers ------------------------------------------------------------- */
 /* Number of kernels this library launched since the context was created. */
 int64_t pimc_ctx_launch_count(pimc_ctx *ctx);
+/* Per-kernel device time, measured with CUDA events on the context's stream around every
+ * launch while timing is enabled (enable = 0/1 also clears the totals). */
+enum {
+    PIMC_KERNEL_PAIR_FULL = 1,   /* K1 */
+    PIMC_KERNEL_RHOK_BUILD = 2,  /* K2 */
+    PIMC_KERNEL_KSUM = 3,        /* K3 */
+    PIMC_KERNEL_PAIR_WINDOW = 4, /* K4 */
+    PIMC_KERNEL_GOFR = 5,        /* K5 */
+    PIMC_KERNEL_SOFK = 6         /* K6 */
+};
+int pimc_ctx_set_timing(pimc_ctx *ctx, int32_t enable);
+int pimc_ctx_kernel_time(pimc_ctx *ctx, int32_t kernel_id, double *total_ms, int64_t *n_launches);
 /* FP64 FMA micro-benchmark on the context's device: returns achieved TFLOP/s (2 flop/FMA). */
 int pimc_fp64_peak(pimc_ctx *ctx, double *tflops);
 

@@ -147,8 +147,8 @@ EXPORTS = [
     "pimc_action_create_ilkka", "pimc_action_create_bare", "pimc_action_create_david", "pimc_action_destroy",
     "pimc_action_dbeta", "pimc_action_potential", "pimc_action_dbeta_device", "pimc_action_potential_device",
     "pimc_action_get", "pimc_action_total", "pimc_action_total_device", "pimc_action_accept", "pimc_action_reject",
-    "pimc_action_calc_pair", "pimc_propose", "pimc_commit", "pimc_est_gofr", "pimc_est_gofr_counts", "pimc_est_sofk",
-    "pimc_ctx_launch_count", "pimc_fp64_peak",
+    "pimc_action_calc_pair", "pimc_propose", "pimc_beads_download", "pimc_commit", "pimc_est_gofr", "pimc_est_gofr_counts", "pimc_est_sofk",
+    "pimc_ctx_launch_count", "pimc_fp64_peak", "pimc_ctx_set_timing", "pimc_ctx_kernel_time",
 ]
 
 _lib = None
@@ -194,12 +194,15 @@ def lib():
     L.pimc_action_calc_pair.argtypes = [vp, i32, i32, vp, vp, vp, i32, vp]
     L.pimc_propose.argtypes = [vp, i32, vp, vp, i32, vp]
     L.pimc_commit.argtypes = [vp, vp]
+    L.pimc_beads_download.argtypes = [vp, i32, vp, vp, i32, vp]
     L.pimc_est_gofr.argtypes = [vp, i32, i32, dbl, dbl, i32, vp, vp]
     L.pimc_est_gofr_counts.argtypes = [vp, i32, i32, dbl, dbl, i32, vp]
     L.pimc_est_sofk.argtypes = [vp, i32, i32, dbl, vp, vp]
     L.pimc_ctx_launch_count.restype = C.c_int64
     L.pimc_ctx_launch_count.argtypes = [vp]
     L.pimc_fp64_peak.argtypes = [vp, c_double_p]
+    L.pimc_ctx_set_timing.argtypes = [vp, i32]
+    L.pimc_ctx_kernel_time.argtypes = [vp, i32, c_double_p, C.POINTER(C.c_int64)]
     _lib = L
     return L
 

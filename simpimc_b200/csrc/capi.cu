@@ -98,6 +98,13 @@ struct pimc_ctx {
     DevBuf<double> est;
     std::vector<pimc_action *> actions;
     int64_t launches = 0;
+    // optional per-kernel device timing (CUDA events on the context's stream)
+    bool timing = false;
+    struct KTimer {
+        std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+        double total_ms = 0.;
+        int64_t n = 0;
+    } timers[8];
 
     int n_k() const { return (int)k_mag.size(); }
     PathView View() const {
@@ -153,6 +160,29 @@ struct pimc_action {
 namespace {
 
 // -------------------------------------------------------------------------------- helpers
+/// Brackets one kernel launch with CUDA events when timing is enabled.
+struct ScopedKernelTimer {
+    pimc_ctx *ctx;
+    int id;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ScopedKernelTimer(pimc_ctx *c, int kernel_id);
+    ~ScopedKernelTimer();
+};
+
+ScopedKernelTimer::ScopedKernelTimer(pimc_ctx *c, int kernel_id) : ctx(c), id(kernel_id) {
+    if (!ctx->timing) return;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
+        e0 = e1 = nullptr;
+        return;
+    }
+    cudaEventRecord(e0, ctx->stream);
+}
+ScopedKernelTimer::~ScopedKernelTimer() {
+    if (!e0) return;
+    cudaEventRecord(e1, ctx->stream);
+    ctx->timers[id].pending.push_back(std::make_pair(e0, e1));
+}
+
 int EnsureI32(pimc_ctx *ctx, DevBuf<int32_t> &buf, const int32_t *host, size_t n) {
     if (buf.n < n) PIMC_CUDA(buf.Alloc(n));
     PIMC_CUDA(cudaMemcpyAsync(buf.p, host, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -239,7 +269,10 @@ int RebuildRhoK(pimc_ctx *ctx, int s) {
     int chunk = std::max(1, std::min(32, (int)(40000 / (3 * tl * sizeof(double2)))));
     const size_t smem = (size_t)chunk * 3 * tl * sizeof(double2);
     const int items = ctx->C * ctx->Mloc;
-    rhok_build_kernel<<<GridFor(ctx, items), 256, smem, ctx->stream>>>(ctx->View(), ctx->SView(s, false), ctx->KView(), chunk, st.rho.p);
+    {
+        ScopedKernelTimer t(ctx, PIMC_KERNEL_RHOK_BUILD);
+        rhok_build_kernel<<<GridFor(ctx, items), 256, smem, ctx->stream>>>(ctx->View(), ctx->SView(s, false), ctx->KView(), chunk, st.rho.p);
+    }
     ctx->launches++;
     PIMC_CUDA(cudaGetLastError());
     return PIMC_OK;
@@ -345,7 +378,10 @@ template <int ATYPE, int WHICH>
 int LaunchPairFullT(pimc_ctx *ctx, const PairFullArgs &args, size_t smem, int grid) {
     if (smem > 48 * 1024)
         PIMC_CUDA(cudaFuncSetAttribute(pair_full_kernel<ATYPE, WHICH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pair_full_kernel<ATYPE, WHICH><<<grid, kPairThreads, smem, ctx->stream>>>(args);
+    {
+        ScopedKernelTimer t(ctx, PIMC_KERNEL_PAIR_FULL);
+        pair_full_kernel<ATYPE, WHICH><<<grid, kPairThreads, smem, ctx->stream>>>(args);
+    }
     ctx->launches++;
     PIMC_CUDA(cudaGetLastError());
     return PIMC_OK;
@@ -405,7 +441,10 @@ int LaunchKSum(pimc_action *a, int which, const int32_t *d_b0, int n_window, boo
     k.twice = a->sa != a->sb;
     k.scale = scale;
     k.out = ctx->lr_dev.p;
-    ksum_kernel<<<ctx->C, 256, 0, ctx->stream>>>(k);
+    {
+        ScopedKernelTimer t(ctx, PIMC_KERNEL_KSUM);
+        ksum_kernel<<<ctx->C, 256, 0, ctx->stream>>>(k);
+    }
     ctx->launches++;
     PIMC_CUDA(cudaGetLastError());
     return PIMC_OK;
@@ -936,10 +975,13 @@ int pimc_action_get(pimc_action *act, int32_t mode, const int32_t *b0, int32_t n
     if (ctx->partial.n < items) PIMC_CUDA(ctx->partial.Alloc(items));
     w.partial = ctx->partial.p;
     const int grid = (int)std::min<size_t>(items, (size_t)ctx->n_sm * 16);
-    switch (act->atype) {
-        case ATYPE_ILKKA: pair_window_kernel<ATYPE_ILKKA><<<grid, 128, 0, ctx->stream>>>(w); break;
-        case ATYPE_BARE: pair_window_kernel<ATYPE_BARE><<<grid, 128, 0, ctx->stream>>>(w); break;
-        default: pair_window_kernel<ATYPE_DAVID><<<grid, 128, 0, ctx->stream>>>(w); break;
+    {
+        ScopedKernelTimer t(ctx, PIMC_KERNEL_PAIR_WINDOW);
+        switch (act->atype) {
+            case ATYPE_ILKKA: pair_window_kernel<ATYPE_ILKKA><<<grid, 128, 0, ctx->stream>>>(w); break;
+            case ATYPE_BARE: pair_window_kernel<ATYPE_BARE><<<grid, 128, 0, ctx->stream>>>(w); break;
+            default: pair_window_kernel<ATYPE_DAVID><<<grid, 128, 0, ctx->stream>>>(w); break;
+        }
     }
     ctx->launches++;
     PIMC_CUDA(cudaGetLastError());
@@ -1057,6 +1099,28 @@ int pimc_propose(pimc_ctx *ctx, int32_t s, const int32_t *particle, const int32_
     return PIMC_OK;
 }
 
+int pimc_beads_download(pimc_ctx *ctx, int32_t s, const int32_t *particle, const int32_t *b_first, int32_t n_beads, double *out) {
+    if (!ctx || !particle || !b_first || !out) return Fail(PIMC_ERR_INVALID, "null argument");
+    if (s < 0 || s >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
+    if (n_beads < 1 || n_beads > 2 * ctx->M) return Fail(PIMC_ERR_INVALID, "bad bead count");
+    if (ctx->sharded) return Fail(PIMC_ERR_UNSUPPORTED, "bead windows on a slice-sharded context");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    SpeciesState &st = *ctx->species[s];
+    for (int c = 0; c < ctx->C; ++c) {
+        if (particle[c] < 0 || particle[c] >= st.N) return Fail(PIMC_ERR_INVALID, "particle out of range");
+        if (b_first[c] < 0 || b_first[c] >= ctx->M) return Fail(PIMC_ERR_INVALID, "bead out of range");
+    }
+    int rc;
+    if ((rc = EnsureI32(ctx, ctx->i32_a, particle, ctx->C)) != PIMC_OK) return rc;
+    if ((rc = EnsureI32(ctx, ctx->i32_b, b_first, ctx->C)) != PIMC_OK) return rc;
+    const size_t n = (size_t)ctx->C * n_beads * 3;
+    if (ctx->stage.n < n) PIMC_CUDA(ctx->stage.Alloc(n));
+    gather_beads_kernel<<<ctx->C, 64, 0, ctx->stream>>>(ctx->View(), st.R.p, st.Npad, ctx->i32_a.p, ctx->i32_b.p, n_beads, ctx->stage.p);
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    return ToHost(ctx, ctx->stage.p, out, n);
+}
+
 int pimc_commit(pimc_ctx *ctx, const int32_t *accept) {
     if (!ctx || !accept) return Fail(PIMC_ERR_INVALID, "null argument");
     PIMC_CUDA(cudaSetDevice(ctx->device));
@@ -1110,7 +1174,10 @@ int pimc_est_gofr_counts(pimc_ctx *ctx, int32_t sa, int32_t sb, double r_min, do
     g.n_r = n_r;
     g.counts = ctx->counts.p;
     const int items = ctx->C * ctx->Mloc;
-    gofr_kernel<<<GridFor(ctx, items), 256, n_r * sizeof(unsigned int), ctx->stream>>>(g);
+    {
+        ScopedKernelTimer t(ctx, PIMC_KERNEL_GOFR);
+        gofr_kernel<<<GridFor(ctx, items), 256, n_r * sizeof(unsigned int), ctx->stream>>>(g);
+    }
     ctx->launches++;
     PIMC_CUDA(cudaGetLastError());
     PIMC_CUDA(cudaMemcpyAsync(counts, ctx->counts.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1151,11 +1218,50 @@ int pimc_est_sofk(pimc_ctx *ctx, int32_t sa, int32_t sb, double k_cut, const dou
         PIMC_CUDA(cudaMemcpyAsync(d_cf, cofactor, ctx->C * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
     dim3 grid((n_k + 127) / 128, ctx->C);
-    sofk_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->View(), n_k, ctx->species[sa]->rho.p, ctx->species[sb]->rho.p, ctx->d_kmag.p, k_cut, d_cf,
-                                               ctx->est.p);
+    {
+        ScopedKernelTimer t(ctx, PIMC_KERNEL_SOFK);
+        sofk_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->View(), n_k, ctx->species[sa]->rho.p, ctx->species[sb]->rho.p, ctx->d_kmag.p, k_cut,
+                                                   d_cf, ctx->est.p);
+    }
     ctx->launches++;
     PIMC_CUDA(cudaGetLastError());
     return ToHost(ctx, ctx->est.p, sk, n);
+}
+
+int pimc_ctx_set_timing(pimc_ctx *ctx, int32_t enable) {
+    if (!ctx) return Fail(PIMC_ERR_INVALID, "null context");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    PIMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (auto &t : ctx->timers) {
+        for (auto &p : t.pending) {
+            cudaEventDestroy(p.first);
+            cudaEventDestroy(p.second);
+        }
+        t.pending.clear();
+        t.total_ms = 0.;
+        t.n = 0;
+    }
+    ctx->timing = enable != 0;
+    return PIMC_OK;
+}
+
+int pimc_ctx_kernel_time(pimc_ctx *ctx, int32_t kernel_id, double *total_ms, int64_t *n_launches) {
+    if (!ctx || kernel_id < 0 || kernel_id >= 8) return Fail(PIMC_ERR_INVALID, "bad kernel id");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    PIMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    auto &t = ctx->timers[kernel_id];
+    for (auto &p : t.pending) {
+        float ms = 0.f;
+        PIMC_CUDA(cudaEventElapsedTime(&ms, p.first, p.second));
+        t.total_ms += ms;
+        t.n += 1;
+        cudaEventDestroy(p.first);
+        cudaEventDestroy(p.second);
+    }
+    t.pending.clear();
+    if (total_ms) *total_ms = t.total_ms;
+    if (n_launches) *n_launches = t.n;
+    return PIMC_OK;
 }
 
 int pimc_fp64_peak(pimc_ctx *ctx, double *tflops) {

@@ -502,6 +502,19 @@ __global__ void positions_out_kernel(const double *__restrict__ src, int n_clone
     }
 }
 
+/// out[c][j][d] = committed position of particle[c] at slice b_first[c] + j (mod M).
+__global__ void gather_beads_kernel(PathView pv, const double *__restrict__ R, int Npad, const int32_t *__restrict__ particle,
+                                    const int32_t *__restrict__ b_first, int n_beads, double *__restrict__ out) {
+    const int c = blockIdx.x;
+    const int p = particle[c];
+    for (int t = threadIdx.x; t < n_beads * 3; t += blockDim.x) {
+        const int j = t / 3, d = t - j * 3;
+        int bg = b_first[c] + j;
+        while (bg >= pv.M) bg -= pv.M;
+        out[((size_t)c * n_beads + j) * 3 + d] = R[PosIndex(pv, Npad, c, bg - pv.slice_lo, d, p)];
+    }
+}
+
 /// Move::Accept for the clones whose accept flag is set: committed positions take the
 /// proposal, committed rho_k takes rho_k + drho on the window slices.
 __global__ void commit_positions_kernel(PathView pv, int Npad, const double *__restrict__ P, const int32_t *__restrict__ P_particle,

@@ -133,6 +133,14 @@ class Path:
         assert newR.shape[0] == self.n_clones and newR.shape[2] == self.n_d
         capi.check(self.L.pimc_propose(self.h, species, _vp(particle), _vp(b_first), newR.shape[1], _vp(newR)))
 
+    def GetBeads(self, species, particle, b_first, n_beads):
+        """Committed positions [clone][i][dim] of beads b_first[c]+i of particle[c]."""
+        particle = np.ascontiguousarray(np.broadcast_to(particle, (self.n_clones,)), dtype=np.int32)
+        b_first = np.ascontiguousarray(np.broadcast_to(b_first, (self.n_clones,)), dtype=np.int32)
+        out = np.zeros((self.n_clones, n_beads, self.n_d))
+        capi.check(self.L.pimc_beads_download(self.h, species, _vp(particle), _vp(b_first), n_beads, _vp(out)))
+        return out
+
     def Commit(self, accept):
         accept = np.ascontiguousarray(np.broadcast_to(accept, (self.n_clones,)), dtype=np.int32)
         capi.check(self.L.pimc_commit(self.h, _vp(accept)))
@@ -142,6 +150,15 @@ class Path:
 
     def Sync(self):
         capi.check(self.L.pimc_ctx_sync(self.h))
+
+    def SetTiming(self, enable=True):
+        capi.check(self.L.pimc_ctx_set_timing(self.h, 1 if enable else 0))
+
+    def KernelTime(self, kernel_id):
+        """(total ms, launches) of one kernel family since timing was enabled."""
+        ms, n = C.c_double(), C.c_int64()
+        capi.check(self.L.pimc_ctx_kernel_time(self.h, kernel_id, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def Fp64Peak(self):
         t = C.c_double()
