@@ -148,8 +148,11 @@ struct pimc_action {
     int max_level = 0;
     bool use_long_range = false;
     bool is_constant = false;
-    // table blobs per evaluated quantity (U, dU, V)
+    // per evaluated quantity (U, dU, V): the stageable blob (grids, LUTs, 1-D pp coefficients;
+    // for David the B-spline multi-spline, read from global memory), the 2-D cell polynomials
     DevBuf<double> blob[3];
+    DevBuf<double> cells[3];
+    bool stageable[3] = {true, true, true};
     PairTable table[3];
     // long range: weight per k vector and scaled constants
     DevBuf<double> wk[3];
@@ -279,6 +282,42 @@ int RebuildRhoK(pimc_ctx *ctx, int s) {
 }
 
 // --------------------------------------------------------------------------- table packing
+void PadEven(std::vector<double> &blob) {
+    if (blob.size() & 1) blob.push_back(0.0);
+}
+
+void AppendLut(std::vector<double> &blob, LutDesc &d, const double *grid, int n) {
+    PadEven(blob);
+    BitLut L = BuildBitLut(grid, n);
+    d.off = (int)(blob.size() * 4);
+    d.n_keys = (int)L.lut.size();
+    d.shift = L.shift;
+    d.key0 = L.key0;
+    const size_t n_dbl = (L.lut.size() + 3) / 4;
+    const size_t base = blob.size();
+    blob.resize(base + n_dbl, 0.0);
+    std::memcpy(reinterpret_cast<char *>(blob.data() + base), L.lut.data(), L.lut.size() * sizeof(uint16_t));
+}
+
+/// Appends [grid | pp | lut] of the natural spline through (grid, data) and describes it.
+void AppendPP1(std::vector<double> &blob, PP1Desc &d, const double *grid, const double *data, int n) {
+    KnotBasis kb;
+    kb.Build(grid, n);
+    std::vector<double> coefs(n + 3, 0.0);
+    SolveNatural(kb, data, 1, coefs.data(), 1);
+    std::vector<double> pp = PPFrom1D(kb, coefs.data());
+    PadEven(blob);
+    d.n = n;
+    d.off_g = (int)blob.size();
+    blob.insert(blob.end(), grid, grid + n);
+    PadEven(blob);
+    d.off_pp = (int)blob.size();
+    blob.insert(blob.end(), pp.begin(), pp.end());
+    AppendLut(blob, d.lut, grid, n);
+    d.r_min = grid[0];
+    d.r_max = grid[n - 1];
+}
+
 void Fill1D(Sp1Desc &d, int n, int base, const double *grid) {
     d.n = n;
     d.off_t = base;
@@ -359,13 +398,10 @@ int NewAction(pimc_ctx *ctx, int atype, int sa, int sb, int max_level, int use_l
     return PIMC_OK;
 }
 
-int LoadLongRange(pimc_ctx *ctx, pimc_action *a, int which, const pimc_long_range &lr, std::vector<double> &blob, Sp1Desc &desc) {
+int LoadLongRange(pimc_ctx *ctx, pimc_action *a, int which, const pimc_long_range &lr, std::vector<double> &blob, PP1Desc &desc) {
     CheckTable1D(lr.f_r, "long-range r table");
     if (lr.n_k < 1 || !lr.k || !lr.f_k) throw std::invalid_argument("long-range k table missing");
-    const int base = (int)blob.size();
-    std::vector<double> b = BuildBlob1D(lr.f_r.r, lr.f_r.f, lr.f_r.n);
-    blob.insert(blob.end(), b.begin(), b.end());
-    Fill1D(desc, lr.f_r.n, base, lr.f_r.r);
+    AppendPP1(blob, desc, lr.f_r.r, lr.f_r.f, lr.f_r.n);
     int rc = UploadVec(a->wk[which], MatchShells(ctx, lr));
     if (rc != PIMC_OK) return rc;
     a->k0[which] = lr.f_k_0;
@@ -402,13 +438,13 @@ int LaunchPairFull(pimc_action *a, int which, bool independent_images) {
     if (ctx->partial.n < items) PIMC_CUDA(ctx->partial.Alloc(items));
     args.partial = ctx->partial.p;
     const size_t pos_bytes = sizeof(double) * 2 * 3 * (args.A.Npad + (args.same ? 0 : args.B.Npad));
-    const size_t blob_bytes = sizeof(double) * a->blob[which].n;
-    args.stage = (pos_bytes + blob_bytes + 1024 <= ctx->smem_optin) ? 1 : 0;
+    const size_t blob_bytes = a->stageable[which] ? sizeof(double) * a->blob[which].n : 0;
+    args.stage = (a->stageable[which] && pos_bytes + blob_bytes + 1024 <= ctx->smem_optin) ? 1 : 0;
     const size_t smem = pos_bytes + (args.stage ? blob_bytes : 0);
     if (smem > ctx->smem_optin) return Fail(PIMC_ERR_UNSUPPORTED, "species too large for the shared-memory position tile");
     // persistent CTAs: as many as fit per SM given the staged table, never more than the items
     int per_sm = std::max(1, (int)(ctx->smem_optin / std::max<size_t>(smem + 1024, 1)));
-    per_sm = std::min(per_sm, 2048 / kPairThreads);
+    per_sm = std::min(per_sm, kPairCtasPerSm);
     const int grid = (int)std::min<size_t>(items, (size_t)ctx->n_sm * per_sm);
 #define PIMC_DISPATCH(AT)                                                                    \
     switch (which) {                                                                         \
@@ -707,16 +743,27 @@ int pimc_action_create_ilkka(pimc_ctx *ctx, int32_t sa, int32_t sb, const pimc_i
         for (int which = 0; which < 2; ++which) {
             const pimc_table_2d &g = *xy[which];
             if (g.n_x < 4 || g.n_y < 4 || !g.x || !g.y || !g.f) throw std::invalid_argument("off-diagonal table missing");
-            std::vector<double> blob = BuildBlob2D(g.x, g.n_x, g.y, g.n_y, g.f);
+            // tensor-product natural spline (create_NUBspline_2d_d), then one bicubic per cell
+            std::vector<double> bs = BuildBlob2D(g.x, g.n_x, g.y, g.n_y, g.f);
+            KnotBasis bx, by;
+            bx.Build(g.x, g.n_x);
+            by.Build(g.y, g.n_y);
+            const size_t off_c = (size_t)(g.n_x + 5) + 3 * (g.n_x + 2) + (g.n_y + 5) + 3 * (g.n_y + 2);
+            std::vector<double> cells = PPFrom2D(bx, by, bs.data() + off_c);
+            rc = UploadBlob(ctx, a->cells[which], cells);
+            if (rc != PIMC_OK) return rc;
             PairTable &T = a->table[which];
             std::memset(&T, 0, sizeof(T));
+            std::vector<double> blob;
             T.xy.nx = g.n_x;
             T.xy.ny = g.n_y;
-            T.xy.off_tx = 0;
-            T.xy.off_wx = g.n_x + 5;
-            T.xy.off_ty = T.xy.off_wx + 3 * (g.n_x + 2);
-            T.xy.off_wy = T.xy.off_ty + g.n_y + 5;
-            T.xy.off_c = T.xy.off_wy + 3 * (g.n_y + 2);
+            T.xy.off_gx = (int)blob.size();
+            blob.insert(blob.end(), g.x, g.x + g.n_x);
+            T.xy.off_gy = (int)blob.size();
+            blob.insert(blob.end(), g.y, g.y + g.n_y);
+            AppendLut(blob, T.xy.lutx, g.x, g.n_x);
+            AppendLut(blob, T.xy.luty, g.y, g.n_y);
+            T.xy.cells = a->cells[which].p;
             T.use_lr = a->use_long_range;
             if (a->use_long_range) {
                 rc = LoadLongRange(ctx, a, which, *lrs[which], blob, T.lr);
@@ -727,10 +774,10 @@ int pimc_action_create_ilkka(pimc_ctx *ctx, int32_t sa, int32_t sb, const pimc_i
         }
         {
             CheckTable1D(t->v_r, "v_r table");
-            std::vector<double> blob = BuildBlob1D(t->v_r.r, t->v_r.f, t->v_r.n);
             PairTable &T = a->table[WHICH_V];
             std::memset(&T, 0, sizeof(T));
-            Fill1D(T.a, t->v_r.n, 0, t->v_r.r);
+            std::vector<double> blob;
+            AppendPP1(blob, T.a, t->v_r.r, t->v_r.f, t->v_r.n);
             T.use_lr = a->use_long_range;
             if (a->use_long_range) {
                 rc = LoadLongRange(ctx, a, WHICH_V, t->v_long, blob, T.lr);
@@ -765,10 +812,10 @@ int pimc_action_create_bare(pimc_ctx *ctx, int32_t sa, int32_t sb, const pimc_ba
         // U, dU/dbeta and V all evaluate CalcV (bare...:146-150,175-182); one blob each keeps
         // the kernels' addressing uniform
         for (int which = 0; which < 3; ++which) {
-            std::vector<double> blob = BuildBlob1D(t->v_r.r, t->v_r.f, t->v_r.n);
             PairTable &T = a->table[which];
             std::memset(&T, 0, sizeof(T));
-            Fill1D(T.a, t->v_r.n, 0, t->v_r.r);
+            std::vector<double> blob;
+            AppendPP1(blob, T.a, t->v_r.r, t->v_r.f, t->v_r.n);
             T.use_lr = a->use_long_range;
             T.is_coulomb = t->is_coulomb != 0;
             T.u_scale = ctx->tau;  // level 0: (1 >> 0) * tau
@@ -833,17 +880,19 @@ int pimc_action_create_david(pimc_ctx *ctx, int32_t sa, int32_t sb, const pimc_d
             std::vector<double> blob = BuildBlobMulti(grid.data(), n, values);
             PairTable &T = a->table[which];
             std::memset(&T, 0, sizeof(T));
-            Fill1D(T.a, n, 0, grid.data());
-            T.a.n_splines = n_val + 1;
-            T.a.code = code;
-            T.a.ainv = ainv;
-            T.a.startinv = startinv;
-            T.a.r_min = (code == GRIDCODE_LOG) ? t->r_start : grid[0];
-            T.a.r_max = (code == GRIDCODE_LOG) ? t->r_end : grid[n - 1];
+            Fill1D(T.dav, n, 0, grid.data());
+            T.dav.n_splines = n_val + 1;
+            T.dav.code = code;
+            T.dav.ainv = ainv;
+            T.dav.startinv = startinv;
+            T.dav.r_min = (code == GRIDCODE_LOG) ? t->r_start : grid[0];
+            T.dav.r_max = (code == GRIDCODE_LOG) ? t->r_end : grid[n - 1];
             T.n_order = t->n_order;
             T.use_lr = 0;  // David subtracts nothing in r space
             rc = UploadBlob(ctx, a->blob[which], blob);
             if (rc != PIMC_OK) return rc;
+            T.dav_blob = a->blob[which].p;
+            a->stageable[which] = false;
         }
     } catch (const std::exception &e) {
         return Fail(PIMC_ERR_TABLE, e.what());

@@ -27,7 +27,7 @@ struct Box {
     double L, iL;
 };
 
-/// Offsets (in doubles) of one 1-D / multi spline inside a table blob.
+/// Offsets (in doubles) of one B-spline-form 1-D / multi spline inside a table blob.
 struct Sp1Desc {
     int n;            // grid points
     int off_t, off_w, off_c;
@@ -36,19 +36,37 @@ struct Sp1Desc {
     double r_min, r_max;  // grid start / end (SetLimits)
     double ainv, startinv;  // log grid reverse map
 };
-struct Sp2Desc {
-    int nx, ny;
-    int off_tx, off_wx, off_ty, off_wy, off_c;
+/// Interval-search accelerator: key = (bits(x) >> shift) - key0 clamped to [0, n_keys);
+/// lut[key] (uint16, `off` counted in uint16 units from the blob start) is a lower bound of
+/// the interval index, finished by a forward scan on the grid.
+struct LutDesc {
+    int off, n_keys, shift;
+    long long key0;
+};
+/// pp-form 1-D spline inside the (stageable) blob: grid g[n], coefficients pp[n][4].
+struct PP1Desc {
+    int n, off_g, off_pp;
+    LutDesc lut;
+    double r_min, r_max;
+};
+/// pp-form 2-D spline: grids and LUTs inside the blob, the cell polynomials
+/// cells[ix][iy][4][4] in global memory (read through the read-only path).
+struct PP2Desc {
+    int nx, ny, off_gx, off_gy;
+    LutDesc lutx, luty;
+    const double *cells;
 };
 /// Everything a pair kernel needs to evaluate one of U / dU/dbeta / V of one action.
 struct PairTable {
     int use_lr;
     int is_coulomb;
     int n_order;
-    double u_scale;  // Bare CalcU: (1 >> level) * tau
-    Sp2Desc xy;      // Ilkka u_xy / du_xy
-    Sp1Desc a;       // Ilkka/Bare v_r, David multi-spline
-    Sp1Desc lr;      // the long-range r-space spline subtracted from the short-range part
+    double u_scale;      // Bare CalcU: (1 >> level) * tau
+    PP2Desc xy;          // Ilkka u_xy / du_xy
+    PP1Desc a;           // Ilkka / Bare v_r
+    PP1Desc lr;          // long-range r-space spline subtracted from the short-range part
+    Sp1Desc dav;         // David multi-spline (B-spline form) ...
+    const double *dav_blob;  // ... in global memory
 };
 
 // nearbyint() in the default rounding mode is round-half-even == rint()
@@ -131,14 +149,6 @@ __device__ __forceinline__ int Sp1Interval(const double *__restrict__ blob, cons
     return GridInterval(blob + s.off_t + 2, s.n, x);
 }
 
-__device__ __forceinline__ double Sp1Eval(const double *__restrict__ blob, const Sp1Desc &s, double x) {
-    double b[4];
-    const int i = Sp1Interval(blob, s, x);
-    BasisOnInterval(blob + s.off_t, blob + s.off_w, i, x, b);
-    const double *c = blob + s.off_c + i;
-    return (c[0] * b[0] + c[1] * b[1] + c[2] * b[2] + c[3] * b[3]);
-}
-
 /// One value of a multi-spline (coefficient rows of n_splines doubles).
 __device__ __forceinline__ double MultiTap(const double *__restrict__ blob, const Sp1Desc &s, int i, const double b[4], int v) {
     const double *c = blob + s.off_c + (size_t)i * s.n_splines + v;
@@ -146,35 +156,53 @@ __device__ __forceinline__ double MultiTap(const double *__restrict__ blob, cons
     return c[0] * b[0] + c[st] * b[1] + c[2 * st] * b[2] + c[3 * st] * b[3];
 }
 
-__device__ __forceinline__ double Sp2Eval(const double *__restrict__ blob, const Sp2Desc &s, double x, double y) {
-    double a[4], b[4];
-    const int ix = GridInterval(blob + s.off_tx + 2, s.nx, x);
-    const int iy = GridInterval(blob + s.off_ty + 2, s.ny, y);
-    BasisOnInterval(blob + s.off_tx, blob + s.off_wx, ix, x, a);
-    BasisOnInterval(blob + s.off_ty, blob + s.off_wy, iy, y, b);
-    const int sy = s.ny + 2;
-    const double *c = blob + s.off_c + (size_t)ix * sy + iy;
-    double v = 0.;
+/// Interval of x on grid g[0..n): LUT lower bound + forward scan.  Equals GridInterval.
+__device__ __forceinline__ int LutInterval(const double *__restrict__ blob, const LutDesc &L, const double *__restrict__ g, int n,
+                                           double x) {
+    long long key = (__double_as_longlong(x) >> L.shift) - L.key0;
+    key = key < 0 ? 0 : (key > (long long)(L.n_keys - 1) ? (long long)(L.n_keys - 1) : key);
+    int i = reinterpret_cast<const unsigned short *>(blob)[L.off + (int)key];
+    while (i + 1 < n && g[i + 1] <= x) ++i;
+    return i;
+}
+
+__device__ __forceinline__ double PP1Eval(const double *__restrict__ blob, const PP1Desc &d, double x) {
+    const double *g = blob + d.off_g;
+    const int i = LutInterval(blob, d.lut, g, d.n, x);
+    const double t = x - g[i];
+    const double2 *c = reinterpret_cast<const double2 *>(blob + d.off_pp) + 2 * i;
+    const double2 c01 = c[0], c23 = c[1];
+    return fma(fma(fma(c23.y, t, c23.x), t, c01.y), t, c01.x);
+}
+
+__device__ __forceinline__ double PP2Eval(const double *__restrict__ blob, const PP2Desc &d, double x, double y) {
+    const double *gx = blob + d.off_gx, *gy = blob + d.off_gy;
+    const int ix = LutInterval(blob, d.lutx, gx, d.nx, x);
+    const int iy = LutInterval(blob, d.luty, gy, d.ny, y);
+    const double tx = x - gx[ix], ty = y - gy[iy];
+    const double2 *c = reinterpret_cast<const double2 *>(d.cells) + ((size_t)ix * d.ny + iy) * 8;
+    double row[4];
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-        const double *cm = c + m * sy;
-        v += a[m] * (cm[0] * b[0] + cm[1] * b[1] + cm[2] * b[2] + cm[3] * b[3]);
+        const double2 c01 = __ldg(c + 2 * m), c23 = __ldg(c + 2 * m + 1);
+        row[m] = fma(fma(fma(c23.y, ty, c23.x), ty, c01.y), ty, c01.x);
     }
-    return v;
+    return fma(fma(fma(row[3], tx, row[2]), tx, row[1]), tx, row[0]);
 }
 
 /// CalcV of the three action families.
 template <int ATYPE>
 __device__ __forceinline__ double PairV(const double *__restrict__ blob, const PairTable &T, double r, double r_p) {
     if (ATYPE == ATYPE_DAVID) {
-        SetLimits(T.a.r_min, T.a.r_max, r, r_p);
+        const double *db = T.dav_blob;
+        SetLimits(T.dav.r_min, T.dav.r_max, r, r_p);
         double b[4];
-        int i = Sp1Interval(blob, T.a, r);
-        BasisOnInterval(blob + T.a.off_t, blob + T.a.off_w, i, r, b);
-        double v0 = MultiTap(blob, T.a, i, b, 0);
-        i = Sp1Interval(blob, T.a, r_p);
-        BasisOnInterval(blob + T.a.off_t, blob + T.a.off_w, i, r_p, b);
-        double v1 = MultiTap(blob, T.a, i, b, 0);
+        int i = Sp1Interval(db, T.dav, r);
+        BasisOnInterval(db + T.dav.off_t, db + T.dav.off_w, i, r, b);
+        double v0 = MultiTap(db, T.dav, i, b, 0);
+        i = Sp1Interval(db, T.dav, r_p);
+        BasisOnInterval(db + T.dav.off_t, db + T.dav.off_w, i, r_p, b);
+        double v1 = MultiTap(db, T.dav, i, b, 0);
         return 0.5 * (v0 + v1);
     }
     SetLimits(T.a.r_min, T.a.r_max, r, r_p);
@@ -182,13 +210,13 @@ __device__ __forceinline__ double PairV(const double *__restrict__ blob, const P
     if (ATYPE == ATYPE_BARE && T.is_coulomb) {
         v += (0.5 / r) + (0.5 / r_p);
     } else {
-        v += 0.5 * Sp1Eval(blob, T.a, r);
-        v += 0.5 * Sp1Eval(blob, T.a, r_p);
+        v += 0.5 * PP1Eval(blob, T.a, r);
+        v += 0.5 * PP1Eval(blob, T.a, r_p);
     }
     if (T.use_lr) {
         SetLimits(T.lr.r_min, T.lr.r_max, r, r_p);
-        v -= 0.5 * Sp1Eval(blob, T.lr, r);
-        v -= 0.5 * Sp1Eval(blob, T.lr, r_p);
+        v -= 0.5 * PP1Eval(blob, T.lr, r);
+        v -= 0.5 * PP1Eval(blob, T.lr, r_p);
     }
     return v;
 }
@@ -205,39 +233,40 @@ __device__ __forceinline__ double PairEval(const double *__restrict__ blob, cons
         const double q = 0.5 * (r + r_p);
         const double x = q + 0.5 * s;
         const double y = q - 0.5 * s;
-        double u = Sp2Eval(blob, T.xy, x, y);
+        double u = PP2Eval(blob, T.xy, x, y);
         if (T.use_lr) {
             SetLimits(T.lr.r_min, T.lr.r_max, r, r_p);
-            u -= 0.5 * Sp1Eval(blob, T.lr, r);
-            u -= 0.5 * Sp1Eval(blob, T.lr, r_p);
+            u -= 0.5 * PP1Eval(blob, T.lr, r);
+            u -= 0.5 * PP1Eval(blob, T.lr, r_p);
         }
         return u;
     }
     // David: endpoint term plus the off-diagonal polynomial in z^2 and s^2
+    const double *db = T.dav_blob;
     const double q = 0.5 * (r + r_p);
     const double z = r - r_p;
-    const double r_max = T.a.r_max;
-    SetLimits(T.a.r_min, T.a.r_max, r, r_p);
+    const double r_max = T.dav.r_max;
+    SetLimits(T.dav.r_min, T.dav.r_max, r, r_p);
     double b[4];
-    int i = Sp1Interval(blob, T.a, r);
-    BasisOnInterval(blob + T.a.off_t, blob + T.a.off_w, i, r, b);
-    double e1 = MultiTap(blob, T.a, i, b, 1);
-    double e0 = (WHICH == WHICH_DU) ? MultiTap(blob, T.a, i, b, 0) : 0.;
-    i = Sp1Interval(blob, T.a, r_p);
-    BasisOnInterval(blob + T.a.off_t, blob + T.a.off_w, i, r_p, b);
-    double f1 = MultiTap(blob, T.a, i, b, 1);
-    double f0 = (WHICH == WHICH_DU) ? MultiTap(blob, T.a, i, b, 0) : 0.;
+    int i = Sp1Interval(db, T.dav, r);
+    BasisOnInterval(db + T.dav.off_t, db + T.dav.off_w, i, r, b);
+    double e1 = MultiTap(db, T.dav, i, b, 1);
+    double e0 = (WHICH == WHICH_DU) ? MultiTap(db, T.dav, i, b, 0) : 0.;
+    i = Sp1Interval(db, T.dav, r_p);
+    BasisOnInterval(db + T.dav.off_t, db + T.dav.off_w, i, r_p, b);
+    double f1 = MultiTap(db, T.dav, i, b, 1);
+    double f0 = (WHICH == WHICH_DU) ? MultiTap(db, T.dav, i, b, 0) : 0.;
     double u = 0.5 * (e1 + f1);
     if (WHICH == WHICH_DU) u += 0.5 * (e0 + f0);
     if (s > 0.0 && q < r_max) {
-        i = Sp1Interval(blob, T.a, q);
-        BasisOnInterval(blob + T.a.off_t, blob + T.a.off_w, i, q, b);
+        i = Sp1Interval(db, T.dav, q);
+        BasisOnInterval(db + T.dav.off_t, db + T.dav.off_w, i, q, b);
         const double z_2 = z * z, s_2 = s * s, i_s_2 = 1. / s_2;
         double s_2_k = s_2;
         for (int k = 1; k <= T.n_order; k++) {
             double z_2_j = 1, current_s = s_2_k;
             for (int j = 0; j <= k; j++) {
-                const double cof = MultiTap(blob, T.a, i, b, k * (k + 1) / 2 + (j + 1));
+                const double cof = MultiTap(db, T.dav, i, b, k * (k + 1) / 2 + (j + 1));
                 u += cof * z_2_j * current_s;
                 z_2_j *= z_2;
                 current_s *= i_s_2;

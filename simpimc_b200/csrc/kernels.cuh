@@ -23,7 +23,8 @@
 
 namespace pimc {
 
-constexpr int kPairThreads = 256;
+constexpr int kPairThreads = 512;
+constexpr int kPairCtasPerSm = 2;  // 2 x 512 threads x 64 registers fill the register file
 
 /// One species' committed positions plus its pending proposal.
 struct SpeciesView {
@@ -90,7 +91,7 @@ struct PairFullArgs {
 /// Persistent CTAs: stage the table once, then walk (clone, slice) items.  Per item the two
 /// slices' positions are staged in shared memory (SoA) and the threads stride over pairs.
 template <int ATYPE, int WHICH>
-__global__ void __launch_bounds__(kPairThreads) pair_full_kernel(const PairFullArgs a) {
+__global__ void __launch_bounds__(kPairThreads, kPairCtasPerSm) pair_full_kernel(const PairFullArgs a) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double red[kPairThreads / 32];
     const int tid = threadIdx.x;

@@ -18,8 +18,11 @@
 #ifndef SIMPIMC_B200_SPLINE_BUILD_H_
 #define SIMPIMC_B200_SPLINE_BUILD_H_
 
+#include <algorithm>
 #include <cmath>
 #include <cstddef>
+#include <cstdint>
+#include <cstring>
 #include <stdexcept>
 #include <vector>
 
@@ -160,6 +163,158 @@ inline std::vector<double> BuildBlobMulti(const double *grid, int n, const std::
     double *c = blob.data() + (n + 5) + 3 * (n + 2);
     for (int s = 0; s < ns; ++s) SolveNatural(kb, values[s].data(), 1, c + s, ns);
     return blob;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Piecewise-polynomial (pp) form of the same splines.
+//
+// On grid interval i the spline is ONE cubic in tau = x - g[i]; expanding the four live
+// B-spline basis functions of that interval into monomials of tau (in long double, from the
+// same knots t and inverse spans w the B-spline form uses) and contracting with the
+// coefficients gives it directly.  The device then needs one interval lookup, 4 (1-D) or 16
+// (2-D cell) coefficients and a Horner evaluation instead of the Cox-de Boor recursion: the
+// function evaluated is identical up to rounding (~1e-16 relative to the local magnitude).
+// Interval n-1 (the phantom interval right of the grid end, which einspline selects for
+// x >= grid end) is included, so x == end and x > end reproduce the B-spline form as well.
+
+struct CubicLD {
+    long double c[4] = {0, 0, 0, 0};
+    CubicLD TimesLinear(long double a, long double b) const {  // this * (a + b tau), degree stays <= 3
+        CubicLD r;
+        for (int k = 0; k < 4; ++k) {
+            r.c[k] += c[k] * a;
+            if (k + 1 < 4) r.c[k + 1] += c[k] * b;
+        }
+        return r;
+    }
+    CubicLD Plus(const CubicLD &o) const {
+        CubicLD r;
+        for (int k = 0; k < 4; ++k) r.c[k] = c[k] + o.c[k];
+        return r;
+    }
+    CubicLD Scaled(long double f) const {
+        CubicLD r;
+        for (int k = 0; k < 4; ++k) r.c[k] = c[k] * f;
+        return r;
+    }
+};
+
+/// The four cubic basis polynomials alive on interval i, in tau = x - t[i+2].
+inline void BasisPolynomials(const KnotBasis &kb, int i, CubicLD b[4]) {
+    const int i2 = i + 2;
+    const std::vector<double> &t = kb.t, &w = kb.w;
+    const long double t0 = t[i2];
+    const long double dm2 = t0 - (long double)t[i2 - 2], dm1 = t0 - (long double)t[i2 - 1];
+    const long double d1 = (long double)t[i2 + 1] - t0, d2 = (long double)t[i2 + 2] - t0, d3 = (long double)t[i2 + 3] - t0;
+    const long double w00 = w[3 * i + 2], w11 = w[3 * (i + 1) + 1], w12 = w[3 * (i + 1) + 2];
+    const long double w20 = w[3 * (i + 2) + 0], w21 = w[3 * (i + 2) + 1], w22 = w[3 * (i + 2) + 2];
+    CubicLD one;
+    one.c[0] = 1;
+    // (t1 - x) = d1 - tau, (x - t0) = tau, (x - tm1) = tau + dm1, (t2 - x) = d2 - tau, ...
+    const CubicLD l0 = one.TimesLinear(d1, -1).Scaled(w20);
+    const CubicLD l1 = one.TimesLinear(0, 1).Scaled(w20);
+    const CubicLD q0 = l0.TimesLinear(d1, -1).Scaled(w11);
+    const CubicLD q1 = l0.TimesLinear(dm1, 1).Scaled(w11).Plus(l1.TimesLinear(d2, -1).Scaled(w21));
+    const CubicLD q2 = l1.TimesLinear(0, 1).Scaled(w21);
+    b[0] = q0.TimesLinear(d1, -1).Scaled(w00);
+    b[1] = q0.TimesLinear(dm2, 1).Scaled(w00).Plus(q1.TimesLinear(d2, -1).Scaled(w12));
+    b[2] = q1.TimesLinear(dm1, 1).Scaled(w12).Plus(q2.TimesLinear(d3, -1).Scaled(w22));
+    b[3] = q2.TimesLinear(0, 1).Scaled(w22);
+}
+
+/// pp[i][4] for i = 0..n-1 from the n+3 B-spline coefficients c.
+inline std::vector<double> PPFrom1D(const KnotBasis &kb, const double *c, std::size_t cstride = 1) {
+    const int n = kb.n;
+    std::vector<double> pp((std::size_t)n * 4, 0.0);
+    for (int i = 0; i < n; ++i) {
+        CubicLD b[4];
+        BasisPolynomials(kb, i, b);
+        for (int m = 0; m < 4; ++m) {
+            long double acc = 0;
+            for (int k = 0; k < 4; ++k) acc += (long double)c[(std::size_t)(i + k) * cstride] * b[k].c[m];
+            pp[(std::size_t)i * 4 + m] = (double)acc;
+        }
+    }
+    return pp;
+}
+
+/// cells[ix][iy][m][n] (power m of tau_x, power n of tau_y) from the 2-D coefficient array
+/// C[(nx+3)][(ny+2)] (row stride sy = ny + 2, plus guard).
+inline std::vector<double> PPFrom2D(const KnotBasis &bx, const KnotBasis &by, const double *C) {
+    const int nx = bx.n, ny = by.n, sy = ny + 2;
+    std::vector<double> cells((std::size_t)nx * ny * 16, 0.0);
+    std::vector<CubicLD> polyy((std::size_t)ny * 4);
+    for (int iy = 0; iy < ny; ++iy) BasisPolynomials(by, iy, &polyy[(std::size_t)iy * 4]);
+    for (int ix = 0; ix < nx; ++ix) {
+        CubicLD a[4];
+        BasisPolynomials(bx, ix, a);
+        for (int iy = 0; iy < ny; ++iy) {
+            const CubicLD *b = &polyy[(std::size_t)iy * 4];
+            long double P[4][4] = {{0}};
+            for (int k = 0; k < 4; ++k)
+                for (int l = 0; l < 4; ++l) {
+                    // the tap past the last coefficient column has zero weight in the B-spline
+                    // form (x == grid end); it must not pick up the next row's first entry
+                    const long double cc = (iy + l < sy) ? (long double)C[(std::size_t)(ix + k) * sy + iy + l] : 0.0L;
+                    if (cc == 0) continue;
+                    for (int m = 0; m < 4; ++m)
+                        for (int nn = 0; nn < 4; ++nn) P[m][nn] += cc * a[k].c[m] * b[l].c[nn];
+                }
+            double *dst = &cells[((std::size_t)ix * ny + iy) * 16];
+            for (int m = 0; m < 4; ++m)
+                for (int nn = 0; nn < 4; ++nn) dst[m * 4 + nn] = (double)P[m][nn];
+        }
+    }
+    return cells;
+}
+
+/// Interval-search accelerator: buckets of the IEEE-754 bit pattern of x (exponent plus the
+/// top `mant_bits` mantissa bits), lut[key] = a lower bound of the interval index for every x
+/// in the bucket; the device finishes with a forward scan on the grid.
+struct BitLut {
+    int shift = 0;        // key = (bits(x) >> shift) - key0, clamped to [0, n_keys)
+    long long key0 = 0;
+    std::vector<uint16_t> lut;
+};
+
+inline long long DoubleBits(double x) {
+    long long b;
+    static_assert(sizeof(b) == sizeof(x), "size");
+    std::memcpy(&b, &x, sizeof(b));
+    return b;
+}
+
+inline BitLut BuildBitLut(const double *g, int n) {
+    if (n > 65535) throw std::invalid_argument("grid too long for the 16-bit interval LUT");
+    BitLut best;
+    // everything below x_lo falls into bucket 0, which must map to interval 0
+    const double x_lo = g[0] > 0 ? g[0] : g[1] * (1.0 / 64.0);
+    const double x_hi = g[n - 1];
+    if (!(x_lo > 0) || !(x_hi > x_lo)) throw std::invalid_argument("interval LUT needs a positive ascending grid");
+    for (int mant_bits = 3; mant_bits <= 14; ++mant_bits) {
+        BitLut L;
+        L.shift = 52 - mant_bits;
+        L.key0 = DoubleBits(x_lo) >> L.shift;
+        const long long n_keys = (DoubleBits(x_hi) >> L.shift) - L.key0 + 1;
+        if (n_keys > 16384 && !best.lut.empty()) break;
+        if (n_keys > 65536) break;
+        L.lut.assign((std::size_t)n_keys, 0);
+        int max_per_bucket = 0, i = 0;
+        for (long long key = 1; key < n_keys; ++key) {
+            const long long bits = (key + L.key0) << L.shift;
+            double edge;
+            std::memcpy(&edge, &bits, sizeof(edge));
+            int before = i;
+            while (i + 1 < n && g[i + 1] <= edge) ++i;
+            L.lut[(std::size_t)key] = (uint16_t)i;
+            max_per_bucket = std::max(max_per_bucket, i - before);
+        }
+        best = L;
+        if (max_per_bucket <= 1) break;
+    }
+    if (best.lut.empty()) throw std::runtime_error("could not build the interval LUT");
+    return best;
 }
 
 }  // namespace pimc
