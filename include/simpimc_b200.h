@@ -134,7 +134,8 @@ int pimc_kspace_get(pimc_ctx *ctx, int32_t *k_index, double *k_mag);
  * exactly n_bead beads when unsharded. */
 int pimc_positions_upload(pimc_ctx *ctx, int32_t species, int32_t clone_lo, int32_t clone_hi, const double *R);
 int pimc_positions_download(pimc_ctx *ctx, int32_t species, int32_t mode, int32_t clone_lo, int32_t clone_hi, double *R);
-/* Same, from / to DEVICE memory in the library's own layout R[clone][bead][dim][particle]. */
+/* Same, from / to DEVICE memory in the library's own layout R[clone][particle][dim][slice], each
+ * slice row padded to a multiple of 4 doubles. */
 int pimc_positions_set_device(pimc_ctx *ctx, int32_t species, const double *d_R);
 double *pimc_positions_device_ptr(pimc_ctx *ctx, int32_t species);
 int pimc_rhok_rebuild(pimc_ctx *ctx, int32_t species); /* Species::InitRhoK */

@@ -58,9 +58,9 @@ struct DevBuf {
 };
 
 struct SpeciesState {
-    int N = 0, Npad = 0;
+    int N = 0;
     double lambda = 0.;
-    DevBuf<double> R;        // committed positions [C][Mstore][3][Npad]
+    DevBuf<double> R;        // committed positions [C][N][3][Ms]
     DevBuf<double2> rho;     // committed rho_k [C][Mloc][n_k]
     // pending proposal
     DevBuf<double> P;        // [C][n_prop][3]
@@ -79,7 +79,7 @@ struct SpeciesState {
 struct pimc_ctx {
     int n_d = 3, pbc = 1, M = 0, C = 0, device = 0;
     double L = 0, iL = 0, vol = 1, beta = 0, tau = 0;
-    int slice_lo = 0, slice_hi = 0, Mloc = 0, Mstore = 0, sharded = 0;
+    int slice_lo = 0, slice_hi = 0, Mloc = 0, Mstore = 0, Ms = 0, sharded = 0;
     cudaStream_t stream = nullptr;
     int n_sm = 148;
     size_t smem_optin = 0;
@@ -113,6 +113,7 @@ struct pimc_ctx {
         v.M = M;
         v.Mloc = Mloc;
         v.Mstore = Mstore;
+        v.Ms = Ms;
         v.slice_lo = slice_lo;
         v.sharded = sharded;
         v.box.L = L;
@@ -124,7 +125,6 @@ struct pimc_ctx {
         SpeciesView v;
         v.R = st.R.p;
         v.N = st.N;
-        v.Npad = st.Npad;
         v.P = st.P.p;
         v.P_particle = st.P_particle.p;
         v.P_first = st.P_first.p;
@@ -423,7 +423,7 @@ int LaunchPairFullT(pimc_ctx *ctx, const PairFullArgs &args, size_t smem, int gr
     return PIMC_OK;
 }
 
-int LaunchPairFull(pimc_action *a, int which, bool independent_images) {
+int LaunchPairFull(pimc_action *a, int which, bool independent_images, int *n_per_clone) {
     pimc_ctx *ctx = a->ctx;
     PairFullArgs args;
     args.pv = ctx->View();
@@ -434,18 +434,18 @@ int LaunchPairFull(pimc_action *a, int which, bool independent_images) {
     args.blob = a->blob[which].p;
     args.blob_doubles = (int)a->blob[which].n;
     args.independent_images = independent_images ? 1 : 0;
-    const size_t items = (size_t)ctx->C * ctx->Mloc;
+    args.n_chunks = (ctx->Mloc + kChunk - 1) / kChunk;
+    args.n_pgroups = (args.A.N + kPairWarps - 1) / kPairWarps;
+    *n_per_clone = args.n_chunks * args.n_pgroups;
+    const size_t items = (size_t)ctx->C * *n_per_clone;
     if (ctx->partial.n < items) PIMC_CUDA(ctx->partial.Alloc(items));
     args.partial = ctx->partial.p;
-    const size_t pos_bytes = sizeof(double) * 2 * 3 * (args.A.Npad + (args.same ? 0 : args.B.Npad));
+    const size_t pos_bytes = sizeof(double) * kQTile * 3 * kRow;
     const size_t blob_bytes = a->stageable[which] ? sizeof(double) * a->blob[which].n : 0;
     args.stage = (a->stageable[which] && pos_bytes + blob_bytes + 1024 <= ctx->smem_optin) ? 1 : 0;
     const size_t smem = pos_bytes + (args.stage ? blob_bytes : 0);
-    if (smem > ctx->smem_optin) return Fail(PIMC_ERR_UNSUPPORTED, "species too large for the shared-memory position tile");
-    // persistent CTAs: as many as fit per SM given the staged table, never more than the items
-    int per_sm = std::max(1, (int)(ctx->smem_optin / std::max<size_t>(smem + 1024, 1)));
-    per_sm = std::min(per_sm, kPairCtasPerSm);
-    const int grid = (int)std::min<size_t>(items, (size_t)ctx->n_sm * per_sm);
+    // persistent CTAs: one per SM (1024 threads), never more than the items
+    const int grid = (int)std::min<size_t>(items, (size_t)ctx->n_sm);
 #define PIMC_DISPATCH(AT)                                                                    \
     switch (which) {                                                                         \
         case WHICH_U: return LaunchPairFullT<AT, WHICH_U>(ctx, args, smem, grid);            \
@@ -503,7 +503,8 @@ int FullEvaluation(pimc_action *a, int which, double *d_out) {
         if (ctx->species[a->sa]->N != 1)
             return Fail(PIMC_ERR_UNSUPPORTED, "constant action with lambda = 0 and more than one particle");
     }
-    int rc = LaunchPairFull(a, which, which == WHICH_V);
+    int n_per_clone = 0;
+    int rc = LaunchPairFull(a, which, which == WHICH_V, &n_per_clone);
     if (rc != PIMC_OK) return rc;
     if (a->use_long_range) {
         if (ctx->n_k() > 0) {
@@ -518,7 +519,7 @@ int FullEvaluation(pimc_action *a, int which, double *d_out) {
     // constants belong to the rank that owns slice 0 when the path is sharded
     const bool add_const = (which != WHICH_U) && (!ctx->sharded || ctx->slice_lo == 0);
     const double k0 = a->k0[which], r0 = a->r0[which];
-    return Finalize(ctx, ctx->Mloc, a->use_long_range, k0, r0, add_const, d_out);
+    return Finalize(ctx, n_per_clone, a->use_long_range, k0, r0, add_const, d_out);
 }
 
 int ToHost(pimc_ctx *ctx, const double *d_src, double *host, size_t n) {
@@ -575,6 +576,7 @@ int pimc_ctx_create(const pimc_config *cfg, pimc_ctx **out) {
     ctx->Mloc = hi - lo;
     ctx->sharded = (ctx->Mloc != ctx->M);
     ctx->Mstore = ctx->Mloc + (ctx->sharded ? 1 : 0);
+    ctx->Ms = (ctx->Mstore + 3) & ~3;
     PIMC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     cudaDeviceProp prop;
     PIMC_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
@@ -584,9 +586,8 @@ int pimc_ctx_create(const pimc_config *cfg, pimc_ctx **out) {
         std::unique_ptr<SpeciesState> st(new SpeciesState);
         st->N = cfg->n_part[s];
         if (st->N < 1) return Fail(PIMC_ERR_INVALID, "species without particles");
-        st->Npad = (st->N + 3) & ~3;
         st->lambda = cfg->lambda[s];
-        const size_t n = (size_t)ctx->C * ctx->Mstore * 3 * st->Npad;
+        const size_t n = (size_t)ctx->C * st->N * 3 * ctx->Ms;
         PIMC_CUDA(st->R.Alloc(n));
         PIMC_CUDA(cudaMemsetAsync(st->R.p, 0, n * sizeof(double), ctx->stream));
         PIMC_CUDA(st->P_particle.Alloc(ctx->C));
@@ -651,8 +652,8 @@ int pimc_positions_upload(pimc_ctx *ctx, int32_t s, int32_t clone_lo, int32_t cl
     const size_t n_host = (size_t)nc * st.N * ctx->Mstore * 3;
     if (ctx->stage.n < n_host) PIMC_CUDA(ctx->stage.Alloc(n_host));
     PIMC_CUDA(cudaMemcpyAsync(ctx->stage.p, R, n_host * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    double *dst = st.R.p + (size_t)clone_lo * ctx->Mstore * 3 * st.Npad;
-    positions_in_kernel<<<ctx->n_sm * 4, 256, 0, ctx->stream>>>(ctx->stage.p, nc, st.N, st.Npad, ctx->Mstore, dst);
+    double *dst = st.R.p + (size_t)clone_lo * st.N * 3 * ctx->Ms;
+    positions_in_kernel<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(ctx->stage.p, nc, st.N, ctx->Mstore, ctx->Ms, dst);
     ctx->launches++;
     PIMC_CUDA(cudaGetLastError());
     st.n_prop = 0;
@@ -672,8 +673,8 @@ int pimc_positions_download(pimc_ctx *ctx, int32_t s, int32_t mode, int32_t clon
     const int nc = clone_hi - clone_lo;
     const size_t n_host = (size_t)nc * st.N * ctx->Mstore * 3;
     if (ctx->stage.n < n_host) PIMC_CUDA(ctx->stage.Alloc(n_host));
-    const double *src = st.R.p + (size_t)clone_lo * ctx->Mstore * 3 * st.Npad;
-    positions_out_kernel<<<ctx->n_sm * 4, 256, 0, ctx->stream>>>(src, nc, st.N, st.Npad, ctx->Mstore, ctx->stage.p);
+    const double *src = st.R.p + (size_t)clone_lo * st.N * 3 * ctx->Ms;
+    positions_out_kernel<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(src, nc, st.N, ctx->Mstore, ctx->Ms, ctx->stage.p);
     ctx->launches++;
     PIMC_CUDA(cudaGetLastError());
     return ToHost(ctx, ctx->stage.p, R, n_host);
@@ -1164,7 +1165,7 @@ int pimc_beads_download(pimc_ctx *ctx, int32_t s, const int32_t *particle, const
     if ((rc = EnsureI32(ctx, ctx->i32_b, b_first, ctx->C)) != PIMC_OK) return rc;
     const size_t n = (size_t)ctx->C * n_beads * 3;
     if (ctx->stage.n < n) PIMC_CUDA(ctx->stage.Alloc(n));
-    gather_beads_kernel<<<ctx->C, 64, 0, ctx->stream>>>(ctx->View(), st.R.p, st.Npad, ctx->i32_a.p, ctx->i32_b.p, n_beads, ctx->stage.p);
+    gather_beads_kernel<<<ctx->C, 64, 0, ctx->stream>>>(ctx->View(), st.R.p, st.N, ctx->i32_a.p, ctx->i32_b.p, n_beads, ctx->stage.p);
     ctx->launches++;
     PIMC_CUDA(cudaGetLastError());
     return ToHost(ctx, ctx->stage.p, out, n);
@@ -1178,7 +1179,7 @@ int pimc_commit(pimc_ctx *ctx, const int32_t *accept) {
     for (auto &sp : ctx->species) {
         SpeciesState &st = *sp;
         if (st.n_prop > 0) {
-            commit_positions_kernel<<<ctx->C, 64, 0, ctx->stream>>>(ctx->View(), st.Npad, st.P.p, st.P_particle.p, st.P_first.p, st.n_prop,
+            commit_positions_kernel<<<ctx->C, 64, 0, ctx->stream>>>(ctx->View(), st.N, st.P.p, st.P_particle.p, st.P_first.p, st.n_prop,
                                                                   ctx->i32_d.p, st.R.p);
             ctx->launches++;
             PIMC_CUDA(cudaGetLastError());

@@ -12,7 +12,10 @@
 //   K6 sofk_kernel          StructureFactor::Accumulate (structure_factor_class.h:15-32)
 //
 // Device layouts (private to the library):
-//   positions  R[clone][slice][dim][particle (padded to a multiple of 4)]       double
+//   positions  R[clone][particle][dim][slice (row padded to a multiple of 4)]   double
+//              -- the imaginary-time index is fastest: a warp's 32 lanes walk 32 consecutive
+//              slices of one particle pair, loads coalesce, and because paths are continuous
+//              in imaginary time neighbouring lanes land in the same spline cells
 //   rho_k      rho[clone][slice][k]                                              double2 (re, im)
 //   proposal   P[clone][bead of the proposal][dim]                               double
 //   drho       D[clone][window slice][k]                                         double2
@@ -23,13 +26,10 @@
 
 namespace pimc {
 
-constexpr int kPairThreads = 512;
-constexpr int kPairCtasPerSm = 2;  // 2 x 512 threads x 64 registers fill the register file
-
 /// One species' committed positions plus its pending proposal.
 struct SpeciesView {
     const double *R;     // committed positions
-    int N, Npad;
+    int N;
     // proposal overlay (NEW mode)
     const double *P;          // [C][n_prop][3]
     const int32_t *P_particle;  // [C]
@@ -42,6 +42,7 @@ struct PathView {
     int M;        // slices of the whole path
     int Mloc;     // slices owned by this context
     int Mstore;   // slices stored (Mloc, +1 halo when sharded)
+    int Ms;       // row length of the position arrays (Mstore rounded up to a multiple of 4)
     int slice_lo; // first owned slice
     int sharded;
     Box box;
@@ -52,8 +53,8 @@ __device__ __forceinline__ int NextSlice(const PathView &pv, int b) {
     return pv.sharded ? b + 1 : (b + 1 == pv.M ? 0 : b + 1);
 }
 
-__device__ __forceinline__ size_t PosIndex(const PathView &pv, int Npad, int c, int b, int d, int p) {
-    return (((size_t)c * pv.Mstore + b) * 3 + d) * Npad + p;
+__device__ __forceinline__ size_t PosIndex(const PathView &pv, int N, int c, int p, int d, int b) {
+    return (((size_t)c * N + p) * 3 + d) * pv.Ms + b;
 }
 
 /// Position of (species view, clone c, particle p, GLOBAL slice bg) in OLD or NEW mode.
@@ -72,94 +73,117 @@ __device__ __forceinline__ void LoadPos(const PathView &pv, const SpeciesView &s
     }
     const int b = bl - pv.slice_lo;
 #pragma unroll
-    for (int d = 0; d < 3; ++d) out[d] = sv.R[PosIndex(pv, sv.Npad, c, b, d, p)];
+    for (int d = 0; d < 3; ++d) out[d] = sv.R[PosIndex(pv, sv.N, c, p, d, b)];
 }
 
 // ------------------------------------------------------------------------------------ K1
+constexpr int kPairThreads = 1024;  // one persistent CTA per SM, 32 warps
+constexpr int kPairWarps = kPairThreads / 32;
+constexpr int kChunk = 32;          // links per work item = lanes of a warp
+constexpr int kQTile = 64;          // partner particles staged per shared-memory tile
+constexpr int kRow = 34;            // 33 slices of a chunk (+1 pad) per staged row
+
 struct PairFullArgs {
     PathView pv;
     SpeciesView A, B;
     int same;               // species_a == species_b
     PairTable T;
-    const double *blob;     // table blob in global memory
+    const double *blob;     // stageable table blob in global memory
     int blob_doubles;
     int stage;              // 1: copy the blob into shared memory first
     int independent_images; // Potential(): r and r' minimum-imaged independently (App. A-6)
-    double *partial;        // [C][Mloc]
+    int n_chunks;           // ceil(Mloc / 32)
+    int n_pgroups;          // ceil(Na / 32)
+    double *partial;        // [C][n_chunks][n_pgroups]
 };
 
-/// Persistent CTAs: stage the table once, then walk (clone, slice) items.  Per item the two
-/// slices' positions are staged in shared memory (SoA) and the threads stride over pairs.
+/// Storage index of local slice s (s == Mloc is the slice after the shard: wraps to 0 on an
+/// unsharded path, is the halo otherwise); -1 beyond.
+__device__ __forceinline__ int StoreIndex(const PathView &pv, int s) {
+    if (s < pv.Mloc) return s;
+    if (s == pv.Mloc) return pv.sharded ? s : 0;
+    return -1;
+}
+
+/// Persistent CTAs, one per SM.  A work item is (clone, 32-link chunk, group of 32 particles
+/// of species a): warp w owns particle p of the group, its 32 lanes own the chunk's links, and
+/// the warp walks over the partner particles q, staged tile by tile in shared memory.  The
+/// tables' 1-D parts, grids and LUTs are staged once per CTA.
 template <int ATYPE, int WHICH>
-__global__ void __launch_bounds__(kPairThreads, kPairCtasPerSm) pair_full_kernel(const PairFullArgs a) {
+__global__ void __launch_bounds__(kPairThreads, 1) pair_full_kernel(const PairFullArgs a) {
     extern __shared__ __align__(16) double smem[];
-    __shared__ double red[kPairThreads / 32];
-    const int tid = threadIdx.x;
-    double *pos = smem;  // [2 slices][2 species][3][Npad]
-    const int NpA = a.A.Npad, NpB = a.B.Npad;
-    const int pos_doubles = 2 * 3 * (NpA + (a.same ? 0 : NpB));
+    __shared__ double red[kPairWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *qpos = smem;  // [kQTile][3][kRow]
     const double *tab = a.blob;
     if (a.stage) {
-        double *stab = smem + pos_doubles;
+        double *stab = smem + kQTile * 3 * kRow;
         for (int i = tid; i < a.blob_doubles; i += kPairThreads) stab[i] = a.blob[i];
         tab = stab;
     }
     __syncthreads();
     const PathView &pv = a.pv;
-    const int n_items = pv.C * pv.Mloc;
     const int Na = a.A.N, Nb = a.B.N;
-    // same species: particle p pairs with (p+d) mod N for d = 1..N/2 (the last offset only for
-    // the first half when N is even) -- every unordered pair exactly once
     const int half = Na / 2;
-    const int n_work = a.same ? ((Na & 1) ? Na * half : Na * (half - 1) + half) : Na * Nb;
-    double *xa0 = pos, *xa1 = pos + 3 * NpA;
-    double *xb0 = a.same ? xa0 : pos + 6 * NpA, *xb1 = a.same ? xa1 : pos + 6 * NpA + 3 * NpB;
+    const bool even = (Na & 1) == 0;
+    const int per_clone = a.n_chunks * a.n_pgroups;
+    const int n_items = pv.C * per_clone;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int c = item / pv.Mloc, b = item - c * pv.Mloc;
-        const int b1 = NextSlice(pv, b);
-        __syncthreads();
-        {
-            const double *s0 = a.A.R + PosIndex(pv, NpA, c, b, 0, 0);
-            const double *s1 = a.A.R + PosIndex(pv, NpA, c, b1, 0, 0);
-            for (int i = tid; i < 3 * NpA; i += kPairThreads) {
-                xa0[i] = s0[i];
-                xa1[i] = s1[i];
-            }
-            if (!a.same) {
-                const double *u0 = a.B.R + PosIndex(pv, NpB, c, b, 0, 0);
-                const double *u1 = a.B.R + PosIndex(pv, NpB, c, b1, 0, 0);
-                for (int i = tid; i < 3 * NpB; i += kPairThreads) {
-                    xb0[i] = u0[i];
-                    xb1[i] = u1[i];
-                }
+        const int c = item / per_clone;
+        const int rem = item - c * per_clone;
+        const int chunk = rem / a.n_pgroups, pg = rem - chunk * a.n_pgroups;
+        const int s0 = chunk * kChunk;            // first local slice of the chunk
+        const int p = pg * kPairWarps + warp;
+        const bool warp_on = p < Na;
+        const bool lane_on = s0 + lane < pv.Mloc;
+        double p0[3] = {0., 0., 0.}, p1[3] = {0., 0., 0.};
+        if (warp_on && lane_on) {
+            const int i0 = s0 + lane, i1 = StoreIndex(pv, s0 + lane + 1);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                p0[d] = a.A.R[PosIndex(pv, Na, c, p, d, i0)];
+                p1[d] = a.A.R[PosIndex(pv, Na, c, p, d, i1)];
             }
         }
-        __syncthreads();
         double acc = 0.;
-        for (int w = tid; w < n_work; w += kPairThreads) {
-            int p, q;
-            if (a.same) {
-                const int d = w / Na;
-                p = w - d * Na;
-                q = p + d + 1;
-                if (q >= Na) q -= Na;
-            } else {
-                p = w / Nb;
-                q = w - p * Nb;
+        for (int q0 = 0; q0 < Nb; q0 += kQTile) {
+            const int nq = min(kQTile, Nb - q0);
+            __syncthreads();  // the previous tile has been consumed
+            for (int row = warp; row < nq * 3; row += kPairWarps) {
+                const int qq = row / 3, d = row - qq * 3;
+                const double *src = a.B.R + PosIndex(pv, Nb, c, q0 + qq, d, 0);
+                const int i0 = StoreIndex(pv, s0 + lane);
+                qpos[row * kRow + lane] = i0 >= 0 ? src[i0] : 0.;
+                if (lane == 0) {
+                    const int i1 = StoreIndex(pv, s0 + kChunk);
+                    qpos[row * kRow + kChunk] = i1 >= 0 ? src[i1] : 0.;
+                }
             }
-            const double pa0[3] = {xa0[p], xa0[NpA + p], xa0[2 * NpA + p]};
-            const double pa1[3] = {xa1[p], xa1[NpA + p], xa1[2 * NpA + p]};
-            const double pb0[3] = {xb0[q], xb0[NpB + q], xb0[2 * NpB + q]};
-            const double pb1[3] = {xb1[q], xb1[NpB + q], xb1[2 * NpB + q]};
-            double r, rp, s;
-            if (a.independent_images) {
-                r = Mag3(MinImage(pa0[0] - pb0[0], pv.box), MinImage(pa0[1] - pb0[1], pv.box), MinImage(pa0[2] - pb0[2], pv.box));
-                rp = Mag3(MinImage(pa1[0] - pb1[0], pv.box), MinImage(pa1[1] - pb1[1], pv.box), MinImage(pa1[2] - pb1[2], pv.box));
-                s = 0.;
-            } else {
-                DrDrpDrrp(pa0, pb0, pa1, pb1, pv.box, r, rp, s);
+            __syncthreads();
+            if (!warp_on) continue;
+            for (int qq = 0; qq < nq; ++qq) {
+                const int q = q0 + qq;
+                if (a.same) {
+                    // every unordered pair once: q = p + dd (mod N) for dd = 1..N/2, the last
+                    // offset only from the lower half when N is even (warp-uniform test)
+                    int dd = q - p;
+                    if (dd < 0) dd += Na;
+                    if (dd == 0 || dd > half || (even && dd == half && p >= half)) continue;
+                }
+                if (!lane_on) continue;
+                const double *row = qpos + (qq * 3) * kRow + lane;
+                const double b0[3] = {row[0], row[kRow], row[2 * kRow]};
+                const double b1[3] = {row[1], row[kRow + 1], row[2 * kRow + 1]};
+                double r, rp, s;
+                if (a.independent_images) {
+                    r = Mag3(MinImage(p0[0] - b0[0], pv.box), MinImage(p0[1] - b0[1], pv.box), MinImage(p0[2] - b0[2], pv.box));
+                    rp = Mag3(MinImage(p1[0] - b1[0], pv.box), MinImage(p1[1] - b1[1], pv.box), MinImage(p1[2] - b1[2], pv.box));
+                    s = 0.;
+                } else {
+                    DrDrpDrrp(p0, b0, p1, b1, pv.box, r, rp, s);
+                }
+                acc += PairEval<ATYPE, WHICH>(tab, a.T, r, rp, s);
             }
-            acc += PairEval<ATYPE, WHICH>(tab, a.T, r, rp, s);
         }
         const double tot = BlockSum<kPairThreads>(acc, red);
         if (tid == 0) a.partial[item] = tot;
@@ -231,7 +255,7 @@ __global__ void __launch_bounds__(256) rhok_build_kernel(PathView pv, SpeciesVie
                 __syncthreads();
                 for (int t = tid; t < np * 3; t += blockDim.x) {
                     const int pp = t / 3, d = t - pp * 3;
-                    PhaseTable(sv.R[PosIndex(pv, sv.Npad, c, b, d, p0 + pp)], ks.kbox, ks.max_index, ctab + (size_t)(pp * 3 + d) * tl);
+                    PhaseTable(sv.R[PosIndex(pv, sv.N, c, p0 + pp, d, b)], ks.kbox, ks.max_index, ctab + (size_t)(pp * 3 + d) * tl);
                 }
                 __syncthreads();
                 if (k < ks.n_k) {
@@ -440,7 +464,7 @@ __global__ void __launch_bounds__(256) gofr_kernel(const GofrArgs a) {
             double dr[3];
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
-                const double x = __dsub_rn(a.A.R[PosIndex(pv, a.A.Npad, c, b, d, p)], a.B.R[PosIndex(pv, a.B.Npad, c, b, d, q)]);
+                const double x = __dsub_rn(a.A.R[PosIndex(pv, a.A.N, c, p, d, b)], a.B.R[PosIndex(pv, a.B.N, c, q, d, b)]);
                 dr[d] = __dsub_rn(x, __dmul_rn(rint(__dmul_rn(x, pv.box.iL)), pv.box.L));
             }
             const double dist = Mag3Exact(dr[0], dr[1], dr[2]);
@@ -477,34 +501,30 @@ __global__ void sofk_kernel(PathView pv, int n_k, const double2 *__restrict__ rh
 }
 
 // ------------------------------------------------------------------------- data movement
-/// host order R[clone][particle][bead][dim] -> device order R[clone][slice][dim][particle].
-__global__ void positions_in_kernel(const double *__restrict__ src, int n_clones, int N, int Npad, int Mstore, double *__restrict__ dst) {
-    const size_t total = (size_t)n_clones * Mstore * 3 * Npad;
+/// host order R[clone][particle][bead][dim] -> device order R[clone][particle][dim][slice].
+__global__ void positions_in_kernel(const double *__restrict__ src, int n_clones, int N, int Mstore, int Ms, double *__restrict__ dst) {
+    const size_t total = (size_t)n_clones * N * 3 * Ms;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int p = i % Npad;
-        size_t r = i / Npad;
+        const int b = i % Ms;
+        size_t r = i / Ms;
         const int d = r % 3;
-        r /= 3;
-        const int b = r % Mstore;
-        const size_t c = r / Mstore;
-        dst[i] = p < N ? src[((c * N + p) * Mstore + b) * 3 + d] : 0.0;
+        const size_t cp = r / 3;  // clone * N + particle
+        dst[i] = b < Mstore ? src[(cp * Mstore + b) * 3 + d] : 0.0;
     }
 }
-__global__ void positions_out_kernel(const double *__restrict__ src, int n_clones, int N, int Npad, int Mstore, double *__restrict__ dst) {
+__global__ void positions_out_kernel(const double *__restrict__ src, int n_clones, int N, int Mstore, int Ms, double *__restrict__ dst) {
     const size_t total = (size_t)n_clones * N * Mstore * 3;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int d = i % 3;
         size_t r = i / 3;
         const int b = r % Mstore;
-        r /= Mstore;
-        const int p = r % N;
-        const size_t c = r / N;
-        dst[i] = src[((c * Mstore + b) * 3 + d) * Npad + p];
+        const size_t cp = r / Mstore;
+        dst[i] = src[(cp * 3 + d) * Ms + b];
     }
 }
 
 /// out[c][j][d] = committed position of particle[c] at slice b_first[c] + j (mod M).
-__global__ void gather_beads_kernel(PathView pv, const double *__restrict__ R, int Npad, const int32_t *__restrict__ particle,
+__global__ void gather_beads_kernel(PathView pv, const double *__restrict__ R, int N, const int32_t *__restrict__ particle,
                                     const int32_t *__restrict__ b_first, int n_beads, double *__restrict__ out) {
     const int c = blockIdx.x;
     const int p = particle[c];
@@ -512,13 +532,13 @@ __global__ void gather_beads_kernel(PathView pv, const double *__restrict__ R, i
         const int j = t / 3, d = t - j * 3;
         int bg = b_first[c] + j;
         while (bg >= pv.M) bg -= pv.M;
-        out[((size_t)c * n_beads + j) * 3 + d] = R[PosIndex(pv, Npad, c, bg - pv.slice_lo, d, p)];
+        out[((size_t)c * n_beads + j) * 3 + d] = R[PosIndex(pv, N, c, p, d, bg - pv.slice_lo)];
     }
 }
 
 /// Move::Accept for the clones whose accept flag is set: committed positions take the
 /// proposal, committed rho_k takes rho_k + drho on the window slices.
-__global__ void commit_positions_kernel(PathView pv, int Npad, const double *__restrict__ P, const int32_t *__restrict__ P_particle,
+__global__ void commit_positions_kernel(PathView pv, int N, const double *__restrict__ P, const int32_t *__restrict__ P_particle,
                                         const int32_t *__restrict__ P_first, int n_prop, const int32_t *__restrict__ accept,
                                         double *__restrict__ R) {
     const int c = blockIdx.x;
@@ -530,7 +550,7 @@ __global__ void commit_positions_kernel(PathView pv, int Npad, const double *__r
         if (bg >= pv.M) bg -= pv.M;
         const int b = bg - pv.slice_lo;
         if (b < 0 || b >= pv.Mstore) continue;
-        R[PosIndex(pv, Npad, c, b, d, p)] = P[((size_t)c * n_prop + j) * 3 + d];
+        R[PosIndex(pv, N, c, p, d, b)] = P[((size_t)c * n_prop + j) * 3 + d];
     }
 }
 __global__ void commit_rhok_kernel(PathView pv, int n_k, const double2 *__restrict__ drho, const int32_t *__restrict__ b0, int n_window,
