@@ -181,6 +181,15 @@ int pimc_action_reject(pimc_action *act); /* PairAction::Reject, :414-419 */
 int pimc_action_calc_pair(pimc_action *act, int32_t which, int32_t n, const double *r, const double *r_p,
                           const double *s, int32_t level, double *out);
 
+/* Same through the fast Ilkka evaluation the whole-path kernel uses (shared-memory table layout,
+ * uniform interval tables; csrc/pair_fast.cuh).  which: 0 = U, 1 = dU/dbeta. */
+int pimc_action_calc_pair_fast(pimc_action *act, int32_t which, int32_t n, const double *r, const double *r_p,
+                               const double *s, double *out);
+/* Device square root of the fast path on caller data (tests: <= 1 ulp from sqrt). */
+int pimc_debug_fast_sqrt(pimc_ctx *ctx, int32_t n, const double *x, double *out);
+/* enable != 0: evaluate with the general kernels even where the fast path applies (tests). */
+int pimc_ctx_force_general(pimc_ctx *ctx, int32_t enable);
+
 /* ---- moves' contract ------------------------------------------------------------------ */
 /* NEW-mode Bead::SetR for one particle per clone (bisect_class.h:89-94,
  * displace_particle_class.h:40-50): beads b_first[c] .. b_first[c]+n_beads-1 (mod n_bead)

@@ -16,6 +16,7 @@
 
 #include "../../include/simpimc_b200.h"
 #include "kernels.cuh"
+#include "pair_fast.cuh"
 #include "spline_build.h"
 
 using namespace pimc;
@@ -98,6 +99,7 @@ struct pimc_ctx {
     DevBuf<double> est;
     std::vector<pimc_action *> actions;
     int64_t launches = 0;
+    bool force_general = false;  // tests: evaluate with the general kernels even where the fast path applies
     // optional per-kernel device timing (CUDA events on the context's stream)
     bool timing = false;
     struct KTimer {
@@ -158,6 +160,10 @@ struct pimc_action {
     DevBuf<double> wk[3];
     double k0[3] = {0, 0, 0}, r0[3] = {0, 0, 0};
     double ulong_scale = 1.;  // Bare CalcULong: level_tau
+    // Ilkka U / dU fast path (pair_fast.cuh): every table in one shared-memory block
+    DevBuf<unsigned char> fast_tab[2];
+    FastTable fast[2];
+    bool fast_ok[2] = {false, false};
 };
 
 namespace {
@@ -409,6 +415,114 @@ int LoadLongRange(pimc_ctx *ctx, pimc_action *a, int which, const pimc_long_rang
     return PIMC_OK;
 }
 
+
+// ------------------------------------------------------------------- fast Ilkka tables
+struct ByteBlob {
+    std::vector<unsigned char> b;
+    int Reserve(size_t bytes) {  // 16-byte aligned region, returns its offset
+        const size_t off = (b.size() + 15) & ~(size_t)15;
+        b.resize(off + bytes, 0);
+        return (int)off;
+    }
+    template <class T>
+    T *At(int off) { return reinterpret_cast<T *>(b.data() + off); }
+};
+
+int AppendULut(ByteBlob &blob, ULutDesc &d, const ULut &L) {
+    d.off_lut = blob.Reserve(L.lut.size() * sizeof(uint16_t));
+    std::memcpy(blob.At<uint16_t>(d.off_lut), L.lut.data(), L.lut.size() * sizeof(uint16_t));
+    d.key_max = (int)L.lut.size() - 1;
+    d.inv_h = L.inv_h;
+    return d.off_lut;
+}
+
+int AppendKnotPairs(ByteBlob &blob, const double *g, int n) {
+    const int off = blob.Reserve((size_t)n * 16);
+    double *p = blob.At<double>(off);
+    for (int i = 0; i < n; ++i) {
+        p[2 * i] = g[i];
+        p[2 * i + 1] = (i + 1 < n) ? g[i + 1] : HUGE_VAL;
+    }
+    return off;
+}
+
+/// Packs the shared-memory block of the fast pair kernel for one of u_xy / du_xy (+ its
+/// long-range r-space spline).  `cells` = PPFrom2D output [nx][ny][16].  Leaves ok = false when
+/// a grid does not admit the uniform interval table or nothing fits.
+int BuildFastIlkka(pimc_ctx *ctx, pimc_action *a, int which, const pimc_table_2d &g, const std::vector<double> &cells,
+                   const pimc_long_range *lr) {
+    a->fast_ok[which] = false;
+    FastTable &T = a->fast[which];
+    std::memset(&T, 0, sizeof(T));
+    ULut lx, ly, ll;
+    const int kMaxKeys = 16384;
+    if (!BuildULut(g.x, g.n_x, kMaxKeys, lx) || !BuildULut(g.y, g.n_y, kMaxKeys, ly)) return PIMC_OK;
+    ByteBlob blob;
+    T.xy.off_gxpair = AppendKnotPairs(blob, g.x, g.n_x);
+    T.xy.off_gypair = AppendKnotPairs(blob, g.y, g.n_y);
+    AppendULut(blob, T.xy.lutx, lx);
+    AppendULut(blob, T.xy.luty, ly);
+    T.xy.ny = g.n_y;
+    T.xy.cells_global = a->cells[which].p;
+    T.use_lr = a->use_long_range ? 1 : 0;
+    if (a->use_long_range) {
+        const pimc_table_1d &f = lr->f_r;
+        if (!BuildULut(f.r, f.n, kMaxKeys, ll)) return PIMC_OK;
+        KnotBasis kb;
+        kb.Build(f.r, f.n);
+        std::vector<double> coefs(f.n + 3, 0.0);
+        SolveNatural(kb, f.f, 1, coefs.data(), 1);
+        const std::vector<double> pp = PPFrom1D(kb, coefs.data());
+        T.lr.off_gpair = AppendKnotPairs(blob, f.r, f.n);
+        T.lr.off_c01 = blob.Reserve((size_t)f.n * 16);
+        T.lr.off_c23 = blob.Reserve((size_t)f.n * 16);
+        for (int i = 0; i < f.n; ++i) {
+            blob.At<double>(T.lr.off_c01)[2 * i] = pp[4 * (size_t)i];
+            blob.At<double>(T.lr.off_c01)[2 * i + 1] = pp[4 * (size_t)i + 1];
+            blob.At<double>(T.lr.off_c23)[2 * i] = pp[4 * (size_t)i + 2];
+            blob.At<double>(T.lr.off_c23)[2 * i + 1] = pp[4 * (size_t)i + 3];
+        }
+        AppendULut(blob, T.lr.lut, ll);
+        T.lr.r_min = f.r[0];
+        T.lr.r_max = f.r[f.n - 1];
+    }
+    // block of cells the box can reach: x = q + s/2 <= 1.5 * (sqrt(3) L / 2)
+    int n_need = std::min(g.n_x, g.n_y);
+    if (ctx->pbc) {
+        const double x_max = 1.5 * 0.5 * std::sqrt(3.0) * ctx->L;
+        const int ix = (int)(std::upper_bound(g.x, g.x + g.n_x, x_max) - g.x);
+        const int iy = (int)(std::upper_bound(g.y, g.y + g.n_y, x_max) - g.y);
+        n_need = std::min(n_need, std::max(ix, iy) + 1);
+    }
+    const size_t fixed = sizeof(double) * kFastRows * 3 * kFastRow + ((blob.b.size() + 15) & ~(size_t)15) + 2048;
+    int n_stage = 0, row_stride = 0;
+    for (int n = n_need; n >= 1; --n) {
+        const int pad_slots = (4 - (n % 8) + 8) % 8;  // row stride = 4 (mod 8) sixteen-byte slots: rows fall into disjoint banks
+        const int rs = n * kCellRecord + pad_slots * 16;
+        if (fixed + (size_t)n * rs <= ctx->smem_optin) {
+            n_stage = n;
+            row_stride = rs;
+            break;
+        }
+    }
+    T.xy.n_stage = n_stage;
+    T.xy.row_stride = row_stride;
+    if (n_stage > 0) {
+        T.xy.off_cells = blob.Reserve((size_t)n_stage * row_stride);
+        for (int ix = 0; ix < n_stage; ++ix)
+            for (int iy = 0; iy < n_stage; ++iy)
+                std::memcpy(blob.b.data() + T.xy.off_cells + (size_t)ix * row_stride + (size_t)iy * kCellRecord,
+                            &cells[((size_t)ix * g.n_y + iy) * 16], 128);
+    }
+    blob.Reserve(0);
+    blob.b.resize((blob.b.size() + 15) & ~(size_t)15, 0);
+    T.n_bytes = (int)blob.b.size();
+    PIMC_CUDA(a->fast_tab[which].Alloc(blob.b.size()));
+    PIMC_CUDA(cudaMemcpy(a->fast_tab[which].p, blob.b.data(), blob.b.size(), cudaMemcpyHostToDevice));
+    a->fast_ok[which] = true;
+    return PIMC_OK;
+}
+
 // ------------------------------------------------------------------------------ launchers
 template <int ATYPE, int WHICH>
 int LaunchPairFullT(pimc_ctx *ctx, const PairFullArgs &args, size_t smem, int grid) {
@@ -423,8 +537,37 @@ int LaunchPairFullT(pimc_ctx *ctx, const PairFullArgs &args, size_t smem, int gr
     return PIMC_OK;
 }
 
+int LaunchPairFast(pimc_action *a, int which, int *n_per_clone) {
+    pimc_ctx *ctx = a->ctx;
+    PairFastArgs args;
+    args.pv = ctx->View();
+    args.A = ctx->SView(a->sa, false);
+    args.B = ctx->SView(a->sb, false);
+    args.same = a->sa == a->sb;
+    args.T = a->fast[which];
+    args.tables = a->fast_tab[which].p;
+    args.n_chunks = (ctx->Mloc + kChunk - 1) / kChunk;
+    args.n_pgroups = (args.A.N + kFastWarps - 1) / kFastWarps;
+    *n_per_clone = args.n_chunks * args.n_pgroups;
+    const size_t items = (size_t)ctx->C * *n_per_clone;
+    if (ctx->partial.n < items) PIMC_CUDA(ctx->partial.Alloc(items));
+    args.partial = ctx->partial.p;
+    const size_t smem = sizeof(double) * kFastRows * 3 * kFastRow + (size_t)args.T.n_bytes;
+    PIMC_CUDA(cudaFuncSetAttribute(pair_full_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<size_t>(items, (size_t)ctx->n_sm);
+    {
+        ScopedKernelTimer t(ctx, PIMC_KERNEL_PAIR_FULL);
+        pair_full_fast_kernel<<<grid, kFastThreads, smem, ctx->stream>>>(args);
+    }
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    return PIMC_OK;
+}
+
 int LaunchPairFull(pimc_action *a, int which, bool independent_images, int *n_per_clone) {
     pimc_ctx *ctx = a->ctx;
+    if (a->atype == ATYPE_ILKKA && which != WHICH_V && !independent_images && a->fast_ok[which] && !ctx->force_general)
+        return LaunchPairFast(a, which, n_per_clone);
     PairFullArgs args;
     args.pv = ctx->View();
     args.A = ctx->SView(a->sa, false);
@@ -771,6 +914,8 @@ int pimc_action_create_ilkka(pimc_ctx *ctx, int32_t sa, int32_t sb, const pimc_i
                 if (rc != PIMC_OK) return rc;
             }
             rc = UploadBlob(ctx, a->blob[which], blob);
+            if (rc != PIMC_OK) return rc;
+            rc = BuildFastIlkka(ctx, a, which, g, cells, a->use_long_range ? lrs[which] : nullptr);
             if (rc != PIMC_OK) return rc;
         }
         {
@@ -1276,6 +1421,44 @@ int pimc_est_sofk(pimc_ctx *ctx, int32_t sa, int32_t sb, double k_cut, const dou
     ctx->launches++;
     PIMC_CUDA(cudaGetLastError());
     return ToHost(ctx, ctx->est.p, sk, n);
+}
+
+int pimc_action_calc_pair_fast(pimc_action *act, int32_t which, int32_t n, const double *r, const double *r_p, const double *s,
+                               double *out) {
+    if (!act || !r || !r_p || !s || !out || n < 0 || which < 0 || which > 1) return Fail(PIMC_ERR_INVALID, "bad argument");
+    if (act->atype != ATYPE_ILKKA || !act->fast_ok[which]) return Fail(PIMC_ERR_UNSUPPORTED, "action has no fast-path tables");
+    if (n == 0) return PIMC_OK;
+    pimc_ctx *ctx = act->ctx;
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    DevBuf<double> buf;
+    PIMC_CUDA(buf.Alloc((size_t)4 * n));
+    PIMC_CUDA(cudaMemcpyAsync(buf.p, r, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    PIMC_CUDA(cudaMemcpyAsync(buf.p + n, r_p, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    PIMC_CUDA(cudaMemcpyAsync(buf.p + 2 * (size_t)n, s, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    calc_pair_fast_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(act->fast_tab[which].p, act->fast[which], n, buf.p, buf.p + n,
+                                                                    buf.p + 2 * (size_t)n, buf.p + 3 * (size_t)n);
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    return ToHost(ctx, buf.p + 3 * (size_t)n, out, n);
+}
+
+int pimc_debug_fast_sqrt(pimc_ctx *ctx, int32_t n, const double *x, double *out) {
+    if (!ctx || !x || !out || n < 0) return Fail(PIMC_ERR_INVALID, "bad argument");
+    if (n == 0) return PIMC_OK;
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    DevBuf<double> buf;
+    PIMC_CUDA(buf.Alloc((size_t)2 * n));
+    PIMC_CUDA(cudaMemcpyAsync(buf.p, x, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    fast_sqrt_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, buf.p, buf.p + n);
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    return ToHost(ctx, buf.p + n, out, n);
+}
+
+int pimc_ctx_force_general(pimc_ctx *ctx, int32_t enable) {
+    if (!ctx) return Fail(PIMC_ERR_INVALID, "null context");
+    ctx->force_general = enable != 0;
+    return PIMC_OK;
 }
 
 int pimc_ctx_set_timing(pimc_ctx *ctx, int32_t enable) {

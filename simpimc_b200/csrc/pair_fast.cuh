@@ -1,0 +1,270 @@
+// Fast path of the Ilkka pair action (U and dU/dbeta): every table the evaluation touches
+// lives in shared memory and every access is sized for the LSU, which -- not the FP64 pipe --
+// bounds the first versions of this kernel (profiles/r1_k1_v3_*.txt: 145 LSU wavefronts per
+// warp-evaluation, 80 % of the pipe).  Measured on B200 (tools/microbench.cu,
+// profiles/r1_microbench.txt): an LDS.128 costs 2 wavefronts when <= 16 distinct
+// bank-disjoint addresses are read, 4 for 32; an L1-hit LDG.128 costs 4 even fully broadcast
+// and one per distinct line beyond; records 32 B apart conflict 2-way.  Hence:
+//
+//   * interval search = ONE fused multiply-add: key = low word of fma(x, 1/h, 2^52+2^51)
+//     (round-to-nearest integer of x/h), a uint16 table gives the interval of the bucket's
+//     lower edge, and because h is smaller than the smallest knot spacing at most one knot
+//     lies inside a bucket: one compare against g[i+1] finishes the search.  The result is the
+//     einspline interval index exactly (integer work: bit-exact, tested against the oracle);
+//   * knots are stored as pairs (g[i], g[i+1]) so that one LDS.128 feeds the compare and
+//     tau = x - g[i];
+//   * 1-D pp coefficients are split into two 16-byte-stride arrays (c0,c1) and (c2,c3);
+//   * the bicubic cell polynomials of the block of cells the box can reach are staged with a
+//     144-byte record stride (neighbouring cells fall into disjoint banks); cells outside the
+//     block are read from global memory;
+//   * sqrt = MUFU.RSQ64H seed + one coupled Newton step + one Markstein correction (7 FP64
+//     instructions, no slow-path branch).
+//
+// Reference semantics: Path::DrDrpDrrp (src/data_structures/path_class.h:137-150),
+// IlkkaPairAction::CalcU / CalcdUdBeta (src/actions/pair_action/ilkka_pair_action_class.h:77-101,
+// 125-149), PairAction::SetLimits (pair_action_class.h:32-42).
+#ifndef SIMPIMC_B200_PAIR_FAST_CUH_
+#define SIMPIMC_B200_PAIR_FAST_CUH_
+
+#include "device_math.cuh"
+
+namespace pimc {
+
+constexpr double kRoundMagic = 6755399441055744.0;  // 2^52 + 2^51: low word of (x + magic) = rint(x)
+constexpr int kCellRecord = 144;                    // bytes per staged bicubic cell (128 + 16 pad)
+
+/// Uniform-bucket interval table; offsets are bytes from the start of the staged table block.
+struct ULutDesc {
+    int off_lut;    // uint16 [n_keys]
+    int key_max;    // n_keys - 1
+    double inv_h;   // 1 / bucket width
+};
+struct FastPP1 {
+    ULutDesc lut;
+    int off_gpair;  // double2 [n]: (g[i], g[i+1]); g[n] = +inf
+    int off_c01;    // double2 [n]: (c0, c1) of interval i
+    int off_c23;    // double2 [n]: (c2, c3)
+    double r_min, r_max;
+};
+struct FastPP2 {
+    ULutDesc lutx, luty;
+    int off_gxpair, off_gypair;
+    int off_cells;      // staged block: record (ix, iy) at off_cells + ix * row_stride + iy * kCellRecord
+    int n_stage;        // cells with ix < n_stage and iy < n_stage are staged
+    int row_stride;     // bytes
+    int ny;             // cells per row of the global array
+    const double *cells_global;  // [nx][ny][16]
+};
+struct FastTable {
+    FastPP2 xy;
+    FastPP1 lr;
+    int use_lr;
+    int n_bytes;  // size of the staged block
+};
+
+__device__ __forceinline__ void ULookup(const unsigned char *__restrict__ tb, const ULutDesc &L, int off_gpair, double x, int &i,
+                                        double &t) {
+    const double kd = fma(x, L.inv_h, kRoundMagic);
+    int key = __double2loint(kd);
+    key = min(max(key, 0), L.key_max);
+    const int i0 = *reinterpret_cast<const unsigned short *>(tb + L.off_lut + 2 * key);
+    const double2 g = *reinterpret_cast<const double2 *>(tb + off_gpair + 16 * i0);
+    const bool up = x >= g.y;
+    i = up ? i0 + 1 : i0;
+    t = x - (up ? g.y : g.x);
+}
+
+__device__ __forceinline__ double FastPP1Eval(const unsigned char *__restrict__ tb, const FastPP1 &d, double x) {
+    int i;
+    double t;
+    ULookup(tb, d.lut, d.off_gpair, x, i, t);
+    const double2 c01 = *reinterpret_cast<const double2 *>(tb + d.off_c01 + 16 * i);
+    const double2 c23 = *reinterpret_cast<const double2 *>(tb + d.off_c23 + 16 * i);
+    return fma(fma(fma(c23.y, t, c23.x), t, c01.y), t, c01.x);
+}
+
+__device__ __forceinline__ double FastPP2Eval(const unsigned char *__restrict__ tb, const FastPP2 &d, double x, double y) {
+    int ix, iy;
+    double tx, ty;
+    ULookup(tb, d.lutx, d.off_gxpair, x, ix, tx);
+    ULookup(tb, d.luty, d.off_gypair, y, iy, ty);
+    double2 c[8];
+    if (ix < d.n_stage && iy < d.n_stage) {
+        const double2 *p = reinterpret_cast<const double2 *>(tb + d.off_cells + ix * d.row_stride + iy * kCellRecord);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) c[k] = p[k];
+    } else {
+        const double2 *p = reinterpret_cast<const double2 *>(d.cells_global) + ((size_t)ix * d.ny + iy) * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) c[k] = __ldg(p + k);
+    }
+    double row[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) row[m] = fma(fma(fma(c[2 * m + 1].y, ty, c[2 * m + 1].x), ty, c[2 * m].y), ty, c[2 * m].x);
+    return fma(fma(fma(row[3], tx, row[2]), tx, row[1]), tx, row[0]);
+}
+
+/// sqrt(x) for x >= 0 to within 1 ulp (0 for x = 0): reciprocal-square-root seed (relative
+/// error 2^-26), one coupled Newton step for sqrt and 1/(2 sqrt), one Markstein correction.
+__device__ __forceinline__ double FastSqrt(double x) {
+    const int hi = max(__double2hiint(x), 0x00100000);  // keeps the seed finite at x = 0
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(__hiloint2double(hi, __double2loint(x))));
+    double g = x * y;
+    double h = 0.5 * y;
+    const double r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    const double d = fma(-g, g, x);
+    return fma(d, h, g);
+}
+
+/// The three magnitudes of Path::DrDrpDrrp.  The reference's last step, PutInBox(r - r'), is
+/// skipped: r' has just been moved to the image nearest to r, so every component of r - r'
+/// already lies in [-L/2, L/2] and the rounding it would apply is zero (it could differ only
+/// when a component sits within one rounding error of exactly L/2, where the reference's own
+/// result depends on its compiler's contraction choices).
+__device__ __forceinline__ void DrDrpDrrpFast(const double a0[3], const double b0[3], const double a1[3], const double b1[3],
+                                              const Box &bx, double &r_mag, double &rp_mag, double &rrp_mag) {
+    double r[3], rp[3], s[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        r[d] = b0[d] - a0[d];
+        rp[d] = b1[d] - a1[d];
+        r[d] = fma(-rint(r[d] * bx.iL), bx.L, r[d]);
+        rp[d] = fma(rint((r[d] - rp[d]) * bx.iL), bx.L, rp[d]);
+        s[d] = r[d] - rp[d];
+    }
+    r_mag = FastSqrt(fma(r[1], r[1], fma(r[2], r[2], r[0] * r[0])));
+    rp_mag = FastSqrt(fma(rp[1], rp[1], fma(rp[2], rp[2], rp[0] * rp[0])));
+    rrp_mag = FastSqrt(fma(s[1], s[1], fma(s[2], s[2], s[0] * s[0])));
+}
+
+__device__ __forceinline__ double Clamp(double x, double lo, double hi) { return x > hi ? hi : (x < lo ? lo : x); }
+
+/// IlkkaPairAction::CalcU / CalcdUdBeta (the table decides which).
+__device__ __forceinline__ double FastIlkkaEval(const unsigned char *__restrict__ tb, const FastTable &T, double r, double r_p, double s) {
+    const double q = 0.5 * (r + r_p);
+    const double x = fma(0.5, s, q);
+    const double y = fma(-0.5, s, q);
+    double u = FastPP2Eval(tb, T.xy, x, y);
+    if (T.use_lr) {
+        u = fma(-0.5, FastPP1Eval(tb, T.lr, Clamp(r, T.lr.r_min, T.lr.r_max)), u);
+        u = fma(-0.5, FastPP1Eval(tb, T.lr, Clamp(r_p, T.lr.r_min, T.lr.r_max)), u);
+    }
+    return u;
+}
+
+// ------------------------------------------------------------------------------ K1 (fast)
+constexpr int kFastThreads = 1024;
+constexpr int kFastWarps = kFastThreads / 32;
+constexpr int kFastQ = 32;                         // partner offsets handled per staged window
+constexpr int kFastRows = kFastQ + kFastWarps - 1; // window rows (same species: sliding window)
+constexpr int kFastRow = 34;                       // 33 slices of a chunk (+1 pad) per row
+
+struct PairFastArgs {
+    PathView pv;
+    SpeciesView A, B;
+    int same;
+    FastTable T;
+    const unsigned char *tables;  // the block to stage (T.n_bytes)
+    int n_chunks, n_pgroups;
+    double *partial;              // [C][n_chunks][n_pgroups]
+};
+
+/// Persistent CTAs, one per SM.  Work item = (clone, 32-slice chunk, group of 32 particles of
+/// species a): warp w owns particle p = 32 g + w, its lanes own the chunk's 32 links.  Same
+/// species: the warp pairs p with q = p + dd (mod N) for dd = 1..N/2 (the last offset only
+/// from the lower half when N is even), so every unordered pair is visited once and every
+/// warp does the same amount of work per staged window; window t holds the Q + 31 particles
+/// q = 32 g + t Q + 1 ... and warp w reads row w + i at step i.  Different species: the window
+/// holds Q particles of species b and every warp walks all of them.
+__global__ void __launch_bounds__(kFastThreads, 1) pair_full_fast_kernel(const PairFastArgs a) {
+    extern __shared__ __align__(16) unsigned char fsm[];
+    __shared__ double red[kFastWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *qpos = reinterpret_cast<double *>(fsm);               // [kFastRows][3][kFastRow]
+    unsigned char *tb = fsm + sizeof(double) * kFastRows * 3 * kFastRow;
+    {
+        const int4 *src = reinterpret_cast<const int4 *>(a.tables);
+        int4 *dst = reinterpret_cast<int4 *>(tb);
+        for (int i = tid; i < a.T.n_bytes / 16; i += kFastThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+    const PathView &pv = a.pv;
+    const int Na = a.A.N, Nb = a.B.N;
+    const int half = Na / 2;
+    const int n_dd = a.same ? half : Nb;  // partner steps per particle
+    const int per_clone = a.n_chunks * a.n_pgroups;
+    const int n_items = pv.C * per_clone;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int c = item / per_clone;
+        const int rem = item - c * per_clone;
+        const int chunk = rem / a.n_pgroups, pg = rem - chunk * a.n_pgroups;
+        const int s0 = chunk * kChunk;
+        const int p_lo = pg * kFastWarps;
+        const int p = p_lo + warp;
+        const bool warp_on = p < Na;
+        const bool lane_on = s0 + lane < pv.Mloc;
+        double p0[3] = {0., 0., 0.}, p1[3] = {0., 0., 0.};
+        if (warp_on && lane_on) {
+            const int i0 = s0 + lane, i1 = StoreIndex(pv, s0 + lane + 1);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                p0[d] = a.A.R[PosIndex(pv, Na, c, p, d, i0)];
+                p1[d] = a.A.R[PosIndex(pv, Na, c, p, d, i1)];
+            }
+        }
+        // steps this warp really takes: the offset N/2 of an even N belongs to the lower half
+        int my_dd = n_dd;
+        if (a.same && (Na & 1) == 0 && p >= half) my_dd = half - 1;
+        if (!warp_on) my_dd = 0;
+        double acc = 0.;
+        for (int t0 = 0; t0 < n_dd; t0 += kFastQ) {
+            const int n_rows = a.same ? min(kFastQ, n_dd - t0) + kFastWarps - 1 : min(kFastQ, Nb - t0);
+            const int q_first = a.same ? p_lo + t0 + 1 : t0;
+            __syncthreads();  // the previous window has been consumed
+            for (int row = warp; row < n_rows * 3; row += kFastWarps) {
+                const int qq = row / 3, d = row - qq * 3;
+                int q = q_first + qq;
+                if (a.same) q %= Na;
+                const double *src = a.B.R + PosIndex(pv, Nb, c, q, d, 0);
+                const int i0 = StoreIndex(pv, s0 + lane);
+                qpos[row * kFastRow + lane] = i0 >= 0 ? src[i0] : 0.;
+                if (lane == 0) {
+                    const int i1 = StoreIndex(pv, s0 + kChunk);
+                    qpos[row * kFastRow + kChunk] = i1 >= 0 ? src[i1] : 0.;
+                }
+            }
+            __syncthreads();
+            const int n_step = min(kFastQ, my_dd - t0);
+            const double *rowp = qpos + (a.same ? warp * 3 * kFastRow : 0) + lane;
+            for (int i = 0; i < n_step; ++i, rowp += 3 * kFastRow) {
+                const double b0[3] = {rowp[0], rowp[kFastRow], rowp[2 * kFastRow]};
+                const double b1[3] = {rowp[1], rowp[kFastRow + 1], rowp[2 * kFastRow + 1]};
+                double r, rp, s;
+                DrDrpDrrpFast(p0, b0, p1, b1, pv.box, r, rp, s);
+                const double u = FastIlkkaEval(tb, a.T, r, rp, s);
+                acc += lane_on ? u : 0.;
+            }
+        }
+        const double tot = BlockSum<kFastThreads>(acc, red);
+        if (tid == 0) a.partial[item] = tot;
+    }
+}
+
+/// Test hooks: the fast evaluation on caller-supplied triples (tables read from global memory
+/// through the same code) and the square root on its own.
+__global__ void calc_pair_fast_kernel(const unsigned char *__restrict__ tables, FastTable T, int n, const double *__restrict__ r,
+                                      const double *__restrict__ rp, const double *__restrict__ s, double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = FastIlkkaEval(tables, T, r[i], rp[i], s[i]);
+}
+__global__ void fast_sqrt_kernel(int n, const double *__restrict__ x, double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = FastSqrt(x[i]);
+}
+
+}  // namespace pimc
+
+#endif  // SIMPIMC_B200_PAIR_FAST_CUH_

@@ -317,6 +317,49 @@ inline BitLut BuildBitLut(const double *g, int n) {
     return best;
 }
 
+
+/// Uniform-bucket interval table for the fast kernels: bucket k holds every x whose x/h rounds
+/// to k (the device computes the key with one fused multiply-add against 2^52+2^51).  lut[k] is
+/// the einspline interval of the bucket's lower edge; h is chosen below the smallest knot
+/// spacing so that at most one knot lies inside a bucket and a single compare against the
+/// next knot finishes the search.  Returns false when the table would need more than
+/// `max_keys` buckets (the caller then keeps the general kernel).
+struct ULut {
+    double inv_h = 0.;
+    std::vector<uint16_t> lut;
+};
+
+inline bool BuildULut(const double *g, int n, int max_keys, ULut &out) {
+    if (n < 2 || n > 65535 || g[0] < 0.) return false;
+    double min_sp = g[1] - g[0];
+    for (int i = 2; i < n; ++i) min_sp = std::min(min_sp, g[i] - g[i - 1]);
+    if (!(min_sp > 0.)) return false;
+    const double h = 0.96 * min_sp;
+    const double inv_h = 1.0 / h;
+    const double n_keys_d = std::ceil(g[n - 1] * inv_h) + 3.0;
+    if (n_keys_d > (double)max_keys) return false;
+    const int n_keys = (int)n_keys_d;
+    out.inv_h = inv_h;
+    out.lut.assign((std::size_t)n_keys, 0);
+    // interval of x (einspline general-grid reverse map): last i with g[i] <= x, 0 below the
+    // grid, n-1 at or above its end
+    auto interval = [&](double x) {
+        if (x <= g[0]) return 0;
+        if (x >= g[n - 1]) return n - 1;
+        return (int)(std::upper_bound(g, g + n, x) - g) - 1;
+    };
+    const double slack = 1e-6;  // covers the rounding of x * inv_h at the bucket edges
+    for (int k = 0; k < n_keys; ++k) {
+        const double lo = ((double)k - 0.5 - slack) * h, hi = ((double)k + 0.5 + slack) * h;
+        const int i_lo = interval(lo), i_hi = interval(hi);
+        if (i_hi - i_lo > 1) return false;  // cannot happen while h < min spacing
+        out.lut[(std::size_t)k] = (uint16_t)i_lo;
+    }
+    // the last bucket must lie wholly at or above the grid end: keys are clamped to it
+    if (out.lut.back() != n - 1) return false;
+    return true;
+}
+
 }  // namespace pimc
 
 #endif  // SIMPIMC_B200_SPLINE_BUILD_H_

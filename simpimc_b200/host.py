@@ -160,6 +160,16 @@ class Path:
         capi.check(self.L.pimc_ctx_kernel_time(self.h, kernel_id, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def ForceGeneral(self, enable=True):
+        """Tests: evaluate with the general kernels even where the fast Ilkka path applies."""
+        capi.check(self.L.pimc_ctx_force_general(self.h, 1 if enable else 0))
+
+    def FastSqrt(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.zeros_like(x)
+        capi.check(self.L.pimc_debug_fast_sqrt(self.h, len(x), _vp(x), _vp(out)))
+        return out
+
     def Fp64Peak(self):
         t = C.c_double()
         capi.check(self.L.pimc_fp64_peak(self.h, C.byref(t)))
@@ -238,6 +248,15 @@ class PairAction:
         s = np.ascontiguousarray(s, dtype=np.float64)
         out = np.zeros_like(r)
         capi.check(self.L.pimc_action_calc_pair(self.h, which, len(r), _vp(r), _vp(r_p), _vp(s), level, _vp(out)))
+        return out
+
+
+    def CalcPairFast(self, which, r, r_p, s):
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        r_p = np.ascontiguousarray(r_p, dtype=np.float64)
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        out = np.zeros_like(r)
+        capi.check(self.L.pimc_action_calc_pair_fast(self.h, which, len(r), _vp(r), _vp(r_p), _vp(s), _vp(out)))
         return out
 
 

@@ -224,3 +224,66 @@ def test_errors_are_loud():
     cfg.n_d = 2
     with pytest.raises(RuntimeError):
         host.Path(cfg, n_clones=1)
+
+
+@pytest.mark.parametrize("name", ["ilkka_lr_n7", "ilkka_lr_n33", "ilkka_nolr_n8", "plasma", "n2"])
+def test_fast_and_general_kernels_agree_with_oracle(name):
+    """The whole-path Ilkka evaluation runs through the fast kernel (pair_fast.cuh) by default;
+    the general kernel is kept for the other action types.  Both must match the oracle."""
+    cfg = CONFIGS[name]()
+    path, oracles, _ = make_pair(cfg, 3)
+    for general in (False, True):
+        path.ForceGeneral(general)
+        for ai, act in enumerate(path.actions):
+            du, u = act.DActionDBeta(), act.TotalAction()
+            parts = [(s, p) for s in range(len(cfg.species)) for p in range(cfg.species[s].n_part)]
+            for c, o in enumerate(oracles):
+                assert rel_ok(du[c], o.dbeta(ai)), (name, general, ai, c, du[c], o.dbeta(ai))
+                assert rel_ok(u[c], o.get_action(ai, 0, 0, cfg.n_bead, parts, 0)), (name, general, ai, c)
+    path.close()
+
+
+def test_fast_per_pair_matches_oracle_and_general():
+    cfg = CONFIGS["ilkka_lr_n33"]()
+    path, oracles, _ = make_pair(cfg, 1)
+    rng = np.random.default_rng(5)
+    n = 20000
+    rmax = np.sqrt(3) * cfg.L / 2
+    r = rng.uniform(1e-5, rmax, n)
+    rp = np.clip(r + rng.normal(0, 0.1, n), 1e-5, 1.2 * rmax)
+    s = np.abs(r - rp) + np.abs(rng.normal(0, 0.05, n))
+    # knots themselves, grid ends, zero separation, far outside the staged block of cells
+    tab = cfg.actions[0].table
+    knots = np.asarray(tab["u/diag/r_long"])[:200]
+    r[:200] = knots
+    rp[:200] = knots
+    s[:200] = 0.0
+    xk = np.asarray(tab["u/off_diag/x"])[1:40]
+    r[200:239] = xk
+    rp[200:239] = xk
+    s[200:239] = 0.0
+    r[300:310] = np.linspace(20.0, 99.0, 10)
+    rp[300:310] = r[300:310] + 0.3
+    s[300:310] = 0.5
+    act = path.actions[0]
+    for which in (0, 1):
+        fast = act.CalcPairFast(which, r, rp, s)
+        gen = act.CalcPair(which, r, rp, s)
+        ref = oracles[0].calc_pair(0, which, r, rp, s)
+        scale = 1e-3 * np.max(np.abs(ref))
+        assert rel_ok(fast, ref, scale=scale), (which, np.max(np.abs(fast - ref)))
+        assert rel_ok(fast, gen, scale=scale)
+    path.close()
+
+
+def test_fast_sqrt_within_one_ulp():
+    cfg = CONFIGS["n2"]()
+    path, _, _ = make_pair(cfg, 1)
+    rng = np.random.default_rng(9)
+    x = np.concatenate([[0.0, 1e-300, 1e-30, 1.0, 2.0, 4.0, 1e10], rng.uniform(0, 100, 50000), 10.0 ** rng.uniform(-20, 8, 50000)])
+    got = path.FastSqrt(x)
+    ref = np.sqrt(x)
+    assert got[0] == 0.0
+    ulp = np.spacing(ref)
+    assert np.all(np.abs(got - ref) <= ulp), np.max(np.abs(got - ref) / ulp)
+    path.close()
