@@ -1,0 +1,102 @@
+"""CPU tests (no GPU): the oracle -- oracle/pimc_oracle.cc, the CPU restatement the GPU parity
+tests check against -- is itself pinned here:
+
+* against tests/golden/*.npz, numbers produced by the REFERENCE'S OWN classes compiled in place
+  (oracle/make_golden.py; the reference tree does not travel, the fixtures do);
+* against the reference library directly where oracle/_ref exists (this container);
+* against the known answers the reference tree offers for this path: the k-vector list of
+  KSpace::Setup (182 vectors / 17 shells for every shipped k_cut = 14/(L/2), first and last
+  triples) and the Madelung constant of the StandardEwald breakup (scripts/pagen/Ewald.py).
+"""
+import numpy as np
+import pytest
+
+import golden_util as G
+from simpimc_b200 import system as S, tables as T
+
+
+@pytest.mark.parametrize("name", sorted(G.CONFIGS))
+def test_oracle_matches_reference_golden(name, oracle_mod):
+    G.check_backend(name, G.OracleBackend)
+
+
+def test_kspace_known_answers(oracle_mod):
+    # 182 half-space vectors in 17 shells; first kept triples (1,-4,-1), (1,-1,-4),
+    # (0,1,-4); last (3,2,2) -- for every shipped k_cut = 14/(L/2)
+    for N in (7, 33, 256):
+        cfg = S.ueg_config(N=N, M=4, n_xy=20, n_r_long=50)
+        o = oracle_mod.Oracle(cfg)
+        idx, mags = o.kspace()
+        assert len(idx) == 182
+        assert len(np.unique(np.round(mags / (2 * np.pi / cfg.L), 9))) == 17
+        assert [tuple(v) for v in idx[:3]] == [(1, -4, -1), (1, -1, -4), (0, 1, -4)]
+        assert tuple(idx[-1]) == (3, 2, 2)
+        o.close()
+    # strict '<' at the default cutoff 2 pi / L leaves no vector (App. A-14)
+    cfg = S.ueg_config(N=7, M=4, n_xy=20, n_r_long=50)
+    cfg.k_cut = 2 * np.pi / cfg.L
+    cfg.actions[0].k_cut = cfg.k_cut
+    o = oracle_mod.Oracle(cfg)
+    assert len(o.kspace()[0]) == 0
+    o.close()
+
+
+def test_madelung_constant_from_ewald_breakup(oracle_mod):
+    """NaCl cell (4 Na+ and 4 Cl- on a cube of side 2, nearest-neighbour distance 1), one time
+    slice: BarePairAction::Potential with the StandardEwald tables of scripts/pagen/Ewald.py
+    (v = Z1 Z2 / r short range, long-range r and k parts, constants) sums to N_pairs * Madelung.
+    Exact value -1.7475645946331822 (Ewald.py:743-748); the breakup at this cutoff with the
+    minimum-image short-range sum reproduces it to ~4e-8."""
+    L = 2.0
+    k_cut = 30.0 / (L / 2.0)  # alpha * L/2 = sqrt(15): the minimum-image short-range sum is converged to ~1e-7
+    cfg = S.SystemConfig(n_d=3, n_bead=1, beta=1.0, L=L, pbc=True, k_cut=k_cut)
+    cfg.species.append(S.SpeciesConfig("Na", 4, 0.5))
+    cfg.species.append(S.SpeciesConfig("Cl", 4, 0.5))
+    for nm, a, b, z in (("NaNa", "Na", "Na", 1.0), ("NaCl", "Na", "Cl", -1.0), ("ClCl", "Cl", "Cl", 1.0)):
+        # v(r) = Z1 Z2 / r as a spline table (the analytic is_coulomb branch carries no charges)
+        tab = T.make_bare_table(z, L, k_cut, n_r=4000, r_max=4.0, n_r_long=2000)
+        cfg.actions.append(S.ActionConfig(nm, "BarePairAction", a, b, table=tab, max_level=0, use_long_range=True, k_cut=k_cut))
+    o = oracle_mod.Oracle(cfg)
+    na = np.array([[0, 0, 0], [1, 1, 0], [1, 0, 1], [0, 1, 1]], dtype=float) - 0.5
+    cl = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 1]], dtype=float) - 0.5
+    o.set_positions(0, na.reshape(4, 1, 3))
+    o.set_positions(1, cl.reshape(4, 1, 3))
+    v = sum(o.potential(a) for a in range(3))
+    o.close()
+    madelung = v / 4.0  # energy per ion pair, nearest-neighbour distance 1
+    assert abs(madelung - (-1.7475645946331822)) < 2e-7, madelung
+
+
+def test_gofr_bin_map_matches_reference(oracle_mod):
+    g = G.load("ilkka_lr_n7")
+    cfg = G.CONFIGS["ilkka_lr_n7"]()
+    bins = oracle_mod.gofr_bins(0.0, cfg.L / 2.0, 100, g["gofr_probe_r"])
+    ref = g["gofr_probe_bins"]
+    # negative arguments wrap to huge unsigned values in the reference (App. A-11); both sides
+    # agree on every index that passes the i < n_r test and on which samples are dropped
+    keep = ref < 100
+    assert np.array_equal(bins < 100, keep)
+    assert np.array_equal(bins[keep], ref[keep])
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_oracle_matches_live_reference(seed, oracle_mod):
+    """Fresh seeds against the reference library itself (only where oracle/_ref was built)."""
+    from oracle import refsim
+    if not refsim.available():
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    cfg = S.plasma_config(Ne=5, Np=4, M=8)
+    sim = refsim.RefSim(cfg, seed=seed)
+    o = oracle_mod.Oracle(cfg)
+    for sp in range(2):
+        R = S.synthetic_paths(cfg, sp, 0, 1000 + seed)
+        sim.set_positions(sp, R)
+        o.set_positions(sp, R)
+    for a in range(3):
+        assert G.rel_ok(o.dbeta(a), sim.dbeta(a))
+        assert G.rel_ok(o.potential(a), sim.potential(a))
+    for sp in range(2):
+        assert np.max(np.abs(o.rhok(sp) - sim.rhok(sp))) <= 1e-12 * 5
+    sim.close()
+    o.close()
