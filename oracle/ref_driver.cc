@@ -55,6 +55,13 @@ using namespace scaffold::rand;
 #undef private
 #undef protected
 
+// integration/Makefile compiles this same driver with -DPIMC_DROPIN_GPU: the reference's moves
+// and observables then run on top of the CUDA library through the adapter a maintainer would
+// add to the reference tree (include/simpimc_b200_action.hpp).
+#ifdef PIMC_DROPIN_GPU
+#include "simpimc_b200_action.hpp"
+#endif
+
 namespace {
 
 struct RefSim {
@@ -70,6 +77,9 @@ struct RefSim {
 std::shared_ptr<Action> MakeAction(Input &in, IO &out, Path &path) {
     std::string type = in.GetAttribute<std::string>("type");
     if (type == "Kinetic") return std::make_shared<Kinetic>(path, in, out);
+#ifdef PIMC_DROPIN_GPU
+    if (type == "IlkkaPairAction" || type == "BarePairAction") return std::make_shared<GpuPairAction>(path, in, out);
+#endif
     if (type == "BarePairAction") return std::make_shared<BarePairAction>(path, in, out);
     if (type == "DavidPairAction") return std::make_shared<DavidPairAction>(path, in, out);
     if (type == "IlkkaPairAction") return std::make_shared<IlkkaPairAction>(path, in, out);

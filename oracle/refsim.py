@@ -27,11 +27,18 @@ def available(fast=False):
 _libs = {}
 
 
-def _load(fast=False):
-    key = bool(fast)
+DROPIN_LIB = os.path.join(os.path.dirname(HERE), "integration", "_build", "libsimpimc_dropin.so")
+
+
+def dropin_available():
+    return os.path.exists(DROPIN_LIB)
+
+
+def _load(fast=False, dropin=False):
+    key = "dropin" if dropin else bool(fast)
     if key in _libs:
         return _libs[key]
-    lib = C.CDLL(REF_LIB_FAST if fast else REF_LIB)
+    lib = C.CDLL(DROPIN_LIB if dropin else (REF_LIB_FAST if fast else REF_LIB))
     lib.ref_create.restype = C.c_void_p
     lib.ref_create.argtypes = [C.c_char_p, C.c_int, C.c_int]
     lib.ref_destroy.argtypes = [C.c_void_p]
@@ -147,9 +154,9 @@ def system_xml(cfg, table_files, workdir):
 class RefSim:
     """One reference Path + actions + moves + observables, built from a SystemConfig."""
 
-    def __init__(self, cfg, seed=12345, workdir=None, fast=False, quiet=True):
+    def __init__(self, cfg, seed=12345, workdir=None, fast=False, quiet=True, dropin=False):
         from simpimc_b200 import tables as T
-        self.lib = _load(fast)
+        self.lib = _load(fast, dropin)
         self.cfg = cfg
         self._tmp = None
         if workdir is None:

@@ -1,0 +1,62 @@
+"""Drop-in test: the REFERENCE'S OWN moves and estimators (Bisect::Attempt / Accept / Reject,
+DisplaceParticle, Energy -- compiled in place from /root/reference/src into
+integration/_build/libsimpimc_dropin.so) running on top of the CUDA library through
+include/simpimc_b200_action.hpp (class GpuPairAction : public Action), against the same
+program with the reference's IlkkaPairAction / BarePairAction (oracle/_ref).  Same seed, same
+RNG stream: every Metropolis decision, hence every bead position, must come out identical,
+and the energies must agree to 1e-10."""
+import numpy as np
+import pytest
+
+from simpimc_b200 import system as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _sims(cfg, seed):
+    from oracle import refsim
+    if not (refsim.available() and refsim.dropin_available()):
+        pytest.skip("oracle/_ref or integration/_build not built (needs /root/reference at build time)")
+    a = refsim.RefSim(cfg, seed=seed)
+    b = refsim.RefSim(cfg, seed=seed, dropin=True)
+    for sp in range(len(cfg.species)):
+        R = S.synthetic_paths(cfg, sp, 0, 77 + seed)
+        a.set_positions(sp, R)
+        b.set_positions(sp, R)
+    return a, b
+
+
+@pytest.mark.parametrize("which", ["ueg", "plasma"])
+def test_reference_moves_on_gpu_actions_reproduce_the_reference_run(which):
+    if which == "ueg":
+        cfg = S.ueg_config(N=14, M=16, with_kinetic=True)
+        cfg.moves = [{"name": "BisectE", "type": "Bisect", "species": "e", "n_level": 3},
+                     {"name": "DisplaceE", "type": "DisplaceParticle", "species": "e", "step_size": 0.3}]
+    else:
+        cfg = S.plasma_config(Ne=6, Np=5, M=8)
+        cfg.actions.insert(0, S.ActionConfig("KineticE", "Kinetic", "e"))
+        cfg.actions.insert(1, S.ActionConfig("KineticP", "Kinetic", "p"))
+        cfg.moves = [{"name": "BisectE", "type": "Bisect", "species": "e", "n_level": 2},
+                     {"name": "BisectP", "type": "Bisect", "species": "p", "n_level": 2},
+                     {"name": "DisplaceP", "type": "DisplaceParticle", "species": "p", "step_size": 0.2}]
+    cfg.observables = [{"name": "Energy", "type": "Energy", "measure_potential": 1}]
+    a, b = _sims(cfg, seed=5)
+    n_moves = len(cfg.moves)
+    for sweep in range(30):
+        for m in range(n_moves):
+            a.move_do(m, 5)
+            b.move_do(m, 5)
+        a.observable_accumulate(0)
+        b.observable_accumulate(0)
+    for m in range(n_moves):
+        assert a.move_counts(m) == b.move_counts(m), "accept/reject history differs"
+        att, acc = a.move_counts(m)
+        assert att == 150 and 0 < acc
+    for sp in range(len(cfg.species)):
+        assert np.array_equal(a.get_positions(sp, 0), b.get_positions(sp, 0)), "trajectories diverged"
+    ea, va = a.energy_sums(0)
+    eb, vb = b.energy_sums(0)
+    assert np.all(np.abs(ea - eb) <= 1e-10 * np.maximum(np.abs(ea), 1e-300)), (ea, eb)
+    assert np.all(np.abs(va - vb) <= 1e-10 * np.maximum(np.abs(va), 1e-300)), (va, vb)
+    a.close()
+    b.close()
