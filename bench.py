@@ -246,24 +246,40 @@ def run_ours(args):
     e2e_value = world * evals_step * args.steps / (float(te.item()) * 1e-3)
     # correctness guard for the bench itself: both paths computed the same energies
     assert np.allclose(out_dev.cpu().numpy(), out_host, rtol=1e-12, atol=0), "resident and e2e energies differ"
-    # ---- MC sweeps: host-driven bisection attempts on all clones ------------------------------
-    rng = np.random.default_rng(1234 + rank)
-    bis = moves.Bisect(path, rng, 0, BISECT_LEVEL)
-    for _ in range(2):
-        bis.DoEvent()
-    barrier()
+    # ---- MC sweeps: device-resident bisection (pimc_bisect_sweep: Levy sampling, kinetic + pair +
+    # long-range action deltas, Metropolis, commit -- no host round trip per attempt) ---------------
     n_att = args.attempts
-    s0 = time.perf_counter()
-    for _ in range(n_att):
-        bis.DoEvent()
-    path.Sync()
-    s1 = time.perf_counter()
-    ts = torch.tensor([s1 - s0], dtype=torch.float64, device="cuda")
+    path.BisectSweep(0, BISECT_LEVEL, 8, 1234 + rank, attempt0=0)   # warm-up
+    barrier()
+    path.SetTiming(True)
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches_mc0 = path.LaunchCount()
+    m0.record(stream)
+    n_acc = path.BisectSweep(0, BISECT_LEVEL, n_att, 1234 + rank, attempt0=8)
+    m1.record(stream)
+    m1.synchronize()
+    barrier()
+    launches_mc = path.LaunchCount() - launches_mc0
+    k4_ms, k4_n = path.KernelTime(4)
+    path.SetTiming(False)
+    ts = torch.tensor([m0.elapsed_time(m1) * 1e-3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ts, op=dist.ReduceOp.MAX)
     attempts_per_sweep = N_PART * N_SLICE // (1 << BISECT_LEVEL)
     sweeps_per_s = world * C * n_att / attempts_per_sweep / float(ts.item())
     window_evals_per_s = world * C * n_att * 2 * (N_PART - 1) * (1 << BISECT_LEVEL) / float(ts.item())
+    accept_ratio = float(n_acc.sum()) / (C * n_att)
+    # the same move driven from the host through propose / GetAction(OLD, NEW) / commit (the
+    # reference-shaped call sequence), a few attempts for comparison
+    rng = np.random.default_rng(1234 + rank)
+    bis = moves.Bisect(path, rng, 0, BISECT_LEVEL)
+    bis.DoEvent()
+    path.Sync()
+    s0 = time.perf_counter()
+    for _ in range(4):
+        bis.DoEvent()
+    path.Sync()
+    host_driven_sweeps_per_s = C * 4 / attempts_per_sweep / (time.perf_counter() - s0)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -307,8 +323,11 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "mc_sweeps_per_s": sweeps_per_s,
             "mc": {"unit": "clone-sweeps/s (one sweep = N*M/2^n_level bisection attempts)", "attempts_timed": n_att,
-                   "accept_ratio": bis.accept_ratio(), "window_pair_evals_per_s": window_evals_per_s,
-                   "driver": "host-driven Bisect (simpimc_b200.moves) calling GetAction OLD/NEW + commit through the C ABI"},
+                   "accept_ratio": accept_ratio, "window_pair_evals_per_s": window_evals_per_s,
+                   "ms_per_attempt": 1e3 * float(ts.item()) / n_att, "launches": int(launches_mc),
+                   "pair_window_kernel_ms_per_attempt": k4_ms / max(1, n_att),
+                   "driver": "device-resident pimc_bisect_sweep (Philox stream; kinetic + Ilkka pair + long-range deltas, Metropolis, commit)",
+                   "host_driven_sweeps_per_s_per_gpu": host_driven_sweeps_per_s},
             "roofline": roofline}
     if base:
         line["cpu_baseline"] = base
@@ -324,7 +343,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clones", type=int, default=int(os.environ.get("BENCH_CLONES", "1024")))
-    ap.add_argument("--attempts", type=int, default=24, help="bisection attempts timed for the MC-sweep figure")
+    ap.add_argument("--attempts", type=int, default=256, help="bisection attempts per clone timed for the MC-sweep figure")
     ap.add_argument("--cpu-evals", type=int, default=2, help="DActionDBeta() calls per core for cpu_baseline (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -205,6 +205,17 @@ int pimc_beads_download(pimc_ctx *ctx, int32_t species, const int32_t *particle,
  * StoreR/StoreRhoK or RestoreR/RestoreRhoK, then every action's flag is re-armed. */
 int pimc_commit(pimc_ctx *ctx, const int32_t *accept);
 
+/* n_attempts x Bisect::DoEvent (move_class.h:61-77 -> bisect_class.h:39-139) on every clone,
+ * entirely on the device: particle and window choice, Levy construction, the free-particle
+ * action in closed form (Kinetic with n_images = 0; with_kinetic = 0 leaves it out), every pair
+ * action of the context that involves `species` in OLD and NEW mode, the Metropolis test per
+ * level, Accept / Reject.  Random numbers are Philox4x32-10 (key = seed, counter = attempt0 + i,
+ * clone, slot): the stream is reproducible and documented in csrc/mc.cuh, but it is not
+ * std::mt19937 -- sampled runs match the reference statistically.  n_accept[n_clones] (host,
+ * may be NULL) is ADDED to. */
+int pimc_bisect_sweep(pimc_ctx *ctx, int32_t species, int32_t n_level, int32_t n_attempts, uint64_t seed, uint64_t attempt0,
+                      int32_t with_kinetic, int64_t *n_accept);
+
 /* ---- estimators ------------------------------------------------------------------------ */
 /* PairCorrelation::Accumulate (pair_correlation_class.h:15-28): y[c][i] += cofactor[c] for
  * every pair and slice, bin i = (uint32)nearbyint((|dr|-r_min)*d_ir - 0.5), i < n_r kept.

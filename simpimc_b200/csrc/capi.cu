@@ -17,6 +17,7 @@
 #include "../../include/simpimc_b200.h"
 #include "kernels.cuh"
 #include "pair_fast.cuh"
+#include "mc.cuh"
 #include "spline_build.h"
 
 using namespace pimc;
@@ -97,6 +98,10 @@ struct pimc_ctx {
     DevBuf<int32_t> i32_a, i32_b, i32_c, i32_d;
     DevBuf<unsigned long long> counts;
     DevBuf<double> est;
+    // device-resident moves (mc.cuh): per-clone scalars of the attempt in flight
+    DevBuf<double> mc_f64;    // partial, logu0, pair_old, pair_new, lr_old, lr_new: 6 x [C]
+    DevBuf<int32_t> mc_i32;   // alive, b0, accept: 3 x [C]
+    DevBuf<long long> mc_naccept;
     std::vector<pimc_action *> actions;
     int64_t launches = 0;
     bool force_general = false;  // tests: evaluate with the general kernels even where the fast path applies
@@ -619,6 +624,7 @@ int LaunchKSum(pimc_action *a, int which, const int32_t *d_b0, int n_window, boo
     k.n_window = n_window;
     k.twice = a->sa != a->sb;
     k.scale = scale;
+    k.accumulate = 0;
     k.out = ctx->lr_dev.p;
     {
         ScopedKernelTimer t(ctx, PIMC_KERNEL_KSUM);
@@ -1345,6 +1351,158 @@ int pimc_commit(pimc_ctx *ctx, const int32_t *accept) {
         st.need_update_rho_k = true;  // every action's Accept/Reject re-arms the flag
     }
     PIMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PIMC_OK;
+}
+
+
+// ------------------------------------------------------------------- device-resident moves
+int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attempts, uint64_t seed, uint64_t attempt0,
+                      int32_t with_kinetic, int64_t *n_accept) {
+    if (!ctx) return Fail(PIMC_ERR_INVALID, "null context");
+    if (s < 0 || s >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
+    if (n_level < 1 || (1 << n_level) > kMaxBisectBeads || (1 << n_level) > ctx->M)
+        return Fail(PIMC_ERR_INVALID, "n_level must satisfy 2 <= 2^n_level <= min(32, n_bead)");
+    if (n_attempts < 0) return Fail(PIMC_ERR_INVALID, "negative attempt count");
+    if (ctx->sharded) return Fail(PIMC_ERR_UNSUPPORTED, "moves on a slice-sharded context");
+    SpeciesState &st = *ctx->species[s];
+    if (!(st.lambda > 0.)) return Fail(PIMC_ERR_INVALID, "bisection of a species with lambda = 0");
+    for (auto &sp : ctx->species)
+        if (sp->n_prop > 0) return Fail(PIMC_ERR_INVALID, "a proposal is pending: call pimc_commit first");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    const int C = ctx->C, nb = 1 << n_level, n_prop = nb - 1, n_k = ctx->n_k();
+    if (ctx->mc_f64.n < (size_t)6 * C) PIMC_CUDA(ctx->mc_f64.Alloc((size_t)6 * C));
+    if (ctx->mc_i32.n < (size_t)3 * C) PIMC_CUDA(ctx->mc_i32.Alloc((size_t)3 * C));
+    if (ctx->mc_naccept.n < (size_t)C) PIMC_CUDA(ctx->mc_naccept.Alloc(C));
+    PIMC_CUDA(cudaMemsetAsync(ctx->mc_naccept.p, 0, C * sizeof(long long), ctx->stream));
+    if (st.P.n < (size_t)C * n_prop * 3) PIMC_CUDA(st.P.Alloc((size_t)C * n_prop * 3));
+    double *partial = ctx->mc_f64.p, *logu0 = partial + C, *pair_old = logu0 + C, *pair_new = pair_old + C, *lr_old = pair_new + C,
+           *lr_new = lr_old + C;
+    int32_t *alive = ctx->mc_i32.p, *b0 = alive + C, *accept = b0 + C;
+    // move_class.h:27-31: the actions that involve this species
+    std::vector<pimc_action *> acts;
+    bool any_lr = false;
+    for (pimc_action *a : ctx->actions) {
+        if (a->sa != s && a->sb != s) continue;
+        if (a->is_constant) continue;
+        acts.push_back(a);
+        any_lr = any_lr || (a->use_long_range && n_k > 0);
+    }
+    if (any_lr) {
+        const size_t need = (size_t)C * nb * n_k;
+        if (st.drho.n < need) PIMC_CUDA(st.drho.Alloc(need));
+    }
+    const PathView pv = ctx->View();
+    for (int it = 0; it < n_attempts; ++it) {
+        const uint64_t attempt = attempt0 + (uint64_t)it;
+        BisectArgs ba;
+        ba.pv = pv;
+        ba.R = st.R.p;
+        ba.N = st.N;
+        ba.lambda = st.lambda;
+        ba.tau = ctx->tau;
+        ba.n_level = n_level;
+        ba.with_kinetic = with_kinetic ? 1 : 0;
+        ba.seed_lo = (uint32_t)seed;
+        ba.seed_hi = (uint32_t)(seed >> 32);
+        ba.attempt_lo = (uint32_t)attempt;
+        ba.attempt_hi = (uint32_t)(attempt >> 32);
+        ba.P = st.P.p;
+        ba.P_particle = st.P_particle.p;
+        ba.P_first = st.P_first.p;
+        ba.b0 = b0;
+        ba.partial = partial;
+        ba.logu0 = logu0;
+        ba.alive = alive;
+        ba.pair_old = pair_old;
+        ba.pair_new = pair_new;
+        ba.lr_old = lr_old;
+        ba.lr_new = lr_new;
+        bisect_sample_kernel<<<(C + 127) / 128, 128, 0, ctx->stream>>>(ba);
+        ctx->launches++;
+        for (pimc_action *a : acts) {
+            const int partner = (a->sa == s) ? a->sb : a->sa;
+            WindowBothArgs w;
+            w.pv = pv;
+            w.R_moved = st.R.p;
+            w.N_moved = st.N;
+            w.R_partner = ctx->species[partner]->R.p;
+            w.N_partner = ctx->species[partner]->N;
+            w.same = partner == s;
+            w.P = st.P.p;
+            w.P_particle = st.P_particle.p;
+            w.b0 = b0;
+            w.alive = alive;
+            w.n_links = nb;
+            w.FT = a->fast[WHICH_U];
+            w.fast_tables = a->fast_tab[WHICH_U].p;
+            w.T = a->table[WHICH_U];
+            w.blob = a->blob[WHICH_U].p;
+            w.out_old = pair_old;
+            w.out_new = pair_new;
+            {
+                ScopedKernelTimer t(ctx, PIMC_KERNEL_PAIR_WINDOW);
+                if (a->atype == ATYPE_ILKKA && a->fast_ok[WHICH_U] && !ctx->force_general)
+                    pair_window_both_kernel<ATYPE_ILKKA, true><<<C, kWindowThreads, 0, ctx->stream>>>(w);
+                else if (a->atype == ATYPE_ILKKA)
+                    pair_window_both_kernel<ATYPE_ILKKA, false><<<C, kWindowThreads, 0, ctx->stream>>>(w);
+                else if (a->atype == ATYPE_BARE)
+                    pair_window_both_kernel<ATYPE_BARE, false><<<C, kWindowThreads, 0, ctx->stream>>>(w);
+                else
+                    pair_window_both_kernel<ATYPE_DAVID, false><<<C, kWindowThreads, 0, ctx->stream>>>(w);
+            }
+            ctx->launches++;
+        }
+        if (any_lr) {
+            SpeciesView sv = ctx->SView(s, false);
+            sv.n_prop = n_prop;  // the proposal the sample kernel has just written
+            const int tl = 2 * ctx->max_index + 1;
+            rhok_delta_kernel<<<GridFor(ctx, C * nb), 256, (size_t)6 * tl * sizeof(double2), ctx->stream>>>(pv, sv, ctx->KView(), b0, nb,
+                                                                                                          st.drho.p);
+            ctx->launches++;
+            for (pimc_action *a : acts) {
+                if (!(a->use_long_range && n_k > 0)) continue;
+                for (int mode = 0; mode < 2; ++mode) {
+                    KSumArgs k;
+                    k.pv = pv;
+                    k.n_k = n_k;
+                    k.rho_a = ctx->species[a->sa]->rho.p;
+                    k.rho_b = ctx->species[a->sb]->rho.p;
+                    k.drho_a = (mode && a->sa == s) ? st.drho.p : nullptr;
+                    k.drho_b = (mode && a->sb == s) ? st.drho.p : nullptr;
+                    k.wk = a->wk[WHICH_U].p;
+                    k.b0 = b0;
+                    k.n_window = nb;
+                    k.twice = a->sa != a->sb;
+                    k.scale = a->ulong_scale;
+                    k.accumulate = 1;
+                    k.out = mode ? lr_new : lr_old;
+                    ScopedKernelTimer t(ctx, PIMC_KERNEL_KSUM);
+                    ksum_kernel<<<C, 256, 0, ctx->stream>>>(k);
+                    ctx->launches++;
+                }
+            }
+        }
+        bisect_decide_kernel<<<(C + 127) / 128, 128, 0, ctx->stream>>>(C, alive, partial, logu0, pair_old, pair_new, lr_old, lr_new, accept,
+                                                                       (int64_t *)ctx->mc_naccept.p);
+        ctx->launches++;
+        commit_positions_kernel<<<C, 64, 0, ctx->stream>>>(pv, st.N, st.P.p, st.P_particle.p, st.P_first.p, n_prop, accept, st.R.p);
+        ctx->launches++;
+        if (any_lr) {
+            dim3 grid((nb * n_k + 255) / 256, C);
+            commit_rhok_kernel<<<grid, 256, 0, ctx->stream>>>(pv, n_k, st.drho.p, b0, nb, accept, st.rho.p);
+            ctx->launches++;
+        }
+    }
+    PIMC_CUDA(cudaGetLastError());
+    st.n_prop = 0;
+    st.drho_valid = false;
+    for (auto &sp : ctx->species) sp->need_update_rho_k = true;
+    if (n_accept) {
+        std::vector<long long> h(C);
+        PIMC_CUDA(cudaMemcpyAsync(h.data(), ctx->mc_naccept.p, C * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        PIMC_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int c = 0; c < C; ++c) n_accept[c] += (int64_t)h[c];
+    }
     return PIMC_OK;
 }
 

@@ -312,6 +312,7 @@ struct KSumArgs {
     int n_window;
     int twice;                      // species differ
     double scale;                   // Bare CalcULong: level_tau
+    int accumulate;                 // add to out[c] instead of overwriting it
     double *out;                    // [C]
 };
 
@@ -349,7 +350,10 @@ __global__ void __launch_bounds__(256) ksum_kernel(const KSumArgs a) {
     double tot = BlockSum<256>(acc, red);
     if (threadIdx.x == 0) {
         if (a.twice) tot *= 2.;
-        a.out[c] = a.scale * tot;
+        if (a.accumulate)
+            a.out[c] += a.scale * tot;
+        else
+            a.out[c] = a.scale * tot;
     }
 }
 

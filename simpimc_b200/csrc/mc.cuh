@@ -1,0 +1,307 @@
+// Device-resident bisection moves: Bisect::Attempt / Accept / Reject
+// (src/events/moves/single_species_move/bisect/bisect_class.h:24-139) for every clone of a
+// context at once, without a host round trip per attempt.
+//
+//   bisect_sample_kernel      pick particle and window, Levy construction level by level, the
+//                             free-particle (Kinetic, n_images = 0) action and sampling
+//                             probabilities, Metropolis tests of the levels above 0 (pair
+//                             actions return 0 there, pair_action_class.h:269)
+//   pair_window_both_kernel   sum over the window's links and all partner particles of the
+//                             pair action in OLD and in NEW mode (PairAction::GetAction,
+//                             pair_action_class.h:267-302, as called at bisect_class.h:103-108)
+//   (rhok_delta_kernel + ksum_kernel from kernels.cuh give the long-range part)
+//   bisect_decide_kernel      level-0 Metropolis test (bisect_class.h:110-115) -> accept flags
+//   (commit_positions_kernel / commit_rhok_kernel apply Move::Accept)
+//
+// Random numbers: Philox4x32-10 keyed by the caller's seed, counter = (attempt, clone, slot);
+// the reference draws from std::mt19937, so sampled runs agree with it statistically, not
+// stream for stream.  simpimc_b200/moves.py holds the host mirror of the same stream.
+#ifndef SIMPIMC_B200_MC_CUH_
+#define SIMPIMC_B200_MC_CUH_
+
+#include "kernels.cuh"
+#include "pair_fast.cuh"
+
+namespace pimc {
+
+__host__ __device__ __forceinline__ void PhiloxRound(uint32_t c[4], uint32_t k[2]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    const uint64_t p0 = (uint64_t)M0 * c[0], p1 = (uint64_t)M1 * c[2];
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    const uint32_t n0 = hi1 ^ c[1] ^ k[0], n2 = hi0 ^ c[3] ^ k[1];
+    c[0] = n0;
+    c[1] = lo1;
+    c[2] = n2;
+    c[3] = lo0;
+}
+
+/// Philox4x32-10 (Salmon et al., SC'11): out = f_key(counter).
+__host__ __device__ __forceinline__ void Philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                                    uint32_t out[4]) {
+    uint32_t c[4] = {c0, c1, c2, c3}, k[2] = {k0, k1};
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        PhiloxRound(c, k);
+        k[0] += 0x9E3779B9u;
+        k[1] += 0xBB67AE85u;
+    }
+    out[0] = c[0];
+    out[1] = c[1];
+    out[2] = c[2];
+    out[3] = c[3];
+}
+
+/// Uniform double in (0, 1] from two 32-bit words (53 bits; never 0, so log(u) is finite).
+__host__ __device__ __forceinline__ double UniformFromBits(uint32_t a, uint32_t b) {
+    const uint64_t x = ((uint64_t)(a >> 5) << 26) | (uint64_t)(b >> 6);
+    return ((double)x + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+constexpr int kMaxBisectBeads = 32;  // n_level <= 5
+
+struct BisectArgs {
+    PathView pv;
+    const double *R;   // committed positions of the species
+    int N;
+    double lambda, tau;
+    int n_level;
+    int with_kinetic;
+    uint32_t seed_lo, seed_hi;
+    uint32_t attempt_lo, attempt_hi;
+    // outputs (proposal of the species + per-clone scalars)
+    double *P;              // [C][nb-1][3]
+    int32_t *P_particle;    // [C]
+    int32_t *P_first;       // [C]
+    int32_t *b0;            // [C]
+    double *partial;        // [C] log_sample_ratio - kinetic change at level 0 + previous level's change
+    double *logu0;          // [C]
+    int32_t *alive;         // [C] passed the levels above 0
+    double *pair_old, *pair_new, *lr_old, *lr_new;  // [C] accumulators, zeroed here
+};
+
+__device__ __forceinline__ double PutInBox1(double d, const Box &bx) { return d - rint(d * bx.iL) * bx.L; }
+
+/// One thread per clone.
+__global__ void __launch_bounds__(128) bisect_sample_kernel(const BisectArgs a) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const PathView &pv = a.pv;
+    if (c >= pv.C) return;
+    const int nb = 1 << a.n_level;
+    uint32_t rnd[4];
+    Philox4x32(a.attempt_lo, a.attempt_hi, (uint32_t)c, 0u, a.seed_lo, a.seed_hi, rnd);
+    // rng.UnifRand(n) - 1: uniform integer in [0, n)
+    int p_i = (int)(UniformFromBits(rnd[0], rnd[1]) * a.N);
+    p_i = p_i < a.N ? p_i : a.N - 1;
+    int bead0 = (int)(UniformFromBits(rnd[2], rnd[3]) * pv.M);
+    bead0 = bead0 < pv.M ? bead0 : pv.M - 1;
+    double oldb[kMaxBisectBeads + 1][3], newb[kMaxBisectBeads + 1][3];
+    for (int j = 0; j <= nb; ++j) {
+        int bg = bead0 + j;
+        while (bg >= pv.M) bg -= pv.M;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const double x = a.R[PosIndex(pv, a.N, c, p_i, d, bg - pv.slice_lo)];
+            oldb[j][d] = x;
+            newb[j][d] = x;
+        }
+    }
+    uint32_t slot = 1;
+    bool alive = true;
+    double prev_change = 0., partial = 0., logu0 = 0.;
+    for (int level = a.n_level - 1; level >= 0; --level) {
+        const int skip = 1 << level;
+        const double level_tau = a.tau * skip;
+        const double sigma = sqrt(a.lambda * level_tau);
+        // FreeSpline(L, n_images = 0, lambda, 0.5 * tau * 2^level): log rho = -|r|^2 / (4 lambda (level_tau / 2))
+        const double i4lt_sample = 1. / (4. * a.lambda * (0.5 * level_tau));
+        const double i4lt_kin = 1. / (4. * a.lambda * level_tau);
+        double old_lp = 0., new_lp = 0.;
+        for (int ia = 0; ia < nb; ia += 2 * skip) {
+            const int ib = ia + skip, ic = ia + 2 * skip;
+            uint32_t r0[4], r1[4];
+            Philox4x32(a.attempt_lo, a.attempt_hi, (uint32_t)c, slot, a.seed_lo, a.seed_hi, r0);
+            Philox4x32(a.attempt_lo, a.attempt_hi, (uint32_t)c, slot + 1, a.seed_lo, a.seed_hi, r1);
+            slot += 2;
+            // Box-Muller: three of the four normals
+            const double ua = UniformFromBits(r0[0], r0[1]), ub = UniformFromBits(r0[2], r0[3]);
+            const double uc = UniformFromBits(r1[0], r1[1]), ud = UniformFromBits(r1[2], r1[3]);
+            const double ra = sqrt(-2. * log(ua)), rc = sqrt(-2. * log(uc));
+            double sb, cb, sd, cd;
+            sincospi(2. * ub, &sb, &cb);
+            sincospi(2. * ud, &sd, &cd);
+            const double nrm[3] = {ra * cb, ra * sb, rc * cd};
+            double d2_old = 0., d2_new = 0.;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                // RBar(bead_c, bead_a) = r_a + 0.5 * Dr(r_c, r_a)   (path_class.h:124)
+                const double rbar_old = oldb[ia][d] + 0.5 * PutInBox1(oldb[ic][d] - oldb[ia][d], pv.box);
+                const double del_old = PutInBox1(oldb[ib][d] - rbar_old, pv.box);
+                d2_old += del_old * del_old;
+                const double rbar_new = newb[ia][d] + 0.5 * PutInBox1(newb[ic][d] - newb[ia][d], pv.box);
+                const double del_new = PutInBox1(sigma * nrm[d], pv.box);
+                newb[ib][d] = rbar_new + del_new;
+                d2_new += del_new * del_new;
+            }
+            old_lp -= d2_old * i4lt_sample;
+            new_lp -= d2_new * i4lt_sample;
+        }
+        double old_kin = 0., new_kin = 0.;
+        if (a.with_kinetic) {  // Kinetic::GetAction (kinetic_class.h:105-122), n_images = 0
+            for (int ia = 0; ia < nb; ia += skip) {
+                double d2o = 0., d2n = 0.;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const double o = PutInBox1(oldb[ia][d] - oldb[ia + skip][d], pv.box);
+                    const double n = PutInBox1(newb[ia][d] - newb[ia + skip][d], pv.box);
+                    d2o += o * o;
+                    d2n += n * n;
+                }
+                old_kin += d2o * i4lt_kin;
+                new_kin += d2n * i4lt_kin;
+            }
+        }
+        uint32_t ru[4];
+        Philox4x32(a.attempt_lo, a.attempt_hi, (uint32_t)c, slot, a.seed_lo, a.seed_hi, ru);
+        slot += 1;
+        const double logu = log(UniformFromBits(ru[0], ru[1]));
+        const double lsr = -new_lp + old_lp;
+        const double change = new_kin - old_kin;
+        if (level > 0) {
+            const double log_accept = lsr - change + prev_change;
+            if (log_accept < logu) alive = false;
+            prev_change = change;
+        } else {
+            partial = lsr - change + prev_change;
+            logu0 = logu;
+        }
+    }
+    const int n_prop = nb - 1;
+    for (int j = 0; j < n_prop; ++j)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) a.P[((size_t)c * n_prop + j) * 3 + d] = alive ? newb[j + 1][d] : oldb[j + 1][d];
+    a.P_particle[c] = p_i;
+    int first = bead0 + 1;
+    if (first >= pv.M) first -= pv.M;
+    a.P_first[c] = first;
+    a.b0[c] = bead0;
+    a.partial[c] = partial;
+    a.logu0[c] = logu0;
+    a.alive[c] = alive ? 1 : 0;
+    a.pair_old[c] = 0.;
+    a.pair_new[c] = 0.;
+    a.lr_old[c] = 0.;
+    a.lr_new[c] = 0.;
+}
+
+struct WindowBothArgs {
+    PathView pv;
+    const double *R_moved;    // committed positions of the moved species
+    int N_moved;
+    const double *R_partner;  // committed positions of the partner species
+    int N_partner;
+    int same;                 // partner species == moved species (skip the moved particle itself)
+    const double *P;          // proposal [C][n_links-1][3]
+    const int32_t *P_particle;
+    const int32_t *b0;
+    const int32_t *alive;
+    int n_links;
+    // tables: fast Ilkka block (global memory) or the general blob
+    FastTable FT;
+    const unsigned char *fast_tables;
+    PairTable T;
+    const double *blob;
+    double *out_old, *out_new;  // [C], added to
+};
+
+constexpr int kWindowThreads = 256;
+
+/// One CTA per clone: thread t walks partner particles q = t, t + 256, ...; for each it evaluates
+/// the window's links in OLD and NEW positions of the moved particle.
+template <int ATYPE, bool FAST>
+__global__ void __launch_bounds__(kWindowThreads) pair_window_both_kernel(const WindowBothArgs a) {
+    __shared__ double pold[kMaxBisectBeads + 1][3], pnew[kMaxBisectBeads + 1][3];
+    __shared__ double red[2][kWindowThreads / 32];
+    const PathView &pv = a.pv;
+    const int c = blockIdx.x;
+    if (!a.alive[c]) return;  // rejected above level 0: the decision does not need the sums
+    const int p = a.P_particle[c], bead0 = a.b0[c], nl = a.n_links;
+    for (int t = threadIdx.x; t < (nl + 1) * 3; t += blockDim.x) {
+        const int j = t / 3, d = t - j * 3;
+        int bg = bead0 + j;
+        while (bg >= pv.M) bg -= pv.M;
+        const double x = a.R_moved[PosIndex(pv, a.N_moved, c, p, d, bg - pv.slice_lo)];
+        pold[j][d] = x;
+        pnew[j][d] = (j >= 1 && j < nl) ? a.P[((size_t)c * (nl - 1) + (j - 1)) * 3 + d] : x;
+    }
+    __syncthreads();
+    double acc_old = 0., acc_new = 0.;
+    for (int q = threadIdx.x; q < a.N_partner; q += blockDim.x) {
+        if (a.same && q == p) continue;
+        double q0[3], q1[3];
+        int bg = bead0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) q0[d] = a.R_partner[PosIndex(pv, a.N_partner, c, q, d, bg - pv.slice_lo)];
+        for (int j = 0; j < nl; ++j) {
+            int bn = bg + 1;
+            if (bn >= pv.M) bn -= pv.M;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) q1[d] = a.R_partner[PosIndex(pv, a.N_partner, c, q, d, bn - pv.slice_lo)];
+            double r, rp, s;
+            if (FAST) {
+                DrDrpDrrpFast(pold[j], q0, pold[j + 1], q1, pv.box, r, rp, s);
+                acc_old += FastIlkkaEval(a.fast_tables, a.FT, r, rp, s);
+                DrDrpDrrpFast(pnew[j], q0, pnew[j + 1], q1, pv.box, r, rp, s);
+                acc_new += FastIlkkaEval(a.fast_tables, a.FT, r, rp, s);
+            } else {
+                DrDrpDrrp(pold[j], q0, pold[j + 1], q1, pv.box, r, rp, s);
+                acc_old += PairEval<ATYPE, WHICH_U>(a.blob, a.T, r, rp, s);
+                DrDrpDrrp(pnew[j], q0, pnew[j + 1], q1, pv.box, r, rp, s);
+                acc_new += PairEval<ATYPE, WHICH_U>(a.blob, a.T, r, rp, s);
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) q0[d] = q1[d];
+            bg = bn;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc_old += __shfl_down_sync(0xffffffffu, acc_old, o);
+        acc_new += __shfl_down_sync(0xffffffffu, acc_new, o);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+        red[0][wid] = acc_old;
+        red[1][wid] = acc_new;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double to = 0., tn = 0.;
+        for (int i = 0; i < kWindowThreads / 32; ++i) {
+            to += red[0][i];
+            tn += red[1][i];
+        }
+        a.out_old[c] += to;
+        a.out_new[c] += tn;
+    }
+}
+
+/// Level-0 Metropolis test: log_accept = log_sample_ratio - (new_action - old_action) + previous change.
+__global__ void bisect_decide_kernel(int C, const int32_t *__restrict__ alive, const double *__restrict__ partial,
+                                     const double *__restrict__ logu0, const double *__restrict__ pair_old,
+                                     const double *__restrict__ pair_new, const double *__restrict__ lr_old,
+                                     const double *__restrict__ lr_new, int32_t *__restrict__ accept, int64_t *__restrict__ n_accept) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    int acc = 0;
+    if (alive[c]) {
+        const double old_action = pair_old[c] + lr_old[c], new_action = pair_new[c] + lr_new[c];
+        const double log_accept = partial[c] - (new_action - old_action);
+        acc = log_accept < logu0[c] ? 0 : 1;
+    }
+    accept[c] = acc;
+    n_accept[c] += acc;
+}
+
+}  // namespace pimc
+
+#endif  // SIMPIMC_B200_MC_CUH_

@@ -145,6 +145,13 @@ class Path:
         accept = np.ascontiguousarray(np.broadcast_to(accept, (self.n_clones,)), dtype=np.int32)
         capi.check(self.L.pimc_commit(self.h, _vp(accept)))
 
+    def BisectSweep(self, species, n_level, n_attempts, seed, attempt0=0, with_kinetic=True):
+        """n_attempts device-resident Bisect::DoEvent calls per clone; returns accepts per clone."""
+        n_accept = np.zeros(self.n_clones, dtype=np.int64)
+        capi.check(self.L.pimc_bisect_sweep(self.h, species, n_level, n_attempts, seed, attempt0, 1 if with_kinetic else 0,
+                                            _vp(n_accept)))
+        return n_accept
+
     def LaunchCount(self):
         return int(self.L.pimc_ctx_launch_count(self.h))
 

@@ -137,3 +137,80 @@ class DisplaceParticle(_Move):
         path.Commit(accept.astype(np.int32))
         self.n_accept += accept
         return accept
+
+
+def bisect_attempt_philox(cfg, species, n_level, seed, attempt, n_clones, get_beads, action_old_new, finish, with_kinetic=True):
+    """Host mirror of ONE device-resident bisection attempt (csrc/mc.cuh: bisect_sample_kernel +
+    pair_window_both_kernel + k-sums + bisect_decide_kernel) drawing the same Philox stream.
+
+    get_beads(c, p, bead0, n)            -> committed positions [n][3] of beads bead0.. of particle p
+    action_old_new(c, p, bead0, nb, new) -> (old_action, new_action) summed over the pair actions
+                                            that involve `species`, `new` = proposed beads 1..nb-1
+    finish(c, p, bead0, nb, accept)      -> Move::Accept / Reject
+    Returns (particle[c], bead0[c], accept[c]).
+    """
+    from . import philox as PX
+    sp = cfg.species[species]
+    N, M, lam, tau, L, pbc = sp.n_part, cfg.n_bead, sp.lam, cfg.tau, cfg.L, cfg.pbc
+    nb = 1 << n_level
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    a_lo, a_hi = attempt & 0xFFFFFFFF, (attempt >> 32) & 0xFFFFFFFF
+    out_p, out_b, out_acc = [], [], []
+
+    def pib(d):
+        return _put_in_box(d, L, pbc)
+
+    for c in range(n_clones):
+        r = PX.philox4x32(a_lo, a_hi, c, 0, k0, k1)
+        p_i = min(int(PX.uniform_from_bits(r[0], r[1]) * N), N - 1)
+        bead0 = min(int(PX.uniform_from_bits(r[2], r[3]) * M), M - 1)
+        old = np.array(get_beads(c, p_i, bead0, nb + 1), dtype=np.float64)
+        new = old.copy()
+        slot, alive, prev_change, partial, logu0 = 1, True, 0.0, 0.0, 0.0
+        for level in range(n_level - 1, -1, -1):
+            skip = 1 << level
+            level_tau = tau * skip
+            sigma = math.sqrt(lam * level_tau)
+            i4s, i4k = 1.0 / (4.0 * lam * (0.5 * level_tau)), 1.0 / (4.0 * lam * level_tau)
+            old_lp = new_lp = 0.0
+            for ia in range(0, nb, 2 * skip):
+                ib, ic = ia + skip, ia + 2 * skip
+                r0 = PX.philox4x32(a_lo, a_hi, c, slot, k0, k1)
+                r1 = PX.philox4x32(a_lo, a_hi, c, slot + 1, k0, k1)
+                slot += 2
+                ua, ub = PX.uniform_from_bits(r0[0], r0[1]), PX.uniform_from_bits(r0[2], r0[3])
+                uc, ud = PX.uniform_from_bits(r1[0], r1[1]), PX.uniform_from_bits(r1[2], r1[3])
+                ra, rc = math.sqrt(-2.0 * math.log(ua)), math.sqrt(-2.0 * math.log(uc))
+                nrm = np.array([ra * math.cos(2 * math.pi * ub), ra * math.sin(2 * math.pi * ub), rc * math.cos(2 * math.pi * ud)])
+                rbar_old = old[ia] + 0.5 * pib(old[ic] - old[ia])
+                del_old = pib(old[ib] - rbar_old)
+                rbar_new = new[ia] + 0.5 * pib(new[ic] - new[ia])
+                del_new = pib(sigma * nrm)
+                new[ib] = rbar_new + del_new
+                old_lp -= float(np.sum(del_old * del_old)) * i4s
+                new_lp -= float(np.sum(del_new * del_new)) * i4s
+            old_kin = new_kin = 0.0
+            if with_kinetic:
+                for ia in range(0, nb, skip):
+                    o, n_ = pib(old[ia] - old[ia + skip]), pib(new[ia] - new[ia + skip])
+                    old_kin += float(np.sum(o * o)) * i4k
+                    new_kin += float(np.sum(n_ * n_)) * i4k
+            ru = PX.philox4x32(a_lo, a_hi, c, slot, k0, k1)
+            slot += 1
+            logu = math.log(PX.uniform_from_bits(ru[0], ru[1]))
+            lsr, change = -new_lp + old_lp, new_kin - old_kin
+            if level > 0:
+                if lsr - change + prev_change < logu:
+                    alive = False
+                prev_change = change
+            else:
+                partial, logu0 = lsr - change + prev_change, logu
+        accept = False
+        if alive:
+            old_a, new_a = action_old_new(c, p_i, bead0, nb, new[1:nb])
+            accept = not (partial - (new_a - old_a) < logu0)
+        finish(c, p_i, bead0, nb, accept, new[1:nb] if alive else None)
+        out_p.append(p_i)
+        out_b.append(bead0)
+        out_acc.append(accept)
+    return np.array(out_p), np.array(out_b), np.array(out_acc)

@@ -55,3 +55,15 @@ def test_config_struct_layout_matches_header():
     assert capi.Config.L.offset == 8 and capi.Config.n_part.offset == 32 and capi.Config.slice_lo.offset == 56
     assert ctypes.sizeof(capi.Table1D) == 24 and ctypes.sizeof(capi.Table2D) == 32
     assert ctypes.sizeof(capi.LongRange) == 24 + 8 + 8 + 8 + 8 + 8
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10: the host mirror of the device stream."""
+    from simpimc_b200 import philox as P
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, out in kat:
+        assert tuple(int(x) for x in P.philox4x32(*ctr, *key)) == out
+    u = P.uniform_from_bits(0, 0), P.uniform_from_bits(0xffffffff, 0xffffffff)
+    assert 0.0 < u[0] < u[1] <= 1.0  # never 0: log(u) is finite

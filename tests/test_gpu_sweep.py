@@ -1,0 +1,137 @@
+"""Device-resident bisection moves (pimc_bisect_sweep, csrc/mc.cuh).
+
+(1) Exact stream parity: the host mirror simpimc_b200.moves.bisect_attempt_philox draws the
+    same Philox numbers and takes its pair-action values from the CPU oracle; after every
+    attempt the device walkers must sit at the same positions (1e-12) with the same
+    accept/reject history.
+(2) Statistical parity with the REFERENCE program (oracle/_ref: the reference's own Bisect,
+    Kinetic and IlkkaPairAction, std::mt19937): thermal energy within combined error bars.
+"""
+import numpy as np
+import pytest
+
+from simpimc_b200 import system as S
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["ueg", "plasma", "nolr"])
+def test_device_sweep_follows_the_host_mirror_of_its_stream(name):
+    from simpimc_b200 import host, moves
+    from oracle import oracle as O
+    if name == "ueg":
+        cfg, n_level = S.ueg_config(N=9, M=16), 3
+    elif name == "nolr":
+        cfg, n_level = S.ueg_config(N=6, M=8, use_long_range=False), 2
+    else:
+        cfg, n_level = S.plasma_config(Ne=5, Np=4, M=8), 2
+    C = 3
+    path = host.Path(cfg, n_clones=C)
+    oracles = []
+    for c in range(C):
+        o = O.Oracle(cfg)
+        oracles.append(o)
+    for sp in range(len(cfg.species)):
+        R = np.stack([S.synthetic_paths(cfg, sp, c, 99) for c in range(C)])
+        path.SetPositions(sp, R)
+        for c in range(C):
+            oracles[c].set_positions(sp, R[c])
+    seed = 0x1234567800000042
+    M = cfg.n_bead
+    n_acc_dev = np.zeros(C, dtype=np.int64)
+    n_acc_host = np.zeros(C, dtype=np.int64)
+    for attempt in range(40):
+        sp = attempt % len(cfg.species)
+        acts = [ai for ai, a in enumerate(cfg.actions) if cfg.species[sp].name in (a.species_a, a.species_b)]
+
+        def get_beads(c, p, b0, n):
+            return oracles[c].get_positions(sp, 0)[p, (b0 + np.arange(n)) % M]
+
+        def action_old_new(c, p, b0, nb, new):
+            oracles[c].propose(sp, p, (b0 + 1) % M, new)
+            old = sum(oracles[c].get_action(ai, 0, b0, b0 + nb, [(sp, p)], 0) for ai in acts)
+            nw = sum(oracles[c].get_action(ai, 1, b0, b0 + nb, [(sp, p)], 0) for ai in acts)
+            return old, nw
+
+        def finish(c, p, b0, nb, accept, new):
+            if new is not None:
+                oracles[c].finish_move(sp, p, b0, b0 + nb, bool(accept))
+
+        _, _, acc = moves.bisect_attempt_philox(cfg, sp, n_level, seed, attempt, C, get_beads, action_old_new, finish)
+        n_acc_host += acc
+        n_acc_dev += path.BisectSweep(sp, n_level, 1, seed, attempt0=attempt)
+        got = path.GetPositions(sp)
+        for c in range(C):
+            ref = oracles[c].get_positions(sp, 0)
+            assert np.max(np.abs(got[c] - ref)) <= 1e-12 * max(1.0, np.max(np.abs(ref))), (name, attempt, c)
+        assert np.array_equal(n_acc_dev, n_acc_host), (name, attempt, n_acc_dev, n_acc_host)
+    assert n_acc_dev.sum() > 0
+    # rho_k was carried along incrementally on the device: compare with a rebuild by the oracle
+    if path._n_k():
+        for sp in range(len(cfg.species)):
+            for c in range(C):
+                assert np.max(np.abs(path.GetRhoK(sp, c, host.OLD_MODE) - oracles[c].rhok(sp, 0))) <= 1e-10 * cfg.species[sp].n_part
+    for ai, act in enumerate(path.actions):
+        du = act.DActionDBeta()
+        for c in range(C):
+            ref = oracles[c].dbeta(ai)
+            assert abs(du[c] - ref) <= 1e-10 * abs(ref)
+    path.close()
+
+
+def _mean_err(x):
+    """scripts/Stats.cpp:42-87: mean, autocorrelation time kappa = 1 + 2 sum_{t: C(t) > 0} C(t), error."""
+    x = np.asarray(x, dtype=np.float64)
+    n = len(x)
+    m, var = x.mean(), x.var()
+    if var == 0:
+        return m, 0.0
+    kappa = 1.0
+    for t in range(1, n // 2):
+        ct = np.mean((x[:n - t] - m) * (x[t:] - m)) / var
+        if ct <= 0:
+            break
+        kappa += 2.0 * ct
+    return m, np.sqrt(var * kappa / n)
+
+
+def test_sampled_energy_matches_the_reference_program():
+    from oracle import refsim
+    if not refsim.available():
+        pytest.skip("oracle/_ref not built")
+    from simpimc_b200 import host
+    cfg = S.ueg_config(N=4, M=8, with_kinetic=True, n_xy=60, n_r_long=400)
+    n_level = 2
+    cfg.moves = [{"name": "BisectE", "type": "Bisect", "species": "e", "n_level": n_level}]
+    cfg.observables = []
+    attempts_per_sweep = 4 * 8 // (1 << n_level)
+    # reference: one walker, its own Bisect + Kinetic + IlkkaPairAction, std::mt19937
+    sim = refsim.RefSim(cfg, seed=11)
+    R0 = S.synthetic_paths(cfg, 0, 0, 5)
+    sim.set_positions(0, R0)
+    sim.move_do(0, 400 * attempts_per_sweep)
+    ref_series = []
+    for _ in range(3000):
+        sim.move_do(0, attempts_per_sweep)
+        ref_series.append(sim.dbeta(1) / cfg.n_bead)   # pair-action part of the thermal energy
+    sim.close()
+    # device: 256 walkers, Philox
+    C = 256
+    gcfg = S.ueg_config(N=4, M=8, n_xy=60, n_r_long=400)
+    path = host.Path(gcfg, n_clones=C)
+    path.SetPositions(0, np.stack([S.synthetic_paths(gcfg, 0, c, 5) for c in range(C)]))
+    act = path.actions[0]
+    att = 0
+    path.BisectSweep(0, n_level, 200 * attempts_per_sweep, 7, attempt0=att)
+    att += 200 * attempts_per_sweep
+    blocks = []
+    for _ in range(40):
+        path.BisectSweep(0, n_level, 5 * attempts_per_sweep, 7, attempt0=att)
+        att += 5 * attempts_per_sweep
+        blocks.append(act.DActionDBeta() / gcfg.n_bead)
+    path.close()
+    per_clone = np.mean(np.array(blocks), axis=0)          # independent walkers
+    g_mean, g_err = per_clone.mean(), per_clone.std(ddof=1) / np.sqrt(C)
+    r_mean, r_err = _mean_err(ref_series)
+    assert abs(g_mean - r_mean) <= 4.0 * np.hypot(g_err, r_err), (g_mean, g_err, r_mean, r_err)
+    assert g_err < 0.05 * abs(r_mean) and r_err < 0.05 * abs(r_mean)
