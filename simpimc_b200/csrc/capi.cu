@@ -1441,9 +1441,11 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
             w.out_new = pair_new;
             {
                 ScopedKernelTimer t(ctx, PIMC_KERNEL_PAIR_WINDOW);
-                if (a->atype == ATYPE_ILKKA && a->fast_ok[WHICH_U] && !ctx->force_general)
-                    pair_window_both_kernel<ATYPE_ILKKA, true><<<C, kWindowThreads, 0, ctx->stream>>>(w);
-                else if (a->atype == ATYPE_ILKKA)
+                if (a->atype == ATYPE_ILKKA && a->fast_ok[WHICH_U] && !ctx->force_general) {
+                    const size_t smem = (size_t)w.FT.n_bytes;
+                    PIMC_CUDA(cudaFuncSetAttribute(pair_window_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    pair_window_fast_kernel<<<std::min(C, ctx->n_sm), kWinFastThreads, smem, ctx->stream>>>(w);
+                } else if (a->atype == ATYPE_ILKKA)
                     pair_window_both_kernel<ATYPE_ILKKA, false><<<C, kWindowThreads, 0, ctx->stream>>>(w);
                 else if (a->atype == ATYPE_BARE)
                     pair_window_both_kernel<ATYPE_BARE, false><<<C, kWindowThreads, 0, ctx->stream>>>(w);
@@ -1453,45 +1455,38 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
             ctx->launches++;
         }
         if (any_lr) {
-            SpeciesView sv = ctx->SView(s, false);
-            sv.n_prop = n_prop;  // the proposal the sample kernel has just written
-            const int tl = 2 * ctx->max_index + 1;
-            rhok_delta_kernel<<<GridFor(ctx, C * nb), 256, (size_t)6 * tl * sizeof(double2), ctx->stream>>>(pv, sv, ctx->KView(), b0, nb,
-                                                                                                          st.drho.p);
-            ctx->launches++;
+            LrWindowArgs l;
+            l.pv = pv;
+            l.sv = ctx->SView(s, false);
+            l.sv.n_prop = n_prop;  // the proposal the sample kernel has just written
+            l.ks = ctx->KView();
+            l.b0 = b0;
+            l.n_window = nb;
+            l.rho_self = st.rho.p;
+            l.drho = st.drho.p;
+            l.lr_old = lr_old;
+            l.lr_new = lr_new;
+            l.n_actions = 0;
             for (pimc_action *a : acts) {
                 if (!(a->use_long_range && n_k > 0)) continue;
-                for (int mode = 0; mode < 2; ++mode) {
-                    KSumArgs k;
-                    k.pv = pv;
-                    k.n_k = n_k;
-                    k.rho_a = ctx->species[a->sa]->rho.p;
-                    k.rho_b = ctx->species[a->sb]->rho.p;
-                    k.drho_a = (mode && a->sa == s) ? st.drho.p : nullptr;
-                    k.drho_b = (mode && a->sb == s) ? st.drho.p : nullptr;
-                    k.wk = a->wk[WHICH_U].p;
-                    k.b0 = b0;
-                    k.n_window = nb;
-                    k.twice = a->sa != a->sb;
-                    k.scale = a->ulong_scale;
-                    k.accumulate = 1;
-                    k.out = mode ? lr_new : lr_old;
-                    ScopedKernelTimer t(ctx, PIMC_KERNEL_KSUM);
-                    ksum_kernel<<<C, 256, 0, ctx->stream>>>(k);
-                    ctx->launches++;
-                }
+                if (l.n_actions == kMaxLrActions) return Fail(PIMC_ERR_UNSUPPORTED, "more than 4 long-range actions on one species");
+                const int partner = (a->sa == s) ? a->sb : a->sa;
+                l.rho_other[l.n_actions] = (partner == s) ? nullptr : ctx->species[partner]->rho.p;
+                l.wk[l.n_actions] = a->wk[WHICH_U].p;
+                l.factor[l.n_actions] = a->ulong_scale * (partner == s ? 1.0 : 2.0);
+                l.n_actions++;
             }
-        }
-        bisect_decide_kernel<<<(C + 127) / 128, 128, 0, ctx->stream>>>(C, alive, partial, logu0, pair_old, pair_new, lr_old, lr_new, accept,
-                                                                       (int64_t *)ctx->mc_naccept.p);
-        ctx->launches++;
-        commit_positions_kernel<<<C, 64, 0, ctx->stream>>>(pv, st.N, st.P.p, st.P_particle.p, st.P_first.p, n_prop, accept, st.R.p);
-        ctx->launches++;
-        if (any_lr) {
-            dim3 grid((nb * n_k + 255) / 256, C);
-            commit_rhok_kernel<<<grid, 256, 0, ctx->stream>>>(pv, n_k, st.drho.p, b0, nb, accept, st.rho.p);
+            const int tl = 2 * ctx->max_index + 1;
+            {
+                ScopedKernelTimer t(ctx, PIMC_KERNEL_KSUM);
+                lr_window_kernel<<<C, 256, (size_t)6 * tl * sizeof(double2), ctx->stream>>>(l);
+            }
             ctx->launches++;
         }
+        bisect_decide_commit_kernel<<<C, 256, 0, ctx->stream>>>(pv, st.N, n_k, nb, alive, partial, logu0, pair_old, pair_new, lr_old, lr_new,
+                                                               st.P.p, st.P_particle.p, b0, any_lr ? st.drho.p : nullptr, st.R.p,
+                                                               any_lr ? st.rho.p : nullptr, accept, ctx->mc_naccept.p);
+        ctx->launches++;
     }
     PIMC_CUDA(cudaGetLastError());
     st.n_prop = 0;

@@ -302,6 +302,211 @@ __global__ void bisect_decide_kernel(int C, const int32_t *__restrict__ alive, c
     n_accept[c] += acc;
 }
 
+// ---------------------------------------------------------------- staged window kernel
+constexpr int kWinFastThreads = 1024;
+
+/// Same sums as pair_window_both_kernel<ILKKA, fast> with the fast tables staged in shared
+/// memory: persistent CTAs (one per SM) walk the clones; inside a clone, n_links consecutive
+/// lanes own the links of one (moved particle, partner) pair -- the quarter-warp granularity at
+/// which LDS.128 is served -- and the 1024 / n_links pair slots walk the partner particles.
+__global__ void __launch_bounds__(kWinFastThreads, 1) pair_window_fast_kernel(const WindowBothArgs a) {
+    extern __shared__ __align__(16) unsigned char wsm[];
+    __shared__ double pold[kMaxBisectBeads + 1][3], pnew[kMaxBisectBeads + 1][3];
+    __shared__ double red[2][kWinFastThreads / 32];
+    const int tid = threadIdx.x;
+    {
+        const int4 *src = reinterpret_cast<const int4 *>(a.fast_tables);
+        int4 *dst = reinterpret_cast<int4 *>(wsm);
+        for (int i = tid; i < a.FT.n_bytes / 16; i += kWinFastThreads) dst[i] = src[i];
+    }
+    const PathView &pv = a.pv;
+    const int nl = a.n_links;
+    const int j = tid & (nl - 1), slot = tid / nl, n_slots = kWinFastThreads / nl;
+    for (int c = blockIdx.x; c < pv.C; c += gridDim.x) {
+        __syncthreads();  // tables staged / previous clone's pold, pnew, red consumed
+        if (!a.alive[c]) continue;
+        const int p = a.P_particle[c], bead0 = a.b0[c];
+        for (int t = tid; t < (nl + 1) * 3; t += kWinFastThreads) {
+            const int jj = t / 3, d = t - jj * 3;
+            int bg = bead0 + jj;
+            while (bg >= pv.M) bg -= pv.M;
+            const double x = a.R_moved[PosIndex(pv, a.N_moved, c, p, d, bg - pv.slice_lo)];
+            pold[jj][d] = x;
+            pnew[jj][d] = (jj >= 1 && jj < nl) ? a.P[((size_t)c * (nl - 1) + (jj - 1)) * 3 + d] : x;
+        }
+        __syncthreads();
+        int b0s = bead0 + j, b1s = bead0 + j + 1;
+        while (b0s >= pv.M) b0s -= pv.M;
+        while (b1s >= pv.M) b1s -= pv.M;
+        // OLD pass, then NEW pass: one set of moved-particle positions in registers at a time
+        double acc_old = 0., acc_new = 0.;
+#pragma unroll 1
+        for (int mode = 0; mode < 2; ++mode) {
+            const double(*pp)[3] = mode ? pnew : pold;
+            const double p0[3] = {pp[j][0], pp[j][1], pp[j][2]}, p1[3] = {pp[j + 1][0], pp[j + 1][1], pp[j + 1][2]};
+            double acc = 0.;
+            for (int q = slot; q < a.N_partner; q += n_slots) {
+                if (a.same && q == p) continue;
+                double q0[3], q1[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    q0[d] = a.R_partner[PosIndex(pv, a.N_partner, c, q, d, b0s - pv.slice_lo)];
+                    q1[d] = a.R_partner[PosIndex(pv, a.N_partner, c, q, d, b1s - pv.slice_lo)];
+                }
+                double r, rp, s;
+                DrDrpDrrpFast(p0, q0, p1, q1, pv.box, r, rp, s);
+                acc += FastIlkkaEval(wsm, a.FT, r, rp, s);
+            }
+            if (mode)
+                acc_new = acc;
+            else
+                acc_old = acc;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc_old += __shfl_down_sync(0xffffffffu, acc_old, o);
+            acc_new += __shfl_down_sync(0xffffffffu, acc_new, o);
+        }
+        if ((tid & 31) == 0) {
+            red[0][tid >> 5] = acc_old;
+            red[1][tid >> 5] = acc_new;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double to = 0., tn = 0.;
+            for (int i = 0; i < kWinFastThreads / 32; ++i) {
+                to += red[0][i];
+                tn += red[1][i];
+            }
+            a.out_old[c] += to;
+            a.out_new[c] += tn;
+        }
+    }
+}
+
+// ------------------------------------------------------------ long-range part of a window
+constexpr int kMaxLrActions = 4;
+struct LrWindowArgs {
+    PathView pv;
+    SpeciesView sv;          // moved species with the pending proposal
+    KSpaceView ks;
+    const int32_t *b0;
+    int n_window;
+    const double2 *rho_self;  // committed rho_k of the moved species
+    double2 *drho;            // [C][n_window][n_k] out
+    int n_actions;
+    const double2 *rho_other[kMaxLrActions];  // partner species' rho_k (nullptr: same species)
+    const double *wk[kMaxLrActions];
+    double factor[kMaxLrActions];             // scale * (2 if the species differ)
+    double *lr_old, *lr_new;                  // [C], overwritten
+};
+
+/// Species::UpdateRhoK for the proposal (species_class.h:406-425) fused with CalcULong over the
+/// window in OLD and NEW mode (ilkka_pair_action_class.h:104-122) for every long-range action
+/// that involves the moved species.  One CTA per clone, thread per k vector.
+__global__ void __launch_bounds__(256) lr_window_kernel(const LrWindowArgs a) {
+    extern __shared__ __align__(16) double2 ptab[];  // [2][3][2m+1]
+    __shared__ double red[2][256 / 32];
+    const PathView &pv = a.pv;
+    const int c = blockIdx.x, tid = threadIdx.x;
+    const int tl = 2 * a.ks.max_index + 1, n_k = a.ks.n_k;
+    const int p = a.sv.P_particle[c];
+    double acc_old = 0., acc_new = 0.;
+    for (int j = 0; j < a.n_window; ++j) {
+        int bg = a.b0[c] + j;
+        if (bg >= pv.M) bg -= pv.M;
+        __syncthreads();
+        if (tid < 6) {
+            const int mode = tid / 3, d = tid - mode * 3;
+            double r[3];
+            LoadPos(pv, a.sv, c, p, bg, mode, r);
+            PhaseTable(r[d], a.ks.kbox, a.ks.max_index, ptab + (size_t)(mode * 3 + d) * tl);
+        }
+        __syncthreads();
+        for (int k = tid; k < n_k; k += blockDim.x) {
+            const int i0 = a.ks.kidx[3 * k], i1 = a.ks.kidx[3 * k + 1], i2 = a.ks.kidx[3 * k + 2];
+            const double2 fo = CMul(CMul(ptab[i0], ptab[tl + i1]), ptab[2 * tl + i2]);
+            const double2 *tn = ptab + 3 * tl;
+            const double2 fn = CMul(CMul(tn[i0], tn[tl + i1]), tn[2 * tl + i2]);
+            const double2 d = make_double2(fn.x - fo.x, fn.y - fo.y);
+            a.drho[((size_t)c * a.n_window + j) * n_k + k] = d;
+            const size_t ri = ((size_t)c * pv.Mloc + (bg - pv.slice_lo)) * n_k + k;
+            const double2 rs = a.rho_self[ri];
+            const double2 rn = make_double2(rs.x + d.x, rs.y + d.y);
+            for (int t = 0; t < a.n_actions; ++t) {
+                const double w = a.wk[t][k] * a.factor[t];
+                if (a.rho_other[t]) {
+                    const double2 ro = a.rho_other[t][ri];
+                    acc_old += w * (rs.x * ro.x + rs.y * ro.y);
+                    acc_new += w * (rn.x * ro.x + rn.y * ro.y);
+                } else {
+                    acc_old += w * (rs.x * rs.x + rs.y * rs.y);
+                    acc_new += w * (rn.x * rn.x + rn.y * rn.y);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc_old += __shfl_down_sync(0xffffffffu, acc_old, o);
+        acc_new += __shfl_down_sync(0xffffffffu, acc_new, o);
+    }
+    if ((tid & 31) == 0) {
+        red[0][tid >> 5] = acc_old;
+        red[1][tid >> 5] = acc_new;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double to = 0., tn = 0.;
+        for (int i = 0; i < 256 / 32; ++i) {
+            to += red[0][i];
+            tn += red[1][i];
+        }
+        a.lr_old[c] = to;
+        a.lr_new[c] = tn;
+    }
+}
+
+/// bisect_decide_kernel + Move::Accept in one launch: one CTA per clone.
+__global__ void __launch_bounds__(256) bisect_decide_commit_kernel(PathView pv, int N, int n_k, int n_window, const int32_t *__restrict__ alive,
+                                                                   const double *__restrict__ partial, const double *__restrict__ logu0,
+                                                                   const double *__restrict__ pair_old, const double *__restrict__ pair_new,
+                                                                   const double *__restrict__ lr_old, const double *__restrict__ lr_new,
+                                                                   const double *__restrict__ P, const int32_t *__restrict__ P_particle,
+                                                                   const int32_t *__restrict__ b0, const double2 *__restrict__ drho,
+                                                                   double *__restrict__ R, double2 *__restrict__ rho,
+                                                                   int32_t *__restrict__ accept, long long *__restrict__ n_accept) {
+    const int c = blockIdx.x;
+    int acc = 0;
+    if (alive[c]) {
+        const double old_action = pair_old[c] + lr_old[c], new_action = pair_new[c] + lr_new[c];
+        acc = (partial[c] - (new_action - old_action)) < logu0[c] ? 0 : 1;
+    }
+    if (threadIdx.x == 0) {
+        accept[c] = acc;
+        n_accept[c] += acc;
+    }
+    if (!acc) return;
+    const int p = P_particle[c], bead0 = b0[c], n_prop = n_window - 1;
+    for (int t = threadIdx.x; t < n_prop * 3; t += blockDim.x) {
+        const int j = t / 3, d = t - j * 3;
+        int bg = bead0 + 1 + j;
+        while (bg >= pv.M) bg -= pv.M;
+        R[PosIndex(pv, N, c, p, d, bg - pv.slice_lo)] = P[((size_t)c * n_prop + j) * 3 + d];
+    }
+    if (drho) {
+        for (int t = threadIdx.x; t < n_window * n_k; t += blockDim.x) {
+            const int j = t / n_k, k = t - j * n_k;
+            int bg = bead0 + j;
+            if (bg >= pv.M) bg -= pv.M;
+            double2 *dst = rho + ((size_t)c * pv.Mloc + (bg - pv.slice_lo)) * n_k + k;
+            const double2 d = drho[((size_t)c * n_window + j) * n_k + k];
+            dst->x += d.x;
+            dst->y += d.y;
+        }
+    }
+}
+
 }  // namespace pimc
 
 #endif  // SIMPIMC_B200_MC_CUH_
