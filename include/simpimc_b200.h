@@ -139,6 +139,13 @@ int pimc_positions_download(pimc_ctx *ctx, int32_t species, int32_t mode, int32_
 int pimc_positions_set_device(pimc_ctx *ctx, int32_t species, const double *d_R);
 double *pimc_positions_device_ptr(pimc_ctx *ctx, int32_t species);
 int pimc_rhok_rebuild(pimc_ctx *ctx, int32_t species); /* Species::InitRhoK */
+/* Slice-shard halo (no reference counterpart; the reference never splits a path): pack the
+ * FIRST owned slice of every clone and particle into d_buf[clone][particle][dim] (device
+ * memory) for the rank that owns the preceding shard, and store a received buffer into the
+ * halo slot that follows the last owned slice.  The exchange itself is the caller's
+ * (ncclSend/ncclRecv on the context's stream; simpimc_b200/sharded.py). */
+int pimc_halo_pack(pimc_ctx *ctx, int32_t species, double *d_buf);
+int pimc_halo_unpack(pimc_ctx *ctx, int32_t species, const double *d_buf);
 /* rho_k of one clone, out[bead][n_k][2] (re, im) (Species::GetRhoK, species_class.h:428). */
 int pimc_rhok_download(pimc_ctx *ctx, int32_t species, int32_t mode, int32_t clone, double *out);
 

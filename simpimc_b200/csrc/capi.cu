@@ -844,6 +844,31 @@ double *pimc_positions_device_ptr(pimc_ctx *ctx, int32_t s) {
     return ctx->species[s]->R.p;
 }
 
+int pimc_halo_pack(pimc_ctx *ctx, int32_t s, double *d_buf) {
+    if (!ctx || !d_buf) return Fail(PIMC_ERR_INVALID, "null argument");
+    if (s < 0 || s >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    SpeciesState &st = *ctx->species[s];
+    const size_t n_rows = (size_t)ctx->C * st.N * 3;
+    halo_pack_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, ctx->stream>>>(st.R.p, n_rows, ctx->Ms, 0, d_buf);
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    return PIMC_OK;
+}
+
+int pimc_halo_unpack(pimc_ctx *ctx, int32_t s, const double *d_buf) {
+    if (!ctx || !d_buf) return Fail(PIMC_ERR_INVALID, "null argument");
+    if (s < 0 || s >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
+    if (!ctx->sharded) return Fail(PIMC_ERR_INVALID, "an unsharded context has no halo slice");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    SpeciesState &st = *ctx->species[s];
+    const size_t n_rows = (size_t)ctx->C * st.N * 3;
+    halo_unpack_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, ctx->stream>>>(st.R.p, n_rows, ctx->Ms, ctx->Mloc, d_buf);
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    return PIMC_OK;
+}
+
 int pimc_rhok_rebuild(pimc_ctx *ctx, int32_t s) {
     if (!ctx) return Fail(PIMC_ERR_INVALID, "null context");
     if (s < 0 || s >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");

@@ -573,6 +573,16 @@ __global__ void commit_rhok_kernel(PathView pv, int n_k, const double2 *__restri
     dst->y += d.y;
 }
 
+/// Slice-shard halo: buf[clone][particle][dim] <-> one stored slice of the position array.
+__global__ void halo_pack_kernel(const double *__restrict__ R, size_t n_rows, int Ms, int slot, double *__restrict__ buf) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n_rows) buf[i] = R[i * Ms + slot];
+}
+__global__ void halo_unpack_kernel(double *__restrict__ R, size_t n_rows, int Ms, int slot, const double *__restrict__ buf) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n_rows) R[i * Ms + slot] = buf[i];
+}
+
 /// Dependent-FMA chains: FP64 pipe throughput (2 flop per FMA).
 __global__ void fp64_peak_kernel(double *out, int iters) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1., a2 = a0 + 2., a3 = a0 + 3., a4 = a0 + 4., a5 = a0 + 5., a6 = a0 + 6., a7 = a0 + 7.;
