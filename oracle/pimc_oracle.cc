@@ -210,6 +210,7 @@ struct World {  // src/data_structures/path_class.h:8-23
 
     // KSpace::CalcC + Bead::CalcRhoK (k_space_class.h:83-94, bead_class.h:125-133)
     void BeadRhoK(const double *r, cplx *out) const {
+        if (ks.n_k() == 0) return;  // no k vectors (open boundary, or cutoff at its default): nothing to fill
         std::vector<std::vector<cplx>> c_k(n_d);
         for (int d = 0; d < n_d; d++) {
             const int mx = ks.max_index[d];

@@ -129,3 +129,53 @@ def synthetic_paths(cfg, sp, clone, seed=12345):
         if i == sp:
             out = np.ascontiguousarray(R)
     return out
+
+
+def egas_config(N=7, M=1280, n_xy=100, n_r_long=1000):
+    """inputs/e-gas/e-gas.xml (BASELINE config C1): N polarized electrons at r_s = 1, theta = 0.1
+    (beta = 3.42075, L = 3.08363 and k_cut = 14/(L/2) = 9.08021 for the shipped N = 7), M = 1280,
+    one IlkkaPairAction with long range."""
+    return ueg_config(N=N, M=M, rs=1.0, theta=0.1, n_xy=n_xy, n_r_long=n_r_long)
+
+
+def hatom_config(M=320, n_xy=100):
+    """inputs/h-atom/h-ilkka.xml (config C2): one electron and one classical proton (lambda = 0),
+    no periodic box, beta = 40, an e-p IlkkaPairAction without long range."""
+    beta = 40.0
+    cfg = SystemConfig(n_d=3, n_bead=M, beta=beta, L=1000.0, pbc=False, k_cut=None)
+    cfg.species.append(SpeciesConfig("e", 1, 0.5))
+    cfg.species.append(SpeciesConfig("p", 1, 0.0))
+    tab = T.make_ilkka_table(-1.0, beta / M, 10.0, 1.0, use_long_range=False, n_xy=n_xy, sigma=0.4)
+    cfg.actions.append(ActionConfig("Coulomb", "IlkkaPairAction", "e", "p", table=tab, max_level=0, use_long_range=False))
+    return cfg
+
+
+def hatom_paths(cfg, clone, seed=12345):
+    """Proton at rest at the origin on every slice, electron on a closed bridge around it."""
+    rng = np.random.default_rng(seed + clone)
+    M = cfg.n_bead
+    steps = rng.normal(0.0, math.sqrt(2.0 * 0.5 * cfg.tau), size=(1, M, 3))
+    walk = np.cumsum(steps, axis=1)
+    frac = (np.arange(1, M + 1) / M).reshape(1, M, 1)
+    e = walk - frac * walk[:, -1:, :] + rng.normal(0.0, 0.7, size=(1, 1, 3))
+    p = np.zeros((1, M, 3))
+    return [np.ascontiguousarray(e), p]
+
+
+def carbon_config(n_xy=60, n_r_long=400):
+    """inputs/C/c.xml (config C4): 10 e-up + 10 e-down + 20 p + 1 C in a periodic box, M = 16,
+    nine IlkkaPairActions and one BarePairAction (C-C, a one-particle species: constant), all
+    with long range."""
+    M, beta, L, k_cut = 16, 0.031577464, 1.53327785176, 18.2615303337
+    tau = beta / M
+    cfg = SystemConfig(n_d=3, n_bead=M, beta=beta, L=L, pbc=True, k_cut=k_cut)
+    for name, n, lam in (("eU", 10, 0.5), ("eD", 10, 0.5), ("p", 20, 0.00027216030018605583), ("C", 1, 0.000022857496211250974)):
+        cfg.species.append(SpeciesConfig(name, n, lam))
+    charge = {"eU": -1.0, "eD": -1.0, "p": 1.0, "C": 6.0}
+    pairs = [("eU", "eU"), ("eU", "eD"), ("eD", "eD"), ("eU", "p"), ("eD", "p"), ("eU", "C"), ("eD", "C"), ("p", "p"), ("p", "C")]
+    for a, b in pairs:
+        tab = T.make_ilkka_table(charge[a] * charge[b], tau, L, k_cut, n_xy=n_xy, xy_r_max=20.0, n_r_long=n_r_long, sigma=0.15)
+        cfg.actions.append(ActionConfig("Coulomb" + a + b, "IlkkaPairAction", a, b, table=tab, max_level=0, use_long_range=True, k_cut=k_cut))
+    cfg.actions.append(ActionConfig("CoulombCC", "BarePairAction", "C", "C", max_level=0, use_long_range=True, k_cut=k_cut,
+                                    table=T.make_bare_table(36.0, L, k_cut, n_r_long=n_r_long)))
+    return cfg
