@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libsimpimc_b200.so")
+# SIMPIMC_B200_LIB selects another build of the same library (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("SIMPIMC_B200_LIB") or os.path.join(HERE, "csrc", "libsimpimc_b200.so")
 
 PIMC_OLD, PIMC_NEW = 0, 1
 GRID_GENERAL, GRID_LOG, GRID_LINEAR = 0, 1, 2

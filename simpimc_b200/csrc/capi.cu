@@ -499,7 +499,8 @@ int BuildFastIlkka(pimc_ctx *ctx, pimc_action *a, int which, const pimc_table_2d
         const int iy = (int)(std::upper_bound(g.y, g.y + g.n_y, x_max) - g.y);
         n_need = std::min(n_need, std::max(ix, iy) + 1);
     }
-    const size_t fixed = sizeof(double) * kFastRows * 3 * kFastRow + ((blob.b.size() + 15) & ~(size_t)15) + 2048;
+    const size_t fixed = sizeof(double) * kFastRows * 3 * kFastRow + ((blob.b.size() + 15) & ~(size_t)15) + 2048 +
+                         sizeof(double) * kFastWarps * 33;  // static shared memory of the kernel (ring, red)
     int n_stage = 0, row_stride = 0;
     for (int n = n_need; n >= 1; --n) {
         const int pad_slots = (4 - (n % 8) + 8) % 8;  // row stride = 4 (mod 8) sixteen-byte slots: rows fall into disjoint banks

@@ -249,9 +249,9 @@ __global__ void __launch_bounds__(kWindowThreads) pair_window_both_kernel(const 
             double r, rp, s;
             if (FAST) {
                 DrDrpDrrpFast(pold[j], q0, pold[j + 1], q1, pv.box, r, rp, s);
-                acc_old += FastIlkkaEval(a.fast_tables, a.FT, r, rp, s);
+                acc_old += FastIlkkaEval(GlobalTab(a.fast_tables), a.FT, r, rp, s);
                 DrDrpDrrpFast(pnew[j], q0, pnew[j + 1], q1, pv.box, r, rp, s);
-                acc_new += FastIlkkaEval(a.fast_tables, a.FT, r, rp, s);
+                acc_new += FastIlkkaEval(GlobalTab(a.fast_tables), a.FT, r, rp, s);
             } else {
                 DrDrpDrrp(pold[j], q0, pold[j + 1], q1, pv.box, r, rp, s);
                 acc_old += PairEval<ATYPE, WHICH_U>(a.blob, a.T, r, rp, s);
@@ -319,6 +319,7 @@ __global__ void __launch_bounds__(kWinFastThreads, 1) pair_window_fast_kernel(co
         int4 *dst = reinterpret_cast<int4 *>(wsm);
         for (int i = tid; i < a.FT.n_bytes / 16; i += kWinFastThreads) dst[i] = src[i];
     }
+    const SharedTab wtab(wsm);
     const PathView &pv = a.pv;
     const int nl = a.n_links;
     const int j = tid & (nl - 1), slot = tid / nl, n_slots = kWinFastThreads / nl;
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(kWinFastThreads, 1) pair_window_fast_kernel(co
                 }
                 double r, rp, s;
                 DrDrpDrrpFast(p0, q0, p1, q1, pv.box, r, rp, s);
-                acc += FastIlkkaEval(wsm, a.FT, r, rp, s);
+                acc += FastIlkkaEval(wtab, a.FT, r, rp, s);
             }
             if (mode)
                 acc_new = acc;

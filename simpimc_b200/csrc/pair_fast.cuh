@@ -28,6 +28,12 @@
 
 #include "device_math.cuh"
 
+// -DPIMC_EXPERIMENT=7 builds K1 without the neighbour-lane reuse of the long-range spline
+// (A/B timing, tools/gpu_ab.sh)
+#ifndef PIMC_EXPERIMENT
+#define PIMC_EXPERIMENT 0
+#endif
+
 namespace pimc {
 
 constexpr double kRoundMagic = 6755399441055744.0;  // 2^52 + 2^51: low word of (x + magic) = rint(x)
@@ -62,37 +68,66 @@ struct FastTable {
     int n_bytes;  // size of the staged block
 };
 
-__device__ __forceinline__ void ULookup(const unsigned char *__restrict__ tb, const ULutDesc &L, int off_gpair, double x, int &i,
-                                        double &t) {
+/// Where the staged table block lives: shared memory addressed by explicit 32-bit window
+/// addresses (LDS with register + immediate operands, no generic-address arithmetic), or
+/// global memory for the kernels that evaluate too little to stage 160 KB.
+struct SharedTab {
+    uint32_t base;
+    __device__ __forceinline__ explicit SharedTab(const void *p) : base((uint32_t)__cvta_generic_to_shared(p)) {}
+    __device__ __forceinline__ double2 LdV2(int off) const {
+        double2 v;
+        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(base + (uint32_t)off));
+        return v;
+    }
+    __device__ __forceinline__ int LdU16(int off) const {
+        uint32_t v;
+        asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(base + (uint32_t)off));
+        return (int)v;
+    }
+};
+struct GlobalTab {
+    const unsigned char *base;
+    __device__ __forceinline__ explicit GlobalTab(const void *p) : base(reinterpret_cast<const unsigned char *>(p)) {}
+    __device__ __forceinline__ double2 LdV2(int off) const { return __ldg(reinterpret_cast<const double2 *>(base + off)); }
+    __device__ __forceinline__ int LdU16(int off) const { return __ldg(reinterpret_cast<const unsigned short *>(base + off)); }
+};
+
+/// Interval of x >= 0 and tau = x - g[interval].  `clamp_key`: x may lie beyond the grid end
+/// (keys above the table are clamped to its last bucket, whose interval is the last one).
+template <class Tab>
+__device__ __forceinline__ void ULookup(const Tab &tb, const ULutDesc &L, int off_gpair, double x, bool clamp_key, int &i, double &t) {
     const double kd = fma(x, L.inv_h, kRoundMagic);
     int key = __double2loint(kd);
-    key = min(max(key, 0), L.key_max);
-    const int i0 = *reinterpret_cast<const unsigned short *>(tb + L.off_lut + 2 * key);
-    const double2 g = *reinterpret_cast<const double2 *>(tb + off_gpair + 16 * i0);
+    if (clamp_key) key = min(key, L.key_max);
+    const int i0 = tb.LdU16(L.off_lut + 2 * key);
+    const double2 g = tb.LdV2(off_gpair + 16 * i0);
     const bool up = x >= g.y;
     i = up ? i0 + 1 : i0;
     t = x - (up ? g.y : g.x);
 }
 
-__device__ __forceinline__ double FastPP1Eval(const unsigned char *__restrict__ tb, const FastPP1 &d, double x) {
+/// x must already lie inside [r_min, r_max] (SetLimits).
+template <class Tab>
+__device__ __forceinline__ double FastPP1Eval(const Tab &tb, const FastPP1 &d, double x) {
     int i;
     double t;
-    ULookup(tb, d.lut, d.off_gpair, x, i, t);
-    const double2 c01 = *reinterpret_cast<const double2 *>(tb + d.off_c01 + 16 * i);
-    const double2 c23 = *reinterpret_cast<const double2 *>(tb + d.off_c23 + 16 * i);
+    ULookup(tb, d.lut, d.off_gpair, x, false, i, t);
+    const double2 c01 = tb.LdV2(d.off_c01 + 16 * i);
+    const double2 c23 = tb.LdV2(d.off_c23 + 16 * i);
     return fma(fma(fma(c23.y, t, c23.x), t, c01.y), t, c01.x);
 }
 
-__device__ __forceinline__ double FastPP2Eval(const unsigned char *__restrict__ tb, const FastPP2 &d, double x, double y) {
+template <class Tab>
+__device__ __forceinline__ double FastPP2Eval(const Tab &tb, const FastPP2 &d, double x, double y) {
     int ix, iy;
     double tx, ty;
-    ULookup(tb, d.lutx, d.off_gxpair, x, ix, tx);
-    ULookup(tb, d.luty, d.off_gypair, y, iy, ty);
+    ULookup(tb, d.lutx, d.off_gxpair, x, true, ix, tx);
+    ULookup(tb, d.luty, d.off_gypair, y, true, iy, ty);
     double2 c[8];
     if (ix < d.n_stage && iy < d.n_stage) {
-        const double2 *p = reinterpret_cast<const double2 *>(tb + d.off_cells + ix * d.row_stride + iy * kCellRecord);
+        const int off = d.off_cells + ix * d.row_stride + iy * kCellRecord;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) c[k] = p[k];
+        for (int k = 0; k < 8; ++k) c[k] = tb.LdV2(off + 16 * k);
     } else {
         const double2 *p = reinterpret_cast<const double2 *>(d.cells_global) + ((size_t)ix * d.ny + iy) * 8;
 #pragma unroll
@@ -107,7 +142,7 @@ __device__ __forceinline__ double FastPP2Eval(const unsigned char *__restrict__ 
 /// sqrt(x) for x >= 0 to within 1 ulp (0 for x = 0): reciprocal-square-root seed (relative
 /// error 2^-26), one coupled Newton step for sqrt and 1/(2 sqrt), one Markstein correction.
 __device__ __forceinline__ double FastSqrt(double x) {
-    const int hi = max(__double2hiint(x), 0x00100000);  // keeps the seed finite at x = 0
+    const int hi = max(__double2hiint(x), 0x00100000);  // keeps the seed finite at x = 0 (s = 0 for beads at rest)
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(__hiloint2double(hi, __double2loint(x))));
     double g = x * y;
@@ -143,16 +178,71 @@ __device__ __forceinline__ void DrDrpDrrpFast(const double a0[3], const double b
 __device__ __forceinline__ double Clamp(double x, double lo, double hi) { return x > hi ? hi : (x < lo ? lo : x); }
 
 /// IlkkaPairAction::CalcU / CalcdUdBeta (the table decides which).
-__device__ __forceinline__ double FastIlkkaEval(const unsigned char *__restrict__ tb, const FastTable &T, double r, double r_p, double s) {
+template <class Tab>
+__device__ __forceinline__ double FastIlkkaEval(const Tab &tb, const FastTable &T, double r, double r_p, double s) {
+    const double q = 0.5 * (r + r_p);
+    const double x = fma(0.5, s, q);
+    const double y = fma(-0.5, s, q);  // >= 0 up to rounding (r + r' >= s); a tiny negative still rounds to key 0
+    double u = FastPP2Eval(tb, T.xy, x, y);
+    if (T.use_lr) {
+        // SetLimits (pair_action_class.h:32-42); distances inside the grid range -- all of them
+        // in a periodic box whose table reaches sqrt(3) L / 2 -- skip the selects
+        const bool outside = r < T.lr.r_min || r > T.lr.r_max || r_p < T.lr.r_min || r_p > T.lr.r_max;
+        if (__any_sync(__activemask(), outside)) {  // a real (warp-uniform, rarely taken) branch, not eight selects
+            r = Clamp(r, T.lr.r_min, T.lr.r_max);
+            r_p = Clamp(r_p, T.lr.r_min, T.lr.r_max);
+        }
+        u = fma(-0.5, FastPP1Eval(tb, T.lr, r), u);
+        u = fma(-0.5, FastPP1Eval(tb, T.lr, r_p), u);
+    }
+    return u;
+}
+
+/// SetLimits for one value, as a warp-uniform rarely taken branch.
+__device__ __forceinline__ double ClampRare(double x, const FastPP1 &d) {
+    if (__any_sync(__activemask(), x < d.r_min || x > d.r_max)) x = Clamp(x, d.r_min, d.r_max);
+    return x;
+}
+
+/// FastIlkkaEval for a converged warp whose 32 lanes hold consecutive links (b, b+1) of ONE
+/// particle pair.  u_long is evaluated once per lane, for r; u_long(r') is the next lane's
+/// u_long(r) -- the same bead pair one slice later -- whenever r' == r(next lane) bit for bit
+/// (equal inputs, equal outputs: exact).  That fails only where the image shift between the
+/// two slices differs (those lanes evaluate u_long(r') themselves: a rare branch with one or
+/// two active lanes) and on lane 31, which has no next lane: it parks its r' in `ring` (one
+/// slot per step) and the caller evaluates 32 parked values together (LrRingFlush) -- the
+/// term -u_long(r')/2 is simply added to whichever lane's partial sum.
+template <class Tab>
+__device__ __forceinline__ double FastIlkkaEvalWarp(const Tab &tb, const FastTable &T, double r, double r_p, double s, int lane,
+                                                    double *ring_slot) {
     const double q = 0.5 * (r + r_p);
     const double x = fma(0.5, s, q);
     const double y = fma(-0.5, s, q);
     double u = FastPP2Eval(tb, T.xy, x, y);
     if (T.use_lr) {
-        u = fma(-0.5, FastPP1Eval(tb, T.lr, Clamp(r, T.lr.r_min, T.lr.r_max)), u);
-        u = fma(-0.5, FastPP1Eval(tb, T.lr, Clamp(r_p, T.lr.r_min, T.lr.r_max)), u);
+        const double lr_r = FastPP1Eval(tb, T.lr, ClampRare(r, T.lr));
+        const double r_next = __shfl_down_sync(0xffffffffu, r, 1);
+        double lr_p = __shfl_down_sync(0xffffffffu, lr_r, 1);
+        if (lane == 31) {
+            *ring_slot = r_p;
+            lr_p = 0.;
+        } else if (r_p != r_next) {
+            lr_p = FastPP1Eval(tb, T.lr, Clamp(r_p, T.lr.r_min, T.lr.r_max));
+        }
+        u = fma(-0.5, lr_r, u);
+        u = fma(-0.5, lr_p, u);
     }
     return u;
+}
+
+/// -u_long/2 of the first `count` parked values of a warp's ring, one per lane.
+template <class Tab>
+__device__ __forceinline__ double LrRingFlush(const Tab &tb, const FastTable &T, const double *ring, int lane, int count) {
+    __syncwarp();
+    double v = 0.;
+    if (lane < count) v = -0.5 * FastPP1Eval(tb, T.lr, Clamp(ring[lane], T.lr.r_min, T.lr.r_max));
+    __syncwarp();
+    return v;
 }
 
 // ------------------------------------------------------------------------------ K1 (fast)
@@ -182,12 +272,14 @@ struct PairFastArgs {
 __global__ void __launch_bounds__(kFastThreads, 1) pair_full_fast_kernel(const PairFastArgs a) {
     extern __shared__ __align__(16) unsigned char fsm[];
     __shared__ double red[kFastWarps];
+    __shared__ double ring[kFastWarps][32];  // lane 31's parked r' per warp and step (FastIlkkaEvalWarp)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double *qpos = reinterpret_cast<double *>(fsm);               // [kFastRows][3][kFastRow]
-    unsigned char *tb = fsm + sizeof(double) * kFastRows * 3 * kFastRow;
+    unsigned char *tb_ptr = fsm + sizeof(double) * kFastRows * 3 * kFastRow;
+    const SharedTab tb(tb_ptr);
     {
         const int4 *src = reinterpret_cast<const int4 *>(a.tables);
-        int4 *dst = reinterpret_cast<int4 *>(tb);
+        int4 *dst = reinterpret_cast<int4 *>(tb_ptr);
         for (int i = tid; i < a.T.n_bytes / 16; i += kFastThreads) dst[i] = src[i];
     }
     __syncthreads();
@@ -220,6 +312,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) pair_full_fast_kernel(const P
         if (a.same && (Na & 1) == 0 && p >= half) my_dd = half - 1;
         if (!warp_on) my_dd = 0;
         double acc = 0.;
+        const bool lane31_counts = s0 + 31 < pv.Mloc;
         for (int t0 = 0; t0 < n_dd; t0 += kFastQ) {
             const int n_rows = a.same ? min(kFastQ, n_dd - t0) + kFastWarps - 1 : min(kFastQ, Nb - t0);
             const int q_first = a.same ? p_lo + t0 + 1 : t0;
@@ -244,9 +337,17 @@ __global__ void __launch_bounds__(kFastThreads, 1) pair_full_fast_kernel(const P
                 const double b1[3] = {rowp[1], rowp[kFastRow + 1], rowp[2 * kFastRow + 1]};
                 double r, rp, s;
                 DrDrpDrrpFast(p0, b0, p1, b1, pv.box, r, rp, s);
+#if PIMC_EXPERIMENT == 7
                 const double u = FastIlkkaEval(tb, a.T, r, rp, s);
+#else
+                const double u = FastIlkkaEvalWarp(tb, a.T, r, rp, s, lane, &ring[warp][i]);
+#endif
                 acc += lane_on ? u : 0.;
             }
+#if PIMC_EXPERIMENT != 7
+            // a window holds at most kFastQ = 32 steps: one parked value per step
+            if (a.T.use_lr && lane31_counts && n_step > 0) acc += LrRingFlush(tb, a.T, ring[warp], lane, n_step);
+#endif
         }
         const double tot = BlockSum<kFastThreads>(acc, red);
         if (tid == 0) a.partial[item] = tot;
@@ -258,7 +359,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) pair_full_fast_kernel(const P
 __global__ void calc_pair_fast_kernel(const unsigned char *__restrict__ tables, FastTable T, int n, const double *__restrict__ r,
                                       const double *__restrict__ rp, const double *__restrict__ s, double *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = FastIlkkaEval(tables, T, r[i], rp[i], s[i]);
+    if (i < n) out[i] = FastIlkkaEval(GlobalTab(tables), T, r[i], rp[i], s[i]);
 }
 __global__ void fast_sqrt_kernel(int n, const double *__restrict__ x, double *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
