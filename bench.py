@@ -309,7 +309,7 @@ def run_ours(args):
             traffic = json.load(open(tf)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "fp64", "kernel": "pair_full_kernel<ILKKA,DU>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+    roofline = {"bound": "fp64", "kernel": "pair_full_fast_kernel (IlkkaPairAction::CalcdUdBeta over all pairs x slices)", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
                 "peak_source": "DFMA micro-benchmark (pimc_fp64_peak) measured in this run; MEASURED_PEAKS.json holds no FP64 figure",
                 "algorithmic_flop_per_launch": evals_step * FLOP_PER_EVAL,
@@ -323,7 +323,7 @@ def run_ours(args):
         hbm = 6650.0
     roofline["hbm_gbs_peak"] = hbm
     roofline["k1_hbm_gbs_algorithmic"] = C * N_SLICE * N_PART * 24 / k1_avg_s / 1e9
-    base = cpu_baseline(n_eval=args.cpu_evals) if args.cpu_evals > 0 else None
+    base = cpu_baseline(n_eval=args.cpu_evals) if (args.cpu_evals > 0 and world == 1) else None
     line = {"metric": "bead-pair action evals/s", "value": value, "unit": "bead-pair action evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
