@@ -18,6 +18,7 @@
 #include "kernels.cuh"
 #include "pair_fast.cuh"
 #include "mc.cuh"
+#include "sweep_fused.cuh"
 #include "spline_build.h"
 
 using namespace pimc;
@@ -1418,7 +1419,46 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
         if (st.drho.n < need) PIMC_CUDA(st.drho.Alloc(need));
     }
     const PathView pv = ctx->View();
-    for (int it = 0; it < n_attempts; ++it) {
+    // one same-species fast Ilkka action on the moved species: the whole sweep is one launch
+    // (sweep_fused.cuh); everything else takes the kernel-per-phase path below
+    bool fused = acts.size() == 1 && acts[0]->sa == s && acts[0]->sb == s && acts[0]->atype == ATYPE_ILKKA && acts[0]->fast_ok[WHICH_U] &&
+                 !ctx->force_general && nb <= kSweepMaxBeads && n_level <= kSweepMaxLevel;
+    size_t fused_smem = 0;
+    if (fused) {
+        const int tl = 2 * ctx->max_index + 1;
+        fused_smem = (size_t)acts[0]->fast[WHICH_U].n_bytes + (any_lr ? (size_t)kSweepClones * nb * 6 * tl * sizeof(double2) : 0);
+        if (fused_smem + sizeof(SweepShared) + 1024 > (size_t)ctx->smem_optin) fused = false;
+    }
+    if (fused && n_attempts > 0) {
+        pimc_action *a = acts[0];
+        SweepFusedArgs f;
+        f.pv = pv;
+        f.R = st.R.p;
+        f.N = st.N;
+        f.lambda = st.lambda;
+        f.tau = ctx->tau;
+        f.n_level = n_level;
+        f.with_kinetic = with_kinetic ? 1 : 0;
+        f.seed_lo = (uint32_t)seed;
+        f.seed_hi = (uint32_t)(seed >> 32);
+        f.attempt0 = attempt0;
+        f.n_attempts = n_attempts;
+        f.FT = a->fast[WHICH_U];
+        f.fast_tables = a->fast_tab[WHICH_U].p;
+        f.use_lr = any_lr ? 1 : 0;
+        f.ks = ctx->KView();
+        f.rho = any_lr ? st.rho.p : nullptr;
+        f.wk = any_lr ? a->wk[WHICH_U].p : nullptr;
+        f.lr_factor = a->ulong_scale;
+        f.n_accept = ctx->mc_naccept.p;
+        PIMC_CUDA(cudaFuncSetAttribute(bisect_sweep_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
+        {
+            ScopedKernelTimer t(ctx, PIMC_KERNEL_PAIR_WINDOW);
+            bisect_sweep_fused_kernel<<<std::min(C, ctx->n_sm), kSweepThreads, fused_smem, ctx->stream>>>(f);
+        }
+        ctx->launches++;
+    }
+    for (int it = 0; it < (fused ? 0 : n_attempts); ++it) {
         const uint64_t attempt = attempt0 + (uint64_t)it;
         BisectArgs ba;
         ba.pv = pv;

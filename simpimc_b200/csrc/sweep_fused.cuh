@@ -1,0 +1,379 @@
+// One launch = n_attempts x Bisect::DoEvent on every clone
+// (src/events/moves/move_class.h:61-77 -> single_species_move/bisect/bisect_class.h:39-139)
+// for the common case of ONE same-species Ilkka pair action (with or without its long-range
+// part) acting on the moved species -- the uniform electron gas of BASELINE.json.
+//
+// Clones are independent walkers, so a sweep needs no grid-wide synchronisation: persistent
+// CTAs (one per SM, 1024 threads) each own up to kSweepClones clones, stage the fast Ilkka
+// tables in shared memory ONCE, and then run the attempts back to back, block-synchronising
+// between the phases of an attempt:
+//
+//   A   Philox draws for every (clone, bead) in parallel: particle and window, the Levy
+//       displacements sigma * normal of every midpoint, the Metropolis uniforms; the window's
+//       committed beads are loaded
+//   A'  one thread per clone: Levy construction level by level (bisect_class.h:69-98), kinetic
+//       action in closed form, Metropolis tests of the levels above 0
+//   B   PairAction::GetAction in OLD and NEW mode (pair_action_class.h:267-302): lanes = (partner
+//       particle, link); the partner's beads are read once for both modes; per-axis phase
+//       tables of the window's old and new beads are built on the side
+//   C   Species::UpdateRhoK for the proposal (species_class.h:406-425) fused with CalcULong over
+//       the window in OLD and NEW mode (ilkka_pair_action_class.h:104-122)
+//   D   level-0 Metropolis test (bisect_class.h:110-115)
+//   E   Move::Accept: positions and rho_k += (new - old) (bisect_class.h:24-36)
+//
+// The multi-kernel path in mc.cuh (any action mix, any species pair) draws the same Philox
+// stream and remains the general implementation; both are tested against the same host mirror.
+#ifndef SIMPIMC_B200_SWEEP_FUSED_CUH_
+#define SIMPIMC_B200_SWEEP_FUSED_CUH_
+
+#include "mc.cuh"
+
+namespace pimc {
+
+constexpr int kSweepThreads = 1024;
+constexpr int kSweepWarps = kSweepThreads / 32;
+constexpr int kSweepClones = 8;                              // clones a CTA advances together
+constexpr int kSweepGroup = kSweepThreads / kSweepClones;    // threads that own one clone in phases C-E
+constexpr int kSweepGroupWarps = kSweepGroup / 32;
+constexpr int kSweepMaxBeads = 16;                           // 2^n_level <= 16
+constexpr int kSweepMaxLevel = 4;
+
+struct SweepFusedArgs {
+    PathView pv;
+    double *R;  // committed positions (read and written here: no const, no __restrict__)
+    int N;
+    double lambda, tau;
+    int n_level;
+    int with_kinetic;
+    uint32_t seed_lo, seed_hi;
+    unsigned long long attempt0;
+    int n_attempts;
+    FastTable FT;
+    const unsigned char *fast_tables;
+    int use_lr;
+    KSpaceView ks;
+    double2 *rho;      // committed rho_k of the species (read and written)
+    const double *wk;  // [n_k]
+    double lr_factor;
+    long long *n_accept;  // [C], added to
+};
+
+/// Shared state of the clones a CTA is advancing.
+struct SweepShared {
+    double pold[kSweepClones][kSweepMaxBeads + 1][3];
+    double pnew[kSweepClones][kSweepMaxBeads + 1][3];
+    double del_new[kSweepClones][kSweepMaxBeads][3];  // sigma * normal, folded into the box
+    double d2_new[kSweepClones][kSweepMaxBeads];
+    double logu[kSweepClones][kSweepMaxLevel];
+    double partial[kSweepClones];
+    double wsum[kSweepClones][2][kSweepWarps];
+    double lrsum[kSweepClones][2][kSweepGroupWarps];
+    int particle[kSweepClones];
+    int bead0[kSweepClones];
+    int alive[kSweepClones];
+    int accept[kSweepClones];
+};
+
+/// First Philox slot of a level: slot 0 picks particle and window, then every level from the
+/// top takes two slots per midpoint and one for its Metropolis uniform (bisect_sample_kernel).
+__device__ __forceinline__ uint32_t SweepSlotStart(int level, int n_level, int nb) {
+    uint32_t s = 1;
+    for (int l = n_level - 1; l > level; --l) s += 2u * (uint32_t)(nb >> (l + 1)) + 1u;
+    return s;
+}
+
+/// Beads j and j + 1 of one clone's window ([j][3] doubles, consecutive) from shared memory.
+__device__ __forceinline__ void LdsBeadPair(uint32_t addr, double b0[3], double b1[3]) {
+    asm volatile("ld.shared.f64 %0, [%6];\n\tld.shared.f64 %1, [%6+8];\n\tld.shared.f64 %2, [%6+16];\n\t"
+                 "ld.shared.f64 %3, [%6+24];\n\tld.shared.f64 %4, [%6+32];\n\tld.shared.f64 %5, [%6+40];"
+                 : "=d"(b0[0]), "=d"(b0[1]), "=d"(b0[2]), "=d"(b1[0]), "=d"(b1[1]), "=d"(b1[2])
+                 : "r"(addr));
+}
+
+__global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(const SweepFusedArgs a) {
+    extern __shared__ __align__(16) unsigned char ssm[];
+    __shared__ SweepShared sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const PathView &pv = a.pv;
+    const int nb = 1 << a.n_level;
+    const int tl = 2 * a.ks.max_index + 1, n_k = a.use_lr ? a.ks.n_k : 0;
+    // dynamic shared memory: [fast tables][phase tables: clone, window slice, mode, axis, 2m+1]
+    {
+        const int4 *src = reinterpret_cast<const int4 *>(a.fast_tables);
+        int4 *dst = reinterpret_cast<int4 *>(ssm);
+        for (int i = tid; i < a.FT.n_bytes / 16; i += kSweepThreads) dst[i] = src[i];
+    }
+    const SharedTab tb(ssm);
+    double2 *ptab = reinterpret_cast<double2 *>(ssm + a.FT.n_bytes);
+    const int grp = tid / kSweepGroup, tg = tid - grp * kSweepGroup;
+    const int per_cta = (pv.C + gridDim.x - 1) / gridDim.x;
+    for (int batch = 0; batch < per_cta; batch += kSweepClones) {
+        // clone of local slot lc: strided over the grid so that every CTA holds the same count +-1
+        int nlc = 0;
+        for (int lc = 0; lc < kSweepClones; ++lc)
+            if (batch + lc < per_cta && (int)blockIdx.x + (batch + lc) * (int)gridDim.x < pv.C) nlc = lc + 1;
+        if (nlc == 0) break;
+        const int c_grp = (int)blockIdx.x + (batch + grp) * (int)gridDim.x;  // clone of this thread's group (phases C-E)
+        long long my_accepts = 0;
+        for (int it = 0; it < a.n_attempts; ++it) {
+            const unsigned long long attempt = a.attempt0 + (unsigned long long)it;
+            const uint32_t at_lo = (uint32_t)attempt, at_hi = (uint32_t)(attempt >> 32);
+            // ---------------------------------------------------------------- phase A
+            if (tid < nlc * (nb + 1) * 3) {  // committed beads of the window
+                const int lc = tid / ((nb + 1) * 3), rem = tid - lc * (nb + 1) * 3;
+                const int j = rem / 3, d = rem - j * 3;
+                const int c = (int)blockIdx.x + (batch + lc) * (int)gridDim.x;
+                uint32_t rnd[4];
+                Philox4x32(at_lo, at_hi, (uint32_t)c, 0u, a.seed_lo, a.seed_hi, rnd);
+                int p_i = (int)(UniformFromBits(rnd[0], rnd[1]) * a.N);
+                p_i = p_i < a.N ? p_i : a.N - 1;
+                int b0 = (int)(UniformFromBits(rnd[2], rnd[3]) * pv.M);
+                b0 = b0 < pv.M ? b0 : pv.M - 1;
+                int bg = b0 + j;
+                while (bg >= pv.M) bg -= pv.M;
+                const double x = a.R[PosIndex(pv, a.N, c, p_i, d, bg - pv.slice_lo)];
+                sh.pold[lc][j][d] = x;
+                sh.pnew[lc][j][d] = x;
+                if (rem == 0) {
+                    sh.particle[lc] = p_i;
+                    sh.bead0[lc] = b0;
+                }
+            } else if (tid >= 512 && tid < 512 + nlc * (nb - 1)) {  // Levy displacements
+                const int t = tid - 512;
+                const int lc = t / (nb - 1), ib = t - lc * (nb - 1) + 1;
+                const int c = (int)blockIdx.x + (batch + lc) * (int)gridDim.x;
+                const int level = __ffs(ib) - 1, skip = 1 << level;
+                const int idx = (ib - skip) >> (level + 1);
+                const uint32_t slot = SweepSlotStart(level, a.n_level, nb) + 2u * (uint32_t)idx;
+                uint32_t r0[4], r1[4];
+                Philox4x32(at_lo, at_hi, (uint32_t)c, slot, a.seed_lo, a.seed_hi, r0);
+                Philox4x32(at_lo, at_hi, (uint32_t)c, slot + 1, a.seed_lo, a.seed_hi, r1);
+                const double ua = UniformFromBits(r0[0], r0[1]), ub = UniformFromBits(r0[2], r0[3]);
+                const double uc = UniformFromBits(r1[0], r1[1]), ud = UniformFromBits(r1[2], r1[3]);
+                const double ra = sqrt(-2. * log(ua)), rc = sqrt(-2. * log(uc));
+                double sb, cb, sd, cd;
+                sincospi(2. * ub, &sb, &cb);
+                sincospi(2. * ud, &sd, &cd);
+                (void)sd;
+                const double nrm[3] = {ra * cb, ra * sb, rc * cd};
+                const double sigma = sqrt(a.lambda * (a.tau * skip));
+                double d2 = 0.;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const double del = PutInBox1(sigma * nrm[d], pv.box);
+                    sh.del_new[lc][ib][d] = del;
+                    d2 += del * del;
+                }
+                sh.d2_new[lc][ib] = d2;
+            } else if (tid >= 768 && tid < 768 + nlc * a.n_level) {  // Metropolis uniforms
+                const int t = tid - 768;
+                const int lc = t / a.n_level, level = t - lc * a.n_level;
+                const int c = (int)blockIdx.x + (batch + lc) * (int)gridDim.x;
+                const uint32_t slot = SweepSlotStart(level, a.n_level, nb) + 2u * (uint32_t)(nb >> (level + 1));
+                uint32_t ru[4];
+                Philox4x32(at_lo, at_hi, (uint32_t)c, slot, a.seed_lo, a.seed_hi, ru);
+                sh.logu[lc][level] = log(UniformFromBits(ru[0], ru[1]));
+            }
+            __syncthreads();
+            // ---------------------------------------------------------------- phase A'
+            if (tg == 0 && grp < nlc) {
+                const int lc = grp;
+                double(*oldb)[3] = sh.pold[lc];
+                double(*newb)[3] = sh.pnew[lc];
+                bool alive = true;
+                double prev_change = 0., partial = 0.;
+                for (int level = a.n_level - 1; level >= 0; --level) {
+                    const int skip = 1 << level;
+                    const double level_tau = a.tau * skip;
+                    const double i4lt_sample = 1. / (4. * a.lambda * (0.5 * level_tau));
+                    const double i4lt_kin = 1. / (4. * a.lambda * level_tau);
+                    double old_lp = 0., new_lp = 0.;
+                    for (int ia = 0; ia < nb; ia += 2 * skip) {
+                        const int ib = ia + skip, ic = ia + 2 * skip;
+                        double d2_old = 0.;
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) {
+                            const double rbar_old = oldb[ia][d] + 0.5 * PutInBox1(oldb[ic][d] - oldb[ia][d], pv.box);
+                            const double del_old = PutInBox1(oldb[ib][d] - rbar_old, pv.box);
+                            d2_old += del_old * del_old;
+                            const double rbar_new = newb[ia][d] + 0.5 * PutInBox1(newb[ic][d] - newb[ia][d], pv.box);
+                            newb[ib][d] = rbar_new + sh.del_new[lc][ib][d];
+                        }
+                        old_lp -= d2_old * i4lt_sample;
+                        new_lp -= sh.d2_new[lc][ib] * i4lt_sample;
+                    }
+                    double old_kin = 0., new_kin = 0.;
+                    if (a.with_kinetic) {
+                        for (int ia = 0; ia < nb; ia += skip) {
+                            double d2o = 0., d2n = 0.;
+#pragma unroll
+                            for (int d = 0; d < 3; ++d) {
+                                const double o = PutInBox1(oldb[ia][d] - oldb[ia + skip][d], pv.box);
+                                const double n = PutInBox1(newb[ia][d] - newb[ia + skip][d], pv.box);
+                                d2o += o * o;
+                                d2n += n * n;
+                            }
+                            old_kin += d2o * i4lt_kin;
+                            new_kin += d2n * i4lt_kin;
+                        }
+                    }
+                    const double lsr = -new_lp + old_lp;
+                    const double change = new_kin - old_kin;
+                    if (level > 0) {
+                        if (lsr - change + prev_change < sh.logu[lc][level]) alive = false;
+                        prev_change = change;
+                    } else {
+                        partial = lsr - change + prev_change;
+                    }
+                }
+                sh.partial[lc] = partial;
+                sh.alive[lc] = alive ? 1 : 0;
+            }
+            __syncthreads();
+            // ---------------------------------------------------------------- phase B
+            if (n_k > 0 && tid < nlc * nb * 6) {  // phase tables of the window's old and new beads
+                const int lc = tid / (nb * 6), rem = tid - lc * nb * 6;
+                const int j = rem / 6, md = rem - j * 6;
+                const int mode = md / 3, d = md - mode * 3;
+                if (sh.alive[lc]) PhaseTable(mode ? sh.pnew[lc][j][d] : sh.pold[lc][j][d], a.ks.kbox, a.ks.max_index, ptab + (size_t)tid * tl);
+            }
+            {
+                const int per_warp = 32 / nb;  // partner particles per warp item
+                const int n_groups = (a.N + per_warp - 1) / per_warp;
+                const int j = lane & (nb - 1), sub = lane / nb;
+                for (int lc = 0; lc < nlc; ++lc) {
+                    if (!sh.alive[lc]) continue;  // rejected above level 0
+                    const int c = (int)blockIdx.x + (batch + lc) * (int)gridDim.x;
+                    const int p = sh.particle[lc];
+                    int b0s = sh.bead0[lc] + j, b1s = b0s + 1;
+                    if (b0s >= pv.M) b0s -= pv.M;
+                    if (b1s >= pv.M) b1s -= pv.M;
+                    // moved-particle beads are re-read from shared memory for every evaluation (asm
+                    // volatile: not hoisted) -- holding OLD and NEW copies in registers spills at 64
+                    const uint32_t po_addr = (uint32_t)__cvta_generic_to_shared(&sh.pold[lc][j][0]);
+                    const uint32_t pn_addr = (uint32_t)__cvta_generic_to_shared(&sh.pnew[lc][j][0]);
+                    double acc_old = 0., acc_new = 0.;
+                    for (int g = warp; g < n_groups; g += kSweepWarps) {
+                        const int q = g * per_warp + sub;
+                        const bool on = q < a.N && q != p;
+                        const int ql = q < a.N ? q : a.N - 1;
+                        double q0[3], q1[3];
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) {
+                            q0[d] = a.R[PosIndex(pv, a.N, c, ql, d, b0s - pv.slice_lo)];
+                            q1[d] = a.R[PosIndex(pv, a.N, c, ql, d, b1s - pv.slice_lo)];
+                        }
+                        double r, rp, s, m0[3], m1[3];
+                        LdsBeadPair(po_addr, m0, m1);
+                        DrDrpDrrpFast(m0, q0, m1, q1, pv.box, r, rp, s);
+                        const double uo = FastIlkkaEval(tb, a.FT, r, rp, s);
+                        LdsBeadPair(pn_addr, m0, m1);
+                        DrDrpDrrpFast(m0, q0, m1, q1, pv.box, r, rp, s);
+                        const double un = FastIlkkaEval(tb, a.FT, r, rp, s);
+                        acc_old += on ? uo : 0.;
+                        acc_new += on ? un : 0.;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        acc_old += __shfl_down_sync(0xffffffffu, acc_old, o);
+                        acc_new += __shfl_down_sync(0xffffffffu, acc_new, o);
+                    }
+                    if (lane == 0) {
+                        sh.wsum[lc][0][warp] = acc_old;
+                        sh.wsum[lc][1][warp] = acc_new;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---------------------------------------------------------------- phase C
+            const bool grp_on = grp < nlc && sh.alive[grp < nlc ? grp : 0];
+            if (n_k > 0) {
+                double acc_old = 0., acc_new = 0.;
+                if (grp_on) {
+                    const int bead0 = sh.bead0[grp];
+                    const double2 *pt = ptab + (size_t)grp * nb * 6 * tl;
+                    for (int t = tg; t < nb * n_k; t += kSweepGroup) {
+                        const int j = t / n_k, k = t - j * n_k;
+                        int bg = bead0 + j;
+                        if (bg >= pv.M) bg -= pv.M;
+                        const int i0 = a.ks.kidx[3 * k], i1 = a.ks.kidx[3 * k + 1], i2 = a.ks.kidx[3 * k + 2];
+                        const double2 *to = pt + (size_t)j * 6 * tl, *tn = to + 3 * tl;
+                        const double2 fo = CMul(CMul(to[i0], to[tl + i1]), to[2 * tl + i2]);
+                        const double2 fn = CMul(CMul(tn[i0], tn[tl + i1]), tn[2 * tl + i2]);
+                        const double2 dk = make_double2(fn.x - fo.x, fn.y - fo.y);
+                        const double2 rs = a.rho[((size_t)c_grp * pv.Mloc + (bg - pv.slice_lo)) * n_k + k];
+                        const double2 rn = make_double2(rs.x + dk.x, rs.y + dk.y);
+                        const double w = a.wk[k] * a.lr_factor;
+                        acc_old += w * (rs.x * rs.x + rs.y * rs.y);
+                        acc_new += w * (rn.x * rn.x + rn.y * rn.y);
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    acc_old += __shfl_down_sync(0xffffffffu, acc_old, o);
+                    acc_new += __shfl_down_sync(0xffffffffu, acc_new, o);
+                }
+                if (lane == 0) {
+                    sh.lrsum[grp][0][warp - grp * kSweepGroupWarps] = acc_old;
+                    sh.lrsum[grp][1][warp - grp * kSweepGroupWarps] = acc_new;
+                }
+                __syncthreads();
+            }
+            // ---------------------------------------------------------------- phase D
+            if (tg == 0 && grp < nlc) {
+                int acc = 0;
+                if (sh.alive[grp]) {
+                    double po = 0., pn = 0., lo = 0., ln = 0.;
+                    for (int w = 0; w < kSweepWarps; ++w) {
+                        po += sh.wsum[grp][0][w];
+                        pn += sh.wsum[grp][1][w];
+                    }
+                    if (n_k > 0)
+                        for (int w = 0; w < kSweepGroupWarps; ++w) {
+                            lo += sh.lrsum[grp][0][w];
+                            ln += sh.lrsum[grp][1][w];
+                        }
+                    const double old_action = po + lo, new_action = pn + ln;
+                    acc = (sh.partial[grp] - (new_action - old_action)) < sh.logu[grp][0] ? 0 : 1;
+                }
+                sh.accept[grp] = acc;
+                my_accepts += acc;
+            }
+            __syncthreads();
+            // ---------------------------------------------------------------- phase E
+            if (grp < nlc && sh.accept[grp]) {
+                const int p = sh.particle[grp], bead0 = sh.bead0[grp];
+                for (int t = tg; t < (nb - 1) * 3; t += kSweepGroup) {
+                    const int j = t / 3 + 1, d = t - (j - 1) * 3;
+                    int bg = bead0 + j;
+                    while (bg >= pv.M) bg -= pv.M;
+                    a.R[PosIndex(pv, a.N, c_grp, p, d, bg - pv.slice_lo)] = sh.pnew[grp][j][d];
+                }
+                if (n_k > 0) {
+                    const double2 *pt = ptab + (size_t)grp * nb * 6 * tl;
+                    // slice 0 of the window keeps its bead: its increment is zero
+                    for (int t = n_k + tg; t < nb * n_k; t += kSweepGroup) {
+                        const int j = t / n_k, k = t - j * n_k;
+                        int bg = bead0 + j;
+                        if (bg >= pv.M) bg -= pv.M;
+                        const int i0 = a.ks.kidx[3 * k], i1 = a.ks.kidx[3 * k + 1], i2 = a.ks.kidx[3 * k + 2];
+                        const double2 *to = pt + (size_t)j * 6 * tl, *tn = to + 3 * tl;
+                        const double2 fo = CMul(CMul(to[i0], to[tl + i1]), to[2 * tl + i2]);
+                        const double2 fn = CMul(CMul(tn[i0], tn[tl + i1]), tn[2 * tl + i2]);
+                        double2 *dst = a.rho + ((size_t)c_grp * pv.Mloc + (bg - pv.slice_lo)) * n_k + k;
+                        double2 v = *dst;
+                        v.x += fn.x - fo.x;
+                        v.y += fn.y - fo.y;
+                        *dst = v;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (tg == 0 && grp < nlc) a.n_accept[c_grp] += my_accepts;
+    }
+}
+
+}  // namespace pimc
+
+#endif  // SIMPIMC_B200_SWEEP_FUSED_CUH_

@@ -15,18 +15,24 @@ from simpimc_b200 import system as S
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["ueg", "plasma", "nolr"])
-def test_device_sweep_follows_the_host_mirror_of_its_stream(name):
+@pytest.mark.parametrize("name,general", [("ueg", False), ("ueg", True), ("plasma", False), ("nolr", False), ("nolr", True), ("ueg4", False)])
+def test_device_sweep_follows_the_host_mirror_of_its_stream(name, general):
+    """general = False: the single-launch sweep (csrc/sweep_fused.cuh) where it applies (ueg, nolr,
+    ueg4: one same-species Ilkka action), the kernel-per-phase path otherwise (plasma);
+    general = True forces the kernel-per-phase path."""
     from simpimc_b200 import host, moves
     from oracle import oracle as O
     if name == "ueg":
         cfg, n_level = S.ueg_config(N=9, M=16), 3
+    elif name == "ueg4":
+        cfg, n_level = S.ueg_config(N=37, M=32), 4
     elif name == "nolr":
         cfg, n_level = S.ueg_config(N=6, M=8, use_long_range=False), 2
     else:
         cfg, n_level = S.plasma_config(Ne=5, Np=4, M=8), 2
     C = 3
     path = host.Path(cfg, n_clones=C)
+    path.ForceGeneral(general)
     oracles = []
     for c in range(C):
         o = O.Oracle(cfg)
@@ -77,6 +83,34 @@ def test_device_sweep_follows_the_host_mirror_of_its_stream(name):
             ref = oracles[c].dbeta(ai)
             assert abs(du[c] - ref) <= 1e-10 * abs(ref)
     path.close()
+
+
+@pytest.mark.parametrize("C,N,M,n_level,lr", [(310, 9, 16, 3, True), (1337, 5, 8, 2, True), (150, 7, 8, 1, False)])
+def test_single_launch_sweep_equals_the_kernel_per_phase_path(C, N, M, n_level, lr):
+    """Many clones per CTA (C > 148), several batches of 8 clones per CTA (C > 8 x 148) and many
+    attempts inside ONE launch: same accept history and positions as the general path, which
+    the test above pins to the oracle attempt by attempt."""
+    from simpimc_b200 import host
+    cfg = S.ueg_config(N=N, M=M, use_long_range=lr)
+    R = np.stack([S.synthetic_paths(cfg, 0, c, 3) for c in range(C)])
+    out = []
+    for general in (False, True):
+        path = host.Path(cfg, n_clones=C)
+        path.ForceGeneral(general)
+        path.SetPositions(0, R)
+        launches0 = path.LaunchCount()
+        acc = path.BisectSweep(0, n_level, 24, 77, attempt0=5)
+        acc = acc + path.BisectSweep(0, n_level, 9, 77, attempt0=29)
+        n_launch = path.LaunchCount() - launches0
+        out.append((acc, path.GetPositions(0), path.GetRhoK(0, C - 1, host.OLD_MODE) if lr else None, path.actions[0].DActionDBeta(), n_launch))
+        path.close()
+    (a0, r0, k0, d0, l0), (a1, r1, k1, d1, l1) = out
+    assert l0 == 2 and l1 > 2 * 24          # one launch per call vs several per attempt
+    assert np.array_equal(a0, a1) and a0.sum() > 0
+    assert np.max(np.abs(r0 - r1)) <= 1e-12 * cfg.L
+    if lr:
+        assert np.max(np.abs(k0 - k1)) <= 1e-11 * N
+    assert np.max(np.abs(d0 - d1) / np.abs(d1)) <= 1e-10
 
 
 def _mean_err(x):
