@@ -82,6 +82,47 @@ __device__ __forceinline__ uint32_t SweepSlotStart(int level, int n_level, int n
     return s;
 }
 
+/// IlkkaPairAction::CalcU of one link of a bisection window in OLD and in NEW mode, for a
+/// converged warp whose lanes are (partner, link j) with the nb links of a partner in consecutive
+/// lanes.  The 2-D part is evaluated per lane and mode.  The long-range spline is needed at the
+/// nb + 1 bead distances of the OLD window and at the nb - 1 moved ones of the NEW window (beads 0
+/// and nb are common) = 2 nb values for 2 nb evaluations, so every lane evaluates it exactly
+/// twice instead of four times: lrA = u_long(r_old(j)); lrB = u_long(r_new(j)) -- except that
+/// lane j = 0, whose r is the same in both modes, spends its second evaluation on the window's
+/// last bead nb.  u_long(r') of a link is the next lane's u_long(r) whenever r' equals that r
+/// bit for bit (same inputs, same image: exact); otherwise -- the image shift changed between
+/// the two slices -- the lane evaluates it itself (rare branch).
+template <class Tab>
+__device__ __forceinline__ void FastIlkkaEvalWindow(const Tab &tb, const FastTable &T, int j, int nb, int lane, double ro, double rpo,
+                                                    double so, double rn, double rpn, double sn, double &uo, double &un) {
+    const double qo = 0.5 * (ro + rpo), qn = 0.5 * (rn + rpn);
+    uo = FastPP2Eval(tb, T.xy, fma(0.5, so, qo), fma(-0.5, so, qo));
+    un = FastPP2Eval(tb, T.xy, fma(0.5, sn, qn), fma(-0.5, sn, qn));
+    if (T.use_lr) {
+        const unsigned full = 0xffffffffu;
+        const double r_end = __shfl_sync(full, rpo, lane | (nb - 1));  // bead nb as the group's last lane sees it
+        const double lrA = FastPP1Eval(tb, T.lr, ClampRare(ro, T.lr));
+        const double lrB = FastPP1Eval(tb, T.lr, ClampRare(j == 0 ? r_end : rn, T.lr));
+        const double lr_end = __shfl_sync(full, lrB, lane & ~(nb - 1));
+        double nxt_o = __shfl_down_sync(full, lrA, 1), rnx_o = __shfl_down_sync(full, ro, 1);
+        double nxt_n = __shfl_down_sync(full, lrB, 1), rnx_n = __shfl_down_sync(full, rn, 1);
+        if (j == nb - 1) {
+            nxt_o = lr_end;
+            nxt_n = lr_end;
+            rnx_o = r_end;
+            rnx_n = r_end;
+        }
+        if (rpo != rnx_o) nxt_o = FastPP1Eval(tb, T.lr, Clamp(rpo, T.lr.r_min, T.lr.r_max));
+        if (rpn != rnx_n) nxt_n = FastPP1Eval(tb, T.lr, Clamp(rpn, T.lr.r_min, T.lr.r_max));
+        uo = fma(-0.5, lrA, uo);
+        uo = fma(-0.5, nxt_o, uo);
+        un = fma(-0.5, j == 0 ? lrA : lrB, un);
+        un = fma(-0.5, nxt_n, un);
+    }
+}
+
+__device__ __forceinline__ void PrefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 /// Beads j and j + 1 of one clone's window ([j][3] doubles, consecutive) from shared memory.
 __device__ __forceinline__ void LdsBeadPair(uint32_t addr, double b0[3], double b1[3]) {
     asm volatile("ld.shared.f64 %0, [%6];\n\tld.shared.f64 %1, [%6+8];\n\tld.shared.f64 %2, [%6+16];\n\t"
@@ -228,6 +269,29 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                 }
                 sh.partial[lc] = partial;
                 sh.alive[lc] = alive ? 1 : 0;
+            } else if (grp < nlc) {
+                // the other threads of the group pull what phases B and C will read towards L2 while
+                // the Levy construction runs: the window's slices of every particle row (first and
+                // last byte: a 72-byte window touches one or two 128-byte lines) and of rho_k
+                const int bead0 = sh.bead0[grp];
+                int b_last = bead0 + nb;
+                if (b_last >= pv.M) b_last -= pv.M;
+                const double *Rc = a.R + PosIndex(pv, a.N, c_grp, 0, 0, 0);
+                const int n_rows = a.N * 3;
+                for (int t = tg - 1; t < 2 * n_rows; t += kSweepGroup - 1) {
+                    const int row = t >> 1;
+                    PrefetchL2(Rc + (size_t)row * pv.Ms + ((t & 1) ? b_last : bead0) - pv.slice_lo);
+                }
+                if (n_k > 0) {
+                    const int lines = (n_k * (int)sizeof(double2) + 127) / 128;
+                    for (int t = tg - 1; t < nb * lines; t += kSweepGroup - 1) {
+                        const int j = t / lines, l = t - j * lines;
+                        int bg = bead0 + j;
+                        if (bg >= pv.M) bg -= pv.M;
+                        const char *p = reinterpret_cast<const char *>(a.rho + ((size_t)c_grp * pv.Mloc + (bg - pv.slice_lo)) * n_k);
+                        PrefetchL2(p + min(l * 128, n_k * (int)sizeof(double2) - 1));
+                    }
+                }
             }
             __syncthreads();
             // ---------------------------------------------------------------- phase B
@@ -252,24 +316,29 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                     // volatile: not hoisted) -- holding OLD and NEW copies in registers spills at 64
                     const uint32_t po_addr = (uint32_t)__cvta_generic_to_shared(&sh.pold[lc][j][0]);
                     const uint32_t pn_addr = (uint32_t)__cvta_generic_to_shared(&sh.pnew[lc][j][0]);
+                    // 32-bit offsets inside the clone's block of rows
+                    const double *Rc = a.R + PosIndex(pv, a.N, c, 0, 0, 0);
+                    const unsigned row_stride = 3u * (unsigned)pv.Ms, ms = (unsigned)pv.Ms;
+                    const unsigned o0 = (unsigned)(b0s - pv.slice_lo), o1 = (unsigned)(b1s - pv.slice_lo);
                     double acc_old = 0., acc_new = 0.;
                     for (int g = warp; g < n_groups; g += kSweepWarps) {
                         const int q = g * per_warp + sub;
                         const bool on = q < a.N && q != p;
-                        const int ql = q < a.N ? q : a.N - 1;
+                        const unsigned row = (unsigned)(q < a.N ? q : a.N - 1) * row_stride;
                         double q0[3], q1[3];
 #pragma unroll
                         for (int d = 0; d < 3; ++d) {
-                            q0[d] = a.R[PosIndex(pv, a.N, c, ql, d, b0s - pv.slice_lo)];
-                            q1[d] = a.R[PosIndex(pv, a.N, c, ql, d, b1s - pv.slice_lo)];
+                            q0[d] = Rc[row + d * ms + o0];
+                            q1[d] = Rc[row + d * ms + o1];
                         }
-                        double r, rp, s, m0[3], m1[3];
+                        // both sets of distances first: the partner's beads die before the table work
+                        double ro, rpo, so, rn, rpn, sn, m0[3], m1[3];
                         LdsBeadPair(po_addr, m0, m1);
-                        DrDrpDrrpFast(m0, q0, m1, q1, pv.box, r, rp, s);
-                        const double uo = FastIlkkaEval(tb, a.FT, r, rp, s);
+                        DrDrpDrrpFast(m0, q0, m1, q1, pv.box, ro, rpo, so);
                         LdsBeadPair(pn_addr, m0, m1);
-                        DrDrpDrrpFast(m0, q0, m1, q1, pv.box, r, rp, s);
-                        const double un = FastIlkkaEval(tb, a.FT, r, rp, s);
+                        DrDrpDrrpFast(m0, q0, m1, q1, pv.box, rn, rpn, sn);
+                        double uo, un;
+                        FastIlkkaEvalWindow(tb, a.FT, j, nb, lane, ro, rpo, so, rn, rpn, sn, uo, un);
                         acc_old += on ? uo : 0.;
                         acc_new += on ? un : 0.;
                     }
