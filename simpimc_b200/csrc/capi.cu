@@ -94,6 +94,9 @@ struct pimc_ctx {
     std::vector<double> k_mag;
     DevBuf<int32_t> d_kidx;        // [n_k][3] offset by max_index
     DevBuf<double> d_kmag;
+    // the same set grouped into (i_x, i_y) columns for rhok_build_cols_kernel
+    DevBuf<int32_t> d_col_info, d_kmap;
+    int n_cols = 0, cols_tm = 0;
     // scratch
     DevBuf<double> partial, out_dev, lr_dev, stage;
     DevBuf<int32_t> i32_a, i32_b, i32_c, i32_d;
@@ -265,7 +268,48 @@ int UploadKSpace(pimc_ctx *ctx) {
         PIMC_CUDA(cudaMemcpyAsync(ctx->d_kidx.p, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
         PIMC_CUDA(cudaMemcpyAsync(ctx->d_kmag.p, ctx->k_mag.data(), n_k * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
+    // columns (i_x, i_y) in order of first appearance; kmap[col][i_z + TM] = k
+    int tm = 0;
+    for (int32_t v : ctx->k_index) tm = std::max(tm, std::abs(v));
+    std::vector<int32_t> col_info, col_key;
+    for (int k = 0; k < n_k; ++k) {
+        const int32_t key = (ctx->k_index[3 * k] + 128) * 256 + ctx->k_index[3 * k + 1] + 128;
+        if (std::find(col_key.begin(), col_key.end(), key) == col_key.end()) col_key.push_back(key);
+    }
+    ctx->n_cols = (int)col_key.size();
+    ctx->cols_tm = tm;
+    std::vector<int32_t> kmap((size_t)std::max(1, ctx->n_cols) * (2 * tm + 1), -1);
+    for (int k = 0; k < n_k; ++k) {
+        const int32_t ix = ctx->k_index[3 * k], iy = ctx->k_index[3 * k + 1], iz = ctx->k_index[3 * k + 2];
+        const int col = (int)(std::find(col_key.begin(), col_key.end(), (ix + 128) * 256 + iy + 128) - col_key.begin());
+        kmap[(size_t)col * (2 * tm + 1) + iz + tm] = k;
+    }
+    for (int32_t key : col_key) {
+        const int ix = key / 256 - 128, iy = key % 256 - 128;
+        col_info.push_back(std::abs(ix) | (std::abs(iy) << 8) | ((ix < 0) << 16) | ((iy < 0) << 17));
+    }
+    PIMC_CUDA(ctx->d_col_info.Alloc(std::max(1, ctx->n_cols)));
+    PIMC_CUDA(ctx->d_kmap.Alloc(kmap.size()));
+    if (n_k) {
+        PIMC_CUDA(cudaMemcpyAsync(ctx->d_col_info.p, col_info.data(), col_info.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        PIMC_CUDA(cudaMemcpyAsync(ctx->d_kmap.p, kmap.data(), kmap.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
     PIMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PIMC_OK;
+}
+
+template <int TM>
+int LaunchRhokCols(pimc_ctx *ctx, int s, const KColsView &kc, double2 *rho) {
+    const int S = kColsWarps / kc.n_groups;
+    const size_t smem = (size_t)S * 32 * ColsEntries(TM) * sizeof(double2);
+    PIMC_CUDA(cudaFuncSetAttribute(rhok_build_cols_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = ctx->C * ((ctx->Mloc + S - 1) / S);
+    {
+        ScopedKernelTimer t(ctx, PIMC_KERNEL_RHOK_BUILD);
+        rhok_build_cols_kernel<TM><<<grid, kColsWarps * 32, smem, ctx->stream>>>(ctx->View(), ctx->SView(s, false), kc, rho);
+    }
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
     return PIMC_OK;
 }
 
@@ -280,6 +324,25 @@ int RebuildRhoK(pimc_ctx *ctx, int s) {
     }
     const size_t need = (size_t)ctx->C * ctx->Mloc * n_k;
     if (st.rho.n != need) PIMC_CUDA(st.rho.Alloc(need));
+    // column-factorised build (every KSpace::Setup set with |index| <= 6 and <= 256 columns)
+    if (!ctx->force_general && ctx->cols_tm >= 1 && ctx->cols_tm <= 6 && ctx->n_cols <= 32 * kColsWarps) {
+        KColsView kc;
+        kc.n_k = n_k;
+        kc.n_cols = ctx->n_cols;
+        kc.n_groups = (ctx->n_cols + 31) / 32;
+        kc.col_info = ctx->d_col_info.p;
+        kc.kmap = ctx->d_kmap.p;
+        kc.kbox = 2. * M_PI / ctx->L;
+        kc.stage_out = n_k <= 32 * ColsEntries(ctx->cols_tm) ? 1 : 0;
+        switch (ctx->cols_tm) {
+            case 1: return LaunchRhokCols<1>(ctx, s, kc, st.rho.p);
+            case 2: return LaunchRhokCols<2>(ctx, s, kc, st.rho.p);
+            case 3: return LaunchRhokCols<3>(ctx, s, kc, st.rho.p);
+            case 4: return LaunchRhokCols<4>(ctx, s, kc, st.rho.p);
+            case 5: return LaunchRhokCols<5>(ctx, s, kc, st.rho.p);
+            default: return LaunchRhokCols<6>(ctx, s, kc, st.rho.p);
+        }
+    }
     const int tl = 2 * ctx->max_index + 1;
     int chunk = std::max(1, std::min(32, (int)(40000 / (3 * tl * sizeof(double2)))));
     const size_t smem = (size_t)chunk * 3 * tl * sizeof(double2);

@@ -272,6 +272,116 @@ __global__ void __launch_bounds__(256) rhok_build_kernel(PathView pv, SpeciesVie
     }
 }
 
+// K2 v2: the k set of KSpace::Setup is a half ball, so it factors into COLUMNS (i_x, i_y) that
+// each hold the lattice indices i_z = -z_max .. z_max (the column (0, 0) only i_z > 0).  With
+// A_p = c_x[i_x] c_y[i_y] of particle p and z_p = c_z[|i_z|],
+//     rho(i_x, i_y, +|i_z|) = sum_p A_p z_p       = (S1 - S2) + i (S3 + S4)
+//     rho(i_x, i_y, -|i_z|) = sum_p A_p conj(z_p) = (S1 + S2) + i (S4 - S3)
+// with S1 = sum Re A Re z, S2 = sum Im A Im z, S3 = sum Re A Im z, S4 = sum Im A Re z: four FMAs
+// per particle serve BOTH k vectors, and c_z is the same address for every lane (one broadcast
+// LDS.128).  Lane = column, warp = slice; per particle and warp 22 FP64 instructions and 6 LDS
+// instead of 182 x (10 FP64 + 3 LDS) / 32 = 57 + 17 of the thread-per-k form above.  The sums run
+// over particles in index order but associate differently from species_class.h:391-395
+// (products are added component-wise): |difference| <= a few N ulp, inside the 1e-12 N bound the
+// parity tests hold rho_k to.
+struct KColsView {
+    int n_k, n_cols, n_groups;     // n_groups = ceil(n_cols / 32) warps share one slice
+    const int32_t *col_info;       // [n_cols] |i_x| | |i_y| << 8 | (i_x < 0) << 16 | (i_y < 0) << 17
+    const int32_t *kmap;           // [n_cols][2 TM + 1] index of the k vector (i_x, i_y, i_z), -1 = absent
+    double kbox;
+    int stage_out;                 // n_k complex numbers fit in one slice's table region
+};
+
+constexpr int kColsWarps = 8;
+__host__ __device__ constexpr int ColsEntries(int TM) { return (3 * TM + 2) | 1; }  // odd: 16-byte records of 8 lanes hit disjoint banks
+
+__device__ __forceinline__ double FlipSign(double v, int flip) { return __hiloint2double(__double2hiint(v) ^ flip, __double2loint(v)); }
+
+template <int TM>
+__global__ void __launch_bounds__(kColsWarps * 32) rhok_build_cols_kernel(PathView pv, SpeciesView sv, KColsView kc, double2 *__restrict__ rho) {
+    constexpr int E = ColsEntries(TM);
+    extern __shared__ __align__(16) double2 ctab[];  // [slice of the CTA][32 particles][E]
+    const int G = kc.n_groups, S = kColsWarps / G;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = warp / G, g = warp - s * G;
+    const int groups_per_clone = (pv.Mloc + S - 1) / S;
+    const int c = blockIdx.x / groups_per_clone;
+    const int b = (blockIdx.x - c * groups_per_clone) * S + s;
+    const bool valid = s < S && b < pv.Mloc;
+    const int col = g * 32 + lane;
+    const bool col_ok = col < kc.n_cols;
+    const int info = col_ok ? kc.col_info[col] : 0;
+    const int xo = info & 0xff, yo = (TM + 1) + ((info >> 8) & 0xff);
+    const int fx = (info >> 16) & 1 ? (int)0x80000000 : 0, fy = (info >> 17) & 1 ? (int)0x80000000 : 0;
+    double2 *T = ctab + (size_t)(s < S ? s : 0) * 32 * E;
+    double a0r = 0., a0i = 0.;
+    double S1[TM], S2[TM], S3[TM], S4[TM];
+#pragma unroll
+    for (int j = 0; j < TM; ++j) S1[j] = S2[j] = S3[j] = S4[j] = 0.;
+    for (int p0 = 0; p0 < sv.N; p0 += 32) {
+        if (G > 1) __syncthreads(); else __syncwarp();
+        if (g == 0 && valid && p0 + lane < sv.N) {
+            // KSpace::CalcC (k_space_class.h:83-94): c[j] = e^{i phi} c[j-1], entries 0..TM (z: 1..TM)
+            double2 *t = T + lane * E;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                double sn, cs;
+                sincos(sv.R[PosIndex(pv, sv.N, c, p0 + lane, d, b)] * kc.kbox, &sn, &cs);
+                double2 cur = make_double2(1., 0.);
+                double2 *td = d < 2 ? t + d * (TM + 1) : t + 2 * TM + 1;
+                if (d < 2) td[0] = cur;
+#pragma unroll
+                for (int j = 1; j <= TM; ++j) {
+                    cur = make_double2(cs * cur.x - sn * cur.y, cs * cur.y + sn * cur.x);
+                    td[j] = cur;
+                }
+            }
+        }
+        if (G > 1) __syncthreads(); else __syncwarp();
+        if (valid) {
+            const int np = min(32, sv.N - p0);
+#pragma unroll 4
+            for (int pp = 0; pp < np; ++pp) {
+                const double2 *t = T + pp * E;
+                const double2 X = t[xo], Y = t[yo];
+                const double xi = FlipSign(X.y, fx), yi = FlipSign(Y.y, fy);
+                const double ar = X.x * Y.x - xi * yi, ai = X.x * yi + xi * Y.x;
+                a0r += ar;
+                a0i += ai;
+#pragma unroll
+                for (int j = 0; j < TM; ++j) {
+                    const double2 Z = t[2 * TM + 2 + j];
+                    S1[j] = fma(ar, Z.x, S1[j]);
+                    S2[j] = fma(ai, Z.y, S2[j]);
+                    S3[j] = fma(ar, Z.y, S3[j]);
+                    S4[j] = fma(ai, Z.x, S4[j]);
+                }
+            }
+        }
+    }
+    // emit: through the slice's table region when it is large enough (coalesced 16-byte stores)
+    double2 *out = rho + ((size_t)c * pv.Mloc + (valid ? b : 0)) * kc.n_k;
+    double2 *dst = kc.stage_out ? T : out;
+    if (kc.stage_out) { if (G > 1) __syncthreads(); else __syncwarp(); }
+    if (valid && col_ok) {
+        const int32_t *km = kc.kmap + (size_t)col * (2 * TM + 1);
+        int k = km[TM];
+        if (k >= 0) dst[k] = make_double2(a0r, a0i);
+#pragma unroll
+        for (int j = 0; j < TM; ++j) {
+            k = km[TM + 1 + j];
+            if (k >= 0) dst[k] = make_double2(S1[j] - S2[j], S3[j] + S4[j]);
+            k = km[TM - 1 - j];
+            if (k >= 0) dst[k] = make_double2(S1[j] + S2[j], S4[j] - S3[j]);
+        }
+    }
+    if (kc.stage_out) {
+        if (G > 1) __syncthreads(); else __syncwarp();
+        if (valid)
+            for (int k = g * 32 + lane; k < kc.n_k; k += 32 * G) out[k] = T[k];
+    }
+}
+
 /// drho(c, j, k) = rho_bead(new position) - rho_bead(old position) of the proposal's particle
 /// at window slice j (global slice b0[c] + j), zero where the proposal does not cover it.
 __global__ void __launch_bounds__(256) rhok_delta_kernel(PathView pv, SpeciesView sv, KSpaceView ks, const int32_t *__restrict__ b0,
