@@ -1,11 +1,15 @@
 #!/bin/bash
-# One GPU-box pass: parity tests, bench, ncu launch list, ncu full capture of K1.
+# One GPU-box pass: parity tests, smoke, bench (+ reference arm), ncu launch list, ncu full
+# captures of K1 (pair_full_fast), K2 (rhok_build_cols) and the fused bisection sweep.
 set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2>&1; echo "bench rc=$?" >> gpurun_out/bench.log
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1; echo "bench rc=$?" >> gpurun_out/bench_ref.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --cpu-evals 0 --attempts 4 > gpurun_out/bench_ncu.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:pair_full -s 1 -c 1 -o gpurun_out/prof_k1 -f python bench.py --steps 1 --warmup 1 --cpu-evals 0 --attempts 1 --clones 256 > gpurun_out/prof_k1.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:rhok_build -s 1 -c 1 -o gpurun_out/prof_k2 -f python bench.py --steps 1 --warmup 1 --cpu-evals 0 --attempts 1 --clones 256 > gpurun_out/prof_k2.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:bisect_sweep_fused -c 1 -o gpurun_out/prof_sweep -f python bench.py --steps 1 --warmup 1 --cpu-evals 0 --attempts 8 --clones 256 > gpurun_out/prof_sweep.log 2>&1
 ls -la gpurun_out
