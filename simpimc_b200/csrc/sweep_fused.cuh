@@ -4,9 +4,12 @@
 // part) acting on the moved species -- the uniform electron gas of BASELINE.json.
 //
 // Clones are independent walkers, so a sweep needs no grid-wide synchronisation: persistent
-// CTAs (one per SM, 1024 threads) each own up to kSweepClones clones, stage the fast Ilkka
-// tables in shared memory ONCE, and then run the attempts back to back, block-synchronising
-// between the phases of an attempt:
+// CTAs (one per SM, 1024 threads) stage the fast Ilkka tables in shared memory ONCE and then
+// split into kSweepTeams independent TEAMS of 8 warps.  A team owns up to kTeamClones clones
+// at a time and runs their attempts back to back, synchronising only with itself (named
+// barrier) between the phases of an attempt -- the teams drift apart, so the serial phases of
+// one (Levy construction, Metropolis test: one thread per clone) are hidden behind the pair
+// work of the others while all of them share one copy of the tables:
 //
 //   A   Philox draws for every (clone, bead) in parallel: particle and window, the Levy
 //       displacements sigma * normal of every midpoint, the Metropolis uniforms; the window's
@@ -31,9 +34,12 @@
 namespace pimc {
 
 constexpr int kSweepThreads = 1024;
-constexpr int kSweepWarps = kSweepThreads / 32;
-constexpr int kSweepClones = 8;                              // clones a CTA advances together
-constexpr int kSweepGroup = kSweepThreads / kSweepClones;    // threads that own one clone in phases C-E
+constexpr int kSweepTeams = 4;                               // independent sub-CTA teams
+constexpr int kTeamThreads = kSweepThreads / kSweepTeams;
+constexpr int kTeamWarps = kTeamThreads / 32;
+constexpr int kTeamClones = 2;                               // clones a team advances together
+constexpr int kSweepClones = kSweepTeams * kTeamClones;      // clones in flight per CTA
+constexpr int kSweepGroup = kTeamThreads / kTeamClones;      // threads that own one clone in phases C-E
 constexpr int kSweepGroupWarps = kSweepGroup / 32;
 constexpr int kSweepMaxBeads = 16;                           // 2^n_level <= 16
 constexpr int kSweepMaxLevel = 4;
@@ -66,7 +72,7 @@ struct SweepShared {
     double d2_new[kSweepClones][kSweepMaxBeads];
     double logu[kSweepClones][kSweepMaxLevel];
     double partial[kSweepClones];
-    double wsum[kSweepClones][2][kSweepWarps];
+    double wsum[kSweepClones][2][kTeamWarps];
     double lrsum[kSweepClones][2][kSweepGroupWarps];
     int particle[kSweepClones];
     int bead0[kSweepClones];
@@ -121,6 +127,9 @@ __device__ __forceinline__ void FastIlkkaEvalWindow(const Tab &tb, const FastTab
     }
 }
 
+/// Barrier among the kTeamThreads threads of one team (barrier 0 is __syncthreads).
+__device__ __forceinline__ void TeamSync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(kTeamThreads) : "memory"); }
+
 __device__ __forceinline__ void PrefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 /// Beads j and j + 1 of one clone's window ([j][3] doubles, consecutive) from shared memory.
@@ -134,27 +143,35 @@ __device__ __forceinline__ void LdsBeadPair(uint32_t addr, double b0[3], double 
 __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(const SweepFusedArgs a) {
     extern __shared__ __align__(16) unsigned char ssm[];
     __shared__ SweepShared sh;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31;
+    const int team = threadIdx.x / kTeamThreads, tid = threadIdx.x - team * kTeamThreads;  // tid: inside the team
+    const int warp = tid >> 5;                                                              // warp inside the team
     const PathView &pv = a.pv;
     const int nb = 1 << a.n_level;
     const int tl = 2 * a.ks.max_index + 1, n_k = a.use_lr ? a.ks.n_k : 0;
-    // dynamic shared memory: [fast tables][phase tables: clone, window slice, mode, axis, 2m+1]
+    // dynamic shared memory: [fast tables][phase tables: clone slot, window slice, mode, axis, 2m+1]
     {
         const int4 *src = reinterpret_cast<const int4 *>(a.fast_tables);
         int4 *dst = reinterpret_cast<int4 *>(ssm);
-        for (int i = tid; i < a.FT.n_bytes / 16; i += kSweepThreads) dst[i] = src[i];
+        for (int i = threadIdx.x; i < a.FT.n_bytes / 16; i += kSweepThreads) dst[i] = src[i];
     }
+    __syncthreads();  // the only CTA-wide barrier: from here on the teams run on their own
     const SharedTab tb(ssm);
-    double2 *ptab = reinterpret_cast<double2 *>(ssm + a.FT.n_bytes);
+    const int s0 = team * kTeamClones;  // first shared-memory clone slot of this team
+    double2 *ptab = reinterpret_cast<double2 *>(ssm + a.FT.n_bytes) + (size_t)s0 * nb * 6 * tl;
     const int grp = tid / kSweepGroup, tg = tid - grp * kSweepGroup;
+    // clones of a CTA: blockIdx.x + i * gridDim.x, i < per_cta (every CTA holds the same count +-1);
+    // team t takes i = t, t + kSweepTeams, ... , kTeamClones of them at a time
     const int per_cta = (pv.C + gridDim.x - 1) / gridDim.x;
-    for (int batch = 0; batch < per_cta; batch += kSweepClones) {
-        // clone of local slot lc: strided over the grid so that every CTA holds the same count +-1
+    const int per_team = (per_cta - team + kSweepTeams - 1) / kSweepTeams;
+#define SWEEP_CLONE(lc) ((int)blockIdx.x + (team + (batch + (lc)) * kSweepTeams) * (int)gridDim.x)
+    for (int batch = 0; batch < per_team; batch += kTeamClones) {
         int nlc = 0;
-        for (int lc = 0; lc < kSweepClones; ++lc)
-            if (batch + lc < per_cta && (int)blockIdx.x + (batch + lc) * (int)gridDim.x < pv.C) nlc = lc + 1;
+        for (int lc = 0; lc < kTeamClones; ++lc)
+            if (batch + lc < per_team && SWEEP_CLONE(lc) < pv.C) nlc = lc + 1;
         if (nlc == 0) break;
-        const int c_grp = (int)blockIdx.x + (batch + grp) * (int)gridDim.x;  // clone of this thread's group (phases C-E)
+        const int c_grp = SWEEP_CLONE(grp);  // clone of this thread's group (phases C-E)
+        const int sg = s0 + grp;             // its shared-memory slot
         long long my_accepts = 0;
         for (int it = 0; it < a.n_attempts; ++it) {
             const unsigned long long attempt = a.attempt0 + (unsigned long long)it;
@@ -163,7 +180,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
             if (tid < nlc * (nb + 1) * 3) {  // committed beads of the window
                 const int lc = tid / ((nb + 1) * 3), rem = tid - lc * (nb + 1) * 3;
                 const int j = rem / 3, d = rem - j * 3;
-                const int c = (int)blockIdx.x + (batch + lc) * (int)gridDim.x;
+                const int c = SWEEP_CLONE(lc);
                 uint32_t rnd[4];
                 Philox4x32(at_lo, at_hi, (uint32_t)c, 0u, a.seed_lo, a.seed_hi, rnd);
                 int p_i = (int)(UniformFromBits(rnd[0], rnd[1]) * a.N);
@@ -173,16 +190,16 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                 int bg = b0 + j;
                 while (bg >= pv.M) bg -= pv.M;
                 const double x = a.R[PosIndex(pv, a.N, c, p_i, d, bg - pv.slice_lo)];
-                sh.pold[lc][j][d] = x;
-                sh.pnew[lc][j][d] = x;
+                sh.pold[s0 + lc][j][d] = x;
+                sh.pnew[s0 + lc][j][d] = x;
                 if (rem == 0) {
-                    sh.particle[lc] = p_i;
-                    sh.bead0[lc] = b0;
+                    sh.particle[s0 + lc] = p_i;
+                    sh.bead0[s0 + lc] = b0;
                 }
-            } else if (tid >= 512 && tid < 512 + nlc * (nb - 1)) {  // Levy displacements
-                const int t = tid - 512;
+            } else if (tid >= 128 && tid < 128 + nlc * (nb - 1)) {  // Levy displacements
+                const int t = tid - 128;
                 const int lc = t / (nb - 1), ib = t - lc * (nb - 1) + 1;
-                const int c = (int)blockIdx.x + (batch + lc) * (int)gridDim.x;
+                const int c = SWEEP_CLONE(lc);
                 const int level = __ffs(ib) - 1, skip = 1 << level;
                 const int idx = (ib - skip) >> (level + 1);
                 const uint32_t slot = SweepSlotStart(level, a.n_level, nb) + 2u * (uint32_t)idx;
@@ -202,25 +219,24 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
                     const double del = PutInBox1(sigma * nrm[d], pv.box);
-                    sh.del_new[lc][ib][d] = del;
+                    sh.del_new[s0 + lc][ib][d] = del;
                     d2 += del * del;
                 }
-                sh.d2_new[lc][ib] = d2;
-            } else if (tid >= 768 && tid < 768 + nlc * a.n_level) {  // Metropolis uniforms
-                const int t = tid - 768;
+                sh.d2_new[s0 + lc][ib] = d2;
+            } else if (tid >= 192 && tid < 192 + nlc * a.n_level) {  // Metropolis uniforms
+                const int t = tid - 192;
                 const int lc = t / a.n_level, level = t - lc * a.n_level;
-                const int c = (int)blockIdx.x + (batch + lc) * (int)gridDim.x;
+                const int c = SWEEP_CLONE(lc);
                 const uint32_t slot = SweepSlotStart(level, a.n_level, nb) + 2u * (uint32_t)(nb >> (level + 1));
                 uint32_t ru[4];
                 Philox4x32(at_lo, at_hi, (uint32_t)c, slot, a.seed_lo, a.seed_hi, ru);
-                sh.logu[lc][level] = log(UniformFromBits(ru[0], ru[1]));
+                sh.logu[s0 + lc][level] = log(UniformFromBits(ru[0], ru[1]));
             }
-            __syncthreads();
+            TeamSync(team);
             // ---------------------------------------------------------------- phase A'
             if (tg == 0 && grp < nlc) {
-                const int lc = grp;
-                double(*oldb)[3] = sh.pold[lc];
-                double(*newb)[3] = sh.pnew[lc];
+                double(*oldb)[3] = sh.pold[sg];
+                double(*newb)[3] = sh.pnew[sg];
                 bool alive = true;
                 double prev_change = 0., partial = 0.;
                 for (int level = a.n_level - 1; level >= 0; --level) {
@@ -238,10 +254,10 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                             const double del_old = PutInBox1(oldb[ib][d] - rbar_old, pv.box);
                             d2_old += del_old * del_old;
                             const double rbar_new = newb[ia][d] + 0.5 * PutInBox1(newb[ic][d] - newb[ia][d], pv.box);
-                            newb[ib][d] = rbar_new + sh.del_new[lc][ib][d];
+                            newb[ib][d] = rbar_new + sh.del_new[sg][ib][d];
                         }
                         old_lp -= d2_old * i4lt_sample;
-                        new_lp -= sh.d2_new[lc][ib] * i4lt_sample;
+                        new_lp -= sh.d2_new[sg][ib] * i4lt_sample;
                     }
                     double old_kin = 0., new_kin = 0.;
                     if (a.with_kinetic) {
@@ -261,19 +277,19 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                     const double lsr = -new_lp + old_lp;
                     const double change = new_kin - old_kin;
                     if (level > 0) {
-                        if (lsr - change + prev_change < sh.logu[lc][level]) alive = false;
+                        if (lsr - change + prev_change < sh.logu[sg][level]) alive = false;
                         prev_change = change;
                     } else {
                         partial = lsr - change + prev_change;
                     }
                 }
-                sh.partial[lc] = partial;
-                sh.alive[lc] = alive ? 1 : 0;
+                sh.partial[sg] = partial;
+                sh.alive[sg] = alive ? 1 : 0;
             } else if (grp < nlc) {
                 // the other threads of the group pull what phases B and C will read towards L2 while
                 // the Levy construction runs: the window's slices of every particle row (first and
                 // last byte: a 72-byte window touches one or two 128-byte lines) and of rho_k
-                const int bead0 = sh.bead0[grp];
+                const int bead0 = sh.bead0[sg];
                 int b_last = bead0 + nb;
                 if (b_last >= pv.M) b_last -= pv.M;
                 const double *Rc = a.R + PosIndex(pv, a.N, c_grp, 0, 0, 0);
@@ -293,35 +309,36 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                     }
                 }
             }
-            __syncthreads();
+            TeamSync(team);
             // ---------------------------------------------------------------- phase B
             if (n_k > 0 && tid < nlc * nb * 6) {  // phase tables of the window's old and new beads
                 const int lc = tid / (nb * 6), rem = tid - lc * nb * 6;
                 const int j = rem / 6, md = rem - j * 6;
                 const int mode = md / 3, d = md - mode * 3;
-                if (sh.alive[lc]) PhaseTable(mode ? sh.pnew[lc][j][d] : sh.pold[lc][j][d], a.ks.kbox, a.ks.max_index, ptab + (size_t)tid * tl);
+                if (sh.alive[s0 + lc])
+                    PhaseTable(mode ? sh.pnew[s0 + lc][j][d] : sh.pold[s0 + lc][j][d], a.ks.kbox, a.ks.max_index, ptab + (size_t)tid * tl);
             }
             {
                 const int per_warp = 32 / nb;  // partner particles per warp item
                 const int n_groups = (a.N + per_warp - 1) / per_warp;
                 const int j = lane & (nb - 1), sub = lane / nb;
                 for (int lc = 0; lc < nlc; ++lc) {
-                    if (!sh.alive[lc]) continue;  // rejected above level 0
-                    const int c = (int)blockIdx.x + (batch + lc) * (int)gridDim.x;
-                    const int p = sh.particle[lc];
-                    int b0s = sh.bead0[lc] + j, b1s = b0s + 1;
+                    if (!sh.alive[s0 + lc]) continue;  // rejected above level 0
+                    const int c = SWEEP_CLONE(lc);
+                    const int p = sh.particle[s0 + lc];
+                    int b0s = sh.bead0[s0 + lc] + j, b1s = b0s + 1;
                     if (b0s >= pv.M) b0s -= pv.M;
                     if (b1s >= pv.M) b1s -= pv.M;
                     // moved-particle beads are re-read from shared memory for every evaluation (asm
                     // volatile: not hoisted) -- holding OLD and NEW copies in registers spills at 64
-                    const uint32_t po_addr = (uint32_t)__cvta_generic_to_shared(&sh.pold[lc][j][0]);
-                    const uint32_t pn_addr = (uint32_t)__cvta_generic_to_shared(&sh.pnew[lc][j][0]);
+                    const uint32_t po_addr = (uint32_t)__cvta_generic_to_shared(&sh.pold[s0 + lc][j][0]);
+                    const uint32_t pn_addr = (uint32_t)__cvta_generic_to_shared(&sh.pnew[s0 + lc][j][0]);
                     // 32-bit offsets inside the clone's block of rows
                     const double *Rc = a.R + PosIndex(pv, a.N, c, 0, 0, 0);
                     const unsigned row_stride = 3u * (unsigned)pv.Ms, ms = (unsigned)pv.Ms;
                     const unsigned o0 = (unsigned)(b0s - pv.slice_lo), o1 = (unsigned)(b1s - pv.slice_lo);
                     double acc_old = 0., acc_new = 0.;
-                    for (int g = warp; g < n_groups; g += kSweepWarps) {
+                    for (int g = warp; g < n_groups; g += kTeamWarps) {
                         const int q = g * per_warp + sub;
                         const bool on = q < a.N && q != p;
                         const unsigned row = (unsigned)(q < a.N ? q : a.N - 1) * row_stride;
@@ -348,33 +365,37 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                         acc_new += __shfl_down_sync(0xffffffffu, acc_new, o);
                     }
                     if (lane == 0) {
-                        sh.wsum[lc][0][warp] = acc_old;
-                        sh.wsum[lc][1][warp] = acc_new;
+                        sh.wsum[s0 + lc][0][warp] = acc_old;
+                        sh.wsum[s0 + lc][1][warp] = acc_new;
                     }
                 }
             }
-            __syncthreads();
+            TeamSync(team);
             // ---------------------------------------------------------------- phase C
-            const bool grp_on = grp < nlc && sh.alive[grp < nlc ? grp : 0];
+            const bool grp_on = grp < nlc && sh.alive[grp < nlc ? sg : s0];
             if (n_k > 0) {
                 double acc_old = 0., acc_new = 0.;
                 if (grp_on) {
-                    const int bead0 = sh.bead0[grp];
+                    // thread = k vector (its indices and weight are read once), inner loop = the
+                    // window's slices, unrolled so that the rho_k loads of several slices are in flight
+                    const int bead0 = sh.bead0[sg];
                     const double2 *pt = ptab + (size_t)grp * nb * 6 * tl;
-                    for (int t = tg; t < nb * n_k; t += kSweepGroup) {
-                        const int j = t / n_k, k = t - j * n_k;
-                        int bg = bead0 + j;
-                        if (bg >= pv.M) bg -= pv.M;
-                        const int i0 = a.ks.kidx[3 * k], i1 = a.ks.kidx[3 * k + 1], i2 = a.ks.kidx[3 * k + 2];
-                        const double2 *to = pt + (size_t)j * 6 * tl, *tn = to + 3 * tl;
-                        const double2 fo = CMul(CMul(to[i0], to[tl + i1]), to[2 * tl + i2]);
-                        const double2 fn = CMul(CMul(tn[i0], tn[tl + i1]), tn[2 * tl + i2]);
-                        const double2 dk = make_double2(fn.x - fo.x, fn.y - fo.y);
-                        const double2 rs = a.rho[((size_t)c_grp * pv.Mloc + (bg - pv.slice_lo)) * n_k + k];
-                        const double2 rn = make_double2(rs.x + dk.x, rs.y + dk.y);
+                    const double2 *rho_c = a.rho + (size_t)c_grp * pv.Mloc * n_k;
+                    for (int k = tg; k < n_k; k += kSweepGroup) {
+                        const int i0 = a.ks.kidx[3 * k], i1 = tl + a.ks.kidx[3 * k + 1], i2 = 2 * tl + a.ks.kidx[3 * k + 2];
                         const double w = a.wk[k] * a.lr_factor;
-                        acc_old += w * (rs.x * rs.x + rs.y * rs.y);
-                        acc_new += w * (rn.x * rn.x + rn.y * rn.y);
+#pragma unroll 4
+                        for (int j = 0; j < nb; ++j) {
+                            int bg = bead0 + j;
+                            if (bg >= pv.M) bg -= pv.M;
+                            const double2 rs = rho_c[(size_t)(bg - pv.slice_lo) * n_k + k];
+                            const double2 *to = pt + (size_t)j * 6 * tl, *tn = to + 3 * tl;
+                            const double2 fo = CMul(CMul(to[i0], to[i1]), to[i2]);
+                            const double2 fn = CMul(CMul(tn[i0], tn[i1]), tn[i2]);
+                            const double2 rn = make_double2(rs.x + (fn.x - fo.x), rs.y + (fn.y - fo.y));
+                            acc_old += w * (rs.x * rs.x + rs.y * rs.y);
+                            acc_new += w * (rn.x * rn.x + rn.y * rn.y);
+                        }
                     }
                 }
 #pragma unroll
@@ -383,64 +404,68 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                     acc_new += __shfl_down_sync(0xffffffffu, acc_new, o);
                 }
                 if (lane == 0) {
-                    sh.lrsum[grp][0][warp - grp * kSweepGroupWarps] = acc_old;
-                    sh.lrsum[grp][1][warp - grp * kSweepGroupWarps] = acc_new;
+                    sh.lrsum[sg][0][warp - grp * kSweepGroupWarps] = acc_old;
+                    sh.lrsum[sg][1][warp - grp * kSweepGroupWarps] = acc_new;
                 }
-                __syncthreads();
+                TeamSync(team);
             }
             // ---------------------------------------------------------------- phase D
             if (tg == 0 && grp < nlc) {
                 int acc = 0;
-                if (sh.alive[grp]) {
+                if (sh.alive[sg]) {
                     double po = 0., pn = 0., lo = 0., ln = 0.;
-                    for (int w = 0; w < kSweepWarps; ++w) {
-                        po += sh.wsum[grp][0][w];
-                        pn += sh.wsum[grp][1][w];
+                    for (int w = 0; w < kTeamWarps; ++w) {
+                        po += sh.wsum[sg][0][w];
+                        pn += sh.wsum[sg][1][w];
                     }
                     if (n_k > 0)
                         for (int w = 0; w < kSweepGroupWarps; ++w) {
-                            lo += sh.lrsum[grp][0][w];
-                            ln += sh.lrsum[grp][1][w];
+                            lo += sh.lrsum[sg][0][w];
+                            ln += sh.lrsum[sg][1][w];
                         }
                     const double old_action = po + lo, new_action = pn + ln;
-                    acc = (sh.partial[grp] - (new_action - old_action)) < sh.logu[grp][0] ? 0 : 1;
+                    acc = (sh.partial[sg] - (new_action - old_action)) < sh.logu[sg][0] ? 0 : 1;
                 }
-                sh.accept[grp] = acc;
+                sh.accept[sg] = acc;
                 my_accepts += acc;
             }
-            __syncthreads();
+            TeamSync(team);
             // ---------------------------------------------------------------- phase E
-            if (grp < nlc && sh.accept[grp]) {
-                const int p = sh.particle[grp], bead0 = sh.bead0[grp];
+            if (grp < nlc && sh.accept[sg]) {
+                const int p = sh.particle[sg], bead0 = sh.bead0[sg];
                 for (int t = tg; t < (nb - 1) * 3; t += kSweepGroup) {
                     const int j = t / 3 + 1, d = t - (j - 1) * 3;
                     int bg = bead0 + j;
                     while (bg >= pv.M) bg -= pv.M;
-                    a.R[PosIndex(pv, a.N, c_grp, p, d, bg - pv.slice_lo)] = sh.pnew[grp][j][d];
+                    a.R[PosIndex(pv, a.N, c_grp, p, d, bg - pv.slice_lo)] = sh.pnew[sg][j][d];
                 }
                 if (n_k > 0) {
                     const double2 *pt = ptab + (size_t)grp * nb * 6 * tl;
                     // slice 0 of the window keeps its bead: its increment is zero
-                    for (int t = n_k + tg; t < nb * n_k; t += kSweepGroup) {
-                        const int j = t / n_k, k = t - j * n_k;
-                        int bg = bead0 + j;
-                        if (bg >= pv.M) bg -= pv.M;
-                        const int i0 = a.ks.kidx[3 * k], i1 = a.ks.kidx[3 * k + 1], i2 = a.ks.kidx[3 * k + 2];
-                        const double2 *to = pt + (size_t)j * 6 * tl, *tn = to + 3 * tl;
-                        const double2 fo = CMul(CMul(to[i0], to[tl + i1]), to[2 * tl + i2]);
-                        const double2 fn = CMul(CMul(tn[i0], tn[tl + i1]), tn[2 * tl + i2]);
-                        double2 *dst = a.rho + ((size_t)c_grp * pv.Mloc + (bg - pv.slice_lo)) * n_k + k;
-                        double2 v = *dst;
-                        v.x += fn.x - fo.x;
-                        v.y += fn.y - fo.y;
-                        *dst = v;
+                    double2 *rho_c = a.rho + (size_t)c_grp * pv.Mloc * n_k;
+                    for (int k = tg; k < n_k; k += kSweepGroup) {
+                        const int i0 = a.ks.kidx[3 * k], i1 = tl + a.ks.kidx[3 * k + 1], i2 = 2 * tl + a.ks.kidx[3 * k + 2];
+#pragma unroll 4
+                        for (int j = 1; j < nb; ++j) {
+                            int bg = bead0 + j;
+                            if (bg >= pv.M) bg -= pv.M;
+                            double2 *dst = rho_c + (size_t)(bg - pv.slice_lo) * n_k + k;
+                            double2 v = *dst;
+                            const double2 *to = pt + (size_t)j * 6 * tl, *tn = to + 3 * tl;
+                            const double2 fo = CMul(CMul(to[i0], to[i1]), to[i2]);
+                            const double2 fn = CMul(CMul(tn[i0], tn[i1]), tn[i2]);
+                            v.x += fn.x - fo.x;
+                            v.y += fn.y - fo.y;
+                            *dst = v;
+                        }
                     }
                 }
             }
-            __syncthreads();
+            TeamSync(team);
         }
         if (tg == 0 && grp < nlc) a.n_accept[c_grp] += my_accepts;
     }
+#undef SWEEP_CLONE
 }
 
 }  // namespace pimc
