@@ -352,6 +352,143 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------- config C5: one large path, slices sharded over the GPUs
+def run_c5(args):
+    """BASELINE config C5: dense hydrogen plasma, 1024 e + 1024 p, M = 512, three pair actions
+    (e-e, e-p, p-p; Ilkka tables with long range), ONE path whose time slices are sharded over
+    the ranks (strong scaling).  Step = rho_k rebuild of both species + DActionDBeta of the three
+    actions on the local slices + one NCCL all-reduce of the partial sums; the end-to-end leg
+    uploads the shard's positions from pinned host memory, fills the halo slice over the NCCL
+    ring and reads the energies back."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from simpimc_b200 import sharded, system as S, capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    Ne, M, C = args.c5_n, args.c5_m, args.c5_clones
+    cfg = S.plasma_config(Ne=Ne, Np=Ne, M=M, n_xy=100, n_r_long=1000, pp_action="IlkkaPairAction")
+    sp_path = sharded.ShardedPath(cfg, C, local, rank, world)
+    path, lib = sp_path.path, sp_path.path.L
+    sh = sp_path.sh
+    pinned, shards = [], []
+    for sp in range(2):
+        full = np.stack([S.synthetic_paths(cfg, sp, c, 777) for c in range(C)])   # same walkers on every rank
+        own = full[:, :, sh.lo:sh.hi, :]
+        t = torch.empty((C, Ne, path.n_store, 3), dtype=torch.float64, pin_memory=True)
+        t.zero_()
+        t.numpy()[:, :, :sh.n_local, :] = own      # the halo slot is filled by the ring exchange
+        if world == 1:
+            t.numpy()[...] = full
+        pinned.append(t)
+        shards.append(t.numpy())
+    n_act = 3
+    out_dev = torch.zeros((n_act, C), dtype=torch.float64, device="cuda")
+    out_host = np.zeros((n_act, C))
+    stream = sp_path.stream
+
+    def upload_and_halo():
+        for sp in range(2):
+            path.SetPositions(sp, shards[sp])
+            sp_path.ExchangeHalo(sp)
+
+    def step_resident():
+        sp_path.RebuildRhoK()
+        sp_path.DActionDBetaAllDevice(out_dev)
+
+    def step_e2e():
+        upload_and_halo()
+        step_resident()
+        with torch.cuda.stream(stream):
+            out_host[...] = out_dev.cpu().numpy()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        path.Sync()
+
+    upload_and_halo()
+    fp64_peak = path.Fp64Peak()
+    for _ in range(args.warmup):
+        step_resident()
+    path.Sync()
+    path.SetTiming(True)
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    launches0 = path.LaunchCount()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    e1.record(stream)
+    e1.synchronize()
+    barrier()
+    launches = path.LaunchCount() - launches0
+    clk = clocks.stop()
+    k1_ms, k1_n = path.KernelTime(1)
+    k2_ms, k2_n = path.KernelTime(2)
+    k3_ms, k3_n = path.KernelTime(3)
+    path.SetTiming(False)
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    pairs = Ne * (Ne - 1) // 2 * 2 + Ne * Ne
+    evals_step = C * pairs * M            # whole path, all ranks together
+    value = evals_step * args.steps / (ms_max * 1e-3)
+    for _ in range(min(2, args.warmup)):
+        step_e2e()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    w1 = time.perf_counter()
+    barrier()
+    te = torch.tensor([1e3 * (w1 - w0)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = evals_step * args.steps / (float(te.item()) * 1e-3)
+    energies = out_dev.cpu().numpy().copy()
+    assert np.allclose(energies, out_host, rtol=1e-12, atol=0), "resident and e2e energies differ"
+    if rank == 0:
+        k1_step_s = k1_ms / args.steps * 1e-3          # the three K1 launches of a step on this rank
+        achieved = (evals_step / world) * FLOP_PER_EVAL / k1_step_s / 1e12
+        line = {"metric": "bead-pair action evals/s", "value": value, "unit": "bead-pair action evals/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "C5 dense hydrogen plasma %d e + %d p, M=%d, 3 Ilkka pair actions with long range (n_k=%d), %d path(s), slices sharded %d per GPU"
+                                       % (Ne, Ne, M, path.n_k, C, sh.n_local),
+                           "step": "rho_k rebuild (2 species) + DActionDBeta of 3 actions on the local slices + one NCCL all-reduce of %d doubles" % (n_act * C),
+                           "parallelism": "slice sharding, ring halo of one slice per species + all-reduce",
+                           "l2": "positions %.1f MB + rho_k %.1f MB per GPU%s" % (2 * shards[0].nbytes / 1e6, 2 * C * sh.n_local * path.n_k * 16 / 1e6,
+                                                                                  "" if 2 * shards[0].nbytes > 126e6 else " (fits L2: one system is that small; every step rewrites rho_k and the partial sums)")},
+                "clocks": clk,
+                "e2e": {"value": e2e_value, "unit": "bead-pair action evals/s", "h2d_bytes_per_step": int(2 * shards[0].nbytes),
+                        "d2h_bytes_per_step": int(out_host.nbytes), "halo_bytes_per_step": int(2 * C * Ne * 3 * 8) if world > 1 else 0},
+                "gpu_launches": int(launches),
+                "energies": {"dU/dbeta per action (clone 0)": [float(x) for x in energies[:, 0]]},
+                "roofline": {"bound": "fp64", "kernel": "pair_full_fast_kernel x 3 actions", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                             "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                             "kernel_ms_per_step": {"K1_pair_full": k1_ms / args.steps, "K2_rhok_build": k2_ms / args.steps, "K3_ksum": k3_ms / args.steps},
+                             "kernel_share_of_step": {"K1": k1_ms / ms_total, "K2": k2_ms / ms_total, "K3": k3_ms / ms_total}}}
+        print(json.dumps(line), flush=True)
+    sp_path.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -362,9 +499,15 @@ def main():
     ap.add_argument("--attempts", type=int, default=256, help="bisection attempts per clone timed for the MC-sweep figure")
     ap.add_argument("--pipeline", type=int, default=4, help="contexts the end-to-end leg splits the clones over (H2D/compute overlap)")
     ap.add_argument("--cpu-evals", type=int, default=2, help="DActionDBeta() calls per core for cpu_baseline (0 = skip)")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c5"], help="c3: UEG N=256 M=128 x clones (headline); c5: plasma 1024+1024, M=512, slices sharded over the GPUs")
+    ap.add_argument("--c5-n", type=int, default=1024)
+    ap.add_argument("--c5-m", type=int, default=512)
+    ap.add_argument("--c5-clones", type=int, default=1)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5":
+        run_c5(args)
     else:
         run_ours(args)
 

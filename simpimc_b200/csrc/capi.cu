@@ -618,7 +618,16 @@ int LaunchPairFast(pimc_action *a, int which, int *n_per_clone) {
     args.tables = a->fast_tab[which].p;
     args.n_chunks = (ctx->Mloc + kChunk - 1) / kChunk;
     args.n_pgroups = (args.A.N + kFastWarps - 1) / kFastWarps;
-    *n_per_clone = args.n_chunks * args.n_pgroups;
+    // too few items to fill the SMs (one large slice-sharded path): split the partner loop of an
+    // item by windows of kFastQ partners until there are about six items per SM
+    const int n_dd = args.same ? args.A.N / 2 : args.B.N;
+    const int n_windows = std::max(1, (n_dd + kFastQ - 1) / kFastQ);
+    const size_t base_items = (size_t)ctx->C * args.n_chunks * args.n_pgroups;
+    int want = (int)std::min<size_t>((size_t)n_windows, ((size_t)6 * ctx->n_sm + base_items - 1) / std::max<size_t>(base_items, 1));
+    want = std::max(want, 1);
+    args.t_windows = std::max(1, n_windows / want);
+    args.n_tsplit = (n_windows + args.t_windows - 1) / args.t_windows;
+    *n_per_clone = args.n_chunks * args.n_pgroups * args.n_tsplit;
     const size_t items = (size_t)ctx->C * *n_per_clone;
     if (ctx->partial.n < items) PIMC_CUDA(ctx->partial.Alloc(items));
     args.partial = ctx->partial.p;

@@ -259,11 +259,14 @@ struct PairFastArgs {
     FastTable T;
     const unsigned char *tables;  // the block to stage (T.n_bytes)
     int n_chunks, n_pgroups;
-    double *partial;              // [C][n_chunks][n_pgroups]
+    int n_tsplit, t_windows;      // the partner windows of an item group are split n_tsplit ways, t_windows windows each
+    double *partial;              // [C][n_chunks][n_pgroups][n_tsplit]
 };
 
 /// Persistent CTAs, one per SM.  Work item = (clone, 32-slice chunk, group of 32 particles of
-/// species a): warp w owns particle p = 32 g + w, its lanes own the chunk's 32 links.  Same
+/// species a, range of partner windows -- the whole partner loop unless the launch has too few
+/// items to fill the GPU, e.g. one slice-sharded path): warp w owns particle p = 32 g + w, its
+/// lanes own the chunk's 32 links.  Same
 /// species: the warp pairs p with q = p + dd (mod N) for dd = 1..N/2 (the last offset only
 /// from the lower half when N is even), so every unordered pair is visited once and every
 /// warp does the same amount of work per staged window; window t holds the Q + 31 particles
@@ -287,12 +290,15 @@ __global__ void __launch_bounds__(kFastThreads, 1) pair_full_fast_kernel(const P
     const int Na = a.A.N, Nb = a.B.N;
     const int half = Na / 2;
     const int n_dd = a.same ? half : Nb;  // partner steps per particle
-    const int per_clone = a.n_chunks * a.n_pgroups;
+    const int per_clone = a.n_chunks * a.n_pgroups * a.n_tsplit;
     const int n_items = pv.C * per_clone;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int c = item / per_clone;
-        const int rem = item - c * per_clone;
+        int rem = item - c * per_clone;
+        const int ts = rem % a.n_tsplit;
+        rem /= a.n_tsplit;
         const int chunk = rem / a.n_pgroups, pg = rem - chunk * a.n_pgroups;
+        const int t_begin = ts * a.t_windows * kFastQ, t_end = min(n_dd, t_begin + a.t_windows * kFastQ);
         const int s0 = chunk * kChunk;
         const int p_lo = pg * kFastWarps;
         const int p = p_lo + warp;
@@ -313,7 +319,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) pair_full_fast_kernel(const P
         if (!warp_on) my_dd = 0;
         double acc = 0.;
         const bool lane31_counts = s0 + 31 < pv.Mloc;
-        for (int t0 = 0; t0 < n_dd; t0 += kFastQ) {
+        for (int t0 = t_begin; t0 < t_end; t0 += kFastQ) {
             const int n_rows = a.same ? min(kFastQ, n_dd - t0) + kFastWarps - 1 : min(kFastQ, Nb - t0);
             const int q_first = a.same ? p_lo + t0 + 1 : t0;
             __syncthreads();  // the previous window has been consumed

@@ -133,6 +133,28 @@ class ShardedPath:
             res = out.cpu().numpy()
         return res
 
+    def RebuildRhoK(self):
+        """Species::InitRhoK of every species with rho_k (slice-local: no communication)."""
+        from . import capi
+        if self.path.n_k:
+            for sp in range(len(self.cfg.species)):
+                capi.check(self.path.L.pimc_rhok_rebuild(self.path.h, sp))
+
+    def DActionDBetaAllDevice(self, out):
+        """Every pair action's DActionDBeta into the device tensor out[action][clone], shard partial
+        sums combined by ONE all-reduce; asynchronous on the context's stream."""
+        from . import capi
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            row = 0
+            for act in self.actions:
+                if act is None:
+                    continue
+                capi.check(self.path.L.pimc_action_dbeta_device(act.h, out[row].data_ptr()))
+                row += 1
+            allreduce_sum(out, self.group)
+        return out
+
     def DActionDBeta(self, ai):
         return self._reduced(self.path.L.pimc_action_dbeta_device, self.actions[ai])
 

@@ -93,9 +93,10 @@ def ueg_config(N=256, M=128, rs=1.0, theta=1.0, action="IlkkaPairAction", use_lo
     return cfg
 
 
-def plasma_config(Ne=8, Np=8, M=16, rs=1.0, theta=1.0, n_xy=60, n_r_long=400):
+def plasma_config(Ne=8, Np=8, M=16, rs=1.0, theta=1.0, n_xy=60, n_r_long=400, pp_action="BarePairAction"):
     """Two-species hydrogen-like plasma (config C5 shape at reduced size): e-e, e-p Ilkka
-    actions and a Bare p-p action, all with long range (as inputs/C/c.xml mixes them)."""
+    actions and a p-p action -- Bare by default (as inputs/C/c.xml mixes the types), Ilkka with
+    pp_action="IlkkaPairAction" -- all with long range."""
     L, k_cut, beta = ueg_parameters(Ne, rs, theta)
     tau = beta / M
     cfg = SystemConfig(n_d=3, n_bead=M, beta=beta, L=L, pbc=True, k_cut=k_cut)
@@ -105,8 +106,11 @@ def plasma_config(Ne=8, Np=8, M=16, rs=1.0, theta=1.0, n_xy=60, n_r_long=400):
                                     table=T.make_ilkka_table(1.0, tau, L, k_cut, n_xy=n_xy, n_r_long=n_r_long)))
     cfg.actions.append(ActionConfig("CoulombEP", "IlkkaPairAction", "e", "p", max_level=0, use_long_range=True, k_cut=k_cut,
                                     table=T.make_ilkka_table(-1.0, tau, L, k_cut, n_xy=n_xy, n_r_long=n_r_long, sigma=0.4)))
-    cfg.actions.append(ActionConfig("CoulombPP", "BarePairAction", "p", "p", max_level=0, use_long_range=True, k_cut=k_cut,
-                                    table=T.make_bare_table(1.0, L, k_cut, n_r_long=n_r_long)))
+    if pp_action == "IlkkaPairAction":
+        pp_table = T.make_ilkka_table(1.0, tau, L, k_cut, n_xy=n_xy, n_r_long=n_r_long, sigma=0.3)
+    else:
+        pp_table = T.make_bare_table(1.0, L, k_cut, n_r_long=n_r_long)
+    cfg.actions.append(ActionConfig("CoulombPP", pp_action, "p", "p", max_level=0, use_long_range=True, k_cut=k_cut, table=pp_table))
     return cfg
 
 
