@@ -86,6 +86,7 @@ struct pimc_ctx {
     cudaStream_t stream = nullptr;
     int n_sm = 148;
     size_t smem_optin = 0;
+    DevBuf<double2> rho_part;  // partial rho_k of a particle-split build
     std::vector<std::unique_ptr<SpeciesState>> species;
     // KSpace (k_space_class.h:6-15)
     double k_cutoff = 0.;
@@ -299,16 +300,30 @@ int UploadKSpace(pimc_ctx *ctx) {
 }
 
 template <int TM>
-int LaunchRhokCols(pimc_ctx *ctx, int s, const KColsView &kc, double2 *rho) {
+int LaunchRhokCols(pimc_ctx *ctx, int s, KColsView kc, double2 *rho) {
     const int S = kColsWarps / kc.n_groups;
     const size_t smem = (size_t)S * 32 * ColsEntries(TM) * sizeof(double2);
     PIMC_CUDA(cudaFuncSetAttribute(rhok_build_cols_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = ctx->C * ((ctx->Mloc + S - 1) / S);
+    const int base_grid = ctx->C * ((ctx->Mloc + S - 1) / S);
+    // few (clone, slice) items and many particles: split the particle loop (partial sums, then
+    // a fixed-order reduction) until there are about two CTAs per SM
+    const int N = ctx->species[s]->N;
+    const int n_chunks32 = (N + 31) / 32;
+    int p_split = std::max(1, std::min(n_chunks32 / 4, (2 * ctx->n_sm + base_grid - 1) / base_grid));
+    kc.p_chunk = 32 * ((n_chunks32 + p_split - 1) / p_split);
+    kc.p_split = p_split = (N + kc.p_chunk - 1) / kc.p_chunk;
+    const size_t n = (size_t)ctx->C * ctx->Mloc * kc.n_k;
+    double2 *dst = rho;
+    if (p_split > 1) {
+        if (ctx->rho_part.n < n * p_split) PIMC_CUDA(ctx->rho_part.Alloc(n * p_split));
+        dst = ctx->rho_part.p;
+    }
     {
         ScopedKernelTimer t(ctx, PIMC_KERNEL_RHOK_BUILD);
-        rhok_build_cols_kernel<TM><<<grid, kColsWarps * 32, smem, ctx->stream>>>(ctx->View(), ctx->SView(s, false), kc, rho);
+        rhok_build_cols_kernel<TM><<<base_grid * p_split, kColsWarps * 32, smem, ctx->stream>>>(ctx->View(), ctx->SView(s, false), kc, dst);
+        if (p_split > 1) rhok_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dst, p_split, n, rho);
     }
-    ctx->launches++;
+    ctx->launches += p_split > 1 ? 2 : 1;
     PIMC_CUDA(cudaGetLastError());
     return PIMC_OK;
 }

@@ -290,6 +290,9 @@ struct KColsView {
     const int32_t *kmap;           // [n_cols][2 TM + 1] index of the k vector (i_x, i_y, i_z), -1 = absent
     double kbox;
     int stage_out;                 // n_k complex numbers fit in one slice's table region
+    int p_split, p_chunk;          // particles split p_split ways (p_chunk each, a multiple of 32): a launch with
+                                   // few (clone, slice) items -- one slice-sharded path -- still fills the GPU;
+                                   // part ps writes its partial sums to rho + ps * C * Mloc * n_k
 };
 
 constexpr int kColsWarps = 8;
@@ -305,8 +308,10 @@ __global__ void __launch_bounds__(kColsWarps * 32) rhok_build_cols_kernel(PathVi
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = warp / G, g = warp - s * G;
     const int groups_per_clone = (pv.Mloc + S - 1) / S;
-    const int c = blockIdx.x / groups_per_clone;
-    const int b = (blockIdx.x - c * groups_per_clone) * S + s;
+    const int ps = blockIdx.x % kc.p_split, blk = blockIdx.x / kc.p_split;
+    const int c = blk / groups_per_clone;
+    const int b = (blk - c * groups_per_clone) * S + s;
+    const int p_begin = ps * kc.p_chunk, p_end = min(sv.N, p_begin + kc.p_chunk);
     const bool valid = s < S && b < pv.Mloc;
     const int col = g * 32 + lane;
     const bool col_ok = col < kc.n_cols;
@@ -318,9 +323,9 @@ __global__ void __launch_bounds__(kColsWarps * 32) rhok_build_cols_kernel(PathVi
     double S1[TM], S2[TM], S3[TM], S4[TM];
 #pragma unroll
     for (int j = 0; j < TM; ++j) S1[j] = S2[j] = S3[j] = S4[j] = 0.;
-    for (int p0 = 0; p0 < sv.N; p0 += 32) {
+    for (int p0 = p_begin; p0 < p_end; p0 += 32) {
         if (G > 1) __syncthreads(); else __syncwarp();
-        if (g == 0 && valid && p0 + lane < sv.N) {
+        if (g == 0 && valid && p0 + lane < p_end) {
             // KSpace::CalcC (k_space_class.h:83-94): c[j] = e^{i phi} c[j-1], entries 0..TM (z: 1..TM)
             double2 *t = T + lane * E;
 #pragma unroll
@@ -339,7 +344,7 @@ __global__ void __launch_bounds__(kColsWarps * 32) rhok_build_cols_kernel(PathVi
         }
         if (G > 1) __syncthreads(); else __syncwarp();
         if (valid) {
-            const int np = min(32, sv.N - p0);
+            const int np = min(32, p_end - p0);
 #pragma unroll 4
             for (int pp = 0; pp < np; ++pp) {
                 const double2 *t = T + pp * E;
@@ -360,7 +365,7 @@ __global__ void __launch_bounds__(kColsWarps * 32) rhok_build_cols_kernel(PathVi
         }
     }
     // emit: through the slice's table region when it is large enough (coalesced 16-byte stores)
-    double2 *out = rho + ((size_t)c * pv.Mloc + (valid ? b : 0)) * kc.n_k;
+    double2 *out = rho + (((size_t)ps * pv.C + c) * pv.Mloc + (valid ? b : 0)) * kc.n_k;
     double2 *dst = kc.stage_out ? T : out;
     if (kc.stage_out) { if (G > 1) __syncthreads(); else __syncwarp(); }
     if (valid && col_ok) {
@@ -380,6 +385,19 @@ __global__ void __launch_bounds__(kColsWarps * 32) rhok_build_cols_kernel(PathVi
         if (valid)
             for (int k = g * 32 + lane; k < kc.n_k; k += 32 * G) out[k] = T[k];
     }
+}
+
+/// rho[i] = sum over the particle parts of a split build, in part order.
+__global__ void rhok_reduce_kernel(const double2 *__restrict__ part, int n_parts, size_t n, double2 *__restrict__ rho) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double2 acc = part[i];
+    for (int ps = 1; ps < n_parts; ++ps) {
+        const double2 v = part[(size_t)ps * n + i];
+        acc.x += v.x;
+        acc.y += v.y;
+    }
+    rho[i] = acc;
 }
 
 /// drho(c, j, k) = rho_bead(new position) - rho_bead(old position) of the proposal's particle

@@ -341,3 +341,28 @@ def test_slice_sharded_contexts_sum_to_the_whole_path(n_shards):
             assert np.array_equal(p.GetPositions(sp), sh.shard_positions(Rs[sp]))
     for _, p in shards:
         p.close()
+
+
+@pytest.mark.parametrize("kind", ["ueg", "plasma"])
+def test_one_large_path_fills_the_gpu_by_splitting(kind):
+    """One path with many particles and few slices (what a slice shard of BASELINE config C5
+    looks like): K1 splits an item's partner loop by windows and K2 splits the particle loop
+    (partial rho_k + fixed-order reduction) so the launch still fills the SMs.  Values against
+    the oracle; two launches give identical bits (no atomics)."""
+    from simpimc_b200 import host
+    if kind == "ueg":
+        cfg = S.ueg_config(N=300, M=8, n_xy=60, n_r_long=400)
+    else:
+        cfg = S.plasma_config(Ne=260, Np=131, M=8, pp_action="IlkkaPairAction")
+    path, oracles, _ = make_pair(cfg, 1, seed=31)
+    o = oracles[0]
+    for sp in range(len(cfg.species)):
+        got, ref = path.GetRhoK(sp, 0, host.OLD_MODE), o.rhok(sp, 0)
+        assert np.max(np.abs(got - ref)) <= 1e-12 * cfg.species[sp].n_part
+    for ai, act in enumerate(path.actions):
+        du, du2 = act.DActionDBeta(), act.DActionDBeta()
+        assert du[0] == du2[0]
+        assert rel_ok(du[0], o.dbeta(ai))
+        assert rel_ok(act.Potential()[0], o.potential(ai))
+    path.close()
+    o.close()
