@@ -177,6 +177,16 @@ int pimc_action_potential_device(pimc_action *act, double *d_out);
  * proposal's rho_k (Species::UpdateRhoK, species_class.h:406-425). */
 int pimc_action_get(pimc_action *act, int32_t mode, const int32_t *b0, int32_t n_window, int32_t n_moved,
                     const int32_t *moved_species, const int32_t *moved_particle, int32_t level, double *out);
+/* Action::GetActionGradient / GetActionLaplacian (action_class.h:46,49; pair_action_class.h:305-366):
+ * derivative of the action of the window [b0, b0 + n_window) with respect to the species-a bead of
+ * every pair that touches a listed particle (forward and backward link of each slice; Ilkka:
+ * analytic gradient + k-space force, Bare / David and every Laplacian: the reference's central
+ * differences with eps = 1e-4).  Arguments as pimc_action_get; grad is [n_clones][3], lap
+ * [n_clones] (host memory).  No proposal may be pending (the estimators run between moves). */
+int pimc_action_gradient(pimc_action *act, const int32_t *b0, int32_t n_window, int32_t n_moved, const int32_t *moved_species,
+                         const int32_t *moved_particle, int32_t level, double *grad);
+int pimc_action_laplacian(pimc_action *act, const int32_t *b0, int32_t n_window, int32_t n_moved, const int32_t *moved_species,
+                          const int32_t *moved_particle, int32_t level, double *lap);
 /* Whole-path action of every clone: GetAction(0, n_bead, all particles, 0) in OLD mode. */
 int pimc_action_total(pimc_action *act, double *out);
 int pimc_action_total_device(pimc_action *act, double *d_out);

@@ -309,6 +309,45 @@ class GpuPairAction : public Action {
         return v;
     }
 
+    /// Action::GetActionGradient / GetActionLaplacian (action_class.h:46,49): called by the
+    /// contact-density and virial estimators between moves (no proposal pending).
+    virtual vec<double> GetActionGradient(const uint32_t b0, const uint32_t b1,
+                                          const std::vector<std::pair<std::shared_ptr<Species>, uint32_t>> &particles, const uint32_t level) {
+        vec<double> g(zeros<vec<double>>(path.GetND()));
+        if (level > max_level || is_constant) return g;  // pair_action_class.h:308
+        if (mirror->stale) mirror->UploadCommitted();
+        std::vector<int32_t> sp, pi;
+        for (auto &p : particles) {
+            sp.push_back((int32_t)p.first->GetId());
+            pi.push_back((int32_t)p.second);
+        }
+        const int32_t first = (int32_t)(b0 % path.GetNBead());
+        double v[3] = {0., 0., 0.};
+        GpuPathMirror::Check(pimc_action_gradient(act, &first, (int32_t)(b1 - b0), (int32_t)sp.size(), sp.data(), pi.data(), (int32_t)level, v),
+                             "pimc_action_gradient");
+        for (uint32_t d = 0; d < path.GetND(); ++d) g(d) = v[d];
+        return g;
+    }
+
+    virtual double GetActionLaplacian(const uint32_t b0, const uint32_t b1,
+                                      const std::vector<std::pair<std::shared_ptr<Species>, uint32_t>> &particles, const uint32_t level) {
+        if (level > max_level || is_constant) return 0.;  // pair_action_class.h:342
+        if (mirror->stale) mirror->UploadCommitted();
+        std::vector<int32_t> sp, pi;
+        for (auto &p : particles) {
+            sp.push_back((int32_t)p.first->GetId());
+            pi.push_back((int32_t)p.second);
+        }
+        const int32_t first = (int32_t)(b0 % path.GetNBead());
+        double v = 0.;
+        GpuPathMirror::Check(pimc_action_laplacian(act, &first, (int32_t)(b1 - b0), (int32_t)sp.size(), sp.data(), pi.data(), (int32_t)level, &v),
+                             "pimc_action_laplacian");
+        return v;
+    }
+
+    /// PairAction::ImportanceWeight (pair_action_class.h:398-400).
+    virtual double ImportanceWeight() { return is_importance_weight ? exp(DActionDBeta() / path.GetNBead()) : 1.; }
+
     virtual void Accept() {
         mirror->Finish(true);
         pimc_action_accept(act);

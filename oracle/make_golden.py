@@ -18,6 +18,8 @@ What a fixture holds (all float64 unless noted), for one named configuration:
                                                              accept flag, rho_k and positions after commit
     gofr_<sa><sb> [n_r] (counts), gofr_bins uint32           PairCorrelation::Accumulate / ReverseMap
     sofk_<sa><sb> [n_k]                                      StructureFactor::Accumulate
+    grad_meta int64 [n][4] (species, particle, b0, n links), grad_val [n][A][3], lap_val [n][A]
+                                                             GetActionGradient / GetActionLaplacian
 The inputs are regenerated in the tests from (config name, seed) by simpimc_b200.system.
 """
 import os
@@ -136,6 +138,18 @@ def make_one(name):
                 sim.observable_accumulate(oi)
                 out["sofk_%d%d" % (sa, sb)] = sim.sofk_sums(oi)
                 oi += 1
+    # spatial derivatives on the initial configuration (the last case wraps past n_bead)
+    grng = np.random.default_rng(SEED + 3)
+    metas, gvals, lvals = [], [], []
+    for t in range(6):
+        sp = t % ns
+        p = int(grng.integers(0, cfg.species[sp].n_part))
+        n_w = [1, 3, 2, cfg.n_bead, 2, 2][t]
+        b0 = int(grng.integers(0, cfg.n_bead - n_w + 1)) if t < 5 else cfg.n_bead - 1
+        metas.append([sp, p, b0, n_w])
+        gvals.append([sim.action_gradient(a, 1, b0, b0 + n_w, [(sp, p)], 0) for a in range(n_act)])
+        lvals.append([sim.action_laplacian(a, 1, b0, b0 + n_w, [(sp, p)], 0) for a in range(n_act)])
+    out["grad_meta"], out["grad_val"], out["lap_val"] = np.array(metas, dtype=np.int64), np.array(gvals), np.array(lvals)
     # move windows: OLD / NEW action of every action touching the species, then commit
     cases = window_cases(cfg, np.random.default_rng(SEED + 2))
     out["win_n"] = np.int64(len(cases))

@@ -50,6 +50,9 @@ def lib():
         L.orc_potential.argtypes = [vp, i32]
         L.orc_get_action.restype = dbl
         L.orc_get_action.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, i32]
+        L.orc_action_gradient.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, i32, vp]
+        L.orc_action_laplacian.restype = dbl
+        L.orc_action_laplacian.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, i32]
         L.orc_calc_pair.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, vp]
         L.orc_calc_long.restype = dbl
         L.orc_calc_long.argtypes = [vp, i32, i32, i32, i32, i32]
@@ -152,6 +155,18 @@ class Oracle:
         sp = np.array([p[0] for p in particles], dtype=np.int32)
         pi = np.array([p[1] for p in particles], dtype=np.int32)
         return self.L.orc_get_action(self.h, self.actions[a], mode, b0, b1, len(particles), _p(sp), _p(pi), level)
+
+    def action_gradient(self, a, mode, b0, b1, particles, level):
+        sp = np.array([p[0] for p in particles], dtype=np.int32)
+        pi = np.array([p[1] for p in particles], dtype=np.int32)
+        out = np.zeros(3)
+        self.L.orc_action_gradient(self.h, self.actions[a], mode, b0, b1, len(particles), _p(sp), _p(pi), level, _p(out))
+        return out
+
+    def action_laplacian(self, a, mode, b0, b1, particles, level):
+        sp = np.array([p[0] for p in particles], dtype=np.int32)
+        pi = np.array([p[1] for p in particles], dtype=np.int32)
+        return self.L.orc_action_laplacian(self.h, self.actions[a], mode, b0, b1, len(particles), _p(sp), _p(pi), level)
 
     def calc_pair(self, a, which, r, rp, s, level=0):
         r, rp, s = _d(r), _d(rp), _d(s)

@@ -561,6 +561,167 @@ double GetAction(Action &a, int b0, int b1, int n, const int *sp, const int *pi,
     return tot;
 }
 
+// ---- spatial derivatives of the action (contact-density and virial estimators) -------------
+// Vector-keeping Path::DrDrpDrrp (path_class.h:153-166).
+void DrDrpDrrpVec(World &w, int b0, int b1, int s0, int s1, int p0, int p1, double &r_mag, double &r_p_mag, double &r_r_p_mag,
+                  double *r, double *r_p, double *r_r_p) {
+    const double *a0 = w.species[s0].R(w.mode, p0, b0), *a1 = w.species[s1].R(w.mode, p1, b0);
+    const double *c0 = w.species[s0].R(w.mode, p0, b1), *c1 = w.species[s1].R(w.mode, p1, b1);
+    for (int d = 0; d < w.n_d; ++d) {
+        r[d] = a1[d] - a0[d];
+        r_p[d] = c1[d] - c0[d];
+    }
+    for (int d = 0; d < w.n_d; ++d) {
+        r[d] -= std::nearbyint(r[d] * w.iL) * w.L;
+        r_p[d] += std::nearbyint((r[d] - r_p[d]) * w.iL) * w.L;
+    }
+    for (int d = 0; d < w.n_d; ++d) r_r_p[d] = r[d] - r_p[d];
+    for (int d = 0; d < w.n_d; ++d) r_r_p[d] -= std::nearbyint(r_r_p[d] * w.iL) * w.L;
+    r_mag = Mag(r, w.n_d);
+    r_p_mag = Mag(r_p, w.n_d);
+    r_r_p_mag = Mag(r_r_p, w.n_d);
+}
+
+// PairAction::CalcGradientU (pair_action_class.h:135-155): central differences, eps = 1e-4,
+// of CalcU with respect to the bead (species a, p_i, b_i); Ilkka overrides it analytically
+// (ilkka_pair_action_class.h:172-222).
+void CalcGradientU(Action &a, int b_i, int b_j, int p_i, int p_j, int level, double *tot) {
+    World &w = *a.w;
+    if (a.type == Action::ILKKA) {
+        double r[3], r_p[3], r_r_p[3], r_mag, r_p_mag, r_r_p_mag;
+        DrDrpDrrpVec(w, b_i, b_j, a.sa, a.sb, p_i, p_j, r_mag, r_p_mag, r_r_p_mag, r, r_p, r_r_p);
+        double q = 0.5 * (r_mag + r_p_mag);
+        double x = q + 0.5 * r_r_p_mag;
+        double y = q - 0.5 * r_r_p_mag;
+        double u = 0., g[2];
+        a.u_xy.EvalVG(x, y, &u, g);
+        double rh[3], sh[3];
+        for (int d = 0; d < w.n_d; ++d) {
+            rh[d] = r[d] / r_mag;
+            sh[d] = r_r_p[d] / r_r_p_mag;
+        }
+        if (r_mag == 0.)
+            for (int d = 0; d < w.n_d; ++d) rh[d] = 0.;
+        if (r_r_p_mag == 0.)
+            for (int d = 0; d < w.n_d; ++d) sh[d] = 0.;
+        for (int d = 0; d < w.n_d; ++d) tot[d] = -0.5 * (g[0] * (rh[d] + sh[d]) + g[1] * (rh[d] - sh[d]));
+        if (a.use_long_range) {
+            SetLimits(a.u_long.r_min, a.u_long.r_max, r_mag, r_p_mag);
+            double tmp_u, tmp_du_dr;
+            a.u_long.r_spline.EvalVG(r_mag, &tmp_u, &tmp_du_dr);
+            for (int d = 0; d < w.n_d; ++d) tot[d] -= 0.5 * tmp_du_dr * rh[d];
+        }
+        return;
+    }
+    double *b = w.species[a.sa].R(w.mode, p_i, b_i);
+    double r0[3] = {b[0], b[1], b[2]};
+    const double eps = 1.e-4;
+    double r_mag, r_p_mag, r_r_p_mag;
+    for (int d = 0; d < w.n_d; ++d) {
+        b[d] = r0[d] + eps;
+        w.DrDrpDrrp(b_i, b_j, a.sa, a.sb, p_i, p_j, r_mag, r_p_mag, r_r_p_mag);
+        double f1 = CalcU(a, r_mag, r_p_mag, r_r_p_mag, level);
+        b[d] = r0[d] - eps;
+        w.DrDrpDrrp(b_i, b_j, a.sa, a.sb, p_i, p_j, r_mag, r_p_mag, r_r_p_mag);
+        double f2 = CalcU(a, r_mag, r_p_mag, r_r_p_mag, level);
+        tot[d] = (f1 - f2) / (2. * eps);
+        b[d] = r0[d];
+    }
+}
+
+// CalcGradientULong(b_0, b_1, p_i, level): zero in the base class (pair_action_class.h:163-165),
+// the k-space force on bead (species a, p_i) for Ilkka (ilkka_pair_action_class.h:231-249).
+void CalcGradientULong(Action &a, int b_0, int b_1, int p_i, int level, double *tot) {
+    World &w = *a.w;
+    for (int d = 0; d < w.n_d; ++d) tot[d] = 0.;
+    if (a.type != Action::ILKKA) return;
+    const std::vector<cplx> &rb = w.RhoK(a.sb);
+    const size_t n_k = w.ks.n_k();
+    const int skip = 1 << level;
+    std::vector<cplx> ra(n_k);
+    for (int b_i = b_0; b_i < b_1; b_i += skip) {
+        w.BeadRhoK(w.species[a.sa].R(w.mode, p_i, b_i), ra.data());  // the bead's own rho_k (bead_class.h:125-133)
+        const int bl = w.species[a.sb].bead_loop(b_i);
+        for (size_t k = 0; k < n_k; k++) {
+            const double f = ra[k].real() * rb[bl * n_k + k].imag() - ra[k].imag() * rb[bl * n_k + k].real();
+            for (int d = 0; d < w.n_d; ++d) tot[d] += (a.u_long.f_k[k] * w.ks.vecs[k * w.n_d + d]) * f;
+        }
+    }
+    if (a.sa != a.sb)
+        for (int d = 0; d < w.n_d; ++d) tot[d] *= 2.;
+}
+
+// PairAction::CalcLaplacianU (pair_action_class.h:168-203): second central differences of CalcU.
+double CalcLaplacianU(Action &a, int b_i, int b_j, int p_i, int p_j, int level) {
+    World &w = *a.w;
+    double *b = w.species[a.sa].R(w.mode, p_i, b_i);
+    double r0[3] = {b[0], b[1], b[2]};
+    const double eps = 1.e-4;
+    double r_mag, r_p_mag, r_r_p_mag, tot = 0.;
+    w.DrDrpDrrp(b_i, b_j, a.sa, a.sb, p_i, p_j, r_mag, r_p_mag, r_r_p_mag);
+    double f0 = CalcU(a, r_mag, r_p_mag, r_r_p_mag, level);
+    for (int d = 0; d < w.n_d; ++d) {
+        b[d] = r0[d] + eps;
+        w.DrDrpDrrp(b_i, b_j, a.sa, a.sb, p_i, p_j, r_mag, r_p_mag, r_r_p_mag);
+        double fp1 = CalcU(a, r_mag, r_p_mag, r_r_p_mag, level);
+        b[d] = r0[d] - eps;
+        w.DrDrpDrrp(b_i, b_j, a.sa, a.sb, p_i, p_j, r_mag, r_p_mag, r_r_p_mag);
+        double fm1 = CalcU(a, r_mag, r_p_mag, r_r_p_mag, level);
+        tot += (fp1 + fm1 - 2 * f0) / (eps * eps);
+        b[d] = r0[d];
+    }
+    return tot;
+}
+
+// PairAction::GetActionGradient (pair_action_class.h:305-337): the forward link (b_i, b_i + skip)
+// and the backward link (b_i, b_i - skip + n_bead) of every pair; the long-range term once per
+// PAIR (sic), always for the pair's species-a particle.
+void GetActionGradient(Action &a, int b0, int b1, int n, const int *sp, const int *pi, int level, double *tot) {
+    World &w = *a.w;
+    for (int d = 0; d < w.n_d; ++d) tot[d] = 0.;
+    if (level > a.max_level || a.is_constant) return;
+    std::vector<int> pa, pb;
+    std::vector<std::pair<int, int>> pairs;
+    MovedPairs(a, n, sp, pi, pa, pb, pairs);
+    if (pairs.size() == 0) return;
+    const int skip = 1 << level;
+    double g[3];
+    for (int b_i = b0; b_i < b1; b_i += skip) {
+        int b_j = b_i + skip;
+        int b_k = b_i - skip + w.species[a.sa].n_bead;
+        for (auto &pp : pairs) {
+            CalcGradientU(a, b_i, b_j, pp.first, pp.second, level, g);
+            for (int d = 0; d < w.n_d; ++d) tot[d] += g[d];
+            CalcGradientU(a, b_i, b_k, pp.first, pp.second, level, g);
+            for (int d = 0; d < w.n_d; ++d) tot[d] += g[d];
+        }
+    }
+    if (a.use_long_range)
+        for (auto &pp : pairs) {
+            CalcGradientULong(a, b0, b1, pp.first, level, g);
+            for (int d = 0; d < w.n_d; ++d) tot[d] += g[d];
+        }
+}
+
+// PairAction::GetActionLaplacian (pair_action_class.h:340-366); no long-range part ("FIXME" there).
+double GetActionLaplacian(Action &a, int b0, int b1, int n, const int *sp, const int *pi, int level) {
+    World &w = *a.w;
+    if (level > a.max_level || a.is_constant) return 0.;
+    std::vector<int> pa, pb;
+    std::vector<std::pair<int, int>> pairs;
+    MovedPairs(a, n, sp, pi, pa, pb, pairs);
+    if (pairs.size() == 0) return 0.;
+    const int skip = 1 << level;
+    double tot = 0.;
+    for (int b_i = b0; b_i < b1; b_i += skip) {
+        int b_j = b_i + skip;
+        int b_k = b_i - skip + w.species[a.sa].n_bead;
+        for (auto &pp : pairs)
+            tot += CalcLaplacianU(a, b_i, b_j, pp.first, pp.second, level) + CalcLaplacianU(a, b_i, b_k, pp.first, pp.second, level);
+    }
+    return tot;
+}
+
 // ---- construction -----------------------------------------------------------------------
 void LoadLongRange(World &w, LongRange &lr, const pimc_long_range &t) {
     // ilkka_pair_action_class.h:283-316 (same block three times; bare...:53-86)
@@ -819,6 +980,16 @@ double orc_get_action(void *h, int a, int mode, int b0, int b1, int n, const int
     World *w = (World *)h;
     w->mode = mode;
     return GetAction(*w->actions[a], b0, b1, n, sp, pi, level);
+}
+void orc_action_gradient(void *h, int a, int mode, int b0, int b1, int n, const int *sp, const int *pi, int level, double *out) {
+    World *w = (World *)h;
+    w->mode = mode;
+    GetActionGradient(*w->actions[a], b0, b1, n, sp, pi, level, out);
+}
+double orc_action_laplacian(void *h, int a, int mode, int b0, int b1, int n, const int *sp, const int *pi, int level) {
+    World *w = (World *)h;
+    w->mode = mode;
+    return GetActionLaplacian(*w->actions[a], b0, b1, n, sp, pi, level);
 }
 void orc_calc_pair(void *h, int a, int which, int n, const double *r, const double *rp, const double *s, int level, double *out) {
     World *w = (World *)h;

@@ -279,6 +279,24 @@ double ref_get_action(void *h, int a, int mode, int b0, int b1, int n, const int
     return s->actions[a]->GetAction(b0, b1, particles, level);
 }
 
+/// Action::GetActionGradient / GetActionLaplacian (pair_action_class.h:305-366).
+void ref_action_gradient(void *h, int a, int mode, int b0, int b1, int n, const int *sp, const int *pi, int level, double *out) {
+    RefSim *s = (RefSim *)h;
+    std::vector<std::pair<std::shared_ptr<Species>, uint32_t>> particles;
+    for (int i = 0; i < n; ++i) particles.push_back(std::make_pair(s->path->GetSpecies()[sp[i]], (uint32_t)pi[i]));
+    s->path->SetMode(mode ? NEW_MODE : OLD_MODE);
+    vec<double> g = s->actions[a]->GetActionGradient(b0, b1, particles, level);
+    for (uint32_t d = 0; d < s->path->GetND(); ++d) out[d] = g(d);
+}
+
+double ref_action_laplacian(void *h, int a, int mode, int b0, int b1, int n, const int *sp, const int *pi, int level) {
+    RefSim *s = (RefSim *)h;
+    std::vector<std::pair<std::shared_ptr<Species>, uint32_t>> particles;
+    for (int i = 0; i < n; ++i) particles.push_back(std::make_pair(s->path->GetSpecies()[sp[i]], (uint32_t)pi[i]));
+    s->path->SetMode(mode ? NEW_MODE : OLD_MODE);
+    return s->actions[a]->GetActionLaplacian(b0, b1, particles, level);
+}
+
 void ref_action_accept(void *h, int a, int accept) {
     RefSim *s = (RefSim *)h;
     if (accept)

@@ -62,6 +62,10 @@ def _load(fast=False, dropin=False):
     lib.ref_get_action.restype = C.c_double
     lib.ref_get_action.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, C.c_int]
     lib.ref_action_accept.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    if hasattr(lib, "ref_action_gradient"):
+        lib.ref_action_gradient.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, C.c_int, _dp]
+        lib.ref_action_laplacian.restype = C.c_double
+        lib.ref_action_laplacian.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, C.c_int]
     lib.ref_calc_pair.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _dp]
     lib.ref_dr_drp_drrp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp]
     lib.ref_calc_long.restype = C.c_double
@@ -219,6 +223,18 @@ class RefSim:
         sp = np.array([p[0] for p in particles], dtype=np.int32)
         pi = np.array([p[1] for p in particles], dtype=np.int32)
         return self.lib.ref_get_action(self.h, a, mode, b0, b1, len(particles), sp, pi, level)
+
+    def action_gradient(self, a, mode, b0, b1, particles, level):
+        sp = np.array([p[0] for p in particles], dtype=np.int32)
+        pi = np.array([p[1] for p in particles], dtype=np.int32)
+        out = np.zeros(3)
+        self.lib.ref_action_gradient(self.h, a, mode, b0, b1, len(particles), sp, pi, level, out)
+        return out
+
+    def action_laplacian(self, a, mode, b0, b1, particles, level):
+        sp = np.array([p[0] for p in particles], dtype=np.int32)
+        pi = np.array([p[1] for p in particles], dtype=np.int32)
+        return self.lib.ref_action_laplacian(self.h, a, mode, b0, b1, len(particles), sp, pi, level)
 
     def calc_pair(self, a, which, r, rp, s, level=0):
         r = np.ascontiguousarray(r, dtype=np.float64)

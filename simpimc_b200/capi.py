@@ -147,7 +147,7 @@ EXPORTS = [
     "pimc_positions_set_device", "pimc_positions_device_ptr", "pimc_rhok_rebuild", "pimc_rhok_download",
     "pimc_action_create_ilkka", "pimc_action_create_bare", "pimc_action_create_david", "pimc_action_destroy",
     "pimc_action_dbeta", "pimc_action_potential", "pimc_action_dbeta_device", "pimc_action_potential_device",
-    "pimc_action_get", "pimc_action_total", "pimc_action_total_device", "pimc_action_accept", "pimc_action_reject",
+    "pimc_action_get", "pimc_action_gradient", "pimc_action_laplacian", "pimc_action_total", "pimc_action_total_device", "pimc_action_accept", "pimc_action_reject",
     "pimc_action_calc_pair", "pimc_propose", "pimc_beads_download", "pimc_commit", "pimc_est_gofr", "pimc_est_gofr_counts", "pimc_est_sofk",
     "pimc_ctx_launch_count", "pimc_fp64_peak", "pimc_ctx_set_timing", "pimc_ctx_kernel_time",
     "pimc_action_calc_pair_fast", "pimc_debug_fast_sqrt", "pimc_ctx_force_general", "pimc_bisect_sweep", "pimc_halo_pack", "pimc_halo_unpack",
@@ -191,6 +191,8 @@ def lib():
               "pimc_action_total", "pimc_action_total_device"):
         getattr(L, n).argtypes = [vp, vp]
     L.pimc_action_get.argtypes = [vp, i32, vp, i32, i32, vp, vp, i32, vp]
+    L.pimc_action_gradient.argtypes = [vp, vp, i32, i32, vp, vp, i32, vp]
+    L.pimc_action_laplacian.argtypes = [vp, vp, i32, i32, vp, vp, i32, vp]
     L.pimc_action_accept.argtypes = [vp]
     L.pimc_action_reject.argtypes = [vp]
     L.pimc_action_calc_pair.argtypes = [vp, i32, i32, vp, vp, vp, i32, vp]

@@ -19,6 +19,7 @@
 #include "pair_fast.cuh"
 #include "mc.cuh"
 #include "sweep_fused.cuh"
+#include "grad.cuh"
 #include "spline_build.h"
 
 using namespace pimc;
@@ -1341,6 +1342,114 @@ int pimc_action_get(pimc_action *act, int32_t mode, const int32_t *b0, int32_t n
     rc = Finalize(ctx, n_window, act->use_long_range, 0., 0., false, ctx->out_dev.p);
     if (rc != PIMC_OK) return rc;
     return ToHost(ctx, ctx->out_dev.p, out, ctx->C);
+}
+
+// --------------------------------------------------------- spatial derivatives of the action
+/// what = 0: GetActionGradient -> out[C][3]; what = 1: GetActionLaplacian -> out[C].
+static int ActionDerivative(pimc_action *act, const int32_t *b0, int32_t n_window, int32_t n_moved, const int32_t *moved_species,
+                            const int32_t *moved_particle, int32_t level, int what, double *out) {
+    if (!act || !out || !b0 || (n_moved > 0 && (!moved_species || !moved_particle))) return Fail(PIMC_ERR_INVALID, "null argument");
+    pimc_ctx *ctx = act->ctx;
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    const int nv = what ? 1 : 3;
+    auto zero = [&]() {
+        for (size_t i = 0; i < (size_t)ctx->C * nv; ++i) out[i] = 0.;
+        return PIMC_OK;
+    };
+    if (level > act->max_level || act->is_constant) return zero();  // pair_action_class.h:308,342
+    if (ctx->sharded) return Fail(PIMC_ERR_UNSUPPORTED, "action derivatives on a slice-sharded context");
+    if (n_window < 1 || n_window > ctx->M) return Fail(PIMC_ERR_INVALID, "window must cover 1..n_bead slices");
+    if (ctx->species[act->sa]->n_prop > 0 || ctx->species[act->sb]->n_prop > 0)
+        return Fail(PIMC_ERR_UNSUPPORTED, "action derivatives while a proposal is pending (estimators run between moves)");
+    int ia = -1, ib = -1;
+    for (int i = 0; i < n_moved; ++i) {
+        if (moved_species[i] == act->sa) {
+            if (ia >= 0) return Fail(PIMC_ERR_UNSUPPORTED, "two listed particles of one species");
+            ia = i;
+        } else if (moved_species[i] == act->sb) {
+            if (ib >= 0) return Fail(PIMC_ERR_UNSUPPORTED, "two listed particles of one species");
+            ib = i;
+        }
+    }
+    if (act->sa == act->sb) ib = -1;
+    if (ia < 0 && ib < 0) return zero();
+    const int Na = ctx->species[act->sa]->N, Nb = ctx->species[act->sb]->N;
+    std::vector<int32_t> pa(ctx->C, 0), pb(ctx->C, 0);
+    for (int c = 0; c < ctx->C; ++c) {
+        if (ia >= 0) pa[c] = moved_particle[(size_t)c * n_moved + ia];
+        if (ib >= 0) pb[c] = moved_particle[(size_t)c * n_moved + ib];
+        if (b0[c] < 0 || b0[c] >= ctx->M) return Fail(PIMC_ERR_INVALID, "window start out of range");
+        if (ia >= 0 && (pa[c] < 0 || pa[c] >= Na)) return Fail(PIMC_ERR_INVALID, "listed particle out of range");
+        if (ib >= 0 && (pb[c] < 0 || pb[c] >= Nb)) return Fail(PIMC_ERR_INVALID, "listed particle out of range");
+    }
+    int rc;
+    if ((rc = EnsureI32(ctx, ctx->i32_a, pa.data(), ctx->C)) != PIMC_OK) return rc;
+    if ((rc = EnsureI32(ctx, ctx->i32_b, pb.data(), ctx->C)) != PIMC_OK) return rc;
+    if ((rc = EnsureI32(ctx, ctx->i32_c, b0, ctx->C)) != PIMC_OK) return rc;
+    PairGradArgs w;
+    w.pv = ctx->View();
+    w.A = ctx->SView(act->sa, false);
+    w.B = ctx->SView(act->sb, false);
+    w.same = act->sa == act->sb;
+    w.moved_a = ia >= 0;
+    w.moved_b = ib >= 0;
+    w.part_a = ctx->i32_a.p;
+    w.part_b = ctx->i32_b.p;
+    w.b0 = ctx->i32_c.p;
+    w.n_links = n_window;
+    w.what = what;
+    w.T = act->table[WHICH_U];
+    w.blob = act->blob[WHICH_U].p;
+    const size_t items = (size_t)ctx->C * n_window;
+    if (ctx->partial.n < items * nv) PIMC_CUDA(ctx->partial.Alloc(items * nv));
+    w.partial = ctx->partial.p;
+    const int grid = (int)std::min<size_t>(items, (size_t)ctx->n_sm * 16);
+    switch (act->atype) {
+        case ATYPE_ILKKA: pair_grad_kernel<ATYPE_ILKKA><<<grid, 128, 0, ctx->stream>>>(w); break;
+        case ATYPE_BARE: pair_grad_kernel<ATYPE_BARE><<<grid, 128, 0, ctx->stream>>>(w); break;
+        default: pair_grad_kernel<ATYPE_DAVID><<<grid, 128, 0, ctx->stream>>>(w); break;
+    }
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    // long-range part of the gradient: Ilkka only (the base class returns zero, pair_action_class.h:163-165)
+    const bool lr = what == 0 && act->atype == ATYPE_ILKKA && act->use_long_range && ctx->n_k() > 0;
+    if ((size_t)ctx->lr_dev.n < (size_t)ctx->C * 3) PIMC_CUDA(ctx->lr_dev.Alloc((size_t)ctx->C * 3));
+    if (lr) {
+        GradLongArgs g;
+        g.pv = w.pv;
+        g.A = w.A;
+        g.ks = ctx->KView();
+        g.rho_b = ctx->species[act->sb]->rho.p;
+        g.wk = act->wk[WHICH_U].p;
+        g.part_a = ia >= 0 ? ctx->i32_a.p : nullptr;
+        g.b0 = ctx->i32_c.p;
+        g.n_links = n_window;
+        g.mult_moved = w.same ? Na - 1 : Nb;
+        g.mult_others = ib >= 0 ? 1 : 0;
+        g.factor = w.same ? 1. : 2.;
+        g.out = ctx->lr_dev.p;
+        const size_t smem = (size_t)32 * 3 * (2 * ctx->max_index + 1) * sizeof(double2);
+        if (smem > 48 * 1024) PIMC_CUDA(cudaFuncSetAttribute(grad_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        grad_long_kernel<<<ctx->C, 256, smem, ctx->stream>>>(g);
+        ctx->launches++;
+        PIMC_CUDA(cudaGetLastError());
+    }
+    if ((size_t)ctx->out_dev.n < (size_t)ctx->C * 3) PIMC_CUDA(ctx->out_dev.Alloc((size_t)ctx->C * 3));
+    grad_finalize_kernel<<<(ctx->C * nv + 127) / 128, 128, 0, ctx->stream>>>(ctx->partial.p, ctx->C, n_window, nv, lr ? ctx->lr_dev.p : nullptr,
+                                                                              ctx->out_dev.p);
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    return ToHost(ctx, ctx->out_dev.p, out, (size_t)ctx->C * nv);
+}
+
+int pimc_action_gradient(pimc_action *act, const int32_t *b0, int32_t n_window, int32_t n_moved, const int32_t *moved_species,
+                         const int32_t *moved_particle, int32_t level, double *grad) {
+    return ActionDerivative(act, b0, n_window, n_moved, moved_species, moved_particle, level, 0, grad);
+}
+
+int pimc_action_laplacian(pimc_action *act, const int32_t *b0, int32_t n_window, int32_t n_moved, const int32_t *moved_species,
+                          const int32_t *moved_particle, int32_t level, double *lap) {
+    return ActionDerivative(act, b0, n_window, n_moved, moved_species, moved_particle, level, 1, lap);
 }
 
 static int ArmFlags(pimc_action *act) {

@@ -193,6 +193,7 @@ class PairAction:
         self.type = acfg.type
         self.use_long_range = acfg.use_long_range
         self.max_level = acfg.max_level
+        self.is_importance_weight = bool(getattr(acfg, "is_importance_weight", False))  # action_class.h:31
         cfg = path.cfg
         sa, sb = cfg.species_index(acfg.species_a), cfg.species_index(acfg.species_b)
         self.species_a, self.species_b = sa, sb
@@ -242,6 +243,40 @@ class PairAction:
         capi.check(self.L.pimc_action_get(self.h, self.path.mode, _vp(b0a), n_window, len(particles), _vp(sp), _vp(pi), level,
                                           _vp(out)))
         return out
+
+    def _window_args(self, b0, b1, particles):
+        C_ = self.path.n_clones
+        b0a = np.ascontiguousarray(np.broadcast_to(b0, (C_,)), dtype=np.int32)
+        n_window = int(np.broadcast_to(b1, (C_,))[0] - b0a[0])
+        sp = np.ascontiguousarray([p[0] for p in particles], dtype=np.int32)
+        pi = np.zeros((C_, len(particles)), dtype=np.int32)
+        for i, p in enumerate(particles):
+            pi[:, i] = np.broadcast_to(p[1], (C_,))
+        return b0a, n_window, sp, pi
+
+    def GetActionGradient(self, b0, b1, particles, level):
+        """Action::GetActionGradient (action_class.h:46): [clone][3]; arguments as GetAction."""
+        b0a, n_window, sp, pi = self._window_args(b0, b1, particles)
+        out = np.zeros((self.path.n_clones, 3))
+        capi.check(self.L.pimc_action_gradient(self.h, _vp(b0a), n_window, len(particles), _vp(sp), _vp(pi), level, _vp(out)))
+        return out
+
+    def GetActionLaplacian(self, b0, b1, particles, level):
+        """Action::GetActionLaplacian (action_class.h:49): one value per clone."""
+        b0a, n_window, sp, pi = self._window_args(b0, b1, particles)
+        out = np.zeros(self.path.n_clones)
+        capi.check(self.L.pimc_action_laplacian(self.h, _vp(b0a), n_window, len(particles), _vp(sp), _vp(pi), level, _vp(out)))
+        return out
+
+    def VirialEnergy(self, virial_window_size=1):
+        """Action::VirialEnergy (action_class.h:40): DActionDBeta for every pair action."""
+        return self.DActionDBeta()
+
+    def ImportanceWeight(self):
+        """PairAction::ImportanceWeight (pair_action_class.h:398-400)."""
+        if not self.is_importance_weight:
+            return np.ones(self.path.n_clones)
+        return np.exp(self.DActionDBeta() / self.path.n_bead)
 
     def Accept(self):
         capi.check(self.L.pimc_action_accept(self.h))

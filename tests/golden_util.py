@@ -77,6 +77,12 @@ class OracleBackend:
     def sofk(self, sa, sb):
         return self.o.sofk(sa, sb, self.cfg.k_cut)
 
+    def gradient(self, a, b0, b1, sp, p):
+        return self.o.action_gradient(a, 1, b0, b1, [(sp, p)], 0)
+
+    def laplacian(self, a, b0, b1, sp, p):
+        return self.o.action_laplacian(a, 1, b0, b1, [(sp, p)], 0)
+
     def propose(self, sp, p, first, newR):
         self.o.propose(sp, p, first, newR)
 
@@ -141,6 +147,14 @@ class GpuBackend:
         assert np.array_equal(sk.sk[0], sk.sk[1])
         return sk.sk[0]
 
+    def gradient(self, a, b0, b1, sp, p):
+        g = self.path.actions[a].GetActionGradient(b0, b1, [(sp, p)], 0)
+        assert np.array_equal(g[0], g[1])
+        return g[0]
+
+    def laplacian(self, a, b0, b1, sp, p):
+        return self._both(self.path.actions[a].GetActionLaplacian(b0, b1, [(sp, p)], 0))
+
     def propose(self, sp, p, first, newR):
         self.path.Propose(sp, p, first, np.stack([newR, newR]))
 
@@ -186,6 +200,21 @@ def check_backend(name, make_backend):
             if has_k:
                 ref = g["sofk_%d%d" % (sa, sb)]
                 assert np.max(np.abs(be.sofk(sa, sb) - ref)) <= 1e-10 * max(1.0, np.max(np.abs(ref)))
+    # spatial derivatives (pair_action_class.h:305-366).  Analytic Ilkka gradients: RTOL of the
+    # largest component; central differences (eps = 1e-4) amplify the rounding of U by 1 / eps
+    # (gradient) and 1 / eps^2 (Laplacian): RTOL of |U of the window's pairs| / eps resp. / eps^2
+    if "grad_meta" in g:
+        eps = 1e-4
+        for t, (sp, p, b0, n_w) in enumerate(g["grad_meta"].tolist()):
+            for a in range(n_act):
+                g_ref, l_ref = g["grad_val"][t][a], g["lap_val"][t][a]
+                u_scale = 2.0 * abs(be.get_action(a, 0, b0, b0 + n_w, sp, p)) + 1e-3   # OLD mode: leaves the rho_k refresh flag alone
+                analytic = cfg.actions[a].type == "IlkkaPairAction"
+                got = be.gradient(a, b0, b0 + n_w, sp, p)
+                tol = RTOL * max(np.max(np.abs(g_ref)), u_scale if analytic else u_scale / eps)
+                assert np.max(np.abs(got - g_ref)) <= tol, (name, "gradient", t, a, got, g_ref)
+                got = be.laplacian(a, b0, b0 + n_w, sp, p)
+                assert abs(got - l_ref) <= RTOL * max(abs(l_ref), u_scale / eps ** 2), (name, "laplacian", t, a, got, l_ref)
     for t in range(int(g["win_n"])):
         sp, p, b0, nb, n_beads, first, accept = [int(v) for v in g["win_%d_meta" % t]]
         be.propose(sp, p, first, g["win_%d_newR" % t])

@@ -54,6 +54,17 @@ def test_reference_moves_on_gpu_actions_reproduce_the_reference_run(which):
         assert att == 150 and 0 < acc
     for sp in range(len(cfg.species)):
         assert np.array_equal(a.get_positions(sp, 0), b.get_positions(sp, 0)), "trajectories diverged"
+    # the adapter's GetActionGradient / GetActionLaplacian after the run (pair actions only: Kinetic is the reference's own)
+    for ai, acfg in enumerate(cfg.actions):
+        if acfg.type == "Kinetic":
+            continue
+        for sp, p, b0, b1 in ((0, 1, 3, 6), (len(cfg.species) - 1, 2, cfg.n_bead - 1, cfg.n_bead)):
+            ga, gb = a.action_gradient(ai, 1, b0, b1, [(sp, p)], 0), b.action_gradient(ai, 1, b0, b1, [(sp, p)], 0)
+            la, lb = a.action_laplacian(ai, 1, b0, b1, [(sp, p)], 0), b.action_laplacian(ai, 1, b0, b1, [(sp, p)], 0)
+            u = 2.0 * abs(a.get_action(ai, 0, b0, b1, [(sp, p)], 0)) + 1e-3
+            analytic = acfg.type == "IlkkaPairAction"
+            assert np.max(np.abs(ga - gb)) <= 1e-10 * max(np.max(np.abs(ga)), u if analytic else u / 1e-4), (ai, ga, gb)
+            assert abs(la - lb) <= 1e-10 * max(abs(la), u / 1e-8), (ai, la, lb)
     ea, va = a.energy_sums(0)
     eb, vb = b.energy_sums(0)
     assert np.all(np.abs(ea - eb) <= 1e-10 * np.maximum(np.abs(ea), 1e-300)), (ea, eb)

@@ -366,3 +366,44 @@ def test_one_large_path_fills_the_gpu_by_splitting(kind):
         assert rel_ok(act.Potential()[0], o.potential(ai))
     path.close()
     o.close()
+
+
+@pytest.mark.parametrize("name", ["ilkka_lr_n7", "ilkka_nolr_n8", "bare_lr_n7", "david_n7", "plasma"])
+def test_action_gradient_and_laplacian(name):
+    """Action::GetActionGradient / GetActionLaplacian (pair_action_class.h:305-366) against the
+    oracle.  Ilkka gradients are analytic: 1e-10 relative to the sum of |link terms|.  The Bare /
+    David gradients and every Laplacian are the reference's own central differences with
+    eps = 1e-4, whose rounding noise is |U| * 2^-52 / eps (gradient) and / eps^2 (Laplacian): the
+    bound is 1e-10 of the size of the differenced terms, |U_window| / eps resp. / eps^2."""
+    cfg = CONFIGS[name]()
+    C_ = 3
+    path, oracles, _ = make_pair(cfg, C_, seed=77)
+    M = cfg.n_bead
+    rng = np.random.default_rng(5)
+    eps = 1e-4
+    for trial in range(4):
+        sp = trial % len(cfg.species)
+        parts = [(sp, rng.integers(0, cfg.species[sp].n_part, size=C_))]
+        if trial == 3 and len(cfg.species) > 1:   # one particle of each species listed
+            parts.append((1 - sp, rng.integers(0, cfg.species[1 - sp].n_part, size=C_)))
+        b0 = rng.integers(0, M - 3, size=C_) if trial < 3 else np.full(C_, M - 2)
+        n_w = 3 if trial < 3 else 2
+        for ai, act in enumerate(path.actions):
+            g = act.GetActionGradient(b0, b0 + n_w, parts, 0)
+            lap = act.GetActionLaplacian(b0, b0 + n_w, parts, 0)
+            for c, o in enumerate(oracles):
+                pl = [(s, int(p[c])) for s, p in parts]
+                g_ref = o.action_gradient(ai, 1, int(b0[c]), int(b0[c]) + n_w, pl, 0)
+                l_ref = o.action_laplacian(ai, 1, int(b0[c]), int(b0[c]) + n_w, pl, 0)
+                # size of the terms: |U| of the window's pairs, forward and backward links
+                u_scale = 2.0 * abs(o.get_action(ai, 1, int(b0[c]), int(b0[c]) + n_w, pl, 0)) + 1e-3
+                analytic = cfg.actions[ai].type == "IlkkaPairAction"
+                g_tol = RTOL * max(np.max(np.abs(g_ref)), u_scale if analytic else u_scale / eps)
+                assert np.max(np.abs(g[c] - g_ref)) <= g_tol, (name, trial, ai, c, g[c], g_ref)
+                assert abs(lap[c] - l_ref) <= RTOL * max(abs(l_ref), u_scale / eps ** 2), (name, trial, ai, c, lap[c], l_ref)
+    # level above max_level: zero, as the reference returns
+    assert np.all(path.actions[0].GetActionGradient(0, 2, [(0, 0)], 1) == 0.0)
+    assert np.all(path.actions[0].GetActionLaplacian(0, 2, [(0, 0)], 1) == 0.0)
+    path.close()
+    for o in oracles:
+        o.close()
