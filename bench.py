@@ -295,6 +295,21 @@ def run_ours(args):
         bis.DoEvent()
     path.Sync()
     host_driven_sweeps_per_s = C * 4 / attempts_per_sweep / (time.perf_counter() - s0)
+    # ---- estimators: g(r) histogram (K5) and S(k) (K6) over every clone ---------------------------
+    gr = host.PairCorrelation(path, 0, 0, 0.0, cfg.L / 2.0, 100)
+    sk = host.StructureFactor(path, 0, 0, cfg.k_cut)
+    gr.Accumulate()
+    sk.Accumulate()
+    path.SetTiming(True)
+    for _ in range(2):
+        gr.Accumulate()
+        sk.Accumulate()
+    k5_ms, k5_n = path.KernelTime(5)
+    k6_ms, k6_n = path.KernelTime(6)
+    path.SetTiming(False)
+    estimators = {"gofr_kernel_ms": k5_ms / max(1, k5_n), "gofr_pair_slices_per_s": C * pair_evals_per_clone() / (k5_ms / max(1, k5_n) * 1e-3),
+                  "sofk_kernel_ms": k6_ms / max(1, k6_n), "sofk_gbs": C * N_SLICE * 182 * 16 / (k6_ms / max(1, k6_n) * 1e-3) / 1e9,
+                  "unit": "one PairCorrelation::Accumulate / StructureFactor::Accumulate over all clones (kernel time, CUDA events)"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -344,6 +359,7 @@ def run_ours(args):
                    "pair_window_kernel_ms_per_attempt": k4_ms / max(1, n_att),
                    "driver": "device-resident pimc_bisect_sweep (Philox stream; kinetic + Ilkka pair + long-range deltas, Metropolis, commit)",
                    "host_driven_sweeps_per_s_per_gpu": host_driven_sweeps_per_s},
+            "estimators": estimators,
             "roofline": roofline}
     if base:
         line["cpu_baseline"] = base

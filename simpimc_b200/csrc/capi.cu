@@ -1783,9 +1783,33 @@ int pimc_est_gofr_counts(pimc_ctx *ctx, int32_t sa, int32_t sb, double r_min, do
     g.d_ir = 1. / dr;
     g.n_r = n_r;
     g.counts = ctx->counts.p;
-    const int items = ctx->C * ctx->Mloc;
-    {
-        ScopedKernelTimer t(ctx, PIMC_KERNEL_GOFR);
+    // tiled kernel (K5 v2): the largest tile whose two copies leave room for the histograms
+    const int Na = g.A.N, Nb = g.B.N;
+    GofrTiledArgs t;
+    t.g = g;
+    t.T = 0;
+    t.warp_hist = 0;
+    for (int pass = 0; pass < 2 && t.T == 0; ++pass)  // per-warp histograms if they fit beside some tile size, else one per CTA
+        for (int T : {128, 64, 32}) {
+            const size_t need = (size_t)2 * T * 3 * kGofrRow * sizeof(double) + (size_t)(pass == 0 ? kGofrThreads / 32 : 1) * n_r * sizeof(unsigned int) + 1024;
+            if (need > ctx->smem_optin) continue;
+            t.T = T;
+            t.warp_hist = pass == 0 ? 1 : 0;
+            break;
+        }
+    if (t.T > 0 && !ctx->force_general) {
+        t.T = std::min(t.T, 32 * ((std::max(Na, Nb) + 31) / 32));
+        t.n_ti = (Na + t.T - 1) / t.T;
+        t.n_tj = (Nb + t.T - 1) / t.T;
+        t.n_chunks = (ctx->Mloc + 31) / 32;
+        const size_t smem = (size_t)2 * t.T * 3 * kGofrRow * sizeof(double) + (size_t)(t.warp_hist ? kGofrThreads / 32 : 1) * n_r * sizeof(unsigned int);
+        const size_t n_items = (size_t)ctx->C * t.n_chunks * (g.same ? (size_t)t.n_ti * (t.n_ti + 1) / 2 : (size_t)t.n_ti * t.n_tj);
+        PIMC_CUDA(cudaFuncSetAttribute(gofr_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ScopedKernelTimer tm(ctx, PIMC_KERNEL_GOFR);
+        gofr_tiled_kernel<<<(int)std::min<size_t>(n_items, (size_t)ctx->n_sm), kGofrThreads, smem, ctx->stream>>>(t);
+    } else {
+        const int items = ctx->C * ctx->Mloc;
+        ScopedKernelTimer tm(ctx, PIMC_KERNEL_GOFR);
         gofr_kernel<<<GridFor(ctx, items), 256, n_r * sizeof(unsigned int), ctx->stream>>>(g);
     }
     ctx->launches++;

@@ -612,6 +612,110 @@ __global__ void __launch_bounds__(256) gofr_kernel(const GofrArgs a) {
     }
 }
 
+/// K5 v2.  Work item = (clone, chunk of 32 slices, tile I of species a, tile J of species b):
+/// the tiles' positions are staged in shared memory with coalesced loads (32 consecutive slices
+/// per row), warp w owns slice w of the chunk, its lanes own 32 particles p of tile I and walk
+/// the particles q of tile J together, so q's position is one broadcast LDS per axis for 32
+/// pairs and p's position stays in registers.  Rows are 33 doubles apart (odd lane stride:
+/// conflict-free).  Each warp counts into its own shared histogram when n_r allows (lanes hold
+/// different pairs: few same-bin collisions), else into one per CTA.  Same arithmetic as
+/// gofr_kernel: bins are bit-exact and the counts are integers, so the order does not matter.
+constexpr int kGofrThreads = 1024;
+constexpr int kGofrRow = 33;
+
+struct GofrTiledArgs {
+    GofrArgs g;
+    int T;            // particles per tile
+    int n_ti, n_tj;   // tiles of species a / b
+    int n_chunks;     // ceil(Mloc / 32)
+    int warp_hist;    // 1: one histogram per warp
+};
+
+__global__ void __launch_bounds__(kGofrThreads, 1) gofr_tiled_kernel(const GofrTiledArgs t) {
+    extern __shared__ __align__(16) unsigned char gsm[];
+    const GofrArgs &a = t.g;
+    const PathView &pv = a.pv;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *ti = reinterpret_cast<double *>(gsm);                // [T][3][33]
+    double *tj = ti + (size_t)t.T * 3 * kGofrRow;                // [T][3][33]
+    unsigned int *hist = reinterpret_cast<unsigned int *>(tj + (size_t)t.T * 3 * kGofrRow);
+    unsigned int *my_hist = hist + (t.warp_hist ? warp * a.n_r : 0);
+    const int n_hist = (t.warp_hist ? kGofrThreads / 32 : 1) * a.n_r;
+    const int Na = a.A.N, Nb = a.B.N;
+    // tile pairs: same species -> I <= J
+    const int n_tp = a.same ? t.n_ti * (t.n_ti + 1) / 2 : t.n_ti * t.n_tj;
+    const int per_clone = t.n_chunks * n_tp;
+    const int n_items = pv.C * per_clone;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int c = item / per_clone;
+        int rem = item - c * per_clone;
+        const int chunk = rem / n_tp;
+        rem -= chunk * n_tp;
+        int I, J;
+        if (a.same) {
+            I = 0;
+            while (rem >= t.n_ti - I) {
+                rem -= t.n_ti - I;
+                ++I;
+            }
+            J = I + rem;
+        } else {
+            I = rem / t.n_tj;
+            J = rem - I * t.n_tj;
+        }
+        const int s0 = chunk * 32;
+        const int p_lo = I * t.T, q_lo = J * t.T;
+        const int np = min(t.T, Na - p_lo), nq = min(t.T, Nb - q_lo);
+        const bool diag = a.same && I == J;
+        __syncthreads();  // previous item fully consumed
+        for (int i = tid; i < n_hist; i += kGofrThreads) hist[i] = 0u;
+        for (int row = warp; row < np * 3; row += kGofrThreads / 32) {
+            const int pp = row / 3, d = row - pp * 3;
+            ti[row * kGofrRow + lane] = s0 + lane < pv.Mloc ? a.A.R[PosIndex(pv, Na, c, p_lo + pp, d, s0 + lane)] : 0.;
+        }
+        if (!diag)
+            for (int row = warp; row < nq * 3; row += kGofrThreads / 32) {
+                const int qq = row / 3, d = row - qq * 3;
+                tj[row * kGofrRow + lane] = s0 + lane < pv.Mloc ? a.B.R[PosIndex(pv, Nb, c, q_lo + qq, d, s0 + lane)] : 0.;
+            }
+        __syncthreads();
+        const double *qt = diag ? ti : tj;
+        if (s0 + warp < pv.Mloc) {
+            for (int pb = 0; pb < np; pb += 32) {
+                const int pp = pb + lane;
+                const bool p_on = pp < np;
+                const double *prow = ti + (size_t)(p_on ? pp : 0) * 3 * kGofrRow + warp;
+                const double px = prow[0], py = prow[kGofrRow], pz = prow[2 * kGofrRow];
+                // same tile: pairs p < q only; the warp starts at the first q any of its lanes needs
+                for (int qq = diag ? pb + 1 : 0; qq < nq; ++qq) {
+                    const double *qrow = qt + (size_t)qq * 3 * kGofrRow + warp;
+                    double dr[3];
+                    const double pxyz[3] = {px, py, pz};
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const double x = __dsub_rn(pxyz[d], qrow[d * kGofrRow]);
+                        dr[d] = __dsub_rn(x, __dmul_rn(rint(__dmul_rn(x, pv.box.iL)), pv.box.L));
+                    }
+                    const double dist = Mag3Exact(dr[0], dr[1], dr[2]);
+                    const double arg = __dsub_rn(__dmul_rn(__dsub_rn(dist, a.r_min), a.d_ir), 0.5);
+                    const double ri = rint(arg);
+                    if (p_on && (!diag || pp < qq) && ri >= 0. && ri < (double)a.n_r) atomicAdd(&my_hist[(unsigned int)ri], 1u);
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < a.n_r; i += kGofrThreads) {
+            unsigned long long tot = 0;
+            if (t.warp_hist) {
+                for (int w = 0; w < kGofrThreads / 32; ++w) tot += hist[w * a.n_r + i];
+            } else {
+                tot = hist[i];
+            }
+            if (tot) atomicAdd(&a.counts[(size_t)c * a.n_r + i], tot);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------ K6
 /// sk[c][k] += cofactor[c] * CMag2(rho_a, rho_b) for b = 0..Mloc-1 in order (no FMA contraction:
 /// the accumulation then matches the reference bit for bit given equal rho_k).
