@@ -175,6 +175,10 @@ struct pimc_action {
     DevBuf<unsigned char> fast_tab[2];
     FastTable fast[2];
     bool fast_ok[2] = {false, false};
+    // fast Potential() kernel (Ilkka / Bare): v(r) and v_long(r) in the shared-memory layout
+    DevBuf<unsigned char> fastv_tab;
+    FastVTable fastv;
+    bool fastv_ok = false;
 };
 
 namespace {
@@ -609,6 +613,58 @@ int BuildFastIlkka(pimc_ctx *ctx, pimc_action *a, int which, const pimc_table_2d
     return PIMC_OK;
 }
 
+/// One pp-form 1-D spline in the fast shared-memory layout; false if the grid admits no uniform interval table.
+bool AppendFastPP1(ByteBlob &blob, FastPP1 &d, const pimc_table_1d &f, int max_keys) {
+    ULut lut;
+    if (!BuildULut(f.r, f.n, max_keys, lut)) return false;
+    KnotBasis kb;
+    kb.Build(f.r, f.n);
+    std::vector<double> coefs(f.n + 3, 0.0);
+    SolveNatural(kb, f.f, 1, coefs.data(), 1);
+    const std::vector<double> pp = PPFrom1D(kb, coefs.data());
+    d.off_gpair = AppendKnotPairs(blob, f.r, f.n);
+    d.off_c01 = blob.Reserve((size_t)f.n * 16);
+    d.off_c23 = blob.Reserve((size_t)f.n * 16);
+    for (int i = 0; i < f.n; ++i) {
+        blob.At<double>(d.off_c01)[2 * i] = pp[4 * (size_t)i];
+        blob.At<double>(d.off_c01)[2 * i + 1] = pp[4 * (size_t)i + 1];
+        blob.At<double>(d.off_c23)[2 * i] = pp[4 * (size_t)i + 2];
+        blob.At<double>(d.off_c23)[2 * i + 1] = pp[4 * (size_t)i + 3];
+    }
+    AppendULut(blob, d.lut, lut);
+    d.r_min = f.r[0];
+    d.r_max = f.r[f.n - 1];
+    return true;
+}
+
+/// Tables of potential_fast_kernel for an Ilkka or Bare action; fastv_ok stays false when a grid
+/// does not admit the uniform interval table or the block does not fit in shared memory.
+int BuildFastV(pimc_ctx *ctx, pimc_action *a, const pimc_table_1d &v_r, int is_coulomb, const pimc_long_range *lr) {
+    a->fastv_ok = false;
+    FastVTable &T = a->fastv;
+    std::memset(&T, 0, sizeof(T));
+    ByteBlob blob;
+    const int kMaxKeys = 16384;
+    T.is_coulomb = is_coulomb ? 1 : 0;
+    T.use_lr = a->use_long_range ? 1 : 0;
+    if (is_coulomb) {  // analytic 1/r: only the clamp limits of the (unused) table matter
+        T.v.r_min = v_r.r[0];
+        T.v.r_max = v_r.r[v_r.n - 1];
+    } else if (!AppendFastPP1(blob, T.v, v_r, kMaxKeys)) {
+        return PIMC_OK;
+    }
+    if (a->use_long_range && !AppendFastPP1(blob, T.lr, lr->f_r, kMaxKeys)) return PIMC_OK;
+    blob.b.resize((blob.b.size() + 15) & ~(size_t)15, 0);
+    if (blob.b.empty()) blob.b.resize(16, 0);
+    const size_t need = sizeof(double) * kFastRows * 3 * kFastRow + blob.b.size() + 2048;
+    if (need > ctx->smem_optin) return PIMC_OK;
+    T.n_bytes = (int)blob.b.size();
+    PIMC_CUDA(a->fastv_tab.Alloc(blob.b.size()));
+    PIMC_CUDA(cudaMemcpy(a->fastv_tab.p, blob.b.data(), blob.b.size(), cudaMemcpyHostToDevice));
+    a->fastv_ok = true;
+    return PIMC_OK;
+}
+
 // ------------------------------------------------------------------------------ launchers
 template <int ATYPE, int WHICH>
 int LaunchPairFullT(pimc_ctx *ctx, const PairFullArgs &args, size_t smem, int grid) {
@@ -659,8 +715,48 @@ int LaunchPairFast(pimc_action *a, int which, int *n_per_clone) {
     return PIMC_OK;
 }
 
+/// Items and partner-window split shared by the fast whole-path kernels (see LaunchPairFast).
+void FastItems(const pimc_ctx *ctx, int Na, int Nb, bool same, int n_chunks, int &n_pgroups, int &n_tsplit, int &t_windows) {
+    n_pgroups = (Na + kFastWarps - 1) / kFastWarps;
+    const int n_dd = same ? Na / 2 : Nb;
+    const int n_windows = std::max(1, (n_dd + kFastQ - 1) / kFastQ);
+    const size_t base_items = (size_t)ctx->C * n_chunks * n_pgroups;
+    int want = (int)std::min<size_t>((size_t)n_windows, ((size_t)6 * ctx->n_sm + base_items - 1) / std::max<size_t>(base_items, 1));
+    want = std::max(want, 1);
+    t_windows = std::max(1, n_windows / want);
+    n_tsplit = (n_windows + t_windows - 1) / t_windows;
+}
+
+int LaunchPotentialFast(pimc_action *a, int *n_per_clone) {
+    pimc_ctx *ctx = a->ctx;
+    PotFastArgs args;
+    args.pv = ctx->View();
+    args.A = ctx->SView(a->sa, false);
+    args.B = ctx->SView(a->sb, false);
+    args.same = a->sa == a->sb;
+    args.T = a->fastv;
+    args.tables = a->fastv_tab.p;
+    args.n_chunks = (ctx->Mloc + (ctx->sharded ? 1 : 0) + kChunk - 1) / kChunk;
+    FastItems(ctx, args.A.N, args.B.N, args.same != 0, args.n_chunks, args.n_pgroups, args.n_tsplit, args.t_windows);
+    *n_per_clone = args.n_chunks * args.n_pgroups * args.n_tsplit;
+    const size_t items = (size_t)ctx->C * *n_per_clone;
+    if (ctx->partial.n < items) PIMC_CUDA(ctx->partial.Alloc(items));
+    args.partial = ctx->partial.p;
+    const size_t smem = sizeof(double) * kFastRows * 3 * kFastRow + (size_t)args.T.n_bytes;
+    PIMC_CUDA(cudaFuncSetAttribute(potential_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<size_t>(items, (size_t)ctx->n_sm);
+    {
+        ScopedKernelTimer t(ctx, PIMC_KERNEL_PAIR_FULL);
+        potential_fast_kernel<<<grid, kFastThreads, smem, ctx->stream>>>(args);
+    }
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    return PIMC_OK;
+}
+
 int LaunchPairFull(pimc_action *a, int which, bool independent_images, int *n_per_clone) {
     pimc_ctx *ctx = a->ctx;
+    if (which == WHICH_V && independent_images && a->fastv_ok && !ctx->force_general) return LaunchPotentialFast(a, n_per_clone);
     if (a->atype == ATYPE_ILKKA && which != WHICH_V && !independent_images && a->fast_ok[which] && !ctx->force_general)
         return LaunchPairFast(a, which, n_per_clone);
     PairFullArgs args;
@@ -1052,6 +1148,8 @@ int pimc_action_create_ilkka(pimc_ctx *ctx, int32_t sa, int32_t sb, const pimc_i
             }
             rc = UploadBlob(ctx, a->blob[WHICH_V], blob);
             if (rc != PIMC_OK) return rc;
+            rc = BuildFastV(ctx, a, t->v_r, 0, a->use_long_range ? &t->v_long : nullptr);
+            if (rc != PIMC_OK) return rc;
         }
     } catch (const std::exception &e) {
         return Fail(PIMC_ERR_TABLE, e.what());
@@ -1093,6 +1191,8 @@ int pimc_action_create_bare(pimc_ctx *ctx, int32_t sa, int32_t sb, const pimc_ba
             rc = UploadBlob(ctx, a->blob[which], blob);
             if (rc != PIMC_OK) return rc;
         }
+        rc = BuildFastV(ctx, a, t->v_r, t->is_coulomb != 0, a->use_long_range ? &t->v_long : nullptr);
+        if (rc != PIMC_OK) return rc;
     } catch (const std::exception &e) {
         return Fail(PIMC_ERR_TABLE, e.what());
     }

@@ -360,6 +360,109 @@ __global__ void __launch_bounds__(kFastThreads, 1) pair_full_fast_kernel(const P
     }
 }
 
+// ------------------------------------------------------------------------- K1 (potential)
+/// Tables of the fast Potential() kernel: v(r) and the long-range r-space part, both pp-form
+/// with uniform interval tables, staged in shared memory.
+struct FastVTable {
+    FastPP1 v, lr;
+    int use_lr, is_coulomb;
+    int n_bytes;
+};
+
+struct PotFastArgs {
+    PathView pv;
+    SpeciesView A, B;
+    int same;
+    FastVTable T;
+    const unsigned char *tables;
+    int n_chunks, n_pgroups;   // chunks of 32 STORED slices (the halo slice of a shard included)
+    int n_tsplit, t_windows;
+    double *partial;           // [C][n_chunks][n_pgroups][n_tsplit]
+};
+
+/// PairAction::Potential (pair_action_class.h:369-395) for Ilkka / Bare CalcV
+/// (ilkka_pair_action_class.h:34-54, bare_pair_action_class.h:99-123).  Potential() measures r at
+/// slice b and r' at slice b + 1 with INDEPENDENT minimum images (App. A-6), so r' of link
+/// (b, b+1) is exactly r of link (b+1, b+2): with g(r) = v(clamp_v(r))/2 - v_long(clamp_l(clamp_v(r)))/2
+/// the sum over links of g(r) + g(r') is the sum over slices of w_s g(r_s), w_s = number of the
+/// shard's links that touch slice s (2; 1 for a shard's first slice and for its halo slice).
+/// One distance and two 1-D lookups per pair and slice instead of two and four.  Same work
+/// decomposition as pair_full_fast_kernel (warp = particle of species a, lanes = slices,
+/// partner rows staged per window of 32 offsets).
+__global__ void __launch_bounds__(kFastThreads, 1) potential_fast_kernel(const PotFastArgs a) {
+    extern __shared__ __align__(16) unsigned char fsm[];
+    __shared__ double red[kFastWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *qpos = reinterpret_cast<double *>(fsm);               // [kFastRows][3][kFastRow]
+    unsigned char *tb_ptr = fsm + sizeof(double) * kFastRows * 3 * kFastRow;
+    const SharedTab tb(tb_ptr);
+    {
+        const int4 *src = reinterpret_cast<const int4 *>(a.tables);
+        int4 *dst = reinterpret_cast<int4 *>(tb_ptr);
+        for (int i = tid; i < a.T.n_bytes / 16; i += kFastThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+    const PathView &pv = a.pv;
+    const int Na = a.A.N, Nb = a.B.N;
+    const int half = Na / 2;
+    const int n_dd = a.same ? half : Nb;
+    const int per_clone = a.n_chunks * a.n_pgroups * a.n_tsplit;
+    const int n_items = pv.C * per_clone;
+    const int n_store = pv.Mloc + (pv.sharded ? 1 : 0);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int c = item / per_clone;
+        int rem = item - c * per_clone;
+        const int ts = rem % a.n_tsplit;
+        rem /= a.n_tsplit;
+        const int chunk = rem / a.n_pgroups, pg = rem - chunk * a.n_pgroups;
+        const int t_begin = ts * a.t_windows * kFastQ, t_end = min(n_dd, t_begin + a.t_windows * kFastQ);
+        const int s = chunk * kChunk + lane;  // stored slice of this lane
+        const int p_lo = pg * kFastWarps;
+        const int p = p_lo + warp;
+        const bool warp_on = p < Na;
+        const bool lane_on = s < n_store;
+        const double weight = !lane_on ? 0. : ((pv.sharded && (s == 0 || s == pv.Mloc)) ? 1. : 2.);
+        double p0[3] = {0., 0., 0.};
+        if (warp_on && lane_on) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) p0[d] = a.A.R[PosIndex(pv, Na, c, p, d, s)];
+        }
+        int my_dd = n_dd;
+        if (a.same && (Na & 1) == 0 && p >= half) my_dd = half - 1;
+        if (!warp_on) my_dd = 0;
+        double acc = 0.;
+        for (int t0 = t_begin; t0 < t_end; t0 += kFastQ) {
+            const int n_rows = a.same ? min(kFastQ, n_dd - t0) + kFastWarps - 1 : min(kFastQ, Nb - t0);
+            const int q_first = a.same ? p_lo + t0 + 1 : t0;
+            __syncthreads();
+            for (int row = warp; row < n_rows * 3; row += kFastWarps) {
+                const int qq = row / 3, d = row - qq * 3;
+                int q = q_first + qq;
+                if (a.same) q %= Na;
+                qpos[row * kFastRow + lane] = lane_on ? a.B.R[PosIndex(pv, Nb, c, q, d, s)] : 0.;
+            }
+            __syncthreads();
+            const int n_step = min(kFastQ, my_dd - t0);
+            const double *rowp = qpos + (a.same ? warp * 3 * kFastRow : 0) + lane;
+            for (int i = 0; i < n_step; ++i, rowp += 3 * kFastRow) {
+                double dr[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const double x = p0[d] - rowp[d * kFastRow];   // Path::Dr (path_class.h:108-112)
+                    dr[d] = fma(-rint(x * pv.box.iL), pv.box.L, x);
+                }
+                double r = FastSqrt(fma(dr[1], dr[1], fma(dr[2], dr[2], dr[0] * dr[0])));
+                r = ClampRare(r, a.T.v);
+                double g = a.T.is_coulomb ? 0.5 / r : 0.5 * FastPP1Eval(tb, a.T.v, r);
+                if (a.T.use_lr) g = fma(-0.5, FastPP1Eval(tb, a.T.lr, ClampRare(r, a.T.lr)), g);
+                acc = fma(weight, g, acc);
+            }
+        }
+        const double tot = BlockSum<kFastThreads>(acc, red);
+        if (tid == 0) a.partial[item] = tot;
+    }
+}
+
 /// Test hooks: the fast evaluation on caller-supplied triples (tables read from global memory
 /// through the same code) and the square root on its own.
 __global__ void calc_pair_fast_kernel(const unsigned char *__restrict__ tables, FastTable T, int n, const double *__restrict__ r,
