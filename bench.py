@@ -95,11 +95,23 @@ def _cpu_worker(args):
     from simpimc_b200 import system as S
     cfg = S.ueg_config(N=N, M=M)
     R = S.synthetic_paths(cfg, 0, clone)
+    n_att, t_att = 0, 0.0
     if kind == "reference":
         from oracle import refsim
         sim = refsim.RefSim(cfg, fast=refsim.available(fast=True))
         sim.set_positions(0, R)
         f = lambda: sim.dbeta(0)
+        # the reference's own Bisect::DoEvent (Kinetic + IlkkaPairAction, n_level as the GPU sweep)
+        cfg_mc = S.ueg_config(N=N, M=M, with_kinetic=True)
+        cfg_mc.moves = [{"name": "BisectE", "type": "Bisect", "species": "e", "n_level": BISECT_LEVEL}]
+        mc = refsim.RefSim(cfg_mc, seed=1000 + clone, fast=refsim.available(fast=True))
+        mc.set_positions(0, R)
+        mc.move_do(0, 20)
+        n_att = 100 * max(1, n_eval)
+        t0 = time.perf_counter()
+        mc.move_do(0, n_att)
+        t_att = time.perf_counter() - t0
+        mc.close()
     else:
         from oracle import oracle as O
         sim = O.Oracle(cfg)
@@ -110,7 +122,7 @@ def _cpu_worker(args):
     val = 0.0
     for _ in range(n_eval):
         val = f()
-    return time.perf_counter() - t0, val
+    return time.perf_counter() - t0, val, n_att, t_att
 
 
 def cpu_baseline(n_eval=1, N=N_PART, M=N_SLICE, cores=None):
@@ -127,9 +139,14 @@ def cpu_baseline(n_eval=1, N=N_PART, M=N_SLICE, cores=None):
     wall = time.perf_counter() - t0
     slowest = max(r[0] for r in res)
     evals = cores * n_eval * pair_evals_per_clone(N, M)
-    return {"value": evals / slowest, "unit": "bead-pair action evals/s", "cores": cores, "kind": kind,
-            "sample": "%d clone(s) x %d DActionDBeta() of UEG N=%d M=%d, one process per core, %.1f s wall incl. setup"
-                      % (cores, n_eval, N, M, wall)}
+    out = {"value": evals / slowest, "unit": "bead-pair action evals/s", "cores": cores, "kind": kind,
+           "sample": "%d clone(s) x %d DActionDBeta() of UEG N=%d M=%d, one process per core, %.1f s wall incl. setup"
+                     % (cores, n_eval, N, M, wall)}
+    if res[0][2] > 0:
+        slowest_mc = max(r[3] for r in res)
+        out["mc_sweeps_per_s"] = cores * res[0][2] / (N * M // (1 << BISECT_LEVEL)) / slowest_mc
+        out["mc_sample"] = "%d reference Bisect::DoEvent (n_level=%d, Kinetic + IlkkaPairAction) per core" % (res[0][2], BISECT_LEVEL)
+    return out
 
 
 def run_reference(args):
@@ -514,7 +531,7 @@ def main():
     ap.add_argument("--clones", type=int, default=int(os.environ.get("BENCH_CLONES", "1024")))
     ap.add_argument("--attempts", type=int, default=256, help="bisection attempts per clone timed for the MC-sweep figure")
     ap.add_argument("--pipeline", type=int, default=4, help="contexts the end-to-end leg splits the clones over (H2D/compute overlap)")
-    ap.add_argument("--cpu-evals", type=int, default=2, help="DActionDBeta() calls per core for cpu_baseline (0 = skip)")
+    ap.add_argument("--cpu-evals", type=int, default=8, help="DActionDBeta() calls per core for cpu_baseline (0 = skip)")
     ap.add_argument("--workload", default="c3", choices=["c3", "c5"], help="c3: UEG N=256 M=128 x clones (headline); c5: plasma 1024+1024, M=512, slices sharded over the GPUs")
     ap.add_argument("--c5-n", type=int, default=1024)
     ap.add_argument("--c5-m", type=int, default=512)

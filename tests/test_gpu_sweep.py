@@ -129,6 +129,69 @@ def _mean_err(x):
     return m, np.sqrt(var * kappa / n)
 
 
+def test_sampled_gofr_and_sofk_match_the_reference_program():
+    """north_star: sampled runs reproduce the reference's g(r) and S(k) within statistical error
+    bars.  Reference: its own Bisect + PairCorrelation + StructureFactor on one walker
+    (std::mt19937), blocked series.  Device: 256 independent walkers (Philox), the estimators of
+    the CUDA path; error bars from the walker-to-walker spread."""
+    from oracle import refsim
+    if not refsim.available():
+        pytest.skip("oracle/_ref not built")
+    from simpimc_b200 import host
+    N, M, n_level, n_r = 4, 8, 2, 8
+    cfg = S.ueg_config(N=N, M=M, with_kinetic=True, n_xy=60, n_r_long=400)
+    cfg.moves = [{"name": "BisectE", "type": "Bisect", "species": "e", "n_level": n_level}]
+    cfg.observables = [{"name": "gr", "type": "PairCorrelation", "species_a": "e", "species_b": "e", "r_min": 0.0, "r_max": cfg.L / 2.0, "n_r": n_r},
+                       {"name": "sk", "type": "StructureFactor", "species_a": "e", "species_b": "e", "k_cut": cfg.k_cut}]
+    attempts_per_sweep = N * M // (1 << n_level)
+    sim = refsim.RefSim(cfg, seed=23)
+    sim.set_positions(0, S.synthetic_paths(cfg, 0, 0, 5))
+    sim.move_do(0, 400 * attempts_per_sweep)
+    n_blocks, per_block = 40, 60
+    g_blocks, s_blocks = [], []
+    g_prev, s_prev = sim.gofr_counts(0, n_r), sim.sofk_sums(1)
+    for _ in range(n_blocks):
+        for _ in range(per_block):
+            sim.move_do(0, attempts_per_sweep)
+            sim.observable_accumulate(0)
+            sim.observable_accumulate(1)
+        g_now, s_now = sim.gofr_counts(0, n_r), sim.sofk_sums(1)
+        g_blocks.append((g_now - g_prev) / per_block)
+        s_blocks.append((s_now - s_prev) / per_block)
+        g_prev, s_prev = g_now, s_now
+    sim.close()
+    g_ref, s_ref = np.array(g_blocks), np.array(s_blocks)
+    # device
+    C = 256
+    gcfg = S.ueg_config(N=N, M=M, n_xy=60, n_r_long=400)
+    path = host.Path(gcfg, n_clones=C)
+    path.SetPositions(0, np.stack([S.synthetic_paths(gcfg, 0, c, 5) for c in range(C)]))
+    gr = host.PairCorrelation(path, 0, 0, 0.0, gcfg.L / 2.0, n_r)
+    sk = host.StructureFactor(path, 0, 0, gcfg.k_cut)
+    att = 200 * attempts_per_sweep
+    path.BisectSweep(0, n_level, att, 31, attempt0=0)
+    n_meas = 40
+    for _ in range(n_meas):
+        path.BisectSweep(0, n_level, 3 * attempts_per_sweep, 31, attempt0=att)
+        att += 3 * attempts_per_sweep
+        gr.Accumulate()
+        sk.Accumulate()
+    g_dev, s_dev = gr.y / n_meas, sk.sk / n_meas      # per walker: counts per measurement, sum_b |rho_k|^2
+    path.close()
+    n_sig = 4.5
+    for name, dev, ref in (("g(r)", g_dev, g_ref), ("S(k)", s_dev, s_ref)):
+        d_mean, d_err = dev.mean(axis=0), dev.std(axis=0, ddof=1) / np.sqrt(C)
+        r_mean, r_err = ref.mean(axis=0), ref.std(axis=0, ddof=1) / np.sqrt(len(ref))
+        scale = np.max(np.abs(r_mean))
+        sig = np.hypot(d_err, r_err) + 1e-12 * scale
+        assert np.all(np.abs(d_mean - r_mean) <= n_sig * sig), (name, d_mean, r_mean, sig)
+        # the comparison has teeth: the error bars are small against the signal where it is large
+        big = np.abs(r_mean) > 0.2 * scale
+        assert np.all(sig[big] < 0.1 * np.abs(r_mean[big])), (name, sig, r_mean)
+    # same normalisation on both sides: pairs counted per measurement
+    assert abs(g_dev.sum(axis=1).mean() - g_ref.sum(axis=1).mean()) < 0.1 * N * (N - 1) / 2 * M
+
+
 def test_sampled_energy_matches_the_reference_program():
     from oracle import refsim
     if not refsim.available():
