@@ -246,7 +246,10 @@ __device__ __forceinline__ double LrRingFlush(const Tab &tb, const FastTable &T,
 }
 
 // ------------------------------------------------------------------------------ K1 (fast)
-constexpr int kFastThreads = 1024;
+#ifndef PIMC_FAST_THREADS
+#define PIMC_FAST_THREADS 1024
+#endif
+constexpr int kFastThreads = PIMC_FAST_THREADS;
 constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kFastQ = 32;                         // partner offsets handled per staged window
 constexpr int kFastRows = kFastQ + kFastWarps - 1; // window rows (same species: sliding window)
