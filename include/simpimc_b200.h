@@ -146,6 +146,15 @@ int pimc_rhok_rebuild(pimc_ctx *ctx, int32_t species); /* Species::InitRhoK */
  * (ncclSend/ncclRecv on the context's stream; simpimc_b200/sharded.py). */
 int pimc_halo_pack(pimc_ctx *ctx, int32_t species, double *d_buf);
 int pimc_halo_unpack(pimc_ctx *ctx, int32_t species, const double *d_buf);
+/* Ring rotation of a slice-sharded path by `shift` slices (1..slices of the shard): pack this
+ * shard's first `shift` owned slices ([n_clones][N][3][shift] doubles, device memory), send them to
+ * the PREVIOUS rank, and apply what the NEXT rank sent: owned slices slide left, the received ones
+ * are appended.  Global slice labels rotate, every shard keeps its range; imaginary time is a ring,
+ * so actions and estimators are unchanged.  Afterwards refresh the halos (pimc_halo_*) and rho_k
+ * (pimc_rhok_rebuild).  This is what lets shard-boundary slices be moved by pimc_bisect_sweep, whose
+ * windows on a sharded context stay inside the shard's stored slices. */
+int pimc_rotate_pack(pimc_ctx *ctx, int32_t species, int32_t shift, double *d_buf);
+int pimc_rotate_apply(pimc_ctx *ctx, int32_t species, int32_t shift, const double *d_buf);
 /* rho_k of one clone, out[bead][n_k][2] (re, im) (Species::GetRhoK, species_class.h:428). */
 int pimc_rhok_download(pimc_ctx *ctx, int32_t species, int32_t mode, int32_t clone, double *out);
 

@@ -1055,6 +1055,39 @@ int pimc_halo_unpack(pimc_ctx *ctx, int32_t s, const double *d_buf) {
     return PIMC_OK;
 }
 
+int pimc_rotate_pack(pimc_ctx *ctx, int32_t s, int32_t shift, double *d_buf) {
+    if (!ctx || !d_buf) return Fail(PIMC_ERR_INVALID, "null argument");
+    if (s < 0 || s >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
+    if (!ctx->sharded) return Fail(PIMC_ERR_INVALID, "rotation applies to slice-sharded contexts");
+    if (shift < 1 || shift > ctx->Mloc) return Fail(PIMC_ERR_INVALID, "shift must be in 1..slices of the shard");
+    for (auto &sp : ctx->species)
+        if (sp->n_prop > 0) return Fail(PIMC_ERR_INVALID, "a proposal is pending: call pimc_commit first");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    SpeciesState &st = *ctx->species[s];
+    const size_t n = (size_t)ctx->C * st.N * 3 * shift;
+    rotate_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(st.R.p, (size_t)ctx->C * st.N * 3, ctx->Ms, shift, d_buf);
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    return PIMC_OK;
+}
+
+int pimc_rotate_apply(pimc_ctx *ctx, int32_t s, int32_t shift, const double *d_buf) {
+    if (!ctx || !d_buf) return Fail(PIMC_ERR_INVALID, "null argument");
+    if (s < 0 || s >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
+    if (!ctx->sharded) return Fail(PIMC_ERR_INVALID, "rotation applies to slice-sharded contexts");
+    if (shift < 1 || shift > ctx->Mloc) return Fail(PIMC_ERR_INVALID, "shift must be in 1..slices of the shard");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    SpeciesState &st = *ctx->species[s];
+    const size_t n_rows = (size_t)ctx->C * st.N * 3;
+    rotate_apply_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, ctx->stream>>>(st.R.p, n_rows, ctx->Ms, ctx->Mloc, shift, d_buf);
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    // rho_k of the shifted slices: the caller rebuilds (pimc_rhok_rebuild) after the halo exchange
+    st.drho_valid = false;
+    st.need_update_rho_k = true;
+    return PIMC_OK;
+}
+
 int pimc_rhok_rebuild(pimc_ctx *ctx, int32_t s) {
     if (!ctx) return Fail(PIMC_ERR_INVALID, "null context");
     if (s < 0 || s >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
@@ -1686,7 +1719,10 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
     if (n_level < 1 || (1 << n_level) > kMaxBisectBeads || (1 << n_level) > ctx->M)
         return Fail(PIMC_ERR_INVALID, "n_level must satisfy 2 <= 2^n_level <= min(32, n_bead)");
     if (n_attempts < 0) return Fail(PIMC_ERR_INVALID, "negative attempt count");
-    if (ctx->sharded) return Fail(PIMC_ERR_UNSUPPORTED, "moves on a slice-sharded context");
+    // a slice shard moves the windows that lie inside its stored slices [slice_lo, slice_hi]: its first
+    // slice and its halo stay fixed until the caller rotates the ring (pimc_rotate_*) and refreshes the halos
+    if (ctx->sharded && (1 << n_level) > ctx->Mloc) return Fail(PIMC_ERR_INVALID, "window longer than the slice shard");
+    const int b0_lo = ctx->sharded ? ctx->slice_lo : 0, b0_count = ctx->sharded ? ctx->Mloc - (1 << n_level) + 1 : ctx->M;
     SpeciesState &st = *ctx->species[s];
     if (!(st.lambda > 0.)) return Fail(PIMC_ERR_INVALID, "bisection of a species with lambda = 0");
     for (auto &sp : ctx->species)
@@ -1735,6 +1771,8 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
         f.tau = ctx->tau;
         f.n_level = n_level;
         f.with_kinetic = with_kinetic ? 1 : 0;
+        f.b0_lo = b0_lo;
+        f.b0_count = b0_count;
         f.seed_lo = (uint32_t)seed;
         f.seed_hi = (uint32_t)(seed >> 32);
         f.attempt0 = attempt0;
@@ -1764,6 +1802,8 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
         ba.tau = ctx->tau;
         ba.n_level = n_level;
         ba.with_kinetic = with_kinetic ? 1 : 0;
+        ba.b0_lo = b0_lo;
+        ba.b0_count = b0_count;
         ba.seed_lo = (uint32_t)seed;
         ba.seed_hi = (uint32_t)(seed >> 32);
         ba.attempt_lo = (uint32_t)attempt;

@@ -48,6 +48,11 @@ struct PathView {
     Box box;
 };
 
+/// Global slice index after the beta-periodic wrap (bg < 2 M).  A slice shard's move windows never
+/// leave its stored slices [slice_lo, slice_hi]; the halo -- global slice slice_hi, which equals M
+/// on the last rank -- is stored at local index Mloc and must NOT wrap, so sharded views do not.
+__device__ __forceinline__ int WrapSlice(const PathView &pv, int bg) { return (!pv.sharded && bg >= pv.M) ? bg - pv.M : bg; }
+
 /// Local storage index of the slice that follows local slice b.
 __device__ __forceinline__ int NextSlice(const PathView &pv, int b) {
     return pv.sharded ? b + 1 : (b + 1 == pv.M ? 0 : b + 1);
@@ -59,7 +64,7 @@ __device__ __forceinline__ size_t PosIndex(const PathView &pv, int N, int c, int
 
 /// Position of (species view, clone c, particle p, GLOBAL slice bg) in OLD or NEW mode.
 __device__ __forceinline__ void LoadPos(const PathView &pv, const SpeciesView &sv, int c, int p, int bg, int mode, double out[3]) {
-    int bl = bg >= pv.M ? bg - pv.M : bg;
+    const int bl = WrapSlice(pv, bg);
     if (mode && sv.n_prop > 0 && sv.P_particle[c] == p) {
         int off = bl - sv.P_first[c];
         if (off < 0) off += pv.M;
@@ -813,6 +818,28 @@ __global__ void halo_pack_kernel(const double *__restrict__ R, size_t n_rows, in
 __global__ void halo_unpack_kernel(double *__restrict__ R, size_t n_rows, int Ms, int slot, const double *__restrict__ buf) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i < n_rows) R[i * Ms + slot] = buf[i];
+}
+
+/// Ring rotation of a slice-sharded path by `shift` slices: every shard hands its first `shift`
+/// owned slices to the previous rank and appends the ones it receives, i.e. the global slice labels
+/// rotate while every shard keeps its range -- imaginary time is a ring, so actions and estimators
+/// are unchanged, and the slices that were shard boundaries (never moved by shard-interior windows)
+/// become interior.  buf is [row][shift], row = (clone, particle, dim).
+__global__ void rotate_pack_kernel(const double *__restrict__ R, size_t n_rows, int Ms, int shift, double *__restrict__ buf) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n_rows * shift) return;
+    const size_t row = i / shift;
+    const int j = (int)(i - row * shift);
+    buf[i] = R[row * Ms + j];
+}
+/// One thread per row: slide the owned slices left by `shift` (ascending order: in place) and put the
+/// received ones at the end.  The halo slot is left stale (the caller exchanges halos next).
+__global__ void rotate_apply_kernel(double *__restrict__ R, size_t n_rows, int Ms, int Mloc, int shift, const double *__restrict__ buf) {
+    const size_t row = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    double *r = R + row * Ms;
+    for (int i = 0; i + shift < Mloc; ++i) r[i] = r[i + shift];
+    for (int j = 0; j < shift; ++j) r[Mloc - shift + j] = buf[row * shift + j];
 }
 
 /// Dependent-FMA chains: FP64 pipe throughput (2 flop per FMA).

@@ -66,6 +66,7 @@ struct BisectArgs {
     double lambda, tau;
     int n_level;
     int with_kinetic;
+    int b0_lo, b0_count;  // window starts are uniform in [b0_lo, b0_lo + b0_count): the whole path, or a shard's interior windows
     uint32_t seed_lo, seed_hi;
     uint32_t attempt_lo, attempt_hi;
     // outputs (proposal of the species + per-clone scalars)
@@ -92,12 +93,12 @@ __global__ void __launch_bounds__(128) bisect_sample_kernel(const BisectArgs a) 
     // rng.UnifRand(n) - 1: uniform integer in [0, n)
     int p_i = (int)(UniformFromBits(rnd[0], rnd[1]) * a.N);
     p_i = p_i < a.N ? p_i : a.N - 1;
-    int bead0 = (int)(UniformFromBits(rnd[2], rnd[3]) * pv.M);
-    bead0 = bead0 < pv.M ? bead0 : pv.M - 1;
+    int bead0 = (int)(UniformFromBits(rnd[2], rnd[3]) * a.b0_count);
+    bead0 = a.b0_lo + (bead0 < a.b0_count ? bead0 : a.b0_count - 1);
     double oldb[kMaxBisectBeads + 1][3], newb[kMaxBisectBeads + 1][3];
     for (int j = 0; j <= nb; ++j) {
         int bg = bead0 + j;
-        while (bg >= pv.M) bg -= pv.M;
+        bg = WrapSlice(pv, bg);
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
             const double x = a.R[PosIndex(pv, a.N, c, p_i, d, bg - pv.slice_lo)];
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(128) bisect_sample_kernel(const BisectArgs a) 
         for (int d = 0; d < 3; ++d) a.P[((size_t)c * n_prop + j) * 3 + d] = alive ? newb[j + 1][d] : oldb[j + 1][d];
     a.P_particle[c] = p_i;
     int first = bead0 + 1;
-    if (first >= pv.M) first -= pv.M;
+    first = WrapSlice(pv, first);
     a.P_first[c] = first;
     a.b0[c] = bead0;
     a.partial[c] = partial;
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(kWindowThreads) pair_window_both_kernel(const 
     for (int t = threadIdx.x; t < (nl + 1) * 3; t += blockDim.x) {
         const int j = t / 3, d = t - j * 3;
         int bg = bead0 + j;
-        while (bg >= pv.M) bg -= pv.M;
+        bg = WrapSlice(pv, bg);
         const double x = a.R_moved[PosIndex(pv, a.N_moved, c, p, d, bg - pv.slice_lo)];
         pold[j][d] = x;
         pnew[j][d] = (j >= 1 && j < nl) ? a.P[((size_t)c * (nl - 1) + (j - 1)) * 3 + d] : x;
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(kWindowThreads) pair_window_both_kernel(const 
         for (int d = 0; d < 3; ++d) q0[d] = a.R_partner[PosIndex(pv, a.N_partner, c, q, d, bg - pv.slice_lo)];
         for (int j = 0; j < nl; ++j) {
             int bn = bg + 1;
-            if (bn >= pv.M) bn -= pv.M;
+            bn = WrapSlice(pv, bn);
 #pragma unroll
             for (int d = 0; d < 3; ++d) q1[d] = a.R_partner[PosIndex(pv, a.N_partner, c, q, d, bn - pv.slice_lo)];
             double r, rp, s;
@@ -330,15 +331,15 @@ __global__ void __launch_bounds__(kWinFastThreads, 1) pair_window_fast_kernel(co
         for (int t = tid; t < (nl + 1) * 3; t += kWinFastThreads) {
             const int jj = t / 3, d = t - jj * 3;
             int bg = bead0 + jj;
-            while (bg >= pv.M) bg -= pv.M;
+            bg = WrapSlice(pv, bg);
             const double x = a.R_moved[PosIndex(pv, a.N_moved, c, p, d, bg - pv.slice_lo)];
             pold[jj][d] = x;
             pnew[jj][d] = (jj >= 1 && jj < nl) ? a.P[((size_t)c * (nl - 1) + (jj - 1)) * 3 + d] : x;
         }
         __syncthreads();
         int b0s = bead0 + j, b1s = bead0 + j + 1;
-        while (b0s >= pv.M) b0s -= pv.M;
-        while (b1s >= pv.M) b1s -= pv.M;
+        b0s = WrapSlice(pv, b0s);
+        b1s = WrapSlice(pv, b1s);
         // OLD pass, then NEW pass: one set of moved-particle positions in registers at a time
         double acc_old = 0., acc_new = 0.;
 #pragma unroll 1
@@ -415,7 +416,7 @@ __global__ void __launch_bounds__(256) lr_window_kernel(const LrWindowArgs a) {
     double acc_old = 0., acc_new = 0.;
     for (int j = 0; j < a.n_window; ++j) {
         int bg = a.b0[c] + j;
-        if (bg >= pv.M) bg -= pv.M;
+        bg = WrapSlice(pv, bg);
         __syncthreads();
         if (tid < 6) {
             const int mode = tid / 3, d = tid - mode * 3;
@@ -492,14 +493,14 @@ __global__ void __launch_bounds__(256) bisect_decide_commit_kernel(PathView pv, 
     for (int t = threadIdx.x; t < n_prop * 3; t += blockDim.x) {
         const int j = t / 3, d = t - j * 3;
         int bg = bead0 + 1 + j;
-        while (bg >= pv.M) bg -= pv.M;
+        bg = WrapSlice(pv, bg);
         R[PosIndex(pv, N, c, p, d, bg - pv.slice_lo)] = P[((size_t)c * n_prop + j) * 3 + d];
     }
     if (drho) {
         for (int t = threadIdx.x; t < n_window * n_k; t += blockDim.x) {
             const int j = t / n_k, k = t - j * n_k;
             int bg = bead0 + j;
-            if (bg >= pv.M) bg -= pv.M;
+            bg = WrapSlice(pv, bg);
             double2 *dst = rho + ((size_t)c * pv.Mloc + (bg - pv.slice_lo)) * n_k + k;
             const double2 d = drho[((size_t)c * n_window + j) * n_k + k];
             dst->x += d.x;

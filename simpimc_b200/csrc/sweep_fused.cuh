@@ -51,6 +51,7 @@ struct SweepFusedArgs {
     double lambda, tau;
     int n_level;
     int with_kinetic;
+    int b0_lo, b0_count;  // window starts: uniform in [b0_lo, b0_lo + b0_count)
     uint32_t seed_lo, seed_hi;
     unsigned long long attempt0;
     int n_attempts;
@@ -185,10 +186,10 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                 Philox4x32(at_lo, at_hi, (uint32_t)c, 0u, a.seed_lo, a.seed_hi, rnd);
                 int p_i = (int)(UniformFromBits(rnd[0], rnd[1]) * a.N);
                 p_i = p_i < a.N ? p_i : a.N - 1;
-                int b0 = (int)(UniformFromBits(rnd[2], rnd[3]) * pv.M);
-                b0 = b0 < pv.M ? b0 : pv.M - 1;
+                int b0 = (int)(UniformFromBits(rnd[2], rnd[3]) * a.b0_count);
+                b0 = a.b0_lo + (b0 < a.b0_count ? b0 : a.b0_count - 1);
                 int bg = b0 + j;
-                while (bg >= pv.M) bg -= pv.M;
+                bg = WrapSlice(pv, bg);
                 const double x = a.R[PosIndex(pv, a.N, c, p_i, d, bg - pv.slice_lo)];
                 sh.pold[s0 + lc][j][d] = x;
                 sh.pnew[s0 + lc][j][d] = x;
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                 // last byte: a 72-byte window touches one or two 128-byte lines) and of rho_k
                 const int bead0 = sh.bead0[sg];
                 int b_last = bead0 + nb;
-                if (b_last >= pv.M) b_last -= pv.M;
+                b_last = WrapSlice(pv, b_last);
                 const double *Rc = a.R + PosIndex(pv, a.N, c_grp, 0, 0, 0);
                 const int n_rows = a.N * 3;
                 for (int t = tg - 1; t < 2 * n_rows; t += kSweepGroup - 1) {
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                     for (int t = tg - 1; t < nb * lines; t += kSweepGroup - 1) {
                         const int j = t / lines, l = t - j * lines;
                         int bg = bead0 + j;
-                        if (bg >= pv.M) bg -= pv.M;
+                        bg = WrapSlice(pv, bg);
                         const char *p = reinterpret_cast<const char *>(a.rho + ((size_t)c_grp * pv.Mloc + (bg - pv.slice_lo)) * n_k);
                         PrefetchL2(p + min(l * 128, n_k * (int)sizeof(double2) - 1));
                     }
@@ -327,8 +328,8 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                     const int c = SWEEP_CLONE(lc);
                     const int p = sh.particle[s0 + lc];
                     int b0s = sh.bead0[s0 + lc] + j, b1s = b0s + 1;
-                    if (b0s >= pv.M) b0s -= pv.M;
-                    if (b1s >= pv.M) b1s -= pv.M;
+                    b0s = WrapSlice(pv, b0s);
+                    b1s = WrapSlice(pv, b1s);
                     // moved-particle beads are re-read from shared memory for every evaluation (asm
                     // volatile: not hoisted) -- holding OLD and NEW copies in registers spills at 64
                     const uint32_t po_addr = (uint32_t)__cvta_generic_to_shared(&sh.pold[s0 + lc][j][0]);
@@ -387,7 +388,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
 #pragma unroll 4
                         for (int j = 0; j < nb; ++j) {
                             int bg = bead0 + j;
-                            if (bg >= pv.M) bg -= pv.M;
+                            bg = WrapSlice(pv, bg);
                             const double2 rs = rho_c[(size_t)(bg - pv.slice_lo) * n_k + k];
                             const double2 *to = pt + (size_t)j * 6 * tl, *tn = to + 3 * tl;
                             const double2 fo = CMul(CMul(to[i0], to[i1]), to[i2]);
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                 for (int t = tg; t < (nb - 1) * 3; t += kSweepGroup) {
                     const int j = t / 3 + 1, d = t - (j - 1) * 3;
                     int bg = bead0 + j;
-                    while (bg >= pv.M) bg -= pv.M;
+                    bg = WrapSlice(pv, bg);
                     a.R[PosIndex(pv, a.N, c_grp, p, d, bg - pv.slice_lo)] = sh.pnew[sg][j][d];
                 }
                 if (n_k > 0) {
@@ -448,7 +449,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
 #pragma unroll 4
                         for (int j = 1; j < nb; ++j) {
                             int bg = bead0 + j;
-                            if (bg >= pv.M) bg -= pv.M;
+                            bg = WrapSlice(pv, bg);
                             double2 *dst = rho_c + (size_t)(bg - pv.slice_lo) * n_k + k;
                             double2 v = *dst;
                             const double2 *to = pt + (size_t)j * 6 * tl, *tn = to + 3 * tl;

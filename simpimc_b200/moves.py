@@ -139,7 +139,8 @@ class DisplaceParticle(_Move):
         return accept
 
 
-def bisect_attempt_philox(cfg, species, n_level, seed, attempt, n_clones, get_beads, action_old_new, finish, with_kinetic=True):
+def bisect_attempt_philox(cfg, species, n_level, seed, attempt, n_clones, get_beads, action_old_new, finish, with_kinetic=True,
+                          b0_range=None):
     """Host mirror of ONE device-resident bisection attempt (csrc/mc.cuh: bisect_sample_kernel +
     pair_window_both_kernel + k-sums + bisect_decide_kernel) drawing the same Philox stream.
 
@@ -147,6 +148,8 @@ def bisect_attempt_philox(cfg, species, n_level, seed, attempt, n_clones, get_be
     action_old_new(c, p, bead0, nb, new) -> (old_action, new_action) summed over the pair actions
                                             that involve `species`, `new` = proposed beads 1..nb-1
     finish(c, p, bead0, nb, accept)      -> Move::Accept / Reject
+    b0_range = (first, count): window starts uniform in [first, first + count) -- a slice shard's
+    interior windows (pimc_bisect_sweep on a sharded context); default: the whole path.
     Returns (particle[c], bead0[c], accept[c]).
     """
     from . import philox as PX
@@ -163,7 +166,8 @@ def bisect_attempt_philox(cfg, species, n_level, seed, attempt, n_clones, get_be
     for c in range(n_clones):
         r = PX.philox4x32(a_lo, a_hi, c, 0, k0, k1)
         p_i = min(int(PX.uniform_from_bits(r[0], r[1]) * N), N - 1)
-        bead0 = min(int(PX.uniform_from_bits(r[2], r[3]) * M), M - 1)
+        b_first, b_count = (0, M) if b0_range is None else b0_range
+        bead0 = b_first + min(int(PX.uniform_from_bits(r[2], r[3]) * b_count), b_count - 1)
         old = np.array(get_beads(c, p_i, bead0, nb + 1), dtype=np.float64)
         new = old.copy()
         slot, alive, prev_change, partial, logu0 = 1, True, 0.0, 0.0, 0.0

@@ -123,6 +123,33 @@ class ShardedPath:
             capi.check(self.path.L.pimc_halo_unpack(self.path.h, species, recv.data_ptr()))
         self.stream.synchronize()
 
+    def Rotate(self, shift):
+        """Rotate the ring of slices by `shift`: every rank hands its first `shift` owned slices to
+        the previous rank (same ring as the halo), then halos and rho_k are refreshed.  Global slice
+        labels rotate, shard ranges stay; actions and estimators are invariant (imaginary time is a
+        ring), and former shard-boundary slices become interior, where BisectSweep can move them."""
+        from . import capi
+        if not self.sh.sharded:
+            return
+        torch = self.torch
+        for species in range(len(self.cfg.species)):
+            N = self.cfg.species[species].n_part
+            with torch.cuda.stream(self.stream):
+                send = torch.empty((self.n_clones, N, 3, shift), dtype=torch.float64, device=self.device)
+                recv = torch.empty_like(send)
+                capi.check(self.path.L.pimc_rotate_pack(self.path.h, species, shift, send.data_ptr()))
+                ring_halo(send, recv, self.sh, self.group)
+                capi.check(self.path.L.pimc_rotate_apply(self.path.h, species, shift, recv.data_ptr()))
+            self.stream.synchronize()
+            self.ExchangeHalo(species)
+        self.RebuildRhoK()
+
+    def BisectSweep(self, species, n_level, n_attempts, seed, attempt0=0, with_kinetic=True):
+        """n_attempts device-resident bisection attempts per clone on THIS rank's shard-interior
+        windows (no communication: the shard's first slice and its halo stay fixed; call Rotate
+        between batches).  Seeds should differ between ranks.  Returns the accept counts."""
+        return self.path.BisectSweep(species, n_level, n_attempts, seed, attempt0, with_kinetic)
+
     def _reduced(self, fn, act):
         from . import capi
         torch = self.torch

@@ -232,3 +232,119 @@ def test_sampled_energy_matches_the_reference_program():
     r_mean, r_err = _mean_err(ref_series)
     assert abs(g_mean - r_mean) <= 4.0 * np.hypot(g_err, r_err), (g_mean, g_err, r_mean, r_err)
     assert g_err < 0.05 * abs(r_mean) and r_err < 0.05 * abs(r_mean)
+
+
+@pytest.mark.parametrize("name,n_shards", [("plasma", 2), ("ueg", 4)])
+def test_slice_sharded_sweeps_follow_the_host_mirror_and_rotate(name, n_shards):
+    """Moves on a slice-sharded path: every shard bisects windows that lie inside its
+    stored slices (no communication), then the ring of slices is rotated (pimc_rotate_pack /
+    _apply + halo refresh + rho_k rebuild) so that the former boundary slices become interior.
+    Shards live on one GPU here and the ring is moved by hand; in production it is NCCL
+    (sharded.ShardedPath.Rotate).  The host mirror draws each shard's Philox stream with the same
+    window range and takes its action values from the CPU oracle of the WHOLE path: same positions
+    after every attempt, same accept history; the rotated path has the same energy."""
+    import ctypes as C
+    import torch
+    from simpimc_b200 import host, moves, sharded, capi
+    from oracle import oracle as O
+    if name == "plasma":
+        cfg, n_level = S.plasma_config(Ne=5, Np=4, M=16), 2
+    else:
+        cfg, n_level = S.ueg_config(N=7, M=32), 3      # single same-species Ilkka action: the one-launch sweep kernel
+    M, nb, n_clones, ns = cfg.n_bead, 1 << n_level, 2, len(cfg.species)
+    Rs = [np.stack([S.synthetic_paths(cfg, sp, c, 4242) for c in range(n_clones)]) for sp in range(ns)]
+    oracles = [O.Oracle(cfg) for _ in range(n_clones)]
+    for c, o in enumerate(oracles):
+        for sp in range(ns):
+            o.set_positions(sp, Rs[sp][c])
+    e0 = [[o.dbeta(ai) for ai in range(len(cfg.actions))] for o in oracles]
+    shards = []
+    for g in range(n_shards):
+        sh = sharded.SliceSharding(M, n_shards, g)
+        p = host.Path(cfg, n_clones=n_clones, slice_lo=sh.lo, slice_hi=sh.hi)
+        for sp in range(ns):
+            p.SetPositions(sp, sh.shard_positions(Rs[sp]))
+        shards.append((sh, p))
+    attempt, n_acc_dev, n_acc_host = 0, 0, 0
+    for rnd in range(3):
+        for g, (sh, p) in enumerate(shards):
+            seed = 0xABC0000 + 17 * g
+            for _ in range(6):
+                sp = attempt % ns
+                acts = [ai for ai, a in enumerate(cfg.actions) if cfg.species[sp].name in (a.species_a, a.species_b)]
+
+                def get_beads(c, q, b0, n):
+                    return oracles[c].get_positions(sp, 0)[q, (b0 + np.arange(n)) % M]
+
+                def action_old_new(c, q, b0, nb_, new):
+                    oracles[c].propose(sp, q, (b0 + 1) % M, new)
+                    old = sum(oracles[c].get_action(ai, 0, b0, b0 + nb_, [(sp, q)], 0) for ai in acts)
+                    nw = sum(oracles[c].get_action(ai, 1, b0, b0 + nb_, [(sp, q)], 0) for ai in acts)
+                    return old, nw
+
+                def finish(c, q, b0, nb_, accept, new):
+                    if new is not None:
+                        oracles[c].finish_move(sp, q, b0, b0 + nb_, bool(accept))
+
+                _, b0s, acc = moves.bisect_attempt_philox(cfg, sp, n_level, seed, attempt, n_clones, get_beads, action_old_new, finish,
+                                                          b0_range=(sh.lo, sh.n_local - nb + 1))
+                assert all(sh.lo <= b and b + nb <= sh.hi for b in b0s)
+                n_acc_host += int(np.sum(acc))
+                n_acc_dev += int(p.BisectSweep(sp, n_level, 1, seed, attempt0=attempt).sum())
+                attempt += 1
+                for s2 in range(ns):
+                    got = p.GetPositions(s2)
+                    for c in range(n_clones):
+                        ref = oracles[c].get_positions(s2, 0)[:, np.array(sh.stored_slices()), :]
+                        assert np.max(np.abs(got[c] - ref)) <= 1e-12 * cfg.L, (name, rnd, g, attempt, s2, c)
+                assert n_acc_dev == n_acc_host
+        # rotate the ring by `shift` slices: pack everywhere first, then apply, then halos, then rho_k
+        shift = 3
+        for sp in range(ns):
+            N = cfg.species[sp].n_part
+            bufs = []
+            for sh, p in shards:
+                t = torch.zeros((n_clones, N, 3, shift), dtype=torch.float64, device="cuda")
+                capi.check(p.L.pimc_rotate_pack(p.h, sp, shift, C.c_void_p(t.data_ptr())))
+                p.Sync()
+                bufs.append(t)
+            for sh, p in shards:
+                capi.check(p.L.pimc_rotate_apply(p.h, sp, shift, C.c_void_p(bufs[sh.next_rank].data_ptr())))
+                p.Sync()
+            halos = []
+            for sh, p in shards:
+                t = torch.zeros((n_clones, N, 3), dtype=torch.float64, device="cuda")
+                capi.check(p.L.pimc_halo_pack(p.h, sp, C.c_void_p(t.data_ptr())))
+                p.Sync()
+                halos.append(t)
+            for sh, p in shards:
+                capi.check(p.L.pimc_halo_unpack(p.h, sp, C.c_void_p(halos[sh.next_rank].data_ptr())))
+                capi.check(p.L.pimc_rhok_rebuild(p.h, sp))
+                p.Sync()
+        # the same relabelling on the oracle: slice b now holds what slice b + shift held
+        for c, o in enumerate(oracles):
+            for sp in range(ns):
+                o.set_positions(sp, np.roll(o.get_positions(sp, 0), -shift, axis=1))
+        for sp in range(ns):
+            for sh, p in shards:
+                got = p.GetPositions(sp)
+                for c in range(n_clones):
+                    ref = oracles[c].get_positions(sp, 0)[:, np.array(sh.stored_slices()), :]
+                    assert np.max(np.abs(got[c] - ref)) <= 1e-12 * cfg.L, (name, "rotation", sp, c)
+    assert n_acc_dev > 0
+    for ai in range(len(cfg.actions)):
+        du = sum(p.actions[ai].DActionDBeta() for _, p in shards)
+        for c, o in enumerate(oracles):
+            ref = o.dbeta(ai)
+            assert abs(du[c] - ref) <= 1e-10 * abs(ref)
+            assert ref != e0[c][ai]           # the walkers did move
+    # rho_k carried through sweeps and rotations equals a rebuild by the oracle
+    for sh, p in shards:
+        for sp in range(ns):
+            for c in range(n_clones):
+                got = p.GetRhoK(sp, c, host.OLD_MODE)
+                assert np.max(np.abs(got - oracles[c].rhok(sp, 0)[sh.lo:sh.hi])) <= 1e-10 * cfg.species[sp].n_part
+    for _, p in shards:
+        p.close()
+    for o in oracles:
+        o.close()

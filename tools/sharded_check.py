@@ -61,6 +61,40 @@ def main():
         print(json.dumps({"check": "slice-sharded plasma", "n_gpus": world, "N": 2 * Ne, "M": M, "clones": C, "max_rel_err_vs_unsharded": err,
                           "gofr_bins_equal": bool(np.array_equal(counts, ref_counts)), "ok": bool(ok),
                           "dbeta_3_actions_ms": 1e3 * (t1 - t0), "pair_slice_evals": n_pairs * M * C}), flush=True)
+    # ---- moves on the sharded path: shard-interior bisection windows, ring rotation over NCCL ----
+    n_level, n_att = 2, 24
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    n_acc = 0
+    for rnd in range(3):
+        for sp in range(2):
+            n_acc += int(sp_path.BisectSweep(sp, n_level, n_att, 1000 + rank, attempt0=rnd * n_att).sum())
+        sp_path.Rotate(5)
+    torch.cuda.synchronize()
+    t3 = time.perf_counter()
+    du_mc = [sp_path.DActionDBeta(a) for a in range(3)]
+    # gather the shards and evaluate the whole (rotated) path unsharded on rank 0
+    mc_err, moved = 0.0, False
+    gathered = []
+    for sp in range(2):
+        own = torch.from_numpy(np.ascontiguousarray(sp_path.path.GetPositions(sp)[:, :, :sp_path.sh.n_local, :])).to(sp_path.device)
+        parts = [torch.empty_like(own) for _ in range(world)]
+        dist.all_gather(parts, own)
+        gathered.append(torch.cat(parts, dim=2).cpu().numpy())
+    if rank == 0:
+        whole = host.Path(cfg, n_clones=C, device=local)
+        for sp in range(2):
+            whole.SetPositions(sp, gathered[sp])
+        for a in range(3):
+            ref = whole.actions[a].DActionDBeta()
+            mc_err = max(mc_err, float(np.max(np.abs(du_mc[a] - ref) / np.abs(ref))))
+            moved = moved or bool(np.any(du_mc[a] != du[a]))
+        whole.close()
+        ok_mc = mc_err <= 1e-10 and moved and n_acc > 0
+        print(json.dumps({"check": "slice-sharded moves", "n_gpus": world, "attempts_per_rank": 3 * 2 * n_att * C, "accepted_on_rank0": n_acc,
+                          "rotations": 3, "max_rel_err_vs_unsharded_after_moves": mc_err, "ok": bool(ok_mc),
+                          "ms_per_attempt_batch": 1e3 * (t3 - t2) / (3 * 2 * n_att)}), flush=True)
+        ok = ok and ok_mc
     sp_path.close()
     dist.barrier()
     dist.destroy_process_group()
