@@ -301,6 +301,22 @@ def run_ours(args):
     sweeps_per_s = world * C * n_att / attempts_per_sweep / float(ts.item())
     window_evals_per_s = world * C * n_att * 2 * (N_PART - 1) * (1 << BISECT_LEVEL) / float(ts.item())
     accept_ratio = float(n_acc.sum()) / (C * n_att)
+    # device-resident DisplaceParticle (whole-path shift of one particle per clone and attempt)
+    n_disp = max(1, min(16, n_att))
+    path.DisplaceSweep(0, cfg.L / 10.0, 2, 4321 + rank, attempt0=0)
+    barrier()
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record(stream)
+    n_acc_d = path.DisplaceSweep(0, cfg.L / 10.0, n_disp, 4321 + rank, attempt0=2)
+    d1.record(stream)
+    d1.synchronize()
+    barrier()
+    td = torch.tensor([d0.elapsed_time(d1) * 1e-3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(td, op=dist.ReduceOp.MAX)
+    displace = {"ms_per_attempt": 1e3 * float(td.item()) / n_disp, "attempts_timed": n_disp, "accept_ratio": float(n_acc_d.sum()) / (C * n_disp),
+                "pair_evals_per_s": world * C * n_disp * 2 * (N_PART - 1) * N_SLICE / float(td.item()),
+                "driver": "device-resident pimc_displace_sweep (step L/10; pair + long-range deltas over all slices, Metropolis, commit)"}
     # the same move driven from the host through propose / GetAction(OLD, NEW) / commit (the
     # reference-shaped call sequence), a few attempts for comparison
     rng = np.random.default_rng(1234 + rank)
@@ -375,7 +391,7 @@ def run_ours(args):
                    "ms_per_attempt": 1e3 * float(ts.item()) / n_att, "launches": int(launches_mc),
                    "pair_window_kernel_ms_per_attempt": k4_ms / max(1, n_att),
                    "driver": "device-resident pimc_bisect_sweep (Philox stream; kinetic + Ilkka pair + long-range deltas, Metropolis, commit)",
-                   "host_driven_sweeps_per_s_per_gpu": host_driven_sweeps_per_s},
+                   "host_driven_sweeps_per_s_per_gpu": host_driven_sweeps_per_s, "displace": displace},
             "estimators": estimators,
             "roofline": roofline}
     if base:

@@ -242,6 +242,14 @@ int pimc_commit(pimc_ctx *ctx, const int32_t *accept);
 int pimc_bisect_sweep(pimc_ctx *ctx, int32_t species, int32_t n_level, int32_t n_attempts, uint64_t seed, uint64_t attempt0,
                       int32_t with_kinetic, int64_t *n_accept);
 
+/* n_attempts x DisplaceParticle::DoEvent (displace_particle_class.h:13-89) on every clone, on the
+ * device: one particle's whole path shifted by a vector of length step_size (direction: normalised
+ * uniform point of the cube, scaffold/rng/rng.h:38-56), every pair action that involves `species`
+ * over all slices in OLD and NEW mode, Metropolis, Accept / Reject.  Same Philox convention as
+ * pimc_bisect_sweep (slots: 0 particle, 1-2 direction, 3 Metropolis uniform). */
+int pimc_displace_sweep(pimc_ctx *ctx, int32_t species, double step_size, int32_t n_attempts, uint64_t seed, uint64_t attempt0,
+                        int64_t *n_accept);
+
 /* ---- estimators ------------------------------------------------------------------------ */
 /* PairCorrelation::Accumulate (pair_correlation_class.h:15-28): y[c][i] += cofactor[c] for
  * every pair and slice, bin i = (uint32)nearbyint((|dr|-r_min)*d_ir - 0.5), i < n_r kept.

@@ -20,6 +20,7 @@
 #include "mc.cuh"
 #include "sweep_fused.cuh"
 #include "grad.cuh"
+#include "displace.cuh"
 #include "spline_build.h"
 
 using namespace pimc;
@@ -1888,6 +1889,143 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
         bisect_decide_commit_kernel<<<C, 256, 0, ctx->stream>>>(pv, st.N, n_k, nb, alive, partial, logu0, pair_old, pair_new, lr_old, lr_new,
                                                                st.P.p, st.P_particle.p, b0, any_lr ? st.drho.p : nullptr, st.R.p,
                                                                any_lr ? st.rho.p : nullptr, accept, ctx->mc_naccept.p);
+        ctx->launches++;
+    }
+    PIMC_CUDA(cudaGetLastError());
+    st.n_prop = 0;
+    st.drho_valid = false;
+    for (auto &sp : ctx->species) sp->need_update_rho_k = true;
+    if (n_accept) {
+        std::vector<long long> h(C);
+        PIMC_CUDA(cudaMemcpyAsync(h.data(), ctx->mc_naccept.p, C * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        PIMC_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int c = 0; c < C; ++c) n_accept[c] += (int64_t)h[c];
+    }
+    return PIMC_OK;
+}
+
+int pimc_displace_sweep(pimc_ctx *ctx, int32_t s, double step_size, int32_t n_attempts, uint64_t seed, uint64_t attempt0, int64_t *n_accept) {
+    if (!ctx) return Fail(PIMC_ERR_INVALID, "null context");
+    if (s < 0 || s >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
+    if (!(step_size > 0.)) return Fail(PIMC_ERR_INVALID, "step_size must be positive");
+    if (n_attempts < 0) return Fail(PIMC_ERR_INVALID, "negative attempt count");
+    // a whole-path shift spans every shard: it would need one decision for all ranks
+    if (ctx->sharded) return Fail(PIMC_ERR_UNSUPPORTED, "DisplaceParticle on a slice-sharded context");
+    for (auto &sp : ctx->species)
+        if (sp->n_prop > 0) return Fail(PIMC_ERR_INVALID, "a proposal is pending: call pimc_commit first");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    SpeciesState &st = *ctx->species[s];
+    const int C = ctx->C, M = ctx->M, n_k = ctx->n_k();
+    if (ctx->mc_f64.n < (size_t)6 * C) PIMC_CUDA(ctx->mc_f64.Alloc((size_t)6 * C));
+    if (ctx->mc_i32.n < (size_t)3 * C) PIMC_CUDA(ctx->mc_i32.Alloc((size_t)3 * C));
+    if (ctx->mc_naccept.n < (size_t)C) PIMC_CUDA(ctx->mc_naccept.Alloc(C));
+    PIMC_CUDA(cudaMemsetAsync(ctx->mc_naccept.p, 0, C * sizeof(long long), ctx->stream));
+    if (st.P.n < (size_t)C * M * 3) PIMC_CUDA(st.P.Alloc((size_t)C * M * 3));
+    double *dr = ctx->mc_f64.p, *logu = dr + 3 * C, *lr_old = logu + C, *lr_new = lr_old + C;
+    int32_t *b0 = ctx->mc_i32.p, *accept = b0 + C;
+    std::vector<pimc_action *> acts;  // move_class.h:27-31
+    bool any_lr = false;
+    for (pimc_action *a : ctx->actions) {
+        if (a->sa != s && a->sb != s) continue;
+        if (a->is_constant) continue;
+        acts.push_back(a);
+        any_lr = any_lr || (a->use_long_range && n_k > 0);
+    }
+    if (any_lr) {
+        const size_t need = (size_t)C * M * n_k;
+        if (st.drho.n < need) PIMC_CUDA(st.drho.Alloc(need));
+    }
+    const PathView pv = ctx->View();
+    const int n_chunks = (M + 31) / 32;
+    if (ctx->partial.n < (size_t)C * n_chunks * 2) PIMC_CUDA(ctx->partial.Alloc((size_t)C * n_chunks * 2));
+    const int grid = (int)std::min<size_t>((size_t)C * n_chunks, (size_t)ctx->n_sm);
+    for (int it = 0; it < n_attempts; ++it) {
+        const uint64_t attempt = attempt0 + (uint64_t)it;
+        DisplaceSampleArgs sa;
+        sa.pv = pv;
+        sa.R = st.R.p;
+        sa.N = st.N;
+        sa.step = step_size;
+        sa.seed_lo = (uint32_t)seed;
+        sa.seed_hi = (uint32_t)(seed >> 32);
+        sa.attempt_lo = (uint32_t)attempt;
+        sa.attempt_hi = (uint32_t)(attempt >> 32);
+        sa.P = st.P.p;
+        sa.P_particle = st.P_particle.p;
+        sa.P_first = st.P_first.p;
+        sa.b0 = b0;
+        sa.dr = dr;
+        sa.logu = logu;
+        displace_sample_kernel<<<C, 128, 0, ctx->stream>>>(sa);
+        ctx->launches++;
+        if (acts.empty()) PIMC_CUDA(cudaMemsetAsync(ctx->partial.p, 0, (size_t)C * n_chunks * 2 * sizeof(double), ctx->stream));
+        bool first = true;
+        for (pimc_action *a : acts) {
+            const int partner = (a->sa == s) ? a->sb : a->sa;
+            DisplacePairArgs w;
+            w.pv = pv;
+            w.R_moved = st.R.p;
+            w.N_moved = st.N;
+            w.R_partner = ctx->species[partner]->R.p;
+            w.N_partner = ctx->species[partner]->N;
+            w.same = partner == s;
+            w.particle = st.P_particle.p;
+            w.dr = dr;
+            w.n_chunks = n_chunks;
+            w.FT = a->fast[WHICH_U];
+            w.fast_tables = a->fast_tab[WHICH_U].p;
+            w.T = a->table[WHICH_U];
+            w.blob = a->blob[WHICH_U].p;
+            w.accumulate = first ? 0 : 1;
+            w.partial = ctx->partial.p;
+            first = false;
+            {
+                ScopedKernelTimer t(ctx, PIMC_KERNEL_PAIR_WINDOW);
+                if (a->atype == ATYPE_ILKKA && a->fast_ok[WHICH_U] && !ctx->force_general) {
+                    const size_t smem = (size_t)w.FT.n_bytes;
+                    PIMC_CUDA(cudaFuncSetAttribute(displace_pair_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    displace_pair_kernel<-1><<<grid, kDispThreads, smem, ctx->stream>>>(w);
+                } else if (a->atype == ATYPE_ILKKA)
+                    displace_pair_kernel<ATYPE_ILKKA><<<grid, kDispThreads, 0, ctx->stream>>>(w);
+                else if (a->atype == ATYPE_BARE)
+                    displace_pair_kernel<ATYPE_BARE><<<grid, kDispThreads, 0, ctx->stream>>>(w);
+                else
+                    displace_pair_kernel<ATYPE_DAVID><<<grid, kDispThreads, 0, ctx->stream>>>(w);
+            }
+            ctx->launches++;
+        }
+        if (any_lr) {
+            LrWindowArgs l;
+            l.pv = pv;
+            l.sv = ctx->SView(s, false);
+            l.sv.n_prop = M;  // the proposal the sample kernel has just written: every bead of the particle
+            l.ks = ctx->KView();
+            l.b0 = b0;
+            l.n_window = M;
+            l.rho_self = st.rho.p;
+            l.drho = st.drho.p;
+            l.lr_old = lr_old;
+            l.lr_new = lr_new;
+            l.n_actions = 0;
+            for (pimc_action *a : acts) {
+                if (!(a->use_long_range && n_k > 0)) continue;
+                if (l.n_actions == kMaxLrActions) return Fail(PIMC_ERR_UNSUPPORTED, "more than 4 long-range actions on one species");
+                const int partner = (a->sa == s) ? a->sb : a->sa;
+                l.rho_other[l.n_actions] = (partner == s) ? nullptr : ctx->species[partner]->rho.p;
+                l.wk[l.n_actions] = a->wk[WHICH_U].p;
+                l.factor[l.n_actions] = a->ulong_scale * (partner == s ? 1.0 : 2.0);
+                l.n_actions++;
+            }
+            const int tl = 2 * ctx->max_index + 1;
+            {
+                ScopedKernelTimer t(ctx, PIMC_KERNEL_KSUM);
+                lr_window_kernel<<<C, 256, (size_t)6 * tl * sizeof(double2), ctx->stream>>>(l);
+            }
+            ctx->launches++;
+        }
+        displace_decide_commit_kernel<<<C, 256, 0, ctx->stream>>>(pv, st.N, n_k, n_chunks, ctx->partial.p, any_lr ? 1 : 0, lr_old, lr_new, logu, st.P.p,
+                                                                 st.P_particle.p, any_lr ? st.drho.p : nullptr, st.R.p,
+                                                                 any_lr ? st.rho.p : nullptr, accept, ctx->mc_naccept.p);
         ctx->launches++;
     }
     PIMC_CUDA(cudaGetLastError());

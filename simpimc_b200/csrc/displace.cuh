@@ -1,0 +1,213 @@
+// Device-resident DisplaceParticle::DoEvent
+// (src/events/moves/single_species_move/displace_particle_class.h:13-89) on every clone at once:
+// pick a particle, shift its WHOLE path rigidly by a vector of fixed length step_size whose
+// direction is a normalised uniform point of the cube (scaffold/rng/rng.h:38-56 -- not isotropic,
+// App. A-16), evaluate every pair action touching the species over all slices in OLD and NEW mode
+// (GetAction(0, n_bead, particles, 0), displace_particle_class.h:54-63), Metropolis, commit.
+// A rigid shift leaves the free-particle (Kinetic, n_images = 0) action unchanged.
+//
+//   displace_sample_kernel   Philox draws, proposal P = committed beads + dr (the proposal overlay
+//                            that rhok / long-range kernels already understand)
+//   displace_pair_kernel     persistent CTAs; item = (clone, 32 links); lanes = links, warps walk
+//                            the partner particles; OLD and NEW from the same partner loads
+//   lr_window_kernel         (mc.cuh) with the window = the whole path: drho and the k-sums
+//   displace_decide_commit_kernel
+//
+// Philox slots of an attempt (counter = attempt, clone, slot): 0 particle, 1-2 direction, 3
+// Metropolis uniform.  simpimc_b200/moves.py (displace_attempt_philox) mirrors the stream.
+#ifndef SIMPIMC_B200_DISPLACE_CUH_
+#define SIMPIMC_B200_DISPLACE_CUH_
+
+#include "mc.cuh"
+
+namespace pimc {
+
+struct DisplaceSampleArgs {
+    PathView pv;
+    const double *R;
+    int N;
+    double step;
+    uint32_t seed_lo, seed_hi, attempt_lo, attempt_hi;
+    double *P;             // [C][M][3]
+    int32_t *P_particle;   // [C]
+    int32_t *P_first;      // [C] = 0
+    int32_t *b0;           // [C] = 0
+    double *dr;            // [C][3]
+    double *logu;          // [C]
+};
+
+/// One CTA per clone.
+__global__ void __launch_bounds__(128) displace_sample_kernel(const DisplaceSampleArgs a) {
+    __shared__ double sdr[3];
+    __shared__ int sp;
+    const PathView &pv = a.pv;
+    const int c = blockIdx.x;
+    if (threadIdx.x == 0) {
+        uint32_t r0[4], r1[4], r2[4], r3[4];
+        Philox4x32(a.attempt_lo, a.attempt_hi, (uint32_t)c, 0u, a.seed_lo, a.seed_hi, r0);
+        Philox4x32(a.attempt_lo, a.attempt_hi, (uint32_t)c, 1u, a.seed_lo, a.seed_hi, r1);
+        Philox4x32(a.attempt_lo, a.attempt_hi, (uint32_t)c, 2u, a.seed_lo, a.seed_hi, r2);
+        Philox4x32(a.attempt_lo, a.attempt_hi, (uint32_t)c, 3u, a.seed_lo, a.seed_hi, r3);
+        int p_i = (int)(UniformFromBits(r0[0], r0[1]) * a.N);
+        p_i = p_i < a.N ? p_i : a.N - 1;
+        // UnifRand(-1, 1) = (b - a) * u + a per component, r /= mag(r), r *= l
+        double v[3] = {2. * UniformFromBits(r1[0], r1[1]) + -1., 2. * UniformFromBits(r1[2], r1[3]) + -1.,
+                       2. * UniformFromBits(r2[0], r2[1]) + -1.};
+        const double m = Mag3(v[0], v[1], v[2]);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            v[d] = (v[d] / m) * a.step;
+            sdr[d] = v[d];
+            a.dr[(size_t)c * 3 + d] = v[d];
+        }
+        sp = p_i;
+        a.P_particle[c] = p_i;
+        a.P_first[c] = 0;
+        a.b0[c] = 0;
+        a.logu[c] = log(UniformFromBits(r3[0], r3[1]));
+    }
+    __syncthreads();
+    const int p = sp;
+    for (int t = threadIdx.x; t < pv.M * 3; t += blockDim.x) {
+        const int d = t / pv.M, b = t - d * pv.M;  // slice fastest: coalesced reads
+        a.P[((size_t)c * pv.M + b) * 3 + d] = a.R[PosIndex(pv, a.N, c, p, d, b)] + sdr[d];
+    }
+}
+
+constexpr int kDispThreads = 1024;
+constexpr int kDispWarps = kDispThreads / 32;
+
+struct DisplacePairArgs {
+    PathView pv;
+    const double *R_moved, *R_partner;
+    int N_moved, N_partner, same;
+    const int32_t *particle;   // [C]
+    const double *dr;          // [C][3]
+    int n_chunks;
+    // fast Ilkka evaluation (tables staged in shared memory) or the general evaluation
+    FastTable FT;
+    const unsigned char *fast_tables;
+    PairTable T;
+    const double *blob;
+    int accumulate;            // add to the partial sums (second and later actions)
+    double *partial;           // [C][n_chunks][2]: OLD, NEW
+};
+
+/// ATYPE < 0: fast Ilkka path.
+template <int ATYPE>
+__global__ void __launch_bounds__(kDispThreads, 1) displace_pair_kernel(const DisplacePairArgs a) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    __shared__ double red[2][kDispWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const PathView &pv = a.pv;
+    if (ATYPE < 0) {
+        const int4 *src = reinterpret_cast<const int4 *>(a.fast_tables);
+        int4 *dst = reinterpret_cast<int4 *>(dsm);
+        for (int i = tid; i < a.FT.n_bytes / 16; i += kDispThreads) dst[i] = src[i];
+        __syncthreads();
+    }
+    const SharedTab tb(dsm);
+    const int n_items = pv.C * a.n_chunks;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int c = item / a.n_chunks, chunk = item - c * a.n_chunks;
+        const int b = chunk * 32 + lane;
+        const bool lane_on = b < pv.M;
+        const int bn = b + 1 >= pv.M ? b + 1 - pv.M : b + 1;
+        const int p = a.particle[c];
+        double dr[3], p0[3], p1[3], n0[3], n1[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            dr[d] = a.dr[(size_t)c * 3 + d];
+            p0[d] = lane_on ? a.R_moved[PosIndex(pv, a.N_moved, c, p, d, b)] : 0.;
+            p1[d] = lane_on ? a.R_moved[PosIndex(pv, a.N_moved, c, p, d, bn)] : 0.;
+            n0[d] = p0[d] + dr[d];
+            n1[d] = p1[d] + dr[d];
+        }
+        double acc_old = 0., acc_new = 0.;
+        for (int q = warp; q < a.N_partner; q += kDispWarps) {
+            if (a.same && q == p) continue;
+            double q0[3], q1[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                q0[d] = lane_on ? a.R_partner[PosIndex(pv, a.N_partner, c, q, d, b)] : 0.;
+                q1[d] = lane_on ? a.R_partner[PosIndex(pv, a.N_partner, c, q, d, bn)] : 0.;
+            }
+            double r, rp, s, uo, un;
+            if (ATYPE < 0) {
+                DrDrpDrrpFast(p0, q0, p1, q1, pv.box, r, rp, s);
+                uo = FastIlkkaEval(tb, a.FT, r, rp, s);
+                DrDrpDrrpFast(n0, q0, n1, q1, pv.box, r, rp, s);
+                un = FastIlkkaEval(tb, a.FT, r, rp, s);
+            } else {
+                DrDrpDrrp(p0, q0, p1, q1, pv.box, r, rp, s);
+                uo = PairEval<(ATYPE < 0 ? 0 : ATYPE), WHICH_U>(a.blob, a.T, r, rp, s);
+                DrDrpDrrp(n0, q0, n1, q1, pv.box, r, rp, s);
+                un = PairEval<(ATYPE < 0 ? 0 : ATYPE), WHICH_U>(a.blob, a.T, r, rp, s);
+            }
+            acc_old += lane_on ? uo : 0.;
+            acc_new += lane_on ? un : 0.;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc_old += __shfl_down_sync(0xffffffffu, acc_old, o);
+            acc_new += __shfl_down_sync(0xffffffffu, acc_new, o);
+        }
+        __syncthreads();  // red of the previous item has been read
+        if (lane == 0) {
+            red[0][warp] = acc_old;
+            red[1][warp] = acc_new;
+        }
+        __syncthreads();
+        if (tid < 2) {
+            double tot = 0.;
+            for (int w = 0; w < kDispWarps; ++w) tot += red[tid][w];
+            double *dst = a.partial + (size_t)item * 2 + tid;
+            *dst = a.accumulate ? *dst + tot : tot;
+        }
+    }
+}
+
+/// One CTA per clone: Metropolis test (displace_particle_class.h:65-71) and Move::Accept.
+__global__ void __launch_bounds__(256) displace_decide_commit_kernel(PathView pv, int N, int n_k, int n_chunks, const double *__restrict__ partial,
+                                                                     int use_lr, const double *__restrict__ lr_old, const double *__restrict__ lr_new,
+                                                                     const double *__restrict__ logu, const double *__restrict__ P,
+                                                                     const int32_t *__restrict__ P_particle, const double2 *__restrict__ drho,
+                                                                     double *__restrict__ R, double2 *__restrict__ rho, int32_t *__restrict__ accept,
+                                                                     long long *__restrict__ n_accept) {
+    const int c = blockIdx.x;
+    double old_action = 0., new_action = 0.;
+    for (int i = 0; i < n_chunks; ++i) {  // every thread the same fixed-order sum
+        old_action += partial[((size_t)c * n_chunks + i) * 2];
+        new_action += partial[((size_t)c * n_chunks + i) * 2 + 1];
+    }
+    if (use_lr) {
+        old_action += lr_old[c];
+        new_action += lr_new[c];
+    }
+    const int acc = (old_action - new_action) < logu[c] ? 0 : 1;
+    if (threadIdx.x == 0) {
+        accept[c] = acc;
+        n_accept[c] += acc;
+    }
+    if (!acc) return;
+    const int p = P_particle[c];
+    for (int t = threadIdx.x; t < pv.M * 3; t += blockDim.x) {
+        const int d = t / pv.M, b = t - d * pv.M;
+        R[PosIndex(pv, N, c, p, d, b)] = P[((size_t)c * pv.M + b) * 3 + d];
+    }
+    if (drho) {
+        const size_t n = (size_t)pv.M * n_k;
+        double2 *dst = rho + (size_t)c * n;
+        const double2 *src = drho + (size_t)c * n;
+        for (size_t t = threadIdx.x; t < n; t += blockDim.x) {
+            double2 v = dst[t];
+            v.x += src[t].x;
+            v.y += src[t].y;
+            dst[t] = v;
+        }
+    }
+}
+
+}  // namespace pimc
+
+#endif  // SIMPIMC_B200_DISPLACE_CUH_

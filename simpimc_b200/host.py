@@ -152,6 +152,12 @@ class Path:
                                             _vp(n_accept)))
         return n_accept
 
+    def DisplaceSweep(self, species, step_size, n_attempts, seed, attempt0=0):
+        """n_attempts device-resident DisplaceParticle::DoEvent calls per clone; returns accepts per clone."""
+        n_accept = np.zeros(self.n_clones, dtype=np.int64)
+        capi.check(self.L.pimc_displace_sweep(self.h, species, float(step_size), n_attempts, seed, attempt0, _vp(n_accept)))
+        return n_accept
+
     def LaunchCount(self):
         return int(self.L.pimc_ctx_launch_count(self.h))
 

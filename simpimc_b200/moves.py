@@ -218,3 +218,37 @@ def bisect_attempt_philox(cfg, species, n_level, seed, attempt, n_clones, get_be
         out_b.append(bead0)
         out_acc.append(accept)
     return np.array(out_p), np.array(out_b), np.array(out_acc)
+
+
+def displace_attempt_philox(cfg, species, step_size, seed, attempt, n_clones, get_beads, action_old_new, finish):
+    """Host mirror of ONE device-resident DisplaceParticle attempt (csrc/displace.cuh) drawing the
+    same Philox stream: slot 0 particle, slots 1-2 direction, slot 3 Metropolis uniform.
+
+    get_beads(c, p, 0, M) -> committed path [M][3]; action_old_new(c, p, new) -> (old, new) action
+    over the whole path summed over the pair actions that involve `species`; finish(c, p, accept).
+    Returns (particle[c], accept[c])."""
+    from . import philox as PX
+    N, M = cfg.species[species].n_part, cfg.n_bead
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    a_lo, a_hi = attempt & 0xFFFFFFFF, (attempt >> 32) & 0xFFFFFFFF
+    out_p, out_acc = [], []
+    for c in range(n_clones):
+        r0 = PX.philox4x32(a_lo, a_hi, c, 0, k0, k1)
+        r1 = PX.philox4x32(a_lo, a_hi, c, 1, k0, k1)
+        r2 = PX.philox4x32(a_lo, a_hi, c, 2, k0, k1)
+        r3 = PX.philox4x32(a_lo, a_hi, c, 3, k0, k1)
+        p_i = min(int(PX.uniform_from_bits(r0[0], r0[1]) * N), N - 1)
+        # RNG::UnifRand(vec, l): (b - a) * u + a per component, normalised, times l (rng.h:31-56)
+        v = np.array([2.0 * PX.uniform_from_bits(r1[0], r1[1]) + -1.0, 2.0 * PX.uniform_from_bits(r1[2], r1[3]) + -1.0,
+                      2.0 * PX.uniform_from_bits(r2[0], r2[1]) + -1.0])
+        m = math.sqrt((v[0] * v[0] + v[2] * v[2]) + v[1] * v[1])
+        dr = (v / m) * step_size
+        logu = math.log(PX.uniform_from_bits(r3[0], r3[1]))
+        old = np.array(get_beads(c, p_i, 0, M), dtype=np.float64)
+        new = old + dr[None, :]
+        old_action, new_action = action_old_new(c, p_i, new)
+        accept = not ((old_action - new_action) < logu)
+        finish(c, p_i, accept)
+        out_p.append(p_i)
+        out_acc.append(1 if accept else 0)
+    return np.array(out_p), np.array(out_acc)

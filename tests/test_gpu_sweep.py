@@ -348,3 +348,71 @@ def test_slice_sharded_sweeps_follow_the_host_mirror_and_rotate(name, n_shards):
         p.close()
     for o in oracles:
         o.close()
+
+
+@pytest.mark.parametrize("name,general", [("ueg", False), ("ueg", True), ("plasma", False), ("bare", False), ("nolr", False)])
+def test_device_displace_follows_the_host_mirror_of_its_stream(name, general):
+    """pimc_displace_sweep (csrc/displace.cuh): DisplaceParticle::DoEvent on the device.  The host
+    mirror draws the same Philox numbers and takes the whole-path OLD / NEW actions from the CPU
+    oracle: same positions (1e-12) and accept history after every attempt, rho_k carried along."""
+    from simpimc_b200 import host, moves
+    from oracle import oracle as O
+    if name == "ueg":
+        cfg, step = S.ueg_config(N=9, M=40), 0.9      # M = 40: a partial second chunk of 32 links
+    elif name == "bare":
+        cfg, step = S.ueg_config(N=6, M=8, action="BarePairAction"), 1.2
+    elif name == "nolr":
+        cfg, step = S.ueg_config(N=6, M=8, use_long_range=False), 1.0
+    else:
+        cfg, step = S.plasma_config(Ne=5, Np=4, M=8), 0.8
+    C = 3
+    path = host.Path(cfg, n_clones=C)
+    path.ForceGeneral(general)
+    oracles = [O.Oracle(cfg) for _ in range(C)]
+    for sp in range(len(cfg.species)):
+        R = np.stack([S.synthetic_paths(cfg, sp, c, 99) for c in range(C)])
+        path.SetPositions(sp, R)
+        for c in range(C):
+            oracles[c].set_positions(sp, R[c])
+    seed, M = 0x5EED00000007, cfg.n_bead
+    n_dev = np.zeros(C, dtype=np.int64)
+    n_host = np.zeros(C, dtype=np.int64)
+    for attempt in range(24):
+        sp = attempt % len(cfg.species)
+        acts = [ai for ai, a in enumerate(cfg.actions) if cfg.species[sp].name in (a.species_a, a.species_b)]
+
+        def get_beads(c, p, b0, n):
+            return oracles[c].get_positions(sp, 0)[p, (b0 + np.arange(n)) % M]
+
+        def action_old_new(c, p, new):
+            oracles[c].propose(sp, p, 0, new)
+            old = sum(oracles[c].get_action(ai, 0, 0, M, [(sp, p)], 0) for ai in acts)
+            nw = sum(oracles[c].get_action(ai, 1, 0, M, [(sp, p)], 0) for ai in acts)
+            return old, nw
+
+        def finish(c, p, accept):
+            oracles[c].finish_move(sp, p, 0, M, bool(accept))
+
+        _, acc = moves.displace_attempt_philox(cfg, sp, step, seed, attempt, C, get_beads, action_old_new, finish)
+        n_host += acc
+        n_dev += path.DisplaceSweep(sp, step, 1, seed, attempt0=attempt)
+        got = path.GetPositions(sp)
+        for c in range(C):
+            ref = oracles[c].get_positions(sp, 0)
+            assert np.max(np.abs(got[c] - ref)) <= 1e-12 * max(1.0, np.max(np.abs(ref))), (name, attempt, c)
+        assert np.array_equal(n_dev, n_host), (name, attempt, n_dev, n_host)
+    assert 0 < n_dev.sum() < 24 * C          # both outcomes occurred
+    if path._n_k():
+        for sp in range(len(cfg.species)):
+            for c in range(C):
+                assert np.max(np.abs(path.GetRhoK(sp, c, host.OLD_MODE) - oracles[c].rhok(sp, 0))) <= 1e-10 * cfg.species[sp].n_part
+    for ai, act in enumerate(path.actions):
+        du = act.DActionDBeta()
+        for c in range(C):
+            assert abs(du[c] - oracles[c].dbeta(ai)) <= 1e-10 * abs(oracles[c].dbeta(ai))
+    # many attempts in one call == one by one (same stream)
+    a = path.DisplaceSweep(0, step, 5, seed, attempt0=100)
+    assert a.shape == (C,)
+    path.close()
+    for o in oracles:
+        o.close()
