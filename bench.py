@@ -510,6 +510,31 @@ def run_c5(args):
     e2e_value = evals_step * args.steps / (float(te.item()) * 1e-3)
     energies = out_dev.cpu().numpy().copy()
     assert np.allclose(energies, out_host, rtol=1e-12, atol=0), "resident and e2e energies differ"
+    # ---- moves on the sharded path: shard-interior bisection windows on every rank at once (no
+    # communication), then one ring rotation of the slices over NCCL (positions, halos, rho_k) ----
+    mc = None
+    if sh.n_local >= (1 << BISECT_LEVEL) and args.attempts > 0:
+        n_att = max(4, min(args.attempts, 64))
+        for sp in range(2):
+            sp_path.BisectSweep(sp, BISECT_LEVEL, 2, 99 + rank, attempt0=0)
+        barrier()
+        w0 = time.perf_counter()
+        n_acc = 0
+        for sp in range(2):
+            n_acc += int(sp_path.BisectSweep(sp, BISECT_LEVEL, n_att, 99 + rank, attempt0=2).sum())
+        torch.cuda.synchronize()
+        w1 = time.perf_counter()
+        sp_path.Rotate(BISECT_LEVEL + 1)
+        torch.cuda.synchronize()
+        w2 = time.perf_counter()
+        barrier()
+        tm = torch.tensor([w1 - w0, w2 - w1], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        attempts_per_sweep = 2 * Ne * M // (1 << BISECT_LEVEL)
+        mc = {"attempts_per_s": world * C * 2 * n_att / float(tm[0].item()), "sweeps_per_s": world * C * 2 * n_att / attempts_per_sweep / float(tm[0].item()),
+              "attempts_timed_per_rank": 2 * n_att * C, "accept_ratio_rank0": n_acc / (2.0 * n_att * C), "rotate_ms": 1e3 * float(tm[1].item()),
+              "driver": "pimc_bisect_sweep (kernel-per-phase path: 2 species, 3 actions) on each rank's shard, windows of %d slices; ShardedPath.Rotate" % (1 << BISECT_LEVEL)}
     if rank == 0:
         k1_step_s = k1_ms / args.steps * 1e-3          # the three K1 launches of a step on this rank
         achieved = (evals_step / world) * FLOP_PER_EVAL / k1_step_s / 1e12
@@ -527,6 +552,7 @@ def run_c5(args):
                         "d2h_bytes_per_step": int(out_host.nbytes), "halo_bytes_per_step": int(2 * C * Ne * 3 * 8) if world > 1 else 0},
                 "gpu_launches": int(launches),
                 "energies": {"dU/dbeta per action (clone 0)": [float(x) for x in energies[:, 0]]},
+                "mc": mc,
                 "roofline": {"bound": "fp64", "kernel": "pair_full_fast_kernel x 3 actions", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                              "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
                              "kernel_ms_per_step": {"K1_pair_full": k1_ms / args.steps, "K2_rhok_build": k2_ms / args.steps, "K3_ksum": k3_ms / args.steps},
