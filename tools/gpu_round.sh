@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU-box pass: parity tests, smoke, bench (+ reference arm), ncu launch list, ncu full
-# captures of K1 (pair_full_fast), K2 (rhok_build_cols) and the fused bisection sweep.
+# captures of K1 (pair_full_fast), K2 (rhok_build_cols), the fused bisection sweep and K5 (gofr_tiled).
 set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
@@ -11,5 +11,6 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/b
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --cpu-evals 0 --attempts 4 > gpurun_out/bench_ncu.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:pair_full -s 1 -c 1 -o gpurun_out/prof_k1 -f python bench.py --steps 1 --warmup 1 --cpu-evals 0 --attempts 1 --clones 256 > gpurun_out/prof_k1.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:rhok_build -s 1 -c 1 -o gpurun_out/prof_k2 -f python bench.py --steps 1 --warmup 1 --cpu-evals 0 --attempts 1 --clones 256 > gpurun_out/prof_k2.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:bisect_sweep_fused -c 1 -o gpurun_out/prof_sweep -f python bench.py --steps 1 --warmup 1 --cpu-evals 0 --attempts 8 --clones 256 > gpurun_out/prof_sweep.log 2>&1
+bash tools/gpu_prof_sweep.sh
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gofr_tiled -s 1 -c 1 -o gpurun_out/prof_k5 -f python bench.py --steps 1 --warmup 1 --cpu-evals 0 --attempts 1 --clones 256 > gpurun_out/prof_k5.log 2>&1
 ls -la gpurun_out
