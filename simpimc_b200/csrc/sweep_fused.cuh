@@ -5,8 +5,9 @@
 //
 // Clones are independent walkers, so a sweep needs no grid-wide synchronisation: persistent
 // CTAs (one per SM, 1024 threads) stage the fast Ilkka tables in shared memory ONCE and then
-// split into kSweepTeams independent TEAMS of 8 warps.  A team owns up to kTeamClones clones
-// at a time and runs their attempts back to back, synchronising only with itself (named
+// split into kSweepTeams independent TEAMS (8 teams of 4 warps, one clone each, measured best:
+// 2 teams 2863, 4 teams 3037, 8 teams 3194 clone-sweeps/s at C3).  A team owns up to kTeamClones
+// clones at a time and runs their attempts back to back, synchronising only with itself (named
 // barrier) between the phases of an attempt -- the teams drift apart, so the serial phases of
 // one (Levy construction, Metropolis test: one thread per clone) are hidden behind the pair
 // work of the others while all of them share one copy of the tables:
@@ -34,10 +35,13 @@
 namespace pimc {
 
 constexpr int kSweepThreads = 1024;
-constexpr int kSweepTeams = 4;                               // independent sub-CTA teams
+#ifndef PIMC_SWEEP_TEAMS
+#define PIMC_SWEEP_TEAMS 8
+#endif
+constexpr int kSweepTeams = PIMC_SWEEP_TEAMS;                // independent sub-CTA teams
 constexpr int kTeamThreads = kSweepThreads / kSweepTeams;
 constexpr int kTeamWarps = kTeamThreads / 32;
-constexpr int kTeamClones = 2;                               // clones a team advances together
+constexpr int kTeamClones = 8 / kSweepTeams;                 // clones a team advances together
 constexpr int kSweepClones = kSweepTeams * kTeamClones;      // clones in flight per CTA
 constexpr int kSweepGroup = kTeamThreads / kTeamClones;      // threads that own one clone in phases C-E
 constexpr int kSweepGroupWarps = kSweepGroup / 32;
@@ -197,8 +201,8 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                     sh.particle[s0 + lc] = p_i;
                     sh.bead0[s0 + lc] = b0;
                 }
-            } else if (tid >= 128 && tid < 128 + nlc * (nb - 1)) {  // Levy displacements
-                const int t = tid - 128;
+            } else if (tid >= kTeamThreads / 2 && tid < kTeamThreads / 2 + nlc * (nb - 1)) {  // Levy displacements
+                const int t = tid - kTeamThreads / 2;
                 const int lc = t / (nb - 1), ib = t - lc * (nb - 1) + 1;
                 const int c = SWEEP_CLONE(lc);
                 const int level = __ffs(ib) - 1, skip = 1 << level;
@@ -224,8 +228,8 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                     d2 += del * del;
                 }
                 sh.d2_new[s0 + lc][ib] = d2;
-            } else if (tid >= 192 && tid < 192 + nlc * a.n_level) {  // Metropolis uniforms
-                const int t = tid - 192;
+            } else if (tid >= 3 * kTeamThreads / 4 && tid < 3 * kTeamThreads / 4 + nlc * a.n_level) {  // Metropolis uniforms
+                const int t = tid - 3 * kTeamThreads / 4;
                 const int lc = t / a.n_level, level = t - lc * a.n_level;
                 const int c = SWEEP_CLONE(lc);
                 const uint32_t slot = SweepSlotStart(level, a.n_level, nb) + 2u * (uint32_t)(nb >> (level + 1));
