@@ -60,6 +60,16 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def ensure_samples(self, step, sync, n_min=2, max_s=3.0):
+        """Keep the GPU under the same load (untimed extra steps) until nvidia-smi has delivered
+        n_min samples: a timed region shorter than its sampling period would otherwise have none."""
+        if not self.proc:
+            return
+        t0 = time.perf_counter()
+        while len(self.lines) < n_min and time.perf_counter() - t0 < max_s:
+            step()
+            sync()
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -83,7 +93,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": "warm-up + timed steps (+ identical untimed steps until nvidia-smi has delivered 2 samples)"}
 
 
 # ---------------------------------------------------------------------------- CPU baseline
@@ -230,14 +240,16 @@ def run_ours(args):
         path.Sync()
 
     fp64_peak = path.Fp64Peak()
+    # clocks are sampled from the warm-up on (same load as the timed steps): nvidia-smi needs a few
+    # hundred ms for its first line, longer than a short timed region
+    clocks = ClockSampler(local)
+    clocks.start()
     for _ in range(args.warmup):
         step_resident()
     path.Sync()
     # ---- device-resident timing ------------------------------------------------------------
     path.SetTiming(True)
-    clocks = ClockSampler(local)
     barrier()
-    clocks.start()
     launches0 = path.LaunchCount()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -247,12 +259,13 @@ def run_ours(args):
     e1.synchronize()
     barrier()
     launches = path.LaunchCount() - launches0
-    clk = clocks.stop()
     ms_total = e0.elapsed_time(e1)
     k1_ms, k1_n = path.KernelTime(1)
     k2_ms, k2_n = path.KernelTime(2)
     k3_ms, k3_n = path.KernelTime(3)
     path.SetTiming(False)
+    clocks.ensure_samples(step_resident, path.Sync)
+    clk = clocks.stop()
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -466,13 +479,13 @@ def run_c5(args):
 
     upload_and_halo()
     fp64_peak = path.Fp64Peak()
+    clocks = ClockSampler(local)
+    clocks.start()
     for _ in range(args.warmup):
         step_resident()
     path.Sync()
     path.SetTiming(True)
-    clocks = ClockSampler(local)
     barrier()
-    clocks.start()
     launches0 = path.LaunchCount()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -482,11 +495,12 @@ def run_c5(args):
     e1.synchronize()
     barrier()
     launches = path.LaunchCount() - launches0
-    clk = clocks.stop()
     k1_ms, k1_n = path.KernelTime(1)
     k2_ms, k2_n = path.KernelTime(2)
     k3_ms, k3_n = path.KernelTime(3)
     path.SetTiming(False)
+    clocks.ensure_samples(step_resident, path.Sync)
+    clk = clocks.stop()
     ms_total = e0.elapsed_time(e1)
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if world > 1:
