@@ -100,3 +100,32 @@ def test_oracle_matches_live_reference(seed, oracle_mod):
         assert np.max(np.abs(o.rhok(sp) - sim.rhok(sp))) <= 1e-12 * 5
     sim.close()
     o.close()
+
+
+def test_spline_definition_matches_scipy_natural_cubic_spline(oracle_mod):
+    """The spline library the reference links (etano/meinspline, unpinned) is absent; the oracle
+    restates einspline's published algorithm.  Independent check of that restatement: an
+    interpolating cubic spline with NATURAL boundaries (zero second derivative at both ends) is
+    unique, so it must coincide with scipy.interpolate.CubicSpline(bc_type='natural') -- in 1-D on
+    the reference's non-uniform OPTIMIZED grid, and in 2-D as the tensor product (natural along
+    x for every y column, then natural along y), which is how create_NUBspline_2d_d solves."""
+    from scipy.interpolate import CubicSpline
+    from simpimc_b200 import tables as T
+    O = oracle_mod
+    rng = np.random.default_rng(3)
+    g = T.gen_grid("OPTIMIZED", 1.0e-4, 9.0, 200)
+    f = np.exp(-0.3 * g) * np.cos(1.7 * g) / (0.2 + g)
+    x = np.concatenate([rng.uniform(g[0], g[-1], 4000), g, [g[0], g[-1]]])
+    ref = CubicSpline(g, f, bc_type="natural")(x)
+    got = O.spline1d_eval(g, f, x)
+    assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(f))
+    # 2-D tensor product on the (x, y) grid of an off-diagonal table
+    gx = T.gen_grid("OPTIMIZED", 0.0, 12.0, 40)
+    gy = T.gen_grid("OPTIMIZED", 0.0, 12.0, 35)
+    X, Y = np.meshgrid(gx, gy, indexing="ij")
+    F = np.exp(-0.2 * (X + Y)) * (1.0 + 0.3 * np.sin(X - Y)) / (0.5 + X * Y / 10.0)
+    xs, ys = rng.uniform(gx[0], gx[-1], 500), rng.uniform(gy[0], gy[-1], 500)
+    got2 = O.spline2d_eval(gx, gy, F, xs, ys)
+    along_y = CubicSpline(gy, F, axis=1, bc_type="natural")          # for every x row: natural spline in y
+    ref2 = np.array([CubicSpline(gx, along_y(yy), bc_type="natural")(xx) for xx, yy in zip(xs, ys)])
+    assert np.max(np.abs(got2 - ref2)) <= 1e-12 * np.max(np.abs(F))
