@@ -6,8 +6,8 @@
 // github.com/etano/meinspline `master`.  The reference has no test or golden vector at
 // this boundary, so PARITY IS UNPINNED against the reference here; what is pinned is the
 // mathematics: the interpolant (natural cubic spline through the table, tensor product in
-// 2-D) is unique, and tests/test_oracle_spline.py checks this restatement against scipy's
-// independent natural cubic spline to ~1e-13.
+// 2-D) is unique, and tests/test_oracle_cpu.py (test_spline_definition_matches_scipy_...) checks this restatement against scipy's
+// independent natural cubic spline (1-D and tensor-product 2-D) to 1e-12.
 //
 // What follows restates the published einspline 0.9.2 algorithm (nugrid.c, nubasis.c,
 // nubspline_create.c, nubspline_eval_std_d.h, bspline_create.c) as called from
