@@ -15,7 +15,8 @@ from simpimc_b200 import system as S
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name,general", [("ueg", False), ("ueg", True), ("plasma", False), ("nolr", False), ("nolr", True), ("ueg4", False)])
+@pytest.mark.parametrize("name,general", [("ueg", False), ("ueg", True), ("plasma", False), ("nolr", False), ("nolr", True), ("ueg4", False),
+                                          ("carbon", False)])
 def test_device_sweep_follows_the_host_mirror_of_its_stream(name, general):
     """general = False: the single-launch sweep (csrc/sweep_fused.cuh) where it applies (ueg, nolr,
     ueg4: one same-species Ilkka action), the kernel-per-phase path otherwise (plasma);
@@ -28,6 +29,8 @@ def test_device_sweep_follows_the_host_mirror_of_its_stream(name, general):
         cfg, n_level = S.ueg_config(N=37, M=32), 4
     elif name == "nolr":
         cfg, n_level = S.ueg_config(N=6, M=8, use_long_range=False), 2
+    elif name == "carbon":
+        cfg, n_level = S.carbon_config(), 2     # BASELINE config C4: 4 species, 9 Ilkka + 1 Bare action, all long-range
     else:
         cfg, n_level = S.plasma_config(Ne=5, Np=4, M=8), 2
     C = 3
