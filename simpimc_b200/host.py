@@ -407,3 +407,45 @@ class Energy:
         e, v = self.energies / norm, self.potentials / norm
         self.Reset()
         return e, v
+
+
+class PathDump:
+    """src/events/observables/path_dump_class.h:27-68 and the "Restart" branch of Species::InitPaths
+    (species_class.h:336-378): every Write() appends each species' positions -- the reference's
+    cube (n_d, n_bead, n_part) is [n_part][n_bead][n_d] in file order, the order used here, with a
+    leading clone axis -- and the permutation table (previous particle of bead 0, next particle
+    of the last bead: the identity here, permutation moves are not on this path).  The container
+    is a flat .npz with the reference's dataset names as keys (no HDF5 library in this build)."""
+
+    def __init__(self, path, name="path_dump", skip=1):
+        self.path, self.name, self.skip = path, name, max(1, int(skip))
+        self.n_dump, self.n_write_calls = 0, 0
+        self.positions = {s.name: [] for s in path.cfg.species}
+
+    def Write(self):
+        if self.n_write_calls % self.skip == 0:
+            self.n_dump += 1
+            for si, s in enumerate(self.path.cfg.species):
+                self.positions[s.name].append(self.path.GetPositions(si))
+        self.n_write_calls += 1
+
+    def Save(self, file_name):
+        out = {}
+        for s in self.path.cfg.species:
+            key = "Observables/%s/%s/" % (self.name, s.name)
+            out[key + "n_dump"] = np.int64(self.n_dump)
+            out[key + "positions"] = np.stack(self.positions[s.name]) if self.positions[s.name] else np.zeros((0,))
+            ident = np.arange(s.n_part, dtype=np.float64)
+            out[key + "permutation"] = np.tile(np.stack([ident, ident]).T, (self.n_dump, 1, 1))   # [dump][n_part][2]
+        np.savez_compressed(file_name, **out)
+
+    @staticmethod
+    def Restart(path, file_name, name="path_dump"):
+        """init_type="Restart": the LAST dump of every species becomes the configuration."""
+        f = np.load(file_name)
+        for si, s in enumerate(path.cfg.species):
+            key = "Observables/%s/%s/" % (name, s.name)
+            perm = f[key + "permutation"][-1]
+            if not (np.array_equal(perm[:, 0], np.arange(s.n_part)) and np.array_equal(perm[:, 1], np.arange(s.n_part))):
+                raise ValueError("ERROR: permuted paths are not supported on this path")
+            path.SetPositions(si, f[key + "positions"][-1])
