@@ -179,7 +179,8 @@ int pimc_action_potential_device(pimc_action *act, double *d_out);
 
 /* Action::GetAction(b0, b1, particles, level) (pair_action_class.h:267-302).
  *   b0[n_clones]                first slice of each clone's window; b1 = b0 + n_window
- *   moved_species[n_moved]      species of each moved particle (same for all clones)
+ *   moved_species[n_moved]      species of each moved particle (same for all clones); up to four
+ *                               particles of each of the action's species (permutation cycles)
  *   moved_particle[n_clones][n_moved]
  * Returns 0 for level > max_level or constant actions, as the reference does.  In NEW mode
  * with use_long_range the first call after pimc_commit / pimc_action_accept refreshes the
@@ -219,7 +220,9 @@ int pimc_ctx_force_general(pimc_ctx *ctx, int32_t enable);
 /* ---- moves' contract ------------------------------------------------------------------ */
 /* NEW-mode Bead::SetR for one particle per clone (bisect_class.h:89-94,
  * displace_particle_class.h:40-50): beads b_first[c] .. b_first[c]+n_beads-1 (mod n_bead)
- * of particle[c] take newR[c][i][dim]. */
+ * of particle[c] take newR[c][i][dim].  Calling it again for a species that already has a pending
+ * proposal ADDS a particle (same n_beads, a different particle in every clone; at most four per
+ * species): the particles of a permutation cycle. */
 int pimc_propose(pimc_ctx *ctx, int32_t species, const int32_t *particle, const int32_t *b_first, int32_t n_beads,
                  const double *newR);
 /* Committed positions of beads b_first[c] .. b_first[c]+n_beads-1 (mod n_bead) of

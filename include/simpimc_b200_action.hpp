@@ -37,7 +37,7 @@ class GpuPathMirror {
     Path &path;
     bool stale = true;             ///< committed device positions differ from the beads' r_c
     bool proposal_pending = false;  ///< pimc_propose issued, pimc_commit not yet
-    std::vector<int32_t> prop_species;  ///< species with a pending proposal
+    std::vector<std::pair<int32_t, int32_t>> prop_particles;  ///< (species, particle) with a pending proposal
 
     static std::shared_ptr<GpuPathMirror> Get(Path &path) {
         static std::map<Path *, std::weak_ptr<GpuPathMirror>> registry;
@@ -76,7 +76,7 @@ class GpuPathMirror {
         path.SetMode(saved);
         stale = false;
         proposal_pending = false;
-        prop_species.clear();
+        prop_particles.clear();
     }
 
     /// NEW copies of beads b0..b1 of one particle -> pending proposal.
@@ -94,7 +94,7 @@ class GpuPathMirror {
         const int32_t particle = (int32_t)p, first = (int32_t)sp->bead_loop(b0);
         Check(pimc_propose(ctx, (int32_t)sp->GetId(), &particle, &first, (int32_t)n, newR.data()), "pimc_propose");
         proposal_pending = true;
-        prop_species.push_back((int32_t)sp->GetId());
+        prop_particles.push_back(std::make_pair((int32_t)sp->GetId(), (int32_t)p));
     }
 
     void Finish(bool accept) {
@@ -104,8 +104,15 @@ class GpuPathMirror {
         }
         const int32_t flag = accept ? 1 : 0;
         Check(pimc_commit(ctx, &flag), "pimc_commit");
+        // several particles of one species = a permutation move: on acceptance the reference relabels
+        // the permuted beads (PermBisect::AssignParticleLabels, perm_bisect_class.h:47-56), which this
+        // mirror does not follow -- re-upload the committed beads before the next evaluation
+        if (accept)
+            for (size_t i = 0; i < prop_particles.size(); ++i)
+                for (size_t j = i + 1; j < prop_particles.size(); ++j)
+                    if (prop_particles[i].first == prop_particles[j].first) stale = true;
         proposal_pending = false;
-        prop_species.clear();
+        prop_particles.clear();
     }
 
    private:
@@ -298,7 +305,7 @@ class GpuPairAction : public Action {
         if (mode == PIMC_NEW) {
             for (auto &p : particles) {
                 bool have = false;
-                for (int32_t s : mirror->prop_species) have = have || s == (int32_t)p.first->GetId();
+                for (auto &q : mirror->prop_particles) have = have || (q.first == (int32_t)p.first->GetId() && q.second == (int32_t)p.second);
                 if (!have) mirror->Propose(p.first, p.second, b0, b1);
             }
         }

@@ -67,10 +67,11 @@ struct SpeciesState {
     double lambda = 0.;
     DevBuf<double> R;        // committed positions [C][N][3][Ms]
     DevBuf<double2> rho;     // committed rho_k [C][Mloc][n_k]
-    // pending proposal
-    DevBuf<double> P;        // [C][n_prop][3]
-    DevBuf<int32_t> P_particle, P_first;
-    int n_prop = 0;
+    // pending proposals: n_slots particles of the species per clone, n_prop beads each
+    DevBuf<double> P;        // [slot][C][n_prop][3]
+    DevBuf<int32_t> P_particle, P_first;  // [slot][C]
+    int n_prop = 0, n_slots = 0;
+    std::vector<int32_t> h_particle;      // host copy of P_particle (duplicate check)
     // rho_k increment of the proposal over the window it was computed for
     DevBuf<double2> drho;
     DevBuf<int32_t> drho_b0;
@@ -143,6 +144,7 @@ struct pimc_ctx {
         v.P_particle = st.P_particle.p;
         v.P_first = st.P_first.p;
         v.n_prop = with_proposal ? st.n_prop : 0;
+        v.n_slots = with_proposal ? st.n_slots : 0;
         return v;
     }
     KSpaceView KView() const {
@@ -926,8 +928,8 @@ int pimc_ctx_create(const pimc_config *cfg, pimc_ctx **out) {
         const size_t n = (size_t)ctx->C * st->N * 3 * ctx->Ms;
         PIMC_CUDA(st->R.Alloc(n));
         PIMC_CUDA(cudaMemsetAsync(st->R.p, 0, n * sizeof(double), ctx->stream));
-        PIMC_CUDA(st->P_particle.Alloc(ctx->C));
-        PIMC_CUDA(st->P_first.Alloc(ctx->C));
+        PIMC_CUDA(st->P_particle.Alloc((size_t)kMaxPropSlots * ctx->C));
+        PIMC_CUDA(st->P_first.Alloc((size_t)kMaxPropSlots * ctx->C));
         PIMC_CUDA(st->drho_b0.Alloc(ctx->C));
         ctx->species.push_back(std::move(st));
     }
@@ -993,6 +995,7 @@ int pimc_positions_upload(pimc_ctx *ctx, int32_t s, int32_t clone_lo, int32_t cl
     ctx->launches++;
     PIMC_CUDA(cudaGetLastError());
     st.n_prop = 0;
+    st.n_slots = 0;
     if (clone_lo == 0 && clone_hi == ctx->C) return RebuildRhoK(ctx, s);
     st.need_update_rho_k = true;
     st.drho_valid = false;
@@ -1023,6 +1026,7 @@ int pimc_positions_set_device(pimc_ctx *ctx, int32_t s, const double *d_R) {
     SpeciesState &st = *ctx->species[s];
     PIMC_CUDA(cudaMemcpyAsync(st.R.p, d_R, st.R.n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     st.n_prop = 0;
+    st.n_slots = 0;
     return RebuildRhoK(ctx, s);
 }
 
@@ -1380,40 +1384,52 @@ int pimc_action_get(pimc_action *act, int32_t mode, const int32_t *b0, int32_t n
     }
     if (ctx->sharded) return Fail(PIMC_ERR_UNSUPPORTED, "move windows on a slice-sharded context");
     if (n_window < 1 || n_window > ctx->M) return Fail(PIMC_ERR_INVALID, "window must cover 1..n_bead slices");
-    int ia = -1, ib = -1;
+    // the listed particles of the action's two species (GenerateParticlePairs, pair_action_class.h:63-76):
+    // one for Bisect / DisplaceParticle, the particles of a cycle for permutation moves
+    std::vector<int> ia, ib;
     for (int i = 0; i < n_moved; ++i) {
-        if (moved_species[i] == act->sa) {
-            if (ia >= 0) return Fail(PIMC_ERR_UNSUPPORTED, "two moved particles of one species (permutation moves are a later row)");
-            ia = i;
-        } else if (moved_species[i] == act->sb) {
-            if (ib >= 0) return Fail(PIMC_ERR_UNSUPPORTED, "two moved particles of one species (permutation moves are a later row)");
-            ib = i;
-        }
+        if (moved_species[i] == act->sa)
+            ia.push_back(i);
+        else if (moved_species[i] == act->sb)
+            ib.push_back(i);
     }
-    if (act->sa == act->sb) ib = -1;
-    if (ia < 0 && ib < 0) {  // pair_action_class.h:77-78
+    if (act->sa == act->sb) ib.clear();
+    if ((int)ia.size() > kMaxPropSlots || (int)ib.size() > kMaxPropSlots)
+        return Fail(PIMC_ERR_UNSUPPORTED, "more than 4 listed particles of one species");
+    if (ia.empty() && ib.empty()) {  // pair_action_class.h:77-78
         for (int c = 0; c < ctx->C; ++c) out[c] = 0.;
         return PIMC_OK;
     }
-    std::vector<int32_t> pa(ctx->C, 0), pb(ctx->C, 0);
+    const int na = (int)ia.size(), nb_l = (int)ib.size();
+    std::vector<int32_t> pa((size_t)std::max(na, 1) * ctx->C, 0), pb((size_t)std::max(nb_l, 1) * ctx->C, 0);
     for (int c = 0; c < ctx->C; ++c) {
-        if (ia >= 0) pa[c] = moved_particle[(size_t)c * n_moved + ia];
-        if (ib >= 0) pb[c] = moved_particle[(size_t)c * n_moved + ib];
         if (b0[c] < 0 || b0[c] >= ctx->M) return Fail(PIMC_ERR_INVALID, "window start out of range");
-        if (ia >= 0 && (pa[c] < 0 || pa[c] >= ctx->species[act->sa]->N)) return Fail(PIMC_ERR_INVALID, "moved particle out of range");
-        if (ib >= 0 && (pb[c] < 0 || pb[c] >= ctx->species[act->sb]->N)) return Fail(PIMC_ERR_INVALID, "moved particle out of range");
+        for (int i = 0; i < na; ++i) {
+            const int32_t p = moved_particle[(size_t)c * n_moved + ia[i]];
+            if (p < 0 || p >= ctx->species[act->sa]->N) return Fail(PIMC_ERR_INVALID, "moved particle out of range");
+            for (int i2 = 0; i2 < i; ++i2)
+                if (pa[(size_t)i2 * ctx->C + c] == p) return Fail(PIMC_ERR_INVALID, "particle listed twice");
+            pa[(size_t)i * ctx->C + c] = p;
+        }
+        for (int i = 0; i < nb_l; ++i) {
+            const int32_t p = moved_particle[(size_t)c * n_moved + ib[i]];
+            if (p < 0 || p >= ctx->species[act->sb]->N) return Fail(PIMC_ERR_INVALID, "moved particle out of range");
+            for (int i2 = 0; i2 < i; ++i2)
+                if (pb[(size_t)i2 * ctx->C + c] == p) return Fail(PIMC_ERR_INVALID, "particle listed twice");
+            pb[(size_t)i * ctx->C + c] = p;
+        }
     }
     int rc;
-    if ((rc = EnsureI32(ctx, ctx->i32_a, pa.data(), ctx->C)) != PIMC_OK) return rc;
-    if ((rc = EnsureI32(ctx, ctx->i32_b, pb.data(), ctx->C)) != PIMC_OK) return rc;
+    if ((rc = EnsureI32(ctx, ctx->i32_a, pa.data(), pa.size())) != PIMC_OK) return rc;
+    if ((rc = EnsureI32(ctx, ctx->i32_b, pb.data(), pb.size())) != PIMC_OK) return rc;
     if ((rc = EnsureI32(ctx, ctx->i32_c, b0, ctx->C)) != PIMC_OK) return rc;
     PairWindowArgs w;
     w.pv = ctx->View();
     w.A = ctx->SView(act->sa, mode == PIMC_NEW);
     w.B = ctx->SView(act->sb, mode == PIMC_NEW);
     w.same = act->sa == act->sb;
-    w.moved_a = ia >= 0;
-    w.moved_b = ib >= 0;
+    w.n_a = na;
+    w.n_b = nb_l;
     w.part_a = ctx->i32_a.p;
     w.part_b = ctx->i32_b.p;
     w.b0 = ctx->i32_c.p;
@@ -1440,7 +1456,7 @@ int pimc_action_get(pimc_action *act, int32_t mode, const int32_t *b0, int32_t n
         // pair_action_class.h:293-299: refresh the proposal's rho_k once per move per species
         if (mode == PIMC_NEW) {
             const int sp[2] = {act->sa, act->sb};
-            const int idx[2] = {ia, ib};
+            const int idx[2] = {ia.empty() ? -1 : 0, ib.empty() ? -1 : 0};
             for (int t = 0; t < (act->sa == act->sb ? 1 : 2); ++t) {
                 SpeciesState &st = *ctx->species[sp[t]];
                 if (!st.need_update_rho_k) continue;
@@ -1646,14 +1662,32 @@ int pimc_propose(pimc_ctx *ctx, int32_t s, const int32_t *particle, const int32_
         if (particle[c] < 0 || particle[c] >= st.N) return Fail(PIMC_ERR_INVALID, "proposal particle out of range");
         if (b_first[c] < 0 || b_first[c] >= ctx->M) return Fail(PIMC_ERR_INVALID, "proposal bead out of range");
     }
+    // a second proposal on a species that already has one pending ADDS a particle (the cycle of a
+    // permutation move): same bead count, another particle in every clone
+    int slot = 0;
+    if (st.n_prop > 0 && st.n_slots > 0) {
+        if (n_beads != st.n_prop) return Fail(PIMC_ERR_INVALID, "proposals of one species must cover the same number of beads");
+        if (st.n_slots == kMaxPropSlots) return Fail(PIMC_ERR_UNSUPPORTED, "more than 4 proposed particles of one species");
+        for (int sl = 0; sl < st.n_slots; ++sl)
+            for (int c = 0; c < ctx->C; ++c)
+                if (st.h_particle[(size_t)sl * ctx->C + c] == particle[c]) return Fail(PIMC_ERR_INVALID, "particle proposed twice");
+        slot = st.n_slots;
+    }
     const size_t n = (size_t)ctx->C * n_beads * 3;
-    if (st.P.n < n) PIMC_CUDA(st.P.Alloc(n));
-    PIMC_CUDA(cudaMemcpyAsync(st.P.p, newR, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    PIMC_CUDA(cudaMemcpyAsync(st.P_particle.p, particle, ctx->C * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    PIMC_CUDA(cudaMemcpyAsync(st.P_first.p, b_first, ctx->C * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (st.P.n < n * kMaxPropSlots) {
+        if (slot > 0) return Fail(PIMC_ERR_INVALID, "internal: proposal buffer smaller than its slots");
+        PIMC_CUDA(st.P.Alloc(n * kMaxPropSlots));
+    }
+    PIMC_CUDA(cudaMemcpyAsync(st.P.p + slot * n, newR, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    PIMC_CUDA(cudaMemcpyAsync(st.P_particle.p + (size_t)slot * ctx->C, particle, ctx->C * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    PIMC_CUDA(cudaMemcpyAsync(st.P_first.p + (size_t)slot * ctx->C, b_first, ctx->C * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     PIMC_CUDA(cudaStreamSynchronize(ctx->stream));  // host buffers may be reused by the caller
+    st.h_particle.resize((size_t)kMaxPropSlots * ctx->C);
+    std::copy(particle, particle + ctx->C, st.h_particle.begin() + (size_t)slot * ctx->C);
     st.n_prop = n_beads;
+    st.n_slots = slot + 1;
     st.drho_valid = false;
+    st.need_update_rho_k = true;  // the refreshed rho_k (if any) did not include this particle
     return PIMC_OK;
 }
 
@@ -1688,7 +1722,7 @@ int pimc_commit(pimc_ctx *ctx, const int32_t *accept) {
         SpeciesState &st = *sp;
         if (st.n_prop > 0) {
             commit_positions_kernel<<<ctx->C, 64, 0, ctx->stream>>>(ctx->View(), st.N, st.P.p, st.P_particle.p, st.P_first.p, st.n_prop,
-                                                                  ctx->i32_d.p, st.R.p);
+                                                                  std::max(1, st.n_slots), ctx->i32_d.p, st.R.p);
             ctx->launches++;
             PIMC_CUDA(cudaGetLastError());
             if (st.drho_valid) {
@@ -1704,6 +1738,7 @@ int pimc_commit(pimc_ctx *ctx, const int32_t *accept) {
             // (pair_action_class.h:293-299), so StoreRhoK commits the old values there too.
         }
         st.n_prop = 0;
+        st.n_slots = 0;
         st.drho_valid = false;
         st.need_update_rho_k = true;  // every action's Accept/Reject re-arms the flag
     }
@@ -1893,6 +1928,7 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
     }
     PIMC_CUDA(cudaGetLastError());
     st.n_prop = 0;
+    st.n_slots = 0;
     st.drho_valid = false;
     for (auto &sp : ctx->species) sp->need_update_rho_k = true;
     if (n_accept) {
@@ -2030,6 +2066,7 @@ int pimc_displace_sweep(pimc_ctx *ctx, int32_t s, double step_size, int32_t n_at
     }
     PIMC_CUDA(cudaGetLastError());
     st.n_prop = 0;
+    st.n_slots = 0;
     st.drho_valid = false;
     for (auto &sp : ctx->species) sp->need_update_rho_k = true;
     if (n_accept) {

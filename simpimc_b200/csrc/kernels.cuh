@@ -30,12 +30,16 @@ namespace pimc {
 struct SpeciesView {
     const double *R;     // committed positions
     int N;
-    // proposal overlay (NEW mode)
-    const double *P;          // [C][n_prop][3]
-    const int32_t *P_particle;  // [C]
-    const int32_t *P_first;     // [C] first bead (global slice index)
+    // proposal overlay (NEW mode): up to kMaxPropSlots particles of the species per clone (one for
+    // Bisect / DisplaceParticle, the particles of a cycle for permutation moves), all with n_prop beads
+    const double *P;          // [slot][C][n_prop][3]
+    const int32_t *P_particle;  // [slot][C]
+    const int32_t *P_first;     // [slot][C] first bead (global slice index)
     int n_prop;                 // 0 = no pending proposal
+    int n_slots;                // proposals pending (0 with n_prop > 0 is read as 1)
 };
+
+constexpr int kMaxPropSlots = 4;
 
 struct PathView {
     int C;        // clones
@@ -65,15 +69,19 @@ __device__ __forceinline__ size_t PosIndex(const PathView &pv, int N, int c, int
 /// Position of (species view, clone c, particle p, GLOBAL slice bg) in OLD or NEW mode.
 __device__ __forceinline__ void LoadPos(const PathView &pv, const SpeciesView &sv, int c, int p, int bg, int mode, double out[3]) {
     const int bl = WrapSlice(pv, bg);
-    if (mode && sv.n_prop > 0 && sv.P_particle[c] == p) {
-        int off = bl - sv.P_first[c];
-        if (off < 0) off += pv.M;
-        if (off < sv.n_prop) {
-            const double *q = sv.P + ((size_t)c * sv.n_prop + off) * 3;
-            out[0] = q[0];
-            out[1] = q[1];
-            out[2] = q[2];
-            return;
+    if (mode && sv.n_prop > 0) {
+        const int ns = sv.n_slots > 0 ? sv.n_slots : 1;
+        for (int sl = 0; sl < ns; ++sl) {
+            if (sv.P_particle[(size_t)sl * pv.C + c] != p) continue;
+            int off = bl - sv.P_first[(size_t)sl * pv.C + c];
+            if (off < 0) off += pv.M;
+            if (off < sv.n_prop) {
+                const double *q = sv.P + (((size_t)sl * pv.C + c) * sv.n_prop + off) * 3;
+                out[0] = q[0];
+                out[1] = q[1];
+                out[2] = q[2];
+                return;
+            }
         }
     }
     const int b = bl - pv.slice_lo;
@@ -405,31 +413,41 @@ __global__ void rhok_reduce_kernel(const double2 *__restrict__ part, int n_parts
     rho[i] = acc;
 }
 
-/// drho(c, j, k) = rho_bead(new position) - rho_bead(old position) of the proposal's particle
-/// at window slice j (global slice b0[c] + j), zero where the proposal does not cover it.
+/// drho(c, j, k) = sum over the species' pending proposals of rho_bead(new position) -
+/// rho_bead(old position) at window slice j (global slice b0[c] + j); a proposal that does not
+/// cover the slice contributes zero.
 __global__ void __launch_bounds__(256) rhok_delta_kernel(PathView pv, SpeciesView sv, KSpaceView ks, const int32_t *__restrict__ b0,
                                                         int n_window, double2 *__restrict__ drho) {
     extern __shared__ __align__(16) double2 ctab[];  // [2][3][2m+1]
     const int tl = 2 * ks.max_index + 1;
     const int tid = threadIdx.x;
+    const int ns = sv.n_slots > 0 ? sv.n_slots : 1;
     for (int item = blockIdx.x; item < pv.C * n_window; item += gridDim.x) {
         const int c = item / n_window, j = item - c * n_window;
         const int bg = b0[c] + j;
-        const int p = sv.P_particle[c];
-        __syncthreads();
-        if (tid < 6) {
-            const int mode = tid / 3, d = tid - mode * 3;
-            double r[3];
-            LoadPos(pv, sv, c, p, bg, mode, r);
-            PhaseTable(r[d], ks.kbox, ks.max_index, ctab + (size_t)(mode * 3 + d) * tl);
-        }
-        __syncthreads();
-        for (int k = tid; k < ks.n_k; k += blockDim.x) {
-            const int i0 = ks.kidx[3 * k], i1 = ks.kidx[3 * k + 1], i2 = ks.kidx[3 * k + 2];
-            const double2 fo = CMul(CMul(ctab[i0], ctab[tl + i1]), ctab[2 * tl + i2]);
-            const double2 *tn = ctab + 3 * tl;
-            const double2 fn = CMul(CMul(tn[i0], tn[tl + i1]), tn[2 * tl + i2]);
-            drho[((size_t)c * n_window + j) * ks.n_k + k] = make_double2(fn.x - fo.x, fn.y - fo.y);
+        for (int sl = 0; sl < ns; ++sl) {
+            const int p = sv.P_particle[(size_t)sl * pv.C + c];
+            __syncthreads();
+            if (tid < 6) {
+                const int mode = tid / 3, d = tid - mode * 3;
+                double r[3];
+                LoadPos(pv, sv, c, p, bg, mode, r);
+                PhaseTable(r[d], ks.kbox, ks.max_index, ctab + (size_t)(mode * 3 + d) * tl);
+            }
+            __syncthreads();
+            for (int k = tid; k < ks.n_k; k += blockDim.x) {
+                const int i0 = ks.kidx[3 * k], i1 = ks.kidx[3 * k + 1], i2 = ks.kidx[3 * k + 2];
+                const double2 fo = CMul(CMul(ctab[i0], ctab[tl + i1]), ctab[2 * tl + i2]);
+                const double2 *tn = ctab + 3 * tl;
+                const double2 fn = CMul(CMul(tn[i0], tn[tl + i1]), tn[2 * tl + i2]);
+                double2 *dst = drho + ((size_t)c * n_window + j) * ks.n_k + k;
+                double2 v = make_double2(fn.x - fo.x, fn.y - fo.y);
+                if (sl > 0) {  // same thread wrote this element for the previous slot
+                    v.x += dst->x;
+                    v.y += dst->y;
+                }
+                *dst = v;
+            }
         }
     }
 }
@@ -495,9 +513,9 @@ struct PairWindowArgs {
     PathView pv;
     SpeciesView A, B;
     int same;
-    int moved_a, moved_b;       // 1 if the moved list holds a particle of species a / b
-    const int32_t *part_a;      // [C] moved particle of species a (if moved_a)
-    const int32_t *part_b;      // [C]
+    int n_a, n_b;               // listed ("moved") particles of species a / b per clone, <= kMaxPropSlots each
+    const int32_t *part_a;      // [n_a][C]
+    const int32_t *part_b;      // [n_b][C]
     const int32_t *b0;          // [C] window start (global slice)
     int n_links;                // window length (level 0: one link per slice)
     int mode;
@@ -506,7 +524,10 @@ struct PairWindowArgs {
     double *partial;            // [C][n_links]
 };
 
-/// One CTA per (clone, link): all pairs that touch a moved particle, OLD or NEW positions.
+/// One CTA per (clone, link): all pairs that touch a listed particle (PairAction::
+/// GenerateParticlePairs, pair_action_class.h:63-114), OLD or NEW positions.  Same species:
+/// (listed, other) and (listed_i, listed_j), i < j.  Different species: (listed a, every b),
+/// then (every unlisted a, listed b).
 template <int ATYPE>
 __global__ void __launch_bounds__(128) pair_window_kernel(const PairWindowArgs a) {
     __shared__ double red[128 / 32];
@@ -514,15 +535,23 @@ __global__ void __launch_bounds__(128) pair_window_kernel(const PairWindowArgs a
     for (int item = blockIdx.x; item < pv.C * a.n_links; item += gridDim.x) {
         const int c = item / a.n_links, j = item - c * a.n_links;
         const int bg = a.b0[c] + j;
+        int la[kMaxPropSlots], lb[kMaxPropSlots];
+        for (int i = 0; i < a.n_a; ++i) la[i] = a.part_a[(size_t)i * pv.C + c];
+        for (int i = 0; i < a.n_b; ++i) lb[i] = a.part_b[(size_t)i * pv.C + c];
         double acc = 0.;
-        // pairs (moved a, every b partner)
-        if (a.moved_a) {
-            const int m = a.part_a[c];
+        // pairs (listed a, partner of species b)
+        for (int i = 0; i < a.n_a; ++i) {
+            const int m = la[i];
             double m0[3], m1[3];
             LoadPos(pv, a.A, c, m, bg, a.mode, m0);
             LoadPos(pv, a.A, c, m, bg + 1, a.mode, m1);
             for (int q = threadIdx.x; q < a.B.N; q += blockDim.x) {
-                if (a.same && q == m) continue;
+                if (a.same) {
+                    if (q == m) continue;
+                    bool earlier = false;  // (listed_i, listed_j) once: only from the lower list index
+                    for (int i2 = 0; i2 < i; ++i2) earlier = earlier || la[i2] == q;
+                    if (earlier) continue;
+                }
                 double q0[3], q1[3];
                 LoadPos(pv, a.B, c, q, bg, a.mode, q0);
                 LoadPos(pv, a.B, c, q, bg + 1, a.mode, q1);
@@ -533,21 +562,24 @@ __global__ void __launch_bounds__(128) pair_window_kernel(const PairWindowArgs a
                 acc += PairEval<ATYPE, WHICH_U>(a.blob, a.T, r, rp, s);
             }
         }
-        // pairs (every a partner, moved b), skipping the moved a particle counted above
-        if (!a.same && a.moved_b) {
-            const int m = a.part_b[c];
-            const int skip = a.moved_a ? a.part_a[c] : -1;
-            double m0[3], m1[3];
-            LoadPos(pv, a.B, c, m, bg, a.mode, m0);
-            LoadPos(pv, a.B, c, m, bg + 1, a.mode, m1);
-            for (int p = threadIdx.x; p < a.A.N; p += blockDim.x) {
-                if (p == skip) continue;
-                double p0[3], p1[3];
-                LoadPos(pv, a.A, c, p, bg, a.mode, p0);
-                LoadPos(pv, a.A, c, p, bg + 1, a.mode, p1);
-                double r, rp, s;
-                DrDrpDrrp(p0, m0, p1, m1, pv.box, r, rp, s);
-                acc += PairEval<ATYPE, WHICH_U>(a.blob, a.T, r, rp, s);
+        // pairs (unlisted a partner, listed b)
+        if (!a.same) {
+            for (int i = 0; i < a.n_b; ++i) {
+                const int m = lb[i];
+                double m0[3], m1[3];
+                LoadPos(pv, a.B, c, m, bg, a.mode, m0);
+                LoadPos(pv, a.B, c, m, bg + 1, a.mode, m1);
+                for (int p = threadIdx.x; p < a.A.N; p += blockDim.x) {
+                    bool listed = false;
+                    for (int i2 = 0; i2 < a.n_a; ++i2) listed = listed || la[i2] == p;
+                    if (listed) continue;
+                    double p0[3], p1[3];
+                    LoadPos(pv, a.A, c, p, bg, a.mode, p0);
+                    LoadPos(pv, a.A, c, p, bg + 1, a.mode, p1);
+                    double r, rp, s;
+                    DrDrpDrrp(p0, m0, p1, m1, pv.box, r, rp, s);
+                    acc += PairEval<ATYPE, WHICH_U>(a.blob, a.T, r, rp, s);
+                }
             }
         }
         const double tot = BlockSum<128>(acc, red);
@@ -780,18 +812,20 @@ __global__ void gather_beads_kernel(PathView pv, const double *__restrict__ R, i
 /// Move::Accept for the clones whose accept flag is set: committed positions take the
 /// proposal, committed rho_k takes rho_k + drho on the window slices.
 __global__ void commit_positions_kernel(PathView pv, int N, const double *__restrict__ P, const int32_t *__restrict__ P_particle,
-                                        const int32_t *__restrict__ P_first, int n_prop, const int32_t *__restrict__ accept,
+                                        const int32_t *__restrict__ P_first, int n_prop, int n_slots, const int32_t *__restrict__ accept,
                                         double *__restrict__ R) {
     const int c = blockIdx.x;
     if (!accept[c]) return;
-    const int p = P_particle[c];
-    for (int t = threadIdx.x; t < n_prop * 3; t += blockDim.x) {
-        const int j = t / 3, d = t - j * 3;
-        int bg = P_first[c] + j;
-        if (bg >= pv.M) bg -= pv.M;
-        const int b = bg - pv.slice_lo;
-        if (b < 0 || b >= pv.Mstore) continue;
-        R[PosIndex(pv, N, c, p, d, b)] = P[((size_t)c * n_prop + j) * 3 + d];
+    for (int sl = 0; sl < n_slots; ++sl) {
+        const int p = P_particle[(size_t)sl * pv.C + c];
+        for (int t = threadIdx.x; t < n_prop * 3; t += blockDim.x) {
+            const int j = t / 3, d = t - j * 3;
+            int bg = P_first[(size_t)sl * pv.C + c] + j;
+            if (bg >= pv.M) bg -= pv.M;
+            const int b = bg - pv.slice_lo;
+            if (b < 0 || b >= pv.Mstore) continue;
+            R[PosIndex(pv, N, c, p, d, b)] = P[(((size_t)sl * pv.C + c) * n_prop + j) * 3 + d];
+        }
     }
 }
 __global__ void commit_rhok_kernel(PathView pv, int n_k, const double2 *__restrict__ drho, const int32_t *__restrict__ b0, int n_window,

@@ -71,3 +71,36 @@ def test_reference_moves_on_gpu_actions_reproduce_the_reference_run(which):
     assert np.all(np.abs(va - vb) <= 1e-10 * np.maximum(np.abs(va), 1e-300)), (va, vb)
     a.close()
     b.close()
+
+
+def test_adapter_evaluates_the_particle_lists_of_permutation_moves():
+    """GpuPairAction::GetAction with several particles of one species (what PermBisect passes,
+    perm_bisect_iterative_class.h:200-204) and a mixed-species list: the adapter proposes every
+    listed particle's NEW beads and evaluates the (listed, other) + (listed, listed) pairs; same
+    values as the reference's own actions, and the same state after the move is stored."""
+    cfg = S.plasma_config(Ne=6, Np=5, M=8)
+    a, b = _sims(cfg, seed=9)
+    rng = np.random.default_rng(2)
+    M = cfg.n_bead
+    for trial, (plist, b0, nb, accept) in enumerate([([(0, 1), (0, 4)], 2, 4, True), ([(0, 0), (0, 2), (0, 5), (1, 3)], 6, 4, False),
+                                                     ([(1, 0), (1, 4), (0, 3)], 0, 2, True)]):
+        first, n = (b0 + 1) % M, nb - 1
+        for sp, p in plist:
+            cur = a.get_positions(sp, 0)[p, (first + np.arange(n)) % M]
+            new = cur + 0.06 * rng.standard_normal(cur.shape)
+            for sim in (a, b):
+                for i in range(n):      # bead by bead: the window may wrap past n_bead
+                    sim.propose(sp, p, (first + i) % M, new[i:i + 1])
+        for ai in range(len(cfg.actions)):
+            oa, ob = a.get_action(ai, 0, b0, b0 + nb, plist, 0), b.get_action(ai, 0, b0, b0 + nb, plist, 0)
+            na, nb_ = a.get_action(ai, 1, b0, b0 + nb, plist, 0), b.get_action(ai, 1, b0, b0 + nb, plist, 0)
+            assert abs(oa - ob) <= 1e-10 * abs(oa) + 1e-300 and abs(na - nb_) <= 1e-10 * abs(na) + 1e-300, (trial, ai, oa, ob, na, nb_)
+            assert abs((na - oa) - (nb_ - ob)) <= 1e-10 * max(abs(na - oa), 1e-4 * (abs(na) + abs(oa)))
+        for sp, p in plist:
+            for sim in (a, b):
+                sim.finish_move(sp, p, b0, b0 + nb, accept)
+        for ai in range(len(cfg.actions)):
+            ea, eb = a.dbeta(ai), b.dbeta(ai)
+            assert abs(ea - eb) <= 1e-10 * abs(ea), (trial, ai, ea, eb)
+    a.close()
+    b.close()

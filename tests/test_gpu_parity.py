@@ -433,3 +433,68 @@ def test_tiled_gofr_bins_match_oracle_and_general_kernel(kind, n_r):
     path.close()
     for o in oracles:
         o.close()
+
+
+@pytest.mark.parametrize("name", ["ilkka_lr_n7", "ilkka_nolr_n8", "bare_lr_n7", "david_n7", "plasma"])
+def test_get_action_with_several_listed_particles(name):
+    """Action::GetAction with the particle lists permutation moves pass
+    (perm_bisect_iterative_class.h:200-204: the 2-4 particles of a cycle, same species) and lists
+    that touch both species of an action: GenerateParticlePairs' (listed, other) + (listed,
+    listed) pairs, several pending proposals per species, rho_k refreshed for all of them,
+    commit / rollback.  Checked against the oracle: OLD and NEW actions, the Metropolis
+    difference, positions and rho_k after the commit."""
+    from simpimc_b200 import host
+    cfg = CONFIGS[name]()
+    C_ = 3
+    path, oracles, _ = make_pair(cfg, C_, seed=21)
+    M = cfg.n_bead
+    rng = np.random.default_rng(17)
+    ns = len(cfg.species)
+    for trial in range(6):
+        nb = [4, 2, 4, M, 4, 2][trial]
+        b0 = rng.integers(0, M, size=C_) if nb < M else np.zeros(C_, dtype=np.int64)
+        first, n_beads = ((b0 + 1) % M, nb - 1) if nb < M else (b0, M)
+        # the list: 2-3 particles of species 0, on odd trials also one of the other species
+        k0 = 2 + trial % 2
+        plist = []
+        chosen = np.stack([rng.permutation(cfg.species[0].n_part)[:k0] for _ in range(C_)])   # [clone][k0], distinct per clone
+        for i in range(k0):
+            plist.append((0, chosen[:, i].astype(np.int32)))
+        if ns > 1 and trial % 2 == 1:
+            plist.append((1, rng.integers(0, cfg.species[1].n_part, size=C_).astype(np.int32)))
+        news = []
+        for sp, parts in plist:
+            cur = path.GetBeads(sp, parts, first, n_beads)
+            new = cur + 0.07 * rng.standard_normal(cur.shape)
+            path.Propose(sp, parts, first, new)
+            news.append(new)
+            for c, o in enumerate(oracles):
+                o.propose(sp, int(parts[c]), int(first[c]), new[c])
+        accept = rng.integers(0, 2, size=C_)
+        for ai, act in enumerate(path.actions):
+            path.SetMode(host.OLD_MODE)
+            old = act.GetAction(b0, b0 + nb, plist, 0)
+            path.SetMode(host.NEW_MODE)
+            new = act.GetAction(b0, b0 + nb, plist, 0)
+            for c, o in enumerate(oracles):
+                pl = [(sp, int(parts[c])) for sp, parts in plist]
+                ro = o.get_action(ai, 0, int(b0[c]), int(b0[c]) + nb, pl, 0)
+                rn = o.get_action(ai, 1, int(b0[c]), int(b0[c]) + nb, pl, 0)
+                assert rel_ok(old[c], ro) and rel_ok(new[c], rn), (name, trial, ai, c, old[c], ro, new[c], rn)
+                assert abs((new[c] - old[c]) - (rn - ro)) <= RTOL * max(abs(rn - ro), 1e-4 * (abs(rn) + abs(ro))), (name, trial, ai, c)
+        path.Commit(accept)
+        for c, o in enumerate(oracles):
+            for sp, parts in plist:
+                o.finish_move(sp, int(parts[c]), int(b0[c]), int(b0[c]) + nb, bool(accept[c]))
+        for sp in range(ns):
+            got = path.GetPositions(sp)
+            for c, o in enumerate(oracles):
+                assert np.array_equal(got[c], o.get_positions(sp, 0)), (name, trial, "positions after commit", sp, c)
+                if path._n_k():
+                    assert np.max(np.abs(path.GetRhoK(sp, c, host.OLD_MODE) - o.rhok(sp, 0))) <= 1e-11 * cfg.species[sp].n_part
+    # five listed particles of one species: refused loudly
+    with pytest.raises(RuntimeError):
+        path.actions[0].GetAction(0, 2, [(0, i) for i in range(5)], 0)
+    path.close()
+    for o in oracles:
+        o.close()
