@@ -253,6 +253,15 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t species, int32_t n_level, int32_t n
 int pimc_displace_sweep(pimc_ctx *ctx, int32_t species, double step_size, int32_t n_attempts, uint64_t seed, uint64_t attempt0,
                         int64_t *n_accept);
 
+/* Permutation table of the permuting bisection moves for the window [b0, b0 + n_bisect_beads] of
+ * every clone: t[c][i][j] = exp(e) if e > log(epsilon) else 0 with
+ *   relative == 0: e = -|Dr(r_i(b0), r_j(b1))|^2 / (4 lambda tau n)     PermBisectIterative::UpdatePermTable
+ *                                                                        (perm_bisect_iterative_class.h:10-30)
+ *   relative != 0: e = (-|Dr_ij|^2 + |Dr_ii|^2) / (4 lambda tau n)      PermBisectTable (perm_bisect_table_class.h:36-50)
+ * on the unpermuted path.  Cycle selection and the relabelling of an accepted permutation stay with
+ * the caller.  t is host memory, [n_clones][N][N]. */
+int pimc_perm_table(pimc_ctx *ctx, int32_t species, const int32_t *b0, int32_t n_bisect_beads, double epsilon, int32_t relative, double *t);
+
 /* ---- estimators ------------------------------------------------------------------------ */
 /* PairCorrelation::Accumulate (pair_correlation_class.h:15-28): y[c][i] += cofactor[c] for
  * every pair and slice, bin i = (uint32)nearbyint((|dr|-r_min)*d_ir - 0.5), i < n_r kept.

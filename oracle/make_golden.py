@@ -179,12 +179,26 @@ def make_one(name):
     return out
 
 
+def make_perm_table():
+    """PermBisectIterative::UpdatePermTable of the reference on seeded paths -> tests/golden/perm_table_n7.npz."""
+    cfg = S.ueg_config(N=7, M=16, with_kinetic=True)
+    cfg.moves = [{"name": "PermE", "type": "PermBisectIterative", "species": "e", "n_level": 2, "n_images": 0}]
+    sim = refsim.RefSim(cfg, seed=SEED)
+    sim.set_positions(0, S.synthetic_paths(cfg, 0, 0, SEED))
+    b0s = np.array([0, 3, 11, 14, 15], dtype=np.int64)      # the last three windows wrap past n_bead
+    out = {"seed": np.int64(SEED), "n_bisect_beads": np.int64(4), "b0": b0s, "t": np.stack([sim.perm_table(0, int(b), 7) for b in b0s])}
+    sim.close()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "perm_table_n7.npz"), **out)
+    return out
+
+
 def main():
     if not refsim.available():
         raise SystemExit("oracle/_ref/libsimpimc_ref.so missing: run `make -C oracle ref` where /root/reference exists")
     for name in sorted(CONFIGS):
         out = make_one(name)
         print("%-16s dbeta %s" % (name, out["dbeta"]))
+    print("perm_table_n7    max t %.6g" % make_perm_table()["t"].max())
 
 
 if __name__ == "__main__":

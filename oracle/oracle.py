@@ -50,6 +50,7 @@ def lib():
         L.orc_potential.argtypes = [vp, i32]
         L.orc_get_action.restype = dbl
         L.orc_get_action.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, i32]
+        L.orc_perm_table.argtypes = [vp, i32, i32, i32, C.c_double, i32, vp]
         L.orc_action_gradient.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, i32, vp]
         L.orc_action_laplacian.restype = dbl
         L.orc_action_laplacian.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, i32]
@@ -167,6 +168,12 @@ class Oracle:
         sp = np.array([p[0] for p in particles], dtype=np.int32)
         pi = np.array([p[1] for p in particles], dtype=np.int32)
         return self.L.orc_action_laplacian(self.h, self.actions[a], mode, b0, b1, len(particles), _p(sp), _p(pi), level)
+
+    def perm_table(self, sp, bead0, n_bisect_beads, epsilon=1e-100, relative=False):
+        N = self.cfg.species[sp].n_part
+        t = np.zeros((N, N))
+        self.L.orc_perm_table(self.h, sp, bead0, n_bisect_beads, C.c_double(epsilon), 1 if relative else 0, _p(t))
+        return t
 
     def calc_pair(self, a, which, r, rp, s, level=0):
         r, rp, s = _d(r), _d(rp), _d(s)

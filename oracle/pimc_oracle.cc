@@ -991,6 +991,28 @@ double orc_action_laplacian(void *h, int a, int mode, int b0, int b1, int n, con
     w->mode = mode;
     return GetActionLaplacian(*w->actions[a], b0, b1, n, sp, pi, level);
 }
+// PermBisectIterative::UpdatePermTable (perm_bisect_iterative_class.h:10-30); relative != 0: the
+// table of PermBisectTable (perm_bisect_table_class.h:36-50).  Unpermuted path.
+void orc_perm_table(void *h, int sp, int bead0, int n_bisect_beads, double epsilon, int relative, double *t) {
+    World *w = (World *)h;
+    Species &s = w->species[sp];
+    const double i_4_lambda_tau = 1. / (4. * s.lambda * w->tau);           // bisect_class.h:147
+    const double i_4_lambda_tau_n_bisect_beads = i_4_lambda_tau / n_bisect_beads;
+    const double log_epsilon = std::log(epsilon);
+    int b1 = bead0 + n_bisect_beads;
+    while (b1 >= s.n_bead) b1 -= s.n_bead;
+    for (int i = 0; i < s.n_part; i++) {
+        double dr_ii[3];
+        w->Dr(s.R(w->mode, i, bead0), s.R(w->mode, i, b1), dr_ii);
+        for (int j = 0; j < s.n_part; j++) {
+            double dr_ij[3];
+            w->Dr(s.R(w->mode, i, bead0), s.R(w->mode, j, b1), dr_ij);
+            double exponent = relative ? (-Dot(dr_ij, dr_ij, w->n_d) + Dot(dr_ii, dr_ii, w->n_d)) * i_4_lambda_tau_n_bisect_beads
+                                       : (-Dot(dr_ij, dr_ij, w->n_d)) * i_4_lambda_tau_n_bisect_beads;
+            t[(size_t)i * s.n_part + j] = exponent > log_epsilon ? std::exp(exponent) : 0.;
+        }
+    }
+}
 void orc_calc_pair(void *h, int a, int which, int n, const double *r, const double *rp, const double *s, int level, double *out) {
     World *w = (World *)h;
     Action &act = *w->actions[a];

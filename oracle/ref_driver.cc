@@ -49,6 +49,7 @@ using namespace scaffold::rand;
 #include <src/actions/single_action/kinetic_class.h>
 #include <src/events/moves/single_species_move/bisect/bisect_class.h>
 #include <src/events/moves/single_species_move/displace_particle_class.h>
+#include <src/events/moves/single_species_move/bisect/perm_bisect/perm_bisect_iterative_class.h>
 #include <src/events/observables/energy_class.h>
 #include <src/events/observables/pair_correlation_class.h>
 #include <src/events/observables/structure_factor_class.h>
@@ -91,6 +92,7 @@ std::shared_ptr<Move> MakeMove(Input &in, IO &out, Path &path, RNG &rng, std::ve
     std::string type = in.GetAttribute<std::string>("type");
     if (type == "Bisect") return std::make_shared<Bisect>(path, rng, actions, in, out);
     if (type == "DisplaceParticle") return std::make_shared<DisplaceParticle>(path, rng, actions, in, out);
+    if (type == "PermBisectIterative") return std::make_shared<PermBisectIterative>(path, rng, actions, in, out);
     std::cerr << "ref_driver: move type " << type << " is outside the hot path" << std::endl;
     std::abort();
 }
@@ -370,6 +372,20 @@ int ref_energy_sums(void *h, int o, double *energies, double *potentials) {
 }
 
 // ---- moves (sampled runs; the reference's own RNG stream) ----------------------------
+/// PermBisectIterative::UpdatePermTable (perm_bisect_iterative_class.h:10-30) for the window that starts at bead0.
+int ref_perm_table(void *h, int m, int bead0, double *t_out) {
+    RefSim *s = (RefSim *)h;
+    PermBisectIterative *pb = dynamic_cast<PermBisectIterative *>(s->moves[m].get());
+    if (!pb) return -1;
+    s->path->SetMode(NEW_MODE);
+    pb->bead0 = bead0;
+    pb->UpdatePermTable();
+    const uint32_t N = pb->species->GetNPart();
+    for (uint32_t i = 0; i < N; ++i)
+        for (uint32_t j = 0; j < N; ++j) t_out[i * N + j] = pb->t(i, j);
+    return (int)N;
+}
+
 int ref_n_moves(void *h) { return ((RefSim *)h)->moves.size(); }
 void ref_move_do(void *h, int m, int n_times) {
     RefSim *s = (RefSim *)h;

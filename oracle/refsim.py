@@ -62,6 +62,9 @@ def _load(fast=False, dropin=False):
     lib.ref_get_action.restype = C.c_double
     lib.ref_get_action.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, C.c_int]
     lib.ref_action_accept.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    if hasattr(lib, "ref_perm_table"):
+        lib.ref_perm_table.restype = C.c_int
+        lib.ref_perm_table.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp]
     if hasattr(lib, "ref_action_gradient"):
         lib.ref_action_gradient.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, C.c_int, _dp]
         lib.ref_action_laplacian.restype = C.c_double
@@ -133,9 +136,9 @@ def system_xml(cfg, table_files, workdir):
     lines.append("  </Actions>")
     lines.append("  <Moves>")
     for m in cfg.moves:
-        if m["type"] == "Bisect":
-            lines.append('    <Move name="%s" type="Bisect" species="%s" n_level="%d" n_images="%d" />'
-                         % (m["name"], m["species"], m["n_level"], m.get("n_images", 0)))
+        if m["type"] in ("Bisect", "PermBisectIterative"):
+            lines.append('    <Move name="%s" type="%s" species="%s" n_level="%d" n_images="%d" />'
+                         % (m["name"], m["type"], m["species"], m["n_level"], m.get("n_images", 0)))
         else:
             lines.append('    <Move name="%s" type="DisplaceParticle" species="%s" step_size="%.17g" />'
                          % (m["name"], m["species"], m["step_size"]))
@@ -291,6 +294,13 @@ class RefSim:
         v = np.zeros(n_a)
         self.lib.ref_energy_sums(self.h, o, e, v)
         return e, v
+
+    def perm_table(self, m, bead0, n_part):
+        """PermBisectIterative::UpdatePermTable of move m for the window starting at bead0."""
+        t = np.zeros((n_part, n_part))
+        n = self.lib.ref_perm_table(self.h, m, bead0, t)
+        assert n == n_part, n
+        return t
 
     def move_do(self, m, n_times=1):
         self.lib.ref_move_do(self.h, m, n_times)

@@ -150,7 +150,7 @@ EXPORTS = [
     "pimc_action_get", "pimc_action_gradient", "pimc_action_laplacian", "pimc_action_total", "pimc_action_total_device", "pimc_action_accept", "pimc_action_reject",
     "pimc_action_calc_pair", "pimc_propose", "pimc_beads_download", "pimc_commit", "pimc_est_gofr", "pimc_est_gofr_counts", "pimc_est_sofk",
     "pimc_ctx_launch_count", "pimc_fp64_peak", "pimc_ctx_set_timing", "pimc_ctx_kernel_time",
-    "pimc_action_calc_pair_fast", "pimc_debug_fast_sqrt", "pimc_ctx_force_general", "pimc_bisect_sweep", "pimc_displace_sweep", "pimc_halo_pack", "pimc_halo_unpack", "pimc_rotate_pack", "pimc_rotate_apply",
+    "pimc_action_calc_pair_fast", "pimc_debug_fast_sqrt", "pimc_ctx_force_general", "pimc_bisect_sweep", "pimc_displace_sweep", "pimc_perm_table", "pimc_halo_pack", "pimc_halo_unpack", "pimc_rotate_pack", "pimc_rotate_apply",
 ]
 
 _lib = None
@@ -216,6 +216,7 @@ def lib():
     L.pimc_rotate_apply.argtypes = [vp, i32, i32, vp]
     L.pimc_bisect_sweep.argtypes = [vp, i32, i32, i32, C.c_uint64, C.c_uint64, i32, vp]
     L.pimc_displace_sweep.argtypes = [vp, i32, C.c_double, i32, C.c_uint64, C.c_uint64, vp]
+    L.pimc_perm_table.argtypes = [vp, i32, vp, i32, C.c_double, i32, vp]
     _lib = L
     return L
 

@@ -1940,6 +1940,30 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
     return PIMC_OK;
 }
 
+int pimc_perm_table(pimc_ctx *ctx, int32_t s, const int32_t *b0, int32_t n_bisect_beads, double epsilon, int32_t relative, double *t) {
+    if (!ctx || !b0 || !t) return Fail(PIMC_ERR_INVALID, "null argument");
+    if (s < 0 || s >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
+    if (ctx->sharded) return Fail(PIMC_ERR_UNSUPPORTED, "permutation table on a slice-sharded context");
+    if (n_bisect_beads < 1 || n_bisect_beads > ctx->M) return Fail(PIMC_ERR_INVALID, "n_bisect_beads must be in 1..n_bead");
+    if (!(epsilon > 0.)) return Fail(PIMC_ERR_INVALID, "epsilon must be positive");
+    SpeciesState &st = *ctx->species[s];
+    if (!(st.lambda > 0.)) return Fail(PIMC_ERR_INVALID, "permutation table of a species with lambda = 0");
+    for (int c = 0; c < ctx->C; ++c)
+        if (b0[c] < 0 || b0[c] >= ctx->M) return Fail(PIMC_ERR_INVALID, "window start out of range");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = EnsureI32(ctx, ctx->i32_c, b0, ctx->C)) != PIMC_OK) return rc;
+    const size_t n = (size_t)ctx->C * st.N * st.N;
+    if (ctx->stage.n < n) PIMC_CUDA(ctx->stage.Alloc(n));
+    // Bisect: i_4_lambda_tau = 1 / (4 lambda tau), divided by n_bisect_beads (bisect_class.h:147-150)
+    const double i_4_lambda_tau_n = (1. / (4. * st.lambda * ctx->tau)) / n_bisect_beads;
+    perm_table_kernel<<<ctx->C * st.N, 128, 0, ctx->stream>>>(ctx->View(), st.R.p, st.N, ctx->i32_c.p, n_bisect_beads, i_4_lambda_tau_n, std::log(epsilon),
+                                                              relative ? 1 : 0, ctx->stage.p);
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    return ToHost(ctx, ctx->stage.p, t, n);
+}
+
 int pimc_displace_sweep(pimc_ctx *ctx, int32_t s, double step_size, int32_t n_attempts, uint64_t seed, uint64_t attempt0, int64_t *n_accept) {
     if (!ctx) return Fail(PIMC_ERR_INVALID, "null context");
     if (s < 0 || s >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");

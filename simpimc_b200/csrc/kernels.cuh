@@ -773,6 +773,39 @@ __global__ void sofk_kernel(PathView pv, int n_k, const double2 *__restrict__ rh
     sk[(size_t)c * n_k + k] = acc;
 }
 
+// --------------------------------------------------------------------- permutation table
+/// PermBisectIterative::UpdatePermTable (perm_bisect_iterative_class.h:10-30) / the table of
+/// PermBisectTable (perm_bisect_table_class.h:36-50): t(i, j) = exp(e) if e > log_epsilon else 0,
+/// e = -|Dr(r_i(b0), r_j(b1))|^2 / (4 lambda tau n) [+ |Dr(r_i(b0), r_i(b1))|^2 / (4 lambda tau n) for the
+/// table variant], b1 = b0 + n_bisect_beads.  One CTA per (clone, i), threads over j; the path
+/// is taken unpermuted (the bead n slices ahead of particle j is particle j's).
+__global__ void __launch_bounds__(128) perm_table_kernel(PathView pv, const double *__restrict__ R, int N, const int32_t *__restrict__ b0,
+                                                        int n_bisect_beads, double i_4_lambda_tau_n, double log_epsilon, int relative,
+                                                        double *__restrict__ t) {
+    const int c = blockIdx.x / N, i = blockIdx.x - c * N;
+    const int bs = WrapSlice(pv, b0[c]) - pv.slice_lo;
+    int be = b0[c] + n_bisect_beads;
+    while (be >= pv.M) be -= pv.M;
+    be -= pv.slice_lo;
+    double ri[3], d_ii = 0.;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        ri[d] = R[PosIndex(pv, N, c, i, d, bs)];
+        const double x = MinImage(ri[d] - R[PosIndex(pv, N, c, i, d, be)], pv.box);
+        d_ii += x * x;
+    }
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        double d_ij = 0.;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const double x = MinImage(ri[d] - R[PosIndex(pv, N, c, j, d, be)], pv.box);
+            d_ij += x * x;
+        }
+        const double e = relative ? (-d_ij + d_ii) * i_4_lambda_tau_n : (-d_ij) * i_4_lambda_tau_n;
+        t[((size_t)c * N + i) * N + j] = e > log_epsilon ? exp(e) : 0.;
+    }
+}
+
 // ------------------------------------------------------------------------- data movement
 /// host order R[clone][particle][bead][dim] -> device order R[clone][particle][dim][slice].
 __global__ void positions_in_kernel(const double *__restrict__ src, int n_clones, int N, int Mstore, int Ms, double *__restrict__ dst) {

@@ -158,6 +158,14 @@ class Path:
         capi.check(self.L.pimc_displace_sweep(self.h, species, float(step_size), n_attempts, seed, attempt0, _vp(n_accept)))
         return n_accept
 
+    def PermTable(self, species, b0, n_bisect_beads, epsilon=1e-100, relative=False):
+        """PermBisectIterative::UpdatePermTable (relative: the PermBisectTable variant): t[clone][i][j]."""
+        b0 = np.ascontiguousarray(np.broadcast_to(b0, (self.n_clones,)), dtype=np.int32)
+        N = self.cfg.species[species].n_part
+        t = np.zeros((self.n_clones, N, N))
+        capi.check(self.L.pimc_perm_table(self.h, species, _vp(b0), n_bisect_beads, float(epsilon), 1 if relative else 0, _vp(t)))
+        return t
+
     def LaunchCount(self):
         return int(self.L.pimc_ctx_launch_count(self.h))
 

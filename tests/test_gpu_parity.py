@@ -498,3 +498,23 @@ def test_get_action_with_several_listed_particles(name):
     path.close()
     for o in oracles:
         o.close()
+
+
+@pytest.mark.parametrize("relative", [False, True])
+def test_perm_table_matches_oracle(relative):
+    """pimc_perm_table: PermBisectIterative::UpdatePermTable / the PermBisectTable variant for every
+    clone at once; windows that wrap past n_bead; the epsilon cut is applied (exact zeros)."""
+    cfg = S.ueg_config(N=33, M=16)
+    C_ = 3
+    path, oracles, _ = make_pair(cfg, C_, seed=4)
+    b0 = np.array([2, 13, 15], dtype=np.int32)
+    for eps in (1e-100, 1e-3):
+        t = path.PermTable(0, b0, 4, epsilon=eps, relative=relative)
+        for c, o in enumerate(oracles):
+            ref = o.perm_table(0, int(b0[c]), 4, epsilon=eps, relative=relative)
+            assert np.array_equal(t[c] == 0.0, ref == 0.0) or np.max(np.abs(t[c] - ref)) <= 1e-12   # a value within rounding of the cut may fall on either side
+            assert np.max(np.abs(t[c] - ref)) <= 1e-12 * max(1.0, np.max(ref))
+    assert np.any(path.PermTable(0, b0, 4, epsilon=1e-3) == 0.0)
+    path.close()
+    for o in oracles:
+        o.close()

@@ -8,6 +8,8 @@ tests check against -- is itself pinned here:
   KSpace::Setup (182 vectors / 17 shells for every shipped k_cut = 14/(L/2), first and last
   triples) and the Madelung constant of the StandardEwald breakup (scripts/pagen/Ewald.py).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -129,3 +131,20 @@ def test_spline_definition_matches_scipy_natural_cubic_spline(oracle_mod):
     along_y = CubicSpline(gy, F, axis=1, bc_type="natural")          # for every x row: natural spline in y
     ref2 = np.array([CubicSpline(gx, along_y(yy), bc_type="natural")(xx) for xx, yy in zip(xs, ys)])
     assert np.max(np.abs(got2 - ref2)) <= 1e-12 * np.max(np.abs(F))
+
+
+def test_perm_table_matches_reference_golden(oracle_mod):
+    """PermBisectIterative::UpdatePermTable (perm_bisect_iterative_class.h:10-30): the restatement
+    against the reference's own table (tests/golden/perm_table_n7.npz, oracle/make_golden.py)."""
+    from simpimc_b200 import system as S
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "perm_table_n7.npz"))
+    cfg = S.ueg_config(N=7, M=16)
+    o = oracle_mod.Oracle(cfg)
+    o.set_positions(0, S.synthetic_paths(cfg, 0, 0, int(g["seed"])))
+    for b0, t_ref in zip(g["b0"], g["t"]):
+        assert np.array_equal(o.perm_table(0, int(b0), int(g["n_bisect_beads"])), t_ref)
+    # the PermBisectTable variant differs by the row factor exp(+|dr_ii|^2 / (4 lambda tau n))
+    t_rel = o.perm_table(0, 3, 4, relative=True)
+    t_abs = o.perm_table(0, 3, 4)
+    assert np.allclose(np.diag(t_rel), 1.0) and np.allclose(t_rel * np.diag(t_abs)[:, None], t_abs, rtol=1e-12)
+    o.close()
