@@ -386,6 +386,19 @@ int ref_perm_table(void *h, int m, int bead0, double *t_out) {
     return (int)N;
 }
 
+/// PermBisect's per-cycle-length counters (perm_bisect_class.h:26-27): attempts / accepts of 1-, 2-, ... particle cycles.
+int ref_perm_counts(void *h, int m, int n_max, uint32_t *attempt, uint32_t *accept) {
+    RefSim *s = (RefSim *)h;
+    PermBisect *pb = dynamic_cast<PermBisect *>(s->moves[m].get());
+    if (!pb) return -1;
+    const int n = std::min<int>(n_max, pb->perm_attempt.size());
+    for (int i = 0; i < n; ++i) {
+        attempt[i] = pb->perm_attempt(i);
+        accept[i] = pb->perm_accept(i);
+    }
+    return n;
+}
+
 int ref_n_moves(void *h) { return ((RefSim *)h)->moves.size(); }
 void ref_move_do(void *h, int m, int n_times) {
     RefSim *s = (RefSim *)h;

@@ -62,6 +62,9 @@ def _load(fast=False, dropin=False):
     lib.ref_get_action.restype = C.c_double
     lib.ref_get_action.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, C.c_int]
     lib.ref_action_accept.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    if hasattr(lib, "ref_perm_counts"):
+        lib.ref_perm_counts.restype = C.c_int
+        lib.ref_perm_counts.argtypes = [C.c_void_p, C.c_int, C.c_int, _up, _up]
     if hasattr(lib, "ref_perm_table"):
         lib.ref_perm_table.restype = C.c_int
         lib.ref_perm_table.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp]
@@ -301,6 +304,14 @@ class RefSim:
         n = self.lib.ref_perm_table(self.h, m, bead0, t)
         assert n == n_part, n
         return t
+
+    def perm_counts(self, m, n_max=8):
+        """(attempts, accepts) per cycle length 1, 2, ... of a PermBisect move."""
+        att = np.zeros(n_max, dtype=np.uint32)
+        acc = np.zeros(n_max, dtype=np.uint32)
+        n = self.lib.ref_perm_counts(self.h, m, n_max, att, acc)
+        assert n >= 0
+        return att[:n], acc[:n]
 
     def move_do(self, m, n_times=1):
         self.lib.ref_move_do(self.h, m, n_times)

@@ -26,9 +26,16 @@ def _sims(cfg, seed):
     return a, b
 
 
-@pytest.mark.parametrize("which", ["ueg", "plasma"])
+@pytest.mark.parametrize("which", ["ueg", "plasma", "perm"])
 def test_reference_moves_on_gpu_actions_reproduce_the_reference_run(which):
-    if which == "ueg":
+    if which == "perm":
+        # the reference's own permuting bisection (PermBisectIterative: cycle selection from the
+        # permutation table, relabelling of accepted permutations) on top of the CUDA action:
+        # GetAction receives the 1-4 particles of the cycle
+        cfg = S.ueg_config(N=7, M=16, with_kinetic=True)
+        cfg.moves = [{"name": "PermE", "type": "PermBisectIterative", "species": "e", "n_level": 2, "n_images": 0},
+                     {"name": "BisectE", "type": "Bisect", "species": "e", "n_level": 3}]
+    elif which == "ueg":
         cfg = S.ueg_config(N=14, M=16, with_kinetic=True)
         cfg.moves = [{"name": "BisectE", "type": "Bisect", "species": "e", "n_level": 3},
                      {"name": "DisplaceE", "type": "DisplaceParticle", "species": "e", "step_size": 0.3}]
@@ -52,6 +59,10 @@ def test_reference_moves_on_gpu_actions_reproduce_the_reference_run(which):
         assert a.move_counts(m) == b.move_counts(m), "accept/reject history differs"
         att, acc = a.move_counts(m)
         assert att == 150 and 0 < acc
+    if which == "perm":
+        (att_a, acc_a), (att_b, acc_b) = a.perm_counts(0), b.perm_counts(0)
+        assert np.array_equal(att_a, att_b) and np.array_equal(acc_a, acc_b)
+        assert acc_a[1:].sum() >= 1, "no real permutation (cycle of >= 2 particles) was accepted"
     for sp in range(len(cfg.species)):
         assert np.array_equal(a.get_positions(sp, 0), b.get_positions(sp, 0)), "trajectories diverged"
     # the adapter's GetActionGradient / GetActionLaplacian after the run (pair actions only: Kinetic is the reference's own)
