@@ -373,6 +373,7 @@ def run_ours(args):
     roofline = {"bound": "fp64", "kernel": "pair_full_fast_kernel (IlkkaPairAction::CalcdUdBeta over all pairs x slices)", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
                 "peak_source": "DFMA micro-benchmark (pimc_fp64_peak) measured in this run; MEASURED_PEAKS.json holds no FP64 figure",
+                "bound_note": "north_star names the FP64-or-HBM roofline: 273 flop per 0.19 algorithmic bytes puts this kernel on the FP64 side (DRAM at 0.2 % of peak in profiles/); no tensor-core work on this path",
                 "algorithmic_flop_per_launch": evals_step * FLOP_PER_EVAL,
                 "algorithmic_bytes_per_launch": C * N_SLICE * N_PART * 24,
                 "kernel_ms": {"K1_pair_full": k1_ms / max(1, k1_n), "K2_rhok_build": k2_ms / max(1, k2_n), "K3_ksum": k3_ms / max(1, k3_n)},
