@@ -1917,7 +1917,9 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
             const int tl = 2 * ctx->max_index + 1;
             {
                 ScopedKernelTimer t(ctx, PIMC_KERNEL_KSUM);
-                lr_window_kernel<<<C, 256, (size_t)6 * tl * sizeof(double2), ctx->stream>>>(l);
+                const size_t lr_smem = (size_t)kLrChunk * 6 * tl * sizeof(double2);
+                if (lr_smem > 48 * 1024) PIMC_CUDA(cudaFuncSetAttribute(lr_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lr_smem));
+                lr_window_kernel<<<C, 256, lr_smem, ctx->stream>>>(l);
             }
             ctx->launches++;
         }
@@ -2079,7 +2081,9 @@ int pimc_displace_sweep(pimc_ctx *ctx, int32_t s, double step_size, int32_t n_at
             const int tl = 2 * ctx->max_index + 1;
             {
                 ScopedKernelTimer t(ctx, PIMC_KERNEL_KSUM);
-                lr_window_kernel<<<C, 256, (size_t)6 * tl * sizeof(double2), ctx->stream>>>(l);
+                const size_t lr_smem = (size_t)kLrChunk * 6 * tl * sizeof(double2);
+                if (lr_smem > 48 * 1024) PIMC_CUDA(cudaFuncSetAttribute(lr_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lr_smem));
+                lr_window_kernel<<<C, 256, lr_smem, ctx->stream>>>(l);
             }
             ctx->launches++;
         }

@@ -306,79 +306,89 @@ __global__ void bisect_decide_kernel(int C, const int32_t *__restrict__ alive, c
 // ---------------------------------------------------------------- staged window kernel
 constexpr int kWinFastThreads = 1024;
 
+constexpr int kWinTeams = 8;                                  // independent sub-CTA teams (named barriers)
+constexpr int kWinTeamThreads = kWinFastThreads / kWinTeams;
+constexpr int kWinTeamWarps = kWinTeamThreads / 32;
+
 /// Same sums as pair_window_both_kernel<ILKKA, fast> with the fast tables staged in shared
-/// memory: persistent CTAs (one per SM) walk the clones; inside a clone, n_links consecutive
-/// lanes own the links of one (moved particle, partner) pair -- the quarter-warp granularity at
-/// which LDS.128 is served -- and the 1024 / n_links pair slots walk the partner particles.
+/// memory once per CTA: persistent CTAs (one per SM) split into kWinTeams teams of 4 warps, each
+/// walking its own clones (a whole CTA per clone leaves one iteration per warp between barriers
+/// at N = 128).  Inside a clone, n_links consecutive lanes own the links of one (moved particle,
+/// partner) pair and groups of 32 / n_links partners per warp keep every warp converged: OLD and
+/// NEW come from one set of partner loads and the long-range spline is evaluated twice per link
+/// pair instead of four times (FastIlkkaEvalWindow).
 __global__ void __launch_bounds__(kWinFastThreads, 1) pair_window_fast_kernel(const WindowBothArgs a) {
     extern __shared__ __align__(16) unsigned char wsm[];
-    __shared__ double pold[kMaxBisectBeads + 1][3], pnew[kMaxBisectBeads + 1][3];
-    __shared__ double red[2][kWinFastThreads / 32];
-    const int tid = threadIdx.x;
+    __shared__ double pold[kWinTeams][kMaxBisectBeads + 1][3], pnew[kWinTeams][kMaxBisectBeads + 1][3];
+    __shared__ double red[kWinTeams][2][kWinTeamWarps];
     {
         const int4 *src = reinterpret_cast<const int4 *>(a.fast_tables);
         int4 *dst = reinterpret_cast<int4 *>(wsm);
-        for (int i = tid; i < a.FT.n_bytes / 16; i += kWinFastThreads) dst[i] = src[i];
+        for (int i = threadIdx.x; i < a.FT.n_bytes / 16; i += kWinFastThreads) dst[i] = src[i];
     }
+    __syncthreads();  // the only CTA-wide barrier
     const SharedTab wtab(wsm);
     const PathView &pv = a.pv;
     const int nl = a.n_links;
-    const int j = tid & (nl - 1), slot = tid / nl, n_slots = kWinFastThreads / nl;
-    for (int c = blockIdx.x; c < pv.C; c += gridDim.x) {
-        __syncthreads();  // tables staged / previous clone's pold, pnew, red consumed
+    const int team = threadIdx.x / kWinTeamThreads, tid = threadIdx.x - team * kWinTeamThreads;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int j = lane & (nl - 1), sub = lane / nl, per_warp = 32 / nl;
+    const int n_groups = (a.N_partner + per_warp - 1) / per_warp;
+    auto team_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(kWinTeamThreads) : "memory"); };
+    for (int c = (int)blockIdx.x + team * (int)gridDim.x; c < pv.C; c += kWinTeams * (int)gridDim.x) {
+        team_sync();  // previous clone's pold, pnew, red consumed
         if (!a.alive[c]) continue;
         const int p = a.P_particle[c], bead0 = a.b0[c];
-        for (int t = tid; t < (nl + 1) * 3; t += kWinFastThreads) {
+        for (int t = tid; t < (nl + 1) * 3; t += kWinTeamThreads) {
             const int jj = t / 3, d = t - jj * 3;
             int bg = bead0 + jj;
             bg = WrapSlice(pv, bg);
             const double x = a.R_moved[PosIndex(pv, a.N_moved, c, p, d, bg - pv.slice_lo)];
-            pold[jj][d] = x;
-            pnew[jj][d] = (jj >= 1 && jj < nl) ? a.P[((size_t)c * (nl - 1) + (jj - 1)) * 3 + d] : x;
+            pold[team][jj][d] = x;
+            pnew[team][jj][d] = (jj >= 1 && jj < nl) ? a.P[((size_t)c * (nl - 1) + (jj - 1)) * 3 + d] : x;
         }
-        __syncthreads();
+        team_sync();
         int b0s = bead0 + j, b1s = bead0 + j + 1;
         b0s = WrapSlice(pv, b0s);
         b1s = WrapSlice(pv, b1s);
-        // OLD pass, then NEW pass: one set of moved-particle positions in registers at a time
         double acc_old = 0., acc_new = 0.;
-#pragma unroll 1
-        for (int mode = 0; mode < 2; ++mode) {
-            const double(*pp)[3] = mode ? pnew : pold;
-            const double p0[3] = {pp[j][0], pp[j][1], pp[j][2]}, p1[3] = {pp[j + 1][0], pp[j + 1][1], pp[j + 1][2]};
-            double acc = 0.;
-            for (int q = slot; q < a.N_partner; q += n_slots) {
-                if (a.same && q == p) continue;
-                double q0[3], q1[3];
+        const uint32_t po_addr = (uint32_t)__cvta_generic_to_shared(&pold[team][j][0]);
+        const uint32_t pn_addr = (uint32_t)__cvta_generic_to_shared(&pnew[team][j][0]);
+        for (int g = warp; g < n_groups; g += kWinTeamWarps) {
+            const int q = g * per_warp + sub;
+            const bool on = q < a.N_partner && !(a.same && q == p);
+            const int qc = q < a.N_partner ? q : a.N_partner - 1;
+            double q0[3], q1[3];
 #pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    q0[d] = a.R_partner[PosIndex(pv, a.N_partner, c, q, d, b0s - pv.slice_lo)];
-                    q1[d] = a.R_partner[PosIndex(pv, a.N_partner, c, q, d, b1s - pv.slice_lo)];
-                }
-                double r, rp, s;
-                DrDrpDrrpFast(p0, q0, p1, q1, pv.box, r, rp, s);
-                acc += FastIlkkaEval(wtab, a.FT, r, rp, s);
+            for (int d = 0; d < 3; ++d) {
+                q0[d] = a.R_partner[PosIndex(pv, a.N_partner, c, qc, d, b0s - pv.slice_lo)];
+                q1[d] = a.R_partner[PosIndex(pv, a.N_partner, c, qc, d, b1s - pv.slice_lo)];
             }
-            if (mode)
-                acc_new = acc;
-            else
-                acc_old = acc;
+            double ro, rpo, so, rn, rpn, sn, m0[3], m1[3];
+            LdsBeadPair(po_addr, m0, m1);
+            DrDrpDrrpFast(m0, q0, m1, q1, pv.box, ro, rpo, so);
+            LdsBeadPair(pn_addr, m0, m1);
+            DrDrpDrrpFast(m0, q0, m1, q1, pv.box, rn, rpn, sn);
+            double uo, un;
+            FastIlkkaEvalWindow(wtab, a.FT, j, nl, lane, ro, rpo, so, rn, rpn, sn, uo, un);
+            acc_old += on ? uo : 0.;
+            acc_new += on ? un : 0.;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             acc_old += __shfl_down_sync(0xffffffffu, acc_old, o);
             acc_new += __shfl_down_sync(0xffffffffu, acc_new, o);
         }
-        if ((tid & 31) == 0) {
-            red[0][tid >> 5] = acc_old;
-            red[1][tid >> 5] = acc_new;
+        if (lane == 0) {
+            red[team][0][warp] = acc_old;
+            red[team][1][warp] = acc_new;
         }
-        __syncthreads();
+        team_sync();
         if (tid == 0) {
             double to = 0., tn = 0.;
-            for (int i = 0; i < kWinFastThreads / 32; ++i) {
-                to += red[0][i];
-                tn += red[1][i];
+            for (int i = 0; i < kWinTeamWarps; ++i) {
+                to += red[team][0][i];
+                tn += red[team][1][i];
             }
             a.out_old[c] += to;
             a.out_new[c] += tn;
@@ -406,39 +416,47 @@ struct LrWindowArgs {
 /// Species::UpdateRhoK for the proposal (species_class.h:406-425) fused with CalcULong over the
 /// window in OLD and NEW mode (ilkka_pair_action_class.h:104-122) for every long-range action
 /// that involves the moved species.  One CTA per clone, thread per k vector.
+constexpr int kLrChunk = 16;  // window slices whose phase tables are built together
+
 __global__ void __launch_bounds__(256) lr_window_kernel(const LrWindowArgs a) {
-    extern __shared__ __align__(16) double2 ptab[];  // [2][3][2m+1]
+    extern __shared__ __align__(16) double2 ptab[];  // [kLrChunk][2 modes][3 axes][2m+1]
     __shared__ double red[2][256 / 32];
     const PathView &pv = a.pv;
     const int c = blockIdx.x, tid = threadIdx.x;
     const int tl = 2 * a.ks.max_index + 1, n_k = a.ks.n_k;
     const int p = a.sv.P_particle[c];
     double acc_old = 0., acc_new = 0.;
-    for (int j = 0; j < a.n_window; ++j) {
-        int bg = a.b0[c] + j;
-        bg = WrapSlice(pv, bg);
+    for (int j0 = 0; j0 < a.n_window; j0 += kLrChunk) {
+        const int nj = min(kLrChunk, a.n_window - j0);
         __syncthreads();
-        if (tid < 6) {
-            const int mode = tid / 3, d = tid - mode * 3;
+        for (int t = tid; t < nj * 6; t += blockDim.x) {  // one thread per (slice, mode, axis)
+            const int jj = t / 6, md = t - jj * 6;
+            const int mode = md / 3, d = md - mode * 3;
+            int bg = a.b0[c] + j0 + jj;
+            bg = WrapSlice(pv, bg);
             double r[3];
             LoadPos(pv, a.sv, c, p, bg, mode, r);
-            PhaseTable(r[d], a.ks.kbox, a.ks.max_index, ptab + (size_t)(mode * 3 + d) * tl);
+            PhaseTable(r[d], a.ks.kbox, a.ks.max_index, ptab + (size_t)t * tl);
         }
         __syncthreads();
-        for (int k = tid; k < n_k; k += blockDim.x) {
+        for (int t = tid; t < nj * n_k; t += blockDim.x) {
+            const int jj = t / n_k, k = t - jj * n_k;
+            const int j = j0 + jj;
+            int bg = a.b0[c] + j;
+            bg = WrapSlice(pv, bg);
             const int i0 = a.ks.kidx[3 * k], i1 = a.ks.kidx[3 * k + 1], i2 = a.ks.kidx[3 * k + 2];
-            const double2 fo = CMul(CMul(ptab[i0], ptab[tl + i1]), ptab[2 * tl + i2]);
-            const double2 *tn = ptab + 3 * tl;
+            const double2 *to = ptab + (size_t)jj * 6 * tl, *tn = to + 3 * tl;
+            const double2 fo = CMul(CMul(to[i0], to[tl + i1]), to[2 * tl + i2]);
             const double2 fn = CMul(CMul(tn[i0], tn[tl + i1]), tn[2 * tl + i2]);
             const double2 d = make_double2(fn.x - fo.x, fn.y - fo.y);
             a.drho[((size_t)c * a.n_window + j) * n_k + k] = d;
             const size_t ri = ((size_t)c * pv.Mloc + (bg - pv.slice_lo)) * n_k + k;
             const double2 rs = a.rho_self[ri];
             const double2 rn = make_double2(rs.x + d.x, rs.y + d.y);
-            for (int t = 0; t < a.n_actions; ++t) {
-                const double w = a.wk[t][k] * a.factor[t];
-                if (a.rho_other[t]) {
-                    const double2 ro = a.rho_other[t][ri];
+            for (int t2 = 0; t2 < a.n_actions; ++t2) {
+                const double w = a.wk[t2][k] * a.factor[t2];
+                if (a.rho_other[t2]) {
+                    const double2 ro = a.rho_other[t2][ri];
                     acc_old += w * (rs.x * ro.x + rs.y * ro.y);
                     acc_new += w * (rn.x * ro.x + rn.y * ro.y);
                 } else {

@@ -245,6 +245,54 @@ __device__ __forceinline__ double LrRingFlush(const Tab &tb, const FastTable &T,
     return v;
 }
 
+// ------------------------------------------------- window evaluation (bisection moves)
+/// IlkkaPairAction::CalcU of one link of a bisection window in OLD and in NEW mode, for a
+/// converged warp whose lanes are (partner, link j) with the nb links of a partner in consecutive
+/// lanes.  The 2-D part is evaluated per lane and mode.  The long-range spline is needed at the
+/// nb + 1 bead distances of the OLD window and at the nb - 1 moved ones of the NEW window (beads 0
+/// and nb are common) = 2 nb values for 2 nb evaluations, so every lane evaluates it exactly
+/// twice instead of four times: lrA = u_long(r_old(j)); lrB = u_long(r_new(j)) -- except that
+/// lane j = 0, whose r is the same in both modes, spends its second evaluation on the window's
+/// last bead nb.  u_long(r') of a link is the next lane's u_long(r) whenever r' equals that r
+/// bit for bit (same inputs, same image: exact); otherwise -- the image shift changed between
+/// the two slices -- the lane evaluates it itself (rare branch).
+template <class Tab>
+__device__ __forceinline__ void FastIlkkaEvalWindow(const Tab &tb, const FastTable &T, int j, int nb, int lane, double ro, double rpo,
+                                                    double so, double rn, double rpn, double sn, double &uo, double &un) {
+    const double qo = 0.5 * (ro + rpo), qn = 0.5 * (rn + rpn);
+    uo = FastPP2Eval(tb, T.xy, fma(0.5, so, qo), fma(-0.5, so, qo));
+    un = FastPP2Eval(tb, T.xy, fma(0.5, sn, qn), fma(-0.5, sn, qn));
+    if (T.use_lr) {
+        const unsigned full = 0xffffffffu;
+        const double r_end = __shfl_sync(full, rpo, lane | (nb - 1));  // bead nb as the group's last lane sees it
+        const double lrA = FastPP1Eval(tb, T.lr, ClampRare(ro, T.lr));
+        const double lrB = FastPP1Eval(tb, T.lr, ClampRare(j == 0 ? r_end : rn, T.lr));
+        const double lr_end = __shfl_sync(full, lrB, lane & ~(nb - 1));
+        double nxt_o = __shfl_down_sync(full, lrA, 1), rnx_o = __shfl_down_sync(full, ro, 1);
+        double nxt_n = __shfl_down_sync(full, lrB, 1), rnx_n = __shfl_down_sync(full, rn, 1);
+        if (j == nb - 1) {
+            nxt_o = lr_end;
+            nxt_n = lr_end;
+            rnx_o = r_end;
+            rnx_n = r_end;
+        }
+        if (rpo != rnx_o) nxt_o = FastPP1Eval(tb, T.lr, Clamp(rpo, T.lr.r_min, T.lr.r_max));
+        if (rpn != rnx_n) nxt_n = FastPP1Eval(tb, T.lr, Clamp(rpn, T.lr.r_min, T.lr.r_max));
+        uo = fma(-0.5, lrA, uo);
+        uo = fma(-0.5, nxt_o, uo);
+        un = fma(-0.5, j == 0 ? lrA : lrB, un);
+        un = fma(-0.5, nxt_n, un);
+    }
+}
+
+/// Beads j and j + 1 of one clone's window ([j][3] doubles, consecutive) from shared memory.
+__device__ __forceinline__ void LdsBeadPair(uint32_t addr, double b0[3], double b1[3]) {
+    asm volatile("ld.shared.f64 %0, [%6];\n\tld.shared.f64 %1, [%6+8];\n\tld.shared.f64 %2, [%6+16];\n\t"
+                 "ld.shared.f64 %3, [%6+24];\n\tld.shared.f64 %4, [%6+32];\n\tld.shared.f64 %5, [%6+40];"
+                 : "=d"(b0[0]), "=d"(b0[1]), "=d"(b0[2]), "=d"(b1[0]), "=d"(b1[1]), "=d"(b1[2])
+                 : "r"(addr));
+}
+
 // ------------------------------------------------------------------------------ K1 (fast)
 #ifndef PIMC_FAST_THREADS
 #define PIMC_FAST_THREADS 1024
