@@ -1,5 +1,5 @@
 """CPU tests of the multi-GPU host logic (world_size 2 and 3, gloo): slice-shard arithmetic, the
-ring halo exchange and the all-reduce of shard partial sums.  The compute stand-in is the CPU
+ring halo exchange, the ring rotation of the slices and the all-reduce of shard partial sums.  The compute stand-in is the CPU
 oracle evaluating the action over each rank's slice window -- PairAction::GetAction(b0, b1, all
 particles, 0) sums links b0..b1-1 (pair_action_class.h:282-290), which is exactly a shard's
 partial sum -- so the reduced value must equal the whole-path action."""
@@ -64,8 +64,31 @@ def _worker(rank, world, port, ret):
             sharded.ring_halo(send, recv, sh)
             ok_halo = ok_halo and np.array_equal(recv.numpy(), Rs[sp][None][:, :, sh.hi % cfg.n_bead, :])
             ok_halo = ok_halo and np.array_equal(recv.numpy(), mine[:, :, -1, :])
+        # ring rotation (ShardedPath.Rotate): every rank hands its first `shift` owned slices to the
+        # previous rank and appends what the next rank sent; reassembled, the path is the original
+        # rolled by `shift` slices, and its action -- the oracle on the rolled path -- is unchanged
+        shift = 3
+        ok_rot = True
+        rolled = []
+        for sp in range(2):
+            own = np.ascontiguousarray(Rs[sp][None][:, :, sh.lo:sh.hi, :])           # [1][N][n_local][3]
+            send = torch.from_numpy(np.ascontiguousarray(np.moveaxis(own[:, :, :shift, :], 2, 3)))   # [1][N][3][shift] as pimc_rotate_pack lays it out
+            recv = torch.zeros_like(send)
+            sharded.ring_halo(send, recv, sh)
+            new_own = np.concatenate([own[:, :, shift:, :], np.moveaxis(recv.numpy(), 3, 2)], axis=2)
+            parts_t = [torch.zeros_like(torch.from_numpy(new_own)) for _ in range(world)]   # n_bead = 12 divides evenly over 2 and 3 ranks
+            dist.all_gather(parts_t, torch.from_numpy(np.ascontiguousarray(new_own)))
+            full = torch.cat(parts_t, dim=2).numpy()[0]
+            ok_rot = ok_rot and np.array_equal(full, np.roll(Rs[sp], -shift, axis=1))
+            rolled.append(full)
+        o2 = O.Oracle(cfg)
+        for sp in range(2):
+            o2.set_positions(sp, rolled[sp])
+        again = np.array([o2.get_action(a, 0, 0, cfg.n_bead, parts, 0) for a in range(3)])
+        ok_rot = ok_rot and bool(np.all(np.abs(again - whole) <= 1e-11 * np.abs(whole)))
+        o2.close()
         o.close()
-        ret[rank] = (ok_sum, ok_halo)
+        ret[rank] = (ok_sum, ok_halo and ok_rot)
     finally:
         dist.destroy_process_group()
 
