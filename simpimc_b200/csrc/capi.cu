@@ -1818,6 +1818,7 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
         f.use_lr = any_lr ? 1 : 0;
         f.ks = ctx->KView();
         f.rho = any_lr ? st.rho.p : nullptr;
+        f.rho_new = any_lr ? st.drho.p : nullptr;  // the proposal's rho_k buffer doubles as the scratch
         f.wk = any_lr ? a->wk[WHICH_U].p : nullptr;
         f.lr_factor = a->ulong_scale;
         f.n_accept = ctx->mc_naccept.p;

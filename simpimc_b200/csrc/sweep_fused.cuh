@@ -64,6 +64,7 @@ struct SweepFusedArgs {
     int use_lr;
     KSpaceView ks;
     double2 *rho;      // committed rho_k of the species (read and written)
+    double2 *rho_new;  // scratch [C][2^n_level][n_k]: rho_k + delta of the window, written in phase C, committed in phase E
     const double *wk;  // [n_k]
     double lr_factor;
     long long *n_accept;  // [C], added to
@@ -252,9 +253,11 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                 b_last = WrapSlice(pv, b_last);
                 const double *Rc = a.R + PosIndex(pv, a.N, c_grp, 0, 0, 0);
                 const int n_rows = a.N * 3;
-                for (int t = tg - 1; t < 2 * n_rows; t += kSweepGroup - 1) {
-                    const int row = t >> 1;
-                    PrefetchL2(Rc + (size_t)row * pv.Ms + ((t & 1) ? b_last : bead0) - pv.slice_lo);
+                for (int row = tg - 1; row < n_rows; row += kSweepGroup - 1) {
+                    const double *first = Rc + (size_t)row * pv.Ms + bead0 - pv.slice_lo;
+                    const double *last = Rc + (size_t)row * pv.Ms + b_last - pv.slice_lo;
+                    PrefetchL2(first);
+                    if (((uintptr_t)first >> 7) != ((uintptr_t)last >> 7)) PrefetchL2(last);  // second 128-byte line, or the wrapped end
                 }
                 if (n_k > 0) {
                     const int lines = (n_k * (int)sizeof(double2) + 127) / 128;
@@ -339,6 +342,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                     const int bead0 = sh.bead0[sg];
                     const double2 *pt = ptab + (size_t)grp * nb * 6 * tl;
                     const double2 *rho_c = a.rho + (size_t)c_grp * pv.Mloc * n_k;
+                    double2 *rn_c = a.rho_new + (size_t)c_grp * nb * n_k;
                     for (int k = tg; k < n_k; k += kSweepGroup) {
                         const int i0 = a.ks.kidx[3 * k], i1 = tl + a.ks.kidx[3 * k + 1], i2 = 2 * tl + a.ks.kidx[3 * k + 2];
                         const double w = a.wk[k] * a.lr_factor;
@@ -351,6 +355,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                             const double2 fo = CMul(CMul(to[i0], to[i1]), to[i2]);
                             const double2 fn = CMul(CMul(tn[i0], tn[i1]), tn[i2]);
                             const double2 rn = make_double2(rs.x + (fn.x - fo.x), rs.y + (fn.y - fo.y));
+                            rn_c[(size_t)j * n_k + k] = rn;  // phase E copies it (same thread: program order)
                             acc_old += w * (rs.x * rs.x + rs.y * rs.y);
                             acc_new += w * (rn.x * rn.x + rn.y * rn.y);
                         }
@@ -398,23 +403,15 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                     a.R[PosIndex(pv, a.N, c_grp, p, d, bg - pv.slice_lo)] = sh.pnew[sg][j][d];
                 }
                 if (n_k > 0) {
-                    const double2 *pt = ptab + (size_t)grp * nb * 6 * tl;
-                    // slice 0 of the window keeps its bead: its increment is zero
+                    // slice 0 of the window keeps its bead; the others take rho_k + delta as phase C left it
                     double2 *rho_c = a.rho + (size_t)c_grp * pv.Mloc * n_k;
+                    const double2 *rn_c = a.rho_new + (size_t)c_grp * nb * n_k;
                     for (int k = tg; k < n_k; k += kSweepGroup) {
-                        const int i0 = a.ks.kidx[3 * k], i1 = tl + a.ks.kidx[3 * k + 1], i2 = 2 * tl + a.ks.kidx[3 * k + 2];
 #pragma unroll 4
                         for (int j = 1; j < nb; ++j) {
                             int bg = bead0 + j;
                             bg = WrapSlice(pv, bg);
-                            double2 *dst = rho_c + (size_t)(bg - pv.slice_lo) * n_k + k;
-                            double2 v = *dst;
-                            const double2 *to = pt + (size_t)j * 6 * tl, *tn = to + 3 * tl;
-                            const double2 fo = CMul(CMul(to[i0], to[i1]), to[i2]);
-                            const double2 fn = CMul(CMul(tn[i0], tn[i1]), tn[i2]);
-                            v.x += fn.x - fo.x;
-                            v.y += fn.y - fo.y;
-                            *dst = v;
+                            rho_c[(size_t)(bg - pv.slice_lo) * n_k + k] = rn_c[(size_t)j * n_k + k];
                         }
                     }
                 }
