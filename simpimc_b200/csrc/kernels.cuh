@@ -474,6 +474,32 @@ __global__ void __launch_bounds__(256) ksum_kernel(const KSumArgs a) {
     const PathView &pv = a.pv;
     const int nb = a.b0 ? a.n_window : pv.Mloc;
     double acc = 0.;
+    if (!a.b0 && !a.drho_a && !a.drho_b) {
+        // whole shard, committed rho_k: every (k, slice) element is read once -- keep four slices'
+        // loads in flight per thread (one CTA per clone cannot hide the HBM latency otherwise) and
+        // read a same-species rho_k once; the accumulation order (k outer, slices in order) stays
+        const bool same = a.rho_a == a.rho_b;
+        for (int k = threadIdx.x; k < a.n_k; k += blockDim.x) {
+            const double w = a.wk[k];
+            const double2 *pa = a.rho_a + (size_t)c * pv.Mloc * a.n_k + k;
+            const double2 *pb = a.rho_b + (size_t)c * pv.Mloc * a.n_k + k;
+            int j = 0;
+            for (; j + 4 <= nb; j += 4) {
+                double2 ra[4], rb[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) ra[u] = pa[(size_t)(j + u) * a.n_k];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) rb[u] = same ? ra[u] : pb[(size_t)(j + u) * a.n_k];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc += w * (ra[u].x * rb[u].x + ra[u].y * rb[u].y);
+            }
+            for (; j < nb; ++j) {
+                const double2 ra = pa[(size_t)j * a.n_k];
+                const double2 rb = same ? ra : pb[(size_t)j * a.n_k];
+                acc += w * (ra.x * rb.x + ra.y * rb.y);
+            }
+        }
+    } else
     for (int k = threadIdx.x; k < a.n_k; k += blockDim.x) {
         const double w = a.wk[k];
         for (int j = 0; j < nb; ++j) {
