@@ -1856,7 +1856,7 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
         ba.pair_new = pair_new;
         ba.lr_old = lr_old;
         ba.lr_new = lr_new;
-        bisect_sample_kernel<<<(C + 127) / 128, 128, 0, ctx->stream>>>(ba);
+        bisect_sample_kernel<<<(C + kSampleWarps - 1) / kSampleWarps, kSampleWarps * 32, 0, ctx->stream>>>(ba);
         ctx->launches++;
         for (pimc_action *a : acts) {
             const int partner = (a->sa == s) ? a->sb : a->sa;
@@ -1905,6 +1905,17 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
             l.drho = st.drho.p;
             l.lr_old = lr_old;
             l.lr_new = lr_new;
+            l.fuse_decide = 1;  // decision and commit ride on this launch
+            l.alive = alive;
+            l.partial = partial;
+            l.logu0 = logu0;
+            l.pair_old = pair_old;
+            l.pair_new = pair_new;
+            l.N = st.N;
+            l.R = st.R.p;
+            l.rho_commit = st.rho.p;
+            l.accept = accept;
+            l.n_accept = ctx->mc_naccept.p;
             l.n_actions = 0;
             for (pimc_action *a : acts) {
                 if (!(a->use_long_range && n_k > 0)) continue;
@@ -1924,10 +1935,11 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
             }
             ctx->launches++;
         }
-        bisect_decide_commit_kernel<<<C, 256, 0, ctx->stream>>>(pv, st.N, n_k, nb, alive, partial, logu0, pair_old, pair_new, lr_old, lr_new,
-                                                               st.P.p, st.P_particle.p, b0, any_lr ? st.drho.p : nullptr, st.R.p,
-                                                               any_lr ? st.rho.p : nullptr, accept, ctx->mc_naccept.p);
-        ctx->launches++;
+        if (!any_lr) {  // with a long-range action the decision and the commit rode on lr_window_kernel
+            bisect_decide_commit_kernel<<<C, 256, 0, ctx->stream>>>(pv, st.N, n_k, nb, alive, partial, logu0, pair_old, pair_new, lr_old, lr_new,
+                                                                   st.P.p, st.P_particle.p, b0, nullptr, st.R.p, nullptr, accept, ctx->mc_naccept.p);
+            ctx->launches++;
+        }
     }
     PIMC_CUDA(cudaGetLastError());
     st.n_prop = 0;
@@ -2069,6 +2081,14 @@ int pimc_displace_sweep(pimc_ctx *ctx, int32_t s, double step_size, int32_t n_at
             l.drho = st.drho.p;
             l.lr_old = lr_old;
             l.lr_new = lr_new;
+            l.fuse_decide = 0;  // displace_decide_commit_kernel decides: the pair sums are per chunk
+            l.alive = nullptr;
+            l.partial = l.logu0 = l.pair_old = l.pair_new = nullptr;
+            l.N = st.N;
+            l.R = nullptr;
+            l.rho_commit = nullptr;
+            l.accept = nullptr;
+            l.n_accept = nullptr;
             l.n_actions = 0;
             for (pimc_action *a : acts) {
                 if (!(a->use_long_range && n_k > 0)) continue;

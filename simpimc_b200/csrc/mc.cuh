@@ -82,11 +82,27 @@ struct BisectArgs {
 
 __device__ __forceinline__ double PutInBox1(double d, const Box &bx) { return d - rint(d * bx.iL) * bx.L; }
 
-/// One thread per clone.
-__global__ void __launch_bounds__(128) bisect_sample_kernel(const BisectArgs a) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+/// First Philox slot of a level: slot 0 picks particle and window, then every level from the
+/// top takes two slots per midpoint and one for its Metropolis uniform.
+__device__ __forceinline__ uint32_t SweepSlotStart(int level, int n_level, int nb) {
+    uint32_t s = 1;
+    for (int l = n_level - 1; l > level; --l) s += 2u * (uint32_t)(nb >> (l + 1)) + 1u;
+    return s;
+}
+
+constexpr int kSampleWarps = 4;  // clones per CTA
+
+/// One WARP per clone: the Philox draws (Levy displacements of all midpoints, Metropolis
+/// uniforms) and the window's bead loads run in parallel over the lanes, lane 0 then walks the
+/// levels (bisect_class.h:69-98) on shared memory, and the lanes write the proposal.
+__global__ void __launch_bounds__(kSampleWarps * 32) bisect_sample_kernel(const BisectArgs a) {
+    __shared__ double s_old[kSampleWarps][kMaxBisectBeads + 1][3], s_new[kSampleWarps][kMaxBisectBeads + 1][3];
+    __shared__ double s_del[kSampleWarps][kMaxBisectBeads][3], s_d2[kSampleWarps][kMaxBisectBeads], s_logu[kSampleWarps][8];
+    __shared__ int s_alive[kSampleWarps];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * kSampleWarps + w;
     const PathView &pv = a.pv;
-    if (c >= pv.C) return;
+    if (c >= pv.C) return;  // whole warp
     const int nb = 1 << a.n_level;
     uint32_t rnd[4];
     Philox4x32(a.attempt_lo, a.attempt_hi, (uint32_t)c, 0u, a.seed_lo, a.seed_hi, rnd);
@@ -95,103 +111,120 @@ __global__ void __launch_bounds__(128) bisect_sample_kernel(const BisectArgs a) 
     p_i = p_i < a.N ? p_i : a.N - 1;
     int bead0 = (int)(UniformFromBits(rnd[2], rnd[3]) * a.b0_count);
     bead0 = a.b0_lo + (bead0 < a.b0_count ? bead0 : a.b0_count - 1);
-    double oldb[kMaxBisectBeads + 1][3], newb[kMaxBisectBeads + 1][3];
-    for (int j = 0; j <= nb; ++j) {
+    double(*oldb)[3] = s_old[w];
+    double(*newb)[3] = s_new[w];
+    for (int t = lane; t < (nb + 1) * 3; t += 32) {
+        const int j = t / 3, d = t - j * 3;
         int bg = bead0 + j;
         bg = WrapSlice(pv, bg);
+        const double x = a.R[PosIndex(pv, a.N, c, p_i, d, bg - pv.slice_lo)];
+        oldb[j][d] = x;
+        newb[j][d] = x;
+    }
+    if (lane >= 1 && lane < nb) {  // Levy displacement sigma * normal of midpoint ib = lane
+        const int ib = lane;
+        const int level = __ffs(ib) - 1, skip = 1 << level;
+        const int idx = (ib - skip) >> (level + 1);
+        const uint32_t slot = SweepSlotStart(level, a.n_level, nb) + 2u * (uint32_t)idx;
+        uint32_t r0[4], r1[4];
+        Philox4x32(a.attempt_lo, a.attempt_hi, (uint32_t)c, slot, a.seed_lo, a.seed_hi, r0);
+        Philox4x32(a.attempt_lo, a.attempt_hi, (uint32_t)c, slot + 1, a.seed_lo, a.seed_hi, r1);
+        // Box-Muller: three of the four normals
+        const double ua = UniformFromBits(r0[0], r0[1]), ub = UniformFromBits(r0[2], r0[3]);
+        const double uc = UniformFromBits(r1[0], r1[1]), ud = UniformFromBits(r1[2], r1[3]);
+        const double ra = sqrt(-2. * log(ua)), rc = sqrt(-2. * log(uc));
+        double sb, cb, sd, cd;
+        sincospi(2. * ub, &sb, &cb);
+        sincospi(2. * ud, &sd, &cd);
+        (void)sd;
+        const double nrm[3] = {ra * cb, ra * sb, rc * cd};
+        const double sigma = sqrt(a.lambda * (a.tau * skip));
+        double d2 = 0.;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-            const double x = a.R[PosIndex(pv, a.N, c, p_i, d, bg - pv.slice_lo)];
-            oldb[j][d] = x;
-            newb[j][d] = x;
+            const double del = PutInBox1(sigma * nrm[d], pv.box);
+            s_del[w][ib][d] = del;
+            d2 += del * del;
         }
+        s_d2[w][ib] = d2;
     }
-    uint32_t slot = 1;
-    bool alive = true;
-    double prev_change = 0., partial = 0., logu0 = 0.;
-    for (int level = a.n_level - 1; level >= 0; --level) {
-        const int skip = 1 << level;
-        const double level_tau = a.tau * skip;
-        const double sigma = sqrt(a.lambda * level_tau);
-        // FreeSpline(L, n_images = 0, lambda, 0.5 * tau * 2^level): log rho = -|r|^2 / (4 lambda (level_tau / 2))
-        const double i4lt_sample = 1. / (4. * a.lambda * (0.5 * level_tau));
-        const double i4lt_kin = 1. / (4. * a.lambda * level_tau);
-        double old_lp = 0., new_lp = 0.;
-        for (int ia = 0; ia < nb; ia += 2 * skip) {
-            const int ib = ia + skip, ic = ia + 2 * skip;
-            uint32_t r0[4], r1[4];
-            Philox4x32(a.attempt_lo, a.attempt_hi, (uint32_t)c, slot, a.seed_lo, a.seed_hi, r0);
-            Philox4x32(a.attempt_lo, a.attempt_hi, (uint32_t)c, slot + 1, a.seed_lo, a.seed_hi, r1);
-            slot += 2;
-            // Box-Muller: three of the four normals
-            const double ua = UniformFromBits(r0[0], r0[1]), ub = UniformFromBits(r0[2], r0[3]);
-            const double uc = UniformFromBits(r1[0], r1[1]), ud = UniformFromBits(r1[2], r1[3]);
-            const double ra = sqrt(-2. * log(ua)), rc = sqrt(-2. * log(uc));
-            double sb, cb, sd, cd;
-            sincospi(2. * ub, &sb, &cb);
-            sincospi(2. * ud, &sd, &cd);
-            const double nrm[3] = {ra * cb, ra * sb, rc * cd};
-            double d2_old = 0., d2_new = 0.;
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                // RBar(bead_c, bead_a) = r_a + 0.5 * Dr(r_c, r_a)   (path_class.h:124)
-                const double rbar_old = oldb[ia][d] + 0.5 * PutInBox1(oldb[ic][d] - oldb[ia][d], pv.box);
-                const double del_old = PutInBox1(oldb[ib][d] - rbar_old, pv.box);
-                d2_old += del_old * del_old;
-                const double rbar_new = newb[ia][d] + 0.5 * PutInBox1(newb[ic][d] - newb[ia][d], pv.box);
-                const double del_new = PutInBox1(sigma * nrm[d], pv.box);
-                newb[ib][d] = rbar_new + del_new;
-                d2_new += del_new * del_new;
-            }
-            old_lp -= d2_old * i4lt_sample;
-            new_lp -= d2_new * i4lt_sample;
-        }
-        double old_kin = 0., new_kin = 0.;
-        if (a.with_kinetic) {  // Kinetic::GetAction (kinetic_class.h:105-122), n_images = 0
-            for (int ia = 0; ia < nb; ia += skip) {
-                double d2o = 0., d2n = 0.;
-#pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    const double o = PutInBox1(oldb[ia][d] - oldb[ia + skip][d], pv.box);
-                    const double n = PutInBox1(newb[ia][d] - newb[ia + skip][d], pv.box);
-                    d2o += o * o;
-                    d2n += n * n;
-                }
-                old_kin += d2o * i4lt_kin;
-                new_kin += d2n * i4lt_kin;
-            }
-        }
+    if (lane < a.n_level) {  // Metropolis uniform of level = lane
+        const uint32_t slot = SweepSlotStart(lane, a.n_level, nb) + 2u * (uint32_t)(nb >> (lane + 1));
         uint32_t ru[4];
         Philox4x32(a.attempt_lo, a.attempt_hi, (uint32_t)c, slot, a.seed_lo, a.seed_hi, ru);
-        slot += 1;
-        const double logu = log(UniformFromBits(ru[0], ru[1]));
-        const double lsr = -new_lp + old_lp;
-        const double change = new_kin - old_kin;
-        if (level > 0) {
-            const double log_accept = lsr - change + prev_change;
-            if (log_accept < logu) alive = false;
-            prev_change = change;
-        } else {
-            partial = lsr - change + prev_change;
-            logu0 = logu;
-        }
+        s_logu[w][lane] = log(UniformFromBits(ru[0], ru[1]));
     }
-    const int n_prop = nb - 1;
-    for (int j = 0; j < n_prop; ++j)
+    __syncwarp();
+    if (lane == 0) {
+        bool alive = true;
+        double prev_change = 0., partial = 0.;
+        for (int level = a.n_level - 1; level >= 0; --level) {
+            const int skip = 1 << level;
+            const double level_tau = a.tau * skip;
+            // FreeSpline(L, n_images = 0, lambda, 0.5 * tau * 2^level): log rho = -|r|^2 / (4 lambda (level_tau / 2))
+            const double i4lt_sample = 1. / (4. * a.lambda * (0.5 * level_tau));
+            const double i4lt_kin = 1. / (4. * a.lambda * level_tau);
+            double old_lp = 0., new_lp = 0.;
+            for (int ia = 0; ia < nb; ia += 2 * skip) {
+                const int ib = ia + skip, ic = ia + 2 * skip;
+                double d2_old = 0.;
 #pragma unroll
-        for (int d = 0; d < 3; ++d) a.P[((size_t)c * n_prop + j) * 3 + d] = alive ? newb[j + 1][d] : oldb[j + 1][d];
-    a.P_particle[c] = p_i;
-    int first = bead0 + 1;
-    first = WrapSlice(pv, first);
-    a.P_first[c] = first;
-    a.b0[c] = bead0;
-    a.partial[c] = partial;
-    a.logu0[c] = logu0;
-    a.alive[c] = alive ? 1 : 0;
-    a.pair_old[c] = 0.;
-    a.pair_new[c] = 0.;
-    a.lr_old[c] = 0.;
-    a.lr_new[c] = 0.;
+                for (int d = 0; d < 3; ++d) {
+                    // RBar(bead_c, bead_a) = r_a + 0.5 * Dr(r_c, r_a)   (path_class.h:124)
+                    const double rbar_old = oldb[ia][d] + 0.5 * PutInBox1(oldb[ic][d] - oldb[ia][d], pv.box);
+                    const double del_old = PutInBox1(oldb[ib][d] - rbar_old, pv.box);
+                    d2_old += del_old * del_old;
+                    const double rbar_new = newb[ia][d] + 0.5 * PutInBox1(newb[ic][d] - newb[ia][d], pv.box);
+                    newb[ib][d] = rbar_new + s_del[w][ib][d];
+                }
+                old_lp -= d2_old * i4lt_sample;
+                new_lp -= s_d2[w][ib] * i4lt_sample;
+            }
+            double old_kin = 0., new_kin = 0.;
+            if (a.with_kinetic) {  // Kinetic::GetAction (kinetic_class.h:105-122), n_images = 0
+                for (int ia = 0; ia < nb; ia += skip) {
+                    double d2o = 0., d2n = 0.;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const double o = PutInBox1(oldb[ia][d] - oldb[ia + skip][d], pv.box);
+                        const double n = PutInBox1(newb[ia][d] - newb[ia + skip][d], pv.box);
+                        d2o += o * o;
+                        d2n += n * n;
+                    }
+                    old_kin += d2o * i4lt_kin;
+                    new_kin += d2n * i4lt_kin;
+                }
+            }
+            const double lsr = -new_lp + old_lp;
+            const double change = new_kin - old_kin;
+            if (level > 0) {
+                if (lsr - change + prev_change < s_logu[w][level]) alive = false;
+                prev_change = change;
+            } else {
+                partial = lsr - change + prev_change;
+            }
+        }
+        s_alive[w] = alive ? 1 : 0;
+        a.P_particle[c] = p_i;
+        int first = bead0 + 1;
+        first = WrapSlice(pv, first);
+        a.P_first[c] = first;
+        a.b0[c] = bead0;
+        a.partial[c] = partial;
+        a.logu0[c] = s_logu[w][0];
+        a.alive[c] = alive ? 1 : 0;
+        a.pair_old[c] = 0.;
+        a.pair_new[c] = 0.;
+        a.lr_old[c] = 0.;
+        a.lr_new[c] = 0.;
+    }
+    __syncwarp();
+    const bool alive = s_alive[w] != 0;
+    const int n_prop = nb - 1;
+    for (int t = lane; t < n_prop * 3; t += 32) {
+        const int j = t / 3, d = t - j * 3;
+        a.P[((size_t)c * n_prop + j) * 3 + d] = alive ? newb[j + 1][d] : oldb[j + 1][d];
+    }
 }
 
 struct WindowBothArgs {
@@ -411,6 +444,16 @@ struct LrWindowArgs {
     const double *wk[kMaxLrActions];
     double factor[kMaxLrActions];             // scale * (2 if the species differ)
     double *lr_old, *lr_new;                  // [C], overwritten
+    // fuse_decide != 0: the kernel also takes the level-0 Metropolis decision and commits
+    // (bisect_decide_commit_kernel's work, one launch less per attempt)
+    int fuse_decide;
+    const int32_t *alive;
+    const double *partial, *logu0, *pair_old, *pair_new;  // [C]
+    int N;
+    double *R;               // committed positions of the moved species
+    double2 *rho_commit;     // == rho_self, writable
+    int32_t *accept;
+    long long *n_accept;
 };
 
 /// Species::UpdateRhoK for the proposal (species_class.h:406-425) fused with CalcULong over the
@@ -421,6 +464,7 @@ constexpr int kLrChunk = 16;  // window slices whose phase tables are built toge
 __global__ void __launch_bounds__(256) lr_window_kernel(const LrWindowArgs a) {
     extern __shared__ __align__(16) double2 ptab[];  // [kLrChunk][2 modes][3 axes][2m+1]
     __shared__ double red[2][256 / 32];
+    __shared__ int s_accept;
     const PathView &pv = a.pv;
     const int c = blockIdx.x, tid = threadIdx.x;
     const int tl = 2 * a.ks.max_index + 1, n_k = a.ks.n_k;
@@ -484,6 +528,36 @@ __global__ void __launch_bounds__(256) lr_window_kernel(const LrWindowArgs a) {
         }
         a.lr_old[c] = to;
         a.lr_new[c] = tn;
+        if (a.fuse_decide) {  // bisect_class.h:110-115, same arithmetic as bisect_decide_commit_kernel
+            int acc = 0;
+            if (a.alive[c]) {
+                const double old_action = a.pair_old[c] + to, new_action = a.pair_new[c] + tn;
+                acc = (a.partial[c] - (new_action - old_action)) < a.logu0[c] ? 0 : 1;
+            }
+            a.accept[c] = acc;
+            a.n_accept[c] += acc;
+            s_accept = acc;
+        }
+    }
+    if (!a.fuse_decide) return;
+    __syncthreads();
+    if (!s_accept) return;
+    // Move::Accept: the proposal's beads and rho_k += delta on the window (every read of rho_self is behind the barrier)
+    const int n_prop = a.n_window - 1, bead0 = a.b0[c];
+    for (int t = tid; t < n_prop * 3; t += blockDim.x) {
+        const int j = t / 3, d = t - j * 3;
+        int bg = bead0 + 1 + j;
+        bg = WrapSlice(pv, bg);
+        a.R[PosIndex(pv, a.N, c, p, d, bg - pv.slice_lo)] = a.sv.P[((size_t)c * n_prop + j) * 3 + d];
+    }
+    for (int t = tid; t < a.n_window * n_k; t += blockDim.x) {
+        const int j = t / n_k, k = t - j * n_k;
+        int bg = bead0 + j;
+        bg = WrapSlice(pv, bg);
+        double2 *dst = a.rho_commit + ((size_t)c * pv.Mloc + (bg - pv.slice_lo)) * n_k + k;
+        const double2 d = a.drho[((size_t)c * a.n_window + j) * n_k + k];
+        dst->x += d.x;
+        dst->y += d.y;
     }
 }
 

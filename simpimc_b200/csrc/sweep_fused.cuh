@@ -86,14 +86,6 @@ struct SweepShared {
     int accept[kSweepClones];
 };
 
-/// First Philox slot of a level: slot 0 picks particle and window, then every level from the
-/// top takes two slots per midpoint and one for its Metropolis uniform (bisect_sample_kernel).
-__device__ __forceinline__ uint32_t SweepSlotStart(int level, int n_level, int nb) {
-    uint32_t s = 1;
-    for (int l = n_level - 1; l > level; --l) s += 2u * (uint32_t)(nb >> (l + 1)) + 1u;
-    return s;
-}
-
 /// Barrier among the kTeamThreads threads of one team (barrier 0 is __syncthreads).
 __device__ __forceinline__ void TeamSync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(kTeamThreads) : "memory"); }
 
