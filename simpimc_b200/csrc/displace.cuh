@@ -101,10 +101,8 @@ __global__ void __launch_bounds__(kDispThreads, 1) displace_pair_kernel(const Di
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const PathView &pv = a.pv;
     if (ATYPE < 0) {
-        const int4 *src = reinterpret_cast<const int4 *>(a.fast_tables);
-        int4 *dst = reinterpret_cast<int4 *>(dsm);
-        for (int i = tid; i < a.FT.n_bytes / 16; i += kDispThreads) dst[i] = src[i];
-        __syncthreads();
+        __shared__ unsigned long long stage_bar;
+        StageBlockTma(dsm, a.fast_tables, a.FT.n_bytes, &stage_bar);
     }
     const SharedTab tb(dsm);
     const int n_items = pv.C * a.n_chunks;

@@ -354,12 +354,8 @@ __global__ void __launch_bounds__(kWinFastThreads, 1) pair_window_fast_kernel(co
     extern __shared__ __align__(16) unsigned char wsm[];
     __shared__ double pold[kWinTeams][kMaxBisectBeads + 1][3], pnew[kWinTeams][kMaxBisectBeads + 1][3];
     __shared__ double red[kWinTeams][2][kWinTeamWarps];
-    {
-        const int4 *src = reinterpret_cast<const int4 *>(a.fast_tables);
-        int4 *dst = reinterpret_cast<int4 *>(wsm);
-        for (int i = threadIdx.x; i < a.FT.n_bytes / 16; i += kWinFastThreads) dst[i] = src[i];
-    }
-    __syncthreads();  // the only CTA-wide barrier
+    __shared__ unsigned long long stage_bar;
+    StageBlockTma(wsm, a.fast_tables, a.FT.n_bytes, &stage_bar);  // the only CTA-wide synchronisation
     const SharedTab wtab(wsm);
     const PathView &pv = a.pv;
     const int nl = a.n_links;

@@ -92,6 +92,43 @@ struct GlobalTab {
     __device__ __forceinline__ int LdU16(int off) const { return __ldg(reinterpret_cast<const unsigned short *>(base + off)); }
 };
 
+/// Stages `n_bytes` (a multiple of 16; source and destination 16-byte aligned) of table data from
+/// global into shared memory with the TMA engine: one thread arms an mbarrier with the byte count
+/// and issues 1-D bulk copies (cp.async.bulk, SASS UBLKCP), every thread waits on the barrier's
+/// phase 0.  No registers or LSU instructions are spent on the copy and the whole block is in
+/// flight at once (the thread-strided int4 loop it replaces made ~7 dependent L2 round trips).
+/// Ends with the block synchronised and the data visible to ordinary shared-memory loads.
+__device__ __forceinline__ void StageBlockTma(void *smem_dst, const void *gsrc, int n_bytes, unsigned long long *mbar) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(mbar);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)n_bytes) : "memory");
+        const char *src = reinterpret_cast<const char *>(gsrc);
+        constexpr int kChunk = 32768;
+        for (int off = 0; off < n_bytes; off += kChunk) {
+            const uint32_t sz = (uint32_t)min(kChunk, n_bytes - off);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + (uint32_t)off),
+                         "l"(src + off), "r"(sz), "r"(bar)
+                         : "memory");
+        }
+    }
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "STAGE_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra STAGE_DONE;\n"
+        "bra STAGE_WAIT;\n"
+        "STAGE_DONE:\n"
+        "}\n" ::"r"(bar)
+        : "memory");
+}
+
 /// Interval of x >= 0 and tau = x - g[interval].  `clamp_key`: x may lie beyond the grid end
 /// (keys above the table are clamped to its last bucket, whose interval is the last one).
 template <class Tab>
@@ -331,12 +368,8 @@ __global__ void __launch_bounds__(kFastThreads, 1) pair_full_fast_kernel(const P
     double *qpos = reinterpret_cast<double *>(fsm);               // [kFastRows][3][kFastRow]
     unsigned char *tb_ptr = fsm + sizeof(double) * kFastRows * 3 * kFastRow;
     const SharedTab tb(tb_ptr);
-    {
-        const int4 *src = reinterpret_cast<const int4 *>(a.tables);
-        int4 *dst = reinterpret_cast<int4 *>(tb_ptr);
-        for (int i = tid; i < a.T.n_bytes / 16; i += kFastThreads) dst[i] = src[i];
-    }
-    __syncthreads();
+    __shared__ unsigned long long stage_bar;
+    StageBlockTma(tb_ptr, a.tables, a.T.n_bytes, &stage_bar);
     const PathView &pv = a.pv;
     const int Na = a.A.N, Nb = a.B.N;
     const int half = Na / 2;
@@ -447,12 +480,8 @@ __global__ void __launch_bounds__(kFastThreads, 1) potential_fast_kernel(const P
     double *qpos = reinterpret_cast<double *>(fsm);               // [kFastRows][3][kFastRow]
     unsigned char *tb_ptr = fsm + sizeof(double) * kFastRows * 3 * kFastRow;
     const SharedTab tb(tb_ptr);
-    {
-        const int4 *src = reinterpret_cast<const int4 *>(a.tables);
-        int4 *dst = reinterpret_cast<int4 *>(tb_ptr);
-        for (int i = tid; i < a.T.n_bytes / 16; i += kFastThreads) dst[i] = src[i];
-    }
-    __syncthreads();
+    __shared__ unsigned long long stage_bar;
+    StageBlockTma(tb_ptr, a.tables, a.T.n_bytes, &stage_bar);
     const PathView &pv = a.pv;
     const int Na = a.A.N, Nb = a.B.N;
     const int half = Na / 2;

@@ -101,12 +101,8 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
     const int nb = 1 << a.n_level;
     const int tl = 2 * a.ks.max_index + 1, n_k = a.use_lr ? a.ks.n_k : 0;
     // dynamic shared memory: [fast tables][phase tables: clone slot, window slice, mode, axis, 2m+1]
-    {
-        const int4 *src = reinterpret_cast<const int4 *>(a.fast_tables);
-        int4 *dst = reinterpret_cast<int4 *>(ssm);
-        for (int i = threadIdx.x; i < a.FT.n_bytes / 16; i += kSweepThreads) dst[i] = src[i];
-    }
-    __syncthreads();  // the only CTA-wide barrier: from here on the teams run on their own
+    __shared__ unsigned long long stage_bar;
+    StageBlockTma(ssm, a.fast_tables, a.FT.n_bytes, &stage_bar);  // the only CTA-wide synchronisation: from here on the teams run on their own
     const SharedTab tb(ssm);
     const int s0 = team * kTeamClones;  // first shared-memory clone slot of this team
     double2 *ptab = reinterpret_cast<double2 *>(ssm + a.FT.n_bytes) + (size_t)s0 * nb * 6 * tl;
