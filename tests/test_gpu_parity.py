@@ -224,6 +224,38 @@ def test_errors_are_loud():
     cfg.n_d = 2
     with pytest.raises(RuntimeError):
         host.Path(cfg, n_clones=1)
+    # misuse of the move / derivative / sharding entry points: an error code and a message, never a silent result
+    cfg = S.ueg_config(N=7, M=8)
+    path = host.Path(cfg, n_clones=2)
+    R = np.stack([S.synthetic_paths(cfg, 0, c) for c in range(2)])
+    path.SetPositions(0, R)
+    act = path.actions[0]
+    path.Propose(0, 1, 2, R[:, 1, 2:4, :] + 0.01)
+    for bad in (lambda: path.Propose(0, 1, 2, R[:, 1, 2:4, :]),              # the same particle proposed twice
+                lambda: path.Propose(0, 3, 2, R[:, 3, 2:5, :]),              # another bead count on the same species
+                lambda: act.GetActionGradient(1, 3, [(0, 1)], 0),            # derivatives while a proposal is pending
+                lambda: path.BisectSweep(0, 2, 1, 1),                        # a device sweep while a proposal is pending
+                lambda: path.DisplaceSweep(0, 0.1, 1, 1)):
+        with pytest.raises(RuntimeError):
+            bad()
+    path.Commit(0)
+    for bad in (lambda: path.DisplaceSweep(0, -1.0, 1, 1),                   # non-positive step
+                lambda: path.BisectSweep(0, 4, 1, 1),                        # window longer than the path (2^4 > 8)
+                lambda: path.PermTable(0, 0, 9),                             # n_bisect_beads > n_bead
+                lambda: path.PermTable(0, 8, 2),                             # window start out of range
+                lambda: act.GetAction(0, 2, [(0, 7)], 0),                    # particle out of range
+                lambda: act.GetAction(0, 2, [(0, 1), (0, 1)], 0)):           # particle listed twice
+        with pytest.raises(RuntimeError):
+            bad()
+    path.close()
+    shard = host.Path(cfg, n_clones=1, slice_lo=0, slice_hi=4)
+    shard.SetPositions(0, R[:1, :, [0, 1, 2, 3, 4], :])
+    for bad in (lambda: shard.DisplaceSweep(0, 0.1, 1, 1),                   # whole-path move on a slice shard
+                lambda: shard.BisectSweep(0, 3, 1, 1),                       # window longer than the shard
+                lambda: shard.actions[0].GetAction(0, 2, [(0, 1)], 0)):      # host-driven windows on a shard
+        with pytest.raises(RuntimeError):
+            bad()
+    shard.close()
 
 
 @pytest.mark.parametrize("name", ["ilkka_lr_n7", "ilkka_lr_n33", "ilkka_nolr_n8", "plasma", "n2"])
