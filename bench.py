@@ -587,7 +587,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clones", type=int, default=int(os.environ.get("BENCH_CLONES", "1024")))
     ap.add_argument("--attempts", type=int, default=256, help="bisection attempts per clone timed for the MC-sweep figure")
-    ap.add_argument("--pipeline", type=int, default=4, help="contexts the end-to-end leg splits the clones over (H2D/compute overlap)")
+    ap.add_argument("--pipeline", type=int, default=16, help="contexts the end-to-end leg splits the clones over (H2D/compute overlap)")
     ap.add_argument("--cpu-evals", type=int, default=8, help="DActionDBeta() calls per core for cpu_baseline (0 = skip)")
     ap.add_argument("--workload", default="c3", choices=["c3", "c5"], help="c3: UEG N=256 M=128 x clones (headline); c5: plasma 1024+1024, M=512, slices sharded over the GPUs")
     ap.add_argument("--c5-n", type=int, default=1024)
