@@ -659,7 +659,7 @@ int BuildFastV(pimc_ctx *ctx, pimc_action *a, const pimc_table_1d &v_r, int is_c
     if (a->use_long_range && !AppendFastPP1(blob, T.lr, lr->f_r, kMaxKeys)) return PIMC_OK;
     blob.b.resize((blob.b.size() + 15) & ~(size_t)15, 0);
     if (blob.b.empty()) blob.b.resize(16, 0);
-    const size_t need = sizeof(double) * kFastRows * 3 * kFastRow + blob.b.size() + 2048;
+    const size_t need = sizeof(double) * kFastRows * 3 * kFastRow + blob.b.size() + 10240;  // + static shared memory (ring, red) of the kernels that use it
     if (need > ctx->smem_optin) return PIMC_OK;
     T.n_bytes = (int)blob.b.size();
     PIMC_CUDA(a->fastv_tab.Alloc(blob.b.size()));
@@ -757,9 +757,40 @@ int LaunchPotentialFast(pimc_action *a, int *n_per_clone) {
     return PIMC_OK;
 }
 
+/// Bare U / dU/dbeta over the whole path through the fast V tables (CalcV of DrDrpDrrp's r, r').
+int LaunchBareFast(pimc_action *a, int which, int *n_per_clone) {
+    pimc_ctx *ctx = a->ctx;
+    BareFastArgs args;
+    args.pv = ctx->View();
+    args.A = ctx->SView(a->sa, false);
+    args.B = ctx->SView(a->sb, false);
+    args.same = a->sa == a->sb;
+    args.T = a->fastv;
+    args.tables = a->fastv_tab.p;
+    args.scale = which == WHICH_U ? a->table[WHICH_U].u_scale : 1.;
+    args.n_chunks = (ctx->Mloc + kChunk - 1) / kChunk;
+    FastItems(ctx, args.A.N, args.B.N, args.same != 0, args.n_chunks, args.n_pgroups, args.n_tsplit, args.t_windows);
+    *n_per_clone = args.n_chunks * args.n_pgroups * args.n_tsplit;
+    const size_t items = (size_t)ctx->C * *n_per_clone;
+    if (ctx->partial.n < items) PIMC_CUDA(ctx->partial.Alloc(items));
+    args.partial = ctx->partial.p;
+    const size_t smem = sizeof(double) * kFastRows * 3 * kFastRow + (size_t)args.T.n_bytes;
+    PIMC_CUDA(cudaFuncSetAttribute(bare_full_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<size_t>(items, (size_t)ctx->n_sm);
+    {
+        ScopedKernelTimer t(ctx, PIMC_KERNEL_PAIR_FULL);
+        bare_full_fast_kernel<<<grid, kFastThreads, smem, ctx->stream>>>(args);
+    }
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    return PIMC_OK;
+}
+
 int LaunchPairFull(pimc_action *a, int which, bool independent_images, int *n_per_clone) {
     pimc_ctx *ctx = a->ctx;
     if (which == WHICH_V && independent_images && a->fastv_ok && !ctx->force_general) return LaunchPotentialFast(a, n_per_clone);
+    if (a->atype == ATYPE_BARE && which != WHICH_V && !independent_images && a->fastv_ok && !ctx->force_general)
+        return LaunchBareFast(a, which, n_per_clone);
     if (a->atype == ATYPE_ILKKA && which != WHICH_V && !independent_images && a->fast_ok[which] && !ctx->force_general)
         return LaunchPairFast(a, which, n_per_clone);
     PairFullArgs args;

@@ -543,6 +543,129 @@ __global__ void __launch_bounds__(kFastThreads, 1) potential_fast_kernel(const P
     }
 }
 
+// ------------------------------------------------------------------------- K1 (Bare U, dU)
+struct BareFastArgs {
+    PathView pv;
+    SpeciesView A, B;
+    int same;
+    FastVTable T;
+    const unsigned char *tables;
+    double scale;              // tau for CalcU at level 0 (bare_pair_action_class.h:146-150), 1 for CalcdUdBeta
+    int n_chunks, n_pgroups, n_tsplit, t_windows;
+    double *partial;           // [C][n_chunks][n_pgroups][n_tsplit]
+};
+
+/// One distance's half of BarePairAction::CalcV (bare_pair_action_class.h:99-123):
+/// v(clamp_v r) / 2 - v_long(clamp_l clamp_v r) / 2.
+template <class Tab>
+__device__ __forceinline__ double BareHalfV(const Tab &tb, const FastVTable &T, double r) {
+    r = ClampRare(r, T.v);
+    double g = T.is_coulomb ? 0.5 / r : 0.5 * FastPP1Eval(tb, T.v, r);
+    if (T.use_lr) g = fma(-0.5, FastPP1Eval(tb, T.lr, ClampRare(r, T.lr)), g);
+    return g;
+}
+
+/// BarePairAction::CalcU / CalcdUdBeta over all pairs and links (pair_action_class.h:241-264,267-302
+/// with bare_pair_action_class.h:146-150,175-177): both are CalcV(r, r') of Path::DrDrpDrrp's
+/// distances -- r' in the image of r, unlike Potential().  Same decomposition as
+/// pair_full_fast_kernel; the half g(r') of a link is the next lane's g(r) whenever r' equals that
+/// r bit for bit (same image shift, the usual case), lane 31 parks its r' in the ring.
+__global__ void __launch_bounds__(kFastThreads, 1) bare_full_fast_kernel(const BareFastArgs a) {
+    extern __shared__ __align__(16) unsigned char fsm[];
+    __shared__ double red[kFastWarps];
+    __shared__ double ring[kFastWarps][32];
+    __shared__ unsigned long long stage_bar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *qpos = reinterpret_cast<double *>(fsm);               // [kFastRows][3][kFastRow]
+    unsigned char *tb_ptr = fsm + sizeof(double) * kFastRows * 3 * kFastRow;
+    const SharedTab tb(tb_ptr);
+    StageBlockTma(tb_ptr, a.tables, a.T.n_bytes, &stage_bar);
+    const PathView &pv = a.pv;
+    const int Na = a.A.N, Nb = a.B.N;
+    const int half = Na / 2;
+    const int n_dd = a.same ? half : Nb;
+    const int per_clone = a.n_chunks * a.n_pgroups * a.n_tsplit;
+    const int n_items = pv.C * per_clone;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int c = item / per_clone;
+        int rem = item - c * per_clone;
+        const int ts = rem % a.n_tsplit;
+        rem /= a.n_tsplit;
+        const int chunk = rem / a.n_pgroups, pg = rem - chunk * a.n_pgroups;
+        const int t_begin = ts * a.t_windows * kFastQ, t_end = min(n_dd, t_begin + a.t_windows * kFastQ);
+        const int s0 = chunk * kChunk;
+        const int p_lo = pg * kFastWarps;
+        const int p = p_lo + warp;
+        const bool warp_on = p < Na;
+        const bool lane_on = s0 + lane < pv.Mloc;
+        double p0[3] = {0., 0., 0.}, p1[3] = {0., 0., 0.};
+        if (warp_on && lane_on) {
+            const int i0 = s0 + lane, i1 = StoreIndex(pv, s0 + lane + 1);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                p0[d] = a.A.R[PosIndex(pv, Na, c, p, d, i0)];
+                p1[d] = a.A.R[PosIndex(pv, Na, c, p, d, i1)];
+            }
+        }
+        int my_dd = n_dd;
+        if (a.same && (Na & 1) == 0 && p >= half) my_dd = half - 1;
+        if (!warp_on) my_dd = 0;
+        double acc = 0.;
+        const bool lane31_counts = s0 + 31 < pv.Mloc;
+        for (int t0 = t_begin; t0 < t_end; t0 += kFastQ) {
+            const int n_rows = a.same ? min(kFastQ, n_dd - t0) + kFastWarps - 1 : min(kFastQ, Nb - t0);
+            const int q_first = a.same ? p_lo + t0 + 1 : t0;
+            __syncthreads();
+            for (int row = warp; row < n_rows * 3; row += kFastWarps) {
+                const int qq = row / 3, d = row - qq * 3;
+                int q = q_first + qq;
+                if (a.same) q %= Na;
+                const double *src = a.B.R + PosIndex(pv, Nb, c, q, d, 0);
+                const int i0 = StoreIndex(pv, s0 + lane);
+                qpos[row * kFastRow + lane] = i0 >= 0 ? src[i0] : 0.;
+                if (lane == 0) {
+                    const int i1 = StoreIndex(pv, s0 + kChunk);
+                    qpos[row * kFastRow + kChunk] = i1 >= 0 ? src[i1] : 0.;
+                }
+            }
+            __syncthreads();
+            const int n_step = min(kFastQ, my_dd - t0);
+            const double *rowp = qpos + (a.same ? warp * 3 * kFastRow : 0) + lane;
+            for (int i = 0; i < n_step; ++i, rowp += 3 * kFastRow) {
+                // r and r' of Path::DrDrpDrrp (the third magnitude is not used by CalcV)
+                double r2 = 0., rp2 = 0.;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    double r = rowp[d * kFastRow] - p0[d];
+                    double rp = rowp[d * kFastRow + 1] - p1[d];
+                    r = fma(-rint(r * pv.box.iL), pv.box.L, r);
+                    rp = fma(rint((r - rp) * pv.box.iL), pv.box.L, rp);
+                    r2 = d == 0 ? r * r : fma(r, r, r2);
+                    rp2 = d == 0 ? rp * rp : fma(rp, rp, rp2);
+                }
+                const double r_mag = FastSqrt(r2), rp_mag = FastSqrt(rp2);
+                const double g_r = BareHalfV(tb, a.T, r_mag);
+                const double r_next = __shfl_down_sync(0xffffffffu, r_mag, 1);
+                double g_p = __shfl_down_sync(0xffffffffu, g_r, 1);
+                if (lane == 31) {
+                    ring[warp][i] = rp_mag;
+                    g_p = 0.;
+                } else if (rp_mag != r_next) {
+                    g_p = BareHalfV(tb, a.T, rp_mag);
+                }
+                acc += lane_on ? g_r + g_p : 0.;
+            }
+            if (lane31_counts && n_step > 0) {  // the parked r' of lane 31, one per step
+                __syncwarp();
+                if (lane < n_step) acc += BareHalfV(tb, a.T, ring[warp][lane]);
+                __syncwarp();
+            }
+        }
+        const double tot = BlockSum<kFastThreads>(acc, red);
+        if (tid == 0) a.partial[item] = a.scale * tot;
+    }
+}
+
 /// Test hooks: the fast evaluation on caller-supplied triples (tables read from global memory
 /// through the same code) and the square root on its own.
 __global__ void calc_pair_fast_kernel(const unsigned char *__restrict__ tables, FastTable T, int n, const double *__restrict__ r,
