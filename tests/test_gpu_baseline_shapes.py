@@ -163,3 +163,43 @@ def test_headline_size_sweeps_keep_rhok_and_energy_consistent():
     assert np.array_equal(path.GetPositions(0), R)
     path.close()
     fresh.close()
+
+
+def test_config_c5_full_size_shards_sum_to_the_whole_path():
+    """BASELINE config C5 at full size (1024 e + 1024 p, M = 512, three Ilkka actions with long
+    range): the oracle would take minutes, so the checks are size-independent properties -- eight
+    slice shards (the 8-GPU layout, here on one device) sum to the unsharded DActionDBeta /
+    Potential / g(r) counts; a rigid translation, a lattice shift of individual paths and a
+    rotation of the imaginary-time origin leave the energies unchanged; every pair-slice lands in
+    the histogram when r_max exceeds the largest minimum-image distance."""
+    from simpimc_b200 import host, sharded
+    cfg = S.plasma_config(Ne=1024, Np=1024, M=512, n_xy=100, n_r_long=1000, pp_action="IlkkaPairAction")
+    Rs = [S.synthetic_paths(cfg, sp, 0, 777)[None] for sp in range(2)]
+    whole = host.Path(cfg, n_clones=1)
+
+    def evaluate(Rx):
+        for sp in range(2):
+            whole.SetPositions(sp, Rx[sp])
+        return np.array([[a.DActionDBeta()[0], a.Potential()[0]] for a in whole.actions])
+
+    base = evaluate(Rs)
+    counts = host.PairCorrelation(whole, 0, 1, 0.0, 0.9 * cfg.L, 200).Counts()[0]
+    assert counts.sum() == 1024 * 1024 * 512
+    parts = np.zeros_like(base)
+    counts_sh = np.zeros_like(counts)
+    for g in range(8):
+        sh = sharded.SliceSharding(cfg.n_bead, 8, g)
+        p = host.Path(cfg, n_clones=1, slice_lo=sh.lo, slice_hi=sh.hi)
+        for sp in range(2):
+            p.SetPositions(sp, sh.shard_positions(Rs[sp]))
+        parts += np.array([[a.DActionDBeta()[0], a.Potential()[0]] for a in p.actions])
+        counts_sh += host.PairCorrelation(p, 0, 1, 0.0, 0.9 * cfg.L, 200).Counts()[0]
+        p.close()
+    assert rel_ok(parts, base, rtol=1e-11), np.max(np.abs(parts - base) / np.abs(base))
+    assert np.array_equal(counts_sh, counts)
+    rng = np.random.default_rng(3)
+    shift = [rng.integers(-2, 3, size=(1, 1024, 1, 3)) * cfg.L for _ in range(2)]
+    for Rx in ([R + np.array([0.31, -7.0, 1.5]) for R in Rs], [R + s for R, s in zip(Rs, shift)], [np.roll(R, 101, axis=2) for R in Rs]):
+        got = evaluate(Rx)
+        assert rel_ok(got, base), np.max(np.abs(got - base) / np.abs(base))
+    whole.close()
