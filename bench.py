@@ -218,7 +218,7 @@ def run_ours(args):
     # host->device copy of one group overlaps the kernels of the previous one; every call is the
     # public C ABI with HOST buffers (pimc_positions_upload from pinned memory, pimc_action_dbeta
     # returning host doubles)
-    n_pipe = max(1, min(args.pipeline, C))
+    n_pipe = 1 if args.resident_only else max(1, min(args.pipeline, C))
     while C % n_pipe:
         n_pipe -= 1
     Cq = C // n_pipe
@@ -272,6 +272,14 @@ def run_ours(args):
     ms_max = float(t.item())
     evals_step = C * pair_evals_per_clone()
     value = world * evals_step * args.steps / (ms_max * 1e-3)
+    if args.resident_only:   # profiling aid (ncu launch list of the step kernels alone): not a bench line
+        if rank == 0:
+            print(json.dumps({"resident_only": True, "value": value, "ms_per_step": ms_max / args.steps,
+                              "kernel_ms": {"K1": k1_ms / max(1, k1_n), "K2": k2_ms / max(1, k2_n), "K3": k3_ms / max(1, k3_n)},
+                              "kernel_share_of_step": {"K1": k1_ms / ms_total, "K2": k2_ms / ms_total, "K3": k3_ms / ms_total}}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     # ---- end to end through the C ABI with host buffers -------------------------------------
     for _ in range(min(2, args.warmup)):
         step_e2e()
@@ -589,6 +597,7 @@ def main():
     ap.add_argument("--attempts", type=int, default=256, help="bisection attempts per clone timed for the MC-sweep figure")
     ap.add_argument("--pipeline", type=int, default=16, help="contexts the end-to-end leg splits the clones over (H2D/compute overlap)")
     ap.add_argument("--cpu-evals", type=int, default=8, help="DActionDBeta() calls per core for cpu_baseline (0 = skip)")
+    ap.add_argument("--resident-only", action="store_true", help="time the resident steps only and print a reduced line (profiling aid)")
     ap.add_argument("--workload", default="c3", choices=["c3", "c5"], help="c3: UEG N=256 M=128 x clones (headline); c5: plasma 1024+1024, M=512, slices sharded over the GPUs")
     ap.add_argument("--c5-n", type=int, default=1024)
     ap.add_argument("--c5-m", type=int, default=512)

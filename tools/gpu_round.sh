@@ -9,6 +9,7 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smok
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2>&1; echo "bench rc=$?" >> gpurun_out/bench.log
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1; echo "bench rc=$?" >> gpurun_out/bench_ref.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --cpu-evals 0 --attempts 4 > gpurun_out/bench_ncu.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_step.csv python bench.py --steps 5 --warmup 3 --resident-only > gpurun_out/bench_ncu_step.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:pair_full -s 1 -c 1 -o gpurun_out/prof_k1 -f python bench.py --steps 1 --warmup 1 --cpu-evals 0 --attempts 1 --clones 256 > gpurun_out/prof_k1.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:rhok_build -s 1 -c 1 -o gpurun_out/prof_k2 -f python bench.py --steps 1 --warmup 1 --cpu-evals 0 --attempts 1 --clones 256 > gpurun_out/prof_k2.log 2>&1
 bash tools/gpu_prof_sweep.sh
