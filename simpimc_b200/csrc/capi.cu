@@ -182,6 +182,10 @@ struct pimc_action {
     DevBuf<unsigned char> fastv_tab;
     FastVTable fastv;
     bool fastv_ok = false;
+    // David U / dU fast path: endpoint spline and off-diagonal multi-spline in shared memory
+    DevBuf<unsigned char> fastd_tab[2];
+    FastDavidTable fastd[2];
+    bool fastd_ok[2] = {false, false};
 };
 
 namespace {
@@ -668,6 +672,81 @@ int BuildFastV(pimc_ctx *ctx, pimc_action *a, const pimc_table_1d &v_r, int is_c
     return PIMC_OK;
 }
 
+/// Packs the shared-memory block of david_full_fast_kernel for U (which = WHICH_U) or dU/dbeta.
+/// values[v][g] = the multi-spline's data as the reference fills it (david...:262-283).  Leaves
+/// fastd_ok false when the grid admits neither interval table, n_order is outside 1..3 or the
+/// block does not fit in shared memory (the general kernel then evaluates the action).
+int BuildFastDavid(pimc_ctx *ctx, pimc_action *a, int which, const double *grid, int n, const std::vector<std::vector<double>> &values,
+                   int n_order, double r_min, double r_max) {
+    a->fastd_ok[which] = false;
+    FastDavidTable &T = a->fastd[which];
+    std::memset(&T, 0, sizeof(T));
+    if (n_order < 1 || n_order > 3) return PIMC_OK;
+    const int n_q = (int)values.size() - 2;
+    if (n_q != n_order * (n_order + 3) / 2) return PIMC_OK;
+    const int kMaxKeys = 16384;
+    ByteBlob blob;
+    ULut ul;
+    BLut bl;
+    if (BuildULut(grid, n, kMaxKeys, ul)) {
+        T.lut.kind = 0;
+        T.lut.off_lut = blob.Reserve(ul.lut.size() * sizeof(uint16_t));
+        std::memcpy(blob.At<uint16_t>(T.lut.off_lut), ul.lut.data(), ul.lut.size() * sizeof(uint16_t));
+        T.lut.key_max = (int)ul.lut.size() - 1;
+        T.lut.inv_h = ul.inv_h;
+    } else if (BuildBLut(grid, n, kMaxKeys, bl)) {
+        T.lut.kind = 1;
+        T.lut.off_lut = blob.Reserve(bl.lut.size() * sizeof(uint16_t));
+        std::memcpy(blob.At<uint16_t>(T.lut.off_lut), bl.lut.data(), bl.lut.size() * sizeof(uint16_t));
+        T.lut.key_max = (int)bl.lut.size() - 1;
+        T.lut.shift = bl.shift;
+        T.lut.key0 = bl.key0;
+    } else {
+        return PIMC_OK;
+    }
+    KnotBasis kb;
+    kb.Build(grid, n);
+    std::vector<double> coefs(n + 3, 0.0);
+    auto pp_of = [&](const std::vector<double> &data) {
+        std::fill(coefs.begin(), coefs.end(), 0.0);
+        SolveNatural(kb, data.data(), 1, coefs.data(), 1);
+        return PPFrom1D(kb, coefs.data());
+    };
+    T.off_gpair = AppendKnotPairs(blob, grid, n);
+    // endpoint: value 1; dU/dbeta adds the potential (value 0), david...:137-145
+    std::vector<double> pe = pp_of(values[1]);
+    if (which == WHICH_DU) {
+        const std::vector<double> p0 = pp_of(values[0]);
+        for (size_t i = 0; i < pe.size(); ++i) pe[i] += p0[i];
+    }
+    T.off_e01 = blob.Reserve((size_t)n * 16);
+    T.off_e23 = blob.Reserve((size_t)n * 16);
+    for (int i = 0; i < n; ++i) {
+        blob.At<double>(T.off_e01)[2 * i] = pe[4 * (size_t)i];
+        blob.At<double>(T.off_e01)[2 * i + 1] = pe[4 * (size_t)i + 1];
+        blob.At<double>(T.off_e23)[2 * i] = pe[4 * (size_t)i + 2];
+        blob.At<double>(T.off_e23)[2 * i + 1] = pe[4 * (size_t)i + 3];
+    }
+    T.q_stride = 32 * n_q + 16;  // 2 n_q + 1 sixteen-byte slots: odd, neighbouring intervals fall into disjoint banks
+    T.off_q = blob.Reserve((size_t)n * T.q_stride);
+    for (int v = 0; v < n_q; ++v) {
+        const std::vector<double> pq = pp_of(values[v + 2]);
+        for (int i = 0; i < n; ++i)
+            std::memcpy(blob.b.data() + T.off_q + (size_t)i * T.q_stride + 32 * (size_t)v, &pq[4 * (size_t)i], 32);
+    }
+    blob.b.resize((blob.b.size() + 15) & ~(size_t)15, 0);
+    const size_t need = sizeof(double) * kFastRows * 3 * kFastRow + blob.b.size() + 10240;  // + the kernel's static shared memory
+    if (need > ctx->smem_optin) return PIMC_OK;
+    T.n_order = n_order;
+    T.r_min = r_min;
+    T.r_max = r_max;
+    T.n_bytes = (int)blob.b.size();
+    PIMC_CUDA(a->fastd_tab[which].Alloc(blob.b.size()));
+    PIMC_CUDA(cudaMemcpy(a->fastd_tab[which].p, blob.b.data(), blob.b.size(), cudaMemcpyHostToDevice));
+    a->fastd_ok[which] = true;
+    return PIMC_OK;
+}
+
 // ------------------------------------------------------------------------------ launchers
 template <int ATYPE, int WHICH>
 int LaunchPairFullT(pimc_ctx *ctx, const PairFullArgs &args, size_t smem, int grid) {
@@ -786,6 +865,47 @@ int LaunchBareFast(pimc_action *a, int which, int *n_per_clone) {
     return PIMC_OK;
 }
 
+template <int NORD, int KIND>
+int LaunchDavidFastT(pimc_ctx *ctx, const DavidFastArgs &args, size_t smem, int grid) {
+    PIMC_CUDA(cudaFuncSetAttribute(david_full_fast_kernel<NORD, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        ScopedKernelTimer t(ctx, PIMC_KERNEL_PAIR_FULL);
+        david_full_fast_kernel<NORD, KIND><<<grid, kFastThreads, smem, ctx->stream>>>(args);
+    }
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    return PIMC_OK;
+}
+
+/// David U / dU/dbeta over the whole path with every table in shared memory.
+int LaunchDavidFast(pimc_action *a, int which, int *n_per_clone) {
+    pimc_ctx *ctx = a->ctx;
+    DavidFastArgs args;
+    args.pv = ctx->View();
+    args.A = ctx->SView(a->sa, false);
+    args.B = ctx->SView(a->sb, false);
+    args.same = a->sa == a->sb;
+    args.T = a->fastd[which];
+    args.tables = a->fastd_tab[which].p;
+    args.n_chunks = (ctx->Mloc + kChunk - 1) / kChunk;
+    FastItems(ctx, args.A.N, args.B.N, args.same != 0, args.n_chunks, args.n_pgroups, args.n_tsplit, args.t_windows);
+    *n_per_clone = args.n_chunks * args.n_pgroups * args.n_tsplit;
+    const size_t items = (size_t)ctx->C * *n_per_clone;
+    if (ctx->partial.n < items) PIMC_CUDA(ctx->partial.Alloc(items));
+    args.partial = ctx->partial.p;
+    const size_t smem = sizeof(double) * kFastRows * 3 * kFastRow + (size_t)args.T.n_bytes;
+    const int grid = (int)std::min<size_t>(items, (size_t)ctx->n_sm);
+    const int key = args.T.n_order * 2 + args.T.lut.kind;
+    switch (key) {
+        case 2: return LaunchDavidFastT<1, 0>(ctx, args, smem, grid);
+        case 3: return LaunchDavidFastT<1, 1>(ctx, args, smem, grid);
+        case 4: return LaunchDavidFastT<2, 0>(ctx, args, smem, grid);
+        case 5: return LaunchDavidFastT<2, 1>(ctx, args, smem, grid);
+        case 6: return LaunchDavidFastT<3, 0>(ctx, args, smem, grid);
+        default: return LaunchDavidFastT<3, 1>(ctx, args, smem, grid);
+    }
+}
+
 int LaunchPairFull(pimc_action *a, int which, bool independent_images, int *n_per_clone) {
     pimc_ctx *ctx = a->ctx;
     if (which == WHICH_V && independent_images && a->fastv_ok && !ctx->force_general) return LaunchPotentialFast(a, n_per_clone);
@@ -793,6 +913,8 @@ int LaunchPairFull(pimc_action *a, int which, bool independent_images, int *n_pe
         return LaunchBareFast(a, which, n_per_clone);
     if (a->atype == ATYPE_ILKKA && which != WHICH_V && !independent_images && a->fast_ok[which] && !ctx->force_general)
         return LaunchPairFast(a, which, n_per_clone);
+    if (a->atype == ATYPE_DAVID && which != WHICH_V && !independent_images && a->fastd_ok[which] && !ctx->force_general)
+        return LaunchDavidFast(a, which, n_per_clone);
     PairFullArgs args;
     args.pv = ctx->View();
     args.A = ctx->SView(a->sa, false);
@@ -1329,6 +1451,10 @@ int pimc_action_create_david(pimc_ctx *ctx, int32_t sa, int32_t sb, const pimc_d
             if (rc != PIMC_OK) return rc;
             T.dav_blob = a->blob[which].p;
             a->stageable[which] = false;
+            if (which != WHICH_V) {
+                rc = BuildFastDavid(ctx, a, which, grid.data(), n, values, t->n_order, T.dav.r_min, T.dav.r_max);
+                if (rc != PIMC_OK) return rc;
+            }
         }
     } catch (const std::exception &e) {
         return Fail(PIMC_ERR_TABLE, e.what());
@@ -2260,7 +2386,8 @@ int pimc_est_sofk(pimc_ctx *ctx, int32_t sa, int32_t sb, double k_cut, const dou
 int pimc_action_calc_pair_fast(pimc_action *act, int32_t which, int32_t n, const double *r, const double *r_p, const double *s,
                                double *out) {
     if (!act || !r || !r_p || !s || !out || n < 0 || which < 0 || which > 1) return Fail(PIMC_ERR_INVALID, "bad argument");
-    if (act->atype != ATYPE_ILKKA || !act->fast_ok[which]) return Fail(PIMC_ERR_UNSUPPORTED, "action has no fast-path tables");
+    const bool david = act->atype == ATYPE_DAVID && act->fastd_ok[which];
+    if (!david && (act->atype != ATYPE_ILKKA || !act->fast_ok[which])) return Fail(PIMC_ERR_UNSUPPORTED, "action has no fast-path tables");
     if (n == 0) return PIMC_OK;
     pimc_ctx *ctx = act->ctx;
     PIMC_CUDA(cudaSetDevice(ctx->device));
@@ -2269,8 +2396,25 @@ int pimc_action_calc_pair_fast(pimc_action *act, int32_t which, int32_t n, const
     PIMC_CUDA(cudaMemcpyAsync(buf.p, r, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     PIMC_CUDA(cudaMemcpyAsync(buf.p + n, r_p, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     PIMC_CUDA(cudaMemcpyAsync(buf.p + 2 * (size_t)n, s, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    calc_pair_fast_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(act->fast_tab[which].p, act->fast[which], n, buf.p, buf.p + n,
-                                                                    buf.p + 2 * (size_t)n, buf.p + 3 * (size_t)n);
+    if (david) {
+        const FastDavidTable &T = act->fastd[which];
+        const unsigned char *tab = act->fastd_tab[which].p;
+        double *pr = buf.p, *pp = buf.p + n, *ps = buf.p + 2 * (size_t)n, *po = buf.p + 3 * (size_t)n;
+        const int grid = (n + 127) / 128;
+#define PIMC_DAVID_HOOK(NORD, KIND) calc_david_fast_kernel<NORD, KIND><<<grid, 128, 0, ctx->stream>>>(tab, T, n, pr, pp, ps, po)
+        switch (T.n_order * 2 + T.lut.kind) {
+            case 2: PIMC_DAVID_HOOK(1, 0); break;
+            case 3: PIMC_DAVID_HOOK(1, 1); break;
+            case 4: PIMC_DAVID_HOOK(2, 0); break;
+            case 5: PIMC_DAVID_HOOK(2, 1); break;
+            case 6: PIMC_DAVID_HOOK(3, 0); break;
+            default: PIMC_DAVID_HOOK(3, 1); break;
+        }
+#undef PIMC_DAVID_HOOK
+    } else {
+        calc_pair_fast_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(act->fast_tab[which].p, act->fast[which], n, buf.p, buf.p + n,
+                                                                        buf.p + 2 * (size_t)n, buf.p + 3 * (size_t)n);
+    }
     ctx->launches++;
     PIMC_CUDA(cudaGetLastError());
     return ToHost(ctx, buf.p + 3 * (size_t)n, out, n);

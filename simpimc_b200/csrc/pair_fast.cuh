@@ -666,12 +666,224 @@ __global__ void __launch_bounds__(kFastThreads, 1) bare_full_fast_kernel(const B
     }
 }
 
+// ------------------------------------------------------------------------- K1 (David U, dU)
+/// Interval table of the David grid.  kind 0: uniform buckets (ULookup's key).  kind 1: buckets of
+/// the IEEE-754 bit pattern, key = (high word of x >> shift) - key0 -- the exponent and the top
+/// 20 - shift mantissa bits, i.e. buckets of constant RELATIVE width, which is what a
+/// logarithmic grid (the David squarer's usual choice) needs: a uniform table fine enough for
+/// its first interval would not fit.  Either way lut[key] is the interval of the bucket's lower
+/// edge and at most one knot lies inside a bucket.
+struct FastLut {
+    int kind;
+    int off_lut, key_max;
+    int shift, key0;
+    double inv_h;
+};
+/// DavidPairAction tables in the shared-memory layout: the endpoint spline e(r) (value 1 of the
+/// multi-spline for U; value 0 + value 1 for dU/dbeta, david...:137-145) as split (c0,c1)/(c2,c3)
+/// arrays, and one record per interval holding the pp coefficients of the n_q = n_val - 1
+/// off-diagonal values u_kj(q) (32 bytes each, record stride an odd number of 16-byte slots).
+struct FastDavidTable {
+    FastLut lut;
+    int off_gpair;        // double2 [n]: (g[i], g[i+1]); g[n] = +inf
+    int off_e01, off_e23; // double2 [n] each
+    int off_q, q_stride;  // bytes
+    int n_order;
+    double r_min, r_max;
+    int n_bytes;
+};
+
+template <int KIND, class Tab>
+__device__ __forceinline__ void DLookup(const Tab &tb, const FastLut &L, int off_gpair, double x, int &i, double &t) {
+    int key;
+    if (KIND == 0) {
+        key = min(__double2loint(fma(x, L.inv_h, kRoundMagic)), L.key_max);
+    } else {
+        key = min(max((__double2hiint(x) >> L.shift) - L.key0, 0), L.key_max);
+    }
+    const int i0 = tb.LdU16(L.off_lut + 2 * key);
+    const double2 g = tb.LdV2(off_gpair + 16 * i0);
+    const bool up = x >= g.y;
+    i = up ? i0 + 1 : i0;
+    t = x - (up ? g.y : g.x);
+}
+
+/// e(x) for x already inside [r_min, r_max].
+template <int KIND, class Tab>
+__device__ __forceinline__ double DavidEndpoint(const Tab &tb, const FastDavidTable &T, double x) {
+    int i;
+    double t;
+    DLookup<KIND>(tb, T.lut, T.off_gpair, x, i, t);
+    const double2 c01 = tb.LdV2(T.off_e01 + 16 * i);
+    const double2 c23 = tb.LdV2(T.off_e23 + 16 * i);
+    return fma(fma(fma(c23.y, t, c23.x), t, c01.y), t, c01.x);
+}
+
+/// The off-diagonal sum of DavidPairAction::CalcU / CalcdUdBeta (david...:80-99, 146-165):
+/// sum_{k=1..n_order} sum_{j=0..k} u_kj(q) z^(2j) s^(2(k-j)), terms in the reference's order.  The
+/// reference walks the powers of s down by multiplying with 1/s^2; here s^(2m) and z^(2j) are
+/// built upward by multiplication (no division), which differs by rounding only.
+template <int NORD, int KIND, class Tab>
+__device__ __forceinline__ double DavidOffDiagonal(const Tab &tb, const FastDavidTable &T, double q, double z, double s) {
+    int i;
+    double t;
+    DLookup<KIND>(tb, T.lut, T.off_gpair, q, i, t);
+    const int base = T.off_q + i * T.q_stride;
+    double sp[NORD + 1], zp[NORD + 1];
+    sp[0] = 1.;
+    zp[0] = 1.;
+    const double s_2 = s * s, z_2 = z * z;
+#pragma unroll
+    for (int m = 1; m <= NORD; ++m) {
+        sp[m] = sp[m - 1] * s_2;
+        zp[m] = zp[m - 1] * z_2;
+    }
+    double u = 0.;
+    int v = 0;
+#pragma unroll
+    for (int k = 1; k <= NORD; ++k) {
+#pragma unroll
+        for (int j = 0; j <= k; ++j, ++v) {
+            const double2 c01 = tb.LdV2(base + 32 * v);
+            const double2 c23 = tb.LdV2(base + 32 * v + 16);
+            const double cof = fma(fma(fma(c23.y, t, c23.x), t, c01.y), t, c01.x);
+            u = fma(cof, zp[j] * sp[k - j], u);
+        }
+    }
+    return u;
+}
+
+/// DavidPairAction::CalcU / CalcdUdBeta for one (r, r', s) triple (test hook and ring flush).
+template <int NORD, int KIND, class Tab>
+__device__ __forceinline__ double FastDavidEval(const Tab &tb, const FastDavidTable &T, double r, double r_p, double s) {
+    const double q = 0.5 * (r + r_p), z = r - r_p;  // before the clamp (david...:65-70)
+    double u = 0.5 * DavidEndpoint<KIND>(tb, T, Clamp(r, T.r_min, T.r_max));
+    u = fma(0.5, DavidEndpoint<KIND>(tb, T, Clamp(r_p, T.r_min, T.r_max)), u);
+    if (s > 0.0 && q < T.r_max) u += DavidOffDiagonal<NORD, KIND>(tb, T, q, z, s);
+    return u;
+}
+
+struct DavidFastArgs {
+    PathView pv;
+    SpeciesView A, B;
+    int same;
+    FastDavidTable T;
+    const unsigned char *tables;
+    int n_chunks, n_pgroups, n_tsplit, t_windows;
+    double *partial;  // [C][n_chunks][n_pgroups][n_tsplit]
+};
+
+/// DavidPairAction::CalcU / CalcdUdBeta over all pairs and links (pair_action_class.h:241-264,
+/// 267-302 with david_pair_action_class.h:63-102,126-168).  Decomposition of
+/// pair_full_fast_kernel; the endpoint half e(r')/2 of a link is the next lane's e(r)/2 whenever r'
+/// equals that r bit for bit (same image shift between the two slices, the usual case), lane 31
+/// parks its r' in the ring and the warp evaluates the parked values together.
+template <int NORD, int KIND>
+__global__ void __launch_bounds__(kFastThreads, 1) david_full_fast_kernel(const DavidFastArgs a) {
+    extern __shared__ __align__(16) unsigned char fsm[];
+    __shared__ double red[kFastWarps];
+    __shared__ double ring[kFastWarps][32];
+    __shared__ unsigned long long stage_bar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *qpos = reinterpret_cast<double *>(fsm);               // [kFastRows][3][kFastRow]
+    unsigned char *tb_ptr = fsm + sizeof(double) * kFastRows * 3 * kFastRow;
+    const SharedTab tb(tb_ptr);
+    StageBlockTma(tb_ptr, a.tables, a.T.n_bytes, &stage_bar);
+    const PathView &pv = a.pv;
+    const int Na = a.A.N, Nb = a.B.N;
+    const int half = Na / 2;
+    const int n_dd = a.same ? half : Nb;
+    const int per_clone = a.n_chunks * a.n_pgroups * a.n_tsplit;
+    const int n_items = pv.C * per_clone;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int c = item / per_clone;
+        int rem = item - c * per_clone;
+        const int ts = rem % a.n_tsplit;
+        rem /= a.n_tsplit;
+        const int chunk = rem / a.n_pgroups, pg = rem - chunk * a.n_pgroups;
+        const int t_begin = ts * a.t_windows * kFastQ, t_end = min(n_dd, t_begin + a.t_windows * kFastQ);
+        const int s0 = chunk * kChunk;
+        const int p_lo = pg * kFastWarps;
+        const int p = p_lo + warp;
+        const bool warp_on = p < Na;
+        const bool lane_on = s0 + lane < pv.Mloc;
+        double p0[3] = {0., 0., 0.}, p1[3] = {0., 0., 0.};
+        if (warp_on && lane_on) {
+            const int i0 = s0 + lane, i1 = StoreIndex(pv, s0 + lane + 1);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                p0[d] = a.A.R[PosIndex(pv, Na, c, p, d, i0)];
+                p1[d] = a.A.R[PosIndex(pv, Na, c, p, d, i1)];
+            }
+        }
+        int my_dd = n_dd;
+        if (a.same && (Na & 1) == 0 && p >= half) my_dd = half - 1;
+        if (!warp_on) my_dd = 0;
+        double acc = 0.;
+        const bool lane31_counts = s0 + 31 < pv.Mloc;
+        for (int t0 = t_begin; t0 < t_end; t0 += kFastQ) {
+            const int n_rows = a.same ? min(kFastQ, n_dd - t0) + kFastWarps - 1 : min(kFastQ, Nb - t0);
+            const int q_first = a.same ? p_lo + t0 + 1 : t0;
+            __syncthreads();
+            for (int row = warp; row < n_rows * 3; row += kFastWarps) {
+                const int qq = row / 3, d = row - qq * 3;
+                int q = q_first + qq;
+                if (a.same) q %= Na;
+                const double *src = a.B.R + PosIndex(pv, Nb, c, q, d, 0);
+                const int i0 = StoreIndex(pv, s0 + lane);
+                qpos[row * kFastRow + lane] = i0 >= 0 ? src[i0] : 0.;
+                if (lane == 0) {
+                    const int i1 = StoreIndex(pv, s0 + kChunk);
+                    qpos[row * kFastRow + kChunk] = i1 >= 0 ? src[i1] : 0.;
+                }
+            }
+            __syncthreads();
+            const int n_step = min(kFastQ, my_dd - t0);
+            const double *rowp = qpos + (a.same ? warp * 3 * kFastRow : 0) + lane;
+            for (int i = 0; i < n_step; ++i, rowp += 3 * kFastRow) {
+                const double b0[3] = {rowp[0], rowp[kFastRow], rowp[2 * kFastRow]};
+                const double b1[3] = {rowp[1], rowp[kFastRow + 1], rowp[2 * kFastRow + 1]};
+                double r, rp, s;
+                DrDrpDrrpFast(p0, b0, p1, b1, pv.box, r, rp, s);
+                const double q = 0.5 * (r + rp), z = r - rp;  // before the clamp (david...:65-70)
+                double rc = r;
+                if (__any_sync(0xffffffffu, r < a.T.r_min || r > a.T.r_max)) rc = Clamp(r, a.T.r_min, a.T.r_max);
+                const double e_r = DavidEndpoint<KIND>(tb, a.T, rc);
+                const double r_next = __shfl_down_sync(0xffffffffu, r, 1);
+                double e_p = __shfl_down_sync(0xffffffffu, e_r, 1);
+                if (lane == 31) {
+                    ring[warp][i] = rp;
+                    e_p = 0.;
+                } else if (rp != r_next) {
+                    e_p = DavidEndpoint<KIND>(tb, a.T, Clamp(rp, a.T.r_min, a.T.r_max));
+                }
+                double u = 0.5 * (e_r + e_p);
+                if (s > 0.0 && q < a.T.r_max) u += DavidOffDiagonal<NORD, KIND>(tb, a.T, q, z, s);
+                acc += lane_on ? u : 0.;
+            }
+            if (lane31_counts && n_step > 0) {  // the parked r' of lane 31, one per step
+                __syncwarp();
+                if (lane < n_step) acc = fma(0.5, DavidEndpoint<KIND>(tb, a.T, Clamp(ring[warp][lane], a.T.r_min, a.T.r_max)), acc);
+                __syncwarp();
+            }
+        }
+        const double tot = BlockSum<kFastThreads>(acc, red);
+        if (tid == 0) a.partial[item] = tot;
+    }
+}
+
 /// Test hooks: the fast evaluation on caller-supplied triples (tables read from global memory
 /// through the same code) and the square root on its own.
 __global__ void calc_pair_fast_kernel(const unsigned char *__restrict__ tables, FastTable T, int n, const double *__restrict__ r,
                                       const double *__restrict__ rp, const double *__restrict__ s, double *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = FastIlkkaEval(GlobalTab(tables), T, r[i], rp[i], s[i]);
+}
+template <int NORD, int KIND>
+__global__ void calc_david_fast_kernel(const unsigned char *__restrict__ tables, FastDavidTable T, int n, const double *__restrict__ r,
+                                       const double *__restrict__ rp, const double *__restrict__ s, double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = FastDavidEval<NORD, KIND>(GlobalTab(tables), T, r[i], rp[i], s[i]);
 }
 __global__ void fast_sqrt_kernel(int n, const double *__restrict__ x, double *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

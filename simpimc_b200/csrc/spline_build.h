@@ -360,6 +360,62 @@ inline bool BuildULut(const double *g, int n, int max_keys, ULut &out) {
     return true;
 }
 
+/// Bit-pattern interval table for the fast David kernel: bucket k holds every x >= 0 whose
+/// (high 32 bits >> shift) equals k + key0, i.e. one exponent value and the top (20 - shift)
+/// mantissa bits -- buckets of constant relative width 2^-(20-shift), the natural partner of a
+/// logarithmic grid.  lut[k] = interval of the bucket's lower edge; the smallest number of
+/// mantissa bits that leaves at most one knot per bucket is chosen.  Keys are clamped on the
+/// device to [0, n_keys-1]: bucket 0 holds the grid start (everything below it maps to interval
+/// 0), the last bucket lies wholly above the grid end (interval n-1).
+struct BLut {
+    int shift = 0, key0 = 0;
+    std::vector<uint16_t> lut;
+};
+
+inline bool BuildBLut(const double *g, int n, int max_keys, BLut &out) {
+    if (n < 2 || n > 65535 || !(g[0] > 0.)) return false;
+    for (int i = 1; i < n; ++i)
+        if (!(g[i] > g[i - 1])) return false;
+    auto hi_word = [](double x) {
+        uint64_t b;
+        std::memcpy(&b, &x, sizeof(b));
+        return (long long)(b >> 32);
+    };
+    auto from_hi = [](long long hi) {
+        const uint64_t b = (uint64_t)hi << 32;
+        double x;
+        std::memcpy(&x, &b, sizeof(x));
+        return x;
+    };
+    auto interval = [&](double x) {
+        if (x <= g[0]) return 0;
+        if (x >= g[n - 1]) return n - 1;
+        return (int)(std::upper_bound(g, g + n, x) - g) - 1;
+    };
+    for (int mant = 0; mant <= 14; ++mant) {
+        const int shift = 20 - mant;
+        const long long k_first = hi_word(g[0]) >> shift, k_last = (hi_word(g[n - 1]) >> shift) + 1;
+        const long long n_keys = k_last - k_first + 1;
+        if (n_keys > (long long)max_keys) return false;
+        std::vector<uint16_t> lut((std::size_t)n_keys);
+        bool ok = true;
+        for (long long k = 0; k < n_keys && ok; ++k) {
+            const double lo = from_hi((k + k_first) << shift);
+            const double hi = std::nextafter(from_hi((k + k_first + 1) << shift), 0.0);  // largest x of the bucket
+            const int i_lo = interval(lo), i_hi = interval(hi);
+            if (i_hi - i_lo > 1) ok = false;
+            lut[(std::size_t)k] = (uint16_t)i_lo;
+        }
+        if (!ok) continue;
+        if (lut.back() != n - 1 || lut.front() != 0) return false;
+        out.shift = shift;
+        out.key0 = (int)k_first;
+        out.lut.swap(lut);
+        return true;
+    }
+    return false;
+}
+
 }  // namespace pimc
 
 #endif  // SIMPIMC_B200_SPLINE_BUILD_H_

@@ -71,7 +71,7 @@ def ueg_parameters(N, rs=1.0, theta=1.0, polarized=True):
 
 
 def ueg_config(N=256, M=128, rs=1.0, theta=1.0, action="IlkkaPairAction", use_long_range=True, n_xy=100, n_r_long=1000,
-               with_kinetic=False):
+               with_kinetic=False, david_grid="LOG", david_n_grid=200, david_n_order=2):
     """Uniform electron gas, one species "e" (SURVEY.md 8(d), config C3 at the defaults)."""
     L, k_cut, beta = ueg_parameters(N, rs, theta)
     tau = beta / M
@@ -84,12 +84,12 @@ def ueg_config(N=256, M=128, rs=1.0, theta=1.0, action="IlkkaPairAction", use_lo
     elif action == "BarePairAction":
         tab = T.make_bare_table(1.0, L, k_cut, use_long_range=use_long_range, n_r_long=n_r_long)
     elif action == "DavidPairAction":
-        tab = T.make_david_table(1.0, tau, n_order=2, r_end=0.95 * math.sqrt(3.0) * L / 2.0, L=L, k_cut=k_cut,
-                                 use_long_range=use_long_range)
+        tab = T.make_david_table(1.0, tau, n_order=david_n_order, grid_type=david_grid, n_grid=david_n_grid,
+                                 r_end=0.95 * math.sqrt(3.0) * L / 2.0, L=L, k_cut=k_cut, use_long_range=use_long_range)
     else:
         raise ValueError(action)
     cfg.actions.append(ActionConfig("CoulombEE", action, "e", "e", table=tab, max_level=0, use_long_range=use_long_range,
-                                    k_cut=k_cut, n_order=2 if action == "DavidPairAction" else 0))
+                                    k_cut=k_cut, n_order=david_n_order if action == "DavidPairAction" else 0))
     return cfg
 
 

@@ -46,6 +46,13 @@ CONFIGS = {
     "david_lr_n7": lambda: S.ueg_config(N=7, M=8, action="DavidPairAction", use_long_range=True),
     "plasma": lambda: S.plasma_config(Ne=6, Np=5, M=8),
     "n2": lambda: S.ueg_config(N=2, M=4),
+    # David tables on a linear grid (uniform interval table), M > 32 (two slice chunks, lane-31 ring), even N
+    "david_lin_n34": lambda: S.ueg_config(N=34, M=40, action="DavidPairAction", use_long_range=False, david_grid="LINEAR",
+                                          david_n_grid=120),
+    "david_log_n33": lambda: S.ueg_config(N=33, M=40, action="DavidPairAction", use_long_range=True),
+    "david_o1_n9": lambda: S.ueg_config(N=9, M=8, action="DavidPairAction", use_long_range=False, david_n_order=1),
+    "david_o3_n9": lambda: S.ueg_config(N=9, M=8, action="DavidPairAction", use_long_range=False, david_n_order=3,
+                                        david_grid="LINEAR", david_n_grid=90),
 }
 
 
@@ -258,10 +265,12 @@ def test_errors_are_loud():
     shard.close()
 
 
-@pytest.mark.parametrize("name", ["ilkka_lr_n7", "ilkka_lr_n33", "ilkka_nolr_n8", "plasma", "n2"])
+@pytest.mark.parametrize("name", ["ilkka_lr_n7", "ilkka_lr_n33", "ilkka_nolr_n8", "plasma", "n2", "david_n7", "david_lr_n7",
+                                  "david_lin_n34", "david_log_n33", "david_o1_n9", "david_o3_n9"])
 def test_fast_and_general_kernels_agree_with_oracle(name):
-    """The whole-path Ilkka evaluation runs through the fast kernel (pair_fast.cuh) by default;
-    the general kernel is kept for the other action types.  Both must match the oracle."""
+    """The whole-path Ilkka, Bare and David evaluations run through the shared-memory fast kernels
+    (pair_fast.cuh) by default; the general kernel stays for tables the fast layouts cannot hold.
+    Both must match the oracle."""
     cfg = CONFIGS[name]()
     path, oracles, _ = make_pair(cfg, 3)
     for general in (False, True):
@@ -297,6 +306,46 @@ def test_fast_per_pair_matches_oracle_and_general():
     r[300:310] = np.linspace(20.0, 99.0, 10)
     rp[300:310] = r[300:310] + 0.3
     s[300:310] = 0.5
+    act = path.actions[0]
+    for which in (0, 1):
+        fast = act.CalcPairFast(which, r, rp, s)
+        gen = act.CalcPair(which, r, rp, s)
+        ref = oracles[0].calc_pair(0, which, r, rp, s)
+        scale = 1e-3 * np.max(np.abs(ref))
+        assert rel_ok(fast, ref, scale=scale), (which, np.max(np.abs(fast - ref)))
+        assert rel_ok(fast, gen, scale=scale)
+    path.close()
+
+
+@pytest.mark.parametrize("name", ["david_n7", "david_lin_n34", "david_o1_n9", "david_o3_n9"])
+def test_david_fast_per_pair_matches_oracle_and_general(name):
+    """DavidPairAction::CalcU / CalcdUdBeta through the fast kernel's tables (pp-form multi-spline,
+    bit-pattern or uniform interval table) on triples that include the knots themselves, both grid
+    ends, distances outside the grid on either side (SetLimits), s = 0 (no off-diagonal term) and
+    q >= r_max (david_pair_action_class.h:80)."""
+    cfg = CONFIGS[name]()
+    path, oracles, _ = make_pair(cfg, 1)
+    rng = np.random.default_rng(6)
+    n = 20000
+    tab = cfg.actions[0].table
+    grp = "u_kj_%d" % cfg.actions[0].n_order
+    r0, r1, ng = float(tab[grp + "/grid/start"]), float(tab[grp + "/grid/end"]), int(tab[grp + "/grid/n_grid_points"])
+    if tab[grp + "/grid/type"] == "LOG":
+        knots = r0 * np.exp(np.arange(ng) * (np.log(r1 / r0) / (ng - 1)))
+    else:
+        knots = np.linspace(r0, r1, ng)
+    r = rng.uniform(0.2 * r0, 1.1 * r1, n)
+    rp = np.clip(r + rng.normal(0, 0.1, n), 0.1 * r0, 1.2 * r1)
+    s = np.abs(r - rp) + np.abs(rng.normal(0, 0.05, n))
+    r[:ng] = knots
+    rp[:ng] = knots
+    s[:ng] = 0.0
+    r[ng:2 * ng] = knots
+    rp[ng:2 * ng] = np.roll(knots, 1)
+    s[ng:2 * ng] = 0.3
+    r[2 * ng:2 * ng + 4] = [r1, r1, 0.5 * r0, 1.5 * r1]
+    rp[2 * ng:2 * ng + 4] = [r1, 0.999 * r1, 0.5 * r0, 1.5 * r1]
+    s[2 * ng:2 * ng + 4] = [0.1, 0.0, 1e-5, 0.2]
     act = path.actions[0]
     for which in (0, 1):
         fast = act.CalcPairFast(which, r, rp, s)
