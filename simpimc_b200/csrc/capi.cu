@@ -621,9 +621,13 @@ int BuildFastIlkka(pimc_ctx *ctx, pimc_action *a, int which, const pimc_table_2d
 }
 
 /// One pp-form 1-D spline in the fast shared-memory layout; false if the grid admits no uniform interval table.
-bool AppendFastPP1(ByteBlob &blob, FastPP1 &d, const pimc_table_1d &f, int max_keys) {
+bool AppendFastPP1(ByteBlob &blob, FastPP1 &d, const pimc_table_1d &f, int max_keys, int *kind = nullptr) {
     ULut lut;
-    if (!BuildULut(f.r, f.n, max_keys, lut)) return false;
+    BLut blut;
+    const bool uniform = BuildULut(f.r, f.n, max_keys, lut);
+    // callers that pass `kind` can evaluate through the bit-pattern table as well (FastLut)
+    if (!uniform && !(kind && BuildBLut(f.r, f.n, max_keys, blut))) return false;
+    if (kind) *kind = uniform ? 0 : 1;
     KnotBasis kb;
     kb.Build(f.r, f.n);
     std::vector<double> coefs(f.n + 3, 0.0);
@@ -638,14 +642,23 @@ bool AppendFastPP1(ByteBlob &blob, FastPP1 &d, const pimc_table_1d &f, int max_k
         blob.At<double>(d.off_c23)[2 * i] = pp[4 * (size_t)i + 2];
         blob.At<double>(d.off_c23)[2 * i + 1] = pp[4 * (size_t)i + 3];
     }
-    AppendULut(blob, d.lut, lut);
+    if (uniform) {
+        AppendULut(blob, d.lut, lut);
+    } else {
+        d.lut.off_lut = blob.Reserve(blut.lut.size() * sizeof(uint16_t));
+        std::memcpy(blob.At<uint16_t>(d.lut.off_lut), blut.lut.data(), blut.lut.size() * sizeof(uint16_t));
+        d.lut.key_max = (int)blut.lut.size() - 1;
+        d.lut.inv_h = 0.;
+        d.lut.shift = blut.shift;
+        d.lut.key0 = blut.key0;
+    }
     d.r_min = f.r[0];
     d.r_max = f.r[f.n - 1];
     return true;
 }
 
-/// Tables of potential_fast_kernel for an Ilkka or Bare action; fastv_ok stays false when a grid
-/// does not admit the uniform interval table or the block does not fit in shared memory.
+/// Tables of potential_fast_kernel for an Ilkka, Bare or David action; fastv_ok stays false when a
+/// grid admits no interval table (uniform; for v also bit-pattern) or the block does not fit in shared memory.
 int BuildFastV(pimc_ctx *ctx, pimc_action *a, const pimc_table_1d &v_r, int is_coulomb, const pimc_long_range *lr) {
     a->fastv_ok = false;
     FastVTable &T = a->fastv;
@@ -653,14 +666,15 @@ int BuildFastV(pimc_ctx *ctx, pimc_action *a, const pimc_table_1d &v_r, int is_c
     ByteBlob blob;
     const int kMaxKeys = 16384;
     T.is_coulomb = is_coulomb ? 1 : 0;
-    T.use_lr = a->use_long_range ? 1 : 0;
+    const bool use_lr = a->use_long_range && lr != nullptr;  // David has no r-space long-range part (lr == nullptr)
+    T.use_lr = use_lr ? 1 : 0;
     if (is_coulomb) {  // analytic 1/r: only the clamp limits of the (unused) table matter
         T.v.r_min = v_r.r[0];
         T.v.r_max = v_r.r[v_r.n - 1];
-    } else if (!AppendFastPP1(blob, T.v, v_r, kMaxKeys)) {
+    } else if (!AppendFastPP1(blob, T.v, v_r, kMaxKeys, &T.v_kind)) {
         return PIMC_OK;
     }
-    if (a->use_long_range && !AppendFastPP1(blob, T.lr, lr->f_r, kMaxKeys)) return PIMC_OK;
+    if (use_lr && !AppendFastPP1(blob, T.lr, lr->f_r, kMaxKeys)) return PIMC_OK;
     blob.b.resize((blob.b.size() + 15) & ~(size_t)15, 0);
     if (blob.b.empty()) blob.b.resize(16, 0);
     const size_t need = sizeof(double) * kFastRows * 3 * kFastRow + blob.b.size() + 10240;  // + static shared memory (ring, red) of the kernels that use it
@@ -825,11 +839,12 @@ int LaunchPotentialFast(pimc_action *a, int *n_per_clone) {
     if (ctx->partial.n < items) PIMC_CUDA(ctx->partial.Alloc(items));
     args.partial = ctx->partial.p;
     const size_t smem = sizeof(double) * kFastRows * 3 * kFastRow + (size_t)args.T.n_bytes;
-    PIMC_CUDA(cudaFuncSetAttribute(potential_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto *kernel = args.T.v_kind == 1 ? potential_fast_kernel<1> : potential_fast_kernel<0>;
+    PIMC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)std::min<size_t>(items, (size_t)ctx->n_sm);
     {
         ScopedKernelTimer t(ctx, PIMC_KERNEL_PAIR_FULL);
-        potential_fast_kernel<<<grid, kFastThreads, smem, ctx->stream>>>(args);
+        kernel<<<grid, kFastThreads, smem, ctx->stream>>>(args);
     }
     ctx->launches++;
     PIMC_CUDA(cudaGetLastError());
@@ -909,7 +924,7 @@ int LaunchDavidFast(pimc_action *a, int which, int *n_per_clone) {
 int LaunchPairFull(pimc_action *a, int which, bool independent_images, int *n_per_clone) {
     pimc_ctx *ctx = a->ctx;
     if (which == WHICH_V && independent_images && a->fastv_ok && !ctx->force_general) return LaunchPotentialFast(a, n_per_clone);
-    if (a->atype == ATYPE_BARE && which != WHICH_V && !independent_images && a->fastv_ok && !ctx->force_general)
+    if (a->atype == ATYPE_BARE && which != WHICH_V && !independent_images && a->fastv_ok && a->fastv.v_kind == 0 && !ctx->force_general)
         return LaunchBareFast(a, which, n_per_clone);
     if (a->atype == ATYPE_ILKKA && which != WHICH_V && !independent_images && a->fast_ok[which] && !ctx->force_general)
         return LaunchPairFast(a, which, n_per_clone);
@@ -1454,6 +1469,16 @@ int pimc_action_create_david(pimc_ctx *ctx, int32_t sa, int32_t sb, const pimc_d
             if (which != WHICH_V) {
                 rc = BuildFastDavid(ctx, a, which, grid.data(), n, values, t->n_order, T.dav.r_min, T.dav.r_max);
                 if (rc != PIMC_OK) return rc;
+            } else {
+                // CalcV = value 0 of the multi-spline at r and r' (david...:26-39): the fast Potential() kernel's v table
+                pimc_table_1d v0;
+                v0.n = n;
+                v0.r = grid.data();
+                v0.f = values[0].data();
+                rc = BuildFastV(ctx, a, v0, 0, nullptr);
+                if (rc != PIMC_OK) return rc;
+                a->fastv.v.r_min = T.dav.r_min;  // the LOG grid clamps to its nominal start / end (GetLimits)
+                a->fastv.v.r_max = T.dav.r_max;
             }
         }
     } catch (const std::exception &e) {

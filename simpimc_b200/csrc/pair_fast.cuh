@@ -44,6 +44,7 @@ struct ULutDesc {
     int off_lut;    // uint16 [n_keys]
     int key_max;    // n_keys - 1
     double inv_h;   // 1 / bucket width
+    int shift, key0;  // bit-pattern buckets (KIND 1, see FastLut): key = (high word of x >> shift) - key0
 };
 struct FastPP1 {
     ULutDesc lut;
@@ -131,11 +132,15 @@ __device__ __forceinline__ void StageBlockTma(void *smem_dst, const void *gsrc, 
 
 /// Interval of x >= 0 and tau = x - g[interval].  `clamp_key`: x may lie beyond the grid end
 /// (keys above the table are clamped to its last bucket, whose interval is the last one).
-template <class Tab>
+template <class Tab, int KIND = 0>
 __device__ __forceinline__ void ULookup(const Tab &tb, const ULutDesc &L, int off_gpair, double x, bool clamp_key, int &i, double &t) {
-    const double kd = fma(x, L.inv_h, kRoundMagic);
-    int key = __double2loint(kd);
-    if (clamp_key) key = min(key, L.key_max);
+    int key;
+    if (KIND == 0) {
+        key = __double2loint(fma(x, L.inv_h, kRoundMagic));
+        if (clamp_key) key = min(key, L.key_max);
+    } else {
+        key = min(max((__double2hiint(x) >> L.shift) - L.key0, 0), L.key_max);
+    }
     const int i0 = tb.LdU16(L.off_lut + 2 * key);
     const double2 g = tb.LdV2(off_gpair + 16 * i0);
     const bool up = x >= g.y;
@@ -144,11 +149,11 @@ __device__ __forceinline__ void ULookup(const Tab &tb, const ULutDesc &L, int of
 }
 
 /// x must already lie inside [r_min, r_max] (SetLimits).
-template <class Tab>
+template <class Tab, int KIND = 0>
 __device__ __forceinline__ double FastPP1Eval(const Tab &tb, const FastPP1 &d, double x) {
     int i;
     double t;
-    ULookup(tb, d.lut, d.off_gpair, x, false, i, t);
+    ULookup<Tab, KIND>(tb, d.lut, d.off_gpair, x, false, i, t);
     const double2 c01 = tb.LdV2(d.off_c01 + 16 * i);
     const double2 c23 = tb.LdV2(d.off_c23 + 16 * i);
     return fma(fma(fma(c23.y, t, c23.x), t, c01.y), t, c01.x);
@@ -450,6 +455,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) pair_full_fast_kernel(const P
 struct FastVTable {
     FastPP1 v, lr;
     int use_lr, is_coulomb;
+    int v_kind;  // interval table of v: 0 uniform buckets, 1 bit-pattern buckets (David's logarithmic grid)
     int n_bytes;
 };
 
@@ -464,8 +470,9 @@ struct PotFastArgs {
     double *partial;           // [C][n_chunks][n_pgroups][n_tsplit]
 };
 
-/// PairAction::Potential (pair_action_class.h:369-395) for Ilkka / Bare CalcV
-/// (ilkka_pair_action_class.h:34-54, bare_pair_action_class.h:99-123).  Potential() measures r at
+/// PairAction::Potential (pair_action_class.h:369-395) for Ilkka / Bare / David CalcV
+/// (ilkka_pair_action_class.h:34-54, bare_pair_action_class.h:99-123, david_pair_action_class.h:26-39:
+/// value 0 of the multi-spline, no r-space long-range part).  Potential() measures r at
 /// slice b and r' at slice b + 1 with INDEPENDENT minimum images (App. A-6), so r' of link
 /// (b, b+1) is exactly r of link (b+1, b+2): with g(r) = v(clamp_v(r))/2 - v_long(clamp_l(clamp_v(r)))/2
 /// the sum over links of g(r) + g(r') is the sum over slices of w_s g(r_s), w_s = number of the
@@ -473,6 +480,7 @@ struct PotFastArgs {
 /// One distance and two 1-D lookups per pair and slice instead of two and four.  Same work
 /// decomposition as pair_full_fast_kernel (warp = particle of species a, lanes = slices,
 /// partner rows staged per window of 32 offsets).
+template <int KIND>
 __global__ void __launch_bounds__(kFastThreads, 1) potential_fast_kernel(const PotFastArgs a) {
     extern __shared__ __align__(16) unsigned char fsm[];
     __shared__ double red[kFastWarps];
@@ -533,7 +541,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) potential_fast_kernel(const P
                 }
                 double r = FastSqrt(fma(dr[1], dr[1], fma(dr[2], dr[2], dr[0] * dr[0])));
                 r = ClampRare(r, a.T.v);
-                double g = a.T.is_coulomb ? 0.5 / r : 0.5 * FastPP1Eval(tb, a.T.v, r);
+                double g = a.T.is_coulomb ? 0.5 / r : 0.5 * FastPP1Eval<SharedTab, KIND>(tb, a.T.v, r);
                 if (a.T.use_lr) g = fma(-0.5, FastPP1Eval(tb, a.T.lr, ClampRare(r, a.T.lr)), g);
                 acc = fma(weight, g, acc);
             }

@@ -281,6 +281,10 @@ def test_fast_and_general_kernels_agree_with_oracle(name):
             for c, o in enumerate(oracles):
                 assert rel_ok(du[c], o.dbeta(ai)), (name, general, ai, c, du[c], o.dbeta(ai))
                 assert rel_ok(u[c], o.get_action(ai, 0, 0, cfg.n_bead, parts, 0)), (name, general, ai, c)
+            if not (cfg.actions[ai].type == "DavidPairAction" and cfg.actions[ai].use_long_range):
+                v = act.Potential()   # fast: one distance per pair and slice (independent images), every family
+                for c, o in enumerate(oracles):
+                    assert rel_ok(v[c], o.potential(ai)), (name, general, ai, c, v[c], o.potential(ai))
     path.close()
 
 
