@@ -33,6 +33,10 @@
 #ifndef PIMC_EXPERIMENT
 #define PIMC_EXPERIMENT 0
 #endif
+// partner steps per trip of K1's inner loop (A/B: 2 with 512 threads x 128 registers, tools/gpu_ab.sh)
+#ifndef PIMC_K1_UNROLL
+#define PIMC_K1_UNROLL 1
+#endif
 
 namespace pimc {
 
@@ -340,6 +344,7 @@ __device__ __forceinline__ void LdsBeadPair(uint32_t addr, double b0[3], double 
 #define PIMC_FAST_THREADS 1024
 #endif
 constexpr int kFastThreads = PIMC_FAST_THREADS;
+constexpr int kK1Unroll = PIMC_K1_UNROLL;
 constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kFastQ = 32;                         // partner offsets handled per staged window
 constexpr int kFastRows = kFastQ + kFastWarps - 1; // window rows (same species: sliding window)
@@ -427,6 +432,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) pair_full_fast_kernel(const P
             __syncthreads();
             const int n_step = min(kFastQ, my_dd - t0);
             const double *rowp = qpos + (a.same ? warp * 3 * kFastRow : 0) + lane;
+#pragma unroll kK1Unroll
             for (int i = 0; i < n_step; ++i, rowp += 3 * kFastRow) {
                 const double b0[3] = {rowp[0], rowp[kFastRow], rowp[2 * kFastRow]};
                 const double b1[3] = {rowp[1], rowp[kFastRow + 1], rowp[2 * kFastRow + 1]};

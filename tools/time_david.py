@@ -1,11 +1,11 @@
 """Times the whole-path evaluations of the other two action families at the C3 shape (256 clones),
 through the shared-memory fast kernels and (David) through the general kernel."""
-import sys, time
+import os, sys, time
 import numpy as np
 sys.path.insert(0, ".")
 from simpimc_b200 import host, system as S
 for action, lr, kw in (("DavidPairAction", False, {}), ("DavidPairAction", False, {"david_grid": "LINEAR", "david_n_grid": 400}),
-                       ("BarePairAction", True, {})):
+                       ("BarePairAction", True, {}))[:1 if os.environ.get("TIME_DAVID_FIRST_ONLY") else 3]:
     cfg = S.ueg_config(N=256, M=128, action=action, use_long_range=lr, **kw)
     C = 256
     path = host.Path(cfg, n_clones=C)
