@@ -93,7 +93,7 @@ def ueg_config(N=256, M=128, rs=1.0, theta=1.0, action="IlkkaPairAction", use_lo
     return cfg
 
 
-def plasma_config(Ne=8, Np=8, M=16, rs=1.0, theta=1.0, n_xy=60, n_r_long=400, pp_action="BarePairAction"):
+def plasma_config(Ne=8, Np=8, M=16, rs=1.0, theta=1.0, n_xy=60, n_r_long=400, pp_action="BarePairAction", ep_action="IlkkaPairAction"):
     """Two-species hydrogen-like plasma (config C5 shape at reduced size): e-e, e-p Ilkka
     actions and a p-p action -- Bare by default (as inputs/C/c.xml mixes the types), Ilkka with
     pp_action="IlkkaPairAction" -- all with long range."""
@@ -104,8 +104,18 @@ def plasma_config(Ne=8, Np=8, M=16, rs=1.0, theta=1.0, n_xy=60, n_r_long=400, pp
     cfg.species.append(SpeciesConfig("p", Np, 0.5 / 1836.15267))
     cfg.actions.append(ActionConfig("CoulombEE", "IlkkaPairAction", "e", "e", max_level=0, use_long_range=True, k_cut=k_cut,
                                     table=T.make_ilkka_table(1.0, tau, L, k_cut, n_xy=n_xy, n_r_long=n_r_long)))
-    cfg.actions.append(ActionConfig("CoulombEP", "IlkkaPairAction", "e", "p", max_level=0, use_long_range=True, k_cut=k_cut,
-                                    table=T.make_ilkka_table(-1.0, tau, L, k_cut, n_xy=n_xy, n_r_long=n_r_long, sigma=0.4)))
+    r_end = 0.95 * math.sqrt(3.0) * L / 2.0
+    if ep_action == "DavidPairAction":   # a David e-p action (different species), no long range
+        cfg.actions.append(ActionConfig("CoulombEP", "DavidPairAction", "e", "p", max_level=0, use_long_range=False, k_cut=k_cut, n_order=2,
+                                        table=T.make_david_table(-1.0, tau, n_order=2, r_end=r_end, L=L, k_cut=k_cut, sigma=0.4)))
+    else:
+        cfg.actions.append(ActionConfig("CoulombEP", "IlkkaPairAction", "e", "p", max_level=0, use_long_range=True, k_cut=k_cut,
+                                        table=T.make_ilkka_table(-1.0, tau, L, k_cut, n_xy=n_xy, n_r_long=n_r_long, sigma=0.4)))
+    if pp_action == "DavidPairAction":
+        cfg.actions.append(ActionConfig("CoulombPP", "DavidPairAction", "p", "p", max_level=0, use_long_range=False, k_cut=k_cut, n_order=2,
+                                        table=T.make_david_table(1.0, tau, n_order=2, grid_type="LINEAR", n_grid=150, r_end=r_end, L=L,
+                                                                 k_cut=k_cut, sigma=0.3)))
+        return cfg
     if pp_action == "IlkkaPairAction":
         pp_table = T.make_ilkka_table(1.0, tau, L, k_cut, n_xy=n_xy, n_r_long=n_r_long, sigma=0.3)
     else:

@@ -50,6 +50,8 @@ CONFIGS = {
     "david_lin_n34": lambda: S.ueg_config(N=34, M=40, action="DavidPairAction", use_long_range=False, david_grid="LINEAR",
                                           david_n_grid=120),
     "david_log_n33": lambda: S.ueg_config(N=33, M=40, action="DavidPairAction", use_long_range=True),
+    # Ilkka e-e, David e-p (different species) and David p-p on a linear grid; M > 32
+    "plasma_david": lambda: S.plasma_config(Ne=6, Np=5, M=36, pp_action="DavidPairAction", ep_action="DavidPairAction"),
     "david_o1_n9": lambda: S.ueg_config(N=9, M=8, action="DavidPairAction", use_long_range=False, david_n_order=1),
     "david_o3_n9": lambda: S.ueg_config(N=9, M=8, action="DavidPairAction", use_long_range=False, david_n_order=3,
                                         david_grid="LINEAR", david_n_grid=90),
@@ -266,7 +268,7 @@ def test_errors_are_loud():
 
 
 @pytest.mark.parametrize("name", ["ilkka_lr_n7", "ilkka_lr_n33", "ilkka_nolr_n8", "plasma", "n2", "david_n7", "david_lr_n7",
-                                  "david_lin_n34", "david_log_n33", "david_o1_n9", "david_o3_n9"])
+                                  "david_lin_n34", "david_log_n33", "david_o1_n9", "david_o3_n9", "plasma_david"])
 def test_fast_and_general_kernels_agree_with_oracle(name):
     """The whole-path Ilkka, Bare and David evaluations run through the shared-memory fast kernels
     (pair_fast.cuh) by default; the general kernel stays for tables the fast layouts cannot hold.
@@ -374,8 +376,9 @@ def test_fast_sqrt_within_one_ulp():
     path.close()
 
 
+@pytest.mark.parametrize("david", [False, True])
 @pytest.mark.parametrize("n_shards", [2, 4])
-def test_slice_sharded_contexts_sum_to_the_whole_path(n_shards):
+def test_slice_sharded_contexts_sum_to_the_whole_path(n_shards, david):
     """Slice-sharded contexts (one per GPU in production; here all on cuda:0): each shard's
     partial DActionDBeta / Potential / action, g(r) counts and S(k) sum to the unsharded values
     and match the oracle; halo pack/unpack moves the right slice."""
@@ -383,7 +386,7 @@ def test_slice_sharded_contexts_sum_to_the_whole_path(n_shards):
     import torch
     from simpimc_b200 import host, sharded, capi
     from oracle import oracle as O
-    cfg = S.plasma_config(Ne=6, Np=5, M=16)
+    cfg = S.plasma_config(Ne=6, Np=5, M=16, **({"pp_action": "DavidPairAction", "ep_action": "DavidPairAction"} if david else {}))
     n_clones = 2
     Rs = [np.stack([S.synthetic_paths(cfg, sp, c, 4242) for c in range(n_clones)]) for sp in range(2)]
     oracles = []
