@@ -67,6 +67,16 @@ class _Keep:
         return a.ctypes.data_as(c_double_p)
 
 
+
+def _f(x):
+    """Scalar dataset (a 0-d value, or the 1-element array the flat table container stores) -> float."""
+    return float(np.asarray(x).reshape(-1)[0])
+
+
+def _i(x):
+    return int(np.asarray(x).reshape(-1)[0])
+
+
 def _t1(keep, r, f):
     return Table1D(len(r), keep.ptr(r), keep.ptr(f))
 
@@ -79,8 +89,8 @@ def _lr(keep, t, obj, present):
     if not present:
         return LongRange()
     p = obj + "/diag/"
-    return LongRange(_t1(keep, t[p + "r_long"], t[p + obj + "_long_r"]), float(t[p + obj + "_long_r_0"]), int(t[p + "n_k"]),
-                     keep.ptr(t[p + "k"]), keep.ptr(t[p + obj + "_long_k"]), float(t[p + obj + "_long_k_0"]))
+    return LongRange(_t1(keep, t[p + "r_long"], t[p + obj + "_long_r"]), _f(t[p + obj + "_long_r_0"]), _i(t[p + "n_k"]),
+                     keep.ptr(t[p + "k"]), keep.ptr(t[p + obj + "_long_k"]), _f(t[p + obj + "_long_k_0"]))
 
 
 def pack_ilkka(t, use_long_range):
@@ -113,9 +123,9 @@ def pack_david(t, n_order, use_long_range):
     s.grid_type = GRID_LOG if ("LOG" in gt and "LOGLIN" not in gt) else (GRID_LINEAR if "LINEAR" in gt else GRID_GENERAL)
     if "LOGLIN" in gt:
         raise ValueError("LOGLIN grids are fork-only in the reference's einspline and not supported")
-    s.r_start = float(t[g + "/grid/start"])
-    s.r_end = float(t[g + "/grid/end"])
-    s.n_grid = int(t[g + "/grid/n_grid_points"])
+    s.r_start = _f(t[g + "/grid/start"])
+    s.r_end = _f(t[g + "/grid/end"])
+    s.n_grid = _i(t[g + "/grid/n_grid_points"])
     s.grid_points = keep.ptr(t[g + "/grid/grid_points"])
     s.n_order = n_order
     s.n_tau = len(t[g + "/taus"])
@@ -124,10 +134,10 @@ def pack_david(t, n_order, use_long_range):
     s.du_kj_dbeta = keep.ptr(t["du_kj_dbeta_%d/data" % n_order])
     s.potential = keep.ptr(t["potential/data"])
     if use_long_range:
-        s.n_k = int(t["long_range/n_k"])
+        s.n_k = _i(t["long_range/n_k"])
         s.k_points = keep.ptr(t["long_range/k_points"])
         s.u_k = keep.ptr(t["long_range/u_k"])
-        s.v_image = float(t["squarer/v_image"])
+        s.v_image = _f(t["squarer/v_image"])
     return s, keep
 
 
