@@ -1469,6 +1469,11 @@ int pimc_action_create_david(pimc_ctx *ctx, int32_t sa, int32_t sb, const pimc_d
             if (which != WHICH_V) {
                 rc = BuildFastDavid(ctx, a, which, grid.data(), n, values, t->n_order, T.dav.r_min, T.dav.r_max);
                 if (rc != PIMC_OK) return rc;
+                if (a->fastd_ok[which]) {  // every other kernel reads the same block from global memory
+                    T.dav_fast = a->fastd[which];
+                    T.dav_fast_tab = a->fastd_tab[which].p;
+                    T.dav_use_fast = ctx->force_general ? 0 : 1;
+                }
             } else {
                 // CalcV = value 0 of the multi-spline at r and r' (david...:26-39): the fast Potential() kernel's v table
                 pimc_table_1d v0;
@@ -2461,6 +2466,9 @@ int pimc_debug_fast_sqrt(pimc_ctx *ctx, int32_t n, const double *x, double *out)
 int pimc_ctx_force_general(pimc_ctx *ctx, int32_t enable) {
     if (!ctx) return Fail(PIMC_ERR_INVALID, "null context");
     ctx->force_general = enable != 0;
+    for (pimc_action *a : ctx->actions)
+        if (a->atype == ATYPE_DAVID)
+            for (int which = 0; which < 2; ++which) a->table[which].dav_use_fast = (!ctx->force_general && a->fastd_ok[which]) ? 1 : 0;
     return PIMC_OK;
 }
 

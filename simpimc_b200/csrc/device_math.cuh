@@ -56,6 +56,32 @@ struct PP2Desc {
     LutDesc lutx, luty;
     const double *cells;
 };
+/// Interval table of the David grid.  kind 0: uniform buckets (ULookup's key).  kind 1: buckets of
+/// the IEEE-754 bit pattern, key = (high word of x >> shift) - key0 -- the exponent and the top
+/// 20 - shift mantissa bits, i.e. buckets of constant RELATIVE width, which is what a
+/// logarithmic grid (the David squarer's usual choice) needs: a uniform table fine enough for
+/// its first interval would not fit.  Either way lut[key] is the interval of the bucket's lower
+/// edge and at most one knot lies inside a bucket.
+struct FastLut {
+    int kind;
+    int off_lut, key_max;
+    int shift, key0;
+    double inv_h;
+};
+/// DavidPairAction tables in the shared-memory layout: the endpoint spline e(r) (value 1 of the
+/// multi-spline for U; value 0 + value 1 for dU/dbeta, david...:137-145) as split (c0,c1)/(c2,c3)
+/// arrays, and one record per interval holding the pp coefficients of the n_q = n_val - 1
+/// off-diagonal values u_kj(q) (32 bytes each, record stride an odd number of 16-byte slots).
+struct FastDavidTable {
+    FastLut lut;
+    int off_gpair;        // double2 [n]: (g[i], g[i+1]); g[n] = +inf
+    int off_e01, off_e23; // double2 [n] each
+    int off_q, q_stride;  // bytes
+    int n_order;
+    double r_min, r_max;
+    int n_bytes;
+};
+
 /// Everything a pair kernel needs to evaluate one of U / dU/dbeta / V of one action.
 struct PairTable {
     int use_lr;
@@ -67,6 +93,12 @@ struct PairTable {
     PP1Desc lr;          // long-range r-space spline subtracted from the short-range part
     Sp1Desc dav;         // David multi-spline (B-spline form) ...
     const double *dav_blob;  // ... in global memory
+    // David U / dU: the pp-form block of the fast whole-path kernel, read through the read-only
+    // path by every other kernel (windows, displacements, per-pair hooks) unless the context
+    // forces the general B-spline evaluation
+    int dav_use_fast;
+    const unsigned char *dav_fast_tab;
+    FastDavidTable dav_fast;
 };
 
 // nearbyint() in the default rounding mode is round-half-even == rint()
@@ -190,6 +222,64 @@ __device__ __forceinline__ double PP2Eval(const double *__restrict__ blob, const
     return fma(fma(fma(row[3], tx, row[2]), tx, row[1]), tx, row[0]);
 }
 
+/// Interval lookup on the David fast tables held in GLOBAL memory (see DLookup in pair_fast.cuh
+/// for the shared-memory twin); the table kind is a run-time value here.
+__device__ __forceinline__ void DavidLookupGlobal(const unsigned char *__restrict__ tb, const FastLut &L, int off_gpair, double x, int &i,
+                                                  double &t) {
+    int key;
+    if (L.kind == 0)
+        key = min(__double2loint(fma(x, L.inv_h, 6755399441055744.0)), L.key_max);  // 2^52 + 2^51: round to nearest integer
+    else
+        key = min(max((__double2hiint(x) >> L.shift) - L.key0, 0), L.key_max);
+    const int i0 = __ldg(reinterpret_cast<const unsigned short *>(tb + L.off_lut) + key);
+    const double2 g = __ldg(reinterpret_cast<const double2 *>(tb + off_gpair) + i0);
+    const bool up = x >= g.y;
+    i = up ? i0 + 1 : i0;
+    t = x - (up ? g.y : g.x);
+}
+
+__device__ __forceinline__ double DavidEndpointGlobal(const unsigned char *__restrict__ tb, const FastDavidTable &T, double x) {
+    x = x > T.r_max ? T.r_max : (x < T.r_min ? T.r_min : x);
+    int i;
+    double t;
+    DavidLookupGlobal(tb, T.lut, T.off_gpair, x, i, t);
+    const double2 c01 = __ldg(reinterpret_cast<const double2 *>(tb + T.off_e01) + i);
+    const double2 c23 = __ldg(reinterpret_cast<const double2 *>(tb + T.off_e23) + i);
+    return fma(fma(fma(c23.y, t, c23.x), t, c01.y), t, c01.x);
+}
+
+/// DavidPairAction::CalcU / CalcdUdBeta (david_pair_action_class.h:63-102,126-168) in pp form from
+/// the fast kernel's table block; n_order (1..3) and the table kind are run-time values.
+__device__ __forceinline__ double DavidFastGlobal(const unsigned char *__restrict__ tb, const FastDavidTable &T, double r, double r_p,
+                                                  double s) {
+    const double q = 0.5 * (r + r_p), z = r - r_p;  // before the clamp (david...:65-70)
+    double u = 0.5 * DavidEndpointGlobal(tb, T, r);
+    u = fma(0.5, DavidEndpointGlobal(tb, T, r_p), u);
+    if (s > 0.0 && q < T.r_max) {
+        int i;
+        double t;
+        DavidLookupGlobal(tb, T.lut, T.off_gpair, q, i, t);
+        const double2 *rec = reinterpret_cast<const double2 *>(tb + T.off_q + (size_t)i * T.q_stride);
+        const double s_2 = s * s, z_2 = z * z;
+        double sp[4] = {1., s_2, s_2 * s_2, s_2 * s_2 * s_2}, zp[4] = {1., z_2, z_2 * z_2, z_2 * z_2 * z_2};
+        int v = 0;
+        double od = 0.;
+#pragma unroll
+        for (int k = 1; k <= 3; ++k) {
+            if (k <= T.n_order) {
+#pragma unroll
+                for (int j = 0; j <= k; ++j, ++v) {
+                    const double2 c01 = __ldg(rec + 2 * v), c23 = __ldg(rec + 2 * v + 1);
+                    const double cof = fma(fma(fma(c23.y, t, c23.x), t, c01.y), t, c01.x);
+                    od = fma(cof, zp[j] * sp[k - j], od);
+                }
+            }
+        }
+        u += od;
+    }
+    return u;
+}
+
 /// CalcV of the three action families.
 template <int ATYPE>
 __device__ __forceinline__ double PairV(const double *__restrict__ blob, const PairTable &T, double r, double r_p) {
@@ -242,6 +332,7 @@ __device__ __forceinline__ double PairEval(const double *__restrict__ blob, cons
         return u;
     }
     // David: endpoint term plus the off-diagonal polynomial in z^2 and s^2
+    if (T.dav_use_fast) return DavidFastGlobal(T.dav_fast_tab, T.dav_fast, r, r_p, s);
     const double *db = T.dav_blob;
     const double q = 0.5 * (r + r_p);
     const double z = r - r_p;

@@ -681,32 +681,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) bare_full_fast_kernel(const B
 }
 
 // ------------------------------------------------------------------------- K1 (David U, dU)
-/// Interval table of the David grid.  kind 0: uniform buckets (ULookup's key).  kind 1: buckets of
-/// the IEEE-754 bit pattern, key = (high word of x >> shift) - key0 -- the exponent and the top
-/// 20 - shift mantissa bits, i.e. buckets of constant RELATIVE width, which is what a
-/// logarithmic grid (the David squarer's usual choice) needs: a uniform table fine enough for
-/// its first interval would not fit.  Either way lut[key] is the interval of the bucket's lower
-/// edge and at most one knot lies inside a bucket.
-struct FastLut {
-    int kind;
-    int off_lut, key_max;
-    int shift, key0;
-    double inv_h;
-};
-/// DavidPairAction tables in the shared-memory layout: the endpoint spline e(r) (value 1 of the
-/// multi-spline for U; value 0 + value 1 for dU/dbeta, david...:137-145) as split (c0,c1)/(c2,c3)
-/// arrays, and one record per interval holding the pp coefficients of the n_q = n_val - 1
-/// off-diagonal values u_kj(q) (32 bytes each, record stride an odd number of 16-byte slots).
-struct FastDavidTable {
-    FastLut lut;
-    int off_gpair;        // double2 [n]: (g[i], g[i+1]); g[n] = +inf
-    int off_e01, off_e23; // double2 [n] each
-    int off_q, q_stride;  // bytes
-    int n_order;
-    double r_min, r_max;
-    int n_bytes;
-};
-
+// FastLut / FastDavidTable (the David tables' shared-memory layout) are declared in device_math.cuh.
 template <int KIND, class Tab>
 __device__ __forceinline__ void DLookup(const Tab &tb, const FastLut &L, int off_gpair, double x, int &i, double &t) {
     int key;

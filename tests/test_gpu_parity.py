@@ -354,12 +354,17 @@ def test_david_fast_per_pair_matches_oracle_and_general(name):
     s[2 * ng:2 * ng + 4] = [0.1, 0.0, 1e-5, 0.2]
     act = path.actions[0]
     for which in (0, 1):
-        fast = act.CalcPairFast(which, r, rp, s)
-        gen = act.CalcPair(which, r, rp, s)
+        fast = act.CalcPairFast(which, r, rp, s)      # templated evaluation of the whole-path kernel
+        path.ForceGeneral(False)
+        glob = act.CalcPair(which, r, rp, s)          # run-time twin every other kernel uses (DavidFastGlobal)
+        path.ForceGeneral(True)
+        gen = act.CalcPair(which, r, rp, s)           # B-spline form (Cox-de Boor), the reference's own formulation
+        path.ForceGeneral(False)
         ref = oracles[0].calc_pair(0, which, r, rp, s)
         scale = 1e-3 * np.max(np.abs(ref))
         assert rel_ok(fast, ref, scale=scale), (which, np.max(np.abs(fast - ref)))
-        assert rel_ok(fast, gen, scale=scale)
+        assert rel_ok(gen, ref, scale=scale), (which, np.max(np.abs(gen - ref)))
+        assert rel_ok(fast, glob, scale=scale, rtol=1e-13), (which, np.max(np.abs(fast - glob)))   # same tables, same arithmetic
     path.close()
 
 

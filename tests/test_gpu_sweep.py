@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name,general", [("ueg", False), ("ueg", True), ("plasma", False), ("nolr", False), ("nolr", True), ("ueg4", False),
-                                          ("carbon", False)])
+                                          ("carbon", False), ("david", False), ("david", True), ("plasma_david", False)])
 def test_device_sweep_follows_the_host_mirror_of_its_stream(name, general):
     """general = False: the single-launch sweep (csrc/sweep_fused.cuh) where it applies (ueg, nolr,
     ueg4: one same-species Ilkka action), the kernel-per-phase path otherwise (plasma);
@@ -29,6 +29,10 @@ def test_device_sweep_follows_the_host_mirror_of_its_stream(name, general):
         cfg, n_level = S.ueg_config(N=37, M=32), 4
     elif name == "nolr":
         cfg, n_level = S.ueg_config(N=6, M=8, use_long_range=False), 2
+    elif name == "david":      # general = False: the pp-form tables of the fast David kernel, read from global memory
+        cfg, n_level = S.ueg_config(N=7, M=16, action="DavidPairAction", use_long_range=True), 3
+    elif name == "plasma_david":
+        cfg, n_level = S.plasma_config(Ne=5, Np=4, M=8, pp_action="DavidPairAction", ep_action="DavidPairAction"), 2
     elif name == "carbon":
         cfg, n_level = S.carbon_config(), 2     # BASELINE config C4: 4 species, 9 Ilkka + 1 Bare action, all long-range
     else:
@@ -353,7 +357,8 @@ def test_slice_sharded_sweeps_follow_the_host_mirror_and_rotate(name, n_shards):
         o.close()
 
 
-@pytest.mark.parametrize("name,general", [("ueg", False), ("ueg", True), ("plasma", False), ("bare", False), ("nolr", False)])
+@pytest.mark.parametrize("name,general", [("ueg", False), ("ueg", True), ("plasma", False), ("bare", False), ("nolr", False),
+                                          ("david", False), ("david", True), ("plasma_david", False)])
 def test_device_displace_follows_the_host_mirror_of_its_stream(name, general):
     """pimc_displace_sweep (csrc/displace.cuh): DisplaceParticle::DoEvent on the device.  The host
     mirror draws the same Philox numbers and takes the whole-path OLD / NEW actions from the CPU
@@ -366,6 +371,10 @@ def test_device_displace_follows_the_host_mirror_of_its_stream(name, general):
         cfg, step = S.ueg_config(N=6, M=8, action="BarePairAction"), 1.2
     elif name == "nolr":
         cfg, step = S.ueg_config(N=6, M=8, use_long_range=False), 1.0
+    elif name == "david":      # general = False: the pp-form tables of the fast David kernel, read from global memory
+        cfg, step = S.ueg_config(N=6, M=8, action="DavidPairAction", use_long_range=True), 1.0
+    elif name == "plasma_david":
+        cfg, step = S.plasma_config(Ne=5, Np=4, M=8, pp_action="DavidPairAction", ep_action="DavidPairAction"), 0.8
     else:
         cfg, step = S.plasma_config(Ne=5, Np=4, M=8), 0.8
     C = 3
