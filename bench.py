@@ -368,6 +368,34 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    # ---- the other two action families at the same shape (whole-path kernel times, 256 clones) ----
+    families = None
+    if world == 1 and args.cpu_evals > 0:   # skipped in the profiling runs (--cpu-evals 0)
+        families = {"unit": "kernel ms per whole-path evaluation of %d clones (CUDA events), UEG N=%d M=%d" % (min(C, 256), N_PART, N_SLICE)}
+        try:
+            Cf = min(C, 256)
+            for fam, kw in (("BarePairAction", dict(use_long_range=True)), ("DavidPairAction", dict(use_long_range=False))):
+                fcfg = S.ueg_config(N=N_PART, M=N_SLICE, action=fam, **kw)
+                fpath = host.Path(fcfg, n_clones=Cf, device=local)
+                fpath.SetPositions(0, R[:Cf])
+                fact = fpath.actions[0]
+                res = {}
+                for name, fn in (("DActionDBeta", fact.DActionDBeta), ("Potential", fact.Potential)):
+                    fn()
+                    fpath.Sync()
+                    fpath.SetTiming(True)
+                    fn()
+                    fn()
+                    fpath.Sync()
+                    kms, kn = fpath.KernelTime(1)
+                    fpath.SetTiming(False)
+                    res[name + "_kernel_ms"] = kms / max(1, kn)
+                    if name == "DActionDBeta":
+                        res["evals_per_s"] = Cf * pair_evals_per_clone() / (kms / max(1, kn) * 1e-3)
+                families[fam] = res
+                fpath.close()
+        except Exception as e:   # never let the side measurement take the headline line down
+            families["error"] = repr(e)[:200]
     # ---- roofline of the dominant kernel (K1) ------------------------------------------------
     k1_avg_s = (k1_ms / max(1, k1_n)) * 1e-3
     achieved = evals_step * FLOP_PER_EVAL / k1_avg_s / 1e12
@@ -416,6 +444,8 @@ def run_ours(args):
                    "host_driven_sweeps_per_s_per_gpu": host_driven_sweeps_per_s, "displace": displace},
             "estimators": estimators,
             "roofline": roofline}
+    if families:
+        line["other_families"] = families
     if base:
         line["cpu_baseline"] = base
     print(json.dumps(line), flush=True)
