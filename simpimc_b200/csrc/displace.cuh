@@ -98,6 +98,7 @@ template <int ATYPE>
 __global__ void __launch_bounds__(kDispThreads, 1) displace_pair_kernel(const DisplacePairArgs a) {
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ double red[2][kDispWarps];
+    __shared__ double ring[kDispWarps][32];  // lane 31's parked r': slots 0..15 OLD, 16..31 NEW (FastIlkkaEvalWarpBoth)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const PathView &pv = a.pv;
     if (ATYPE < 0) {
@@ -122,6 +123,20 @@ __global__ void __launch_bounds__(kDispThreads, 1) displace_pair_kernel(const Di
             n1[d] = p1[d] + dr[d];
         }
         double acc_old = 0., acc_new = 0.;
+        int n_parked = 0;                                     // warp-uniform
+        const bool lane31_counts = chunk * 32 + 31 < pv.M;    // lane 31 holds a real link
+        // -u_long/2 of the parked r' (n_parked OLD in lanes 0.., n_parked NEW in lanes 16..), one per lane
+        auto flush_ring = [&]() {
+            __syncwarp();
+            double v = 0.;
+            if ((lane & 15) < n_parked) v = -0.5 * FastPP1Eval(tb, a.FT.lr, Clamp(ring[warp][lane], a.FT.lr.r_min, a.FT.lr.r_max));
+            __syncwarp();
+            if (lane < 16)
+                acc_old += v;
+            else
+                acc_new += v;
+            n_parked = 0;
+        };
         for (int q = warp; q < a.N_partner; q += kDispWarps) {
             if (a.same && q == p) continue;
             double q0[3], q1[3];
@@ -132,10 +147,14 @@ __global__ void __launch_bounds__(kDispThreads, 1) displace_pair_kernel(const Di
             }
             double r, rp, s, uo, un;
             if (ATYPE < 0) {
+                double rn, rpn, sn;
                 DrDrpDrrpFast(p0, q0, p1, q1, pv.box, r, rp, s);
-                uo = FastIlkkaEval(tb, a.FT, r, rp, s);
-                DrDrpDrrpFast(n0, q0, n1, q1, pv.box, r, rp, s);
-                un = FastIlkkaEval(tb, a.FT, r, rp, s);
+                DrDrpDrrpFast(n0, q0, n1, q1, pv.box, rn, rpn, sn);
+                // u_long(r') of a link is the next lane's u_long(r) (same bead pair one slice later): one
+                // long-range lookup per lane and mode instead of two (A/B on one box: 1.644 -> 1.519 ms per attempt;
+                // evaluating OLD and NEW one after the other through FastIlkkaEvalWarp: 1.617)
+                FastIlkkaEvalWarpBoth(tb, a.FT, r, rp, s, rn, rpn, sn, lane, &ring[warp][n_parked], &ring[warp][16 + n_parked], uo, un);
+                if (a.FT.use_lr && lane31_counts && ++n_parked == 16) flush_ring();
             } else {
                 DrDrpDrrp(p0, q0, p1, q1, pv.box, r, rp, s);
                 uo = PairEval<(ATYPE < 0 ? 0 : ATYPE), WHICH_U>(a.blob, a.T, r, rp, s);
@@ -145,6 +164,7 @@ __global__ void __launch_bounds__(kDispThreads, 1) displace_pair_kernel(const Di
             acc_old += lane_on ? uo : 0.;
             acc_new += lane_on ? un : 0.;
         }
+        if (ATYPE < 0 && n_parked > 0) flush_ring();
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             acc_old += __shfl_down_sync(0xffffffffu, acc_old, o);

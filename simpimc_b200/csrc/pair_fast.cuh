@@ -281,6 +281,36 @@ __device__ __forceinline__ double FastIlkkaEvalWarp(const Tab &tb, const FastTab
     return u;
 }
 
+/// FastIlkkaEvalWarp for an OLD and a NEW set of distances at once (whole-path displacement: both
+/// sets run over the same 32 consecutive links).  Lane 31 parks its two r' in *ring_old / *ring_new.
+template <class Tab>
+__device__ __forceinline__ void FastIlkkaEvalWarpBoth(const Tab &tb, const FastTable &T, double ro, double rpo, double so, double rn, double rpn,
+                                                      double sn, int lane, double *ring_old, double *ring_new, double &uo, double &un) {
+    const double qo = 0.5 * (ro + rpo), qn = 0.5 * (rn + rpn);
+    uo = FastPP2Eval(tb, T.xy, fma(0.5, so, qo), fma(-0.5, so, qo));
+    un = FastPP2Eval(tb, T.xy, fma(0.5, sn, qn), fma(-0.5, sn, qn));
+    if (T.use_lr) {
+        const unsigned full = 0xffffffffu;
+        const double lro = FastPP1Eval(tb, T.lr, ClampRare(ro, T.lr));
+        const double lrn = FastPP1Eval(tb, T.lr, ClampRare(rn, T.lr));
+        const double ro_next = __shfl_down_sync(full, ro, 1), rn_next = __shfl_down_sync(full, rn, 1);
+        double lpo = __shfl_down_sync(full, lro, 1), lpn = __shfl_down_sync(full, lrn, 1);
+        if (lane == 31) {
+            *ring_old = rpo;
+            *ring_new = rpn;
+            lpo = 0.;
+            lpn = 0.;
+        } else {
+            if (rpo != ro_next) lpo = FastPP1Eval(tb, T.lr, Clamp(rpo, T.lr.r_min, T.lr.r_max));
+            if (rpn != rn_next) lpn = FastPP1Eval(tb, T.lr, Clamp(rpn, T.lr.r_min, T.lr.r_max));
+        }
+        uo = fma(-0.5, lro, uo);
+        uo = fma(-0.5, lpo, uo);
+        un = fma(-0.5, lrn, un);
+        un = fma(-0.5, lpn, un);
+    }
+}
+
 /// -u_long/2 of the first `count` parked values of a warp's ring, one per lane.
 template <class Tab>
 __device__ __forceinline__ double LrRingFlush(const Tab &tb, const FastTable &T, const double *ring, int lane, int count) {

@@ -358,7 +358,7 @@ def test_slice_sharded_sweeps_follow_the_host_mirror_and_rotate(name, n_shards):
 
 
 @pytest.mark.parametrize("name,general", [("ueg", False), ("ueg", True), ("plasma", False), ("bare", False), ("nolr", False),
-                                          ("david", False), ("david", True), ("plasma_david", False)])
+                                          ("david", False), ("david", True), ("plasma_david", False), ("ueg_wide", False)])
 def test_device_displace_follows_the_host_mirror_of_its_stream(name, general):
     """pimc_displace_sweep (csrc/displace.cuh): DisplaceParticle::DoEvent on the device.  The host
     mirror draws the same Philox numbers and takes the whole-path OLD / NEW actions from the CPU
@@ -367,6 +367,8 @@ def test_device_displace_follows_the_host_mirror_of_its_stream(name, general):
     from oracle import oracle as O
     if name == "ueg":
         cfg, step = S.ueg_config(N=9, M=40), 0.9      # M = 40: a partial second chunk of 32 links
+    elif name == "ueg_wide":   # > 16 partner steps per warp: the parked long-range r' of lane 31 are flushed inside the partner loop
+        cfg, step = S.ueg_config(N=530, M=40, n_xy=60, n_r_long=400), 0.9
     elif name == "bare":
         cfg, step = S.ueg_config(N=6, M=8, action="BarePairAction"), 1.2
     elif name == "nolr":
