@@ -214,6 +214,13 @@ int pimc_action_calc_pair_fast(pimc_action *act, int32_t which, int32_t n, const
                                const double *s, double *out);
 /* Device square root of the fast path on caller data (tests: <= 1 ulp from sqrt). */
 int pimc_debug_fast_sqrt(pimc_ctx *ctx, int32_t n, const double *x, double *out);
+/* HOST-ONLY (no device work; callable without a GPU): builds the interval table of the fast kernels for
+ * grid[n] -- kind 0: uniform buckets, kind 1: IEEE-754 bit-pattern buckets (spline_build.h) -- and runs the
+ * device's lookup arithmetic (key, table entry, one compare against the next knot) for x[m] >= 0 on the host.
+ * out[i] = einspline's interval of x[i] (nubspline general_grid_reverse_map semantics: 0 below the grid,
+ * n - 1 at or above its end); n_keys = table size.  PIMC_ERR_UNSUPPORTED if the grid admits no such table. */
+int pimc_debug_interval_table(int32_t kind, int32_t n, const double *grid, int32_t m, const double *x, int32_t *out,
+                              int32_t *n_keys);
 /* enable != 0: evaluate with the general kernels even where the fast path applies (tests). */
 int pimc_ctx_force_general(pimc_ctx *ctx, int32_t enable);
 

@@ -160,7 +160,7 @@ EXPORTS = [
     "pimc_action_get", "pimc_action_gradient", "pimc_action_laplacian", "pimc_action_total", "pimc_action_total_device", "pimc_action_accept", "pimc_action_reject",
     "pimc_action_calc_pair", "pimc_propose", "pimc_beads_download", "pimc_commit", "pimc_est_gofr", "pimc_est_gofr_counts", "pimc_est_sofk",
     "pimc_ctx_launch_count", "pimc_fp64_peak", "pimc_ctx_set_timing", "pimc_ctx_kernel_time",
-    "pimc_action_calc_pair_fast", "pimc_debug_fast_sqrt", "pimc_ctx_force_general", "pimc_bisect_sweep", "pimc_displace_sweep", "pimc_perm_table", "pimc_halo_pack", "pimc_halo_unpack", "pimc_rotate_pack", "pimc_rotate_apply",
+    "pimc_action_calc_pair_fast", "pimc_debug_fast_sqrt", "pimc_debug_interval_table", "pimc_ctx_force_general", "pimc_bisect_sweep", "pimc_displace_sweep", "pimc_perm_table", "pimc_halo_pack", "pimc_halo_unpack", "pimc_rotate_pack", "pimc_rotate_apply",
 ]
 
 _lib = None
@@ -219,6 +219,7 @@ def lib():
     L.pimc_ctx_kernel_time.argtypes = [vp, i32, c_double_p, C.POINTER(C.c_int64)]
     L.pimc_action_calc_pair_fast.argtypes = [vp, i32, i32, vp, vp, vp, vp]
     L.pimc_debug_fast_sqrt.argtypes = [vp, i32, vp, vp]
+    L.pimc_debug_interval_table.argtypes = [i32, i32, vp, i32, vp, vp, vp]
     L.pimc_ctx_force_general.argtypes = [vp, i32]
     L.pimc_halo_pack.argtypes = [vp, i32, vp]
     L.pimc_halo_unpack.argtypes = [vp, i32, vp]

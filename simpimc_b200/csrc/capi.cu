@@ -2463,6 +2463,40 @@ int pimc_debug_fast_sqrt(pimc_ctx *ctx, int32_t n, const double *x, double *out)
     return ToHost(ctx, buf.p + n, out, n);
 }
 
+int pimc_debug_interval_table(int32_t kind, int32_t n, const double *grid, int32_t m, const double *x, int32_t *out, int32_t *n_keys) {
+    if (!grid || !x || !out || n < 2 || m < 0 || kind < 0 || kind > 1) return Fail(PIMC_ERR_INVALID, "bad argument");
+    const int kMaxKeys = 16384;
+    std::vector<uint16_t> lut;
+    ULut ul;
+    BLut bl;
+    if (kind == 0) {
+        if (!BuildULut(grid, n, kMaxKeys, ul)) return Fail(PIMC_ERR_UNSUPPORTED, "grid admits no uniform interval table");
+        lut = ul.lut;
+    } else {
+        if (!BuildBLut(grid, n, kMaxKeys, bl)) return Fail(PIMC_ERR_UNSUPPORTED, "grid admits no bit-pattern interval table");
+        lut = bl.lut;
+    }
+    const int key_max = (int)lut.size() - 1;
+    if (n_keys) *n_keys = (int32_t)lut.size();
+    for (int i = 0; i < m; ++i) {
+        int key;
+        if (kind == 0) {  // ULookup: low word of fma(x, 1/h, 2^52 + 2^51)
+            const double kd = std::fma(x[i], ul.inv_h, kRoundMagic);
+            uint64_t bits;
+            std::memcpy(&bits, &kd, sizeof(bits));
+            key = std::min((int)(int32_t)(uint32_t)bits, key_max);
+        } else {          // DLookup<1>: (high word >> shift) - key0
+            uint64_t bits;
+            std::memcpy(&bits, &x[i], sizeof(bits));
+            key = std::min(std::max(((int)(int32_t)(bits >> 32) >> bl.shift) - bl.key0, 0), key_max);
+        }
+        const int i0 = lut[(size_t)key];
+        const double g_next = (i0 + 1 < n) ? grid[i0 + 1] : HUGE_VAL;
+        out[i] = x[i] >= g_next ? i0 + 1 : i0;
+    }
+    return PIMC_OK;
+}
+
 int pimc_ctx_force_general(pimc_ctx *ctx, int32_t enable) {
     if (!ctx) return Fail(PIMC_ERR_INVALID, "null context");
     ctx->force_general = enable != 0;

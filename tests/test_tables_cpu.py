@@ -80,3 +80,54 @@ def test_h5_tree_walk_gives_the_table_the_oracle_reads(tmp_path):
         got = O.Oracle(cfg)
         got.set_positions(0, R)
         assert got.dbeta(0) == ref.dbeta(0)
+
+
+def _einspline_interval(grid, x):
+    """nubspline general_grid_reverse_map: last i with grid[i] <= x, 0 below the grid, n-1 at or above its end."""
+    i = np.searchsorted(grid, x, side="right") - 1
+    i = np.where(x <= grid[0], 0, i)
+    return np.where(x >= grid[-1], len(grid) - 1, i).astype(np.int32)
+
+
+def _intervals_from_library(kind, grid, x):
+    import ctypes as C
+    from simpimc_b200 import capi
+    L = capi.lib()
+    grid = np.ascontiguousarray(grid, dtype=np.float64)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.zeros(len(x), dtype=np.int32)
+    n_keys = C.c_int32(0)
+    rc = L.pimc_debug_interval_table(kind, len(grid), grid.ctypes.data, len(x), x.ctypes.data, out.ctypes.data, C.addressof(n_keys))
+    return rc, out, n_keys.value
+
+
+def _probe_points(grid, rng):
+    """Random points, the knots themselves and their floating-point neighbours, points outside the grid."""
+    lo, hi = grid[0], grid[-1]
+    xs = [rng.uniform(0.0, 1.05 * hi, 200000), grid, np.nextafter(grid, 0.0), np.nextafter(grid, np.inf),
+          np.array([0.0, 0.5 * lo, hi, 1.5 * hi, 10.0 * hi]), 10.0 ** rng.uniform(np.log10(max(lo, 1e-12)), np.log10(hi), 50000)]
+    return np.concatenate(xs)
+
+
+def test_interval_tables_reproduce_the_einspline_interval_bit_for_bit():
+    """Integer work: the fast kernels' interval lookup (uniform buckets for the squarer's OPTIMIZED / linear grids,
+    IEEE bit-pattern buckets for David's logarithmic grid) must return einspline's interval index exactly, for
+    every x including the knots and their neighbours.  Host twin of the device arithmetic (pimc_debug_interval_table)."""
+    rng = np.random.default_rng(17)
+    opt = T.gen_grid("OPTIMIZED", 1.0e-4, 8.86, 1000)
+    lin = T.gen_grid("LINEAR", 1.0e-3, 8.4, 400)
+    xy = T.gen_grid("OPTIMIZED", 0.0, 100.0, 100)
+    log = 1.0e-3 * np.exp(np.arange(200) * (np.log(8.4 / 1.0e-3) / 199))
+    for kind, grid, must_build in ((0, opt, True), (0, lin, True), (0, xy, True), (1, log, True), (1, lin, True),
+                                   (1, T.gen_grid("OPTIMIZED", 1.0e-2, 8.86, 300), True)):
+        x = _probe_points(grid, rng)
+        rc, got, n_keys = _intervals_from_library(kind, grid, x)
+        assert rc == 0, (kind, len(grid))
+        assert 0 < n_keys <= 16384
+        assert np.array_equal(got, _einspline_interval(grid, x)), (kind, len(grid))
+    # a logarithmic grid is far too fine near its start for a uniform table: refused, not approximated
+    rc, _, _ = _intervals_from_library(0, 1.0e-6 * np.exp(np.arange(400) * (np.log(1e7) / 399)), np.array([1.0]))
+    assert rc != 0
+    # a grid starting at 0 has no bit-pattern table (its first bucket would be unbounded below in the exponent)
+    rc, _, _ = _intervals_from_library(1, xy, np.array([1.0]))
+    assert rc != 0
