@@ -98,6 +98,7 @@ template <int ATYPE>
 __global__ void __launch_bounds__(kDispThreads, 1) displace_pair_kernel(const DisplacePairArgs a) {
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ double red[2][kDispWarps];
+    __shared__ double sdr[3];                // the item's shift vector
     __shared__ double ring[kDispWarps][32];  // lane 31's parked r': slots 0..15 OLD, 16..31 NEW (FastIlkkaEvalWarpBoth)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const PathView &pv = a.pv;
@@ -113,15 +114,16 @@ __global__ void __launch_bounds__(kDispThreads, 1) displace_pair_kernel(const Di
         const bool lane_on = b < pv.M;
         const int bn = b + 1 >= pv.M ? b + 1 - pv.M : b + 1;
         const int p = a.particle[c];
-        double dr[3], p0[3], p1[3], n0[3], n1[3];
+        double p0[3], p1[3];
+        __syncthreads();  // the previous item's shift has been read
+        if (tid < 3) sdr[tid] = a.dr[(size_t)c * 3 + tid];
+        __syncthreads();
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-            dr[d] = a.dr[(size_t)c * 3 + d];
             p0[d] = lane_on ? a.R_moved[PosIndex(pv, a.N_moved, c, p, d, b)] : 0.;
             p1[d] = lane_on ? a.R_moved[PosIndex(pv, a.N_moved, c, p, d, bn)] : 0.;
-            n0[d] = p0[d] + dr[d];
-            n1[d] = p1[d] + dr[d];
         }
+        const uint32_t sdr_addr = (uint32_t)__cvta_generic_to_shared(sdr);
         double acc_old = 0., acc_new = 0.;
         int n_parked = 0;                                     // warp-uniform
         const bool lane31_counts = chunk * 32 + 31 < pv.M;    // lane 31 holds a real link
@@ -144,6 +146,21 @@ __global__ void __launch_bounds__(kDispThreads, 1) displace_pair_kernel(const Di
             for (int d = 0; d < 3; ++d) {
                 q0[d] = lane_on ? a.R_partner[PosIndex(pv, a.N_partner, c, q, d, b)] : 0.;
                 q1[d] = lane_on ? a.R_partner[PosIndex(pv, a.N_partner, c, q, d, bn)] : 0.;
+            }
+            // the shifted beads p + dr (rounded as the stored proposal is) are formed per step from a shift
+            // re-read from shared memory (asm volatile: not hoisted): 12 registers fewer live across the loop
+            double n0[3], n1[3];
+            {
+                double s0, s1, s2;
+                asm volatile("ld.shared.f64 %0, [%3];\n\tld.shared.f64 %1, [%3+8];\n\tld.shared.f64 %2, [%3+16];"
+                             : "=d"(s0), "=d"(s1), "=d"(s2)
+                             : "r"(sdr_addr));
+                n0[0] = p0[0] + s0;
+                n0[1] = p0[1] + s1;
+                n0[2] = p0[2] + s2;
+                n1[0] = p1[0] + s0;
+                n1[1] = p1[1] + s1;
+                n1[2] = p1[2] + s2;
             }
             double r, rp, s, uo, un;
             if (ATYPE < 0) {
