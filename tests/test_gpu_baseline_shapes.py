@@ -139,6 +139,38 @@ def test_headline_size_invariances():
     path.close()
 
 
+@pytest.mark.parametrize("family,lr", [("BarePairAction", True), ("DavidPairAction", False)])
+def test_headline_size_other_families(family, lr):
+    """The Bare and David whole-path kernels at the bench shape (N=256, M=128: eight particle groups, four slice
+    chunks, four staged partner windows, 32 parked r' per ring flush): the shared-memory fast kernels against the
+    general kernels of the same library (independent code: pp form + interval tables vs B-spline form / bit LUT),
+    identical clones bit-identical, and the size-independent invariances."""
+    from simpimc_b200 import host
+    cfg = S.ueg_config(N=256, M=128, action=family, use_long_range=lr)
+    C, N, L = 4, 256, cfg.L
+    rng = np.random.default_rng(23)
+    R = np.stack([S.synthetic_paths(cfg, 0, c % 2) for c in range(C)])     # clones 2, 3 repeat 0, 1
+    path = host.Path(cfg, n_clones=C)
+    act = path.actions[0]
+
+    def evaluate(Rx):
+        path.SetPositions(0, Rx)
+        return act.DActionDBeta(), act.TotalAction(), act.Potential()
+
+    base = evaluate(R)
+    for q in base:
+        assert np.array_equal(q[:2], q[2:]), "identical clones must give identical bits"
+    path.ForceGeneral(True)
+    for got, ref in zip(evaluate(R), base):
+        assert rel_ok(ref, got), (family, np.max(np.abs(got - ref) / np.abs(ref)))
+    path.ForceGeneral(False)
+    shift = rng.integers(-2, 3, size=(C, N, 1, 3)) * L
+    for Rx in (R + shift, R + np.array([0.123, -4.5, 2.718]), np.roll(R, 37, axis=2), R[:, rng.permutation(N)]):
+        for got, ref in zip(evaluate(Rx), base):
+            assert rel_ok(got, ref), (family, np.max(np.abs(got - ref) / np.abs(ref)))
+    path.close()
+
+
 def test_headline_size_sweeps_keep_rhok_and_energy_consistent():
     """After device-resident sweeps at full size, the incrementally updated rho_k and the
     energies equal those of a fresh context built from the downloaded positions."""

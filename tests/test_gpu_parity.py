@@ -52,6 +52,8 @@ CONFIGS = {
     "david_log_n33": lambda: S.ueg_config(N=33, M=40, action="DavidPairAction", use_long_range=True),
     # Ilkka e-e, David e-p (different species) and David p-p on a linear grid; M > 32
     "plasma_david": lambda: S.plasma_config(Ne=6, Np=5, M=36, pp_action="DavidPairAction", ep_action="DavidPairAction"),
+    # more than 32 partner offsets per particle: several staged windows, partner loop split over CTAs, three particle groups
+    "david_log_n70": lambda: S.ueg_config(N=70, M=40, action="DavidPairAction", use_long_range=False),
     "david_o1_n9": lambda: S.ueg_config(N=9, M=8, action="DavidPairAction", use_long_range=False, david_n_order=1),
     "david_o3_n9": lambda: S.ueg_config(N=9, M=8, action="DavidPairAction", use_long_range=False, david_n_order=3,
                                         david_grid="LINEAR", david_n_grid=90),
@@ -268,7 +270,7 @@ def test_errors_are_loud():
 
 
 @pytest.mark.parametrize("name", ["ilkka_lr_n7", "ilkka_lr_n33", "ilkka_nolr_n8", "plasma", "n2", "david_n7", "david_lr_n7",
-                                  "david_lin_n34", "david_log_n33", "david_o1_n9", "david_o3_n9", "plasma_david"])
+                                  "david_lin_n34", "david_log_n33", "david_o1_n9", "david_o3_n9", "plasma_david", "david_log_n70"])
 def test_fast_and_general_kernels_agree_with_oracle(name):
     """The whole-path Ilkka, Bare and David evaluations run through the shared-memory fast kernels
     (pair_fast.cuh) by default; the general kernel stays for tables the fast layouts cannot hold.
