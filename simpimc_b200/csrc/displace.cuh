@@ -74,7 +74,12 @@ __global__ void __launch_bounds__(128) displace_sample_kernel(const DisplaceSamp
     }
 }
 
-constexpr int kDispThreads = 1024;
+// A/B on one box (tools/gpu_ab_disp.sh, ms per attempt over 1024 clones): 1024 threads x 64 registers (112 B of
+// spills) 1.468, 768 x 80 1.396, 512 x 125 (no spills) 1.371 -- unlike K1, this kernel holds OLD and NEW state at once
+#ifndef PIMC_DISP_THREADS
+#define PIMC_DISP_THREADS 512
+#endif
+constexpr int kDispThreads = PIMC_DISP_THREADS;
 constexpr int kDispWarps = kDispThreads / 32;
 
 struct DisplacePairArgs {
