@@ -34,14 +34,19 @@
 
 namespace pimc {
 
-constexpr int kSweepThreads = 1024;
+// A/B (tools/gpu_ab_sweep.sh): 512-thread CTAs (four teams, 123 registers, no spills) 2530 clone-sweeps/s against 3300 with
+// 1024 threads x 64 registers: like K1, this kernel wants the warps more than the registers
+#ifndef PIMC_SWEEP_THREADS
+#define PIMC_SWEEP_THREADS 1024
+#endif
+constexpr int kSweepThreads = PIMC_SWEEP_THREADS;
 #ifndef PIMC_SWEEP_TEAMS
 #define PIMC_SWEEP_TEAMS 8
 #endif
 constexpr int kSweepTeams = PIMC_SWEEP_TEAMS;                // independent sub-CTA teams
 constexpr int kTeamThreads = kSweepThreads / kSweepTeams;
 constexpr int kTeamWarps = kTeamThreads / 32;
-constexpr int kTeamClones = 8 / kSweepTeams;                 // clones a team advances together
+constexpr int kTeamClones = (kSweepThreads / 128) / kSweepTeams;  // clones a team advances together (one per 4 warps)
 constexpr int kSweepClones = kSweepTeams * kTeamClones;      // clones in flight per CTA
 constexpr int kSweepGroup = kTeamThreads / kTeamClones;      // threads that own one clone in phases C-E
 constexpr int kSweepGroupWarps = kSweepGroup / 32;
