@@ -104,6 +104,37 @@ def test_oracle_matches_live_reference(seed, oracle_mod):
     o.close()
 
 
+DAVID_CASES = {
+    "david_lin": lambda: S.ueg_config(N=9, M=8, action="DavidPairAction", use_long_range=False, david_grid="LINEAR", david_n_grid=90),
+    "david_o1": lambda: S.ueg_config(N=9, M=8, action="DavidPairAction", use_long_range=False, david_n_order=1),
+    "david_o3": lambda: S.ueg_config(N=9, M=8, action="DavidPairAction", use_long_range=False, david_n_order=3, david_grid="LINEAR",
+                                     david_n_grid=90),
+    "plasma_david": lambda: S.plasma_config(Ne=5, Np=4, M=8, pp_action="DavidPairAction", ep_action="DavidPairAction"),
+}
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("name", sorted(DAVID_CASES))
+def test_oracle_matches_live_reference_david_variants(name, oracle_mod):
+    """DavidPairAction on a linear grid, with n_order 1 and 3, and between different species: the table shapes the GPU
+    parity tests use beyond the golden fixture, pinned to the reference library itself (where oracle/_ref was built)."""
+    from oracle import refsim
+    if not refsim.available():
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    cfg = DAVID_CASES[name]()
+    sim = refsim.RefSim(cfg, seed=1)
+    o = oracle_mod.Oracle(cfg)
+    for sp in range(len(cfg.species)):
+        R = S.synthetic_paths(cfg, sp, 0, 1001)
+        sim.set_positions(sp, R)
+        o.set_positions(sp, R)
+    for a in range(len(cfg.actions)):
+        assert G.rel_ok(o.dbeta(a), sim.dbeta(a))
+        assert G.rel_ok(o.potential(a), sim.potential(a))
+    sim.close()
+    o.close()
+
+
 def test_spline_definition_matches_scipy_natural_cubic_spline(oracle_mod):
     """The spline library the reference links (etano/meinspline, unpinned) is absent; the oracle
     restates einspline's published algorithm.  Independent check of that restatement: an
