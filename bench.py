@@ -152,6 +152,7 @@ def cpu_baseline(n_eval=1, N=N_PART, M=N_SLICE, cores=None):
     out = {"value": evals / slowest, "unit": "bead-pair action evals/s", "cores": cores, "kind": kind,
            "sample": "%d clone(s) x %d DActionDBeta() of UEG N=%d M=%d, one process per core, %.1f s wall incl. setup"
                      % (cores, n_eval, N, M, wall)}
+    out["_values"] = [r[1] for r in res]   # DActionDBeta() of walker c as the CPU implementation computed it (parity block)
     if res[0][2] > 0:
         slowest_mc = max(r[3] for r in res)
         out["mc_sweeps_per_s"] = cores * res[0][2] / (N * M // (1 << BISECT_LEVEL)) / slowest_mc
@@ -168,6 +169,7 @@ def run_reference(args):
     for _ in range(min(args.warmup, 1)):
         cpu_baseline(n_eval=1)
     base = cpu_baseline(n_eval=steps_evals)
+    base.pop("_values", None)
     ms = 1e3 * (time.perf_counter() - t0) / max(1, args.steps)
     line = {"impl": "reference", "metric": "bead-pair action evals/s", "value": base["value"], "unit": "bead-pair action evals/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -364,6 +366,14 @@ def run_ours(args):
     estimators = {"gofr_kernel_ms": k5_ms / max(1, k5_n), "gofr_pair_slices_per_s": C * pair_evals_per_clone() / (k5_ms / max(1, k5_n) * 1e-3),
                   "sofk_kernel_ms": k6_ms / max(1, k6_n), "sofk_gbs": C * N_SLICE * 182 * 16 / (k6_ms / max(1, k6_n) * 1e-3) / 1e9,
                   "unit": "one PairCorrelation::Accumulate / StructureFactor::Accumulate over all clones (kernel time, CUDA events)"}
+    # ---- BASELINE config C5: ONE large path sharded by imaginary-time slice over the ranks (NCCL halo +
+    # all-reduce behind the C ABI); collective, so every rank runs it; printed inside the same line ----
+    sharded_block = None
+    if not args.no_sharded:
+        try:
+            sharded_block = c5_leg(args, rank, world, local)
+        except Exception as e:   # identical on every rank (setup errors); never take the headline line down
+            sharded_block = {"error": repr(e)[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -422,6 +432,16 @@ def run_ours(args):
     roofline["hbm_gbs_peak"] = hbm
     roofline["k1_hbm_gbs_algorithmic"] = C * N_SLICE * N_PART * 24 / k1_avg_s / 1e9
     base = cpu_baseline(n_eval=args.cpu_evals) if (args.cpu_evals > 0 and world == 1) else None
+    parity = None
+    if base:
+        # the CPU implementation evaluated the walkers 0..cores-1 the GPU holds as clones 0..cores-1: compare the
+        # energies the timed e2e step returned with the reference's own numbers (north_star tolerance 1e-10)
+        cpu_vals = np.array(base.pop("_values"))
+        n_cmp = min(len(cpu_vals), C)
+        rel = np.abs(out_host[:n_cmp] - cpu_vals[:n_cmp]) / np.abs(cpu_vals[:n_cmp])
+        parity = {"clones": int(n_cmp), "max_rel_err": float(rel.max()), "tolerance": 1e-10, "quantity": "DActionDBeta() per clone: C-ABI e2e result vs cpu_baseline (kind=%s)" % base["kind"],
+                  "ok": bool(rel.max() <= 1e-10)}
+        assert parity["ok"], "bench parity: GPU and CPU DActionDBeta differ by %.3e" % rel.max()
     line = {"metric": "bead-pair action evals/s", "value": value, "unit": "bead-pair action evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -444,71 +464,65 @@ def run_ours(args):
                    "host_driven_sweeps_per_s_per_gpu": host_driven_sweeps_per_s, "displace": displace},
             "estimators": estimators,
             "roofline": roofline}
+    if sharded_block:
+        line["sharded"] = sharded_block
     if families:
         line["other_families"] = families
     if base:
         line["cpu_baseline"] = base
+    if parity:
+        line["parity"] = parity
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 # --------------------------------------------- config C5: one large path, slices sharded over the GPUs
-def run_c5(args):
+def c5_leg(args, rank, world, local, with_mc=True):
     """BASELINE config C5: dense hydrogen plasma, 1024 e + 1024 p, M = 512, three pair actions
     (e-e, e-p, p-p; Ilkka tables with long range), ONE path whose time slices are sharded over
     the ranks (strong scaling).  Step = rho_k rebuild of both species + DActionDBeta of the three
-    actions on the local slices + one NCCL all-reduce of the partial sums; the end-to-end leg
-    uploads the shard's positions from pinned host memory, fills the halo slice over the NCCL
-    ring and reads the energies back."""
+    actions on the local slices + ONE NCCL all-reduce of the partial sums -- every collective is the
+    library's own (C ABI: pimc_sharded_evaluate / pimc_halo_exchange / pimc_rotate), the whole step
+    replayed from one captured CUDA graph.  The end-to-end leg uploads the shard's positions from
+    pinned host memory, fills the halo slice over the NCCL ring and reads the energies back.
+    Collective: every rank calls it; returns the result block (meaningful on rank 0)."""
     import numpy as np
     import torch
     import torch.distributed as dist
-    from simpimc_b200 import sharded, system as S, capi
+    from simpimc_b200 import host, sharded, system as S, capi
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     Ne, M, C = args.c5_n, args.c5_m, args.c5_clones
     cfg = S.plasma_config(Ne=Ne, Np=Ne, M=M, n_xy=100, n_r_long=1000, pp_action="IlkkaPairAction")
     sp_path = sharded.ShardedPath(cfg, C, local, rank, world)
     path, lib = sp_path.path, sp_path.path.L
     sh = sp_path.sh
-    pinned, shards = [], []
+    fulls, shards, pinned = [], [], []
     for sp in range(2):
         full = np.stack([S.synthetic_paths(cfg, sp, c, 777) for c in range(C)])   # same walkers on every rank
-        own = full[:, :, sh.lo:sh.hi, :]
+        fulls.append(full)
         t = torch.empty((C, Ne, path.n_store, 3), dtype=torch.float64, pin_memory=True)
         t.zero_()
-        t.numpy()[:, :, :sh.n_local, :] = own      # the halo slot is filled by the ring exchange
         if world == 1:
             t.numpy()[...] = full
+        else:
+            t.numpy()[:, :, :sh.n_local, :] = full[:, :, sh.lo:sh.hi, :]      # the halo slot is filled by the ring exchange
         pinned.append(t)
         shards.append(t.numpy())
     n_act = 3
     out_dev = torch.zeros((n_act, C), dtype=torch.float64, device="cuda")
     out_host = np.zeros((n_act, C))
     stream = sp_path.stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # 2 x L2
 
     def upload_and_halo():
         for sp in range(2):
             path.SetPositions(sp, shards[sp])
             sp_path.ExchangeHalo(sp)
 
-    def step_resident():
+    def step_eager():
         sp_path.RebuildRhoK()
         sp_path.DActionDBetaAllDevice(out_dev)
-
-    def step_e2e():
-        upload_and_halo()
-        step_resident()
-        with torch.cuda.stream(stream):
-            out_host[...] = out_dev.cpu().numpy()
 
     def barrier():
         if world > 1:
@@ -517,42 +531,74 @@ def run_c5(args):
         path.Sync()
 
     upload_and_halo()
+    path.Sync()
     fp64_peak = path.Fp64Peak()
+    step_eager()
+    path.Sync()
+    energies_eager = out_dev.cpu().numpy().copy()
+    step_graph = sp_path.CaptureStep(out_dev)
+
+    def step_e2e():
+        upload_and_halo()
+        step_graph()
+        with torch.cuda.stream(stream):
+            out_host[...] = out_dev.cpu().numpy()
+
+    n_steps = max(1, args.steps) * args.c5_mult
     clocks = ClockSampler(local)
     clocks.start()
-    for _ in range(args.warmup):
-        step_resident()
+    for _ in range(max(3, args.warmup)):
+        step_graph()
     path.Sync()
-    path.SetTiming(True)
-    barrier()
+
+    def timed(step, n, flush_l2):
+        """Sum over n iterations of the device time of `step` (event pair per iteration on the context's
+        stream; the L2 flush between iterations sits outside the pairs), max over ranks."""
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for a, b in evs:
+            if flush_l2:
+                with torch.cuda.stream(stream):
+                    flush.zero_()
+            a.record(stream)
+            step()
+            b.record(stream)
+        evs[-1][1].synchronize()
+        barrier()
+        tt = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
     launches0 = path.LaunchCount()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_resident()
-    e1.record(stream)
-    e1.synchronize()
-    barrier()
+    ms_graph = timed(step_graph, n_steps, True)
     launches = path.LaunchCount() - launches0
-    k1_ms, k1_n = path.KernelTime(1)
-    k2_ms, k2_n = path.KernelTime(2)
-    k3_ms, k3_n = path.KernelTime(3)
+    ms_eager = timed(step_eager, n_steps, True)
+    # per-kernel shares (eager steps, per-kernel CUDA events: not part of the timed figure)
+    path.SetTiming(True)
+    for _ in range(5):
+        step_eager()
+    path.Sync()
+    k1_ms, _ = path.KernelTime(1)
+    k2_ms, _ = path.KernelTime(2)
+    k3_ms, _ = path.KernelTime(3)
     path.SetTiming(False)
-    clocks.ensure_samples(step_resident, path.Sync)
+    clocks.ensure_samples(step_graph, path.Sync)
     clk = clocks.stop()
-    ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
     pairs = Ne * (Ne - 1) // 2 * 2 + Ne * Ne
     evals_step = C * pairs * M            # whole path, all ranks together
-    value = evals_step * args.steps / (ms_max * 1e-3)
-    for _ in range(min(2, args.warmup)):
+    value = evals_step * n_steps / (ms_graph * 1e-3)
+    energies = out_dev.cpu().numpy().copy()
+    graph_matches_eager = bool(np.array_equal(energies, energies_eager))
+    # ---- end to end: host buffers in, host doubles out, every step ----
+    bytes0 = sp_path.BytesSent()
+    for _ in range(2):
         step_e2e()
     barrier()
+    halo_bytes = (sp_path.BytesSent() - bytes0) // 2
+    n_e2e = max(5, n_steps // 4)
     w0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(n_e2e):
         step_e2e()
     torch.cuda.synchronize()
     w1 = time.perf_counter()
@@ -560,21 +606,42 @@ def run_c5(args):
     te = torch.tensor([1e3 * (w1 - w0)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = evals_step * args.steps / (float(te.item()) * 1e-3)
-    energies = out_dev.cpu().numpy().copy()
+    e2e_value = evals_step * n_e2e / (float(te.item()) * 1e-3)
     assert np.allclose(energies, out_host, rtol=1e-12, atol=0), "resident and e2e energies differ"
+    # ---- identity check: the all-reduced shard sums against the unsharded evaluation on rank 0; on one
+    # GPU, eight in-process slice shards (the 8-GPU layout) summed against the whole path ----
+    identity = None
+    if rank == 0:
+        if world > 1:
+            whole = host.Path(cfg, n_clones=C, device=local)
+            for sp in range(2):
+                whole.SetPositions(sp, fulls[sp])
+            ref = np.stack([a.DActionDBeta() for a in whole.actions])
+            whole.close()
+            identity = {"against": "unsharded evaluation of the same path on rank 0", "max_rel_err": float(np.max(np.abs(energies - ref) / np.abs(ref)))}
+        else:
+            parts = np.zeros_like(energies)
+            for g in range(8):
+                shg = sharded.SliceSharding(M, 8, g)
+                pg = host.Path(cfg, n_clones=C, device=local, slice_lo=shg.lo, slice_hi=shg.hi)
+                for sp in range(2):
+                    pg.SetPositions(sp, shg.shard_positions(fulls[sp]))
+                parts += np.stack([a.DActionDBeta() for a in pg.actions])
+                pg.close()
+            identity = {"against": "sum of 8 in-process slice shards (the 8-GPU layout)", "max_rel_err": float(np.max(np.abs(parts - energies) / np.abs(energies)))}
+        identity["ok"] = bool(identity["max_rel_err"] <= 1e-10)
     # ---- moves on the sharded path: shard-interior bisection windows on every rank at once (no
     # communication), then one ring rotation of the slices over NCCL (positions, halos, rho_k) ----
     mc = None
-    if sh.n_local >= (1 << BISECT_LEVEL) and args.attempts > 0:
+    if with_mc and sh.n_local >= (1 << BISECT_LEVEL) and args.attempts > 0:
         n_att = max(4, min(args.attempts, 64))
         for sp in range(2):
-            sp_path.BisectSweep(sp, BISECT_LEVEL, 2, 99 + rank, attempt0=0)
+            sp_path.BisectSweep(sp, BISECT_LEVEL, 2, 99, attempt0=0)
         barrier()
         w0 = time.perf_counter()
         n_acc = 0
         for sp in range(2):
-            n_acc += int(sp_path.BisectSweep(sp, BISECT_LEVEL, n_att, 99 + rank, attempt0=2).sum())
+            n_acc += int(sp_path.BisectSweep(sp, BISECT_LEVEL, n_att, 99, attempt0=2).sum())
         torch.cuda.synchronize()
         w1 = time.perf_counter()
         sp_path.Rotate(BISECT_LEVEL + 1)
@@ -585,33 +652,53 @@ def run_c5(args):
         if world > 1:
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         attempts_per_sweep = 2 * Ne * M // (1 << BISECT_LEVEL)
-        mc = {"attempts_per_s": world * C * 2 * n_att / float(tm[0].item()), "sweeps_per_s": world * C * 2 * n_att / attempts_per_sweep / float(tm[0].item()),
-              "attempts_timed_per_rank": 2 * n_att * C, "accept_ratio_rank0": n_acc / (2.0 * n_att * C), "rotate_ms": 1e3 * float(tm[1].item()),
-              "driver": "pimc_bisect_sweep (kernel-per-phase path: 2 species, 3 actions) on each rank's shard, windows of %d slices; ShardedPath.Rotate" % (1 << BISECT_LEVEL)}
-    if rank == 0:
-        k1_step_s = k1_ms / args.steps * 1e-3          # the three K1 launches of a step on this rank
-        achieved = (evals_step / world) * FLOP_PER_EVAL / k1_step_s / 1e12
-        line = {"metric": "bead-pair action evals/s", "value": value, "unit": "bead-pair action evals/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "C5 dense hydrogen plasma %d e + %d p, M=%d, 3 Ilkka pair actions with long range (n_k=%d), %d path(s), slices sharded %d per GPU"
-                                       % (Ne, Ne, M, path.n_k, C, sh.n_local),
-                           "step": "rho_k rebuild (2 species) + DActionDBeta of 3 actions on the local slices + one NCCL all-reduce of %d doubles" % (n_act * C),
-                           "parallelism": "slice sharding, ring halo of one slice per species + all-reduce",
-                           "l2": "positions %.1f MB + rho_k %.1f MB per GPU%s" % (2 * shards[0].nbytes / 1e6, 2 * C * sh.n_local * path.n_k * 16 / 1e6,
-                                                                                  "" if 2 * shards[0].nbytes > 126e6 else " (fits L2: one system is that small; every step rewrites rho_k and the partial sums)")},
-                "clocks": clk,
-                "e2e": {"value": e2e_value, "unit": "bead-pair action evals/s", "h2d_bytes_per_step": int(2 * shards[0].nbytes),
-                        "d2h_bytes_per_step": int(out_host.nbytes), "halo_bytes_per_step": int(2 * C * Ne * 3 * 8) if world > 1 else 0},
-                "gpu_launches": int(launches),
-                "energies": {"dU/dbeta per action (clone 0)": [float(x) for x in energies[:, 0]]},
-                "mc": mc,
-                "roofline": {"bound": "fp64", "kernel": "pair_full_fast_kernel x 3 actions", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                             "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
-                             "kernel_ms_per_step": {"K1_pair_full": k1_ms / args.steps, "K2_rhok_build": k2_ms / args.steps, "K3_ksum": k3_ms / args.steps},
-                             "kernel_share_of_step": {"K1": k1_ms / ms_total, "K2": k2_ms / ms_total, "K3": k3_ms / ms_total}}}
-        print(json.dumps(line), flush=True)
+        n_win = getattr(sp_path.path, "last_windows_per_attempt", 1)
+        mc = {"attempts_per_s": world * C * 2 * n_att * n_win / float(tm[0].item()), "sweeps_per_s": world * C * 2 * n_att * n_win / attempts_per_sweep / float(tm[0].item()),
+              "attempts_timed_per_rank": 2 * n_att * C * n_win, "windows_per_launch": n_win, "accept_ratio_rank0": n_acc / (2.0 * n_att * C * n_win), "rotate_ms": 1e3 * float(tm[1].item()),
+              "driver": "pimc_bisect_sweep (kernel-per-phase path: 2 species, 3 actions) on each rank's shard, windows of %d slices; pimc_rotate over NCCL" % (1 << BISECT_LEVEL)}
+    k1_step_s = k1_ms / 5 * 1e-3          # the three K1 launches of a step on this rank
+    achieved = (evals_step / world) * FLOP_PER_EVAL / k1_step_s / 1e12 if k1_step_s > 0 else None
+    block = {"metric": "bead-pair action evals/s", "value": value, "unit": "bead-pair action evals/s", "n_gpus": world,
+             "steps": n_steps, "ms_per_step": ms_graph / n_steps, "eager_ms_per_step": ms_eager / n_steps, "scaling": "strong",
+             "config": {"workload": "C5 dense hydrogen plasma %d e + %d p, M=%d, 3 Ilkka pair actions with long range (n_k=%d), %d path(s), slices sharded %d per GPU"
+                                    % (Ne, Ne, M, path.n_k, C, sh.n_local),
+                        "step": "rho_k rebuild (2 species) + DActionDBeta of 3 actions on the local slices + one NCCL all-reduce of %d doubles, replayed from one CUDA graph (%d nodes)" % (n_act * C, step_graph.n_nodes),
+                        "parallelism": "slice sharding; ring halo of one slice per species (ncclSend/ncclRecv) + all-reduce (ncclAllReduce), both issued by the library behind the C ABI on the context's stream",
+                        "l2": "flushed between timed iterations (256 MB memset outside the per-iteration event pairs)"},
+             "clocks": clk,
+             "e2e": {"value": e2e_value, "unit": "bead-pair action evals/s", "h2d_bytes_per_step": int(2 * shards[0].nbytes),
+                     "d2h_bytes_per_step": int(out_host.nbytes), "steps": n_e2e},
+             "halo_bytes": int(halo_bytes) if world > 1 else 0,
+             "halo_note": "payload this rank hands to ncclSend / ncclAllReduce per e2e step (2 species x one slice of positions + the partial sums)",
+             "gpu_launches": int(launches),
+             "energies_match": identity,
+             "graph_replay_bit_identical_to_eager": graph_matches_eager,
+             "energies": {"dU/dbeta per action (clone 0)": [float(x) for x in energies[:, 0]]},
+             "mc": mc,
+             "roofline": {"bound": "fp64", "kernel": "pair_full_fast_kernel x 3 actions", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                          "frac": achieved / fp64_peak if (fp64_peak and achieved) else None, "traffic": None,
+                          "kernel_ms_per_step": {"K1_pair_full": k1_ms / 5, "K2_rhok_build": k2_ms / 5, "K3_ksum": k3_ms / 5}}}
     sp_path.close()
+    del flush
+    return block
+
+
+def run_c5(args):
+    """`--workload c5`: the slice-sharded leg alone, as its own bench line."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    block = c5_leg(args, rank, world, local)
+    if rank == 0:
+        block.update({"warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "dtype": "f64", "data": "synthetic"})
+        print(json.dumps(block), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -632,6 +719,8 @@ def main():
     ap.add_argument("--c5-n", type=int, default=1024)
     ap.add_argument("--c5-m", type=int, default=512)
     ap.add_argument("--c5-clones", type=int, default=1)
+    ap.add_argument("--c5-mult", type=int, default=10, help="evaluation steps of the slice-sharded leg per --steps (its step is ~1.5-11 ms)")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the slice-sharded C5 leg of the default line (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

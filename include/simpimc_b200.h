@@ -142,8 +142,8 @@ int pimc_rhok_rebuild(pimc_ctx *ctx, int32_t species); /* Species::InitRhoK */
 /* Slice-shard halo (no reference counterpart; the reference never splits a path): pack the
  * FIRST owned slice of every clone and particle into d_buf[clone][particle][dim] (device
  * memory) for the rank that owns the preceding shard, and store a received buffer into the
- * halo slot that follows the last owned slice.  The exchange itself is the caller's
- * (ncclSend/ncclRecv on the context's stream; simpimc_b200/sharded.py). */
+ * halo slot that follows the last owned slice.  pimc_halo_exchange (below) does pack, the
+ * NCCL ring and unpack in one call; the two halves are exported for callers with their own transport. */
 int pimc_halo_pack(pimc_ctx *ctx, int32_t species, double *d_buf);
 int pimc_halo_unpack(pimc_ctx *ctx, int32_t species, const double *d_buf);
 /* Ring rotation of a slice-sharded path by `shift` slices (1..slices of the shard): pack this
@@ -268,6 +268,46 @@ int pimc_displace_sweep(pimc_ctx *ctx, int32_t species, double step_size, int32_
  * on the unpermuted path.  Cycle selection and the relabelling of an accepted permutation stay with
  * the caller.  t is host memory, [n_clones][N][N]. */
 int pimc_perm_table(pimc_ctx *ctx, int32_t species, const int32_t *b0, int32_t n_bisect_beads, double epsilon, int32_t relative, double *t);
+
+/* ---- slice sharding over several GPUs ---------------------------------------------------- */
+/* One large path split by imaginary-time slice (pimc_config.slice_lo / slice_hi), one context and one
+ * process per GPU.  No reference counterpart: the reference's MPI ranks are independent walkers
+ * (framework_class.h:44-53).  What makes the split exact: the pair action at level 0 couples slice b
+ * only with b + 1 (pair_action_class.h:282-288), rho_k(b) and the k sums are slice-local
+ * (species_class.h:391-395, ilkka_pair_action_class.h:114-116).  The collectives run on NCCL (bound at
+ * run time: libnccl.so.2 of the process or the system), issued on the context's stream. */
+typedef struct pimc_comm pimc_comm;
+/* Rank 0 creates the 128-byte NCCL unique id and hands it to the other ranks by whatever channel the
+ * host program has (MPI_Bcast in the reference's world, a torch.distributed broadcast in bench.py). */
+int pimc_comm_unique_id(void *id128);
+/* Collective over the `world` ranks; world = 1 yields a communicator whose collectives are no-ops. */
+int pimc_comm_init(pimc_ctx *ctx, const void *id128, int32_t rank, int32_t world, pimc_comm **out);
+int pimc_comm_destroy(pimc_comm *comm);
+int64_t pimc_comm_bytes_sent(pimc_comm *comm); /* payload bytes this rank has sent so far */
+/* After this rank's positions changed: its first owned slice of `species` goes to the previous rank,
+ * the next rank's first slice arrives in the halo slot (pack -> ncclSend/ncclRecv ring -> unpack). */
+int pimc_halo_exchange(pimc_ctx *ctx, pimc_comm *comm, int32_t species);
+/* In-place SUM over the ranks of n doubles in device memory (shard partial sums, estimator rows). */
+int pimc_allreduce_sum(pimc_ctx *ctx, pimc_comm *comm, double *d_buf, int64_t n);
+/* pimc_rotate_pack / ring / pimc_rotate_apply for every species, then halos and rho_k refreshed. */
+int pimc_rotate(pimc_ctx *ctx, pimc_comm *comm, int32_t shift);
+/* which = 0: whole-path action, 1: DActionDBeta, 2: Potential of n_actions actions of this context
+ * into d_out[action][clone] (device memory), the shard partial sums combined by ONE all-reduce. */
+int pimc_sharded_evaluate(pimc_ctx *ctx, pimc_comm *comm, int32_t which, pimc_action *const *actions, int32_t n_actions,
+                          double *d_out);
+
+/* ---- CUDA graphs -------------------------------------------------------------------------- */
+/* Capture the device work of the calls made between begin and end on this context (kernels, copies
+ * between device buffers, the NCCL collectives above) into a graph that replays with one launch.
+ * Only entry points that neither synchronise nor take host output may be captured (the *_device
+ * variants, pimc_rhok_rebuild, pimc_halo_exchange, pimc_allreduce_sum, pimc_sharded_evaluate); run the
+ * sequence once before capturing it so that every scratch buffer exists. */
+typedef struct pimc_graph pimc_graph;
+int pimc_capture_begin(pimc_ctx *ctx);
+int pimc_capture_end(pimc_ctx *ctx, pimc_graph **out);
+int pimc_graph_launch(pimc_graph *graph);
+int64_t pimc_graph_nodes(pimc_graph *graph);
+int pimc_graph_destroy(pimc_graph *graph);
 
 /* ---- estimators ------------------------------------------------------------------------ */
 /* PairCorrelation::Accumulate (pair_correlation_class.h:15-28): y[c][i] += cofactor[c] for

@@ -3,9 +3,10 @@
 // `class GpuPairAction : public Action` is what a simpimc maintainer adds next to
 // src/actions/pair_action/ilkka_pair_action_class.h: same constructor signature as every
 // reference action (Path&, Input&, IO&), same XML attributes as PairAction /
-// IlkkaPairAction / BarePairAction (pair_action_class.h:204-238, ilkka_pair_action_class.h:253-432,
-// bare_pair_action_class.h:22-96), same virtuals (action_class.h:37-73).  ActionFactory
-// (src/actions/actions.h:13-35) returns it for type="IlkkaPairAction" / "BarePairAction";
+// IlkkaPairAction / BarePairAction / DavidPairAction (pair_action_class.h:204-238,
+// ilkka_pair_action_class.h:253-432, bare_pair_action_class.h:22-96, david_pair_action_class.h:192-360),
+// same virtuals (action_class.h:37-73).  ActionFactory (src/actions/actions.h:13-35) returns it for
+// type="IlkkaPairAction" / "BarePairAction" / "DavidPairAction";
 // moves and estimators are untouched.  It compiles only inside the reference tree (it needs
 // the reference's Path / Species / Bead / Input / IO); everything CUDA sits behind
 // include/simpimc_b200.h.
@@ -25,6 +26,8 @@
 #include <iostream>
 #include <map>
 #include <memory>
+#include <mutex>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -37,19 +40,30 @@ class GpuPathMirror {
     Path &path;
     bool stale = true;             ///< committed device positions differ from the beads' r_c
     bool proposal_pending = false;  ///< pimc_propose issued, pimc_commit not yet
+    bool committed_this_move = false;  ///< the pending proposal of the current move has been committed / dropped already
     std::vector<std::pair<int32_t, int32_t>> prop_particles;  ///< (species, particle) with a pending proposal
 
+    /// One mirror per live Path.  The registry is guarded (simulations of different paths may be set up
+    /// from different threads) and an entry dies with its mirror, so a Path allocated later at the same
+    /// address gets a fresh device context.
     static std::shared_ptr<GpuPathMirror> Get(Path &path) {
-        static std::map<Path *, std::weak_ptr<GpuPathMirror>> registry;
-        std::shared_ptr<GpuPathMirror> m = registry[&path].lock();
+        std::lock_guard<std::mutex> lock(RegistryMutex());
+        std::shared_ptr<GpuPathMirror> m = Registry()[&path].lock();
         if (!m) {
             m = std::shared_ptr<GpuPathMirror>(new GpuPathMirror(path));
-            registry[&path] = m;
+            Registry()[&path] = m;
         }
         return m;
     }
 
-    ~GpuPathMirror() { pimc_ctx_destroy(ctx); }
+    ~GpuPathMirror() {
+        {
+            std::lock_guard<std::mutex> lock(RegistryMutex());
+            auto it = Registry().find(&path);
+            if (it != Registry().end() && it->second.expired()) Registry().erase(it);
+        }
+        pimc_ctx_destroy(ctx);
+    }
 
     static void Check(int rc, const char *what) {
         if (rc != PIMC_OK) {  // reference error style: message + exit(1) (actions.h:32-33)
@@ -94,14 +108,20 @@ class GpuPathMirror {
         const int32_t particle = (int32_t)p, first = (int32_t)sp->bead_loop(b0);
         Check(pimc_propose(ctx, (int32_t)sp->GetId(), &particle, &first, (int32_t)n, newR.data()), "pimc_propose");
         proposal_pending = true;
+        committed_this_move = false;
         prop_particles.push_back(std::make_pair((int32_t)sp->GetId(), (int32_t)p));
     }
 
+    /// Accept() / Reject() of every action of a move arrive here (bisect_class.h:34-35,137-138): the
+    /// first one commits or drops the pending proposal, the others of the same move are no-ops.  An
+    /// Accept for a move this mirror never saw a proposal of (e.g. one whose pair actions all returned
+    /// before evaluating) marks the device copy stale.
     void Finish(bool accept) {
         if (!proposal_pending) {
-            if (accept) stale = true;  // something moved that this mirror never saw
+            if (accept && !committed_this_move) stale = true;
             return;
         }
+        committed_this_move = true;
         const int32_t flag = accept ? 1 : 0;
         Check(pimc_commit(ctx, &flag), "pimc_commit");
         // several particles of one species = a permutation move: on acceptance the reference relabels
@@ -116,6 +136,15 @@ class GpuPathMirror {
     }
 
    private:
+    static std::map<Path *, std::weak_ptr<GpuPathMirror>> &Registry() {
+        static std::map<Path *, std::weak_ptr<GpuPathMirror>> registry;
+        return registry;
+    }
+    static std::mutex &RegistryMutex() {
+        static std::mutex m;
+        return m;
+    }
+
     explicit GpuPathMirror(Path &p) : path(p) {
         std::vector<int32_t> n_part;
         std::vector<double> lambda;
@@ -145,7 +174,7 @@ class GpuPathMirror {
     }
 };
 
-/// IlkkaPairAction / BarePairAction evaluated on the GPU behind the reference's Action API.
+/// IlkkaPairAction / BarePairAction / DavidPairAction evaluated on the GPU behind the reference's Action API.
 class GpuPairAction : public Action {
    private:
     std::shared_ptr<GpuPathMirror> mirror;
@@ -209,6 +238,10 @@ class GpuPairAction : public Action {
         }
         is_constant = ((species_a == species_b) && (species_a->GetNPart() == 1 || species_a->GetLambda() == 0.));
         mirror = GpuPathMirror::Get(path);
+        if (use_long_range) {  // an earlier action may have created the mirror with a smaller cutoff
+            int32_t n_k = 0;
+            GpuPathMirror::Check(pimc_kspace_setup(mirror->ctx, k_cut, &n_k), "pimc_kspace_setup");
+        }
         std::string file_name = in.GetAttribute<std::string>("file");
         IO pa_in;
         pa_in.Load(file_name);
@@ -271,6 +304,76 @@ class GpuPairAction : public Action {
             t.is_coulomb = in.GetAttribute<bool>("is_coulomb", 0) ? 1 : 0;
             GpuPathMirror::Check(pimc_action_create_bare(mirror->ctx, sa, sb, &t, (int32_t)max_level, use_long_range ? 1 : 0, k_cut, &act),
                                  "pimc_action_create_bare");
+        } else if (type == "DavidPairAction") {
+            // the datasets DavidPairAction's constructor reads (david_pair_action_class.h:194-336), in its order
+            const uint32_t n_order = in.GetAttribute<uint32_t>("n_order", 0);  // pair_action_class.h:208: a misspelt attribute
+                                                                                // (inputs/h-atom/h-david.xml "nOrder") silently reads order 0
+            std::stringstream su, sdu;
+            su << "/u_kj_" << n_order;
+            sdu << "/du_kj_dbeta_" << n_order;
+            const std::string u_str = su.str(), du_str = sdu.str();
+            double r_start, r_end;
+            uint32_t n_grid;
+            std::string grid_type;
+            vec<double> grid_points;
+            pa_in.Read(u_str + "/grid/start", r_start);
+            pa_in.Read(u_str + "/grid/end", r_end);
+            pa_in.Read(u_str + "/grid/n_grid_points", n_grid);
+            pa_in.Read(u_str + "/grid/type", grid_type);
+            pimc_david_tables t;
+            t.grid_points = nullptr;
+            if ((grid_type.find("LOG") != std::string::npos) && (grid_type.find("LOGLIN") == std::string::npos)) {
+                t.grid_type = PIMC_GRID_LOG;
+            } else if (grid_type.find("LINEAR") != std::string::npos) {
+                t.grid_type = PIMC_GRID_LINEAR;
+            } else if (grid_type.find("LOGLIN") != std::string::npos) {
+                std::cerr << "ERROR: GpuPairAction: LOGLIN grids (create_loglin_grid exists only in the reference's einspline fork) are not supported" << std::endl;
+                exit(1);
+            } else {
+                grid_points.set_size(n_grid);
+                pa_in.Read(u_str + "/grid/grid_points", grid_points);
+                t.grid_type = PIMC_GRID_GENERAL;
+                t.grid_points = grid_points.memptr();
+            }
+            const uint32_t n_tau = max_level + 1;
+            vec<double> taus(n_tau);
+            pa_in.Read(u_str + "/taus", taus);
+            vec<double> V(n_grid);
+            pa_in.Read("/potential/data", V);
+            uint32_t n_val = 1;
+            for (uint32_t i = 1; i <= n_order; ++i) n_val += 1 + i;
+            cube<double> u_kj(n_val, n_grid, n_tau), du_kj(n_val, n_grid, n_tau);  // column-major: [tau][grid][val] in memory
+            pa_in.Read(u_str + "/data", u_kj);
+            pa_in.Read(du_str + "/data", du_kj);
+            vec<double> k_v, u_k;
+            double v_image = 0.;
+            t.n_k = 0;
+            t.k_points = t.u_k = nullptr;
+            if (use_long_range) {
+                uint32_t n_k_v;
+                pa_in.Read("long_range/n_k", n_k_v);
+                k_v.set_size(n_k_v);
+                u_k.set_size(n_k_v);
+                pa_in.Read("long_range/k_points", k_v);
+                pa_in.Read("long_range/u_k", u_k);
+                pa_in.Read("squarer/v_image", v_image);
+                t.n_k = (int32_t)n_k_v;
+                t.k_points = k_v.memptr();
+                t.u_k = u_k.memptr();
+            }
+            t.r_start = r_start;
+            t.r_end = r_end;
+            t.n_grid = (int32_t)n_grid;
+            t.n_order = (int32_t)n_order;
+            t.n_tau = (int32_t)n_tau;
+            t.taus = taus.memptr();
+            t.u_kj = u_kj.memptr();
+            t.du_kj_dbeta = du_kj.memptr();
+            t.potential = V.memptr();
+            t.v_image = v_image;
+            // a tau missing from the table is PIMC_ERR_TABLE -> "ERROR: ..." + exit(1), as david...:241-245
+            GpuPathMirror::Check(pimc_action_create_david(mirror->ctx, sa, sb, &t, (int32_t)max_level, use_long_range ? 1 : 0, &act),
+                                 "pimc_action_create_david");
         } else {
             std::cerr << "ERROR: GpuPairAction does not implement " << type << std::endl;
             exit(1);
@@ -296,6 +399,7 @@ class GpuPairAction : public Action {
                              const uint32_t level) {
         if (level > max_level || is_constant) return 0.;  // pair_action_class.h:269
         if (mirror->stale) mirror->UploadCommitted();
+        if (!mirror->proposal_pending) mirror->committed_this_move = false;  // the first evaluation of the next move
         std::vector<int32_t> sp, pi;
         for (auto &p : particles) {
             sp.push_back((int32_t)p.first->GetId());

@@ -79,7 +79,7 @@ std::shared_ptr<Action> MakeAction(Input &in, IO &out, Path &path) {
     std::string type = in.GetAttribute<std::string>("type");
     if (type == "Kinetic") return std::make_shared<Kinetic>(path, in, out);
 #ifdef PIMC_DROPIN_GPU
-    if (type == "IlkkaPairAction" || type == "BarePairAction") return std::make_shared<GpuPairAction>(path, in, out);
+    if (type == "IlkkaPairAction" || type == "BarePairAction" || type == "DavidPairAction") return std::make_shared<GpuPairAction>(path, in, out);
 #endif
     if (type == "BarePairAction") return std::make_shared<BarePairAction>(path, in, out);
     if (type == "DavidPairAction") return std::make_shared<DavidPairAction>(path, in, out);

@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/simpimc_b200.h"
+#include "internal.h"
 #include "kernels.cuh"
 #include "pair_fast.cuh"
 #include "mc.cuh"
@@ -172,6 +173,10 @@ struct pimc_action {
     PairTable table[3];
     // long range: weight per k vector and scaled constants
     DevBuf<double> wk[3];
+    // host copies of the |k|-shell tables the weights were matched from: KSpace::Setup is grow-only
+    // (k_space_class.h:34-41), so a later, larger k_cut rebuilds the vector list and every action's
+    // weights have to be re-matched against it (RematchWeights)
+    std::vector<double> shell_k[3], shell_f[3];
     double k0[3] = {0, 0, 0}, r0[3] = {0, 0, 0};
     double ulong_scale = 1.;  // Bare CalcULong: level_tau
     // Ilkka U / dU fast path (pair_fast.cuh): every table in one shared-memory block
@@ -186,6 +191,13 @@ struct pimc_action {
     DevBuf<unsigned char> fastd_tab[2];
     FastDavidTable fastd[2];
     bool fastd_ok[2] = {false, false};
+};
+
+struct pimc_graph {
+    pimc_ctx *ctx = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int64_t n_nodes = 0;
 };
 
 namespace {
@@ -439,11 +451,11 @@ void CheckTable1D(const pimc_table_1d &t, const char *what) {
 
 // ilkka_pair_action_class.h:308-315: weight of each k vector = table value of the shell whose
 // |k| matches within 1e-8 (last match wins), else 0.
-std::vector<double> MatchShells(const pimc_ctx *ctx, const pimc_long_range &lr) {
+std::vector<double> MatchShells(const pimc_ctx *ctx, const std::vector<double> &k, const std::vector<double> &f_k) {
     std::vector<double> w(ctx->n_k(), 0.);
     for (int k_i = 0; k_i < ctx->n_k(); ++k_i)
-        for (int k_t = 0; k_t < lr.n_k; ++k_t)
-            if (std::fabs(ctx->k_mag[k_i] - lr.k[k_t]) < 1.e-8) w[k_i] = lr.f_k[k_t];
+        for (size_t k_t = 0; k_t < k.size(); ++k_t)
+            if (std::fabs(ctx->k_mag[k_i] - k[k_t]) < 1.e-8) w[k_i] = f_k[k_t];
     return w;
 }
 
@@ -504,13 +516,27 @@ int LoadLongRange(pimc_ctx *ctx, pimc_action *a, int which, const pimc_long_rang
     CheckTable1D(lr.f_r, "long-range r table");
     if (lr.n_k < 1 || !lr.k || !lr.f_k) throw std::invalid_argument("long-range k table missing");
     AppendPP1(blob, desc, lr.f_r.r, lr.f_r.f, lr.f_r.n);
-    int rc = UploadVec(a->wk[which], MatchShells(ctx, lr));
+    a->shell_k[which].assign(lr.k, lr.k + lr.n_k);
+    a->shell_f[which].assign(lr.f_k, lr.f_k + lr.n_k);
+    int rc = UploadVec(a->wk[which], MatchShells(ctx, a->shell_k[which], a->shell_f[which]));
     if (rc != PIMC_OK) return rc;
     a->k0[which] = lr.f_k_0;
     a->r0[which] = lr.f_r_0;
     return PIMC_OK;
 }
 
+/// Re-matches every long-range action's k-vector weights after KSpace::Setup rebuilt the list.
+int RematchWeights(pimc_ctx *ctx) {
+    for (pimc_action *a : ctx->actions) {
+        if (!a->use_long_range) continue;
+        for (int which = 0; which < 3; ++which) {
+            if (a->shell_k[which].empty()) continue;
+            int rc = UploadVec(a->wk[which], MatchShells(ctx, a->shell_k[which], a->shell_f[which]));
+            if (rc != PIMC_OK) return rc;
+        }
+    }
+    return PIMC_OK;
+}
 
 // ------------------------------------------------------------------- fast Ilkka tables
 struct ByteBlob {
@@ -1132,6 +1158,10 @@ int pimc_kspace_setup(pimc_ctx *ctx, double k_cut, int32_t *n_k) {
         BuildKSpace(ctx, k_cut);
         int rc = UploadKSpace(ctx);
         if (rc != PIMC_OK) return rc;
+        // actions created for the smaller set keep their shell tables: match them to the new vectors
+        // (the reference's actions would keep stale per-vector arrays here; its inputs never grow the
+        // set after an action exists, so the well-defined behaviour is the one implemented)
+        if ((rc = RematchWeights(ctx)) != PIMC_OK) return rc;
         for (size_t s = 0; s < ctx->species.size(); ++s) {
             rc = RebuildRhoK(ctx, (int)s);
             if (rc != PIMC_OK) return rc;
@@ -1491,22 +1521,20 @@ int pimc_action_create_david(pimc_ctx *ctx, int32_t sa, int32_t sb, const pimc_d
     }
     if (a->use_long_range) {  // david...:311-358
         if (t->n_k < 1 || !t->k_points || !t->u_k) return Fail(PIMC_ERR_TABLE, "DavidPairAction long_range table missing");
-        const int n_k = ctx->n_k();
-        std::vector<double> u(n_k, 0.), du(n_k, 0.), v(n_k, 0.);
         double v_long_k_0 = 0.;
+        for (int which = 0; which < 3; ++which) {
+            a->shell_k[which].assign(t->k_points, t->k_points + t->n_k);
+            a->shell_f[which].resize(t->n_k);
+        }
         for (int kv = 0; kv < t->n_k; ++kv) {
             const double vk = t->u_k[kv] / ctx->vol;
             if (std::fabs(0. - t->k_points[kv]) < 1.e-8) v_long_k_0 = vk;
-            for (int k_i = 0; k_i < n_k; ++k_i)
-                if (std::fabs(ctx->k_mag[k_i] - t->k_points[kv]) < 1.e-8) {
-                    u[k_i] = vk * ctx->tau;
-                    du[k_i] = vk;
-                    v[k_i] = vk;  // the reference indexes shells by vector index here (UB); see DESIGN.md
-                }
+            a->shell_f[WHICH_U][kv] = vk * ctx->tau;
+            a->shell_f[WHICH_DU][kv] = vk;
+            a->shell_f[WHICH_V][kv] = vk;  // the reference indexes shells by vector index here (UB); see DESIGN.md
         }
-        if ((rc = UploadVec(a->wk[WHICH_U], u)) != PIMC_OK) return rc;
-        if ((rc = UploadVec(a->wk[WHICH_DU], du)) != PIMC_OK) return rc;
-        if ((rc = UploadVec(a->wk[WHICH_V], v)) != PIMC_OK) return rc;
+        for (int which = 0; which < 3; ++which)
+            if ((rc = UploadVec(a->wk[which], MatchShells(ctx, a->shell_k[which], a->shell_f[which]))) != PIMC_OK) return rc;
         a->r0[WHICH_DU] = t->v_image;
         a->r0[WHICH_V] = t->v_image;
         a->k0[WHICH_DU] = v_long_k_0;
@@ -2541,6 +2569,67 @@ int pimc_ctx_kernel_time(pimc_ctx *ctx, int32_t kernel_id, double *total_ms, int
     if (n_launches) *n_launches = t.n;
     return PIMC_OK;
 }
+
+// ------------------------------------------------------------------------ CUDA graphs
+// Stream capture of a sequence of calls on the context's stream (a launch-latency-bound step such as
+// the slice-sharded evaluation: ~13 short kernels + one NCCL all-reduce).  Everything the sequence
+// allocates must exist already: run it once un-captured first.
+int pimc_capture_begin(pimc_ctx *ctx) {
+    if (!ctx) return Fail(PIMC_ERR_INVALID, "null context");
+    if (ctx->timing) return Fail(PIMC_ERR_INVALID, "per-kernel timing is on: events cannot be recorded inside a capture");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    PIMC_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    return PIMC_OK;
+}
+
+int pimc_capture_end(pimc_ctx *ctx, pimc_graph **out) {
+    if (!ctx || !out) return Fail(PIMC_ERR_INVALID, "null argument");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    cudaGraph_t g = nullptr;
+    PIMC_CUDA(cudaStreamEndCapture(ctx->stream, &g));
+    if (!g) return Fail(PIMC_ERR_CUDA, "stream capture was invalidated (a captured call synchronised or allocated)");
+    pimc_graph *pg = new pimc_graph;
+    pg->ctx = ctx;
+    pg->graph = g;
+    cudaError_t e = cudaGraphInstantiate(&pg->exec, g, 0);
+    if (e != cudaSuccess) {
+        cudaGraphDestroy(g);
+        delete pg;
+        return Fail(PIMC_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    }
+    size_t n_nodes = 0;
+    cudaGraphGetNodes(g, nullptr, &n_nodes);
+    pg->n_nodes = (int64_t)n_nodes;
+    *out = pg;
+    return PIMC_OK;
+}
+
+int pimc_graph_launch(pimc_graph *g) {
+    if (!g) return Fail(PIMC_ERR_INVALID, "null graph");
+    PIMC_CUDA(cudaSetDevice(g->ctx->device));
+    PIMC_CUDA(cudaGraphLaunch(g->exec, g->ctx->stream));
+    g->ctx->launches += g->n_nodes;
+    return PIMC_OK;
+}
+
+int64_t pimc_graph_nodes(pimc_graph *g) { return g ? g->n_nodes : 0; }
+
+int pimc_graph_destroy(pimc_graph *g) {
+    if (!g) return PIMC_OK;
+    cudaSetDevice(g->ctx->device);
+    cudaStreamSynchronize(g->ctx->stream);
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+    return PIMC_OK;
+}
+
+// ------------------------------------------------------------ internal.h (other translation units)
+int pimc_internal_fail(int code, const char *msg) { return Fail(code, msg ? msg : ""); }
+int pimc_internal_device(const pimc_ctx *ctx) { return ctx->device; }
+int pimc_internal_n_clones(const pimc_ctx *ctx) { return ctx->C; }
+int pimc_internal_n_species(const pimc_ctx *ctx) { return (int)ctx->species.size(); }
+int pimc_internal_n_part(const pimc_ctx *ctx, int s) { return (s < 0 || s >= (int)ctx->species.size()) ? -1 : ctx->species[s]->N; }
 
 int pimc_fp64_peak(pimc_ctx *ctx, double *tflops) {
     if (!ctx || !tflops) return Fail(PIMC_ERR_INVALID, "null argument");

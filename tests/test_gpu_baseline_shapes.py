@@ -101,6 +101,83 @@ def test_config_c4_warm_dense_carbon():
     _against_oracle(cfg, Rs, [(0, 8), (2, 4), (1, 8)], gofr=(0, 2, 0.0, cfg.L / 2, 100))
 
 
+def test_headline_config_against_oracle():
+    """The configuration the metric is quoted on -- UEG N=256, M=128, IlkkaPairAction with long
+    range -- compared DIRECTLY with the CPU oracle on two clones (pair_action_class.h:241-264,
+    ilkka_pair_action_class.h:125-169): DActionDBeta, Potential, the whole-path action, an
+    n_level = 3 bisection window and a 32-slice window in OLD / NEW mode with their differences,
+    a whole-path DisplaceParticle difference, rho_k, the g(r) bin counts bit for bit and S(k)."""
+    from simpimc_b200 import host
+    from oracle import oracle as O
+    cfg = S.ueg_config(N=256, M=128)
+    C, N, M = 2, 256, 128
+    R = np.stack([S.synthetic_paths(cfg, 0, c) for c in range(C)])
+    _against_oracle(cfg, [R], [(0, 8), (0, 32)], gofr=(0, 0, 0.0, cfg.L / 2, 100))
+    path = host.Path(cfg, n_clones=C)
+    path.SetPositions(0, R)
+    act = path.actions[0]
+    sk = host.StructureFactor(path, 0, 0, cfg.k_cut)
+    sk.Accumulate()
+    rng = np.random.default_rng(11)
+    part = rng.integers(0, N, C)
+    shift = 0.1 * cfg.L * rng.standard_normal((C, 1, 3))
+    newR = np.stack([R[c, part[c]] for c in range(C)]) + shift      # DisplaceParticle: every bead of one particle
+    path.Propose(0, part, np.zeros(C, dtype=np.int32), newR)
+    path.SetMode(host.OLD_MODE)
+    old = act.GetAction(0, M, [(0, part)], 0)
+    path.SetMode(host.NEW_MODE)
+    new = act.GetAction(0, M, [(0, part)], 0)
+    for c in range(C):
+        o = O.Oracle(cfg)
+        o.set_positions(0, R[c])
+        assert np.max(np.abs(path.GetRhoK(0, c, host.OLD_MODE) - o.rhok(0, 0))) <= 1e-12 * N
+        ref_sk = o.sofk(0, 0, cfg.k_cut)
+        assert np.max(np.abs(sk.sk[c] - ref_sk)) <= 1e-10 * max(1.0, np.max(np.abs(ref_sk)))
+        o.propose(0, int(part[c]), 0, newR[c])
+        ro = o.get_action(0, 0, 0, M, [(0, int(part[c]))], 0)
+        rn = o.get_action(0, 1, 0, M, [(0, int(part[c]))], 0)
+        assert rel_ok(old[c], ro) and rel_ok(new[c], rn), (c, old[c], ro, new[c], rn)
+        assert abs((new[c] - old[c]) - (rn - ro)) <= RTOL * max(abs(rn - ro), 1e-4 * (abs(rn) + abs(ro)))
+        o.close()
+    path.Commit(0)
+    path.close()
+
+
+def test_config_c5_shaped_shards_against_oracle():
+    """BASELINE config C5's shape at a slice count the oracle finishes in seconds: 1024 e + 1024 p,
+    M = 8, three Ilkka actions with long range.  The whole path and the sum of two slice shards
+    (4 + 4 slices, halo included) against the oracle's DActionDBeta / Potential of the whole path
+    (pair_action_class.h:282-288 couples slice b with b + 1 only; rho_k is slice-local,
+    species_class.h:391-395)."""
+    from simpimc_b200 import host, sharded
+    from oracle import oracle as O
+    cfg = S.plasma_config(Ne=1024, Np=1024, M=8, n_xy=100, n_r_long=1000, pp_action="IlkkaPairAction")
+    Rs = [S.synthetic_paths(cfg, sp, 0, 778)[None] for sp in range(2)]
+    o = O.Oracle(cfg)
+    for sp in range(2):
+        o.set_positions(sp, Rs[sp][0])
+    ref = np.array([[o.dbeta(a), o.potential(a)] for a in range(3)])
+    whole = host.Path(cfg, n_clones=1)
+    for sp in range(2):
+        whole.SetPositions(sp, Rs[sp])
+        assert np.max(np.abs(whole.GetRhoK(sp, 0, host.OLD_MODE) - o.rhok(sp, 0))) <= 1e-12 * 1024
+    got = np.array([[a.DActionDBeta()[0], a.Potential()[0]] for a in whole.actions])
+    assert rel_ok(got, ref), (got, ref)
+    counts = host.PairCorrelation(whole, 0, 1, 0.0, cfg.L / 2, 100).Counts()[0]
+    assert np.array_equal(counts, o.gofr(0, 1, 0.0, cfg.L / 2, 100)[1])
+    whole.close()
+    parts = np.zeros_like(ref)
+    for g in range(2):
+        sh = sharded.SliceSharding(cfg.n_bead, 2, g)
+        p = host.Path(cfg, n_clones=1, slice_lo=sh.lo, slice_hi=sh.hi)
+        for sp in range(2):
+            p.SetPositions(sp, sh.shard_positions(Rs[sp]))
+        parts += np.array([[a.DActionDBeta()[0], a.Potential()[0]] for a in p.actions])
+        p.close()
+    assert rel_ok(parts, ref), (parts, ref)
+    o.close()
+
+
 def test_headline_size_invariances():
     """UEG N=256, M=128 (the bench configuration), 8 clones."""
     from simpimc_b200 import host

@@ -26,7 +26,7 @@ def _sims(cfg, seed):
     return a, b
 
 
-@pytest.mark.parametrize("which", ["ueg", "plasma", "perm"])
+@pytest.mark.parametrize("which", ["ueg", "plasma", "perm", "david", "david_lr"])
 def test_reference_moves_on_gpu_actions_reproduce_the_reference_run(which):
     if which == "perm":
         # the reference's own permuting bisection (PermBisectIterative: cycle selection from the
@@ -35,6 +35,23 @@ def test_reference_moves_on_gpu_actions_reproduce_the_reference_run(which):
         cfg = S.ueg_config(N=7, M=16, with_kinetic=True)
         cfg.moves = [{"name": "PermE", "type": "PermBisectIterative", "species": "e", "n_level": 2, "n_images": 0},
                      {"name": "BisectE", "type": "Bisect", "species": "e", "n_level": 3}]
+    elif which == "david":
+        # DavidPairAction behind the adapter (david_pair_action_class.h:192-360 reads u_kj_<n_order>, du_kj_dbeta_<n_order>,
+        # potential): an e-p action between different species on the LOG grid and a p-p action on a LINEAR grid, next
+        # to an Ilkka e-e action with long range
+        cfg = S.plasma_config(Ne=6, Np=5, M=8, pp_action="DavidPairAction", ep_action="DavidPairAction")
+        cfg.actions.insert(0, S.ActionConfig("KineticE", "Kinetic", "e"))
+        cfg.actions.insert(1, S.ActionConfig("KineticP", "Kinetic", "p"))
+        cfg.moves = [{"name": "BisectE", "type": "Bisect", "species": "e", "n_level": 2},
+                     {"name": "BisectP", "type": "Bisect", "species": "p", "n_level": 2},
+                     {"name": "DisplaceP", "type": "DisplaceParticle", "species": "p", "step_size": 0.2}]
+    elif which == "david_lr":
+        # DavidPairAction with use_long_range=1 (long_range/{n_k,k_points,u_k}, squarer/v_image): the k-space part of
+        # the action differences and of DActionDBeta.  Potential() is not measured: the reference's CalcVLong indexes a
+        # shell-length array by k vector (david_pair_action_class.h:42-60 vs :324)
+        cfg = S.ueg_config(N=9, M=16, action="DavidPairAction", use_long_range=True, with_kinetic=True)
+        cfg.moves = [{"name": "BisectE", "type": "Bisect", "species": "e", "n_level": 3},
+                     {"name": "DisplaceE", "type": "DisplaceParticle", "species": "e", "step_size": 0.3}]
     elif which == "ueg":
         cfg = S.ueg_config(N=14, M=16, with_kinetic=True)
         cfg.moves = [{"name": "BisectE", "type": "Bisect", "species": "e", "n_level": 3},
@@ -46,7 +63,7 @@ def test_reference_moves_on_gpu_actions_reproduce_the_reference_run(which):
         cfg.moves = [{"name": "BisectE", "type": "Bisect", "species": "e", "n_level": 2},
                      {"name": "BisectP", "type": "Bisect", "species": "p", "n_level": 2},
                      {"name": "DisplaceP", "type": "DisplaceParticle", "species": "p", "step_size": 0.2}]
-    cfg.observables = [{"name": "Energy", "type": "Energy", "measure_potential": 1}]
+    cfg.observables = [{"name": "Energy", "type": "Energy", "measure_potential": 0 if which == "david_lr" else 1}]
     a, b = _sims(cfg, seed=5)
     n_moves = len(cfg.moves)
     for sweep in range(30):

@@ -613,3 +613,66 @@ def test_perm_table_matches_oracle(relative):
     path.close()
     for o in oracles:
         o.close()
+
+
+@pytest.mark.parametrize("name", ["ilkka_lr_n33", "bare_lr_n7", "david_lr_n7", "plasma"])
+def test_kspace_growth_after_actions_exist(name):
+    """KSpace::Setup is grow-only (k_space_class.h:34-41): a StructureFactor with a larger k_cut
+    (structure_factor_class.h:49-51) rebuilds the k-vector list after the long-range actions matched
+    their weights to the old one.  The actions' values, window differences and device sweeps must
+    not change: the weights are re-matched to the new list (vectors beyond the table's shells get 0)."""
+    from simpimc_b200 import host
+    cfg = CONFIGS[name]()
+    C = 2
+    path, oracles, Rs = make_pair(cfg, C)
+    n_k0 = path._n_k()
+    before = [(a.DActionDBeta(), a.TotalAction(), a.Potential() if a.type != "DavidPairAction" else None) for a in path.actions]
+    sk = host.StructureFactor(path, 0, 0, 1.6 * cfg.k_cut)
+    assert path._n_k() > n_k0
+    sk.Accumulate()
+    for ai, a in enumerate(path.actions):
+        du, u = a.DActionDBeta(), a.TotalAction()
+        assert rel_ok(du, before[ai][0], rtol=1e-12) and rel_ok(u, before[ai][1], rtol=1e-12), (name, ai)
+        if before[ai][2] is not None:
+            assert rel_ok(a.Potential(), before[ai][2], rtol=1e-12)
+        for c, o in enumerate(oracles):
+            assert rel_ok(du[c], o.dbeta(ai)), (name, ai, c)
+    # a move window in OLD / NEW mode against the oracle (whose k set did not grow)
+    rng = np.random.default_rng(5)
+    N, M, nb = cfg.species[0].n_part, cfg.n_bead, 4
+    part, b0 = rng.integers(0, N, C), rng.integers(0, M, C)
+    first = (b0 + 1) % M
+    newR = np.stack([Rs[0][c][part[c], (first[c] + np.arange(nb - 1)) % M] for c in range(C)]) + 0.05 * rng.standard_normal((C, nb - 1, 3))
+    path.Propose(0, part, first, newR)
+    for c, o in enumerate(oracles):
+        o.propose(0, int(part[c]), int(first[c]), newR[c])
+    for ai, a in enumerate(path.actions):
+        if 0 not in (a.species_a, a.species_b):
+            continue
+        path.SetMode(host.OLD_MODE)
+        old = a.GetAction(b0, b0 + nb, [(0, part)], 0)
+        path.SetMode(host.NEW_MODE)
+        new = a.GetAction(b0, b0 + nb, [(0, part)], 0)
+        for c, o in enumerate(oracles):
+            ro = o.get_action(ai, 0, int(b0[c]), int(b0[c]) + nb, [(0, int(part[c]))], 0)
+            rn = o.get_action(ai, 1, int(b0[c]), int(b0[c]) + nb, [(0, int(part[c]))], 0)
+            assert rel_ok(old[c], ro) and rel_ok(new[c], rn), (name, ai, c)
+    path.Commit(1)
+    for c, o in enumerate(oracles):
+        o.finish_move(0, int(part[c]), int(b0[c]), int(b0[c]) + nb, True)
+    for ai, a in enumerate(path.actions):
+        du = a.DActionDBeta()
+        for c, o in enumerate(oracles):
+            assert rel_ok(du[c], o.dbeta(ai)), (name, "after commit", ai, c)
+    n_acc = path.BisectSweep(0, 2, 6, seed=3)       # device sweep with the grown set: rho_k stays consistent
+    R_after = path.GetPositions(0)
+    fresh = host.Path(cfg, n_clones=C)
+    for sp in range(len(cfg.species)):
+        fresh.SetPositions(sp, R_after if sp == 0 else Rs[sp])
+    for ai, a in enumerate(path.actions):
+        assert rel_ok(a.DActionDBeta(), fresh.actions[ai].DActionDBeta(), rtol=1e-11), (name, "after sweep", ai)
+    assert n_acc.shape == (C,)
+    fresh.close()
+    for o in oracles:
+        o.close()
+    path.close()

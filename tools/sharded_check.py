@@ -3,7 +3,11 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/sharded_check.py
 Builds a two-species plasma (config C5 shape at reduced size), shards its slices over the
 ranks, exchanges halos over NCCL, all-reduces the shard partial sums and compares with the
-unsharded single-GPU evaluation and the CPU oracle.  Prints one JSON line on rank 0."""
+unsharded single-GPU evaluation.  Every collective of the data path is the library's own
+(pimc_halo_exchange / pimc_allreduce_sum / pimc_rotate / pimc_sharded_evaluate behind the C ABI);
+torch.distributed only hands rank 0's NCCL unique id to the other ranks and provides the barriers
+around the timed regions.  Also replays the evaluation step from a captured CUDA graph and checks it
+against the eager result.  Prints JSON lines on rank 0."""
 import json
 import os
 import sys
@@ -44,6 +48,14 @@ def main():
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     v = [sp_path.Potential(a) for a in range(3)]
+    # the evaluation step from a captured CUDA graph (kernels + the NCCL all-reduce in one launch)
+    out_g = torch.zeros((3, C), dtype=torch.float64, device=sp_path.device)
+    replay = sp_path.CaptureStep(out_g)
+    out_g.zero_()
+    torch.cuda.synchronize()
+    replay()
+    sp_path.path.Sync()
+    graph_ok = bool(np.array_equal(out_g.cpu().numpy(), np.stack(du)))
     counts = sp_path.PairCorrelationCounts(0, 1, 0.0, cfg.L / 2, 100)
     ok = True
     err = 0.0
@@ -55,11 +67,12 @@ def main():
             ref_du, ref_v = whole.actions[a].DActionDBeta(), whole.actions[a].Potential()
             err = max(err, float(np.max(np.abs(du[a] - ref_du) / np.abs(ref_du))), float(np.max(np.abs(v[a] - ref_v) / np.abs(ref_v))))
         ref_counts = host.PairCorrelation(whole, 0, 1, 0.0, cfg.L / 2, 100).Counts().astype(np.int64)
-        ok = err <= 1e-10 and np.array_equal(counts, ref_counts)
+        ok = err <= 1e-10 and np.array_equal(counts, ref_counts) and graph_ok
         whole.close()
         n_pairs = Ne * (Ne - 1) + Ne * Ne
         print(json.dumps({"check": "slice-sharded plasma", "n_gpus": world, "N": 2 * Ne, "M": M, "clones": C, "max_rel_err_vs_unsharded": err,
-                          "gofr_bins_equal": bool(np.array_equal(counts, ref_counts)), "ok": bool(ok),
+                          "gofr_bins_equal": bool(np.array_equal(counts, ref_counts)), "graph_replay_bit_identical": graph_ok,
+                          "graph_nodes": replay.n_nodes, "comm_bytes_sent_rank0": sp_path.BytesSent(), "ok": bool(ok),
                           "dbeta_3_actions_ms": 1e3 * (t1 - t0), "pair_slice_evals": n_pairs * M * C}), flush=True)
     # ---- moves on the sharded path: shard-interior bisection windows, ring rotation over NCCL ----
     n_level, n_att = 2, 24
@@ -77,10 +90,10 @@ def main():
     mc_err, moved = 0.0, False
     gathered = []
     for sp in range(2):
-        own = torch.from_numpy(np.ascontiguousarray(sp_path.path.GetPositions(sp)[:, :, :sp_path.sh.n_local, :])).to(sp_path.device)
-        parts = [torch.empty_like(own) for _ in range(world)]
-        dist.all_gather(parts, own)
-        gathered.append(torch.cat(parts, dim=2).cpu().numpy())
+        # every rank writes its own slices into a zeroed whole-path array; the library's own all-reduce assembles it
+        full = np.zeros_like(Rs[sp])
+        full[:, :, sp_path.sh.lo:sp_path.sh.hi, :] = sp_path.path.GetPositions(sp)[:, :, :sp_path.sh.n_local, :]
+        gathered.append(sp_path._allreduce_host(full))
     if rank == 0:
         whole = host.Path(cfg, n_clones=C, device=local)
         for sp in range(2):
