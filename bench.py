@@ -366,15 +366,10 @@ def run_ours(args):
     estimators = {"gofr_kernel_ms": k5_ms / max(1, k5_n), "gofr_pair_slices_per_s": C * pair_evals_per_clone() / (k5_ms / max(1, k5_n) * 1e-3),
                   "sofk_kernel_ms": k6_ms / max(1, k6_n), "sofk_gbs": C * N_SLICE * 182 * 16 / (k6_ms / max(1, k6_n) * 1e-3) / 1e9,
                   "unit": "one PairCorrelation::Accumulate / StructureFactor::Accumulate over all clones (kernel time, CUDA events)"}
-    # ---- BASELINE config C5: ONE large path sharded by imaginary-time slice over the ranks (NCCL halo +
-    # all-reduce behind the C ABI); collective, so every rank runs it; printed inside the same line ----
-    sharded_block = None
-    if not args.no_sharded:
-        try:
-            sharded_block = c5_leg(args, rank, world, local)
-        except Exception as e:   # identical on every rank (setup errors); never take the headline line down
-            sharded_block = {"error": repr(e)[:300]}
     if rank != 0:
+        # BASELINE config C5 (below) is collective: every rank runs it, under the same watchdog as rank 0
+        if not args.no_sharded:
+            _run_sharded_leg(args, rank, world, local, None)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -464,17 +459,41 @@ def run_ours(args):
                    "host_driven_sweeps_per_s_per_gpu": host_driven_sweeps_per_s, "displace": displace},
             "estimators": estimators,
             "roofline": roofline}
-    if sharded_block:
-        line["sharded"] = sharded_block
     if families:
         line["other_families"] = families
     if base:
         line["cpu_baseline"] = base
     if parity:
         line["parity"] = parity
+    # ---- BASELINE config C5: ONE large path sharded by imaginary-time slice over the ranks (NCCL halo +
+    # all-reduce behind the C ABI), printed inside the same line.  It runs last and under a watchdog: a
+    # collective that never completes must not cost the headline line ----
+    if not args.no_sharded:
+        line["sharded"] = _run_sharded_leg(args, rank, world, local, line)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _run_sharded_leg(args, rank, world, local, line):
+    """c5_leg under a watchdog.  If it does not return within --sharded-timeout seconds (a hung collective), rank 0
+    prints the line it has with sharded = {"error": ...} and every rank leaves with os._exit(0)."""
+    def bail():
+        if rank == 0 and line is not None:
+            line["sharded"] = {"error": "slice-sharded leg did not finish within %d s (watchdog)" % args.sharded_timeout}
+            print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os._exit(0)
+
+    dog = threading.Timer(args.sharded_timeout, bail)
+    dog.daemon = True
+    dog.start()
+    try:
+        block = c5_leg(args, rank, world, local)
+    except Exception as e:   # setup errors are identical on every rank; never take the headline line down
+        block = {"error": repr(e)[:300]}
+    dog.cancel()
+    return block
 
 
 # --------------------------------------------- config C5: one large path, slices sharded over the GPUs
@@ -583,13 +602,20 @@ def c5_leg(args, rank, world, local, with_mc=True):
     k2_ms, _ = path.KernelTime(2)
     k3_ms, _ = path.KernelTime(3)
     path.SetTiming(False)
-    clocks.ensure_samples(step_graph, path.Sync)
+    # keep the same load on until nvidia-smi has had time for a few samples.  Every step holds a collective, so the
+    # number of extra steps must be the SAME on every rank: it is derived from the all-reduced time, never from
+    # this rank's own sample count (ClockSampler.ensure_samples would deadlock the ranks against each other)
+    n_extra = min(2000, int(700.0 / max(ms_graph / n_steps, 1e-3)) + 1)
+    for _ in range(n_extra):
+        step_graph()
+    path.Sync()
     clk = clocks.stop()
     pairs = Ne * (Ne - 1) // 2 * 2 + Ne * Ne
     evals_step = C * pairs * M            # whole path, all ranks together
     value = evals_step * n_steps / (ms_graph * 1e-3)
     energies = out_dev.cpu().numpy().copy()
-    graph_matches_eager = bool(np.array_equal(energies, energies_eager))
+    # NCCL may pick another reduction order for the captured all-reduce than for the eager one: equal to rounding, not bit for bit
+    graph_vs_eager = float(np.max(np.abs(energies - energies_eager) / np.abs(energies_eager)))
     # ---- end to end: host buffers in, host doubles out, every step ----
     bytes0 = sp_path.BytesSent()
     for _ in range(2):
@@ -672,7 +698,7 @@ def c5_leg(args, rank, world, local, with_mc=True):
              "halo_note": "payload this rank hands to ncclSend / ncclAllReduce per e2e step (2 species x one slice of positions + the partial sums)",
              "gpu_launches": int(launches),
              "energies_match": identity,
-             "graph_replay_bit_identical_to_eager": graph_matches_eager,
+             "graph_replay_max_rel_diff_vs_eager": graph_vs_eager,
              "energies": {"dU/dbeta per action (clone 0)": [float(x) for x in energies[:, 0]]},
              "mc": mc,
              "roofline": {"bound": "fp64", "kernel": "pair_full_fast_kernel x 3 actions", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
@@ -721,6 +747,7 @@ def main():
     ap.add_argument("--c5-clones", type=int, default=1)
     ap.add_argument("--c5-mult", type=int, default=10, help="evaluation steps of the slice-sharded leg per --steps (its step is ~1.5-11 ms)")
     ap.add_argument("--no-sharded", action="store_true", help="skip the slice-sharded C5 leg of the default line (profiling runs)")
+    ap.add_argument("--sharded-timeout", type=int, default=240, help="watchdog of the slice-sharded leg in seconds")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

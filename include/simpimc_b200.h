@@ -165,6 +165,14 @@ int pimc_action_create_bare(pimc_ctx *ctx, int32_t species_a, int32_t species_b,
                             int32_t max_level, int32_t use_long_range, double k_cut, pimc_action **out);
 int pimc_action_create_david(pimc_ctx *ctx, int32_t species_a, int32_t species_b, const pimc_david_tables *t,
                              int32_t max_level, int32_t use_long_range, pimc_action **out);
+/* Kinetic (src/actions/single_action/kinetic_class.h): the free-particle action of one species with
+ * n_images periodic images of the density matrix (FreeSpline, src/actions/free_spline_class.h:25-84:
+ * the image sum tabulated on 10 000 points over [-L/2, L/2], natural cubic spline per dimension;
+ * n_images = 0 is the closed form -|r|^2 / 4 lambda tau).  The handle answers pimc_action_dbeta
+ * (DActionDBeta, kinetic_class.h:35-45), pimc_action_get at any level 0..5 (GetAction, :105-122: only
+ * the listed particles of its species), pimc_action_total, and pimc_action_potential (0, Action's
+ * default); the device-resident sweeps use its n_images for the kinetic part of the acceptance. */
+int pimc_action_create_kinetic(pimc_ctx *ctx, int32_t species, int32_t n_images, pimc_action **out);
 int pimc_action_destroy(pimc_action *act);
 
 /* Action::DActionDBeta (pair_action_class.h:241-264) and Action::Potential (:369-395),
@@ -243,7 +251,8 @@ int pimc_commit(pimc_ctx *ctx, const int32_t *accept);
 
 /* n_attempts x Bisect::DoEvent (move_class.h:61-77 -> bisect_class.h:39-139) on every clone,
  * entirely on the device: particle and window choice, Levy construction, the free-particle
- * action in closed form (Kinetic with n_images = 0; with_kinetic = 0 leaves it out), every pair
+ * action (with_kinetic = 0 leaves it out; the species' Kinetic handle, if one exists, supplies its
+ * n_images, otherwise n_images = 0; sampling probabilities: pimc_move_set_images), every pair
  * action of the context that involves `species` in OLD and NEW mode, the Metropolis test per
  * level, Accept / Reject.  Random numbers are Philox4x32-10 (key = seed, counter = attempt0 + i,
  * clone, slot): the stream is reproducible and documented in csrc/mc.cuh, but it is not
@@ -251,6 +260,10 @@ int pimc_commit(pimc_ctx *ctx, const int32_t *accept);
  * may be NULL) is ADDED to. */
 int pimc_bisect_sweep(pimc_ctx *ctx, int32_t species, int32_t n_level, int32_t n_attempts, uint64_t seed, uint64_t attempt0,
                       int32_t with_kinetic, int64_t *n_accept);
+
+/* Bisect's own n_images attribute (bisect_class.h:173: the FreeSplines of the Levy sampling
+ * probabilities, tau 2^level / 2) for later pimc_bisect_sweep calls on this species; default 0. */
+int pimc_move_set_images(pimc_ctx *ctx, int32_t species, int32_t n_images);
 
 /* n_attempts x DisplaceParticle::DoEvent (displace_particle_class.h:13-89) on every clone, on the
  * device: one particle's whole path shifted by a vector of length step_size (direction: normalised

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -18,6 +19,7 @@
 #include "internal.h"
 #include "kernels.cuh"
 #include "pair_fast.cuh"
+#include "kinetic.cuh"
 #include "mc.cuh"
 #include "sweep_fused.cuh"
 #include "grad.cuh"
@@ -63,10 +65,26 @@ struct DevBuf {
     DevBuf &operator=(const DevBuf &) = delete;
 };
 
+/// The FreeSplines of one (species, n_images): tau_s = tau 2^s / 2, s = 0..6, plus the tau derivative
+/// table of tau itself (Kinetic::SetupSpline, kinetic_class.h:16-24; Bisect::SetupSpline, bisect_class.h:158-163).
+struct FreeSet {
+    DevBuf<double> pp[kMaxFreeSplines], pp_dtau;
+    FreeSplineSet view;
+    FreeSplineTab dtau;
+};
+
 struct SpeciesState {
     int N = 0;
     double lambda = 0.;
+    std::map<int, std::unique_ptr<FreeSet>> free_sets;  // by n_images, built on first use
+    int move_images = 0;                                 // Bisect's n_images attribute (bisect_class.h:173)
+    pimc_action *kinetic = nullptr;                      // the species' Kinetic action, if one was created
     DevBuf<double> R;        // committed positions [C][N][3][Ms]
+    // slice-major mirror [C][Mstore][N][3] for the bisection windows of the single-launch sweep (a 9-slice
+    // window is 9 contiguous 6 KB blocks here, 768 72-byte fragments of 128-byte lines in R); built on
+    // demand, kept in step by the sweep's own commits, invalidated by every other writer of R
+    DevBuf<double> R2;
+    bool R2_valid = false;
     DevBuf<double2> rho;     // committed rho_k [C][Mloc][n_k]
     // pending proposals: n_slots particles of the species per clone, n_prop beads each
     DevBuf<double> P;        // [slot][C][n_prop][3]
@@ -165,6 +183,7 @@ struct pimc_action {
     int max_level = 0;
     bool use_long_range = false;
     bool is_constant = false;
+    int n_images = 0;  // Kinetic: periodic images of the free-particle density matrix (action_class.h:30)
     // per evaluated quantity (U, dU, V): the stageable blob (grids, LUTs, 1-D pp coefficients;
     // for David the B-spline multi-spline, read from global memory), the 2-D cell polynomials
     DevBuf<double> blob[3];
@@ -535,6 +554,60 @@ int RematchWeights(pimc_ctx *ctx) {
             if (rc != PIMC_OK) return rc;
         }
     }
+    return PIMC_OK;
+}
+
+/// The FreeSplines of (species, n_images), built and uploaded on first use.
+int GetFreeSet(pimc_ctx *ctx, int s, int n_images, FreeSet **out) {
+    SpeciesState &st = *ctx->species[s];
+    auto it = st.free_sets.find(n_images);
+    if (it != st.free_sets.end()) {
+        *out = it->second.get();
+        return PIMC_OK;
+    }
+    if (n_images < 0) return Fail(PIMC_ERR_INVALID, "negative n_images");
+    if (!(st.lambda > 0.)) return Fail(PIMC_ERR_INVALID, "free-particle splines of a species with lambda = 0");
+    std::unique_ptr<FreeSet> fs(new FreeSet);
+    std::memset(&fs->view, 0, sizeof(fs->view));
+    std::memset(&fs->dtau, 0, sizeof(fs->dtau));
+    fs->view.n_images = n_images;
+    try {
+        for (int k = 0; k < kMaxFreeSplines; ++k) {
+            const double tau_s = 0.5 * ctx->tau * (double)(1 << k);
+            FreeSplineTab &T = fs->view.s[k];
+            T.i4lt = 1. / (4. * st.lambda * tau_s);
+            if (n_images == 0) {  // the reference's spline of zeros: closed form, no table
+                if (k == 1) {
+                    fs->dtau = T;
+                    fs->dtau.i4lt = 1. / (4. * st.lambda * tau_s * tau_s);
+                }
+                continue;
+            }
+            const FreeSplineHost h = BuildFreeSpline(ctx->pbc ? ctx->L : 0., (unsigned)n_images, st.lambda, tau_s, k == 1);
+            int rc = UploadVec(fs->pp[k], h.pp_action);
+            if (rc != PIMC_OK) return rc;
+            T.pp = fs->pp[k].p;
+            T.n_int = h.n - 1;
+            T.zero_lo = h.zero_lo;
+            T.zero_hi = h.zero_hi;
+            T.start = h.start;
+            T.dr = h.dr;
+            T.inv_dr = 1. / h.dr;
+            T.i4lt = h.i4lt;
+            if (k == 1) {
+                if ((rc = UploadVec(fs->pp_dtau, h.pp_dtau)) != PIMC_OK) return rc;
+                fs->dtau = T;
+                fs->dtau.pp = fs->pp_dtau.p;
+                fs->dtau.zero_lo = h.dtau_zero_lo;
+                fs->dtau.zero_hi = h.dtau_zero_hi;
+                fs->dtau.i4lt = h.i4ltt;
+            }
+        }
+    } catch (const std::exception &e) {
+        return Fail(PIMC_ERR_TABLE, e.what());
+    }
+    *out = fs.get();
+    st.free_sets[n_images] = std::move(fs);
     return PIMC_OK;
 }
 
@@ -1027,8 +1100,11 @@ int Finalize(pimc_ctx *ctx, int n_per_clone, bool add_lr, double k0, double r0, 
 }
 
 /// DActionDBeta (which = DU), Potential (V) or the whole-path action (U) into device memory.
+int KineticFull(pimc_action *a, int which, double *d_out);
+
 int FullEvaluation(pimc_action *a, int which, double *d_out) {
     pimc_ctx *ctx = a->ctx;
+    if (a->atype == ATYPE_KINETIC) return KineticFull(a, which, d_out);
     if (a->is_constant) {
         // App. A-1: a constant action has no pairs (one particle) or never changes; the
         // reference caches its first value.  Only the no-pair case is evaluated here.
@@ -1052,6 +1128,71 @@ int FullEvaluation(pimc_action *a, int which, double *d_out) {
     const bool add_const = (which != WHICH_U) && (!ctx->sharded || ctx->slice_lo == 0);
     const double k0 = a->k0[which], r0 = a->r0[which];
     return Finalize(ctx, n_per_clone, a->use_long_range, k0, r0, add_const, d_out);
+}
+
+/// Kinetic::GetAction (kinetic_class.h:105-122) for `n_listed` particles per clone (device array part[n_listed][C])
+/// over the window [b0, b0 + n_window) at `level`, OLD or NEW mode, into d_out[C].
+int KineticWindow(pimc_action *a, int mode, const int32_t *d_b0, int n_window, int n_listed, const int32_t *d_part, int level, double *d_out) {
+    pimc_ctx *ctx = a->ctx;
+    if (level + 1 >= kMaxFreeSplines) return Fail(PIMC_ERR_UNSUPPORTED, "Kinetic action above level 5");
+    const int skip = 1 << level;
+    if (n_window % skip) return Fail(PIMC_ERR_INVALID, "window is not a multiple of 2^level");
+    FreeSet *fs = nullptr;
+    int rc = GetFreeSet(ctx, a->sa, a->n_images, &fs);
+    if (rc != PIMC_OK) return rc;
+    KineticWindowArgs w;
+    w.pv = ctx->View();
+    w.sv = ctx->SView(a->sa, mode == PIMC_NEW);
+    w.tab = fs->view.s[level + 1];
+    w.n_listed = n_listed;
+    w.part = d_part;
+    w.b0 = d_b0;
+    w.n_links = n_window / skip;
+    w.skip = skip;
+    w.mode = mode;
+    w.out = d_out;
+    kinetic_window_kernel<<<(ctx->C + 3) / 4, 128, 0, ctx->stream>>>(w);
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    return PIMC_OK;
+}
+
+/// Kinetic::DActionDBeta (kinetic_class.h:35-45); Potential() of a Kinetic action is Action's default 0
+/// (action_class.h:43); the whole-path action is GetAction(0, n_bead, every particle, 0).
+int KineticFull(pimc_action *a, int which, double *d_out) {
+    pimc_ctx *ctx = a->ctx;
+    SpeciesState &st = *ctx->species[a->sa];
+    if (which == WHICH_V) {
+        PIMC_CUDA(cudaMemsetAsync(d_out, 0, ctx->C * sizeof(double), ctx->stream));
+        return PIMC_OK;
+    }
+    FreeSet *fs = nullptr;
+    int rc = GetFreeSet(ctx, a->sa, a->n_images, &fs);
+    if (rc != PIMC_OK) return rc;
+    KineticFullArgs k;
+    k.pv = ctx->View();
+    k.sv = ctx->SView(a->sa, false);
+    k.n_chunks = (ctx->Mloc + 31) / 32;
+    const size_t items = (size_t)ctx->C * k.n_chunks;
+    if (ctx->partial.n < items) PIMC_CUDA(ctx->partial.Alloc(items));
+    k.partial = ctx->partial.p;
+    double constant = 0.;
+    if (which == WHICH_DU) {
+        k.dtau = fs->dtau;
+        // d_action_d_beta_const = N M n_d / (2 tau) (kinetic_class.h:31), on the rank that owns slice 0
+        constant = (!ctx->sharded || ctx->slice_lo == 0) ? st.N * (double)ctx->M * ctx->n_d / (2. * ctx->tau) : 0.;
+    } else {  // -log rho_free of every link: the same sum with the action table and the opposite sign
+        k.dtau = fs->view.s[1];
+    }
+    kinetic_dbeta_kernel<<<(int)std::min<size_t>(items, (size_t)ctx->n_sm * 8), 256, 0, ctx->stream>>>(k);
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    if ((int)ctx->lr_dev.n < ctx->C) PIMC_CUDA(ctx->lr_dev.Alloc(ctx->C));
+    PIMC_CUDA(cudaMemsetAsync(ctx->lr_dev.p, 0, ctx->C * sizeof(double), ctx->stream));
+    kinetic_finalize_kernel<<<(ctx->C + 127) / 128, 128, 0, ctx->stream>>>(ctx->partial.p, ctx->C, k.n_chunks, which == WHICH_DU ? 1. : -1., constant, d_out);
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    return PIMC_OK;
 }
 
 int ToHost(pimc_ctx *ctx, const double *d_src, double *host, size_t n) {
@@ -1190,6 +1331,7 @@ int pimc_positions_upload(pimc_ctx *ctx, int32_t s, int32_t clone_lo, int32_t cl
     PIMC_CUDA(cudaMemcpyAsync(ctx->stage.p, R, n_host * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     double *dst = st.R.p + (size_t)clone_lo * st.N * 3 * ctx->Ms;
     positions_in_kernel<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(ctx->stage.p, nc, st.N, ctx->Mstore, ctx->Ms, dst);
+    st.R2_valid = false;
     ctx->launches++;
     PIMC_CUDA(cudaGetLastError());
     st.n_prop = 0;
@@ -1223,6 +1365,7 @@ int pimc_positions_set_device(pimc_ctx *ctx, int32_t s, const double *d_R) {
     PIMC_CUDA(cudaSetDevice(ctx->device));
     SpeciesState &st = *ctx->species[s];
     PIMC_CUDA(cudaMemcpyAsync(st.R.p, d_R, st.R.n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    st.R2_valid = false;
     st.n_prop = 0;
     st.n_slots = 0;
     return RebuildRhoK(ctx, s);
@@ -1230,6 +1373,7 @@ int pimc_positions_set_device(pimc_ctx *ctx, int32_t s, const double *d_R) {
 
 double *pimc_positions_device_ptr(pimc_ctx *ctx, int32_t s) {
     if (!ctx || s < 0 || s >= (int)ctx->species.size()) return nullptr;
+    ctx->species[s]->R2_valid = false;  // the caller may write through the pointer
     return ctx->species[s]->R.p;
 }
 
@@ -1253,6 +1397,7 @@ int pimc_halo_unpack(pimc_ctx *ctx, int32_t s, const double *d_buf) {
     SpeciesState &st = *ctx->species[s];
     const size_t n_rows = (size_t)ctx->C * st.N * 3;
     halo_unpack_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, ctx->stream>>>(st.R.p, n_rows, ctx->Ms, ctx->Mloc, d_buf);
+    st.R2_valid = false;
     ctx->launches++;
     PIMC_CUDA(cudaGetLastError());
     return PIMC_OK;
@@ -1283,6 +1428,7 @@ int pimc_rotate_apply(pimc_ctx *ctx, int32_t s, int32_t shift, const double *d_b
     SpeciesState &st = *ctx->species[s];
     const size_t n_rows = (size_t)ctx->C * st.N * 3;
     rotate_apply_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, ctx->stream>>>(st.R.p, n_rows, ctx->Ms, ctx->Mloc, shift, d_buf);
+    st.R2_valid = false;
     ctx->launches++;
     PIMC_CUDA(cudaGetLastError());
     // rho_k of the shifted slices: the caller rebuilds (pimc_rhok_rebuild) after the halo exchange
@@ -1547,9 +1693,43 @@ int pimc_action_create_david(pimc_ctx *ctx, int32_t sa, int32_t sb, const pimc_d
     return PIMC_OK;
 }
 
+int pimc_action_create_kinetic(pimc_ctx *ctx, int32_t species, int32_t n_images, pimc_action **out) {
+    if (!ctx || !out) return Fail(PIMC_ERR_INVALID, "null context or output");
+    if (species < 0 || species >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
+    if (n_images < 0) return Fail(PIMC_ERR_INVALID, "negative n_images");
+    SpeciesState &st = *ctx->species[species];
+    if (st.kinetic) return Fail(PIMC_ERR_INVALID, "the species already has a Kinetic action");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    std::unique_ptr<pimc_action> a(new pimc_action);
+    a->ctx = ctx;
+    a->atype = ATYPE_KINETIC;
+    a->sa = a->sb = species;
+    a->n_images = n_images;
+    FreeSet *fs = nullptr;  // Kinetic::SetupSpline runs in the constructor (kinetic_class.h:32)
+    int rc = GetFreeSet(ctx, species, n_images, &fs);
+    if (rc != PIMC_OK) return rc;
+    st.kinetic = a.get();
+    ctx->actions.push_back(a.get());
+    *out = a.release();
+    return PIMC_OK;
+}
+
+int pimc_move_set_images(pimc_ctx *ctx, int32_t species, int32_t n_images) {
+    if (!ctx) return Fail(PIMC_ERR_INVALID, "null context");
+    if (species < 0 || species >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
+    if (n_images < 0) return Fail(PIMC_ERR_INVALID, "negative n_images");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    FreeSet *fs = nullptr;
+    int rc = GetFreeSet(ctx, species, n_images, &fs);
+    if (rc != PIMC_OK) return rc;
+    ctx->species[species]->move_images = n_images;
+    return PIMC_OK;
+}
+
 int pimc_action_destroy(pimc_action *act) {
     if (!act) return PIMC_OK;
     pimc_ctx *ctx = act->ctx;
+    if (act->atype == ATYPE_KINETIC && ctx->species[act->sa]->kinetic == act) ctx->species[act->sa]->kinetic = nullptr;
     auto it = std::find(ctx->actions.begin(), ctx->actions.end(), act);
     if (it != ctx->actions.end()) ctx->actions.erase(it);
     cudaSetDevice(ctx->device);
@@ -1592,6 +1772,38 @@ int pimc_action_get(pimc_action *act, int32_t mode, const int32_t *b0, int32_t n
     if (!act || !out || !b0 || (n_moved > 0 && (!moved_species || !moved_particle))) return Fail(PIMC_ERR_INVALID, "null argument");
     pimc_ctx *ctx = act->ctx;
     PIMC_CUDA(cudaSetDevice(ctx->device));
+    if (act->atype == ATYPE_KINETIC) {  // Kinetic::GetAction: every level, only the listed particles of its species
+        if (ctx->sharded) return Fail(PIMC_ERR_UNSUPPORTED, "move windows on a slice-sharded context");
+        if (n_window < 1 || n_window > ctx->M) return Fail(PIMC_ERR_INVALID, "window must cover 1..n_bead slices");
+        if (level < 0) return Fail(PIMC_ERR_INVALID, "negative level");
+        std::vector<int> idx;
+        for (int i = 0; i < n_moved; ++i)
+            if (moved_species[i] == act->sa) idx.push_back(i);
+        if (idx.empty()) {
+            for (int c = 0; c < ctx->C; ++c) out[c] = 0.;
+            return PIMC_OK;
+        }
+        if ((int)idx.size() > kMaxPropSlots) return Fail(PIMC_ERR_UNSUPPORTED, "more than 4 listed particles of one species");
+        if (n_window == ctx->M) {  // bead_a->GetNextBead(b1 - b0) is bead_a itself: the reference's loop body never runs (kinetic_class.h:112-113)
+            for (int c = 0; c < ctx->C; ++c) out[c] = 0.;
+            return PIMC_OK;
+        }
+        std::vector<int32_t> part(idx.size() * (size_t)ctx->C);
+        for (int c = 0; c < ctx->C; ++c) {
+            if (b0[c] < 0 || b0[c] >= ctx->M) return Fail(PIMC_ERR_INVALID, "window start out of range");
+            for (size_t i = 0; i < idx.size(); ++i) {
+                const int32_t p = moved_particle[(size_t)c * n_moved + idx[i]];
+                if (p < 0 || p >= ctx->species[act->sa]->N) return Fail(PIMC_ERR_INVALID, "moved particle out of range");
+                part[i * ctx->C + c] = p;
+            }
+        }
+        int rc;
+        if ((rc = EnsureI32(ctx, ctx->i32_a, part.data(), part.size())) != PIMC_OK) return rc;
+        if ((rc = EnsureI32(ctx, ctx->i32_c, b0, ctx->C)) != PIMC_OK) return rc;
+        if ((rc = EnsureOut(ctx)) != PIMC_OK) return rc;
+        if ((rc = KineticWindow(act, mode, ctx->i32_c.p, n_window, (int)idx.size(), ctx->i32_a.p, level, ctx->out_dev.p)) != PIMC_OK) return rc;
+        return ToHost(ctx, ctx->out_dev.p, out, ctx->C);
+    }
     // pair_action_class.h:269
     if (level > act->max_level || act->is_constant) {
         for (int c = 0; c < ctx->C; ++c) out[c] = 0.;
@@ -1716,6 +1928,7 @@ static int ActionDerivative(pimc_action *act, const int32_t *b0, int32_t n_windo
     if (!act || !out || !b0 || (n_moved > 0 && (!moved_species || !moved_particle))) return Fail(PIMC_ERR_INVALID, "null argument");
     pimc_ctx *ctx = act->ctx;
     PIMC_CUDA(cudaSetDevice(ctx->device));
+    if (act->atype == ATYPE_KINETIC) return Fail(PIMC_ERR_UNSUPPORTED, "gradient / Laplacian of the Kinetic action (closed forms, kinetic_class.h:125-165) are not on the device path");
     const int nv = what ? 1 : 3;
     auto zero = [&]() {
         for (size_t i = 0; i < (size_t)ctx->C * nv; ++i) out[i] = 0.;
@@ -1832,6 +2045,7 @@ int pimc_action_calc_pair(pimc_action *act, int32_t which, int32_t n, const doub
                           int32_t level, double *out) {
     if (!act || !r || !r_p || !s || !out || n < 0 || which < 0 || which > 2) return Fail(PIMC_ERR_INVALID, "bad argument");
     if (level != 0) return Fail(PIMC_ERR_UNSUPPORTED, "level > 0");
+    if (act->atype == ATYPE_KINETIC) return Fail(PIMC_ERR_INVALID, "a Kinetic action has no pair kernels");
     if (n == 0) return PIMC_OK;
     pimc_ctx *ctx = act->ctx;
     PIMC_CUDA(cudaSetDevice(ctx->device));
@@ -1938,6 +2152,7 @@ int pimc_commit(pimc_ctx *ctx, const int32_t *accept) {
         if (st.n_prop > 0) {
             commit_positions_kernel<<<ctx->C, 64, 0, ctx->stream>>>(ctx->View(), st.N, st.P.p, st.P_particle.p, st.P_first.p, st.n_prop,
                                                                   std::max(1, st.n_slots), ctx->i32_d.p, st.R.p);
+            st.R2_valid = false;
             ctx->launches++;
             PIMC_CUDA(cudaGetLastError());
             if (st.drho_valid) {
@@ -1993,7 +2208,7 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
     bool any_lr = false;
     for (pimc_action *a : ctx->actions) {
         if (a->sa != s && a->sb != s) continue;
-        if (a->is_constant) continue;
+        if (a->is_constant || a->atype == ATYPE_KINETIC) continue;  // the kinetic action is evaluated with the Levy construction
         acts.push_back(a);
         any_lr = any_lr || (a->use_long_range && n_k > 0);
     }
@@ -2001,6 +2216,14 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
         const size_t need = (size_t)C * nb * n_k;
         if (st.drho.n < need) PIMC_CUDA(st.drho.Alloc(need));
     }
+    // free-particle splines with periodic images: the move's own (Bisect n_images) for the sampling
+    // probabilities, the Kinetic action's for the action (closed forms when n_images = 0)
+    FreeSet *fs_move = nullptr, *fs_kin = nullptr;
+    int rc_fs;
+    if ((rc_fs = GetFreeSet(ctx, s, st.move_images, &fs_move)) != PIMC_OK) return rc_fs;
+    if ((rc_fs = GetFreeSet(ctx, s, st.kinetic ? st.kinetic->n_images : 0, &fs_kin)) != PIMC_OK) return rc_fs;
+    if ((fs_move->view.n_images || fs_kin->view.n_images) && n_level + 1 > kMaxFreeSplines)
+        return Fail(PIMC_ERR_UNSUPPORTED, "n_level too large for the tabulated free-particle splines");
     const PathView pv = ctx->View();
     // one same-species fast Ilkka action on the moved species: the whole sweep is one launch
     // (sweep_fused.cuh); everything else takes the kernel-per-phase path below
@@ -2015,13 +2238,24 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
     if (fused && n_attempts > 0) {
         pimc_action *a = acts[0];
         SweepFusedArgs f;
+        if (!st.R2_valid) {
+            const size_t n2 = (size_t)C * ctx->Mstore * st.N * 3;
+            if (st.R2.n != n2) PIMC_CUDA(st.R2.Alloc(n2));
+            dim3 tgrid((ctx->Mstore + 31) / 32, (st.N * 3 + 31) / 32, C);
+            slice_major_kernel<<<tgrid, dim3(32, 8), 0, ctx->stream>>>(st.R.p, st.N * 3, ctx->Mstore, ctx->Ms, st.R2.p);
+            ctx->launches++;
+            st.R2_valid = true;
+        }
         f.pv = pv;
         f.R = st.R.p;
+        f.R2 = st.R2.p;
         f.N = st.N;
         f.lambda = st.lambda;
         f.tau = ctx->tau;
         f.n_level = n_level;
         f.with_kinetic = with_kinetic ? 1 : 0;
+        f.fs_move = fs_move->view;
+        f.fs_kin = fs_kin->view;
         f.b0_lo = b0_lo;
         f.b0_count = b0_count;
         f.seed_lo = (uint32_t)seed;
@@ -2044,6 +2278,7 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
         }
         ctx->launches++;
     }
+    if (!fused && n_attempts > 0) st.R2_valid = false;  // the kernel-per-phase path commits into R only
     for (int it = 0; it < (fused ? 0 : n_attempts); ++it) {
         const uint64_t attempt = attempt0 + (uint64_t)it;
         BisectArgs ba;
@@ -2054,6 +2289,8 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
         ba.tau = ctx->tau;
         ba.n_level = n_level;
         ba.with_kinetic = with_kinetic ? 1 : 0;
+        ba.fs_move = fs_move->view;
+        ba.fs_kin = fs_kin->view;
         ba.b0_lo = b0_lo;
         ba.b0_count = b0_count;
         ba.seed_lo = (uint32_t)seed;
@@ -2217,7 +2454,7 @@ int pimc_displace_sweep(pimc_ctx *ctx, int32_t s, double step_size, int32_t n_at
     bool any_lr = false;
     for (pimc_action *a : ctx->actions) {
         if (a->sa != s && a->sb != s) continue;
-        if (a->is_constant) continue;
+        if (a->is_constant || a->atype == ATYPE_KINETIC) continue;  // the kinetic action is evaluated with the Levy construction
         acts.push_back(a);
         any_lr = any_lr || (a->use_long_range && n_k > 0);
     }
@@ -2229,6 +2466,7 @@ int pimc_displace_sweep(pimc_ctx *ctx, int32_t s, double step_size, int32_t n_at
     const int n_chunks = (M + 31) / 32;
     if (ctx->partial.n < (size_t)C * n_chunks * 2) PIMC_CUDA(ctx->partial.Alloc((size_t)C * n_chunks * 2));
     const int grid = (int)std::min<size_t>((size_t)C * n_chunks, (size_t)ctx->n_sm);
+    if (n_attempts > 0) st.R2_valid = false;
     for (int it = 0; it < n_attempts; ++it) {
         const uint64_t attempt = attempt0 + (uint64_t)it;
         DisplaceSampleArgs sa;

@@ -19,7 +19,7 @@
 
 namespace pimc {
 
-enum { ATYPE_ILKKA = 0, ATYPE_BARE = 1, ATYPE_DAVID = 2 };
+enum { ATYPE_ILKKA = 0, ATYPE_BARE = 1, ATYPE_DAVID = 2, ATYPE_KINETIC = 3 };
 enum { WHICH_U = 0, WHICH_DU = 1, WHICH_V = 2 };
 enum { GRIDCODE_GENERAL = 0, GRIDCODE_LOG = 1 };
 

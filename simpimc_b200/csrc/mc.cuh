@@ -21,6 +21,7 @@
 
 #include "kernels.cuh"
 #include "pair_fast.cuh"
+#include "kinetic.cuh"
 
 namespace pimc {
 
@@ -66,6 +67,8 @@ struct BisectArgs {
     double lambda, tau;
     int n_level;
     int with_kinetic;
+    FreeSplineSet fs_move;  // Bisect's rho_free_splines (bisect_class.h:158-163): s[level], tau_s = tau 2^level / 2
+    FreeSplineSet fs_kin;   // Kinetic's (kinetic_class.h:16-24): s[level + 1], tau_s = tau 2^level
     int b0_lo, b0_count;  // window starts are uniform in [b0_lo, b0_lo + b0_count): the whole path, or a shard's interior windows
     uint32_t seed_lo, seed_hi;
     uint32_t attempt_lo, attempt_hi;
@@ -139,14 +142,16 @@ __global__ void __launch_bounds__(kSampleWarps * 32) bisect_sample_kernel(const 
         (void)sd;
         const double nrm[3] = {ra * cb, ra * sb, rc * cd};
         const double sigma = sqrt(a.lambda * (a.tau * skip));
-        double d2 = 0.;
+        double d2 = 0., delv[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
             const double del = PutInBox1(sigma * nrm[d], pv.box);
             s_del[w][ib][d] = del;
+            delv[d] = del;
             d2 += del * del;
         }
-        s_d2[w][ib] = d2;
+        // with images: -log rho_free of the new displacement (bisect_class.h:94); without: |delta|^2
+        s_d2[w][ib] = a.fs_move.n_images ? -FreeLogRho(a.fs_move.s[level], delv) : d2;
     }
     if (lane < a.n_level) {  // Metropolis uniform of level = lane
         const uint32_t slot = SweepSlotStart(lane, a.n_level, nb) + 2u * (uint32_t)(nb >> (lane + 1));
@@ -167,32 +172,45 @@ __global__ void __launch_bounds__(kSampleWarps * 32) bisect_sample_kernel(const 
             double old_lp = 0., new_lp = 0.;
             for (int ia = 0; ia < nb; ia += 2 * skip) {
                 const int ib = ia + skip, ic = ia + 2 * skip;
-                double d2_old = 0.;
+                double d2_old = 0., delo[3];
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
                     // RBar(bead_c, bead_a) = r_a + 0.5 * Dr(r_c, r_a)   (path_class.h:124)
                     const double rbar_old = oldb[ia][d] + 0.5 * PutInBox1(oldb[ic][d] - oldb[ia][d], pv.box);
                     const double del_old = PutInBox1(oldb[ib][d] - rbar_old, pv.box);
+                    delo[d] = del_old;
                     d2_old += del_old * del_old;
                     const double rbar_new = newb[ia][d] + 0.5 * PutInBox1(newb[ic][d] - newb[ia][d], pv.box);
                     newb[ib][d] = rbar_new + s_del[w][ib][d];
                 }
-                old_lp -= d2_old * i4lt_sample;
-                new_lp -= s_d2[w][ib] * i4lt_sample;
+                if (a.fs_move.n_images) {  // FreeSpline with images (free_spline_class.h:75-83)
+                    old_lp += FreeLogRho(a.fs_move.s[level], delo);
+                    new_lp -= s_d2[w][ib];
+                } else {
+                    old_lp -= d2_old * i4lt_sample;
+                    new_lp -= s_d2[w][ib] * i4lt_sample;
+                }
             }
             double old_kin = 0., new_kin = 0.;
-            if (a.with_kinetic) {  // Kinetic::GetAction (kinetic_class.h:105-122), n_images = 0
+            if (a.with_kinetic) {  // Kinetic::GetAction (kinetic_class.h:105-122)
                 for (int ia = 0; ia < nb; ia += skip) {
-                    double d2o = 0., d2n = 0.;
+                    double d2o = 0., d2n = 0., ov[3], nv[3];
 #pragma unroll
                     for (int d = 0; d < 3; ++d) {
                         const double o = PutInBox1(oldb[ia][d] - oldb[ia + skip][d], pv.box);
                         const double n = PutInBox1(newb[ia][d] - newb[ia + skip][d], pv.box);
+                        ov[d] = o;
+                        nv[d] = n;
                         d2o += o * o;
                         d2n += n * n;
                     }
-                    old_kin += d2o * i4lt_kin;
-                    new_kin += d2n * i4lt_kin;
+                    if (a.fs_kin.n_images) {
+                        old_kin -= FreeLogRho(a.fs_kin.s[level + 1], ov);
+                        new_kin -= FreeLogRho(a.fs_kin.s[level + 1], nv);
+                    } else {
+                        old_kin += d2o * i4lt_kin;
+                        new_kin += d2n * i4lt_kin;
+                    }
                 }
             }
             const double lsr = -new_lp + old_lp;

@@ -272,6 +272,79 @@ inline std::vector<double> PPFrom2D(const KnotBasis &bx, const KnotBasis &by, co
 /// Interval-search accelerator: buckets of the IEEE-754 bit pattern of x (exponent plus the
 /// top `mant_bits` mantissa bits), lut[key] = a lower bound of the interval index for every x
 /// in the bucket; the device finishes with a forward scan on the grid.
+// ------------------------------------------------------------------------------ FreeSpline
+/// FreeSpline (src/actions/free_spline_class.h:25-67) in pp form: the image-sum tables on the
+/// uniform 10 000-point grid over [-L/2, L/2] (L = 1000 for an open box, :33-35) and their natural
+/// cubic interpolants -- einspline's create_UBspline_1d_d with NATURAL ends is the unique C2
+/// piecewise cubic through the points with zero second derivative at both ends, which is what
+/// KnotBasis + SolveNatural build on the same points.  [zero_lo, zero_hi) is the run of intervals
+/// whose polynomials are zero (|coefficient| < 1e-290: the image sum underflows there).
+struct FreeSplineHost {
+    int n = 0;                         // grid points
+    double start = 0., dr = 0.;
+    double i4lt = 0., i4ltt = 0.;      // 1 / (4 lambda tau), 1 / (4 lambda tau^2)
+    std::vector<double> pp_action;     // [n][4]
+    std::vector<double> pp_dtau;       // [n][4] (use_tau_derivative only)
+    int zero_lo = 0, zero_hi = 0, dtau_zero_lo = 0, dtau_zero_hi = 0;
+};
+
+inline void ZeroRun(const std::vector<double> &pp, int n_int, int &lo, int &hi) {
+    // the longest run of all-zero intervals that contains the grid centre (none: lo = hi = 0)
+    auto is_zero = [&](int i) {
+        for (int k = 0; k < 4; ++k)
+            if (std::fabs(pp[(std::size_t)i * 4 + k]) >= 1e-290) return false;
+        return true;
+    };
+    const int mid = n_int / 2;
+    lo = hi = 0;
+    if (!is_zero(mid)) return;
+    lo = mid;
+    hi = mid + 1;
+    while (lo > 0 && is_zero(lo - 1)) --lo;
+    while (hi < n_int && is_zero(hi)) ++hi;
+}
+
+inline FreeSplineHost BuildFreeSpline(double L, unsigned n_images, double lambda, double tau, bool use_tau_derivative) {
+    FreeSplineHost f;
+    f.i4lt = 1. / (4. * lambda * tau);
+    f.i4ltt = 1. / (4. * lambda * tau * tau);
+    double t_l = L;
+    if (L == 0.) t_l = 1000.;
+    const int num = 10000;
+    f.n = num;
+    f.start = -t_l / 2.;
+    const double end = t_l / 2.;
+    f.dr = (end - f.start) / (num - 1);
+    std::vector<double> grid(num), action(num, 0.), dtau(num, 0.);
+    for (int i = 0; i < num; ++i) {
+        const double r = f.start + i * f.dr;
+        grid[i] = r;
+        const double r2_i4lt = r * r * f.i4lt;
+        for (unsigned image = 1; image <= n_images; ++image) {
+            const double r_p = r + image * t_l, r_m = r - image * t_l;
+            const double d_p = r2_i4lt - r_p * r_p * f.i4lt, d_m = r2_i4lt - r_m * r_m * f.i4lt;
+            const double e_p = std::exp(d_p), e_m = std::exp(d_m);
+            action[i] += e_p + e_m;
+            if (use_tau_derivative) dtau[i] += (d_p * e_p + d_m * e_m) / tau;
+        }
+        if (use_tau_derivative) dtau[i] = dtau[i] / (1. + action[i]);
+        action[i] = -std::log1p(action[i]);
+    }
+    KnotBasis kb;
+    kb.Build(grid.data(), num);
+    std::vector<double> coefs(num + 3, 0.0);
+    SolveNatural(kb, action.data(), 1, coefs.data(), 1);
+    f.pp_action = PPFrom1D(kb, coefs.data());
+    ZeroRun(f.pp_action, num - 1, f.zero_lo, f.zero_hi);
+    if (use_tau_derivative) {
+        std::fill(coefs.begin(), coefs.end(), 0.0);
+        SolveNatural(kb, dtau.data(), 1, coefs.data(), 1);
+        f.pp_dtau = PPFrom1D(kb, coefs.data());
+        ZeroRun(f.pp_dtau, num - 1, f.dtau_zero_lo, f.dtau_zero_hi);
+    }
+    return f;
+}
+
 struct BitLut {
     int shift = 0;        // key = (bits(x) >> shift) - key0, clamped to [0, n_keys)
     long long key0 = 0;

@@ -55,11 +55,13 @@ constexpr int kSweepMaxLevel = 4;
 
 struct SweepFusedArgs {
     PathView pv;
-    double *R;  // committed positions (read and written here: no const, no __restrict__)
+    double *R;   // committed positions [C][N][3][Ms] (the layout of the whole-path kernels): written on acceptance
+    double *R2;  // slice-major mirror [C][Mstore][N][3]: what the windows are gathered from; written on acceptance too
     int N;
     double lambda, tau;
     int n_level;
     int with_kinetic;
+    FreeSplineSet fs_move, fs_kin;  // as in BisectArgs (mc.cuh)
     int b0_lo, b0_count;  // window starts: uniform in [b0_lo, b0_lo + b0_count)
     uint32_t seed_lo, seed_hi;
     unsigned long long attempt0;
@@ -95,6 +97,24 @@ struct SweepShared {
 __device__ __forceinline__ void TeamSync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(kTeamThreads) : "memory"); }
 
 __device__ __forceinline__ void PrefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+/// R[c][row = particle * 3 + dim][slice (row length Ms)] -> R2[c][slice][row]: 32 x 32 tiles through shared
+/// memory, both sides coalesced.  grid (slice tiles, row tiles, clones), block (32, 8).
+__global__ void __launch_bounds__(256) slice_major_kernel(const double *__restrict__ R, int n_rows, int Mstore, int Ms, double *__restrict__ R2) {
+    __shared__ double tile[32][33];
+    const int c = blockIdx.z, s0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const double *src = R + (size_t)c * n_rows * Ms;
+    double *dst = R2 + (size_t)c * Mstore * n_rows;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int row = r0 + i, sl = s0 + threadIdx.x;
+        if (row < n_rows && sl < Mstore) tile[i][threadIdx.x] = src[(size_t)row * Ms + sl];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int sl = s0 + i, row = r0 + threadIdx.x;
+        if (row < n_rows && sl < Mstore) dst[(size_t)sl * n_rows + row] = tile[threadIdx.x][i];
+    }
+}
 
 __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(const SweepFusedArgs a) {
     extern __shared__ __align__(16) unsigned char ssm[];
@@ -141,7 +161,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                 b0 = a.b0_lo + (b0 < a.b0_count ? b0 : a.b0_count - 1);
                 int bg = b0 + j;
                 bg = WrapSlice(pv, bg);
-                const double x = a.R[PosIndex(pv, a.N, c, p_i, d, bg - pv.slice_lo)];
+                const double x = a.R2[(((size_t)c * pv.Mstore + (bg - pv.slice_lo)) * a.N + p_i) * 3 + d];
                 sh.pold[s0 + lc][j][d] = x;
                 sh.pnew[s0 + lc][j][d] = x;
                 if (rem == 0) {
@@ -167,14 +187,15 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                 (void)sd;
                 const double nrm[3] = {ra * cb, ra * sb, rc * cd};
                 const double sigma = sqrt(a.lambda * (a.tau * skip));
-                double d2 = 0.;
+                double d2 = 0., delv[3];
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
                     const double del = PutInBox1(sigma * nrm[d], pv.box);
                     sh.del_new[s0 + lc][ib][d] = del;
+                    delv[d] = del;
                     d2 += del * del;
                 }
-                sh.d2_new[s0 + lc][ib] = d2;
+                sh.d2_new[s0 + lc][ib] = a.fs_move.n_images ? -FreeLogRho(a.fs_move.s[level], delv) : d2;
             } else if (tid >= 3 * kTeamThreads / 4 && tid < 3 * kTeamThreads / 4 + nlc * a.n_level) {  // Metropolis uniforms
                 const int t = tid - 3 * kTeamThreads / 4;
                 const int lc = t / a.n_level, level = t - lc * a.n_level;
@@ -199,31 +220,44 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                     double old_lp = 0., new_lp = 0.;
                     for (int ia = 0; ia < nb; ia += 2 * skip) {
                         const int ib = ia + skip, ic = ia + 2 * skip;
-                        double d2_old = 0.;
+                        double d2_old = 0., delo[3];
 #pragma unroll
                         for (int d = 0; d < 3; ++d) {
                             const double rbar_old = oldb[ia][d] + 0.5 * PutInBox1(oldb[ic][d] - oldb[ia][d], pv.box);
                             const double del_old = PutInBox1(oldb[ib][d] - rbar_old, pv.box);
+                            delo[d] = del_old;
                             d2_old += del_old * del_old;
                             const double rbar_new = newb[ia][d] + 0.5 * PutInBox1(newb[ic][d] - newb[ia][d], pv.box);
                             newb[ib][d] = rbar_new + sh.del_new[sg][ib][d];
                         }
-                        old_lp -= d2_old * i4lt_sample;
-                        new_lp -= sh.d2_new[sg][ib] * i4lt_sample;
+                        if (a.fs_move.n_images) {
+                            old_lp += FreeLogRho(a.fs_move.s[level], delo);
+                            new_lp -= sh.d2_new[sg][ib];
+                        } else {
+                            old_lp -= d2_old * i4lt_sample;
+                            new_lp -= sh.d2_new[sg][ib] * i4lt_sample;
+                        }
                     }
                     double old_kin = 0., new_kin = 0.;
                     if (a.with_kinetic) {
                         for (int ia = 0; ia < nb; ia += skip) {
-                            double d2o = 0., d2n = 0.;
+                            double d2o = 0., d2n = 0., ov[3], nv[3];
 #pragma unroll
                             for (int d = 0; d < 3; ++d) {
                                 const double o = PutInBox1(oldb[ia][d] - oldb[ia + skip][d], pv.box);
                                 const double n = PutInBox1(newb[ia][d] - newb[ia + skip][d], pv.box);
+                                ov[d] = o;
+                                nv[d] = n;
                                 d2o += o * o;
                                 d2n += n * n;
                             }
-                            old_kin += d2o * i4lt_kin;
-                            new_kin += d2n * i4lt_kin;
+                            if (a.fs_kin.n_images) {
+                                old_kin -= FreeLogRho(a.fs_kin.s[level + 1], ov);
+                                new_kin -= FreeLogRho(a.fs_kin.s[level + 1], nv);
+                            } else {
+                                old_kin += d2o * i4lt_kin;
+                                new_kin += d2n * i4lt_kin;
+                            }
                         }
                     }
                     const double lsr = -new_lp + old_lp;
@@ -244,13 +278,15 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                 const int bead0 = sh.bead0[sg];
                 int b_last = bead0 + nb;
                 b_last = WrapSlice(pv, b_last);
-                const double *Rc = a.R + PosIndex(pv, a.N, c_grp, 0, 0, 0);
-                const int n_rows = a.N * 3;
-                for (int row = tg - 1; row < n_rows; row += kSweepGroup - 1) {
-                    const double *first = Rc + (size_t)row * pv.Ms + bead0 - pv.slice_lo;
-                    const double *last = Rc + (size_t)row * pv.Ms + b_last - pv.slice_lo;
-                    PrefetchL2(first);
-                    if (((uintptr_t)first >> 7) != ((uintptr_t)last >> 7)) PrefetchL2(last);  // second 128-byte line, or the wrapped end
+                (void)b_last;
+                // the window's nb + 1 slices of the slice-major mirror: contiguous blocks of N * 24 bytes
+                const int slice_bytes = a.N * 24, lines = (slice_bytes + 127) / 128;
+                for (int t = tg - 1; t < (nb + 1) * lines; t += kSweepGroup - 1) {
+                    const int j = t / lines, l = t - j * lines;
+                    int bg = bead0 + j;
+                    bg = WrapSlice(pv, bg);
+                    const char *p = reinterpret_cast<const char *>(a.R2 + ((size_t)c_grp * pv.Mstore + (bg - pv.slice_lo)) * a.N * 3);
+                    PrefetchL2(p + min(l * 128, slice_bytes - 8));
                 }
                 if (n_k > 0) {
                     const int lines = (n_k * (int)sizeof(double2) + 127) / 128;
@@ -287,20 +323,19 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                     // volatile: not hoisted) -- holding OLD and NEW copies in registers spills at 64
                     const uint32_t po_addr = (uint32_t)__cvta_generic_to_shared(&sh.pold[s0 + lc][j][0]);
                     const uint32_t pn_addr = (uint32_t)__cvta_generic_to_shared(&sh.pnew[s0 + lc][j][0]);
-                    // 32-bit offsets inside the clone's block of rows
-                    const double *Rc = a.R + PosIndex(pv, a.N, c, 0, 0, 0);
-                    const unsigned row_stride = 3u * (unsigned)pv.Ms, ms = (unsigned)pv.Ms;
-                    const unsigned o0 = (unsigned)(b0s - pv.slice_lo), o1 = (unsigned)(b1s - pv.slice_lo);
+                    // 32-bit offsets inside the clone's block of the slice-major mirror
+                    const double *Rc = a.R2 + (size_t)c * pv.Mstore * a.N * 3;
+                    const unsigned o0 = (unsigned)(b0s - pv.slice_lo) * (unsigned)a.N * 3u, o1 = (unsigned)(b1s - pv.slice_lo) * (unsigned)a.N * 3u;
                     double acc_old = 0., acc_new = 0.;
                     for (int g = warp; g < n_groups; g += kTeamWarps) {
                         const int q = g * per_warp + sub;
                         const bool on = q < a.N && q != p;
-                        const unsigned row = (unsigned)(q < a.N ? q : a.N - 1) * row_stride;
+                        const unsigned row = (unsigned)(q < a.N ? q : a.N - 1) * 3u;
                         double q0[3], q1[3];
 #pragma unroll
                         for (int d = 0; d < 3; ++d) {
-                            q0[d] = Rc[row + d * ms + o0];
-                            q1[d] = Rc[row + d * ms + o1];
+                            q0[d] = Rc[o0 + row + d];
+                            q1[d] = Rc[o1 + row + d];
                         }
                         // both sets of distances first: the partner's beads die before the table work
                         double ro, rpo, so, rn, rpn, sn, m0[3], m1[3];
@@ -394,6 +429,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                     int bg = bead0 + j;
                     bg = WrapSlice(pv, bg);
                     a.R[PosIndex(pv, a.N, c_grp, p, d, bg - pv.slice_lo)] = sh.pnew[sg][j][d];
+                    a.R2[(((size_t)c_grp * pv.Mstore + (bg - pv.slice_lo)) * a.N + p) * 3 + d] = sh.pnew[sg][j][d];
                 }
                 if (n_k > 0) {
                     // slice 0 of the window keeps its bead; the others take rho_k + delta as phase C left it

@@ -53,8 +53,8 @@ class Path:
             self.SetupKSpace(cfg.k_cut)
         self.actions = []
         for a in cfg.actions:
-            self.actions.append(None if a.type == "Kinetic" else PairAction(self, a))
-        if any(a is not None and a.use_long_range for a in self.actions):
+            self.actions.append(Kinetic(self, a) if a.type == "Kinetic" else PairAction(self, a))
+        if any(a.use_long_range for a in self.actions):
             self.n_k = self._n_k()
 
     def close(self):
@@ -145,6 +145,10 @@ class Path:
         accept = np.ascontiguousarray(np.broadcast_to(accept, (self.n_clones,)), dtype=np.int32)
         capi.check(self.L.pimc_commit(self.h, _vp(accept)))
 
+    def SetMoveImages(self, species, n_images):
+        """Bisect's n_images attribute (bisect_class.h:173) for later BisectSweep calls on `species`."""
+        capi.check(self.L.pimc_move_set_images(self.h, species, int(n_images)))
+
     def BisectSweep(self, species, n_level, n_attempts, seed, attempt0=0, with_kinetic=True):
         """n_attempts device-resident Bisect::DoEvent calls per clone; returns accepts per clone."""
         n_accept = np.zeros(self.n_clones, dtype=np.int64)
@@ -195,6 +199,67 @@ class Path:
         t = C.c_double()
         capi.check(self.L.pimc_fp64_peak(self.h, C.byref(t)))
         return t.value
+
+
+class Kinetic:
+    """src/actions/single_action/kinetic_class.h on the device: the free-particle action of one
+    species with `n_images` periodic images (FreeSpline, free_spline_class.h:25-84)."""
+
+    def __init__(self, path, acfg):
+        self.path = path
+        self.L = path.L
+        self.name = acfg.name
+        self.type = "Kinetic"
+        self.use_long_range = False
+        self.max_level = acfg.max_level
+        self.n_images = int(acfg.n_images)
+        self.is_importance_weight = False
+        self.species_a = self.species_b = path.cfg.species_index(acfg.species_a)
+        h = C.c_void_p()
+        capi.check(self.L.pimc_action_create_kinetic(path.h, self.species_a, self.n_images, C.byref(h)))
+        self.h = h
+
+    def _full(self, fn):
+        out = np.zeros(self.path.n_clones)
+        capi.check(fn(self.h, _vp(out)))
+        return out
+
+    def DActionDBeta(self):
+        """kinetic_class.h:35-45: N M n_d / (2 tau) + sum over links of dlog rho_free / dtau."""
+        return self._full(self.L.pimc_action_dbeta)
+
+    def Potential(self):
+        return self._full(self.L.pimc_action_potential)    # Action's default: 0 (action_class.h:43)
+
+    def TotalAction(self):
+        return self._full(self.L.pimc_action_total)
+
+    def GetAction(self, b0, b1, particles, level):
+        """kinetic_class.h:105-122: -sum over the listed particles of this species and the links of stride
+        2^level in [b0, b1) of log rho_free; arguments as PairAction.GetAction."""
+        C_ = self.path.n_clones
+        b0a = np.ascontiguousarray(np.broadcast_to(b0, (C_,)), dtype=np.int32)
+        n_window = int(np.broadcast_to(b1, (C_,))[0] - b0a[0])
+        sp = np.ascontiguousarray([p[0] for p in particles], dtype=np.int32)
+        pi = np.zeros((C_, len(particles)), dtype=np.int32)
+        for i, p in enumerate(particles):
+            pi[:, i] = np.broadcast_to(p[1], (C_,))
+        out = np.zeros(C_)
+        capi.check(self.L.pimc_action_get(self.h, self.path.mode, _vp(b0a), n_window, len(particles), _vp(sp), _vp(pi), level,
+                                          _vp(out)))
+        return out
+
+    def VirialEnergy(self, virial_window_size=1):
+        raise NotImplementedError("Kinetic::VirialEnergy (kinetic_class.h:48-102) is outside the device path")
+
+    def ImportanceWeight(self):
+        return np.ones(self.path.n_clones)
+
+    def Accept(self):
+        pass
+
+    def Reject(self):
+        pass
 
 
 class PairAction:
@@ -395,7 +460,7 @@ class Energy:
     def __init__(self, path, measure_potential=False):
         self.path = path
         self.measure_potential = measure_potential
-        self.actions = [a for a in path.actions if a is not None]
+        self.actions = list(path.actions)   # energy_class.h:22-33: every action, Kinetic included
         self.Reset()
 
     def Reset(self):

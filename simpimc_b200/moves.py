@@ -7,9 +7,9 @@ the clones of a `host.Path`:
 Same call sequence as the reference: pick particle and window, Levy-sample the midpoints
 level by level (NEW mode), evaluate every action in OLD then NEW mode, Metropolis-test the
 difference, then Accept (StoreR / StoreRhoK) or Reject.  The pair actions run on the GPU
-through the C ABI; the free-particle (kinetic) action is evaluated here in closed form,
-which is what src/actions/single_action/kinetic_class.h:105-122 computes when n_images = 0
-(FreeSpline's image sum is then identically zero, free_spline_class.h:47-62).
+through the C ABI; the free-particle (kinetic) action and the Levy sampling probabilities are
+evaluated here with the host mirror of FreeSpline (free_spline.py; with n_images = 0 the closed
+form -|r|^2 / 4 lambda tau that src/actions/single_action/kinetic_class.h:105-122 reduces to).
 Random numbers come from numpy's Generator, not std::mt19937: sampled runs agree with the
 reference statistically, not stream for stream.
 """
@@ -18,6 +18,7 @@ import math
 import numpy as np
 
 from . import host
+from .free_spline import FreeSpline
 
 
 def _put_in_box(d, L, pbc):
@@ -33,16 +34,21 @@ class _Move:
         self.cfg = path.cfg
         self.lam = self.cfg.species[species].lam
         self.with_kinetic = with_kinetic and self.lam > 0.0
-        # move_class.h:27-31: the actions that involve this species
-        self.action_list = [a for a in path.actions if a is not None and species in (a.species_a, a.species_b)]
+        # move_class.h:27-31: the actions that involve this species (the Kinetic action is evaluated by the
+        # host mirror below, with the n_images of the path's Kinetic object when there is one)
+        self.action_list = [a for a in path.actions if a.type != "Kinetic" and species in (a.species_a, a.species_b)]
+        kin = [a for a in path.actions if a.type == "Kinetic" and a.species_a == species]
+        self.kinetic_images = kin[0].n_images if kin else 0
         self.n_attempt = 0
         self.n_accept = np.zeros(path.n_clones, dtype=np.int64)
 
     def _dr(self, a, b):
         return _put_in_box(a - b, self.cfg.L, self.cfg.pbc)
 
-    def _kinetic_log_rho(self, dr, level_tau):
-        # FreeSpline::GetLogRhoFree with no images: -|r|^2 / (4 lambda tau)
+    def _kinetic_log_rho(self, dr, level_tau, n_images=0):
+        # FreeSpline::GetLogRhoFree; with no images: -|r|^2 / (4 lambda tau)
+        if n_images:
+            return _free_spline(self.cfg, self.lam, n_images, level_tau).GetLogRhoFree(dr)
         return -np.sum(dr * dr, axis=-1) / (4.0 * self.lam * level_tau)
 
     def accept_ratio(self):
@@ -50,8 +56,9 @@ class _Move:
 
 
 class Bisect(_Move):
-    def __init__(self, path, rng, species, n_level, with_kinetic=True):
+    def __init__(self, path, rng, species, n_level, with_kinetic=True, n_images=0):
         super().__init__(path, rng, species, with_kinetic)
+        self.n_images = int(n_images)   # bisect_class.h:173
         self.n_level = n_level
         self.n_bisect_beads = 1 << n_level
 
@@ -79,17 +86,17 @@ class Bisect(_Move):
                 b, c = a + skip, a + 2 * skip
                 # RBar(bead_c, bead_a) = r_a + 0.5 * Dr(r_c, r_a)   (path_class.h:124)
                 rbar_old = old[:, a] + 0.5 * self._dr(old[:, c], old[:, a])
-                old_lp += self._kinetic_log_rho(self._dr(old[:, b], rbar_old), 0.5 * level_tau)
+                old_lp += self._kinetic_log_rho(self._dr(old[:, b], rbar_old), 0.5 * level_tau, self.n_images)
                 rbar_new = new[:, a] + 0.5 * self._dr(new[:, c], new[:, a])
                 delta = _put_in_box(self.rng.normal(0.0, sigma, (C, cfg.n_d)), cfg.L, cfg.pbc)
                 new[:, b] = rbar_new + delta
-                new_lp += self._kinetic_log_rho(delta, 0.5 * level_tau)
+                new_lp += self._kinetic_log_rho(delta, 0.5 * level_tau, self.n_images)
             old_action = np.zeros(C)
             new_action = np.zeros(C)
             if self.with_kinetic:  # Kinetic::GetAction (kinetic_class.h:105-122)
                 for a in range(0, nb, skip):
-                    old_action -= self._kinetic_log_rho(self._dr(old[:, a], old[:, a + skip]), level_tau)
-                    new_action -= self._kinetic_log_rho(self._dr(new[:, a], new[:, a + skip]), level_tau)
+                    old_action -= self._kinetic_log_rho(self._dr(old[:, a], old[:, a + skip]), level_tau, self.kinetic_images)
+                    new_action -= self._kinetic_log_rho(self._dr(new[:, a], new[:, a + skip]), level_tau, self.kinetic_images)
             if level == 0 and self.action_list:
                 # pair actions return 0 above max_level = 0 (pair_action_class.h:269)
                 path.Propose(self.species, p_i, (bead0 + 1) % M, new[:, 1:nb])
@@ -139,8 +146,18 @@ class DisplaceParticle(_Move):
         return accept
 
 
+_FS_CACHE = {}
+
+
+def _free_spline(cfg, lam, n_images, tau_s):
+    key = (cfg.L if cfg.pbc else 0.0, int(n_images), lam, tau_s)
+    if key not in _FS_CACHE:
+        _FS_CACHE[key] = FreeSpline(key[0], n_images, lam, tau_s)
+    return _FS_CACHE[key]
+
+
 def bisect_attempt_philox(cfg, species, n_level, seed, attempt, n_clones, get_beads, action_old_new, finish, with_kinetic=True,
-                          b0_range=None):
+                          b0_range=None, n_images_move=0, n_images_kin=0):
     """Host mirror of ONE device-resident bisection attempt (csrc/mc.cuh: bisect_sample_kernel +
     pair_window_both_kernel + k-sums + bisect_decide_kernel) drawing the same Philox stream.
 
@@ -150,6 +167,8 @@ def bisect_attempt_philox(cfg, species, n_level, seed, attempt, n_clones, get_be
     finish(c, p, bead0, nb, accept)      -> Move::Accept / Reject
     b0_range = (first, count): window starts uniform in [first, first + count) -- a slice shard's
     interior windows (pimc_bisect_sweep on a sharded context); default: the whole path.
+    n_images_move / n_images_kin: periodic images of Bisect's sampling splines (bisect_class.h:158-163,173)
+    and of the Kinetic action (kinetic_class.h:16-24), evaluated with the FreeSpline host mirror.
     Returns (particle[c], bead0[c], accept[c]).
     """
     from . import philox as PX
@@ -191,14 +210,24 @@ def bisect_attempt_philox(cfg, species, n_level, seed, attempt, n_clones, get_be
                 rbar_new = new[ia] + 0.5 * pib(new[ic] - new[ia])
                 del_new = pib(sigma * nrm)
                 new[ib] = rbar_new + del_new
-                old_lp -= float(np.sum(del_old * del_old)) * i4s
-                new_lp -= float(np.sum(del_new * del_new)) * i4s
+                if n_images_move:
+                    fs = _free_spline(cfg, lam, n_images_move, 0.5 * level_tau)
+                    old_lp += float(fs.GetLogRhoFree(del_old))
+                    new_lp += float(fs.GetLogRhoFree(del_new))
+                else:
+                    old_lp -= float(np.sum(del_old * del_old)) * i4s
+                    new_lp -= float(np.sum(del_new * del_new)) * i4s
             old_kin = new_kin = 0.0
             if with_kinetic:
+                fk = _free_spline(cfg, lam, n_images_kin, level_tau) if n_images_kin else None
                 for ia in range(0, nb, skip):
                     o, n_ = pib(old[ia] - old[ia + skip]), pib(new[ia] - new[ia + skip])
-                    old_kin += float(np.sum(o * o)) * i4k
-                    new_kin += float(np.sum(n_ * n_)) * i4k
+                    if fk is not None:
+                        old_kin -= float(fk.GetLogRhoFree(o))
+                        new_kin -= float(fk.GetLogRhoFree(n_))
+                    else:
+                        old_kin += float(np.sum(o * o)) * i4k
+                        new_kin += float(np.sum(n_ * n_)) * i4k
             ru = PX.philox4x32(a_lo, a_hi, c, slot, k0, k1)
             slot += 1
             logu = math.log(PX.uniform_from_bits(ru[0], ru[1]))

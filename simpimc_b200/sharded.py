@@ -122,7 +122,7 @@ class ShardedPath:
         self.device = torch.device("cuda", device)
         self.stream = torch.cuda.ExternalStream(self.lib.pimc_ctx_stream(self.path.h), device=self.device)
         self.actions = self.path.actions
-        self.pair_actions = [a for a in self.actions if a is not None]
+        self.pair_actions = [a for a in self.actions if a.type != "Kinetic"]
         if unique_id is None:
             unique_id = bootstrap_unique_id(self.lib, rank, world, group)
         elif isinstance(unique_id, (bytes, bytearray)):

@@ -71,7 +71,7 @@ def ueg_parameters(N, rs=1.0, theta=1.0, polarized=True):
 
 
 def ueg_config(N=256, M=128, rs=1.0, theta=1.0, action="IlkkaPairAction", use_long_range=True, n_xy=100, n_r_long=1000,
-               with_kinetic=False, david_grid="LOG", david_n_grid=200, david_n_order=2):
+               with_kinetic=False, david_grid="LOG", david_n_grid=200, david_n_order=2, xy_asym=None):
     """Uniform electron gas, one species "e" (SURVEY.md 8(d), config C3 at the defaults)."""
     L, k_cut, beta = ueg_parameters(N, rs, theta)
     tau = beta / M
@@ -80,7 +80,9 @@ def ueg_config(N=256, M=128, rs=1.0, theta=1.0, action="IlkkaPairAction", use_lo
     if with_kinetic:
         cfg.actions.append(ActionConfig("Kinetic", "Kinetic", "e"))
     if action == "IlkkaPairAction":
-        tab = T.make_ilkka_table(1.0, tau, L, k_cut, use_long_range=use_long_range, n_xy=n_xy, n_r_long=n_r_long)
+        # xy_asym = (n_y, y_r_max, asym): an off-diagonal table with its own y grid and no x <-> y symmetry
+        extra = {} if xy_asym is None else dict(n_y=xy_asym[0], y_r_max=xy_asym[1], asym=xy_asym[2])
+        tab = T.make_ilkka_table(1.0, tau, L, k_cut, use_long_range=use_long_range, n_xy=n_xy, n_r_long=n_r_long, **extra)
     elif action == "BarePairAction":
         tab = T.make_bare_table(1.0, L, k_cut, use_long_range=use_long_range, n_r_long=n_r_long)
     elif action == "DavidPairAction":

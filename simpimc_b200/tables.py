@@ -103,17 +103,24 @@ def _soft_coulomb(r, sigma):
 
 
 def make_ilkka_table(z1z2, tau, L, k_cut, use_long_range=True, n_xy=100, xy_r_max=100.0, n_r=1000, r_min=1.0e-4,
-                     r_max=100.0, n_r_long=1000, sigma=0.5):
+                     r_max=100.0, n_r_long=1000, sigma=0.5, n_y=None, y_r_max=None, asym=0.0):
     """Analytic stand-in for an Ilkka squarer table.
 
     Grids as inputs/e-gas/gen_e_pa.py:40-69 configures them: OPTIMIZED n=100 up to 100 for
     the off-diagonal u(x,y), du(x,y) (the squarer's own grid starts at 0,
     scripts/pagen/ilkkaSquarer/init.f90:962-968), OPTIMIZED n=1000 on [1e-4,100] for v(r),
     OPTIMIZED n=1000 on [1e-4, sqrt(3) L/2] for the long-range r parts.
+
+    The squarer's table is square, on one radial grid for both axes, and the surrogate above is
+    symmetric in (x, y) -- which would hide an x / y transposition or a row- versus column-major
+    mix-up anywhere between this dict and the kernels.  n_y / y_r_max give the y axis its own
+    grid (n_x != n_y) and asym > 0 multiplies the surfaces by 1 + asym X / (1 + X): a table no
+    transposition leaves invariant (parity config "ilkka_asym").
     """
     t = {}
     xs = gen_grid("OPTIMIZED", 0.0, xy_r_max, n_xy)
-    X, Y = np.meshgrid(xs, xs, indexing="ij")
+    ys = xs if n_y is None else gen_grid("OPTIMIZED", 0.0, xy_r_max if y_r_max is None else y_r_max, n_y)
+    X, Y = np.meshgrid(xs, ys, indexing="ij")
     D = X - Y
     vs_x, vs_y = _soft_coulomb(X, sigma), _soft_coulomb(Y, sigma)
     # u: endpoint average of a softened Coulomb times a smooth off-diagonal damping
@@ -122,11 +129,14 @@ def make_ilkka_table(z1z2, tau, L, k_cut, use_long_range=True, n_xy=100, xy_r_ma
     ws_x = _soft_coulomb(X, 0.8 * sigma) * (1.0 + 0.25 * np.exp(-X * X / (2 * sigma * sigma)))
     ws_y = _soft_coulomb(Y, 0.8 * sigma) * (1.0 + 0.25 * np.exp(-Y * Y / (2 * sigma * sigma)))
     du_xy = z1z2 * 0.5 * (ws_x + ws_y) * (1.0 - 0.2 * D * D / (3.0 * sigma * sigma + D * D))
+    if asym:
+        u_xy = u_xy * (1.0 + asym * X / (1.0 + X))
+        du_xy = du_xy * (1.0 + 0.5 * asym * X / (1.0 + X))
     for name, arr in (("u", u_xy), ("du", du_xy)):
-        t[name + "/off_diag/n_x"] = np.uint32(n_xy)
-        t[name + "/off_diag/n_y"] = np.uint32(n_xy)
+        t[name + "/off_diag/n_x"] = np.uint32(len(xs))
+        t[name + "/off_diag/n_y"] = np.uint32(len(ys))
         t[name + "/off_diag/x"] = _r10(xs)
-        t[name + "/off_diag/y"] = _r10(xs)
+        t[name + "/off_diag/y"] = _r10(ys)
         t[name + "/off_diag/%s_xy" % name] = _r10(arr)
     rv = gen_grid("OPTIMIZED", r_min, r_max, n_r)
     t["v/diag/n_r"] = np.uint32(n_r)

@@ -25,6 +25,8 @@ CONFIGS = {
     "bare_lr_n7": lambda: S.ueg_config(N=7, M=8, action="BarePairAction"),
     "david_n7": lambda: S.ueg_config(N=7, M=8, action="DavidPairAction", use_long_range=False),
     "plasma": lambda: S.plasma_config(Ne=6, Np=5, M=8),
+    # off-diagonal table with n_x != n_y, different x and y grids and no x <-> y symmetry (a transposition would show)
+    "ilkka_asym": lambda: S.ueg_config(N=9, M=8, n_xy=80, xy_asym=(64, 60.0, 0.3)),
 }
 
 

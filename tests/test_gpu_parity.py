@@ -45,6 +45,8 @@ CONFIGS = {
     "david_n7": lambda: S.ueg_config(N=7, M=8, action="DavidPairAction", use_long_range=False),
     "david_lr_n7": lambda: S.ueg_config(N=7, M=8, action="DavidPairAction", use_long_range=True),
     "plasma": lambda: S.plasma_config(Ne=6, Np=5, M=8),
+    # off-diagonal table with n_x != n_y, different x and y grids and no x <-> y symmetry (a transposition would show)
+    "ilkka_asym": lambda: S.ueg_config(N=9, M=8, n_xy=80, xy_asym=(64, 60.0, 0.3)),
     "n2": lambda: S.ueg_config(N=2, M=4),
     # David tables on a linear grid (uniform interval table), M > 32 (two slice chunks, lane-31 ring), even N
     "david_lin_n34": lambda: S.ueg_config(N=34, M=40, action="DavidPairAction", use_long_range=False, david_grid="LINEAR",
@@ -65,7 +67,7 @@ def test_full_path_values(name):
     cfg = CONFIGS[name]()
     path, oracles, _ = make_pair(cfg, 3)
     for ai, act in enumerate(path.actions):
-        if act is None:
+        if act.type == "Kinetic":
             continue
         du, u = act.DActionDBeta(), act.TotalAction()
         # GetAction(0, M, every particle, 0) in OLD mode is the whole-path action
@@ -81,7 +83,7 @@ def test_full_path_values(name):
     path.close()
 
 
-@pytest.mark.parametrize("name", ["ilkka_lr_n7", "bare_lr_n7", "david_n7", "plasma"])
+@pytest.mark.parametrize("name", ["ilkka_lr_n7", "bare_lr_n7", "david_n7", "plasma", "ilkka_asym"])
 def test_per_pair_kernels(name):
     cfg = CONFIGS[name]()
     path, oracles, _ = make_pair(cfg, 1)
@@ -96,7 +98,7 @@ def test_per_pair_kernels(name):
     rp[:4] = [1e-5, rmax * 1.5, 0.3, 2.0]
     s[:4] = [0.0, 0.1, 0.0, 0.0]
     for ai, act in enumerate(path.actions):
-        if act is None:
+        if act.type == "Kinetic":
             continue
         for which in (0, 1, 2):
             got = act.CalcPair(which, r, rp, s)
@@ -122,7 +124,7 @@ def test_kspace_and_rhok(name):
     path.close()
 
 
-@pytest.mark.parametrize("name", ["ilkka_lr_n7", "ilkka_lr_n33", "bare_lr_n7", "david_n7", "plasma", "ilkka_nolr_n8"])
+@pytest.mark.parametrize("name", ["ilkka_lr_n7", "ilkka_lr_n33", "bare_lr_n7", "david_n7", "plasma", "ilkka_nolr_n8", "ilkka_asym"])
 def test_move_windows_old_new_commit(name):
     """Bisect-style windows (incl. wrap-around b1 > n_bead) and a displace-style whole-path
     move: OLD and NEW GetAction, their difference, and the state after accept / reject."""
@@ -154,7 +156,7 @@ def test_move_windows_old_new_commit(name):
             o.propose(sp, int(part[c]), int(first[c]), newR[c])
         sums = {}
         for ai, act in enumerate(path.actions):
-            if act is None or sp not in (act.species_a, act.species_b):
+            if act.type == "Kinetic" or sp not in (act.species_a, act.species_b):
                 continue
             path.SetMode(host.OLD_MODE)
             old = act.GetAction(b0, b0 + nb, [(sp, part)], 0)
@@ -180,7 +182,7 @@ def test_move_windows_old_new_commit(name):
                 assert np.max(np.abs(path.GetRhoK(sp, c, host.OLD_MODE) - o.rhok(sp, 0))) <= 1e-11 * N
     # after the moves the full-path values still agree
     for ai, act in enumerate(path.actions):
-        if act is None:
+        if act.type == "Kinetic":
             continue
         du = act.DActionDBeta()
         for c, o in enumerate(oracles):
@@ -269,7 +271,7 @@ def test_errors_are_loud():
     shard.close()
 
 
-@pytest.mark.parametrize("name", ["ilkka_lr_n7", "ilkka_lr_n33", "ilkka_nolr_n8", "plasma", "n2", "david_n7", "david_lr_n7",
+@pytest.mark.parametrize("name", ["ilkka_lr_n7", "ilkka_lr_n33", "ilkka_nolr_n8", "plasma", "n2", "ilkka_asym", "david_n7", "david_lr_n7",
                                   "david_lin_n34", "david_log_n33", "david_o1_n9", "david_o3_n9", "plasma_david", "david_log_n70"])
 def test_fast_and_general_kernels_agree_with_oracle(name):
     """The whole-path Ilkka, Bare and David evaluations run through the shared-memory fast kernels

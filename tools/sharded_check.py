@@ -55,7 +55,8 @@ def main():
     torch.cuda.synchronize()
     replay()
     sp_path.path.Sync()
-    graph_ok = bool(np.array_equal(out_g.cpu().numpy(), np.stack(du)))
+    # equal to rounding: NCCL may order the captured all-reduce differently from the eager one (bit-identical at 2 ranks)
+    graph_ok = bool(np.max(np.abs(out_g.cpu().numpy() - np.stack(du)) / np.abs(np.stack(du))) <= 1e-13)
     counts = sp_path.PairCorrelationCounts(0, 1, 0.0, cfg.L / 2, 100)
     ok = True
     err = 0.0
@@ -71,7 +72,7 @@ def main():
         whole.close()
         n_pairs = Ne * (Ne - 1) + Ne * Ne
         print(json.dumps({"check": "slice-sharded plasma", "n_gpus": world, "N": 2 * Ne, "M": M, "clones": C, "max_rel_err_vs_unsharded": err,
-                          "gofr_bins_equal": bool(np.array_equal(counts, ref_counts)), "graph_replay_bit_identical": graph_ok,
+                          "gofr_bins_equal": bool(np.array_equal(counts, ref_counts)), "graph_replay_matches_eager": graph_ok,
                           "graph_nodes": replay.n_nodes, "comm_bytes_sent_rank0": sp_path.BytesSent(), "ok": bool(ok),
                           "dbeta_3_actions_ms": 1e3 * (t1 - t0), "pair_slice_evals": n_pairs * M * C}), flush=True)
     # ---- moves on the sharded path: shard-interior bisection windows, ring rotation over NCCL ----
