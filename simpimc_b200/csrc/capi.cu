@@ -2238,7 +2238,7 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
     if (fused && n_attempts > 0) {
         pimc_action *a = acts[0];
         SweepFusedArgs f;
-        if (!st.R2_valid) {
+        if (PIMC_SWEEP_MIRROR && !st.R2_valid) {
             const size_t n2 = (size_t)C * ctx->Mstore * st.N * 3;
             if (st.R2.n != n2) PIMC_CUDA(st.R2.Alloc(n2));
             dim3 tgrid((ctx->Mstore + 31) / 32, (st.N * 3 + 31) / 32, C);
@@ -2271,10 +2271,12 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
         f.wk = any_lr ? a->wk[WHICH_U].p : nullptr;
         f.lr_factor = a->ulong_scale;
         f.n_accept = ctx->mc_naccept.p;
-        PIMC_CUDA(cudaFuncSetAttribute(bisect_sweep_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
+        const bool images = f.fs_move.n_images > 0 || f.fs_kin.n_images > 0;
+        auto *kernel = images ? bisect_sweep_fused_kernel<true> : bisect_sweep_fused_kernel<false>;
+        PIMC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
         {
             ScopedKernelTimer t(ctx, PIMC_KERNEL_PAIR_WINDOW);
-            bisect_sweep_fused_kernel<<<std::min(C, ctx->n_sm), kSweepThreads, fused_smem, ctx->stream>>>(f);
+            kernel<<<std::min(C, ctx->n_sm), kSweepThreads, fused_smem, ctx->stream>>>(f);
         }
         ctx->launches++;
     }

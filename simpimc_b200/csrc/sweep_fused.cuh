@@ -50,6 +50,15 @@ constexpr int kTeamClones = (kSweepThreads / 128) / kSweepTeams;  // clones a te
 constexpr int kSweepClones = kSweepTeams * kTeamClones;      // clones in flight per CTA
 constexpr int kSweepGroup = kTeamThreads / kTeamClones;      // threads that own one clone in phases C-E
 constexpr int kSweepGroupWarps = kSweepGroup / 32;
+// Where the windows' partner beads are gathered from (A/B, tools/gpu_ab_sweep2.sh): 0 = the whole-path layout R
+// ([particle][dim][slice]: 72-byte fragments of 128-byte lines), 1 = slice-major mirror [slice][particle][dim],
+// 2 = slice-major mirror [slice][dim][particle]
+// Measured at C3 (1024 clones, 256 attempts, ms per attempt): 0 -> 0.0750, 1 -> 0.0815, 2 -> 0.0860.  The mirrors cut the
+// DRAM traffic but every load instruction then touches 8 lines (one per slice) instead of 4 (one per partner):
+// the gather is bound by L1 request processing and latency, not by DRAM bytes, so the whole-path layout stays.
+#ifndef PIMC_SWEEP_MIRROR
+#define PIMC_SWEEP_MIRROR 0
+#endif
 constexpr int kSweepMaxBeads = 16;                           // 2^n_level <= 16
 constexpr int kSweepMaxLevel = 4;
 
@@ -98,6 +107,16 @@ __device__ __forceinline__ void TeamSync(int team) { asm volatile("bar.sync %0, 
 
 __device__ __forceinline__ void PrefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+/// Offset of (particle q, dim d) inside one slice block of the mirror.
+__device__ __forceinline__ unsigned MirrorRow(int N, int q, int d) {
+#if PIMC_SWEEP_MIRROR == 2
+    return (unsigned)(d * N + q);
+#else
+    (void)N;
+    return (unsigned)(q * 3 + d);
+#endif
+}
+
 /// R[c][row = particle * 3 + dim][slice (row length Ms)] -> R2[c][slice][row]: 32 x 32 tiles through shared
 /// memory, both sides coalesced.  grid (slice tiles, row tiles, clones), block (32, 8).
 __global__ void __launch_bounds__(256) slice_major_kernel(const double *__restrict__ R, int n_rows, int Mstore, int Ms, double *__restrict__ R2) {
@@ -112,10 +131,13 @@ __global__ void __launch_bounds__(256) slice_major_kernel(const double *__restri
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += 8) {
         const int sl = s0 + i, row = r0 + threadIdx.x;
-        if (row < n_rows && sl < Mstore) dst[(size_t)sl * n_rows + row] = tile[threadIdx.x][i];
+        if (row < n_rows && sl < Mstore) dst[(size_t)sl * n_rows + MirrorRow(n_rows / 3, row / 3, row % 3)] = tile[threadIdx.x][i];
     }
 }
 
+/// IMAGES: the FreeSpline branches (periodic images of the free-particle density matrix) are compiled in; the
+/// n_images = 0 instantiation keeps the closed forms only (0.0750 vs 0.0790 ms per attempt at C3).
+template <bool IMAGES>
 __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(const SweepFusedArgs a) {
     extern __shared__ __align__(16) unsigned char ssm[];
     __shared__ SweepShared sh;
@@ -161,7 +183,11 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                 b0 = a.b0_lo + (b0 < a.b0_count ? b0 : a.b0_count - 1);
                 int bg = b0 + j;
                 bg = WrapSlice(pv, bg);
-                const double x = a.R2[(((size_t)c * pv.Mstore + (bg - pv.slice_lo)) * a.N + p_i) * 3 + d];
+#if PIMC_SWEEP_MIRROR
+                const double x = a.R2[((size_t)c * pv.Mstore + (bg - pv.slice_lo)) * a.N * 3 + MirrorRow(a.N, p_i, d)];
+#else
+                const double x = a.R[PosIndex(pv, a.N, c, p_i, d, bg - pv.slice_lo)];
+#endif
                 sh.pold[s0 + lc][j][d] = x;
                 sh.pnew[s0 + lc][j][d] = x;
                 if (rem == 0) {
@@ -195,7 +221,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                     delv[d] = del;
                     d2 += del * del;
                 }
-                sh.d2_new[s0 + lc][ib] = a.fs_move.n_images ? -FreeLogRho(a.fs_move.s[level], delv) : d2;
+                sh.d2_new[s0 + lc][ib] = (IMAGES && a.fs_move.n_images) ? -FreeLogRho(a.fs_move.s[level], delv) : d2;
             } else if (tid >= 3 * kTeamThreads / 4 && tid < 3 * kTeamThreads / 4 + nlc * a.n_level) {  // Metropolis uniforms
                 const int t = tid - 3 * kTeamThreads / 4;
                 const int lc = t / a.n_level, level = t - lc * a.n_level;
@@ -230,7 +256,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                             const double rbar_new = newb[ia][d] + 0.5 * PutInBox1(newb[ic][d] - newb[ia][d], pv.box);
                             newb[ib][d] = rbar_new + sh.del_new[sg][ib][d];
                         }
-                        if (a.fs_move.n_images) {
+                        if (IMAGES && a.fs_move.n_images) {
                             old_lp += FreeLogRho(a.fs_move.s[level], delo);
                             new_lp -= sh.d2_new[sg][ib];
                         } else {
@@ -251,7 +277,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                                 d2o += o * o;
                                 d2n += n * n;
                             }
-                            if (a.fs_kin.n_images) {
+                            if (IMAGES && a.fs_kin.n_images) {
                                 old_kin -= FreeLogRho(a.fs_kin.s[level + 1], ov);
                                 new_kin -= FreeLogRho(a.fs_kin.s[level + 1], nv);
                             } else {
@@ -278,6 +304,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                 const int bead0 = sh.bead0[sg];
                 int b_last = bead0 + nb;
                 b_last = WrapSlice(pv, b_last);
+#if PIMC_SWEEP_MIRROR
                 (void)b_last;
                 // the window's nb + 1 slices of the slice-major mirror: contiguous blocks of N * 24 bytes
                 const int slice_bytes = a.N * 24, lines = (slice_bytes + 127) / 128;
@@ -288,6 +315,16 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                     const char *p = reinterpret_cast<const char *>(a.R2 + ((size_t)c_grp * pv.Mstore + (bg - pv.slice_lo)) * a.N * 3);
                     PrefetchL2(p + min(l * 128, slice_bytes - 8));
                 }
+#else
+                const double *Rc = a.R + PosIndex(pv, a.N, c_grp, 0, 0, 0);
+                const int n_rows = a.N * 3;
+                for (int row = tg - 1; row < n_rows; row += kSweepGroup - 1) {
+                    const double *first = Rc + (size_t)row * pv.Ms + bead0 - pv.slice_lo;
+                    const double *last = Rc + (size_t)row * pv.Ms + b_last - pv.slice_lo;
+                    PrefetchL2(first);
+                    if (((uintptr_t)first >> 7) != ((uintptr_t)last >> 7)) PrefetchL2(last);  // second 128-byte line, or the wrapped end
+                }
+#endif
                 if (n_k > 0) {
                     const int lines = (n_k * (int)sizeof(double2) + 127) / 128;
                     for (int t = tg - 1; t < nb * lines; t += kSweepGroup - 1) {
@@ -323,20 +360,35 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                     // volatile: not hoisted) -- holding OLD and NEW copies in registers spills at 64
                     const uint32_t po_addr = (uint32_t)__cvta_generic_to_shared(&sh.pold[s0 + lc][j][0]);
                     const uint32_t pn_addr = (uint32_t)__cvta_generic_to_shared(&sh.pnew[s0 + lc][j][0]);
+#if PIMC_SWEEP_MIRROR
                     // 32-bit offsets inside the clone's block of the slice-major mirror
                     const double *Rc = a.R2 + (size_t)c * pv.Mstore * a.N * 3;
                     const unsigned o0 = (unsigned)(b0s - pv.slice_lo) * (unsigned)a.N * 3u, o1 = (unsigned)(b1s - pv.slice_lo) * (unsigned)a.N * 3u;
+#else
+                    const double *Rc = a.R + PosIndex(pv, a.N, c, 0, 0, 0);
+                    const unsigned row_stride = 3u * (unsigned)pv.Ms, ms = (unsigned)pv.Ms;
+                    const unsigned o0 = (unsigned)(b0s - pv.slice_lo), o1 = (unsigned)(b1s - pv.slice_lo);
+#endif
                     double acc_old = 0., acc_new = 0.;
                     for (int g = warp; g < n_groups; g += kTeamWarps) {
                         const int q = g * per_warp + sub;
                         const bool on = q < a.N && q != p;
-                        const unsigned row = (unsigned)(q < a.N ? q : a.N - 1) * 3u;
                         double q0[3], q1[3];
+#if PIMC_SWEEP_MIRROR
+                        const int qq = q < a.N ? q : a.N - 1;
 #pragma unroll
                         for (int d = 0; d < 3; ++d) {
-                            q0[d] = Rc[o0 + row + d];
-                            q1[d] = Rc[o1 + row + d];
+                            q0[d] = Rc[o0 + MirrorRow(a.N, qq, d)];
+                            q1[d] = Rc[o1 + MirrorRow(a.N, qq, d)];
                         }
+#else
+                        const unsigned row = (unsigned)(q < a.N ? q : a.N - 1) * row_stride;
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) {
+                            q0[d] = Rc[row + d * ms + o0];
+                            q1[d] = Rc[row + d * ms + o1];
+                        }
+#endif
                         // both sets of distances first: the partner's beads die before the table work
                         double ro, rpo, so, rn, rpn, sn, m0[3], m1[3];
                         LdsBeadPair(po_addr, m0, m1);
@@ -429,7 +481,9 @@ __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(co
                     int bg = bead0 + j;
                     bg = WrapSlice(pv, bg);
                     a.R[PosIndex(pv, a.N, c_grp, p, d, bg - pv.slice_lo)] = sh.pnew[sg][j][d];
-                    a.R2[(((size_t)c_grp * pv.Mstore + (bg - pv.slice_lo)) * a.N + p) * 3 + d] = sh.pnew[sg][j][d];
+#if PIMC_SWEEP_MIRROR
+                    a.R2[((size_t)c_grp * pv.Mstore + (bg - pv.slice_lo)) * a.N * 3 + MirrorRow(a.N, p, d)] = sh.pnew[sg][j][d];
+#endif
                 }
                 if (n_k > 0) {
                     // slice 0 of the window keeps its bead; the others take rho_k + delta as phase C left it

