@@ -27,11 +27,72 @@
 #include <string>
 #include <vector>
 
+#include <deque>
+
 #include <scaffold/matrix/matrix.h>
 #include <scaffold/algorithm/algorithm.h>
 #include <scaffold/io/io_xml.h>
 #include <scaffold/io/io_hdf5.h>
+
+// Random-number injection (tests only).  The reference's RNG (scaffold/rng/rng.h) draws from
+// std::uniform_real_distribution / std::normal_distribution over a private std::mt19937; a parallel
+// generator cannot reproduce that stream, so the stream-exact tests go the other way: they hand the
+// reference's moves the numbers the device's Philox stream drew.  While the two queues below are
+// empty the stand-ins forward to the real distributions, so every other use of this library sees
+// the unmodified std::mt19937 stream.  (Only the two distribution NAMES are redirected while rng.h
+// is read; the reference's file is included where it lies, unmodified.)
+namespace pimc_inject {
+inline std::deque<double> &Uniforms() {
+    static std::deque<double> q;
+    return q;
+}
+inline std::deque<double> &Normals() {
+    static std::deque<double> q;
+    return q;
+}
+}  // namespace pimc_inject
+namespace std {
+template <class T>
+class pimc_injected_uniform {
+    std::uniform_real_distribution<T> real;
+
+   public:
+    pimc_injected_uniform() : real() {}
+    pimc_injected_uniform(T a, T b) : real(a, b) {}
+    template <class G>
+    T operator()(G &g) {
+        std::deque<double> &q = pimc_inject::Uniforms();
+        if (!q.empty()) {
+            const T v = (T)q.front();
+            q.pop_front();
+            return v;
+        }
+        return real(g);
+    }
+};
+template <class T>
+class pimc_injected_normal {
+    std::normal_distribution<T> real;
+
+   public:
+    pimc_injected_normal() : real() {}
+    template <class G>
+    T operator()(G &g) {
+        std::deque<double> &q = pimc_inject::Normals();
+        if (!q.empty()) {
+            const T v = (T)q.front();
+            q.pop_front();
+            return v;
+        }
+        return real(g);
+    }
+};
+}  // namespace std
+#define uniform_real_distribution pimc_injected_uniform
+#define normal_distribution pimc_injected_normal
 #include <scaffold/rng/rng.h>
+#undef uniform_real_distribution
+#undef normal_distribution
 #include <einspline/nubspline.h>
 
 using namespace scaffold::matrix;
@@ -403,6 +464,20 @@ int ref_n_moves(void *h) { return ((RefSim *)h)->moves.size(); }
 void ref_move_do(void *h, int m, int n_times) {
     RefSim *s = (RefSim *)h;
     for (int i = 0; i < n_times; ++i) s->moves[m]->DoEvent();
+}
+/// Queue uniforms (each answers one RNG::UnifRand()) and normals (one RNG::NormRand() each) for the moves that follow.
+void ref_inject_random(const double *uniforms, int n_u, const double *normals, int n_n) {
+    for (int i = 0; i < n_u; ++i) pimc_inject::Uniforms().push_back(uniforms[i]);
+    for (int i = 0; i < n_n; ++i) pimc_inject::Normals().push_back(normals[i]);
+}
+/// Numbers still queued (a move that rejected early leaves some); clear != 0 drops them.
+void ref_inject_pending(int *n_u, int *n_n, int clear) {
+    *n_u = (int)pimc_inject::Uniforms().size();
+    *n_n = (int)pimc_inject::Normals().size();
+    if (clear) {
+        pimc_inject::Uniforms().clear();
+        pimc_inject::Normals().clear();
+    }
 }
 void ref_move_counts(void *h, int m, uint32_t *n_attempt, uint32_t *n_accept) {
     RefSim *s = (RefSim *)h;

@@ -89,6 +89,9 @@ def _load(fast=False, dropin=False):
     lib.ref_energy_sums.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
     lib.ref_move_do.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.ref_move_counts.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    if hasattr(lib, "ref_inject_random"):
+        lib.ref_inject_random.argtypes = [_dp, C.c_int, _dp, C.c_int]
+        lib.ref_inject_pending.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]
     lib.ref_capture_shape.restype = C.c_int
     lib.ref_capture_shape.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.ref_capture_read.restype = C.c_int
@@ -315,6 +318,18 @@ class RefSim:
 
     def move_do(self, m, n_times=1):
         self.lib.ref_move_do(self.h, m, n_times)
+
+    def inject_random(self, uniforms, normals):
+        """Queue the numbers the next RNG::UnifRand() / NormRand() calls of the reference will return
+        (process-wide queues; the real std::mt19937 stream resumes when they run dry)."""
+        u = np.ascontiguousarray(uniforms, dtype=np.float64)
+        n = np.ascontiguousarray(normals, dtype=np.float64)
+        self.lib.ref_inject_random(u, len(u), n, len(n))
+
+    def inject_pending(self, clear=True):
+        a, b = C.c_int(), C.c_int()
+        self.lib.ref_inject_pending(C.byref(a), C.byref(b), 1 if clear else 0)
+        return a.value, b.value
 
     def move_counts(self, m):
         a, b = C.c_uint32(), C.c_uint32()

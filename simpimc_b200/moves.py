@@ -249,6 +249,47 @@ def bisect_attempt_philox(cfg, species, n_level, seed, attempt, n_clones, get_be
     return np.array(out_p), np.array(out_b), np.array(out_acc)
 
 
+def bisect_philox_numbers(cfg, species, n_level, seed, attempt, clone):
+    """The random numbers ONE device-resident bisection attempt of `clone` draws from its Philox stream, in the order
+    the reference's Bisect::Attempt consumes its own (bisect_class.h:39-125): uniforms = [particle, first bead, then
+    the Metropolis uniform of every level from the top]; normals = the three Levy-displacement normals of every
+    midpoint, level by level from the top.  Feeding them to the reference program (oracle/refsim.py: inject_random)
+    makes it take the very decisions the device takes."""
+    from . import philox as PX
+    nb = 1 << n_level
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    a_lo, a_hi = attempt & 0xFFFFFFFF, (attempt >> 32) & 0xFFFFFFFF
+    r = PX.philox4x32(a_lo, a_hi, clone, 0, k0, k1)
+    uniforms = [PX.uniform_from_bits(r[0], r[1]), PX.uniform_from_bits(r[2], r[3])]
+    normals = []
+    slot = 1
+    for level in range(n_level - 1, -1, -1):
+        skip = 1 << level
+        for _ in range(0, nb, 2 * skip):
+            r0 = PX.philox4x32(a_lo, a_hi, clone, slot, k0, k1)
+            r1 = PX.philox4x32(a_lo, a_hi, clone, slot + 1, k0, k1)
+            slot += 2
+            ua, ub = PX.uniform_from_bits(r0[0], r0[1]), PX.uniform_from_bits(r0[2], r0[3])
+            uc, ud = PX.uniform_from_bits(r1[0], r1[1]), PX.uniform_from_bits(r1[2], r1[3])
+            ra, rc = math.sqrt(-2.0 * math.log(ua)), math.sqrt(-2.0 * math.log(uc))
+            normals += [ra * math.cos(2 * math.pi * ub), ra * math.sin(2 * math.pi * ub), rc * math.cos(2 * math.pi * ud)]
+        ru = PX.philox4x32(a_lo, a_hi, clone, slot, k0, k1)
+        slot += 1
+        uniforms.append(PX.uniform_from_bits(ru[0], ru[1]))
+    return uniforms, normals
+
+
+def displace_philox_numbers(seed, attempt, clone):
+    """The uniforms ONE device-resident DisplaceParticle attempt draws, in the reference's order of consumption
+    (displace_particle_class.h:28-71): particle, three components of the direction, Metropolis uniform."""
+    from . import philox as PX
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    a_lo, a_hi = attempt & 0xFFFFFFFF, (attempt >> 32) & 0xFFFFFFFF
+    r = [PX.philox4x32(a_lo, a_hi, clone, slot, k0, k1) for slot in range(4)]
+    return [PX.uniform_from_bits(r[0][0], r[0][1]), PX.uniform_from_bits(r[1][0], r[1][1]), PX.uniform_from_bits(r[1][2], r[1][3]),
+            PX.uniform_from_bits(r[2][0], r[2][1]), PX.uniform_from_bits(r[3][0], r[3][1])]
+
+
 def displace_attempt_philox(cfg, species, step_size, seed, attempt, n_clones, get_beads, action_old_new, finish):
     """Host mirror of ONE device-resident DisplaceParticle attempt (csrc/displace.cuh) drawing the
     same Philox stream: slot 0 particle, slots 1-2 direction, slot 3 Metropolis uniform.

@@ -1,0 +1,126 @@
+"""CPU test: the host mirror of the device-resident bisection (simpimc_b200.moves.bisect_attempt_philox, which
+tests/test_gpu_sweep.py and tests/test_gpu_kinetic.py pin the CUDA sweeps to attempt by attempt) against the
+REFERENCE PROGRAM ITSELF -- its own Bisect::Attempt / Accept / Reject, Kinetic (FreeSpline with periodic images) and
+IlkkaPairAction, compiled in place (oracle/_ref) -- made to consume the numbers of the device's Philox stream
+(oracle/refsim.py: inject_random).  Same decisions, same bead positions after every attempt: the device sweeps
+therefore follow the reference's Markov chain move for move, not just statistically."""
+import copy
+
+import numpy as np
+import pytest
+
+from simpimc_b200 import moves, system as S
+
+pytestmark = pytest.mark.ref
+
+
+@pytest.mark.parametrize("name,n_images_kin,n_images_move", [("ueg", 0, 0), ("egas", 100, 1), ("egas", 2, 3), ("nolr", 1, 0)])
+def test_host_mirror_follows_the_reference_program(name, n_images_kin, n_images_move, oracle_mod):
+    from oracle import refsim
+    if not refsim.available():
+        pytest.skip("oracle/_ref not built")
+    N, M, n_level = 5, 16, 3
+    if name == "ueg":
+        pair_cfg = S.ueg_config(N=N, M=M, n_xy=40, n_r_long=200)
+    elif name == "nolr":
+        pair_cfg = S.ueg_config(N=N, M=M, rs=1.0, theta=0.1, use_long_range=False, n_xy=40, n_r_long=200)
+    else:
+        pair_cfg = S.egas_config(N=N, M=M, n_xy=40, n_r_long=200)      # theta = 0.1: the images matter
+    cfg = copy.copy(pair_cfg)
+    cfg.actions = [S.ActionConfig("Kinetic", "Kinetic", "e", n_images=n_images_kin)] + list(pair_cfg.actions)
+    cfg.moves = [{"name": "BisectE", "type": "Bisect", "species": "e", "n_level": n_level, "n_images": n_images_move}]
+    cfg.observables = []
+    sim = refsim.RefSim(cfg, seed=1)
+    if not hasattr(sim.lib, "ref_inject_random"):
+        pytest.skip("oracle/_ref predates the injection hooks")
+    R = S.synthetic_paths(cfg, 0, 0, 5)
+    sim.set_positions(0, R)
+    o = oracle_mod.Oracle(pair_cfg)
+    o.set_positions(0, R)
+    seed = 0x5EED00000000ABCD
+
+    def get_beads(c, p, b0, n):
+        return o.get_positions(0, 0)[p, (b0 + np.arange(n)) % M]
+
+    def action_old_new(c, p, b0, nb, new):
+        o.propose(0, p, (b0 + 1) % M, new)
+        return o.get_action(0, 0, b0, b0 + nb, [(0, p)], 0), o.get_action(0, 1, b0, b0 + nb, [(0, p)], 0)
+
+    def finish(c, p, b0, nb, accept, new):
+        if new is not None:
+            o.finish_move(0, p, b0, b0 + nb, bool(accept))
+
+    n_att, n_acc = 120, 0
+    for attempt in range(n_att):
+        u, n = moves.bisect_philox_numbers(cfg, 0, n_level, seed, attempt, 0)
+        sim.inject_random(u, n)
+        sim.move_do(0, 1)
+        left_u, left_n = sim.inject_pending(clear=True)
+        _, _, acc = moves.bisect_attempt_philox(pair_cfg, 0, n_level, seed, attempt, 1, get_beads, action_old_new, finish,
+                                                n_images_move=n_images_move, n_images_kin=n_images_kin)
+        n_acc += int(acc[0])
+        att_ref, acc_ref = sim.move_counts(0)
+        assert (att_ref, acc_ref) == (attempt + 1, n_acc), (name, attempt, att_ref, acc_ref, n_acc)
+        if acc[0]:                      # an accepted attempt consumed every number
+            assert (left_u, left_n) == (0, 0), (attempt, left_u, left_n)
+        a, b = sim.get_positions(0, 0), o.get_positions(0, 0)
+        assert np.max(np.abs(a - b)) <= 1e-12 * max(1.0, np.max(np.abs(b))), (name, attempt, np.max(np.abs(a - b)))
+    assert 0 < n_acc < n_att, n_acc          # both outcomes occurred
+    o.close()
+    sim.close()
+
+
+@pytest.mark.parametrize("name", ["ueg", "plasma"])
+def test_displace_mirror_follows_the_reference_program(name, oracle_mod):
+    """DisplaceParticle::Attempt (displace_particle_class.h:28-71) of the reference on injected Philox numbers against
+    moves.displace_attempt_philox, the host mirror the device-resident pimc_displace_sweep is pinned to."""
+    from oracle import refsim
+    if not refsim.available():
+        pytest.skip("oracle/_ref not built")
+    if name == "ueg":
+        pair_cfg, sp = S.ueg_config(N=6, M=8, n_xy=40, n_r_long=200), 0
+    else:
+        pair_cfg, sp = S.plasma_config(Ne=4, Np=3, M=8), 1
+    cfg = copy.copy(pair_cfg)
+    spn = cfg.species[sp].name
+    step = 0.25
+    cfg.actions = [S.ActionConfig("Kinetic", "Kinetic", spn, n_images=1)] + list(pair_cfg.actions)
+    cfg.moves = [{"name": "Displace", "type": "DisplaceParticle", "species": spn, "step_size": step}]
+    cfg.observables = []
+    sim = refsim.RefSim(cfg, seed=1)
+    if not hasattr(sim.lib, "ref_inject_random"):
+        pytest.skip("oracle/_ref predates the injection hooks")
+    o = oracle_mod.Oracle(pair_cfg)
+    for s_i in range(len(cfg.species)):
+        R = S.synthetic_paths(cfg, s_i, 0, 5)
+        sim.set_positions(s_i, R)
+        o.set_positions(s_i, R)
+    M = cfg.n_bead
+    acts = [ai for ai, a in enumerate(pair_cfg.actions) if spn in (a.species_a, a.species_b)]
+    seed = 0x0D15C0DE
+
+    def get_beads(c, p, b0, n):
+        return o.get_positions(sp, 0)[p, (b0 + np.arange(n)) % M]
+
+    def action_old_new(c, p, new):
+        o.propose(sp, p, 0, new)
+        old = sum(o.get_action(ai, 0, 0, M, [(sp, p)], 0) for ai in acts)
+        nw = sum(o.get_action(ai, 1, 0, M, [(sp, p)], 0) for ai in acts)
+        return old, nw
+
+    def finish(c, p, accept):
+        o.finish_move(sp, p, 0, M, bool(accept))
+
+    n_att, n_acc = 60, 0
+    for attempt in range(n_att):
+        sim.inject_random(moves.displace_philox_numbers(seed, attempt, 0), [])
+        sim.move_do(0, 1)
+        assert sim.inject_pending(clear=True) == (0, 0)
+        _, acc = moves.displace_attempt_philox(pair_cfg, sp, step, seed, attempt, 1, get_beads, action_old_new, finish)
+        n_acc += int(acc[0])
+        assert sim.move_counts(0) == (attempt + 1, n_acc), (name, attempt)
+        a, b = sim.get_positions(sp, 0), o.get_positions(sp, 0)
+        assert np.max(np.abs(a - b)) <= 1e-12 * max(1.0, np.max(np.abs(b))), (name, attempt)
+    assert 0 < n_acc < n_att, n_acc
+    o.close()
+    sim.close()
