@@ -454,6 +454,55 @@ class StructureFactor:
         return out
 
 
+class IO:
+    """scaffold::io::IO (include/scaffold/io/io_hdf5.h:12-212) for the walkers of one context: Write / Rewrite /
+    CreateExtendableDataSet / AppendDataSet with the reference's dataset names, one HDF5 file per walker
+    (`<prefix>.<clone>.h5`, as the reference's ranks write `<output_prefix>.<rank>.h5`).  An extendable dataset is
+    the reference's (n_records, shape(data)...) array -- appended records along a new leading axis -- written
+    contiguously when the file is saved (simpimc_b200.h5lite; no HDF5 library in this build)."""
+
+    def __init__(self, prefix, n_clones):
+        self.prefix, self.n_clones = prefix, n_clones
+        self.fixed = [dict() for _ in range(n_clones)]
+        self.series = [dict() for _ in range(n_clones)]
+
+    @staticmethod
+    def _key(prefix, name=""):
+        return "/".join(p for p in (prefix + name).split("/") if p)
+
+    def Write(self, name, value):
+        """One value for every walker, or an array with a leading clone axis (per_clone=True values come from
+        estimators)."""
+        for c in range(self.n_clones):
+            self.fixed[c][self._key(name)] = value
+
+    Rewrite = Write
+
+    def WritePerClone(self, name, values):
+        for c in range(self.n_clones):
+            self.fixed[c][self._key(name)] = values[c]
+
+    def CreateExtendableDataSet(self, prefix, name, data):
+        for c in range(self.n_clones):
+            self.series[c][self._key(prefix, name)] = [np.asarray(data[c])]
+
+    def AppendDataSet(self, prefix, name, data):
+        for c in range(self.n_clones):
+            self.series[c].setdefault(self._key(prefix, name), []).append(np.asarray(data[c]))
+
+    def FileName(self, clone):
+        return "%s.%d.h5" % (self.prefix, clone)
+
+    def Save(self):
+        from . import h5lite
+        for c in range(self.n_clones):
+            out = dict(self.fixed[c])
+            for k, recs in self.series[c].items():
+                out[k] = np.stack(recs)
+            h5lite.write(self.FileName(c), out)
+        return [self.FileName(c) for c in range(self.n_clones)]
+
+
 class Energy:
     """Thermal and potential estimators of src/events/observables/energy_class.h:22-33,119-161."""
 
@@ -475,9 +524,26 @@ class Energy:
                 self.potentials[i] += cofactor * a.Potential()
         self.n_measure += 1
 
-    def Write(self):
+    def Write(self, out=None, name="Energy"):
+        """energy_class.h:232-276: block means per action and their sum.  With `out` (an IO) the block is appended to
+        the reference's datasets Observables/<name>/{total,<action>,v_total,v_<action>}/x."""
         norm = self.path.cfg.n_bead * self.n_measure  # energy_class.h:234
         e, v = self.energies / norm, self.potentials / norm
+        if out is not None and self.n_measure > 0:
+            prefix = "Observables/%s/" % name
+            first = not getattr(self, "_written", False)
+            put = out.CreateExtendableDataSet if first else out.AppendDataSet
+            groups = [("total", e.sum(axis=0))] + [(a.name, e[i]) for i, a in enumerate(self.actions)]
+            if self.measure_potential:
+                groups += [("v_total", v.sum(axis=0))] + [("v_" + a.name, v[i]) for i, a in enumerate(self.actions)]
+            if first:
+                out.Write(prefix + "type", "Energy")
+                out.Write(prefix + "data_type", "scalar")
+            for g, x in groups:
+                put("/" + prefix + g + "/", "x", x)
+                if first:
+                    out.Write(prefix + g + "/data_type", "scalar")
+            self._written = True
         self.Reset()
         return e, v
 
@@ -495,11 +561,22 @@ class PathDump:
         self.n_dump, self.n_write_calls = 0, 0
         self.positions = {s.name: [] for s in path.cfg.species}
 
-    def Write(self):
+    def Write(self, out=None):
+        """path_dump_class.h:29-68.  With `out` (an IO) the dump is appended to the reference's datasets
+        Observables/<name>/<species>/{n_dump, positions (n_dump, n_part, n_bead, n_d), permutation (n_dump, n_part, 2)}."""
         if self.n_write_calls % self.skip == 0:
             self.n_dump += 1
             for si, s in enumerate(self.path.cfg.species):
-                self.positions[s.name].append(self.path.GetPositions(si))
+                R = self.path.GetPositions(si)
+                self.positions[s.name].append(R)
+                if out is not None:
+                    prefix = "Observables/%s/%s/" % (self.name, s.name)
+                    ident = np.arange(s.n_part, dtype=np.float64)
+                    perm = np.tile(np.stack([ident, ident]).T, (self.path.n_clones, 1, 1))
+                    put = out.CreateExtendableDataSet if self.n_dump == 1 else out.AppendDataSet
+                    out.Write(prefix + "n_dump", np.uint32(self.n_dump))
+                    put(prefix, "positions", R)
+                    put(prefix, "permutation", perm)
         self.n_write_calls += 1
 
     def Save(self, file_name):
@@ -514,7 +591,22 @@ class PathDump:
 
     @staticmethod
     def Restart(path, file_name, name="path_dump"):
-        """init_type="Restart": the LAST dump of every species becomes the configuration."""
+        """init_type="Restart": the LAST dump of every species becomes the configuration.  file_name: the .npz of
+        Save(), or the reference-format HDF5 files of IO.Save() -- one per walker (a list), or one for all."""
+        if isinstance(file_name, (list, tuple)) or str(file_name).endswith(".h5"):
+            from . import h5lite
+            files = list(file_name) if isinstance(file_name, (list, tuple)) else [file_name] * path.n_clones
+            if len(files) != path.n_clones:
+                raise ValueError("one restart file per walker is needed")
+            dumps = [h5lite.read(fn) for fn in files]
+            for si, s in enumerate(path.cfg.species):
+                key = "Observables/%s/%s/" % (name, s.name)
+                for d in dumps:
+                    perm = d[key + "permutation"][-1]
+                    if not (np.array_equal(perm[:, 0], np.arange(s.n_part)) and np.array_equal(perm[:, 1], np.arange(s.n_part))):
+                        raise ValueError("ERROR: permuted paths are not supported on this path")
+                path.SetPositions(si, np.stack([d[key + "positions"][-1] for d in dumps]))
+            return
         f = np.load(file_name)
         for si, s in enumerate(path.cfg.species):
             key = "Observables/%s/%s/" % (name, s.name)

@@ -273,3 +273,39 @@ def read_ptab(path):
                 arr = np.frombuffer(f.read(count * np.dtype(dt).itemsize), dtype=dt).reshape(dims)
                 out[name] = arr.copy() if dims else arr.reshape(())[()]
     return out
+
+
+# ------------------------------------------------------------------------ HDF5 table files
+def read_h5_table(path):
+    """A reference pair-action table file (HDF5, as scripts/pagen/IlkkaSquarer.py:118-163 / DavidParse.py:160-225
+    write it) -> the flat dict {dataset path: array | scalar | str} the packers in capi.py take, dataset paths
+    verbatim.  Read with simpimc_b200.h5lite (no HDF5 library in this build)."""
+    from . import h5lite
+    out = {}
+    for key, val in h5lite.read(path).items():
+        if isinstance(val, np.ndarray) and val.dtype.kind == "f":
+            val = np.ascontiguousarray(val, dtype=np.float64)      # row-major, as the reference's raw reads expect
+        elif isinstance(val, np.ndarray) and val.dtype == object and val.size == 1:
+            val = str(val.reshape(-1)[0])
+        elif np.isscalar(val) and isinstance(val, (np.integer,)):
+            val = np.uint32(val)
+        out[key] = val
+    return out
+
+
+def write_h5_table(path, table):
+    """The inverse: a table dict as an HDF5 file with the reference's dataset paths."""
+    from . import h5lite
+    h5lite.write(path, table)
+
+
+def load_table(path):
+    """A pair-action table from any container this build understands: HDF5 (the reference's own files), the flat
+    PTAB1 container, or a .npz with '|' for '/' in the keys."""
+    from . import h5lite
+    if str(path).endswith(".npz"):
+        f = np.load(path, allow_pickle=False)
+        return {k.replace("|", "/"): (str(f[k]) if f[k].dtype.kind in "US" else f[k]) for k in f.files}
+    if h5lite.is_hdf5(path):
+        return read_h5_table(path)
+    return read_ptab(path)

@@ -457,15 +457,35 @@ def test_path_dump_and_restart_resume_the_same_markov_chain(tmp_path):
     for sp in range(2):
         first.SetPositions(sp, R0[sp])
     dump = host.PathDump(first, skip=2)
+    out = host.IO(str(tmp_path / "run"), C)       # the reference's HDF5 layout, one file per walker (io_hdf5.h)
+    energy = host.Energy(first, measure_potential=True)
     run(first, 0, 4)
-    dump.Write()
+    dump.Write(out)
+    energy.Accumulate()
+    energy.Write(out)
     run(first, 4, 7)
-    dump.Write()            # skipped (skip = 2)
-    dump.Write()
+    dump.Write(out)            # skipped (skip = 2)
+    dump.Write(out)
+    energy.Accumulate()
+    e_last, v_last = energy.Write(out)
     assert dump.n_dump == 2
     fn = str(tmp_path / "run.0.npz")
     dump.Save(fn)
+    files = out.Save()
     first.close()
+    # the HDF5 files carry the reference's dataset names and shapes (path_dump_class.h:54-62, energy_class.h:236-258)
+    from simpimc_b200 import h5lite
+    d0 = h5lite.read(files[0])
+    assert d0["Observables/path_dump/e/positions"].shape == (2, 5, 16, 3) and d0["Observables/path_dump/p/permutation"].shape == (2, 4, 2)
+    assert int(d0["Observables/path_dump/e/n_dump"]) == 2 and d0["Observables/Energy/data_type"] == "scalar"
+    assert d0["Observables/Energy/total/x"].shape == (2,) and d0["Observables/Energy/v_CoulombEP/x"].shape == (2,)
+    assert d0["Observables/Energy/total/x"][1] == e_last.sum(axis=0)[0] and d0["Observables/Energy/v_total/x"][1] == v_last.sum(axis=0)[0]
+    third = host.Path(cfg, n_clones=C)
+    host.PathDump.Restart(third, files)            # restart from the HDF5 files
+    run(third, 7, 12)
+    for sp in range(2):
+        assert np.array_equal(third.GetPositions(sp), ref[sp])
+    third.close()
     second = host.Path(cfg, n_clones=C)
     host.PathDump.Restart(second, fn)
     run(second, 7, 12)
