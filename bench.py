@@ -660,14 +660,15 @@ def c5_leg(args, rank, world, local, with_mc=True):
     # communication), then one ring rotation of the slices over NCCL (positions, halos, rho_k) ----
     mc = None
     if with_mc and sh.n_local >= (1 << BISECT_LEVEL) and args.attempts > 0:
-        n_att = max(4, min(args.attempts, 64))
+        n_att = max(4, min(args.attempts, 64))        # rounds: every disjoint window of the shard is attempted in each
+        n_win = 1
         for sp in range(2):
-            sp_path.BisectSweep(sp, BISECT_LEVEL, 2, 99, attempt0=0)
+            _, n_win = sp_path.BisectSweepWindows(sp, BISECT_LEVEL, 2, 99, attempt0=0)
         barrier()
         w0 = time.perf_counter()
         n_acc = 0
         for sp in range(2):
-            n_acc += int(sp_path.BisectSweep(sp, BISECT_LEVEL, n_att, 99, attempt0=2).sum())
+            n_acc += int(sp_path.BisectSweepWindows(sp, BISECT_LEVEL, n_att, 99, attempt0=2)[0].sum())
         torch.cuda.synchronize()
         w1 = time.perf_counter()
         sp_path.Rotate(BISECT_LEVEL + 1)
@@ -678,10 +679,9 @@ def c5_leg(args, rank, world, local, with_mc=True):
         if world > 1:
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         attempts_per_sweep = 2 * Ne * M // (1 << BISECT_LEVEL)
-        n_win = getattr(sp_path.path, "last_windows_per_attempt", 1)
         mc = {"attempts_per_s": world * C * 2 * n_att * n_win / float(tm[0].item()), "sweeps_per_s": world * C * 2 * n_att * n_win / attempts_per_sweep / float(tm[0].item()),
               "attempts_timed_per_rank": 2 * n_att * C * n_win, "windows_per_launch": n_win, "accept_ratio_rank0": n_acc / (2.0 * n_att * C * n_win), "rotate_ms": 1e3 * float(tm[1].item()),
-              "driver": "pimc_bisect_sweep (kernel-per-phase path: 2 species, 3 actions) on each rank's shard, windows of %d slices; pimc_rotate over NCCL" % (1 << BISECT_LEVEL)}
+              "driver": "pimc_bisect_sweep_windows (kernel-per-phase path: 2 species, 3 actions): every disjoint window of %d slices of each rank's shard attempted in the same launches; pimc_rotate over NCCL" % (1 << BISECT_LEVEL)}
     k1_step_s = k1_ms / 5 * 1e-3          # the three K1 launches of a step on this rank
     achieved = (evals_step / world) * FLOP_PER_EVAL / k1_step_s / 1e12 if k1_step_s > 0 else None
     block = {"metric": "bead-pair action evals/s", "value": value, "unit": "bead-pair action evals/s", "n_gpus": world,

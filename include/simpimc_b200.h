@@ -261,6 +261,18 @@ int pimc_commit(pimc_ctx *ctx, const int32_t *accept);
 int pimc_bisect_sweep(pimc_ctx *ctx, int32_t species, int32_t n_level, int32_t n_attempts, uint64_t seed, uint64_t attempt0,
                       int32_t with_kinetic, int64_t *n_accept);
 
+/* The same move on EVERY disjoint window of a walker at once -- for one large path (few walkers, e.g. a slice
+ * shard of BASELINE config C5), where one window per launch leaves the GPU idle.  A round tiles the path (the
+ * shard's stored slices) with W = floor(slices / 2^n_level) windows starting at offset + w 2^n_level, the offset
+ * drawn once per walker and round; every window picks its own particle, builds its own Levy bridge and takes its
+ * own Metropolis decision.  The windows share only their fixed end-point slices: the pair action at level 0
+ * couples a moved bead with the other particles' beads of the same and the neighbouring slice
+ * (pair_action_class.h:282-288) and rho_k is slice-local, so the W updates are independent and their product
+ * satisfies detailed balance like W sequential Bisect::DoEvent calls on those windows.  Philox counter:
+ * (attempt0 + round, walker * W + window, slot).  n_accept[n_clones] is ADDED to; *n_windows returns W. */
+int pimc_bisect_sweep_windows(pimc_ctx *ctx, int32_t species, int32_t n_level, int32_t n_rounds, uint64_t seed, uint64_t attempt0,
+                              int32_t with_kinetic, int64_t *n_accept, int32_t *n_windows);
+
 /* Bisect's own n_images attribute (bisect_class.h:173: the FreeSplines of the Levy sampling
  * probabilities, tau 2^level / 2) for later pimc_bisect_sweep calls on this species; default 0. */
 int pimc_move_set_images(pimc_ctx *ctx, int32_t species, int32_t n_images);

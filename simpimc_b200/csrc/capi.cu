@@ -150,6 +150,7 @@ struct pimc_ctx {
         v.Ms = Ms;
         v.slice_lo = slice_lo;
         v.sharded = sharded;
+        v.vdiv = 1;
         v.box.L = L;
         v.box.iL = iL;
         return v;
@@ -2178,8 +2179,10 @@ int pimc_commit(pimc_ctx *ctx, const int32_t *accept) {
 
 
 // ------------------------------------------------------------------- device-resident moves
-int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attempts, uint64_t seed, uint64_t attempt0,
-                      int32_t with_kinetic, int64_t *n_accept) {
+/// windows = 0: one window per walker and attempt (Bisect::DoEvent); != 0: every walker's path is tiled with disjoint
+/// windows that are all attempted in the same launches (pimc_bisect_sweep_windows), *n_windows_out = windows per walker.
+static int BisectSweepImpl(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attempts, uint64_t seed, uint64_t attempt0,
+                           int32_t with_kinetic, int64_t *n_accept, int windows, int32_t *n_windows_out) {
     if (!ctx) return Fail(PIMC_ERR_INVALID, "null context");
     if (s < 0 || s >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
     if (n_level < 1 || (1 << n_level) > kMaxBisectBeads || (1 << n_level) > ctx->M)
@@ -2188,13 +2191,30 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
     // a slice shard moves the windows that lie inside its stored slices [slice_lo, slice_hi]: its first
     // slice and its halo stay fixed until the caller rotates the ring (pimc_rotate_*) and refreshes the halos
     if (ctx->sharded && (1 << n_level) > ctx->Mloc) return Fail(PIMC_ERR_INVALID, "window longer than the slice shard");
-    const int b0_lo = ctx->sharded ? ctx->slice_lo : 0, b0_count = ctx->sharded ? ctx->Mloc - (1 << n_level) + 1 : ctx->M;
+    int b0_lo = ctx->sharded ? ctx->slice_lo : 0, b0_count = ctx->sharded ? ctx->Mloc - (1 << n_level) + 1 : ctx->M;
+    // disjoint windows: W = floor(slices / 2^n_level) windows per walker at b0_lo + offset + w 2^n_level; the offset is
+    // one of the shifts that keep every window inside the path (unsharded: any of 2^n_level when the windows tile the
+    // ring exactly, else the slack; a shard: the slack of its stored slices -- its first slice and halo stay fixed)
+    int W = 1;
+    if (windows) {
+        const int span = ctx->sharded ? ctx->Mloc : ctx->M, nbw = 1 << n_level;
+        W = span / nbw;
+        if (W < 1) return Fail(PIMC_ERR_INVALID, "window longer than the path / shard");
+        b0_count = (!ctx->sharded && W * nbw == span) ? nbw : span - W * nbw + 1;
+        if (n_windows_out) *n_windows_out = W;
+    }
     SpeciesState &st = *ctx->species[s];
     if (!(st.lambda > 0.)) return Fail(PIMC_ERR_INVALID, "bisection of a species with lambda = 0");
     for (auto &sp : ctx->species)
         if (sp->n_prop > 0) return Fail(PIMC_ERR_INVALID, "a proposal is pending: call pimc_commit first");
     PIMC_CUDA(cudaSetDevice(ctx->device));
-    const int C = ctx->C, nb = 1 << n_level, n_prop = nb - 1, n_k = ctx->n_k();
+    const int Cw = ctx->C;                       // walkers
+    const int C = Cw * W;                        // virtual clones: (walker, window); == walkers in the classic mode
+    const int nb = 1 << n_level, n_prop = nb - 1, n_k = ctx->n_k();
+    if (windows) {
+        if (st.P_particle.n < (size_t)kMaxPropSlots * C) PIMC_CUDA(st.P_particle.Alloc((size_t)kMaxPropSlots * C));
+        if (st.P_first.n < (size_t)kMaxPropSlots * C) PIMC_CUDA(st.P_first.Alloc((size_t)kMaxPropSlots * C));
+    }
     if (ctx->mc_f64.n < (size_t)6 * C) PIMC_CUDA(ctx->mc_f64.Alloc((size_t)6 * C));
     if (ctx->mc_i32.n < (size_t)3 * C) PIMC_CUDA(ctx->mc_i32.Alloc((size_t)3 * C));
     if (ctx->mc_naccept.n < (size_t)C) PIMC_CUDA(ctx->mc_naccept.Alloc(C));
@@ -2224,10 +2244,14 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
     if ((rc_fs = GetFreeSet(ctx, s, st.kinetic ? st.kinetic->n_images : 0, &fs_kin)) != PIMC_OK) return rc_fs;
     if ((fs_move->view.n_images || fs_kin->view.n_images) && n_level + 1 > kMaxFreeSplines)
         return Fail(PIMC_ERR_UNSUPPORTED, "n_level too large for the tabulated free-particle splines");
-    const PathView pv = ctx->View();
+    PathView pv = ctx->View();
+    if (windows) {
+        pv.C = C;
+        pv.vdiv = W;
+    }
     // one same-species fast Ilkka action on the moved species: the whole sweep is one launch
     // (sweep_fused.cuh); everything else takes the kernel-per-phase path below
-    bool fused = acts.size() == 1 && acts[0]->sa == s && acts[0]->sb == s && acts[0]->atype == ATYPE_ILKKA && acts[0]->fast_ok[WHICH_U] &&
+    bool fused = !windows && acts.size() == 1 && acts[0]->sa == s && acts[0]->sb == s && acts[0]->atype == ATYPE_ILKKA && acts[0]->fast_ok[WHICH_U] &&
                  !ctx->force_general && nb <= kSweepMaxBeads && n_level <= kSweepMaxLevel;
     size_t fused_smem = 0;
     if (fused) {
@@ -2352,6 +2376,7 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
             l.pv = pv;
             l.sv = ctx->SView(s, false);
             l.sv.n_prop = n_prop;  // the proposal the sample kernel has just written
+            l.sv.n_slots = 1;
             l.ks = ctx->KView();
             l.b0 = b0;
             l.n_window = nb;
@@ -2404,10 +2429,21 @@ int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attem
         std::vector<long long> h(C);
         PIMC_CUDA(cudaMemcpyAsync(h.data(), ctx->mc_naccept.p, C * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
         PIMC_CUDA(cudaStreamSynchronize(ctx->stream));
-        for (int c = 0; c < C; ++c) n_accept[c] += (int64_t)h[c];
+        for (int c = 0; c < C; ++c) n_accept[c / W] += (int64_t)h[c];
     }
     return PIMC_OK;
 }
+
+int pimc_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attempts, uint64_t seed, uint64_t attempt0,
+                      int32_t with_kinetic, int64_t *n_accept) {
+    return BisectSweepImpl(ctx, s, n_level, n_attempts, seed, attempt0, with_kinetic, n_accept, 0, nullptr);
+}
+
+int pimc_bisect_sweep_windows(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_rounds, uint64_t seed, uint64_t attempt0,
+                              int32_t with_kinetic, int64_t *n_accept, int32_t *n_windows) {
+    return BisectSweepImpl(ctx, s, n_level, n_rounds, seed, attempt0, with_kinetic, n_accept, 1, n_windows);
+}
+
 
 int pimc_perm_table(pimc_ctx *ctx, int32_t s, const int32_t *b0, int32_t n_bisect_beads, double epsilon, int32_t relative, double *t) {
     if (!ctx || !b0 || !t) return Fail(PIMC_ERR_INVALID, "null argument");

@@ -49,8 +49,15 @@ struct PathView {
     int Ms;       // row length of the position arrays (Mstore rounded up to a multiple of 4)
     int slice_lo; // first owned slice
     int sharded;
+    // Disjoint bisection windows of one walker moved in the same launch (pimc_bisect_sweep_windows): the move kernels
+    // then run over C = n_walkers * vdiv "virtual clones" -- index c = walker * vdiv + window for everything an
+    // attempt owns (proposal, window start, partial sums), walker = c / vdiv for positions and rho_k.  1 elsewhere.
+    int vdiv;
     Box box;
 };
+
+/// Walker whose positions / rho_k virtual clone c works on.
+__device__ __forceinline__ int RealClone(const PathView &pv, int c) { return pv.vdiv > 1 ? c / pv.vdiv : c; }
 
 /// Global slice index after the beta-periodic wrap (bg < 2 M).  A slice shard's move windows never
 /// leave its stored slices [slice_lo, slice_hi]; the halo -- global slice slice_hi, which equals M
@@ -84,9 +91,9 @@ __device__ __forceinline__ void LoadPos(const PathView &pv, const SpeciesView &s
             }
         }
     }
-    const int b = bl - pv.slice_lo;
+    const int b = bl - pv.slice_lo, cr = RealClone(pv, c);
 #pragma unroll
-    for (int d = 0; d < 3; ++d) out[d] = sv.R[PosIndex(pv, sv.N, c, p, d, b)];
+    for (int d = 0; d < 3; ++d) out[d] = sv.R[PosIndex(pv, sv.N, cr, p, d, b)];
 }
 
 // ------------------------------------------------------------------------------------ K1

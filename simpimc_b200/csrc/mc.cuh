@@ -114,13 +114,24 @@ __global__ void __launch_bounds__(kSampleWarps * 32) bisect_sample_kernel(const 
     p_i = p_i < a.N ? p_i : a.N - 1;
     int bead0 = (int)(UniformFromBits(rnd[2], rnd[3]) * a.b0_count);
     bead0 = a.b0_lo + (bead0 < a.b0_count ? bead0 : a.b0_count - 1);
+    if (pv.vdiv > 1) {
+        // disjoint windows of one walker: window w starts at b0_lo + offset + w * nb, the offset drawn once per walker
+        // and attempt from the stream of its window 0 (b0_count = number of admissible offsets)
+        const int c0 = (c / pv.vdiv) * pv.vdiv, wi = c - c0;
+        uint32_t r0[4];
+        Philox4x32(a.attempt_lo, a.attempt_hi, (uint32_t)c0, 0u, a.seed_lo, a.seed_hi, r0);
+        int off = (int)(UniformFromBits(r0[2], r0[3]) * a.b0_count);
+        off = off < a.b0_count ? off : a.b0_count - 1;
+        bead0 = a.b0_lo + off + wi * nb;
+        bead0 = WrapSlice(pv, bead0);
+    }
     double(*oldb)[3] = s_old[w];
     double(*newb)[3] = s_new[w];
     for (int t = lane; t < (nb + 1) * 3; t += 32) {
         const int j = t / 3, d = t - j * 3;
         int bg = bead0 + j;
         bg = WrapSlice(pv, bg);
-        const double x = a.R[PosIndex(pv, a.N, c, p_i, d, bg - pv.slice_lo)];
+        const double x = a.R[PosIndex(pv, a.N, RealClone(pv, c), p_i, d, bg - pv.slice_lo)];
         oldb[j][d] = x;
         newb[j][d] = x;
     }
@@ -281,7 +292,7 @@ __global__ void __launch_bounds__(kWindowThreads) pair_window_both_kernel(const 
         const int j = t / 3, d = t - j * 3;
         int bg = bead0 + j;
         bg = WrapSlice(pv, bg);
-        const double x = a.R_moved[PosIndex(pv, a.N_moved, c, p, d, bg - pv.slice_lo)];
+        const double x = a.R_moved[PosIndex(pv, a.N_moved, RealClone(pv, c), p, d, bg - pv.slice_lo)];
         pold[j][d] = x;
         pnew[j][d] = (j >= 1 && j < nl) ? a.P[((size_t)c * (nl - 1) + (j - 1)) * 3 + d] : x;
     }
@@ -292,12 +303,12 @@ __global__ void __launch_bounds__(kWindowThreads) pair_window_both_kernel(const 
         double q0[3], q1[3];
         int bg = bead0;
 #pragma unroll
-        for (int d = 0; d < 3; ++d) q0[d] = a.R_partner[PosIndex(pv, a.N_partner, c, q, d, bg - pv.slice_lo)];
+        for (int d = 0; d < 3; ++d) q0[d] = a.R_partner[PosIndex(pv, a.N_partner, RealClone(pv, c), q, d, bg - pv.slice_lo)];
         for (int j = 0; j < nl; ++j) {
             int bn = bg + 1;
             bn = WrapSlice(pv, bn);
 #pragma unroll
-            for (int d = 0; d < 3; ++d) q1[d] = a.R_partner[PosIndex(pv, a.N_partner, c, q, d, bn - pv.slice_lo)];
+            for (int d = 0; d < 3; ++d) q1[d] = a.R_partner[PosIndex(pv, a.N_partner, RealClone(pv, c), q, d, bn - pv.slice_lo)];
             double r, rp, s;
             if (FAST) {
                 DrDrpDrrpFast(pold[j], q0, pold[j + 1], q1, pv.box, r, rp, s);
@@ -390,7 +401,7 @@ __global__ void __launch_bounds__(kWinFastThreads, 1) pair_window_fast_kernel(co
             const int jj = t / 3, d = t - jj * 3;
             int bg = bead0 + jj;
             bg = WrapSlice(pv, bg);
-            const double x = a.R_moved[PosIndex(pv, a.N_moved, c, p, d, bg - pv.slice_lo)];
+            const double x = a.R_moved[PosIndex(pv, a.N_moved, RealClone(pv, c), p, d, bg - pv.slice_lo)];
             pold[team][jj][d] = x;
             pnew[team][jj][d] = (jj >= 1 && jj < nl) ? a.P[((size_t)c * (nl - 1) + (jj - 1)) * 3 + d] : x;
         }
@@ -408,8 +419,8 @@ __global__ void __launch_bounds__(kWinFastThreads, 1) pair_window_fast_kernel(co
             double q0[3], q1[3];
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
-                q0[d] = a.R_partner[PosIndex(pv, a.N_partner, c, qc, d, b0s - pv.slice_lo)];
-                q1[d] = a.R_partner[PosIndex(pv, a.N_partner, c, qc, d, b1s - pv.slice_lo)];
+                q0[d] = a.R_partner[PosIndex(pv, a.N_partner, RealClone(pv, c), qc, d, b0s - pv.slice_lo)];
+                q1[d] = a.R_partner[PosIndex(pv, a.N_partner, RealClone(pv, c), qc, d, b1s - pv.slice_lo)];
             }
             double ro, rpo, so, rn, rpn, sn, m0[3], m1[3];
             LdsBeadPair(po_addr, m0, m1);
@@ -508,7 +519,7 @@ __global__ void __launch_bounds__(256) lr_window_kernel(const LrWindowArgs a) {
             const double2 fn = CMul(CMul(tn[i0], tn[tl + i1]), tn[2 * tl + i2]);
             const double2 d = make_double2(fn.x - fo.x, fn.y - fo.y);
             a.drho[((size_t)c * a.n_window + j) * n_k + k] = d;
-            const size_t ri = ((size_t)c * pv.Mloc + (bg - pv.slice_lo)) * n_k + k;
+            const size_t ri = ((size_t)RealClone(pv, c) * pv.Mloc + (bg - pv.slice_lo)) * n_k + k;
             const double2 rs = a.rho_self[ri];
             const double2 rn = make_double2(rs.x + d.x, rs.y + d.y);
             for (int t2 = 0; t2 < a.n_actions; ++t2) {
@@ -562,13 +573,13 @@ __global__ void __launch_bounds__(256) lr_window_kernel(const LrWindowArgs a) {
         const int j = t / 3, d = t - j * 3;
         int bg = bead0 + 1 + j;
         bg = WrapSlice(pv, bg);
-        a.R[PosIndex(pv, a.N, c, p, d, bg - pv.slice_lo)] = a.sv.P[((size_t)c * n_prop + j) * 3 + d];
+        a.R[PosIndex(pv, a.N, RealClone(pv, c), p, d, bg - pv.slice_lo)] = a.sv.P[((size_t)c * n_prop + j) * 3 + d];
     }
     for (int t = tid; t < a.n_window * n_k; t += blockDim.x) {
         const int j = t / n_k, k = t - j * n_k;
         int bg = bead0 + j;
         bg = WrapSlice(pv, bg);
-        double2 *dst = a.rho_commit + ((size_t)c * pv.Mloc + (bg - pv.slice_lo)) * n_k + k;
+        double2 *dst = a.rho_commit + ((size_t)RealClone(pv, c) * pv.Mloc + (bg - pv.slice_lo)) * n_k + k;
         const double2 d = a.drho[((size_t)c * a.n_window + j) * n_k + k];
         dst->x += d.x;
         dst->y += d.y;
@@ -600,14 +611,14 @@ __global__ void __launch_bounds__(256) bisect_decide_commit_kernel(PathView pv, 
         const int j = t / 3, d = t - j * 3;
         int bg = bead0 + 1 + j;
         bg = WrapSlice(pv, bg);
-        R[PosIndex(pv, N, c, p, d, bg - pv.slice_lo)] = P[((size_t)c * n_prop + j) * 3 + d];
+        R[PosIndex(pv, N, RealClone(pv, c), p, d, bg - pv.slice_lo)] = P[((size_t)c * n_prop + j) * 3 + d];
     }
     if (drho) {
         for (int t = threadIdx.x; t < n_window * n_k; t += blockDim.x) {
             const int j = t / n_k, k = t - j * n_k;
             int bg = bead0 + j;
             bg = WrapSlice(pv, bg);
-            double2 *dst = rho + ((size_t)c * pv.Mloc + (bg - pv.slice_lo)) * n_k + k;
+            double2 *dst = rho + ((size_t)RealClone(pv, c) * pv.Mloc + (bg - pv.slice_lo)) * n_k + k;
             const double2 d = drho[((size_t)c * n_window + j) * n_k + k];
             dst->x += d.x;
             dst->y += d.y;

@@ -156,6 +156,15 @@ class Path:
                                             _vp(n_accept)))
         return n_accept
 
+    def BisectSweepWindows(self, species, n_level, n_rounds, seed, attempt0=0, with_kinetic=True):
+        """n_rounds rounds of the bisection move on every disjoint window of every walker at once
+        (pimc_bisect_sweep_windows); returns (accepts per clone, windows per walker and round)."""
+        n_accept = np.zeros(self.n_clones, dtype=np.int64)
+        n_win = C.c_int32()
+        capi.check(self.L.pimc_bisect_sweep_windows(self.h, species, n_level, n_rounds, seed, attempt0, 1 if with_kinetic else 0,
+                                                    _vp(n_accept), C.byref(n_win)))
+        return n_accept, n_win.value
+
     def DisplaceSweep(self, species, step_size, n_attempts, seed, attempt0=0):
         """n_attempts device-resident DisplaceParticle::DoEvent calls per clone; returns accepts per clone."""
         n_accept = np.zeros(self.n_clones, dtype=np.int64)

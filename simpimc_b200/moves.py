@@ -157,7 +157,7 @@ def _free_spline(cfg, lam, n_images, tau_s):
 
 
 def bisect_attempt_philox(cfg, species, n_level, seed, attempt, n_clones, get_beads, action_old_new, finish, with_kinetic=True,
-                          b0_range=None, n_images_move=0, n_images_kin=0):
+                          b0_range=None, n_images_move=0, n_images_kin=0, windows=None):
     """Host mirror of ONE device-resident bisection attempt (csrc/mc.cuh: bisect_sample_kernel +
     pair_window_both_kernel + k-sums + bisect_decide_kernel) drawing the same Philox stream.
 
@@ -167,6 +167,9 @@ def bisect_attempt_philox(cfg, species, n_level, seed, attempt, n_clones, get_be
     finish(c, p, bead0, nb, accept)      -> Move::Accept / Reject
     b0_range = (first, count): window starts uniform in [first, first + count) -- a slice shard's
     interior windows (pimc_bisect_sweep on a sharded context); default: the whole path.
+    windows = W: the multi-window mode of pimc_bisect_sweep_windows -- n_clones counts VIRTUAL clones (walker * W +
+    window, the index the callbacks receive and the stream is keyed by); window w of a walker starts at first + offset
+    + w 2^n_level with the offset drawn from the stream of the walker's window 0 (b0_range = (first, n_offsets)).
     n_images_move / n_images_kin: periodic images of Bisect's sampling splines (bisect_class.h:158-163,173)
     and of the Kinetic action (kinetic_class.h:16-24), evaluated with the FreeSpline host mirror.
     Returns (particle[c], bead0[c], accept[c]).
@@ -187,6 +190,13 @@ def bisect_attempt_philox(cfg, species, n_level, seed, attempt, n_clones, get_be
         p_i = min(int(PX.uniform_from_bits(r[0], r[1]) * N), N - 1)
         b_first, b_count = (0, M) if b0_range is None else b0_range
         bead0 = b_first + min(int(PX.uniform_from_bits(r[2], r[3]) * b_count), b_count - 1)
+        if windows:
+            c0 = (c // windows) * windows
+            r_w = PX.philox4x32(a_lo, a_hi, c0, 0, k0, k1)
+            off = min(int(PX.uniform_from_bits(r_w[2], r_w[3]) * b_count), b_count - 1)
+            bead0 = b_first + off + (c - c0) * nb
+            if b0_range is None or bead0 >= M:
+                bead0 %= M
         old = np.array(get_beads(c, p_i, bead0, nb + 1), dtype=np.float64)
         new = old.copy()
         slot, alive, prev_change, partial, logu0 = 1, True, 0.0, 0.0, 0.0

@@ -168,6 +168,11 @@ class ShardedPath:
         particle picks, window offsets and Levy displacements per shard."""
         return self.path.BisectSweep(species, n_level, n_attempts, shard_seed(seed, self.sh.lo), attempt0, with_kinetic)
 
+    def BisectSweepWindows(self, species, n_level, n_rounds, seed, attempt0=0, with_kinetic=True):
+        """Rounds of the move on every disjoint window of THIS rank's shard at once (no communication; Rotate
+        between batches moves the windows' fixed end points).  Returns (accepts per clone, windows per round)."""
+        return self.path.BisectSweepWindows(species, n_level, n_rounds, shard_seed(seed, self.sh.lo), attempt0, with_kinetic)
+
     def _reduced(self, which, ai):
         import ctypes as C
         from . import capi

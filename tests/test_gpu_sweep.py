@@ -496,3 +496,96 @@ def test_path_dump_and_restart_resume_the_same_markov_chain(tmp_path):
     for a, e in zip(second.actions, ref_e):
         assert np.max(np.abs(a.DActionDBeta() - e) / np.abs(e)) <= 1e-12
     second.close()
+
+
+@pytest.mark.parametrize("name", ["ueg", "plasma", "ueg_slack", "sharded"])
+def test_multi_window_sweeps_follow_the_host_mirror(name):
+    """pimc_bisect_sweep_windows: every disjoint window of every walker attempted in the same launches.  The host
+    mirror walks the windows one after the other on the CPU oracle with the same Philox stream (keyed by walker * W +
+    window): the windows share only fixed end-point slices, so the sequential walk and the simultaneous device
+    update must leave the same positions (1e-12) and the same accept counts after every round."""
+    from simpimc_b200 import host, moves, sharded
+    from oracle import oracle as O
+    n_shards = 1
+    if name == "plasma":
+        cfg, n_level = S.plasma_config(Ne=5, Np=4, M=16), 2          # W = 4, windows tile the ring: 4 offsets
+    elif name == "ueg_slack":
+        cfg, n_level = S.ueg_config(N=7, M=22), 2                    # W = 5, 2 slices of slack: 3 offsets
+    elif name == "sharded":
+        cfg, n_level, n_shards = S.ueg_config(N=7, M=20), 2, 2       # shards of 10 slices: W = 2, 3 offsets
+    else:
+        cfg, n_level = S.ueg_config(N=9, M=16), 3                    # W = 2, 8 offsets
+    M, nb, n_clones, ns = cfg.n_bead, 1 << n_level, 2, len(cfg.species)
+    Rs = [np.stack([S.synthetic_paths(cfg, sp, c, 777) for c in range(n_clones)]) for sp in range(ns)]
+    oracles = [O.Oracle(cfg) for _ in range(n_clones)]
+    for c, o in enumerate(oracles):
+        for sp in range(ns):
+            o.set_positions(sp, Rs[sp][c])
+    shards = []
+    for g in range(n_shards):
+        sh = sharded.SliceSharding(M, n_shards, g)
+        p = host.Path(cfg, n_clones=n_clones, slice_lo=sh.lo, slice_hi=sh.hi) if n_shards > 1 else host.Path(cfg, n_clones=n_clones)
+        for sp in range(ns):
+            p.SetPositions(sp, sh.shard_positions(Rs[sp]) if n_shards > 1 else Rs[sp])
+        shards.append((sh, p))
+    n_dev = np.zeros(n_clones, dtype=np.int64)
+    n_host = np.zeros(n_clones, dtype=np.int64)
+    seed = 0x77AA5500
+    for rnd in range(10):
+        sp = rnd % ns
+        acts = [ai for ai, a in enumerate(cfg.actions) if cfg.species[sp].name in (a.species_a, a.species_b)]
+        for g, (sh, p) in enumerate(shards):
+            span = sh.n_local if n_shards > 1 else M
+            W = span // nb
+            n_off = nb if (n_shards == 1 and W * nb == span) else span - W * nb + 1
+
+            def get_beads(vc, q, b0, n):
+                return oracles[vc // W].get_positions(sp, 0)[q, (b0 + np.arange(n)) % M]
+
+            def action_old_new(vc, q, b0, nb_, new):
+                o = oracles[vc // W]
+                o.propose(sp, q, (b0 + 1) % M, new)
+                old = sum(o.get_action(ai, 0, b0, b0 + nb_, [(sp, q)], 0) for ai in acts)
+                nw = sum(o.get_action(ai, 1, b0, b0 + nb_, [(sp, q)], 0) for ai in acts)
+                return old, nw
+
+            def finish(vc, q, b0, nb_, accept, new):
+                if new is not None:
+                    oracles[vc // W].finish_move(sp, q, b0, b0 + nb_, bool(accept))
+
+            s_seed = seed + 31 * g
+            _, b0s, acc = moves.bisect_attempt_philox(cfg, sp, n_level, s_seed, rnd, n_clones * W, get_beads, action_old_new, finish,
+                                                      b0_range=(sh.lo if n_shards > 1 else 0, n_off), windows=W)
+            b0s = np.asarray(b0s).reshape(n_clones, W)
+            assert np.all(np.diff(b0s, axis=1) == nb)                       # disjoint windows sharing end points
+            if n_shards > 1:
+                assert np.all(b0s >= sh.lo) and np.all(b0s + nb <= sh.hi)
+            n_host += np.asarray(acc).reshape(n_clones, W).sum(axis=1)
+            got_acc, got_w = p.BisectSweepWindows(sp, n_level, 1, s_seed, attempt0=rnd)
+            assert got_w == W
+            n_dev += got_acc
+            for s2 in range(ns):
+                got = p.GetPositions(s2)
+                for c in range(n_clones):
+                    ref = oracles[c].get_positions(s2, 0)
+                    if n_shards > 1:
+                        ref = ref[:, np.array(sh.stored_slices()), :]
+                    assert np.max(np.abs(got[c] - ref)) <= 1e-12 * cfg.L, (name, rnd, g, s2, c)
+            assert np.array_equal(n_dev, n_host), (name, rnd, g, n_dev, n_host)
+    assert n_dev.sum() > 0
+    for ai in range(len(cfg.actions)):
+        du = sum(p.actions[ai].DActionDBeta() for _, p in shards)
+        for c, o in enumerate(oracles):
+            ref = o.dbeta(ai)
+            assert abs(du[c] - ref) <= 1e-10 * abs(ref), (name, ai, c)
+    for sh, p in shards:
+        for sp in range(ns):
+            for c in range(n_clones):
+                ref = oracles[c].rhok(sp, 0)
+                if n_shards > 1:
+                    ref = ref[sh.lo:sh.hi]
+                assert np.max(np.abs(p.GetRhoK(sp, c, host.OLD_MODE) - ref)) <= 1e-10 * cfg.species[sp].n_part
+    for _, p in shards:
+        p.close()
+    for o in oracles:
+        o.close()
