@@ -2398,7 +2398,7 @@ static int BisectSweepImpl(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_
             l.n_actions = 0;
             for (pimc_action *a : acts) {
                 if (!(a->use_long_range && n_k > 0)) continue;
-                if (l.n_actions == kMaxLrActions) return Fail(PIMC_ERR_UNSUPPORTED, "more than 4 long-range actions on one species");
+                if (l.n_actions == kMaxLrActions) return Fail(PIMC_ERR_UNSUPPORTED, "more than 8 long-range actions on one species");
                 const int partner = (a->sa == s) ? a->sb : a->sa;
                 l.rho_other[l.n_actions] = (partner == s) ? nullptr : ctx->species[partner]->rho.p;
                 l.wk[l.n_actions] = a->wk[WHICH_U].p;
@@ -2583,7 +2583,7 @@ int pimc_displace_sweep(pimc_ctx *ctx, int32_t s, double step_size, int32_t n_at
             l.n_actions = 0;
             for (pimc_action *a : acts) {
                 if (!(a->use_long_range && n_k > 0)) continue;
-                if (l.n_actions == kMaxLrActions) return Fail(PIMC_ERR_UNSUPPORTED, "more than 4 long-range actions on one species");
+                if (l.n_actions == kMaxLrActions) return Fail(PIMC_ERR_UNSUPPORTED, "more than 8 long-range actions on one species");
                 const int partner = (a->sa == s) ? a->sb : a->sa;
                 l.rho_other[l.n_actions] = (partner == s) ? nullptr : ctx->species[partner]->rho.p;
                 l.wk[l.n_actions] = a->wk[WHICH_U].p;

@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(kWinFastThreads, 1) pair_window_fast_kernel(co
 }
 
 // ------------------------------------------------------------ long-range part of a window
-constexpr int kMaxLrActions = 4;
+constexpr int kMaxLrActions = 8;  // long-range actions that involve one species (inputs/C/c.xml: 4)
 struct LrWindowArgs {
     PathView pv;
     SpeciesView sv;          // moved species with the pending proposal
