@@ -2385,6 +2385,8 @@ static int BisectSweepImpl(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_
             l.lr_old = lr_old;
             l.lr_new = lr_new;
             l.fuse_decide = 1;  // decision and commit ride on this launch
+            l.chunk_partial = nullptr;
+            l.n_chunks = 0;
             l.alive = alive;
             l.partial = partial;
             l.logu0 = logu0;
@@ -2548,7 +2550,7 @@ int pimc_displace_sweep(pimc_ctx *ctx, int32_t s, double step_size, int32_t n_at
             {
                 ScopedKernelTimer t(ctx, PIMC_KERNEL_PAIR_WINDOW);
                 if (a->atype == ATYPE_ILKKA && a->fast_ok[WHICH_U] && !ctx->force_general) {
-                    const size_t smem = (size_t)w.FT.n_bytes;
+                    const size_t smem = (((size_t)w.FT.n_bytes + 15) / 16 * 16) + kDispRingBytes;   // the ring takes the room K1's partner tile has
                     PIMC_CUDA(cudaFuncSetAttribute(displace_pair_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     displace_pair_kernel<-1><<<grid, kDispThreads, smem, ctx->stream>>>(w);
                 } else if (a->atype == ATYPE_ILKKA)
@@ -2572,14 +2574,17 @@ int pimc_displace_sweep(pimc_ctx *ctx, int32_t s, double step_size, int32_t n_at
             l.drho = st.drho.p;
             l.lr_old = lr_old;
             l.lr_new = lr_new;
-            l.fuse_decide = 0;  // displace_decide_commit_kernel decides: the pair sums are per chunk
+            l.fuse_decide = 1;  // decision and commit ride on this launch (the pair sums arrive per 32-link chunk)
             l.alive = nullptr;
-            l.partial = l.logu0 = l.pair_old = l.pair_new = nullptr;
+            l.partial = l.pair_old = l.pair_new = nullptr;
+            l.logu0 = logu;
+            l.chunk_partial = ctx->partial.p;
+            l.n_chunks = n_chunks;
             l.N = st.N;
-            l.R = nullptr;
-            l.rho_commit = nullptr;
-            l.accept = nullptr;
-            l.n_accept = nullptr;
+            l.R = st.R.p;
+            l.rho_commit = st.rho.p;
+            l.accept = accept;
+            l.n_accept = ctx->mc_naccept.p;
             l.n_actions = 0;
             for (pimc_action *a : acts) {
                 if (!(a->use_long_range && n_k > 0)) continue;
@@ -2599,10 +2604,11 @@ int pimc_displace_sweep(pimc_ctx *ctx, int32_t s, double step_size, int32_t n_at
             }
             ctx->launches++;
         }
-        displace_decide_commit_kernel<<<C, 256, 0, ctx->stream>>>(pv, st.N, n_k, n_chunks, ctx->partial.p, any_lr ? 1 : 0, lr_old, lr_new, logu, st.P.p,
-                                                                 st.P_particle.p, any_lr ? st.drho.p : nullptr, st.R.p,
-                                                                 any_lr ? st.rho.p : nullptr, accept, ctx->mc_naccept.p);
-        ctx->launches++;
+        if (!any_lr) {  // with a long-range action the decision and the commit rode on lr_window_kernel
+            displace_decide_commit_kernel<<<C, 256, 0, ctx->stream>>>(pv, st.N, n_k, n_chunks, ctx->partial.p, 0, lr_old, lr_new, logu, st.P.p,
+                                                                     st.P_particle.p, nullptr, st.R.p, nullptr, accept, ctx->mc_naccept.p);
+            ctx->launches++;
+        }
     }
     PIMC_CUDA(cudaGetLastError());
     st.n_prop = 0;

@@ -81,6 +81,25 @@ __global__ void __launch_bounds__(128) displace_sample_kernel(const DisplaceSamp
 #endif
 constexpr int kDispThreads = PIMC_DISP_THREADS;
 constexpr int kDispWarps = kDispThreads / 32;
+// Partner rows staged per warp through shared memory with cp.async, kDispStages partners ahead (0: each warp loads its
+// partner rows straight into registers when it needs them -- the round-1 kernel, long-scoreboard bound at 16 warps per SM).
+// The ring lives in the shared memory K1 keeps for its partner tile, which this kernel does not use.
+#ifndef PIMC_DISP_STAGES
+#define PIMC_DISP_STAGES 3
+#endif
+constexpr int kDispStages = PIMC_DISP_STAGES;
+constexpr int kDispRingRow = 34;                                  // 33 slices of a chunk (+1 pad)
+constexpr int kDispRingDoubles = 3 * kDispRingRow;                // one partner: 3 dims
+constexpr size_t kDispRingBytes = (size_t)kDispWarps * (kDispStages > 0 ? kDispStages : 1) * kDispRingDoubles * sizeof(double);
+
+__device__ __forceinline__ void CpAsync8(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void CpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void CpAsyncWait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 struct DisplacePairArgs {
     PathView pv;
@@ -112,6 +131,8 @@ __global__ void __launch_bounds__(kDispThreads, 1) displace_pair_kernel(const Di
         StageBlockTma(dsm, a.fast_tables, a.FT.n_bytes, &stage_bar);
     }
     const SharedTab tb(dsm);
+    // per-warp ring of staged partner rows behind the table block (fast path only)
+    double *ring_q = reinterpret_cast<double *>(dsm + ((ATYPE < 0 ? a.FT.n_bytes : 0) + 15) / 16 * 16) + (size_t)warp * (kDispStages > 0 ? kDispStages : 1) * kDispRingDoubles;
     const int n_items = pv.C * a.n_chunks;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int c = item / a.n_chunks, chunk = item - c * a.n_chunks;
@@ -144,13 +165,59 @@ __global__ void __launch_bounds__(kDispThreads, 1) displace_pair_kernel(const Di
                 acc_new += v;
             n_parked = 0;
         };
-        for (int q = warp; q < a.N_partner; q += kDispWarps) {
-            if (a.same && q == p) continue;
-            double q0[3], q1[3];
+        // element i of a staged row = slice chunk * 32 + i; the element after the chunk's last link is that link's next
+        // slice (the beta-periodic wrap included), fetched by lane 0
+        const int n_valid = min(32, pv.M - chunk * 32);
+        const int b_extra = chunk * 32 + n_valid >= pv.M ? chunk * 32 + n_valid - pv.M : chunk * 32 + n_valid;
+        auto stage_partner = [&](int q, int slot) {
+            double *dst = ring_q + (size_t)slot * kDispRingDoubles;
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
-                q0[d] = lane_on ? a.R_partner[PosIndex(pv, a.N_partner, c, q, d, b)] : 0.;
-                q1[d] = lane_on ? a.R_partner[PosIndex(pv, a.N_partner, c, q, d, bn)] : 0.;
+                const double *src = a.R_partner + PosIndex(pv, a.N_partner, c, q, d, 0);
+                if (lane_on)
+                    CpAsync8(dst + d * kDispRingRow + lane, src + b);
+                else
+                    dst[d * kDispRingRow + lane + 1] = 0.;   // unused elements stay finite (they feed lookups of masked lanes)
+                if (lane == 0) CpAsync8(dst + d * kDispRingRow + n_valid, src + b_extra);
+            }
+        };
+        int q_stage = warp;   // next partner to stage
+        if (ATYPE < 0 && kDispStages > 0) {
+            __syncwarp();
+#pragma unroll
+            for (int st = 0; st < (kDispStages > 0 ? kDispStages - 1 : 0); ++st) {
+                if (q_stage < a.N_partner) stage_partner(q_stage, st);
+                CpAsyncCommit();
+                q_stage += kDispWarps;
+            }
+        }
+        int slot = 0;
+        for (int q = warp; q < a.N_partner; q += kDispWarps) {
+            double q0[3], q1[3];
+            if (ATYPE < 0 && kDispStages > 0) {
+                // keep kDispStages - 1 partners in flight, then wait for the oldest
+                const int fill = slot == 0 ? kDispStages - 1 : slot - 1;
+                if (q_stage < a.N_partner) stage_partner(q_stage, fill);
+                CpAsyncCommit();
+                q_stage += kDispWarps;
+                CpAsyncWait<(kDispStages > 0 ? kDispStages - 1 : 0)>();
+                __syncwarp();
+                const double *src = ring_q + (size_t)slot * kDispRingDoubles + lane;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    q0[d] = src[d * kDispRingRow];
+                    q1[d] = src[d * kDispRingRow + 1];
+                }
+                __syncwarp();   // the slot is read before a later iteration refills it
+                slot = slot + 1 == kDispStages ? 0 : slot + 1;
+                if (a.same && q == p) continue;
+            } else {
+                if (a.same && q == p) continue;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    q0[d] = lane_on ? a.R_partner[PosIndex(pv, a.N_partner, c, q, d, b)] : 0.;
+                    q1[d] = lane_on ? a.R_partner[PosIndex(pv, a.N_partner, c, q, d, bn)] : 0.;
+                }
             }
             // the shifted beads p + dr (rounded as the stored proposal is) are formed per step from a shift
             // re-read from shared memory (asm volatile: not hoisted): 12 registers fewer live across the loop
@@ -187,6 +254,7 @@ __global__ void __launch_bounds__(kDispThreads, 1) displace_pair_kernel(const Di
             acc_new += lane_on ? un : 0.;
         }
         if (ATYPE < 0 && n_parked > 0) flush_ring();
+        if (ATYPE < 0 && kDispStages > 0) CpAsyncWait<0>();   // nothing of this item is in flight into the ring any more
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             acc_old += __shfl_down_sync(0xffffffffu, acc_old, o);

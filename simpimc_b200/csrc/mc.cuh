@@ -472,8 +472,11 @@ struct LrWindowArgs {
     // fuse_decide != 0: the kernel also takes the level-0 Metropolis decision and commits
     // (bisect_decide_commit_kernel's work, one launch less per attempt)
     int fuse_decide;
-    const int32_t *alive;
-    const double *partial, *logu0, *pair_old, *pair_new;  // [C]
+    const int32_t *alive;    // nullptr: every clone is alive (DisplaceParticle has no earlier levels)
+    const double *partial, *logu0, *pair_old, *pair_new;  // [C]; partial == nullptr: 0
+    // pair sums left per 32-link chunk by displace_pair_kernel, [C][n_chunks][2] (OLD, NEW), summed here in chunk order
+    const double *chunk_partial;
+    int n_chunks;
     int N;
     double *R;               // committed positions of the moved species
     double2 *rho_commit;     // == rho_self, writable
@@ -553,11 +556,23 @@ __global__ void __launch_bounds__(256) lr_window_kernel(const LrWindowArgs a) {
         }
         a.lr_old[c] = to;
         a.lr_new[c] = tn;
-        if (a.fuse_decide) {  // bisect_class.h:110-115, same arithmetic as bisect_decide_commit_kernel
+        if (a.fuse_decide) {  // bisect_class.h:110-115 / displace_particle_class.h:65-71, same arithmetic as the *_decide_commit kernels
             int acc = 0;
-            if (a.alive[c]) {
-                const double old_action = a.pair_old[c] + to, new_action = a.pair_new[c] + tn;
-                acc = (a.partial[c] - (new_action - old_action)) < a.logu0[c] ? 0 : 1;
+            if (!a.alive || a.alive[c]) {
+                double po, pn;
+                if (a.chunk_partial) {
+                    po = pn = 0.;
+                    for (int i = 0; i < a.n_chunks; ++i) {
+                        po += a.chunk_partial[((size_t)c * a.n_chunks + i) * 2];
+                        pn += a.chunk_partial[((size_t)c * a.n_chunks + i) * 2 + 1];
+                    }
+                } else {
+                    po = a.pair_old[c];
+                    pn = a.pair_new[c];
+                }
+                const double old_action = po + to, new_action = pn + tn;
+                acc = a.partial ? ((a.partial[c] - (new_action - old_action)) < a.logu0[c] ? 0 : 1)
+                                : ((old_action - new_action) < a.logu0[c] ? 0 : 1);
             }
             a.accept[c] = acc;
             a.n_accept[c] += acc;
@@ -567,11 +582,12 @@ __global__ void __launch_bounds__(256) lr_window_kernel(const LrWindowArgs a) {
     if (!a.fuse_decide) return;
     __syncthreads();
     if (!s_accept) return;
-    // Move::Accept: the proposal's beads and rho_k += delta on the window (every read of rho_self is behind the barrier)
-    const int n_prop = a.n_window - 1, bead0 = a.b0[c];
+    // Move::Accept: the proposal's beads (n_prop beads from P_first: the window's interior for a bisection, the whole
+    // path for a displacement) and rho_k += delta on the window (every read of rho_self is behind the barrier)
+    const int n_prop = a.sv.n_prop, bead0 = a.b0[c], first = a.sv.P_first[c];
     for (int t = tid; t < n_prop * 3; t += blockDim.x) {
         const int j = t / 3, d = t - j * 3;
-        int bg = bead0 + 1 + j;
+        int bg = first + j;
         bg = WrapSlice(pv, bg);
         a.R[PosIndex(pv, a.N, RealClone(pv, c), p, d, bg - pv.slice_lo)] = a.sv.P[((size_t)c * n_prop + j) * 3 + d];
     }
