@@ -460,6 +460,17 @@ int ref_perm_counts(void *h, int m, int n_max, uint32_t *attempt, uint32_t *acce
     return n;
 }
 
+/// The permutation as PathDump records it (path_dump_class.h:46-51): next[p] = label of the bead that follows
+/// (p, n_bead - 1), prev[p] = label of the bead that precedes (p, 0).
+void ref_permutation(void *h, int sp, int32_t *prev, int32_t *next) {
+    RefSim *s = (RefSim *)h;
+    std::shared_ptr<Species> species = s->path->GetSpecies()[sp];
+    for (uint32_t p = 0; p < species->GetNPart(); ++p) {
+        prev[p] = (int32_t)species->GetBead(p, 0)->GetPrevBead(1)->GetP();
+        next[p] = (int32_t)species->GetBead(p, species->GetNBead() - 1)->GetNextBead(1)->GetP();
+    }
+}
+
 int ref_n_moves(void *h) { return ((RefSim *)h)->moves.size(); }
 void ref_move_do(void *h, int m, int n_times) {
     RefSim *s = (RefSim *)h;

@@ -89,6 +89,9 @@ def _load(fast=False, dropin=False):
     lib.ref_energy_sums.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
     lib.ref_move_do.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.ref_move_counts.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    if hasattr(lib, "ref_permutation"):
+        lib.ref_permutation.argtypes = [C.c_void_p, C.c_int, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS"),
+                                        np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")]
     if hasattr(lib, "ref_inject_random"):
         lib.ref_inject_random.argtypes = [_dp, C.c_int, _dp, C.c_int]
         lib.ref_inject_pending.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]
@@ -315,6 +318,13 @@ class RefSim:
         n = self.lib.ref_perm_counts(self.h, m, n_max, att, acc)
         assert n >= 0
         return att[:n], acc[:n]
+
+    def permutation(self, sp):
+        """(prev, next): labels of the beads before (p, 0) and after (p, n_bead - 1) (path_dump_class.h:46-51)."""
+        N = self.lib.ref_n_part(self.h, sp)
+        prev, nxt = np.zeros(N, dtype=np.int32), np.zeros(N, dtype=np.int32)
+        self.lib.ref_permutation(self.h, sp, prev, nxt)
+        return prev, nxt
 
     def move_do(self, m, n_times=1):
         self.lib.ref_move_do(self.h, m, n_times)

@@ -124,3 +124,75 @@ def test_displace_mirror_follows_the_reference_program(name, oracle_mod):
     assert 0 < n_acc < n_att, n_acc
     o.close()
     sim.close()
+
+
+@pytest.mark.parametrize("n_images_kin,n_level", [(0, 2), (1, 3)])
+def test_permuting_bisection_mirror_follows_the_reference_program(n_images_kin, n_level, oracle_mod):
+    """PermBisectIterative (cycle selection from the permutation table, PermuteBeads, the members' Levy bridges,
+    AssignParticleLabels; perm_bisect_iterative_class.h:10-222, perm_bisect_class.h:32-82) of the reference on injected
+    Philox numbers against simpimc_b200.perm_moves.perm_bisect_attempt, which keeps positions by label plus the seam
+    permutation.  After every attempt: the same cycle lengths attempted and accepted (integer state,
+    bit-exact), the same seam permutation, the same positions by label; windows that roll over the seam of an already
+    permuted path and cycles of two and more particles occur."""
+    from oracle import refsim
+    from simpimc_b200 import perm_moves as PM
+    if not refsim.available():
+        pytest.skip("oracle/_ref not built")
+    N, M = 5, 16
+    pair_cfg = S.egas_config(N=N, M=M, n_xy=40, n_r_long=200)      # theta = 0.1: exchange is frequent
+    cfg = copy.copy(pair_cfg)
+    cfg.actions = [S.ActionConfig("Kinetic", "Kinetic", "e", n_images=n_images_kin)] + list(pair_cfg.actions)
+    cfg.moves = [{"name": "PermE", "type": "PermBisectIterative", "species": "e", "n_level": n_level, "n_images": 0}]
+    cfg.observables = []
+    sim = refsim.RefSim(cfg, seed=1)
+    if not hasattr(sim.lib, "ref_inject_random") or not hasattr(sim.lib, "ref_permutation"):
+        pytest.skip("oracle/_ref predates the injection hooks")
+    R = S.synthetic_paths(cfg, 0, 0, 5).copy()
+    perm_next = np.arange(N, dtype=np.int32)
+    sim.set_positions(0, R)
+    o = oracle_mod.Oracle(pair_cfg)
+    o.set_positions(0, R)
+    seed = 0x9E3700000000C1C1
+
+    def action_old_new(labels, bead0, nb, windows):
+        for l in labels:
+            o.propose(0, l, bead0, windows[l])
+        parts = [(0, l) for l in labels]
+        old = o.get_action(0, 0, bead0, bead0 + nb, parts, 0)
+        new = o.get_action(0, 1, bead0, bead0 + nb, parts, 0)
+        for l in labels:
+            o.finish_move(0, l, bead0, bead0 + nb, False)
+        return old, new
+
+    n_att = 150
+    attempted = np.zeros(8, dtype=np.int64)
+    accepted = np.zeros(8, dtype=np.int64)
+    n_acc = wrapped_on_permuted = 0
+    for attempt in range(n_att):
+        R_try, perm_try = R.copy(), perm_next.copy()
+        res = PM.perm_bisect_attempt(pair_cfg, 0, n_level, seed, attempt, 0, R_try, perm_try, action_old_new, n_images_kin=n_images_kin)
+        u, n = PM.perm_philox_numbers(pair_cfg, 0, n_level, seed, attempt, 0, res["steps"], max(res["n_perm"], 0))
+        sim.inject_random(u, n)
+        sim.move_do(0, 1)
+        left = sim.inject_pending(clear=True)
+        if res["n_perm"] > 0:
+            attempted[res["n_perm"] - 1] += 1
+            if res["accept"]:
+                accepted[res["n_perm"] - 1] += 1
+                n_acc += 1
+                assert left == (0, 0), (attempt, left)
+                if res["bead0"] + (1 << n_level) > M - 1 and not np.array_equal(perm_next, np.arange(N)):
+                    wrapped_on_permuted += 1
+                R, perm_next = R_try, perm_try
+                o.set_positions(0, R)
+        att_ref, acc_ref = sim.perm_counts(0)
+        assert np.array_equal(att_ref[:N], attempted[:N]) and np.array_equal(acc_ref[:N], accepted[:N]), (attempt, att_ref, attempted, acc_ref, accepted)
+        assert sim.move_counts(0) == (attempt + 1, n_acc)
+        assert np.array_equal(sim.permutation(0)[1], perm_next), (attempt, sim.permutation(0)[1], perm_next)
+        ref_R = sim.get_positions(0, 0)
+        assert np.max(np.abs(ref_R - R)) <= 1e-12 * max(1.0, np.max(np.abs(R))), (attempt, res)
+    assert accepted[1:].sum() >= 3, accepted          # real permutations (two or more particles) were accepted
+    assert wrapped_on_permuted >= 1                   # a window rolled over the seam of an already permuted path
+    assert 0 < n_acc < n_att
+    o.close()
+    sim.close()
