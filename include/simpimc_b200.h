@@ -187,7 +187,7 @@ int pimc_action_potential_device(pimc_action *act, double *d_out);
 
 /* Action::GetAction(b0, b1, particles, level) (pair_action_class.h:267-302).
  *   b0[n_clones]                first slice of each clone's window; b1 = b0 + n_window
- *   moved_species[n_moved]      species of each moved particle (same for all clones); up to four
+ *   moved_species[n_moved]      species of each moved particle (same for all clones); up to sixteen
  *                               particles of each of the action's species (permutation cycles)
  *   moved_particle[n_clones][n_moved]
  * Returns 0 for level > max_level or constant actions, as the reference does.  In NEW mode
@@ -236,7 +236,7 @@ int pimc_ctx_force_general(pimc_ctx *ctx, int32_t enable);
 /* NEW-mode Bead::SetR for one particle per clone (bisect_class.h:89-94,
  * displace_particle_class.h:40-50): beads b_first[c] .. b_first[c]+n_beads-1 (mod n_bead)
  * of particle[c] take newR[c][i][dim].  Calling it again for a species that already has a pending
- * proposal ADDS a particle (same n_beads, a different particle in every clone; at most four per
+ * proposal ADDS a particle (same n_beads, a different particle in every clone; at most sixteen per
  * species): the particles of a permutation cycle. */
 int pimc_propose(pimc_ctx *ctx, int32_t species, const int32_t *particle, const int32_t *b_first, int32_t n_beads,
                  const double *newR);
@@ -293,6 +293,32 @@ int pimc_displace_sweep(pimc_ctx *ctx, int32_t species, double step_size, int32_
  * on the unpermuted path.  Cycle selection and the relabelling of an accepted permutation stay with
  * the caller.  t is host memory, [n_clones][N][N]. */
 int pimc_perm_table(pimc_ctx *ctx, int32_t species, const int32_t *b0, int32_t n_bisect_beads, double epsilon, int32_t relative, double *t);
+
+/* Permuting bisection on the device: n_attempts x PermBisectIterative::DoEvent
+ * (src/events/moves/single_species_move/bisect/perm_bisect/perm_bisect_iterative_class.h:113-222 on
+ * perm_bisect_class.h:32-82) on every clone.  Per attempt: first bead and first particle, the cycle grown from rows of
+ * the permutation table (SelectCycleIterative, :33-111; cycles longer than 8 particles are counted as not attempted),
+ * PermuteBeads + the Levy bridge of every member level by level, the kinetic action along the links, every pair
+ * action of the species in OLD and NEW mode over the listed particles, Metropolis per level starting from
+ * -log(cycle weight), and on acceptance AssignParticleLabels (perm_bisect_class.h:47-56).  The path is kept by particle
+ * LABEL plus the permutation at the beta seam (pimc_permutation_get): a chain keeps its label inside the path and
+ * continues as next[label] across the seam; pair actions pair labels at equal slices, as the reference's GetBead(p, b)
+ * does.  A cycle of one particle is the plain bisection with the links followed.  Philox slots are
+ * documented in csrc/perm.cuh.  n_accept[n_clones], perm_attempt / perm_accept[n_clones][8] (by cycle length - 1;
+ * the reference's perm_attempt / perm_accept vectors, perm_bisect_class.h:21-22) are host memory, ADDED to, may be NULL. */
+int pimc_perm_bisect_sweep(pimc_ctx *ctx, int32_t species, int32_t n_level, int32_t n_attempts, uint64_t seed, uint64_t attempt0,
+                           int32_t with_kinetic, double epsilon, int64_t *n_accept, int64_t *perm_attempt, int64_t *perm_accept);
+/* The permutation at the beta seam, next[n_clones][N] (host memory): next[c][p] = label of the bead that follows
+ * (p, n_bead - 1) of clone c -- the reference's Bead::next link of the last slice (species_class.h:302-321 writes the
+ * same array as the `permutation` dataset of a path dump).  Identity until a permuting move or _set changes it.
+ * While a species is permuted, the entry points that read one particle's path by label across the seam
+ * (pimc_bisect_sweep, pimc_displace_sweep, a Kinetic handle's pimc_action_get) fail with PIMC_ERR_UNSUPPORTED;
+ * whole-path evaluations follow the links (Kinetic) or do not depend on them (pair actions, g(r), S(k)). */
+int pimc_permutation_get(pimc_ctx *ctx, int32_t species, int32_t *next);
+int pimc_permutation_set(pimc_ctx *ctx, int32_t species, const int32_t *next);
+/* Tests: the cycle of the LAST attempt of pimc_perm_bisect_sweep per clone -- window start, cycle length (0: the
+ * selection stopped, -1: longer than 8), members[n_clones][8] (-1 padded), selection steps, accept flag.  Any may be NULL. */
+int pimc_perm_last_cycle(pimc_ctx *ctx, int32_t *b0, int32_t *n_perm, int32_t *particles, int32_t *n_steps, int32_t *accept);
 
 /* ---- slice sharding over several GPUs ---------------------------------------------------- */
 /* One large path split by imaginary-time slice (pimc_config.slice_lo / slice_hi), one context and one

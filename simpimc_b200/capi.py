@@ -163,6 +163,7 @@ EXPORTS = [
     "pimc_action_calc_pair_fast", "pimc_debug_fast_sqrt", "pimc_debug_interval_table", "pimc_ctx_force_general", "pimc_bisect_sweep", "pimc_displace_sweep", "pimc_perm_table", "pimc_halo_pack", "pimc_halo_unpack", "pimc_rotate_pack", "pimc_rotate_apply",
     "pimc_comm_unique_id", "pimc_comm_init", "pimc_comm_destroy", "pimc_comm_bytes_sent", "pimc_halo_exchange", "pimc_allreduce_sum", "pimc_rotate",
     "pimc_action_create_kinetic", "pimc_move_set_images", "pimc_bisect_sweep_windows", "pimc_sharded_evaluate", "pimc_capture_begin", "pimc_capture_end", "pimc_graph_launch", "pimc_graph_nodes", "pimc_graph_destroy",
+    "pimc_perm_bisect_sweep", "pimc_permutation_get", "pimc_permutation_set", "pimc_perm_last_cycle",
 ]
 
 _lib = None
@@ -231,6 +232,10 @@ def lib():
     L.pimc_bisect_sweep_windows.argtypes = [vp, i32, i32, i32, C.c_uint64, C.c_uint64, i32, vp, c_int32_p]
     L.pimc_displace_sweep.argtypes = [vp, i32, C.c_double, i32, C.c_uint64, C.c_uint64, vp]
     L.pimc_perm_table.argtypes = [vp, i32, vp, i32, C.c_double, i32, vp]
+    L.pimc_perm_bisect_sweep.argtypes = [vp, i32, i32, i32, C.c_uint64, C.c_uint64, i32, C.c_double, vp, vp, vp]
+    L.pimc_permutation_get.argtypes = [vp, i32, vp]
+    L.pimc_permutation_set.argtypes = [vp, i32, vp]
+    L.pimc_perm_last_cycle.argtypes = [vp, vp, vp, vp, vp, vp]
     L.pimc_action_create_kinetic.argtypes = [vp, i32, i32, C.POINTER(vp)]
     L.pimc_move_set_images.argtypes = [vp, i32, i32]
     L.pimc_comm_unique_id.argtypes = [vp]

@@ -24,6 +24,7 @@
 #include "sweep_fused.cuh"
 #include "grad.cuh"
 #include "displace.cuh"
+#include "perm.cuh"
 #include "spline_build.h"
 
 using namespace pimc;
@@ -97,6 +98,10 @@ struct SpeciesState {
     int drho_window = 0;
     bool drho_valid = false;
     bool need_update_rho_k = true;  // Species::need_update_rho_k_ (species_class.h:25)
+    // permutation at the beta seam: next[c][p] = label of the bead that follows (p, n_bead - 1);
+    // allocated (as the identity) by the first permuting move or pimc_permutation_set, absent = unpermuted
+    DevBuf<int32_t> perm_next;
+    bool perm_tracked = false;
 };
 
 }  // namespace
@@ -129,6 +134,11 @@ struct pimc_ctx {
     DevBuf<double> mc_f64;    // partial, logu0, pair_old, pair_new, lr_old, lr_new: 6 x [C]
     DevBuf<int32_t> mc_i32;   // alive, b0, accept: 3 x [C]
     DevBuf<long long> mc_naccept;
+    // permuting bisection (perm.cuh): cycle of the attempt in flight, link sums per action and mode, label-rotation scratch
+    DevBuf<int32_t> perm_i32;      // n_perm [C], n_steps [C], particles [C][kPermMaxLen]
+    DevBuf<double> perm_f64;       // weight [C], lr_old [C], lr_new [C], pair_parts [n_actions][2][C][nb]
+    DevBuf<double> perm_stage;     // [C][kPermMaxLen][3][M]
+    DevBuf<long long> perm_counts; // attempted, accepted: 2 x [C][kPermMaxLen]
     std::vector<pimc_action *> actions;
     int64_t launches = 0;
     bool force_general = false;  // tests: evaluate with the general kernels even where the fast path applies
@@ -1174,6 +1184,7 @@ int KineticFull(pimc_action *a, int which, double *d_out) {
     k.pv = ctx->View();
     k.sv = ctx->SView(a->sa, false);
     k.n_chunks = (ctx->Mloc + 31) / 32;
+    k.next = st.perm_tracked ? st.perm_next.p : nullptr;  // the link over the beta seam follows the permutation (GetNextBead)
     const size_t items = (size_t)ctx->C * k.n_chunks;
     if (ctx->partial.n < items) PIMC_CUDA(ctx->partial.Alloc(items));
     k.partial = ctx->partial.p;
@@ -1211,6 +1222,8 @@ int EnsureOut(pimc_ctx *ctx) {
 
 // =========================================================================== C ABI
 extern "C" {
+
+static int RequireUnpermuted(pimc_ctx *ctx, int s, const char *what);  // permuting bisection, below
 
 const char *pimc_last_error(void) { return g_last_error.c_str(); }
 int pimc_version(void) { return 100; }
@@ -1784,7 +1797,11 @@ int pimc_action_get(pimc_action *act, int32_t mode, const int32_t *b0, int32_t n
             for (int c = 0; c < ctx->C; ++c) out[c] = 0.;
             return PIMC_OK;
         }
-        if ((int)idx.size() > kMaxPropSlots) return Fail(PIMC_ERR_UNSUPPORTED, "more than 4 listed particles of one species");
+        if ((int)idx.size() > kMaxPropSlots) return Fail(PIMC_ERR_UNSUPPORTED, "more than 16 listed particles of one species");
+        {  // the window kernel reads a particle's beads by label: exact on an unpermuted path only
+            const int rc_p = RequireUnpermuted(ctx, act->sa, "Kinetic::GetAction over a window");
+            if (rc_p != PIMC_OK) return rc_p;
+        }
         if (n_window == ctx->M) {  // bead_a->GetNextBead(b1 - b0) is bead_a itself: the reference's loop body never runs (kinetic_class.h:112-113)
             for (int c = 0; c < ctx->C; ++c) out[c] = 0.;
             return PIMC_OK;
@@ -1823,7 +1840,7 @@ int pimc_action_get(pimc_action *act, int32_t mode, const int32_t *b0, int32_t n
     }
     if (act->sa == act->sb) ib.clear();
     if ((int)ia.size() > kMaxPropSlots || (int)ib.size() > kMaxPropSlots)
-        return Fail(PIMC_ERR_UNSUPPORTED, "more than 4 listed particles of one species");
+        return Fail(PIMC_ERR_UNSUPPORTED, "more than 16 listed particles of one species");
     if (ia.empty() && ib.empty()) {  // pair_action_class.h:77-78
         for (int c = 0; c < ctx->C; ++c) out[c] = 0.;
         return PIMC_OK;
@@ -2097,7 +2114,7 @@ int pimc_propose(pimc_ctx *ctx, int32_t s, const int32_t *particle, const int32_
     int slot = 0;
     if (st.n_prop > 0 && st.n_slots > 0) {
         if (n_beads != st.n_prop) return Fail(PIMC_ERR_INVALID, "proposals of one species must cover the same number of beads");
-        if (st.n_slots == kMaxPropSlots) return Fail(PIMC_ERR_UNSUPPORTED, "more than 4 proposed particles of one species");
+        if (st.n_slots == kMaxPropSlots) return Fail(PIMC_ERR_UNSUPPORTED, "more than 16 proposed particles of one species");
         for (int sl = 0; sl < st.n_slots; ++sl)
             for (int c = 0; c < ctx->C; ++c)
                 if (st.h_particle[(size_t)sl * ctx->C + c] == particle[c]) return Fail(PIMC_ERR_INVALID, "particle proposed twice");
@@ -2208,6 +2225,10 @@ static int BisectSweepImpl(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_
     for (auto &sp : ctx->species)
         if (sp->n_prop > 0) return Fail(PIMC_ERR_INVALID, "a proposal is pending: call pimc_commit first");
     PIMC_CUDA(cudaSetDevice(ctx->device));
+    {
+        const int rc_p = RequireUnpermuted(ctx, s, "pimc_bisect_sweep");
+        if (rc_p != PIMC_OK) return rc_p;
+    }
     const int Cw = ctx->C;                       // walkers
     const int C = Cw * W;                        // virtual clones: (walker, window); == walkers in the classic mode
     const int nb = 1 << n_level, n_prop = nb - 1, n_k = ctx->n_k();
@@ -2471,6 +2492,321 @@ int pimc_perm_table(pimc_ctx *ctx, int32_t s, const int32_t *b0, int32_t n_bisec
     return ToHost(ctx, ctx->stage.p, t, n);
 }
 
+// ------------------------------------------------------------------- permuting bisection
+/// The species' seam permutation, created as the identity on first use.
+static int EnsurePermutation(pimc_ctx *ctx, int s) {
+    SpeciesState &st = *ctx->species[s];
+    if (st.perm_tracked) return PIMC_OK;
+    const size_t n = (size_t)ctx->C * st.N;
+    PIMC_CUDA(st.perm_next.Alloc(n));
+    perm_identity_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(st.perm_next.p, ctx->C, st.N);
+    ctx->launches++;
+    PIMC_CUDA(cudaGetLastError());
+    st.perm_tracked = true;
+    return PIMC_OK;
+}
+
+/// Entry points that read a particle's path by LABEL across the beta seam (Bisect, DisplaceParticle, Kinetic::GetAction
+/// windows) are exact only on an unpermuted path: refuse loudly once a permuting move has changed the seam.
+static int RequireUnpermuted(pimc_ctx *ctx, int s, const char *what) {
+    SpeciesState &st = *ctx->species[s];
+    if (!st.perm_tracked) return PIMC_OK;
+    std::vector<int32_t> h((size_t)ctx->C * st.N);
+    PIMC_CUDA(cudaMemcpyAsync(h.data(), st.perm_next.p, h.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PIMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < h.size(); ++i)
+        if (h[i] != (int32_t)(i % st.N))
+            return Fail(PIMC_ERR_UNSUPPORTED, std::string(what) + " on a species whose path is permuted at the beta seam: use pimc_perm_bisect_sweep "
+                                                                  "(cycles of one particle are the plain bisection, links followed)");
+    return PIMC_OK;
+}
+
+int pimc_permutation_get(pimc_ctx *ctx, int32_t s, int32_t *next) {
+    if (!ctx || !next) return Fail(PIMC_ERR_INVALID, "null argument");
+    if (s < 0 || s >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
+    SpeciesState &st = *ctx->species[s];
+    if (!st.perm_tracked) {
+        for (int c = 0; c < ctx->C; ++c)
+            for (int p = 0; p < st.N; ++p) next[(size_t)c * st.N + p] = p;
+        return PIMC_OK;
+    }
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    PIMC_CUDA(cudaMemcpyAsync(next, st.perm_next.p, (size_t)ctx->C * st.N * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PIMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PIMC_OK;
+}
+
+int pimc_permutation_set(pimc_ctx *ctx, int32_t s, const int32_t *next) {
+    if (!ctx || !next) return Fail(PIMC_ERR_INVALID, "null argument");
+    if (s < 0 || s >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
+    if (ctx->sharded) return Fail(PIMC_ERR_UNSUPPORTED, "permutations on a slice-sharded context");
+    SpeciesState &st = *ctx->species[s];
+    std::vector<char> seen(st.N);
+    for (int c = 0; c < ctx->C; ++c) {  // a permutation of the labels per walker
+        std::fill(seen.begin(), seen.end(), 0);
+        for (int p = 0; p < st.N; ++p) {
+            const int32_t q = next[(size_t)c * st.N + p];
+            if (q < 0 || q >= st.N || seen[q]) return Fail(PIMC_ERR_INVALID, "next[] is not a permutation of the particle labels");
+            seen[q] = 1;
+        }
+    }
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    int rc = EnsurePermutation(ctx, s);
+    if (rc != PIMC_OK) return rc;
+    PIMC_CUDA(cudaMemcpyAsync(st.perm_next.p, next, (size_t)ctx->C * st.N * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    PIMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PIMC_OK;
+}
+
+int pimc_perm_last_cycle(pimc_ctx *ctx, int32_t *b0, int32_t *n_perm, int32_t *particles, int32_t *n_steps, int32_t *accept) {
+    if (!ctx) return Fail(PIMC_ERR_INVALID, "null context");
+    const int C = ctx->C;
+    if (ctx->perm_i32.n < (size_t)C * (2 + kPermMaxLen) || ctx->mc_i32.n < (size_t)3 * C) return Fail(PIMC_ERR_INVALID, "no permuting bisection has run on this context");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    const int32_t *d_n_perm = ctx->perm_i32.p, *d_steps = d_n_perm + C, *d_part = d_steps + C;
+    const int32_t *d_b0 = ctx->mc_i32.p + C, *d_accept = ctx->mc_i32.p + 2 * C;
+    if (b0) PIMC_CUDA(cudaMemcpyAsync(b0, d_b0, C * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_perm) PIMC_CUDA(cudaMemcpyAsync(n_perm, d_n_perm, C * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (particles) PIMC_CUDA(cudaMemcpyAsync(particles, d_part, (size_t)C * kPermMaxLen * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_steps) PIMC_CUDA(cudaMemcpyAsync(n_steps, d_steps, C * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (accept) PIMC_CUDA(cudaMemcpyAsync(accept, d_accept, C * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PIMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PIMC_OK;
+}
+
+int pimc_perm_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_attempts, uint64_t seed, uint64_t attempt0,
+                           int32_t with_kinetic, double epsilon, int64_t *n_accept, int64_t *perm_attempt, int64_t *perm_accept) {
+    if (!ctx) return Fail(PIMC_ERR_INVALID, "null context");
+    if (s < 0 || s >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
+    if (n_level < 1 || (1 << n_level) > kMaxBisectBeads || (1 << n_level) > ctx->M)
+        return Fail(PIMC_ERR_INVALID, "n_level must satisfy 2 <= 2^n_level <= min(32, n_bead)");
+    if (n_attempts < 0) return Fail(PIMC_ERR_INVALID, "negative attempt count");
+    if (!(epsilon > 0.)) return Fail(PIMC_ERR_INVALID, "epsilon must be positive");
+    // a cycle relabels every slice after the window up to the seam: one decision for all shards of a path
+    if (ctx->sharded) return Fail(PIMC_ERR_UNSUPPORTED, "permuting bisection on a slice-sharded context");
+    SpeciesState &st = *ctx->species[s];
+    if (!(st.lambda > 0.)) return Fail(PIMC_ERR_INVALID, "bisection of a species with lambda = 0");
+    for (auto &sp : ctx->species)
+        if (sp->n_prop > 0) return Fail(PIMC_ERR_INVALID, "a proposal is pending: call pimc_commit first");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = EnsurePermutation(ctx, s)) != PIMC_OK) return rc;
+    const int C = ctx->C, nb = 1 << n_level, n_prop = nb - 1, n_k = ctx->n_k(), N = st.N;
+    // move_class.h:27-31: the actions that involve this species (the kinetic action rides on the Levy construction)
+    std::vector<pimc_action *> acts;
+    bool any_lr = false;
+    for (pimc_action *a : ctx->actions) {
+        if (a->sa != s && a->sb != s) continue;
+        if (a->is_constant || a->atype == ATYPE_KINETIC) continue;
+        acts.push_back(a);
+        any_lr = any_lr || (a->use_long_range && n_k > 0);
+    }
+    const int n_acts = (int)acts.size();
+    if (st.P.n < (size_t)kMaxPropSlots * C * n_prop * 3) PIMC_CUDA(st.P.Alloc((size_t)kMaxPropSlots * C * n_prop * 3));
+    if (st.P_particle.n < (size_t)kMaxPropSlots * C) PIMC_CUDA(st.P_particle.Alloc((size_t)kMaxPropSlots * C));
+    if (st.P_first.n < (size_t)kMaxPropSlots * C) PIMC_CUDA(st.P_first.Alloc((size_t)kMaxPropSlots * C));
+    if (ctx->mc_f64.n < (size_t)6 * C) PIMC_CUDA(ctx->mc_f64.Alloc((size_t)6 * C));
+    if (ctx->mc_i32.n < (size_t)3 * C) PIMC_CUDA(ctx->mc_i32.Alloc((size_t)3 * C));
+    if (ctx->mc_naccept.n < (size_t)C) PIMC_CUDA(ctx->mc_naccept.Alloc(C));
+    if (ctx->perm_i32.n < (size_t)C * (2 + kPermMaxLen)) PIMC_CUDA(ctx->perm_i32.Alloc((size_t)C * (2 + kPermMaxLen)));
+    const size_t n_f64 = (size_t)3 * C + (size_t)std::max(n_acts, 1) * 2 * C * nb;
+    if (ctx->perm_f64.n < n_f64) PIMC_CUDA(ctx->perm_f64.Alloc(n_f64));
+    if (ctx->perm_stage.n < (size_t)C * kPermMaxLen * 3 * ctx->M) PIMC_CUDA(ctx->perm_stage.Alloc((size_t)C * kPermMaxLen * 3 * ctx->M));
+    if (ctx->perm_counts.n < (size_t)2 * C * kPermMaxLen) PIMC_CUDA(ctx->perm_counts.Alloc((size_t)2 * C * kPermMaxLen));
+    PIMC_CUDA(cudaMemsetAsync(ctx->mc_naccept.p, 0, C * sizeof(long long), ctx->stream));
+    PIMC_CUDA(cudaMemsetAsync(ctx->perm_counts.p, 0, (size_t)2 * C * kPermMaxLen * sizeof(long long), ctx->stream));
+    if (any_lr) {
+        const size_t need = (size_t)C * nb * n_k;
+        if (st.drho.n < need) PIMC_CUDA(st.drho.Alloc(need));
+    }
+    double *partial = ctx->mc_f64.p, *logu0 = partial + C;
+    int32_t *alive = ctx->mc_i32.p, *b0 = alive + C, *accept = b0 + C;
+    int32_t *d_n_perm = ctx->perm_i32.p, *d_steps = d_n_perm + C, *d_part = d_steps + C;
+    double *weight = ctx->perm_f64.p, *lr_old = weight + C, *lr_new = lr_old + C, *pair_parts = lr_new + C;
+    long long *cnt_attempt = ctx->perm_counts.p, *cnt_accept = cnt_attempt + (size_t)C * kPermMaxLen;
+    FreeSet *fs_move = nullptr, *fs_kin = nullptr;
+    if ((rc = GetFreeSet(ctx, s, st.move_images, &fs_move)) != PIMC_OK) return rc;
+    if ((rc = GetFreeSet(ctx, s, st.kinetic ? st.kinetic->n_images : 0, &fs_kin)) != PIMC_OK) return rc;
+    if ((fs_move->view.n_images || fs_kin->view.n_images) && n_level + 1 > kMaxFreeSplines)
+        return Fail(PIMC_ERR_UNSUPPORTED, "n_level too large for the tabulated free-particle splines");
+    const PathView pv = ctx->View();
+    const size_t select_smem = (size_t)2 * N * sizeof(double);
+    if (select_smem > (size_t)ctx->smem_optin) return Fail(PIMC_ERR_UNSUPPORTED, "too many particles for the permutation-table row in shared memory");
+    if (select_smem > 48 * 1024) PIMC_CUDA(cudaFuncSetAttribute(perm_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)select_smem));
+    st.R2_valid = false;
+    const int tl = 2 * ctx->max_index + 1;
+    for (int it = 0; it < n_attempts; ++it) {
+        const uint64_t attempt = attempt0 + (uint64_t)it;
+        PermSelectArgs sel;
+        sel.pv = pv;
+        sel.R = st.R.p;
+        sel.N = N;
+        sel.next = st.perm_next.p;
+        sel.n_bisect_beads = nb;
+        sel.i_4_lambda_tau_n = (1. / (4. * st.lambda * ctx->tau)) / nb;  // bisect_class.h:147-150, perm_bisect_iterative_class.h:16
+        sel.log_epsilon = std::log(epsilon);
+        sel.seed_lo = (uint32_t)seed;
+        sel.seed_hi = (uint32_t)(seed >> 32);
+        sel.attempt_lo = (uint32_t)attempt;
+        sel.attempt_hi = (uint32_t)(attempt >> 32);
+        sel.b0 = b0;
+        sel.n_perm = d_n_perm;
+        sel.particles = d_part;
+        sel.weight = weight;
+        sel.n_steps = d_steps;
+        perm_select_kernel<<<C, 32, select_smem, ctx->stream>>>(sel);
+        ctx->launches++;
+        PermSampleArgs sa;
+        sa.pv = pv;
+        sa.R = st.R.p;
+        sa.N = N;
+        sa.next = st.perm_next.p;
+        sa.lambda = st.lambda;
+        sa.tau = ctx->tau;
+        sa.n_level = n_level;
+        sa.with_kinetic = with_kinetic ? 1 : 0;
+        sa.fs_move = fs_move->view;
+        sa.fs_kin = fs_kin->view;
+        sa.seed_lo = sel.seed_lo;
+        sa.seed_hi = sel.seed_hi;
+        sa.attempt_lo = sel.attempt_lo;
+        sa.attempt_hi = sel.attempt_hi;
+        sa.b0 = b0;
+        sa.n_perm = d_n_perm;
+        sa.particles = d_part;
+        sa.weight = weight;
+        sa.P = st.P.p;
+        sa.P_particle = st.P_particle.p;
+        sa.P_first = st.P_first.p;
+        sa.partial = partial;
+        sa.logu0 = logu0;
+        sa.alive = alive;
+        sa.perm_attempt = cnt_attempt;
+        perm_sample_kernel<<<C, 32, 0, ctx->stream>>>(sa);
+        ctx->launches++;
+        // the moved species' view with the label windows as its pending proposal
+        SpeciesView sv_new = ctx->SView(s, false);
+        sv_new.n_prop = n_prop;
+        sv_new.n_slots = kMaxPropSlots;
+        for (int t = 0; t < n_acts; ++t) {
+            pimc_action *a = acts[t];
+            for (int mode = 0; mode < 2; ++mode) {
+                PairWindowArgs w;
+                w.pv = pv;
+                w.A = (a->sa == s && mode) ? sv_new : ctx->SView(a->sa, false);
+                w.B = (a->sb == s && mode) ? sv_new : ctx->SView(a->sb, false);
+                w.same = a->sa == a->sb;
+                w.n_a = a->sa == s ? kMaxPropSlots : 0;
+                w.n_b = (a->sa != s && a->sb == s) ? kMaxPropSlots : 0;
+                w.part_a = st.P_particle.p;
+                w.part_b = st.P_particle.p;
+                w.b0 = b0;
+                w.n_links = nb;
+                w.mode = mode;
+                w.T = a->table[WHICH_U];
+                w.blob = a->blob[WHICH_U].p;
+                w.partial = pair_parts + ((size_t)(2 * t + mode) * C) * nb;
+                w.alive = alive;
+                const int grid = (int)std::min<size_t>((size_t)C * nb, (size_t)ctx->n_sm * 16);
+                {
+                    ScopedKernelTimer tm(ctx, PIMC_KERNEL_PAIR_WINDOW);
+                    switch (a->atype) {
+                        case ATYPE_ILKKA: pair_window_kernel<ATYPE_ILKKA><<<grid, 128, 0, ctx->stream>>>(w); break;
+                        case ATYPE_BARE: pair_window_kernel<ATYPE_BARE><<<grid, 128, 0, ctx->stream>>>(w); break;
+                        default: pair_window_kernel<ATYPE_DAVID><<<grid, 128, 0, ctx->stream>>>(w); break;
+                    }
+                }
+                ctx->launches++;
+            }
+        }
+        if (any_lr) {
+            // Species::UpdateRhoK for every listed label (species_class.h:406-425), then CalcULong over the window
+            // in OLD and NEW mode for every long-range action of the species (ilkka_pair_action_class.h:104-122)
+            rhok_delta_kernel<<<GridFor(ctx, C * nb), 256, (size_t)6 * tl * sizeof(double2), ctx->stream>>>(pv, sv_new, ctx->KView(), b0, nb, st.drho.p);
+            ctx->launches++;
+            PIMC_CUDA(cudaMemsetAsync(lr_old, 0, (size_t)2 * C * sizeof(double), ctx->stream));
+            for (pimc_action *a : acts) {
+                if (!a->use_long_range) continue;
+                for (int mode = 0; mode < 2; ++mode) {
+                    KSumArgs k;
+                    k.pv = pv;
+                    k.n_k = n_k;
+                    k.rho_a = ctx->species[a->sa]->rho.p;
+                    k.rho_b = ctx->species[a->sb]->rho.p;
+                    k.drho_a = (mode && a->sa == s) ? st.drho.p : nullptr;
+                    k.drho_b = (mode && a->sb == s) ? st.drho.p : nullptr;
+                    k.wk = a->wk[WHICH_U].p;
+                    k.b0 = b0;
+                    k.n_window = nb;
+                    k.twice = a->sa != a->sb;
+                    k.scale = a->ulong_scale;
+                    k.accumulate = 1;
+                    k.out = mode ? lr_new : lr_old;
+                    ScopedKernelTimer tm(ctx, PIMC_KERNEL_KSUM);
+                    ksum_kernel<<<C, 256, 0, ctx->stream>>>(k);
+                    ctx->launches++;
+                }
+            }
+        }
+        PermDecideArgs d;
+        d.pv = pv;
+        d.N = N;
+        d.n_k = n_k;
+        d.nb = nb;
+        d.alive = alive;
+        d.partial = partial;
+        d.logu0 = logu0;
+        d.pair_parts = pair_parts;
+        d.n_pair_actions = n_acts;
+        d.lr_old = any_lr ? lr_old : nullptr;
+        d.lr_new = any_lr ? lr_new : nullptr;
+        d.P = st.P.p;
+        d.P_particle = st.P_particle.p;
+        d.b0 = b0;
+        d.drho = any_lr ? st.drho.p : nullptr;
+        d.R = st.R.p;
+        d.rho = st.rho.p;
+        d.n_perm = d_n_perm;
+        d.accept = accept;
+        d.n_accept = ctx->mc_naccept.p;
+        d.perm_accept = cnt_accept;
+        perm_decide_commit_kernel<<<C, 256, 0, ctx->stream>>>(d);
+        ctx->launches++;
+        PermApplyArgs ap;
+        ap.pv = pv;
+        ap.R = st.R.p;
+        ap.N = N;
+        ap.next = st.perm_next.p;
+        ap.b0 = b0;
+        ap.n_bisect_beads = nb;
+        ap.accept = accept;
+        ap.n_perm = d_n_perm;
+        ap.particles = d_part;
+        ap.scratch = ctx->perm_stage.p;
+        perm_apply_kernel<<<C, 256, 0, ctx->stream>>>(ap);
+        ctx->launches++;
+    }
+    PIMC_CUDA(cudaGetLastError());
+    st.n_prop = 0;
+    st.n_slots = 0;
+    st.drho_valid = false;
+    for (auto &sp : ctx->species) sp->need_update_rho_k = true;
+    if (n_accept || perm_attempt || perm_accept) {
+        std::vector<long long> h(C), hc((size_t)2 * C * kPermMaxLen);
+        PIMC_CUDA(cudaMemcpyAsync(h.data(), ctx->mc_naccept.p, C * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        PIMC_CUDA(cudaMemcpyAsync(hc.data(), ctx->perm_counts.p, hc.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        PIMC_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int c = 0; c < C; ++c) {
+            if (n_accept) n_accept[c] += (int64_t)h[c];
+            for (int i = 0; i < kPermMaxLen; ++i) {
+                if (perm_attempt) perm_attempt[(size_t)c * kPermMaxLen + i] += (int64_t)hc[(size_t)c * kPermMaxLen + i];
+                if (perm_accept) perm_accept[(size_t)c * kPermMaxLen + i] += (int64_t)hc[((size_t)C + c) * kPermMaxLen + i];
+            }
+        }
+    }
+    return PIMC_OK;
+}
+
 int pimc_displace_sweep(pimc_ctx *ctx, int32_t s, double step_size, int32_t n_attempts, uint64_t seed, uint64_t attempt0, int64_t *n_accept) {
     if (!ctx) return Fail(PIMC_ERR_INVALID, "null context");
     if (s < 0 || s >= (int)ctx->species.size()) return Fail(PIMC_ERR_INVALID, "species index out of range");
@@ -2481,6 +2817,10 @@ int pimc_displace_sweep(pimc_ctx *ctx, int32_t s, double step_size, int32_t n_at
     for (auto &sp : ctx->species)
         if (sp->n_prop > 0) return Fail(PIMC_ERR_INVALID, "a proposal is pending: call pimc_commit first");
     PIMC_CUDA(cudaSetDevice(ctx->device));
+    {
+        const int rc_p = RequireUnpermuted(ctx, s, "pimc_displace_sweep");
+        if (rc_p != PIMC_OK) return rc_p;
+    }
     SpeciesState &st = *ctx->species[s];
     const int C = ctx->C, M = ctx->M, n_k = ctx->n_k();
     if (ctx->mc_f64.n < (size_t)6 * C) PIMC_CUDA(ctx->mc_f64.Alloc((size_t)6 * C));

@@ -39,7 +39,7 @@ struct SpeciesView {
     int n_slots;                // proposals pending (0 with n_prop > 0 is read as 1)
 };
 
-constexpr int kMaxPropSlots = 4;
+constexpr int kMaxPropSlots = 16;  // members of a permutation cycle (<= 8) plus, when the window rolls over the seam, their end points' labels
 
 struct PathView {
     int C;        // clones
@@ -432,8 +432,10 @@ __global__ void __launch_bounds__(256) rhok_delta_kernel(PathView pv, SpeciesVie
     for (int item = blockIdx.x; item < pv.C * n_window; item += gridDim.x) {
         const int c = item / n_window, j = item - c * n_window;
         const int bg = b0[c] + j;
+        bool wrote = false;
         for (int sl = 0; sl < ns; ++sl) {
             const int p = sv.P_particle[(size_t)sl * pv.C + c];
+            if (p < 0) continue;  // unused slot (uniform over the CTA)
             __syncthreads();
             if (tid < 6) {
                 const int mode = tid / 3, d = tid - mode * 3;
@@ -449,13 +451,16 @@ __global__ void __launch_bounds__(256) rhok_delta_kernel(PathView pv, SpeciesVie
                 const double2 fn = CMul(CMul(tn[i0], tn[tl + i1]), tn[2 * tl + i2]);
                 double2 *dst = drho + ((size_t)c * n_window + j) * ks.n_k + k;
                 double2 v = make_double2(fn.x - fo.x, fn.y - fo.y);
-                if (sl > 0) {  // same thread wrote this element for the previous slot
+                if (wrote) {  // same thread wrote this element for the previous slot
                     v.x += dst->x;
                     v.y += dst->y;
                 }
                 *dst = v;
             }
+            wrote = true;
         }
+        if (!wrote)
+            for (int k = tid; k < ks.n_k; k += blockDim.x) drho[((size_t)c * n_window + j) * ks.n_k + k] = make_double2(0., 0.);
     }
 }
 
@@ -555,6 +560,7 @@ struct PairWindowArgs {
     PairTable T;
     const double *blob;
     double *partial;            // [C][n_links]
+    const int32_t *alive = nullptr;  // [C] (optional): clones whose flag is 0 are skipped, their partial sums left untouched
 };
 
 /// One CTA per (clone, link): all pairs that touch a listed particle (PairAction::
@@ -567,7 +573,9 @@ __global__ void __launch_bounds__(128) pair_window_kernel(const PairWindowArgs a
     const PathView &pv = a.pv;
     for (int item = blockIdx.x; item < pv.C * a.n_links; item += gridDim.x) {
         const int c = item / a.n_links, j = item - c * a.n_links;
+        if (a.alive && !a.alive[c]) continue;  // uniform over the CTA
         const int bg = a.b0[c] + j;
+        // a negative entry is an unused slot (the device-resident permutation move lists a different number of labels per clone)
         int la[kMaxPropSlots], lb[kMaxPropSlots];
         for (int i = 0; i < a.n_a; ++i) la[i] = a.part_a[(size_t)i * pv.C + c];
         for (int i = 0; i < a.n_b; ++i) lb[i] = a.part_b[(size_t)i * pv.C + c];
@@ -575,6 +583,7 @@ __global__ void __launch_bounds__(128) pair_window_kernel(const PairWindowArgs a
         // pairs (listed a, partner of species b)
         for (int i = 0; i < a.n_a; ++i) {
             const int m = la[i];
+            if (m < 0) continue;
             double m0[3], m1[3];
             LoadPos(pv, a.A, c, m, bg, a.mode, m0);
             LoadPos(pv, a.A, c, m, bg + 1, a.mode, m1);
@@ -599,6 +608,7 @@ __global__ void __launch_bounds__(128) pair_window_kernel(const PairWindowArgs a
         if (!a.same) {
             for (int i = 0; i < a.n_b; ++i) {
                 const int m = lb[i];
+                if (m < 0) continue;
                 double m0[3], m1[3];
                 LoadPos(pv, a.B, c, m, bg, a.mode, m0);
                 LoadPos(pv, a.B, c, m, bg + 1, a.mode, m1);

@@ -64,6 +64,7 @@ struct KineticFullArgs {
     FreeSplineTab dtau;   // d_image_action_d_tau of tau (rho_free_splines[0], kinetic_class.h:20)
     int n_chunks;         // chunks of 32 links
     double *partial;      // [C][n_chunks]
+    const int32_t *next = nullptr;  // [C][N] permutation at the beta seam (nullptr: identity): the bead after (p, M - 1) is (next[p], 0)
 };
 
 /// sum over particles and links (b, b + 1) of GetDLogRhoFreeDTau(Dr(bead, next)) (kinetic_class.h:38-43);
@@ -78,11 +79,13 @@ __global__ void __launch_bounds__(256) kinetic_dbeta_kernel(const KineticFullArg
         double acc = 0.;
         if (b < pv.Mloc) {
             const int bn = NextSlice(pv, b);
+            const bool seam = a.next && !pv.sharded && b + 1 == pv.M;
             for (int p = warp; p < a.sv.N; p += 256 / 32) {
+                const int pn = seam ? a.next[(size_t)c * a.sv.N + p] : p;
                 double dr[3];
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
-                    const double x = a.sv.R[PosIndex(pv, a.sv.N, c, p, d, b)] - a.sv.R[PosIndex(pv, a.sv.N, c, p, d, bn)];
+                    const double x = a.sv.R[PosIndex(pv, a.sv.N, c, p, d, b)] - a.sv.R[PosIndex(pv, a.sv.N, c, pn, d, bn)];
                     dr[d] = pv.box.L > 0. ? x - rint(x * pv.box.iL) * pv.box.L : x;   // Path::Dr (path_class.h:108-112)
                 }
                 acc += FreeLogRho(a.dtau, dr);

@@ -179,6 +179,35 @@ class Path:
         capi.check(self.L.pimc_perm_table(self.h, species, _vp(b0), n_bisect_beads, float(epsilon), 1 if relative else 0, _vp(t)))
         return t
 
+    def PermBisectSweep(self, species, n_level, n_attempts, seed, attempt0=0, with_kinetic=True, epsilon=1e-100):
+        """n_attempts device-resident PermBisectIterative::DoEvent calls per clone (perm_bisect_iterative_class.h:113-222).
+        Returns (accepts per clone, perm_attempt[clone][8], perm_accept[clone][8]) -- the last two by cycle length - 1."""
+        n_accept = np.zeros(self.n_clones, dtype=np.int64)
+        att = np.zeros((self.n_clones, 8), dtype=np.int64)
+        acc = np.zeros((self.n_clones, 8), dtype=np.int64)
+        capi.check(self.L.pimc_perm_bisect_sweep(self.h, species, n_level, n_attempts, seed, attempt0, 1 if with_kinetic else 0,
+                                                 float(epsilon), _vp(n_accept), _vp(att), _vp(acc)))
+        return n_accept, att, acc
+
+    def GetPermutation(self, species):
+        """next[clone][p]: label of the bead that follows (p, n_bead - 1) -- the permutation at the beta seam."""
+        nxt = np.zeros((self.n_clones, self.cfg.species[species].n_part), dtype=np.int32)
+        capi.check(self.L.pimc_permutation_get(self.h, species, _vp(nxt)))
+        return nxt
+
+    def SetPermutation(self, species, nxt):
+        nxt = np.ascontiguousarray(np.broadcast_to(nxt, (self.n_clones, self.cfg.species[species].n_part)), dtype=np.int32)
+        capi.check(self.L.pimc_permutation_set(self.h, species, _vp(nxt)))
+
+    def PermLastCycle(self):
+        """Cycle of the last PermBisectSweep attempt per clone: dict(b0, n_perm, particles[clone][8], n_steps, accept)."""
+        Cn = self.n_clones
+        out = {k: np.zeros(Cn, dtype=np.int32) for k in ("b0", "n_perm", "n_steps", "accept")}
+        out["particles"] = np.zeros((Cn, 8), dtype=np.int32)
+        capi.check(self.L.pimc_perm_last_cycle(self.h, _vp(out["b0"]), _vp(out["n_perm"]), _vp(out["particles"]), _vp(out["n_steps"]),
+                                               _vp(out["accept"])))
+        return out
+
     def LaunchCount(self):
         return int(self.L.pimc_ctx_launch_count(self.h))
 
@@ -562,13 +591,22 @@ class PathDump:
     (species_class.h:336-378): every Write() appends each species' positions -- the reference's
     cube (n_d, n_bead, n_part) is [n_part][n_bead][n_d] in file order, the order used here, with a
     leading clone axis -- and the permutation table (previous particle of bead 0, next particle
-    of the last bead: the identity here, permutation moves are not on this path).  The container
-    is a flat .npz with the reference's dataset names as keys (no HDF5 library in this build)."""
+    of the last bead: the context's permutation at the beta seam, Path.GetPermutation).  The container
+    is a flat .npz with the reference's dataset names as keys, or the reference's HDF5 layout through IO."""
 
     def __init__(self, path, name="path_dump", skip=1):
         self.path, self.name, self.skip = path, name, max(1, int(skip))
         self.n_dump, self.n_write_calls = 0, 0
         self.positions = {s.name: [] for s in path.cfg.species}
+        self.permutations = {s.name: [] for s in path.cfg.species}
+
+    @staticmethod
+    def _perm_table(nxt):
+        """[clone][n_part][2]: (particle of the bead before (p, 0), particle of the bead after (p, n_bead - 1))."""
+        prev = np.empty_like(nxt)
+        for c in range(nxt.shape[0]):
+            prev[c, nxt[c]] = np.arange(nxt.shape[1])
+        return np.stack([prev, nxt], axis=-1).astype(np.float64)
 
     def Write(self, out=None):
         """path_dump_class.h:29-68.  With `out` (an IO) the dump is appended to the reference's datasets
@@ -577,11 +615,11 @@ class PathDump:
             self.n_dump += 1
             for si, s in enumerate(self.path.cfg.species):
                 R = self.path.GetPositions(si)
+                perm = self._perm_table(self.path.GetPermutation(si))
                 self.positions[s.name].append(R)
+                self.permutations[s.name].append(perm)
                 if out is not None:
                     prefix = "Observables/%s/%s/" % (self.name, s.name)
-                    ident = np.arange(s.n_part, dtype=np.float64)
-                    perm = np.tile(np.stack([ident, ident]).T, (self.path.n_clones, 1, 1))
                     put = out.CreateExtendableDataSet if self.n_dump == 1 else out.AppendDataSet
                     out.Write(prefix + "n_dump", np.uint32(self.n_dump))
                     put(prefix, "positions", R)
@@ -594,8 +632,8 @@ class PathDump:
             key = "Observables/%s/%s/" % (self.name, s.name)
             out[key + "n_dump"] = np.int64(self.n_dump)
             out[key + "positions"] = np.stack(self.positions[s.name]) if self.positions[s.name] else np.zeros((0,))
-            ident = np.arange(s.n_part, dtype=np.float64)
-            out[key + "permutation"] = np.tile(np.stack([ident, ident]).T, (self.n_dump, 1, 1))   # [dump][n_part][2]
+            out[key + "permutation"] = (np.stack(self.permutations[s.name]) if self.permutations[s.name]
+                                        else np.zeros((0,)))                                  # [dump][clone][n_part][2]
         np.savez_compressed(file_name, **out)
 
     @staticmethod
@@ -610,16 +648,24 @@ class PathDump:
             dumps = [h5lite.read(fn) for fn in files]
             for si, s in enumerate(path.cfg.species):
                 key = "Observables/%s/%s/" % (name, s.name)
-                for d in dumps:
-                    perm = d[key + "permutation"][-1]
-                    if not (np.array_equal(perm[:, 0], np.arange(s.n_part)) and np.array_equal(perm[:, 1], np.arange(s.n_part))):
-                        raise ValueError("ERROR: permuted paths are not supported on this path")
                 path.SetPositions(si, np.stack([d[key + "positions"][-1] for d in dumps]))
+                PathDump._restore_permutation(path, si, np.stack([d[key + "permutation"][-1] for d in dumps]))
             return
         f = np.load(file_name)
         for si, s in enumerate(path.cfg.species):
             key = "Observables/%s/%s/" % (name, s.name)
-            perm = f[key + "permutation"][-1]
-            if not (np.array_equal(perm[:, 0], np.arange(s.n_part)) and np.array_equal(perm[:, 1], np.arange(s.n_part))):
-                raise ValueError("ERROR: permuted paths are not supported on this path")
             path.SetPositions(si, f[key + "positions"][-1])
+            PathDump._restore_permutation(path, si, f[key + "permutation"][-1])
+
+    @staticmethod
+    def _restore_permutation(path, si, perm):
+        """species_class.h:368-377: column 1 is the particle that follows each particle's last bead (column 0 its inverse).
+        perm: [clone][n_part][2] or, from files written before permutations were tracked, [n_part][2]."""
+        perm = np.asarray(perm)
+        if perm.ndim == 2:
+            perm = np.broadcast_to(perm, (path.n_clones,) + perm.shape)
+        nxt = np.rint(perm[..., 1]).astype(np.int32)
+        n_part = nxt.shape[-1]
+        if np.array_equal(nxt, np.broadcast_to(np.arange(n_part, dtype=np.int32), nxt.shape)):
+            return      # unpermuted: leave the context untracked (every move stays available)
+        path.SetPermutation(si, nxt)

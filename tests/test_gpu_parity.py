@@ -589,9 +589,9 @@ def test_get_action_with_several_listed_particles(name):
                 assert np.array_equal(got[c], o.get_positions(sp, 0)), (name, trial, "positions after commit", sp, c)
                 if path._n_k():
                     assert np.max(np.abs(path.GetRhoK(sp, c, host.OLD_MODE) - o.rhok(sp, 0))) <= 1e-11 * cfg.species[sp].n_part
-    # five listed particles of one species: refused loudly
+    # seventeen listed particles of one species (more than the proposal slots): refused loudly
     with pytest.raises(RuntimeError):
-        path.actions[0].GetAction(0, 2, [(0, i) for i in range(5)], 0)
+        path.actions[0].GetAction(0, 2, [(0, i) for i in range(17)], 0)
     path.close()
     for o in oracles:
         o.close()
