@@ -340,6 +340,28 @@ def run_ours(args):
     displace = {"ms_per_attempt": 1e3 * float(td.item()) / n_disp, "attempts_timed": n_disp, "accept_ratio": float(n_acc_d.sum()) / (C * n_disp),
                 "pair_evals_per_s": world * C * n_disp * 2 * (N_PART - 1) * N_SLICE / float(td.item()),
                 "driver": "device-resident pimc_displace_sweep (step L/10; pair + long-range deltas over all slices, Metropolis, commit)"}
+    # device-resident permuting bisection (PermBisectIterative::DoEvent: cycle selection from the permutation table,
+    # the members' Levy bridges, pair + long-range deltas over the listed labels, Metropolis, relabelling)
+    n_pb = max(1, min(16, n_att))
+    path.PermBisectSweep(0, BISECT_LEVEL, 2, 777 + rank, attempt0=0)
+    barrier()
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches_pb0 = path.LaunchCount()
+    q0.record(stream)
+    n_acc_p, att_len, acc_len = path.PermBisectSweep(0, BISECT_LEVEL, n_pb, 777 + rank, attempt0=2)
+    q1.record(stream)
+    q1.synchronize()
+    barrier()
+    tp = torch.tensor([q0.elapsed_time(q1) * 1e-3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+    displace["perm_bisect"] = {"ms_per_attempt": 1e3 * float(tp.item()) / n_pb, "attempts_timed": n_pb, "launches": int(path.LaunchCount() - launches_pb0),
+                               "accept_ratio": float(n_acc_p.sum()) / (C * n_pb),
+                               "cycles_attempted_by_length": [int(x) for x in att_len.sum(axis=0)], "cycles_accepted_by_length": [int(x) for x in acc_len.sum(axis=0)],
+                               "driver": "device-resident pimc_perm_bisect_sweep (kernel-per-phase: select, sample, pair OLD / NEW, long range, decide + commit, relabel)"}
+    # back to the unpermuted walkers for what follows
+    path.SetPermutation(0, np.arange(N_PART, dtype=np.int32))
+    path.SetPositions(0, R)
     # the same move driven from the host through propose / GetAction(OLD, NEW) / commit (the
     # reference-shaped call sequence), a few attempts for comparison
     rng = np.random.default_rng(1234 + rank)
@@ -456,7 +478,8 @@ def run_ours(args):
                    "ms_per_attempt": 1e3 * float(ts.item()) / n_att, "launches": int(launches_mc),
                    "pair_window_kernel_ms_per_attempt": k4_ms / max(1, n_att),
                    "driver": "device-resident pimc_bisect_sweep (Philox stream; kinetic + Ilkka pair + long-range deltas, Metropolis, commit)",
-                   "host_driven_sweeps_per_s_per_gpu": host_driven_sweeps_per_s, "displace": displace},
+                   "host_driven_sweeps_per_s_per_gpu": host_driven_sweeps_per_s, "displace": {k: v for k, v in displace.items() if k != "perm_bisect"},
+                   "perm_bisect": displace["perm_bisect"]},
             "estimators": estimators,
             "roofline": roofline}
     if families:
