@@ -678,6 +678,19 @@ int BuildFastIlkka(pimc_ctx *ctx, pimc_action *a, int which, const pimc_table_2d
         kb.Build(f.r, f.n);
         std::vector<double> coefs(f.n + 3, 0.0);
         SolveNatural(kb, f.f, 1, coefs.data(), 1);
+#if PIMC_LR2
+        // bucket-centred form (pair_fast.cuh: FastLR2): the buckets of the interval table carry the pieces themselves
+        LR2Host l2;
+        if (!BuildLR2(f.r, f.n, kb, coefs.data(), kMaxKeys, l2)) return PIMC_OK;
+        T.lr2.h = l2.h;
+        T.lr2.inv_h16 = l2.inv_h16;
+        T.lr2.off_c01 = blob.Reserve(l2.c01.size() * sizeof(double));
+        std::memcpy(blob.At<double>(T.lr2.off_c01), l2.c01.data(), l2.c01.size() * sizeof(double));
+        T.lr2.off_c23 = blob.Reserve(l2.c23.size() * sizeof(double));
+        std::memcpy(blob.At<double>(T.lr2.off_c23), l2.c23.data(), l2.c23.size() * sizeof(double));
+        T.lr2.off_knot = blob.Reserve(l2.knot.size() * sizeof(uint16_t));
+        std::memcpy(blob.At<uint16_t>(T.lr2.off_knot), l2.knot.data(), l2.knot.size() * sizeof(uint16_t));
+#else
         const std::vector<double> pp = PPFrom1D(kb, coefs.data());
         T.lr.off_gpair = AppendKnotPairs(blob, f.r, f.n);
         T.lr.off_c01 = blob.Reserve((size_t)f.n * 16);
@@ -689,6 +702,7 @@ int BuildFastIlkka(pimc_ctx *ctx, pimc_action *a, int which, const pimc_table_2d
             blob.At<double>(T.lr.off_c23)[2 * i + 1] = pp[4 * (size_t)i + 3];
         }
         AppendULut(blob, T.lr.lut, ll);
+#endif
         T.lr.r_min = f.r[0];
         T.lr.r_max = f.r[f.n - 1];
     }

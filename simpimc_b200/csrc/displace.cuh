@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kDispThreads, 1) displace_pair_kernel(const Di
         auto flush_ring = [&]() {
             __syncwarp();
             double v = 0.;
-            if ((lane & 15) < n_parked) v = -0.5 * FastPP1Eval(tb, a.FT.lr, Clamp(ring[warp][lane], a.FT.lr.r_min, a.FT.lr.r_max));
+            if ((lane & 15) < n_parked) v = -0.5 * FastLrEval(tb, a.FT, Clamp(ring[warp][lane], a.FT.lr.r_min, a.FT.lr.r_max));
             __syncwarp();
             if (lane < 16)
                 acc_old += v;

@@ -37,6 +37,10 @@
 #ifndef PIMC_K1_UNROLL
 #define PIMC_K1_UNROLL 1
 #endif
+// 1: the long-range r-space spline of the fast Ilkka tables in bucket-centred form (FastLR2); 0: interval form (FastPP1)
+#ifndef PIMC_LR2
+#define PIMC_LR2 1
+#endif
 
 namespace pimc {
 
@@ -66,9 +70,26 @@ struct FastPP2 {
     int ny;             // cells per row of the global array
     const double *cells_global;  // [nx][ny][16]
 };
+/// Long-range r-space spline in BUCKET-CENTRED form (PIMC_LR2): the interval table's uniform buckets
+/// [(k - 1/2) h, (k + 1/2) h) -- h below the smallest knot spacing, so at most one knot per bucket -- carry the
+/// polynomial themselves.  Record k is the cubic piece that holds the bucket's lower edge, re-expanded (long double)
+/// about the bucket centre k h; knot[k] is the position of the bucket's knot in 1/65536 of h from its lower edge
+/// (0xFFFF: none).  x at or above the knot belongs to the piece that holds the NEXT bucket's lower edge: record k + 1,
+/// evaluated at the negative offset x - (k + 1) h.  One small load decides, then the two coefficient loads go out
+/// together: the knot-pair load of the interval form (one of three 16-byte gathers at ~8.7 wavefronts each, 32 lanes in
+/// 32 unrelated intervals) and one level of the dependent chain are gone.  The compare is made on a 16-bit fraction
+/// of the bucket: within h / 65536 of a knot either neighbouring piece may be taken, and there the two cubics differ by
+/// (jump of the third derivative) * (h / 65536)^3 / 6 -- a natural spline is C2 -- far below one ulp of the value.
+struct FastLR2 {
+    int off_knot;        // uint16 [n_keys]
+    int off_c01, off_c23;  // double2 [n_keys + 1]
+    double inv_h16;      // 65536 / h
+    double h;
+};
 struct FastTable {
     FastPP2 xy;
-    FastPP1 lr;
+    FastPP1 lr;       // interval form (r_min / r_max always; the arrays only without PIMC_LR2)
+    FastLR2 lr2;
     int use_lr;
     int n_bytes;  // size of the staged block
 };
@@ -163,6 +184,24 @@ __device__ __forceinline__ double FastPP1Eval(const Tab &tb, const FastPP1 &d, d
     return fma(fma(fma(c23.y, t, c23.x), t, c01.y), t, c01.x);
 }
 
+/// u_long(x) of a fast Ilkka table; x must already lie inside [r_min, r_max] (SetLimits).
+template <class Tab>
+__device__ __forceinline__ double FastLrEval(const Tab &tb, const FastTable &T, double x) {
+#if PIMC_LR2
+    // low word of fma(x, 65536 / h, 2^52 + 2^51) = rint(65536 x / h): bucket (nearest) in the high half, position in it below
+    const int k32 = __double2loint(fma(x, T.lr2.inv_h16, kRoundMagic)) + 0x8000;
+    const int key = k32 >> 16;
+    const int knot = tb.LdU16(T.lr2.off_knot + 2 * key);
+    const int rec = key + ((k32 & 0xFFFF) >= knot ? 1 : 0);
+    const double t = fma(-(double)rec, T.lr2.h, x);
+    const double2 c01 = tb.LdV2(T.lr2.off_c01 + 16 * rec);
+    const double2 c23 = tb.LdV2(T.lr2.off_c23 + 16 * rec);
+    return fma(fma(fma(c23.y, t, c23.x), t, c01.y), t, c01.x);
+#else
+    return FastPP1Eval(tb, T.lr, x);
+#endif
+}
+
 template <class Tab>
 __device__ __forceinline__ double FastPP2Eval(const Tab &tb, const FastPP2 &d, double x, double y) {
     int ix, iy;
@@ -238,8 +277,8 @@ __device__ __forceinline__ double FastIlkkaEval(const Tab &tb, const FastTable &
             r = Clamp(r, T.lr.r_min, T.lr.r_max);
             r_p = Clamp(r_p, T.lr.r_min, T.lr.r_max);
         }
-        u = fma(-0.5, FastPP1Eval(tb, T.lr, r), u);
-        u = fma(-0.5, FastPP1Eval(tb, T.lr, r_p), u);
+        u = fma(-0.5, FastLrEval(tb, T, r), u);
+        u = fma(-0.5, FastLrEval(tb, T, r_p), u);
     }
     return u;
 }
@@ -266,14 +305,14 @@ __device__ __forceinline__ double FastIlkkaEvalWarp(const Tab &tb, const FastTab
     const double y = fma(-0.5, s, q);
     double u = FastPP2Eval(tb, T.xy, x, y);
     if (T.use_lr) {
-        const double lr_r = FastPP1Eval(tb, T.lr, ClampRare(r, T.lr));
+        const double lr_r = FastLrEval(tb, T, ClampRare(r, T.lr));
         const double r_next = __shfl_down_sync(0xffffffffu, r, 1);
         double lr_p = __shfl_down_sync(0xffffffffu, lr_r, 1);
         if (lane == 31) {
             *ring_slot = r_p;
             lr_p = 0.;
         } else if (r_p != r_next) {
-            lr_p = FastPP1Eval(tb, T.lr, Clamp(r_p, T.lr.r_min, T.lr.r_max));
+            lr_p = FastLrEval(tb, T, Clamp(r_p, T.lr.r_min, T.lr.r_max));
         }
         u = fma(-0.5, lr_r, u);
         u = fma(-0.5, lr_p, u);
@@ -291,8 +330,8 @@ __device__ __forceinline__ void FastIlkkaEvalWarpBoth(const Tab &tb, const FastT
     un = FastPP2Eval(tb, T.xy, fma(0.5, sn, qn), fma(-0.5, sn, qn));
     if (T.use_lr) {
         const unsigned full = 0xffffffffu;
-        const double lro = FastPP1Eval(tb, T.lr, ClampRare(ro, T.lr));
-        const double lrn = FastPP1Eval(tb, T.lr, ClampRare(rn, T.lr));
+        const double lro = FastLrEval(tb, T, ClampRare(ro, T.lr));
+        const double lrn = FastLrEval(tb, T, ClampRare(rn, T.lr));
         const double ro_next = __shfl_down_sync(full, ro, 1), rn_next = __shfl_down_sync(full, rn, 1);
         double lpo = __shfl_down_sync(full, lro, 1), lpn = __shfl_down_sync(full, lrn, 1);
         if (lane == 31) {
@@ -301,8 +340,8 @@ __device__ __forceinline__ void FastIlkkaEvalWarpBoth(const Tab &tb, const FastT
             lpo = 0.;
             lpn = 0.;
         } else {
-            if (rpo != ro_next) lpo = FastPP1Eval(tb, T.lr, Clamp(rpo, T.lr.r_min, T.lr.r_max));
-            if (rpn != rn_next) lpn = FastPP1Eval(tb, T.lr, Clamp(rpn, T.lr.r_min, T.lr.r_max));
+            if (rpo != ro_next) lpo = FastLrEval(tb, T, Clamp(rpo, T.lr.r_min, T.lr.r_max));
+            if (rpn != rn_next) lpn = FastLrEval(tb, T, Clamp(rpn, T.lr.r_min, T.lr.r_max));
         }
         uo = fma(-0.5, lro, uo);
         uo = fma(-0.5, lpo, uo);
@@ -316,7 +355,7 @@ template <class Tab>
 __device__ __forceinline__ double LrRingFlush(const Tab &tb, const FastTable &T, const double *ring, int lane, int count) {
     __syncwarp();
     double v = 0.;
-    if (lane < count) v = -0.5 * FastPP1Eval(tb, T.lr, Clamp(ring[lane], T.lr.r_min, T.lr.r_max));
+    if (lane < count) v = -0.5 * FastLrEval(tb, T, Clamp(ring[lane], T.lr.r_min, T.lr.r_max));
     __syncwarp();
     return v;
 }
@@ -341,8 +380,8 @@ __device__ __forceinline__ void FastIlkkaEvalWindow(const Tab &tb, const FastTab
     if (T.use_lr) {
         const unsigned full = 0xffffffffu;
         const double r_end = __shfl_sync(full, rpo, lane | (nb - 1));  // bead nb as the group's last lane sees it
-        const double lrA = FastPP1Eval(tb, T.lr, ClampRare(ro, T.lr));
-        const double lrB = FastPP1Eval(tb, T.lr, ClampRare(j == 0 ? r_end : rn, T.lr));
+        const double lrA = FastLrEval(tb, T, ClampRare(ro, T.lr));
+        const double lrB = FastLrEval(tb, T, ClampRare(j == 0 ? r_end : rn, T.lr));
         const double lr_end = __shfl_sync(full, lrB, lane & ~(nb - 1));
         double nxt_o = __shfl_down_sync(full, lrA, 1), rnx_o = __shfl_down_sync(full, ro, 1);
         double nxt_n = __shfl_down_sync(full, lrB, 1), rnx_n = __shfl_down_sync(full, rn, 1);
@@ -352,8 +391,8 @@ __device__ __forceinline__ void FastIlkkaEvalWindow(const Tab &tb, const FastTab
             rnx_o = r_end;
             rnx_n = r_end;
         }
-        if (rpo != rnx_o) nxt_o = FastPP1Eval(tb, T.lr, Clamp(rpo, T.lr.r_min, T.lr.r_max));
-        if (rpn != rnx_n) nxt_n = FastPP1Eval(tb, T.lr, Clamp(rpn, T.lr.r_min, T.lr.r_max));
+        if (rpo != rnx_o) nxt_o = FastLrEval(tb, T, Clamp(rpo, T.lr.r_min, T.lr.r_max));
+        if (rpn != rnx_n) nxt_n = FastLrEval(tb, T, Clamp(rpn, T.lr.r_min, T.lr.r_max));
         uo = fma(-0.5, lrA, uo);
         uo = fma(-0.5, nxt_o, uo);
         un = fma(-0.5, j == 0 ? lrA : lrB, un);

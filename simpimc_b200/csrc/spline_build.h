@@ -433,6 +433,63 @@ inline bool BuildULut(const double *g, int n, int max_keys, ULut &out) {
     return true;
 }
 
+/// Bucket-centred form of a 1-D natural spline (pair_fast.cuh: FastLR2): the uniform buckets of BuildULut
+/// ([(k - 1/2) h, (k + 1/2) h), h = 0.96 x the smallest knot spacing: at most one knot per bucket) carry the cubic piece
+/// that holds their lower edge, re-expanded in long double about the bucket centre k h (records 0 .. n_keys: one more
+/// than buckets, the piece above a knot is the NEXT bucket's record), and the position of their knot in 1/65536 of h
+/// from the lower edge (0xFFFF: none, or so close to the upper edge that the next bucket takes it over).
+struct LR2Host {
+    double h = 0., inv_h16 = 0.;
+    std::vector<uint16_t> knot;      // [n_keys]
+    std::vector<double> c01, c23;    // [n_keys + 1][2]
+};
+
+inline bool BuildLR2(const double *g, int n, const KnotBasis &kb, const double *c, int max_keys, LR2Host &out) {
+    if (n < 2 || g[0] < 0.) return false;
+    double min_sp = g[1] - g[0];
+    for (int i = 2; i < n; ++i) min_sp = std::min(min_sp, g[i] - g[i - 1]);
+    if (!(min_sp > 0.)) return false;
+    const double h = 0.96 * min_sp;
+    const double n_keys_d = std::ceil(g[n - 1] / h) + 3.0;
+    if (n_keys_d > (double)std::min(max_keys, 32767)) return false;   // the device packs bucket and position into 31 bits
+    const int n_keys = (int)n_keys_d;
+    out.h = h;
+    out.inv_h16 = 65536.0 / h;
+    out.knot.assign((std::size_t)n_keys, 0xFFFF);
+    out.c01.assign(2 * ((std::size_t)n_keys + 1), 0.0);
+    out.c23.assign(2 * ((std::size_t)n_keys + 1), 0.0);
+    auto interval = [&](long double x) {   // einspline's reverse map: last i with g[i] <= x, 0 below the grid, n - 1 at or above its end
+        if (x <= g[0]) return 0;
+        if (x >= g[n - 1]) return n - 1;
+        return (int)(std::upper_bound(g, g + n, (double)x) - g) - 1;
+    };
+    for (int k = 0; k <= n_keys; ++k) {
+        const long double centre = (long double)k * (long double)h;
+        const long double lo = centre - 0.5L * h, hi = centre + 0.5L * h;
+        const int i = interval(lo);
+        // piece i about g[i] (PPFrom1D's sums, kept in long double), then about the bucket centre
+        CubicLD b[4];
+        BasisPolynomials(kb, i, b);
+        long double a[4];
+        for (int m = 0; m < 4; ++m) {
+            long double acc = 0;
+            for (int t = 0; t < 4; ++t) acc += (long double)c[i + t] * b[t].c[m];
+            a[m] = acc;
+        }
+        const long double d = centre - (long double)g[i];
+        out.c01[2 * (std::size_t)k] = (double)(a[0] + d * (a[1] + d * (a[2] + d * a[3])));
+        out.c01[2 * (std::size_t)k + 1] = (double)(a[1] + d * (2.0L * a[2] + 3.0L * d * a[3]));
+        out.c23[2 * (std::size_t)k] = (double)(a[2] + 3.0L * d * a[3]);
+        out.c23[2 * (std::size_t)k + 1] = (double)a[3];
+        if (k < n_keys && i + 1 < n && (long double)g[i + 1] > lo && (long double)g[i + 1] < hi) {
+            if (i + 2 < n && (long double)g[i + 2] < hi) return false;   // cannot happen while h < min spacing
+            const long double pos = std::ceil(((long double)g[i + 1] - lo) / h * 65536.0L);
+            out.knot[(std::size_t)k] = (uint16_t)std::min<long double>(pos, 65535.0L);
+        }
+    }
+    return true;
+}
+
 /// Bit-pattern interval table for the fast David kernel: bucket k holds every x >= 0 whose
 /// (high 32 bits >> shift) equals k + key0, i.e. one exponent value and the top (20 - shift)
 /// mantissa bits -- buckets of constant relative width 2^-(20-shift), the natural partner of a
