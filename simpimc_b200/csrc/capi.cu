@@ -642,6 +642,17 @@ int AppendULut(ByteBlob &blob, ULutDesc &d, const ULut &L) {
     return d.off_lut;
 }
 
+#if PIMC_XY16
+/// The packed interval table of ULookup16 (pair_fast.cuh) for a grid whose uniform table is L.
+void AppendULut32(ByteBlob &blob, ULutDesc &d, const ULut &L, const double *g, int n) {
+    const std::vector<uint32_t> pk = PackULut(L, g, n);
+    d.off_lut32 = blob.Reserve(pk.size() * sizeof(uint32_t));
+    std::memcpy(blob.At<uint32_t>(d.off_lut32), pk.data(), pk.size() * sizeof(uint32_t));
+    d.inv_h16 = 32768.0 / L.h;
+    d.x_cap = (double)((int)L.lut.size() - 1) * L.h;
+}
+#endif
+
 int AppendKnotPairs(ByteBlob &blob, const double *g, int n) {
     const int off = blob.Reserve((size_t)n * 16);
     double *p = blob.At<double>(off);
@@ -650,6 +661,51 @@ int AppendKnotPairs(ByteBlob &blob, const double *g, int n) {
         p[2 * i + 1] = (i + 1 < n) ? g[i + 1] : HUGE_VAL;
     }
     return off;
+}
+
+/// The arrays of one 1-D pp-form spline in the fast layout (pair_fast.cuh: FastPP1).  A uniform interval table
+/// (`ulut`) gives the bucket-centred form with PIMC_LR2 (records per bucket + knot positions), the interval form
+/// otherwise; a bit-pattern table (`blut`) always the interval form.
+bool AppendPP1Arrays(ByteBlob &blob, FastPP1 &d, const pimc_table_1d &f, const KnotBasis &kb, const double *coefs, const ULut *ulut,
+                     const BLut *blut, int max_keys) {
+#if PIMC_LR2
+    if (ulut) {
+        LR2Host l2;
+        if (!BuildLR2(f.r, f.n, kb, coefs, max_keys, l2)) return false;
+        d.h = l2.h;
+        d.inv_h16 = l2.inv_h16;
+        d.off_c01 = blob.Reserve(l2.c01.size() * sizeof(double));
+        std::memcpy(blob.At<double>(d.off_c01), l2.c01.data(), l2.c01.size() * sizeof(double));
+        d.off_c23 = blob.Reserve(l2.c23.size() * sizeof(double));
+        std::memcpy(blob.At<double>(d.off_c23), l2.c23.data(), l2.c23.size() * sizeof(double));
+        d.off_knot = blob.Reserve(l2.knot.size() * sizeof(uint16_t));
+        std::memcpy(blob.At<uint16_t>(d.off_knot), l2.knot.data(), l2.knot.size() * sizeof(uint16_t));
+        return true;
+    }
+#else
+    (void)max_keys;
+#endif
+    const std::vector<double> pp = PPFrom1D(kb, coefs);
+    d.off_gpair = AppendKnotPairs(blob, f.r, f.n);
+    d.off_c01 = blob.Reserve((size_t)f.n * 16);
+    d.off_c23 = blob.Reserve((size_t)f.n * 16);
+    for (int i = 0; i < f.n; ++i) {
+        blob.At<double>(d.off_c01)[2 * i] = pp[4 * (size_t)i];
+        blob.At<double>(d.off_c01)[2 * i + 1] = pp[4 * (size_t)i + 1];
+        blob.At<double>(d.off_c23)[2 * i] = pp[4 * (size_t)i + 2];
+        blob.At<double>(d.off_c23)[2 * i + 1] = pp[4 * (size_t)i + 3];
+    }
+    if (ulut) {
+        AppendULut(blob, d.lut, *ulut);
+    } else {
+        d.lut.off_lut = blob.Reserve(blut->lut.size() * sizeof(uint16_t));
+        std::memcpy(blob.At<uint16_t>(d.lut.off_lut), blut->lut.data(), blut->lut.size() * sizeof(uint16_t));
+        d.lut.key_max = (int)blut->lut.size() - 1;
+        d.lut.inv_h = 0.;
+        d.lut.shift = blut->shift;
+        d.lut.key0 = blut->key0;
+    }
+    return true;
 }
 
 /// Packs the shared-memory block of the fast pair kernel for one of u_xy / du_xy (+ its
@@ -668,6 +724,11 @@ int BuildFastIlkka(pimc_ctx *ctx, pimc_action *a, int which, const pimc_table_2d
     T.xy.off_gypair = AppendKnotPairs(blob, g.y, g.n_y);
     AppendULut(blob, T.xy.lutx, lx);
     AppendULut(blob, T.xy.luty, ly);
+#if PIMC_XY16
+    if (lx.lut.size() > 65000 || ly.lut.size() > 65000) return PIMC_OK;  // bucket and position share 31 bits
+    AppendULut32(blob, T.xy.lutx, lx, g.x, g.n_x);
+    AppendULut32(blob, T.xy.luty, ly, g.y, g.n_y);
+#endif
     T.xy.ny = g.n_y;
     T.xy.cells_global = a->cells[which].p;
     T.use_lr = a->use_long_range ? 1 : 0;
@@ -678,31 +739,7 @@ int BuildFastIlkka(pimc_ctx *ctx, pimc_action *a, int which, const pimc_table_2d
         kb.Build(f.r, f.n);
         std::vector<double> coefs(f.n + 3, 0.0);
         SolveNatural(kb, f.f, 1, coefs.data(), 1);
-#if PIMC_LR2
-        // bucket-centred form (pair_fast.cuh: FastLR2): the buckets of the interval table carry the pieces themselves
-        LR2Host l2;
-        if (!BuildLR2(f.r, f.n, kb, coefs.data(), kMaxKeys, l2)) return PIMC_OK;
-        T.lr2.h = l2.h;
-        T.lr2.inv_h16 = l2.inv_h16;
-        T.lr2.off_c01 = blob.Reserve(l2.c01.size() * sizeof(double));
-        std::memcpy(blob.At<double>(T.lr2.off_c01), l2.c01.data(), l2.c01.size() * sizeof(double));
-        T.lr2.off_c23 = blob.Reserve(l2.c23.size() * sizeof(double));
-        std::memcpy(blob.At<double>(T.lr2.off_c23), l2.c23.data(), l2.c23.size() * sizeof(double));
-        T.lr2.off_knot = blob.Reserve(l2.knot.size() * sizeof(uint16_t));
-        std::memcpy(blob.At<uint16_t>(T.lr2.off_knot), l2.knot.data(), l2.knot.size() * sizeof(uint16_t));
-#else
-        const std::vector<double> pp = PPFrom1D(kb, coefs.data());
-        T.lr.off_gpair = AppendKnotPairs(blob, f.r, f.n);
-        T.lr.off_c01 = blob.Reserve((size_t)f.n * 16);
-        T.lr.off_c23 = blob.Reserve((size_t)f.n * 16);
-        for (int i = 0; i < f.n; ++i) {
-            blob.At<double>(T.lr.off_c01)[2 * i] = pp[4 * (size_t)i];
-            blob.At<double>(T.lr.off_c01)[2 * i + 1] = pp[4 * (size_t)i + 1];
-            blob.At<double>(T.lr.off_c23)[2 * i] = pp[4 * (size_t)i + 2];
-            blob.At<double>(T.lr.off_c23)[2 * i + 1] = pp[4 * (size_t)i + 3];
-        }
-        AppendULut(blob, T.lr.lut, ll);
-#endif
+        if (!AppendPP1Arrays(blob, T.lr, f, kb, coefs.data(), &ll, nullptr, kMaxKeys)) return PIMC_OK;
         T.lr.r_min = f.r[0];
         T.lr.r_max = f.r[f.n - 1];
     }
@@ -756,26 +793,7 @@ bool AppendFastPP1(ByteBlob &blob, FastPP1 &d, const pimc_table_1d &f, int max_k
     kb.Build(f.r, f.n);
     std::vector<double> coefs(f.n + 3, 0.0);
     SolveNatural(kb, f.f, 1, coefs.data(), 1);
-    const std::vector<double> pp = PPFrom1D(kb, coefs.data());
-    d.off_gpair = AppendKnotPairs(blob, f.r, f.n);
-    d.off_c01 = blob.Reserve((size_t)f.n * 16);
-    d.off_c23 = blob.Reserve((size_t)f.n * 16);
-    for (int i = 0; i < f.n; ++i) {
-        blob.At<double>(d.off_c01)[2 * i] = pp[4 * (size_t)i];
-        blob.At<double>(d.off_c01)[2 * i + 1] = pp[4 * (size_t)i + 1];
-        blob.At<double>(d.off_c23)[2 * i] = pp[4 * (size_t)i + 2];
-        blob.At<double>(d.off_c23)[2 * i + 1] = pp[4 * (size_t)i + 3];
-    }
-    if (uniform) {
-        AppendULut(blob, d.lut, lut);
-    } else {
-        d.lut.off_lut = blob.Reserve(blut.lut.size() * sizeof(uint16_t));
-        std::memcpy(blob.At<uint16_t>(d.lut.off_lut), blut.lut.data(), blut.lut.size() * sizeof(uint16_t));
-        d.lut.key_max = (int)blut.lut.size() - 1;
-        d.lut.inv_h = 0.;
-        d.lut.shift = blut.shift;
-        d.lut.key0 = blut.key0;
-    }
+    if (!AppendPP1Arrays(blob, d, f, kb, coefs.data(), uniform ? &lut : nullptr, uniform ? nullptr : &blut, max_keys)) return false;
     d.r_min = f.r[0];
     d.r_max = f.r[f.n - 1];
     return true;

@@ -37,7 +37,13 @@
 #ifndef PIMC_K1_UNROLL
 #define PIMC_K1_UNROLL 1
 #endif
-// 1: the long-range r-space spline of the fast Ilkka tables in bucket-centred form (FastLR2); 0: interval form (FastPP1)
+// 1: x / y interval of the 2-D table from the packed interval table (ULookup16: one load, then knot and cell together).
+// Measured (tools/gpu_ab_lr2.sh, same box): K1 44.77 -> 44.64 ms, displace 1.310 -> 1.326 ms per attempt -- inside the
+// run-to-run noise, so it stays OFF and the x / y intervals remain einspline's bit for bit (ULookup).
+#ifndef PIMC_XY16
+#define PIMC_XY16 0
+#endif
+// 1: 1-D splines with a uniform interval table in bucket-centred form (FastPP1); 0: interval form everywhere (A/B)
 #ifndef PIMC_LR2
 #define PIMC_LR2 1
 #endif
@@ -53,13 +59,37 @@ struct ULutDesc {
     int key_max;    // n_keys - 1
     double inv_h;   // 1 / bucket width
     int shift, key0;  // bit-pattern buckets (KIND 1, see FastLut): key = (high word of x >> shift) - key0
+    // packed form (PIMC_XY16, the x / y grids of the 2-D table): entry k = interval of bucket k's lower edge << 16 | position
+    // of the bucket's knot in 1/32768 of the bucket width from its lower edge (0xFFFF: none), so the interval is known
+    // after ONE load and the knot g[i] (for tau) is fetched beside the cell's coefficients instead of before them
+    int off_lut32;  // uint32 [n_keys]
+    double inv_h16; // 32768 / bucket width
+    double x_cap;   // key_max * bucket width: keys of larger x are those of x_cap (the last bucket lies above the grid end)
 };
+/// A 1-D pp-form spline.  Two layouts:
+///   interval form (bit-pattern interval tables, and every table without PIMC_LR2): lut -> interval i, knot pairs
+///   (g[i], g[i+1]) for the finishing compare and tau = x - g[i], coefficients of piece i in off_c01 / off_c23;
+///   BUCKET-CENTRED form (uniform interval tables with PIMC_LR2): the table's uniform buckets
+///   [(k - 1/2) h, (k + 1/2) h) -- h below the smallest knot spacing, so at most one knot per bucket -- carry the
+///   polynomial themselves.  Record k (off_c01 / off_c23, n_keys + 1 of them) is the cubic piece that holds the bucket's
+///   lower edge, re-expanded (long double) about the bucket centre k h; knot[k] (off_knot) is the position of the
+///   bucket's knot in 1/65536 of h from its lower edge (0xFFFF: none).  x at or above the knot belongs to the piece that
+///   holds the NEXT bucket's lower edge: record k + 1, evaluated at the negative offset x - (k + 1) h.  One small load
+///   decides, then the two coefficient loads go out together: the knot-pair load of the interval form (one of three
+///   16-byte gathers at ~8.7 wavefronts each when 32 lanes sit in 32 unrelated intervals) and one level of the
+///   dependent chain are gone (K1: 46.50 -> 44.82 ms, same-box A/B).  The compare is made on a 16-bit fraction of the
+///   bucket: within h / 65536 of a knot either neighbouring piece may be taken, and there the two cubics differ by
+///   (jump of the third derivative) (h / 65536)^3 / 6 -- a natural spline is C2 -- far below one ulp of the value
+///   (host emulation against the interval form, knots and their floating-point neighbours included: 1e-16).
 struct FastPP1 {
     ULutDesc lut;
     int off_gpair;  // double2 [n]: (g[i], g[i+1]); g[n] = +inf
-    int off_c01;    // double2 [n]: (c0, c1) of interval i
-    int off_c23;    // double2 [n]: (c2, c3)
+    int off_c01;    // double2 [n]: (c0, c1) of interval i          | bucket-centred: [n_keys + 1]
+    int off_c23;    // double2 [n]: (c2, c3)                         | bucket-centred: [n_keys + 1]
     double r_min, r_max;
+    int off_knot;   // bucket-centred: uint16 [n_keys]
+    double inv_h16; // bucket-centred: 65536 / h
+    double h;
 };
 struct FastPP2 {
     ULutDesc lutx, luty;
@@ -70,26 +100,9 @@ struct FastPP2 {
     int ny;             // cells per row of the global array
     const double *cells_global;  // [nx][ny][16]
 };
-/// Long-range r-space spline in BUCKET-CENTRED form (PIMC_LR2): the interval table's uniform buckets
-/// [(k - 1/2) h, (k + 1/2) h) -- h below the smallest knot spacing, so at most one knot per bucket -- carry the
-/// polynomial themselves.  Record k is the cubic piece that holds the bucket's lower edge, re-expanded (long double)
-/// about the bucket centre k h; knot[k] is the position of the bucket's knot in 1/65536 of h from its lower edge
-/// (0xFFFF: none).  x at or above the knot belongs to the piece that holds the NEXT bucket's lower edge: record k + 1,
-/// evaluated at the negative offset x - (k + 1) h.  One small load decides, then the two coefficient loads go out
-/// together: the knot-pair load of the interval form (one of three 16-byte gathers at ~8.7 wavefronts each, 32 lanes in
-/// 32 unrelated intervals) and one level of the dependent chain are gone.  The compare is made on a 16-bit fraction
-/// of the bucket: within h / 65536 of a knot either neighbouring piece may be taken, and there the two cubics differ by
-/// (jump of the third derivative) * (h / 65536)^3 / 6 -- a natural spline is C2 -- far below one ulp of the value.
-struct FastLR2 {
-    int off_knot;        // uint16 [n_keys]
-    int off_c01, off_c23;  // double2 [n_keys + 1]
-    double inv_h16;      // 65536 / h
-    double h;
-};
 struct FastTable {
     FastPP2 xy;
-    FastPP1 lr;       // interval form (r_min / r_max always; the arrays only without PIMC_LR2)
-    FastLR2 lr2;
+    FastPP1 lr;
     int use_lr;
     int n_bytes;  // size of the staged block
 };
@@ -110,12 +123,24 @@ struct SharedTab {
         asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(base + (uint32_t)off));
         return (int)v;
     }
+    __device__ __forceinline__ uint32_t LdU32(int off) const {
+        uint32_t v;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + (uint32_t)off));
+        return v;
+    }
+    __device__ __forceinline__ double LdF64(int off) const {
+        double v;
+        asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + (uint32_t)off));
+        return v;
+    }
 };
 struct GlobalTab {
     const unsigned char *base;
     __device__ __forceinline__ explicit GlobalTab(const void *p) : base(reinterpret_cast<const unsigned char *>(p)) {}
     __device__ __forceinline__ double2 LdV2(int off) const { return __ldg(reinterpret_cast<const double2 *>(base + off)); }
     __device__ __forceinline__ int LdU16(int off) const { return __ldg(reinterpret_cast<const unsigned short *>(base + off)); }
+    __device__ __forceinline__ uint32_t LdU32(int off) const { return __ldg(reinterpret_cast<const uint32_t *>(base + off)); }
+    __device__ __forceinline__ double LdF64(int off) const { return __ldg(reinterpret_cast<const double *>(base + off)); }
 };
 
 /// Stages `n_bytes` (a multiple of 16; source and destination 16-byte aligned) of table data from
@@ -173,9 +198,35 @@ __device__ __forceinline__ void ULookup(const Tab &tb, const ULutDesc &L, int of
     t = x - (up ? g.y : g.x);
 }
 
+/// Interval of x >= 0 (any x: beyond the grid end it is the last one) and tau = x - g[interval] from the packed interval
+/// table.  Within 1/32768 of a bucket width of a knot either neighbouring interval may come out; the piecewise polynomial is
+/// C2 there, so the two pieces differ by (jump of the third derivative) (h / 32768)^3 / 6 -- far below one ulp of the value.
+template <class Tab>
+__device__ __forceinline__ void ULookup16(const Tab &tb, const ULutDesc &L, int off_gpair, double x, int &i, double &t) {
+    const double xc = x > L.x_cap ? L.x_cap : x;
+    // low word of fma(x, 32768 / h, 2^52 + 2^51) = rint(32768 x / h): bucket (nearest) above bit 15, position in it below
+    const int k32 = __double2loint(fma(xc, L.inv_h16, kRoundMagic)) + 0x4000;
+    const uint32_t pk = tb.LdU32(L.off_lut32 + 4 * (k32 >> 15));
+    i = (int)(pk >> 16) + (((uint32_t)k32 & 0x7FFFu) >= (pk & 0xFFFFu) ? 1 : 0);
+    t = x - tb.LdF64(off_gpair + 16 * i);
+}
+
 /// x must already lie inside [r_min, r_max] (SetLimits).
 template <class Tab, int KIND = 0>
 __device__ __forceinline__ double FastPP1Eval(const Tab &tb, const FastPP1 &d, double x) {
+#if PIMC_LR2
+    if (KIND == 0) {
+        // low word of fma(x, 65536 / h, 2^52 + 2^51) = rint(65536 x / h): bucket (nearest) in the high half, position in it below
+        const int k32 = __double2loint(fma(x, d.inv_h16, kRoundMagic)) + 0x8000;
+        const int key = k32 >> 16;
+        const int knot = tb.LdU16(d.off_knot + 2 * key);
+        const int rec = key + ((k32 & 0xFFFF) >= knot ? 1 : 0);
+        const double t = fma(-(double)rec, d.h, x);
+        const double2 c01 = tb.LdV2(d.off_c01 + 16 * rec);
+        const double2 c23 = tb.LdV2(d.off_c23 + 16 * rec);
+        return fma(fma(fma(c23.y, t, c23.x), t, c01.y), t, c01.x);
+    }
+#endif
     int i;
     double t;
     ULookup<Tab, KIND>(tb, d.lut, d.off_gpair, x, false, i, t);
@@ -187,27 +238,20 @@ __device__ __forceinline__ double FastPP1Eval(const Tab &tb, const FastPP1 &d, d
 /// u_long(x) of a fast Ilkka table; x must already lie inside [r_min, r_max] (SetLimits).
 template <class Tab>
 __device__ __forceinline__ double FastLrEval(const Tab &tb, const FastTable &T, double x) {
-#if PIMC_LR2
-    // low word of fma(x, 65536 / h, 2^52 + 2^51) = rint(65536 x / h): bucket (nearest) in the high half, position in it below
-    const int k32 = __double2loint(fma(x, T.lr2.inv_h16, kRoundMagic)) + 0x8000;
-    const int key = k32 >> 16;
-    const int knot = tb.LdU16(T.lr2.off_knot + 2 * key);
-    const int rec = key + ((k32 & 0xFFFF) >= knot ? 1 : 0);
-    const double t = fma(-(double)rec, T.lr2.h, x);
-    const double2 c01 = tb.LdV2(T.lr2.off_c01 + 16 * rec);
-    const double2 c23 = tb.LdV2(T.lr2.off_c23 + 16 * rec);
-    return fma(fma(fma(c23.y, t, c23.x), t, c01.y), t, c01.x);
-#else
-    return FastPP1Eval(tb, T.lr, x);
-#endif
+    return FastPP1Eval<Tab, 0>(tb, T.lr, x);
 }
 
 template <class Tab>
 __device__ __forceinline__ double FastPP2Eval(const Tab &tb, const FastPP2 &d, double x, double y) {
     int ix, iy;
     double tx, ty;
+#if PIMC_XY16
+    ULookup16(tb, d.lutx, d.off_gxpair, x, ix, tx);
+    ULookup16(tb, d.luty, d.off_gypair, y, iy, ty);
+#else
     ULookup(tb, d.lutx, d.off_gxpair, x, true, ix, tx);
     ULookup(tb, d.luty, d.off_gypair, y, true, iy, ty);
+#endif
     double2 c[8];
     if (ix < d.n_stage && iy < d.n_stage) {
         const int off = d.off_cells + ix * d.row_stride + iy * kCellRecord;

@@ -400,7 +400,27 @@ inline BitLut BuildBitLut(const double *g, int n) {
 struct ULut {
     double inv_h = 0.;
     std::vector<uint16_t> lut;
+    double h = 0.;
 };
+
+/// Packed form of a uniform interval table (pair_fast.cuh: ULookup16): entry k = lut[k] << 16 | position of the knot that
+/// lies inside bucket k = [(k - 1/2) h, (k + 1/2) h), in 1/32768 of h from the lower edge, rounded up and at most 0x7FFF
+/// (0: the knot sits at or just below the lower edge -- BuildULut's slack; 0xFFFF: no knot -- the 15-bit position of an
+/// x never reaches it).
+inline std::vector<uint32_t> PackULut(const ULut &L, const double *g, int n) {
+    std::vector<uint32_t> out(L.lut.size());
+    for (std::size_t k = 0; k < L.lut.size(); ++k) {
+        const int i = L.lut[k];
+        uint32_t pos = 0xFFFFu;
+        const long double lo = ((long double)k - 0.5L) * (long double)L.h, hi = lo + (long double)L.h;
+        if (i + 1 < n && (long double)g[i + 1] < hi) {
+            const long double p = std::ceil(((long double)g[i + 1] - lo) / (long double)L.h * 32768.0L);
+            pos = p <= 0 ? 0u : (p >= 32767.0L ? 0x7FFFu : (uint32_t)p);
+        }
+        out[k] = ((uint32_t)i << 16) | pos;
+    }
+    return out;
+}
 
 inline bool BuildULut(const double *g, int n, int max_keys, ULut &out) {
     if (n < 2 || n > 65535 || g[0] < 0.) return false;
@@ -413,6 +433,7 @@ inline bool BuildULut(const double *g, int n, int max_keys, ULut &out) {
     if (n_keys_d > (double)max_keys) return false;
     const int n_keys = (int)n_keys_d;
     out.inv_h = inv_h;
+    out.h = h;
     out.lut.assign((std::size_t)n_keys, 0);
     // interval of x (einspline general-grid reverse map): last i with g[i] <= x, 0 below the
     // grid, n-1 at or above its end

@@ -1,8 +1,8 @@
 #!/bin/bash
-# A/B on one box: long-range spline in interval form (ab_libs/lib_lr1.so, -DPIMC_LR2=0) against the bucket-centred form
-# (default build); then every GPU test on the default build
+# A/B on one box: the variant builds in ab_libs/*.so (e.g. -DPIMC_LR2=0: 1-D splines in interval form; -DPIMC_XY16=0: x / y
+# intervals through the knot-pair compare) against the default build; then every GPU test on the default build
 mkdir -p gpurun_out
-for lib in ab_libs/lib_lr1.so simpimc_b200/csrc/libsimpimc_b200.so; do
+for lib in ab_libs/*.so simpimc_b200/csrc/libsimpimc_b200.so; do
   SIMPIMC_B200_LIB=$PWD/$lib timeout 300 python bench.py --steps 5 --warmup 3 --cpu-evals 0 --attempts 64 --no-sharded --pipeline 1 2>&1 | python -c "
 import json,sys
 for l in sys.stdin:
