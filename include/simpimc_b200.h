@@ -229,6 +229,12 @@ int pimc_debug_fast_sqrt(pimc_ctx *ctx, int32_t n, const double *x, double *out)
  * n - 1 at or above its end); n_keys = table size.  PIMC_ERR_UNSUPPORTED if the grid admits no such table. */
 int pimc_debug_interval_table(int32_t kind, int32_t n, const double *grid, int32_t m, const double *x, int32_t *out,
                               int32_t *n_keys);
+/* HOST-ONLY: the natural cubic spline through (grid[n], values[n]) evaluated at x[m] (clamped to the grid, as SetLimits
+ * does) in the two layouts of the fast 1-D tables (csrc/pair_fast.cuh: FastPP1) -- out_interval: one cubic per interval about
+ * its knot (einspline's interval); out_bucket: the bucket-centred records with the device's lookup arithmetic.  The two are
+ * the same piecewise polynomial: they agree to rounding everywhere, the knots and their floating-point neighbours included. */
+int pimc_debug_bucket_spline(int32_t n, const double *grid, const double *values, int32_t m, const double *x, double *out_interval,
+                             double *out_bucket, int32_t *n_keys);
 /* enable != 0: evaluate with the general kernels even where the fast path applies (tests). */
 int pimc_ctx_force_general(pimc_ctx *ctx, int32_t enable);
 

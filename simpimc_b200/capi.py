@@ -163,7 +163,7 @@ EXPORTS = [
     "pimc_action_calc_pair_fast", "pimc_debug_fast_sqrt", "pimc_debug_interval_table", "pimc_ctx_force_general", "pimc_bisect_sweep", "pimc_displace_sweep", "pimc_perm_table", "pimc_halo_pack", "pimc_halo_unpack", "pimc_rotate_pack", "pimc_rotate_apply",
     "pimc_comm_unique_id", "pimc_comm_init", "pimc_comm_destroy", "pimc_comm_bytes_sent", "pimc_halo_exchange", "pimc_allreduce_sum", "pimc_rotate",
     "pimc_action_create_kinetic", "pimc_move_set_images", "pimc_bisect_sweep_windows", "pimc_sharded_evaluate", "pimc_capture_begin", "pimc_capture_end", "pimc_graph_launch", "pimc_graph_nodes", "pimc_graph_destroy",
-    "pimc_perm_bisect_sweep", "pimc_permutation_get", "pimc_permutation_set", "pimc_perm_last_cycle",
+    "pimc_perm_bisect_sweep", "pimc_permutation_get", "pimc_permutation_set", "pimc_perm_last_cycle", "pimc_debug_bucket_spline",
 ]
 
 _lib = None
@@ -223,6 +223,7 @@ def lib():
     L.pimc_action_calc_pair_fast.argtypes = [vp, i32, i32, vp, vp, vp, vp]
     L.pimc_debug_fast_sqrt.argtypes = [vp, i32, vp, vp]
     L.pimc_debug_interval_table.argtypes = [i32, i32, vp, i32, vp, vp, vp]
+    L.pimc_debug_bucket_spline.argtypes = [i32, vp, vp, i32, vp, vp, vp, vp]
     L.pimc_ctx_force_general.argtypes = [vp, i32]
     L.pimc_halo_pack.argtypes = [vp, i32, vp]
     L.pimc_halo_unpack.argtypes = [vp, i32, vp]

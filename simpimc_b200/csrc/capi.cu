@@ -3179,6 +3179,42 @@ int pimc_debug_interval_table(int32_t kind, int32_t n, const double *grid, int32
     return PIMC_OK;
 }
 
+int pimc_debug_bucket_spline(int32_t n, const double *grid, const double *values, int32_t m, const double *x, double *out_interval,
+                             double *out_bucket, int32_t *n_keys) {
+    if (!grid || !values || !x || !out_interval || !out_bucket || n < 2 || m < 0) return Fail(PIMC_ERR_INVALID, "bad argument");
+    try {
+        KnotBasis kb;
+        kb.Build(grid, n);
+        std::vector<double> coefs((size_t)n + 3, 0.0);
+        SolveNatural(kb, values, 1, coefs.data(), 1);
+        const std::vector<double> pp = PPFrom1D(kb, coefs.data());
+        LR2Host l2;
+        if (!BuildLR2(grid, n, kb, coefs.data(), 16384, l2)) return Fail(PIMC_ERR_UNSUPPORTED, "grid admits no uniform interval table");
+        if (n_keys) *n_keys = (int32_t)l2.knot.size();
+        for (int j = 0; j < m; ++j) {
+            const double xx = std::min(std::max(x[j], grid[0]), grid[n - 1]);  // SetLimits: the device evaluates inside the grid only
+            // interval form: einspline's interval, tau = x - g[i]
+            const int i = xx >= grid[n - 1] ? n - 1 : (int)(std::upper_bound(grid, grid + n, xx) - grid) - 1;
+            const double t = xx - grid[i];
+            out_interval[j] = std::fma(std::fma(std::fma(pp[4 * (size_t)i + 3], t, pp[4 * (size_t)i + 2]), t, pp[4 * (size_t)i + 1]), t, pp[4 * (size_t)i]);
+            // bucket-centred form: the device's arithmetic (FastPP1Eval, pair_fast.cuh)
+            const double kd = std::fma(xx, l2.inv_h16, kRoundMagic);
+            uint64_t bits;
+            std::memcpy(&bits, &kd, sizeof(bits));
+            const int k32 = (int)(int32_t)(uint32_t)bits + 0x8000;
+            const int key = k32 >> 16;
+            if (key < 0 || key >= (int)l2.knot.size()) return Fail(PIMC_ERR_INVALID, "internal: bucket outside the table");
+            const int rec = key + ((k32 & 0xFFFF) >= (int)l2.knot[(size_t)key] ? 1 : 0);
+            const double tb = std::fma(-(double)rec, l2.h, xx);
+            out_bucket[j] = std::fma(std::fma(std::fma(l2.c23[2 * (size_t)rec + 1], tb, l2.c23[2 * (size_t)rec]), tb, l2.c01[2 * (size_t)rec + 1]), tb,
+                                     l2.c01[2 * (size_t)rec]);
+        }
+    } catch (const std::exception &e) {
+        return Fail(PIMC_ERR_TABLE, e.what());
+    }
+    return PIMC_OK;
+}
+
 int pimc_ctx_force_general(pimc_ctx *ctx, int32_t enable) {
     if (!ctx) return Fail(PIMC_ERR_INVALID, "null context");
     ctx->force_general = enable != 0;

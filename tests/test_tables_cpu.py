@@ -131,3 +131,37 @@ def test_interval_tables_reproduce_the_einspline_interval_bit_for_bit():
     # a grid starting at 0 has no bit-pattern table (its first bucket would be unbounded below in the exponent)
     rc, _, _ = _intervals_from_library(1, xy, np.array([1.0]))
     assert rc != 0
+
+
+def test_bucket_centred_splines_equal_the_interval_form():
+    """The fast kernels evaluate 1-D splines with a uniform interval table (the long-range r-space parts, v(r)) from
+    bucket-centred records: one small load decides the piece, no knot is fetched (csrc/pair_fast.cuh: FastPP1,
+    csrc/spline_build.h: BuildLR2).  Host twin of the device arithmetic (pimc_debug_bucket_spline): the same piecewise
+    polynomial as the interval form to rounding -- random points, every knot and its floating-point neighbours (where
+    either neighbouring piece may be taken: C2 continuity), the grid ends, points outside the grid (clamped)."""
+    import ctypes as C
+    from simpimc_b200 import capi
+    L = capi.lib()
+    rng = np.random.default_rng(23)
+    for grid in (T.gen_grid("OPTIMIZED", 1.0e-4, 8.86, 1000), T.gen_grid("LINEAR", 1.0e-3, 8.4, 400), T.gen_grid("OPTIMIZED", 0.0, 5.0, 37)):
+        grid = np.ascontiguousarray(grid, dtype=np.float64)
+        vals = np.ascontiguousarray(np.exp(-0.3 * grid) / (grid + 0.2) + 0.05 * np.sin(3.0 * grid))
+        x = np.ascontiguousarray(_probe_points(grid, rng))
+        a, b = np.zeros(len(x)), np.zeros(len(x))
+        n_keys = C.c_int32(0)
+        rc = L.pimc_debug_bucket_spline(len(grid), grid.ctypes.data, vals.ctypes.data, len(x), x.ctypes.data, a.ctypes.data, b.ctypes.data,
+                                        C.addressof(n_keys))
+        assert rc == 0, capi.last_error() if hasattr(capi, "last_error") else rc
+        assert 0 < n_keys.value <= 16384
+        scale = np.max(np.abs(vals))
+        assert np.max(np.abs(a - b)) <= 4e-16 * scale, (len(grid), np.max(np.abs(a - b)))
+        # and the interval form is the spline: it interpolates its data
+        at_knots = np.zeros(len(grid))
+        rc = L.pimc_debug_bucket_spline(len(grid), grid.ctypes.data, vals.ctypes.data, len(grid), grid.ctypes.data, at_knots.ctypes.data,
+                                        b[:len(grid)].ctypes.data, C.addressof(n_keys))
+        assert rc == 0
+        assert np.max(np.abs(at_knots - vals)) <= 1e-13 * scale
+    # a grid too fine near its start for a uniform table is refused
+    fine = np.ascontiguousarray(1.0e-6 * np.exp(np.arange(400) * (np.log(1e7) / 399)))
+    rc = L.pimc_debug_bucket_spline(len(fine), fine.ctypes.data, fine.ctypes.data, 1, fine.ctypes.data, a.ctypes.data, b.ctypes.data, C.addressof(n_keys))
+    assert rc != 0
