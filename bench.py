@@ -474,7 +474,9 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "mc_sweeps_per_s": sweeps_per_s,
             "mc": {"unit": "clone-sweeps/s (one sweep = N*M/2^n_level bisection attempts)", "attempts_timed": n_att,
-                   "accept_ratio": accept_ratio, "window_pair_evals_per_s": window_evals_per_s,
+                   "accept_ratio": accept_ratio,
+                   "accept_note": "an accepted attempt is the expensive branch (positions and rho_k of the window are committed); a rejected one skips phase E and, when it dies above level 0, the pair and k-space phases too -- a high ratio is the conservative timing",
+                   "window_pair_evals_per_s": window_evals_per_s,
                    "ms_per_attempt": 1e3 * float(ts.item()) / n_att, "launches": int(launches_mc),
                    "pair_window_kernel_ms_per_attempt": k4_ms / max(1, n_att),
                    "driver": "device-resident pimc_bisect_sweep (Philox stream; kinetic + Ilkka pair + long-range deltas, Metropolis, commit)",

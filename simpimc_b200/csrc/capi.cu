@@ -2722,6 +2722,31 @@ int pimc_perm_bisect_sweep(pimc_ctx *ctx, int32_t s, int32_t n_level, int32_t n_
         sv_new.n_slots = kMaxPropSlots;
         for (int t = 0; t < n_acts; ++t) {
             pimc_action *a = acts[t];
+            if (a->atype == ATYPE_ILKKA && a->fast_ok[WHICH_U] && !ctx->force_general) {  // OLD and NEW in one launch, pp-form tables
+                PermPairArgs w;
+                w.pv = pv;
+                w.A_old = ctx->SView(a->sa, false);
+                w.B_old = ctx->SView(a->sb, false);
+                w.A_new = a->sa == s ? sv_new : w.A_old;
+                w.B_new = a->sb == s ? sv_new : w.B_old;
+                w.same = a->sa == a->sb;
+                w.moved_is_a = a->sa == s;
+                w.part = st.P_particle.p;
+                w.b0 = b0;
+                w.alive = alive;
+                w.n_links = nb;
+                w.FT = a->fast[WHICH_U];
+                w.fast_tables = a->fast_tab[WHICH_U].p;
+                w.partial_old = pair_parts + ((size_t)(2 * t) * C) * nb;
+                w.partial_new = pair_parts + ((size_t)(2 * t + 1) * C) * nb;
+                const int grid = (int)std::min<size_t>((size_t)C * nb, (size_t)ctx->n_sm * 16);
+                {
+                    ScopedKernelTimer tm(ctx, PIMC_KERNEL_PAIR_WINDOW);
+                    perm_pair_fast_kernel<<<grid, 128, 0, ctx->stream>>>(w);
+                }
+                ctx->launches++;
+                continue;
+            }
             for (int mode = 0; mode < 2; ++mode) {
                 PairWindowArgs w;
                 w.pv = pv;

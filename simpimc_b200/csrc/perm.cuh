@@ -353,6 +353,78 @@ __global__ void __launch_bounds__(32) perm_sample_kernel(const PermSampleArgs a)
     }
 }
 
+struct PermPairArgs {
+    PathView pv;
+    SpeciesView A_old, A_new, B_old, B_new;  // the action's two species without / with the label windows as their proposal
+    int same;                   // species_a == species_b
+    int moved_is_a;             // the moved species is species a of the action (always, when same)
+    const int32_t *part;        // [kMaxPropSlots][C] listed labels of the moved species, packed, -1 = unused slot
+    const int32_t *b0;          // [C]
+    const int32_t *alive;       // [C]
+    int n_links;
+    FastTable FT;
+    const unsigned char *fast_tables;
+    double *partial_old, *partial_new;   // [C][n_links]
+};
+
+/// PairAction::GetAction over the window for the listed labels (GenerateParticlePairs, pair_action_class.h:63-114) in
+/// OLD and NEW mode at once, through the fast Ilkka evaluation with its tables read from global memory: one CTA per
+/// (walker, link), threads over the partners.  Same pair set and order as pair_window_kernel (kernels.cuh), which stays
+/// the path of every other action type.
+__global__ void __launch_bounds__(128) perm_pair_fast_kernel(const PermPairArgs a) {
+    __shared__ double red[128 / 32];
+    const PathView &pv = a.pv;
+    const GlobalTab tb(a.fast_tables);
+    for (int item = blockIdx.x; item < pv.C * a.n_links; item += gridDim.x) {
+        const int c = item / a.n_links, j = item - c * a.n_links;
+        if (!a.alive[c]) continue;  // uniform over the CTA
+        const int bg = a.b0[c] + j;
+        int la[kMaxPropSlots], n_l = 0;
+        for (int i = 0; i < kMaxPropSlots; ++i) {
+            const int l = a.part[(size_t)i * pv.C + c];
+            if (l < 0) break;
+            la[n_l++] = l;
+        }
+        double acc_o = 0., acc_n = 0.;
+        const SpeciesView &M_old = a.moved_is_a ? a.A_old : a.B_old, &M_new = a.moved_is_a ? a.A_new : a.B_new;
+        const SpeciesView &Q_old = a.moved_is_a ? a.B_old : a.A_old, &Q_new = a.moved_is_a ? a.B_new : a.A_new;
+        for (int i = 0; i < n_l; ++i) {
+            const int m = la[i];
+            double m0o[3], m1o[3], m0n[3], m1n[3];
+            LoadPos(pv, M_old, c, m, bg, 0, m0o);
+            LoadPos(pv, M_old, c, m, bg + 1, 0, m1o);
+            LoadPos(pv, M_new, c, m, bg, 1, m0n);
+            LoadPos(pv, M_new, c, m, bg + 1, 1, m1n);
+            for (int q = threadIdx.x; q < Q_old.N; q += blockDim.x) {
+                if (a.same) {
+                    if (q == m) continue;
+                    bool earlier = false;  // (listed_i, listed_j) once: only from the lower list index
+                    for (int i2 = 0; i2 < i; ++i2) earlier = earlier || la[i2] == q;
+                    if (earlier) continue;
+                }
+                double q0[3], q1[3], r, rp, s;
+                LoadPos(pv, Q_old, c, q, bg, 0, q0);
+                LoadPos(pv, Q_old, c, q, bg + 1, 0, q1);
+                DrDrpDrrpFast(m0o, q0, m1o, q1, pv.box, r, rp, s);
+                acc_o += FastIlkkaEval(tb, a.FT, r, rp, s);
+                if (a.same) {  // the partner may be a listed label itself
+                    LoadPos(pv, Q_new, c, q, bg, 1, q0);
+                    LoadPos(pv, Q_new, c, q, bg + 1, 1, q1);
+                }
+                DrDrpDrrpFast(m0n, q0, m1n, q1, pv.box, r, rp, s);
+                acc_n += FastIlkkaEval(tb, a.FT, r, rp, s);
+            }
+        }
+        const double to = BlockSum<128>(acc_o, red);
+        const double tn = BlockSum<128>(acc_n, red);
+        if (threadIdx.x == 0) {
+            a.partial_old[item] = to;
+            a.partial_new[item] = tn;
+        }
+        __syncthreads();
+    }
+}
+
 struct PermDecideArgs {
     PathView pv;
     int N, n_k, nb;
