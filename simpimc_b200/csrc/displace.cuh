@@ -37,7 +37,7 @@ struct DisplaceSampleArgs {
 };
 
 /// One CTA per clone.
-__global__ void __launch_bounds__(128) displace_sample_kernel(const DisplaceSampleArgs a) {
+static __global__ void __launch_bounds__(128) displace_sample_kernel(const DisplaceSampleArgs a) {
     __shared__ double sdr[3];
     __shared__ int sp;
     const PathView &pv = a.pv;
@@ -119,7 +119,7 @@ struct DisplacePairArgs {
 
 /// ATYPE < 0: fast Ilkka path.
 template <int ATYPE>
-__global__ void __launch_bounds__(kDispThreads, 1) displace_pair_kernel(const DisplacePairArgs a) {
+static __global__ void __launch_bounds__(kDispThreads, 1) displace_pair_kernel(const DisplacePairArgs a) {
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ double red[2][kDispWarps];
     __shared__ double sdr[3];                // the item's shift vector
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kDispThreads, 1) displace_pair_kernel(const Di
 }
 
 /// One CTA per clone: Metropolis test (displace_particle_class.h:65-71) and Move::Accept.
-__global__ void __launch_bounds__(256) displace_decide_commit_kernel(PathView pv, int N, int n_k, int n_chunks, const double *__restrict__ partial,
+static __global__ void __launch_bounds__(256) displace_decide_commit_kernel(PathView pv, int N, int n_k, int n_chunks, const double *__restrict__ partial,
                                                                      int use_lr, const double *__restrict__ lr_old, const double *__restrict__ lr_new,
                                                                      const double *__restrict__ logu, const double *__restrict__ P,
                                                                      const int32_t *__restrict__ P_particle, const double2 *__restrict__ drho,

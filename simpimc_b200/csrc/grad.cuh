@@ -155,7 +155,7 @@ struct PairGradArgs {
 /// One CTA per (clone, window slice): the pairs of pair_window_kernel, derivative with respect
 /// to the species-a bead of each pair on its forward and backward links.
 template <int ATYPE>
-__global__ void __launch_bounds__(128) pair_grad_kernel(const PairGradArgs a) {
+static __global__ void __launch_bounds__(128) pair_grad_kernel(const PairGradArgs a) {
     __shared__ double red[128 / 32];
     const PathView &pv = a.pv;
     const int nv = a.what ? 1 : 3;
@@ -222,7 +222,7 @@ struct GradLongArgs {
 };
 
 /// CalcGradientULong summed over the pairs: one CTA per clone, threads over k.
-__global__ void __launch_bounds__(256) grad_long_kernel(const GradLongArgs a) {
+static __global__ void __launch_bounds__(256) grad_long_kernel(const GradLongArgs a) {
     extern __shared__ __align__(16) double2 gtab[];  // [32 particles][3 axes][2 m + 1]
     __shared__ double red[256 / 32];
     const PathView &pv = a.pv;
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) grad_long_kernel(const GradLongArgs a) {
 }
 
 /// out[c][v] = sum over the window items in order (+ the long-range gradient).
-__global__ void grad_finalize_kernel(const double *__restrict__ partial, int C, int n_links, int nv, const double *__restrict__ lr, double *__restrict__ out) {
+static __global__ void grad_finalize_kernel(const double *__restrict__ partial, int C, int n_links, int nv, const double *__restrict__ lr, double *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= C * nv) return;
     const int c = i / nv, v = i - c * nv;

@@ -130,7 +130,7 @@ __device__ __forceinline__ int StoreIndex(const PathView &pv, int s) {
 /// the warp walks over the partner particles q, staged tile by tile in shared memory.  The
 /// tables' 1-D parts, grids and LUTs are staged once per CTA.
 template <int ATYPE, int WHICH>
-__global__ void __launch_bounds__(kPairThreads, 1) pair_full_kernel(const PairFullArgs a) {
+static __global__ void __launch_bounds__(kPairThreads, 1) pair_full_kernel(const PairFullArgs a) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double red[kPairWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) pair_full_kernel(const PairFu
 
 /// out[c] = sum_b partial[c][b] in slice order, then the long-range term and constants in the
 /// reference's association: tot + ((ksum [*2]) + k_0 + r_0).
-__global__ void finalize_kernel(const double *__restrict__ partial, int C, int Mloc, const double *__restrict__ lr_sum,
+static __global__ void finalize_kernel(const double *__restrict__ partial, int C, int Mloc, const double *__restrict__ lr_sum,
                                 int add_lr, double lr_const_k, double lr_const_r, int add_const, double *__restrict__ out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
@@ -255,7 +255,7 @@ __device__ __forceinline__ double2 CMul(double2 a, double2 b) { return make_doub
 /// rho_k(c, b) = sum_p prod_d table_d[kidx(k, d)], particles added in index order.
 /// One CTA per (clone, slice); the phase tables of `chunk` particles at a time live in shared
 /// memory and thread k accumulates its k vector over them.
-__global__ void __launch_bounds__(256) rhok_build_kernel(PathView pv, SpeciesView sv, KSpaceView ks, int chunk, double2 *__restrict__ rho) {
+static __global__ void __launch_bounds__(256) rhok_build_kernel(PathView pv, SpeciesView sv, KSpaceView ks, int chunk, double2 *__restrict__ rho) {
     extern __shared__ __align__(16) double2 ctab[];  // [chunk][3][2m+1]
     const int tl = 2 * ks.max_index + 1;
     const int tid = threadIdx.x;
@@ -321,7 +321,7 @@ __host__ __device__ constexpr int ColsEntries(int TM) { return (3 * TM + 2) | 1;
 __device__ __forceinline__ double FlipSign(double v, int flip) { return __hiloint2double(__double2hiint(v) ^ flip, __double2loint(v)); }
 
 template <int TM>
-__global__ void __launch_bounds__(kColsWarps * 32) rhok_build_cols_kernel(PathView pv, SpeciesView sv, KColsView kc, double2 *__restrict__ rho) {
+static __global__ void __launch_bounds__(kColsWarps * 32) rhok_build_cols_kernel(PathView pv, SpeciesView sv, KColsView kc, double2 *__restrict__ rho) {
     constexpr int E = ColsEntries(TM);
     extern __shared__ __align__(16) double2 ctab[];  // [slice of the CTA][32 particles][E]
     const int G = kc.n_groups, S = kColsWarps / G;
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(kColsWarps * 32) rhok_build_cols_kernel(PathVi
 }
 
 /// rho[i] = sum over the particle parts of a split build, in part order.
-__global__ void rhok_reduce_kernel(const double2 *__restrict__ part, int n_parts, size_t n, double2 *__restrict__ rho) {
+static __global__ void rhok_reduce_kernel(const double2 *__restrict__ part, int n_parts, size_t n, double2 *__restrict__ rho) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double2 acc = part[i];
@@ -423,7 +423,7 @@ __global__ void rhok_reduce_kernel(const double2 *__restrict__ part, int n_parts
 /// drho(c, j, k) = sum over the species' pending proposals of rho_bead(new position) -
 /// rho_bead(old position) at window slice j (global slice b0[c] + j); a proposal that does not
 /// cover the slice contributes zero.
-__global__ void __launch_bounds__(256) rhok_delta_kernel(PathView pv, SpeciesView sv, KSpaceView ks, const int32_t *__restrict__ b0,
+static __global__ void __launch_bounds__(256) rhok_delta_kernel(PathView pv, SpeciesView sv, KSpaceView ks, const int32_t *__restrict__ b0,
                                                         int n_window, double2 *__restrict__ drho) {
     extern __shared__ __align__(16) double2 ctab[];  // [2][3][2m+1]
     const int tl = 2 * ks.max_index + 1;
@@ -480,7 +480,7 @@ struct KSumArgs {
 };
 
 /// out[c] = scale * (twice?2:1) * sum_k sum_b w_k Re(rho_a rho_b^*).
-__global__ void __launch_bounds__(256) ksum_kernel(const KSumArgs a) {
+static __global__ void __launch_bounds__(256) ksum_kernel(const KSumArgs a) {
     __shared__ double red[256 / 32];
     const int c = blockIdx.x;
     const PathView &pv = a.pv;
@@ -568,7 +568,7 @@ struct PairWindowArgs {
 /// (listed, other) and (listed_i, listed_j), i < j.  Different species: (listed a, every b),
 /// then (every unlisted a, listed b).
 template <int ATYPE>
-__global__ void __launch_bounds__(128) pair_window_kernel(const PairWindowArgs a) {
+static __global__ void __launch_bounds__(128) pair_window_kernel(const PairWindowArgs a) {
     __shared__ double red[128 / 32];
     const PathView &pv = a.pv;
     for (int item = blockIdx.x; item < pv.C * a.n_links; item += gridDim.x) {
@@ -633,7 +633,7 @@ __global__ void __launch_bounds__(128) pair_window_kernel(const PairWindowArgs a
 
 /// Per-pair test hook: out[i] = Calc{U,dUdBeta,V}(r[i], rp[i], s[i]).
 template <int ATYPE, int WHICH>
-__global__ void calc_pair_kernel(const double *__restrict__ blob, PairTable T, int n, const double *__restrict__ r,
+static __global__ void calc_pair_kernel(const double *__restrict__ blob, PairTable T, int n, const double *__restrict__ r,
                                  const double *__restrict__ rp, const double *__restrict__ s, double *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = PairEval<ATYPE, WHICH>(blob, T, r[i], rp[i], s[i]);
@@ -651,7 +651,7 @@ struct GofrArgs {
 
 /// Histogram of minimum-image distances; bin = (uint32)rint((|dr| - r_min) * d_ir - 0.5), with
 /// the distance and the bin argument computed without FMA contraction (bit-exact bins).
-__global__ void __launch_bounds__(256) gofr_kernel(const GofrArgs a) {
+static __global__ void __launch_bounds__(256) gofr_kernel(const GofrArgs a) {
     extern __shared__ unsigned int hist[];  // [n_r]
     const PathView &pv = a.pv;
     const int Na = a.A.N, Nb = a.B.N;
@@ -711,7 +711,7 @@ struct GofrTiledArgs {
     int warp_hist;    // 1: one histogram per warp
 };
 
-__global__ void __launch_bounds__(kGofrThreads, 1) gofr_tiled_kernel(const GofrTiledArgs t) {
+static __global__ void __launch_bounds__(kGofrThreads, 1) gofr_tiled_kernel(const GofrTiledArgs t) {
     extern __shared__ __align__(16) unsigned char gsm[];
     const GofrArgs &a = t.g;
     const PathView &pv = a.pv;
@@ -799,7 +799,7 @@ __global__ void __launch_bounds__(kGofrThreads, 1) gofr_tiled_kernel(const GofrT
 // ------------------------------------------------------------------------------------ K6
 /// sk[c][k] += cofactor[c] * CMag2(rho_a, rho_b) for b = 0..Mloc-1 in order (no FMA contraction:
 /// the accumulation then matches the reference bit for bit given equal rho_k).
-__global__ void sofk_kernel(PathView pv, int n_k, const double2 *__restrict__ rho_a, const double2 *__restrict__ rho_b,
+static __global__ void sofk_kernel(PathView pv, int n_k, const double2 *__restrict__ rho_a, const double2 *__restrict__ rho_b,
                             const double *__restrict__ kmag, double k_cut, const double *__restrict__ cofactor,
                             double *__restrict__ sk) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -837,7 +837,7 @@ __global__ void sofk_kernel(PathView pv, int n_k, const double2 *__restrict__ rh
 /// e = -|Dr(r_i(b0), r_j(b1))|^2 / (4 lambda tau n) [+ |Dr(r_i(b0), r_i(b1))|^2 / (4 lambda tau n) for the
 /// table variant], b1 = b0 + n_bisect_beads.  One CTA per (clone, i), threads over j; the path
 /// is taken unpermuted (the bead n slices ahead of particle j is particle j's).
-__global__ void __launch_bounds__(128) perm_table_kernel(PathView pv, const double *__restrict__ R, int N, const int32_t *__restrict__ b0,
+static __global__ void __launch_bounds__(128) perm_table_kernel(PathView pv, const double *__restrict__ R, int N, const int32_t *__restrict__ b0,
                                                         int n_bisect_beads, double i_4_lambda_tau_n, double log_epsilon, int relative,
                                                         double *__restrict__ t) {
     const int c = blockIdx.x / N, i = blockIdx.x - c * N;
@@ -866,7 +866,7 @@ __global__ void __launch_bounds__(128) perm_table_kernel(PathView pv, const doub
 
 // ------------------------------------------------------------------------- data movement
 /// host order R[clone][particle][bead][dim] -> device order R[clone][particle][dim][slice].
-__global__ void positions_in_kernel(const double *__restrict__ src, int n_clones, int N, int Mstore, int Ms, double *__restrict__ dst) {
+static __global__ void positions_in_kernel(const double *__restrict__ src, int n_clones, int N, int Mstore, int Ms, double *__restrict__ dst) {
     const size_t total = (size_t)n_clones * N * 3 * Ms;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int b = i % Ms;
@@ -876,7 +876,7 @@ __global__ void positions_in_kernel(const double *__restrict__ src, int n_clones
         dst[i] = b < Mstore ? src[(cp * Mstore + b) * 3 + d] : 0.0;
     }
 }
-__global__ void positions_out_kernel(const double *__restrict__ src, int n_clones, int N, int Mstore, int Ms, double *__restrict__ dst) {
+static __global__ void positions_out_kernel(const double *__restrict__ src, int n_clones, int N, int Mstore, int Ms, double *__restrict__ dst) {
     const size_t total = (size_t)n_clones * N * Mstore * 3;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int d = i % 3;
@@ -888,7 +888,7 @@ __global__ void positions_out_kernel(const double *__restrict__ src, int n_clone
 }
 
 /// out[c][j][d] = committed position of particle[c] at slice b_first[c] + j (mod M).
-__global__ void gather_beads_kernel(PathView pv, const double *__restrict__ R, int N, const int32_t *__restrict__ particle,
+static __global__ void gather_beads_kernel(PathView pv, const double *__restrict__ R, int N, const int32_t *__restrict__ particle,
                                     const int32_t *__restrict__ b_first, int n_beads, double *__restrict__ out) {
     const int c = blockIdx.x;
     const int p = particle[c];
@@ -902,7 +902,7 @@ __global__ void gather_beads_kernel(PathView pv, const double *__restrict__ R, i
 
 /// Move::Accept for the clones whose accept flag is set: committed positions take the
 /// proposal, committed rho_k takes rho_k + drho on the window slices.
-__global__ void commit_positions_kernel(PathView pv, int N, const double *__restrict__ P, const int32_t *__restrict__ P_particle,
+static __global__ void commit_positions_kernel(PathView pv, int N, const double *__restrict__ P, const int32_t *__restrict__ P_particle,
                                         const int32_t *__restrict__ P_first, int n_prop, int n_slots, const int32_t *__restrict__ accept,
                                         double *__restrict__ R) {
     const int c = blockIdx.x;
@@ -919,7 +919,7 @@ __global__ void commit_positions_kernel(PathView pv, int N, const double *__rest
         }
     }
 }
-__global__ void commit_rhok_kernel(PathView pv, int n_k, const double2 *__restrict__ drho, const int32_t *__restrict__ b0, int n_window,
+static __global__ void commit_rhok_kernel(PathView pv, int n_k, const double2 *__restrict__ drho, const int32_t *__restrict__ b0, int n_window,
                                    const int32_t *__restrict__ accept, double2 *__restrict__ rho) {
     const int c = blockIdx.y;
     if (!accept[c]) return;
@@ -936,11 +936,11 @@ __global__ void commit_rhok_kernel(PathView pv, int n_k, const double2 *__restri
 }
 
 /// Slice-shard halo: buf[clone][particle][dim] <-> one stored slice of the position array.
-__global__ void halo_pack_kernel(const double *__restrict__ R, size_t n_rows, int Ms, int slot, double *__restrict__ buf) {
+static __global__ void halo_pack_kernel(const double *__restrict__ R, size_t n_rows, int Ms, int slot, double *__restrict__ buf) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i < n_rows) buf[i] = R[i * Ms + slot];
 }
-__global__ void halo_unpack_kernel(double *__restrict__ R, size_t n_rows, int Ms, int slot, const double *__restrict__ buf) {
+static __global__ void halo_unpack_kernel(double *__restrict__ R, size_t n_rows, int Ms, int slot, const double *__restrict__ buf) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i < n_rows) R[i * Ms + slot] = buf[i];
 }
@@ -950,7 +950,7 @@ __global__ void halo_unpack_kernel(double *__restrict__ R, size_t n_rows, int Ms
 /// rotate while every shard keeps its range -- imaginary time is a ring, so actions and estimators
 /// are unchanged, and the slices that were shard boundaries (never moved by shard-interior windows)
 /// become interior.  buf is [row][shift], row = (clone, particle, dim).
-__global__ void rotate_pack_kernel(const double *__restrict__ R, size_t n_rows, int Ms, int shift, double *__restrict__ buf) {
+static __global__ void rotate_pack_kernel(const double *__restrict__ R, size_t n_rows, int Ms, int shift, double *__restrict__ buf) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n_rows * shift) return;
     const size_t row = i / shift;
@@ -959,7 +959,7 @@ __global__ void rotate_pack_kernel(const double *__restrict__ R, size_t n_rows, 
 }
 /// One thread per row: slide the owned slices left by `shift` (ascending order: in place) and put the
 /// received ones at the end.  The halo slot is left stale (the caller exchanges halos next).
-__global__ void rotate_apply_kernel(double *__restrict__ R, size_t n_rows, int Ms, int Mloc, int shift, const double *__restrict__ buf) {
+static __global__ void rotate_apply_kernel(double *__restrict__ R, size_t n_rows, int Ms, int Mloc, int shift, const double *__restrict__ buf) {
     const size_t row = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (row >= n_rows) return;
     double *r = R + row * Ms;
@@ -968,7 +968,7 @@ __global__ void rotate_apply_kernel(double *__restrict__ R, size_t n_rows, int M
 }
 
 /// Dependent-FMA chains: FP64 pipe throughput (2 flop per FMA).
-__global__ void fp64_peak_kernel(double *out, int iters) {
+static __global__ void fp64_peak_kernel(double *out, int iters) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1., a2 = a0 + 2., a3 = a0 + 3., a4 = a0 + 4., a5 = a0 + 5., a6 = a0 + 6., a7 = a0 + 7.;
     const double m = 1.0000001, k = 1e-7;
     for (int i = 0; i < iters; ++i) {

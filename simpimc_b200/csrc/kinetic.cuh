@@ -69,7 +69,7 @@ struct KineticFullArgs {
 
 /// sum over particles and links (b, b + 1) of GetDLogRhoFreeDTau(Dr(bead, next)) (kinetic_class.h:38-43);
 /// the constant N M n_d / (2 tau) is added by the caller.  CTA = (clone, 32-link chunk), lanes = links.
-__global__ void __launch_bounds__(256) kinetic_dbeta_kernel(const KineticFullArgs a) {
+static __global__ void __launch_bounds__(256) kinetic_dbeta_kernel(const KineticFullArgs a) {
     __shared__ double red[256 / 32];
     const PathView &pv = a.pv;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) kinetic_dbeta_kernel(const KineticFullArg
 }
 
 /// out[c] = constant + sign * sum of the clone's chunk partial sums, in chunk order.
-__global__ void kinetic_finalize_kernel(const double *__restrict__ partial, int C, int n_chunks, double sign, double constant,
+static __global__ void kinetic_finalize_kernel(const double *__restrict__ partial, int C, int n_chunks, double sign, double constant,
                                         double *__restrict__ out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
@@ -123,7 +123,7 @@ struct KineticWindowArgs {
 
 /// -sum over listed particles and links (a, a + skip), a = b0, b0 + skip, ... < b1, of
 /// GetLogRhoFree(Dr(bead_a, bead_{a + skip})) (kinetic_class.h:105-122).  One warp per clone.
-__global__ void __launch_bounds__(128) kinetic_window_kernel(const KineticWindowArgs a) {
+static __global__ void __launch_bounds__(128) kinetic_window_kernel(const KineticWindowArgs a) {
     const PathView &pv = a.pv;
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

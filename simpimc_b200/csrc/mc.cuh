@@ -98,7 +98,7 @@ constexpr int kSampleWarps = 4;  // clones per CTA
 /// One WARP per clone: the Philox draws (Levy displacements of all midpoints, Metropolis
 /// uniforms) and the window's bead loads run in parallel over the lanes, lane 0 then walks the
 /// levels (bisect_class.h:69-98) on shared memory, and the lanes write the proposal.
-__global__ void __launch_bounds__(kSampleWarps * 32) bisect_sample_kernel(const BisectArgs a) {
+static __global__ void __launch_bounds__(kSampleWarps * 32) bisect_sample_kernel(const BisectArgs a) {
     __shared__ double s_old[kSampleWarps][kMaxBisectBeads + 1][3], s_new[kSampleWarps][kMaxBisectBeads + 1][3];
     __shared__ double s_del[kSampleWarps][kMaxBisectBeads][3], s_d2[kSampleWarps][kMaxBisectBeads], s_logu[kSampleWarps][8];
     __shared__ int s_alive[kSampleWarps];
@@ -281,7 +281,7 @@ constexpr int kWindowThreads = 256;
 /// One CTA per clone: thread t walks partner particles q = t, t + 256, ...; for each it evaluates
 /// the window's links in OLD and NEW positions of the moved particle.
 template <int ATYPE, bool FAST>
-__global__ void __launch_bounds__(kWindowThreads) pair_window_both_kernel(const WindowBothArgs a) {
+static __global__ void __launch_bounds__(kWindowThreads) pair_window_both_kernel(const WindowBothArgs a) {
     __shared__ double pold[kMaxBisectBeads + 1][3], pnew[kMaxBisectBeads + 1][3];
     __shared__ double red[2][kWindowThreads / 32];
     const PathView &pv = a.pv;
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(kWindowThreads) pair_window_both_kernel(const 
 }
 
 /// Level-0 Metropolis test: log_accept = log_sample_ratio - (new_action - old_action) + previous change.
-__global__ void bisect_decide_kernel(int C, const int32_t *__restrict__ alive, const double *__restrict__ partial,
+static __global__ void bisect_decide_kernel(int C, const int32_t *__restrict__ alive, const double *__restrict__ partial,
                                      const double *__restrict__ logu0, const double *__restrict__ pair_old,
                                      const double *__restrict__ pair_new, const double *__restrict__ lr_old,
                                      const double *__restrict__ lr_new, int32_t *__restrict__ accept, int64_t *__restrict__ n_accept) {
@@ -379,7 +379,7 @@ constexpr int kWinTeamWarps = kWinTeamThreads / 32;
 /// partner) pair and groups of 32 / n_links partners per warp keep every warp converged: OLD and
 /// NEW come from one set of partner loads and the long-range spline is evaluated twice per link
 /// pair instead of four times (FastIlkkaEvalWindow).
-__global__ void __launch_bounds__(kWinFastThreads, 1) pair_window_fast_kernel(const WindowBothArgs a) {
+static __global__ void __launch_bounds__(kWinFastThreads, 1) pair_window_fast_kernel(const WindowBothArgs a) {
     extern __shared__ __align__(16) unsigned char wsm[];
     __shared__ double pold[kWinTeams][kMaxBisectBeads + 1][3], pnew[kWinTeams][kMaxBisectBeads + 1][3];
     __shared__ double red[kWinTeams][2][kWinTeamWarps];
@@ -489,7 +489,7 @@ struct LrWindowArgs {
 /// that involves the moved species.  One CTA per clone, thread per k vector.
 constexpr int kLrChunk = 16;  // window slices whose phase tables are built together
 
-__global__ void __launch_bounds__(256) lr_window_kernel(const LrWindowArgs a) {
+static __global__ void __launch_bounds__(256) lr_window_kernel(const LrWindowArgs a) {
     extern __shared__ __align__(16) double2 ptab[];  // [kLrChunk][2 modes][3 axes][2m+1]
     __shared__ double red[2][256 / 32];
     __shared__ int s_accept;
@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(256) lr_window_kernel(const LrWindowArgs a) {
 }
 
 /// bisect_decide_kernel + Move::Accept in one launch: one CTA per clone.
-__global__ void __launch_bounds__(256) bisect_decide_commit_kernel(PathView pv, int N, int n_k, int n_window, const int32_t *__restrict__ alive,
+static __global__ void __launch_bounds__(256) bisect_decide_commit_kernel(PathView pv, int N, int n_k, int n_window, const int32_t *__restrict__ alive,
                                                                    const double *__restrict__ partial, const double *__restrict__ logu0,
                                                                    const double *__restrict__ pair_old, const double *__restrict__ pair_new,
                                                                    const double *__restrict__ lr_old, const double *__restrict__ lr_new,

@@ -483,7 +483,7 @@ struct PairFastArgs {
 /// warp does the same amount of work per staged window; window t holds the Q + 31 particles
 /// q = 32 g + t Q + 1 ... and warp w reads row w + i at step i.  Different species: the window
 /// holds Q particles of species b and every warp walks all of them.
-__global__ void __launch_bounds__(kFastThreads, 1) pair_full_fast_kernel(const PairFastArgs a) {
+static __global__ void __launch_bounds__(kFastThreads, 1) pair_full_fast_kernel(const PairFastArgs a) {
     extern __shared__ __align__(16) unsigned char fsm[];
     __shared__ double red[kFastWarps];
     __shared__ double ring[kFastWarps][32];  // lane 31's parked r' per warp and step (FastIlkkaEvalWarp)
@@ -600,7 +600,7 @@ struct PotFastArgs {
 /// decomposition as pair_full_fast_kernel (warp = particle of species a, lanes = slices,
 /// partner rows staged per window of 32 offsets).
 template <int KIND>
-__global__ void __launch_bounds__(kFastThreads, 1) potential_fast_kernel(const PotFastArgs a) {
+static __global__ void __launch_bounds__(kFastThreads, 1) potential_fast_kernel(const PotFastArgs a) {
     extern __shared__ __align__(16) unsigned char fsm[];
     __shared__ double red[kFastWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -697,7 +697,7 @@ __device__ __forceinline__ double BareHalfV(const Tab &tb, const FastVTable &T, 
 /// distances -- r' in the image of r, unlike Potential().  Same decomposition as
 /// pair_full_fast_kernel; the half g(r') of a link is the next lane's g(r) whenever r' equals that
 /// r bit for bit (same image shift, the usual case), lane 31 parks its r' in the ring.
-__global__ void __launch_bounds__(kFastThreads, 1) bare_full_fast_kernel(const BareFastArgs a) {
+static __global__ void __launch_bounds__(kFastThreads, 1) bare_full_fast_kernel(const BareFastArgs a) {
     extern __shared__ __align__(16) unsigned char fsm[];
     __shared__ double red[kFastWarps];
     __shared__ double ring[kFastWarps][32];
@@ -881,7 +881,7 @@ struct DavidFastArgs {
 /// equals that r bit for bit (same image shift between the two slices, the usual case), lane 31
 /// parks its r' in the ring and the warp evaluates the parked values together.
 template <int NORD, int KIND>
-__global__ void __launch_bounds__(kFastThreads, 1) david_full_fast_kernel(const DavidFastArgs a) {
+static __global__ void __launch_bounds__(kFastThreads, 1) david_full_fast_kernel(const DavidFastArgs a) {
     extern __shared__ __align__(16) unsigned char fsm[];
     __shared__ double red[kFastWarps];
     __shared__ double ring[kFastWarps][32];
@@ -976,18 +976,18 @@ __global__ void __launch_bounds__(kFastThreads, 1) david_full_fast_kernel(const 
 
 /// Test hooks: the fast evaluation on caller-supplied triples (tables read from global memory
 /// through the same code) and the square root on its own.
-__global__ void calc_pair_fast_kernel(const unsigned char *__restrict__ tables, FastTable T, int n, const double *__restrict__ r,
+static __global__ void calc_pair_fast_kernel(const unsigned char *__restrict__ tables, FastTable T, int n, const double *__restrict__ r,
                                       const double *__restrict__ rp, const double *__restrict__ s, double *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = FastIlkkaEval(GlobalTab(tables), T, r[i], rp[i], s[i]);
 }
 template <int NORD, int KIND>
-__global__ void calc_david_fast_kernel(const unsigned char *__restrict__ tables, FastDavidTable T, int n, const double *__restrict__ r,
+static __global__ void calc_david_fast_kernel(const unsigned char *__restrict__ tables, FastDavidTable T, int n, const double *__restrict__ r,
                                        const double *__restrict__ rp, const double *__restrict__ s, double *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = FastDavidEval<NORD, KIND>(GlobalTab(tables), T, r[i], rp[i], s[i]);
 }
-__global__ void fast_sqrt_kernel(int n, const double *__restrict__ x, double *__restrict__ out) {
+static __global__ void fast_sqrt_kernel(int n, const double *__restrict__ x, double *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = FastSqrt(x[i]);
 }

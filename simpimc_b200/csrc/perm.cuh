@@ -55,7 +55,7 @@ struct PermSelectArgs {
 };
 
 /// One warp per walker; the row of the table lives in shared memory ([2][N] doubles).
-__global__ void __launch_bounds__(32) perm_select_kernel(const PermSelectArgs a) {
+static __global__ void __launch_bounds__(32) perm_select_kernel(const PermSelectArgs a) {
     extern __shared__ double row[];  // t(p, .) then t_c(p, .): [2][N]
     const PathView &pv = a.pv;
     const int c = blockIdx.x, lane = threadIdx.x, N = a.N;
@@ -174,7 +174,7 @@ struct PermSampleArgs {
 };
 
 /// One warp per walker: the lanes load the members' chains and draw the Levy displacements, lane 0 walks the levels.
-__global__ void __launch_bounds__(32) perm_sample_kernel(const PermSampleArgs a) {
+static __global__ void __launch_bounds__(32) perm_sample_kernel(const PermSampleArgs a) {
     __shared__ double s_old[kPermMaxLen][kMaxBisectBeads + 1][3], s_new[kPermMaxLen][kMaxBisectBeads + 1][3];
     __shared__ double s_del[kPermMaxLen][kMaxBisectBeads][3], s_d2[kPermMaxLen][kMaxBisectBeads], s_logu[8];
     __shared__ int s_ps[kPermMaxLen], s_nx[kPermMaxLen], s_lab[kMaxPropSlots], s_nlab;
@@ -371,7 +371,7 @@ struct PermPairArgs {
 /// OLD and NEW mode at once, through the fast Ilkka evaluation with its tables read from global memory: one CTA per
 /// (walker, link), threads over the partners.  Same pair set and order as pair_window_kernel (kernels.cuh), which stays
 /// the path of every other action type.
-__global__ void __launch_bounds__(128) perm_pair_fast_kernel(const PermPairArgs a) {
+static __global__ void __launch_bounds__(128) perm_pair_fast_kernel(const PermPairArgs a) {
     __shared__ double red[128 / 32];
     const PathView &pv = a.pv;
     const GlobalTab tb(a.fast_tables);
@@ -445,7 +445,7 @@ struct PermDecideArgs {
 };
 
 /// Level-0 Metropolis test (perm_bisect_iterative_class.h:196-208) + Move::Accept of the label windows: one CTA per walker.
-__global__ void __launch_bounds__(256) perm_decide_commit_kernel(const PermDecideArgs a) {
+static __global__ void __launch_bounds__(256) perm_decide_commit_kernel(const PermDecideArgs a) {
     __shared__ int s_acc;
     const PathView &pv = a.pv;
     const int c = blockIdx.x, C = pv.C, nb = a.nb, n_prop = nb - 1;
@@ -514,7 +514,7 @@ struct PermApplyArgs {
 };
 
 /// One CTA per walker: rows (member, dim) x slices (e, M) copied to the walker's scratch, written back rotated by one member.
-__global__ void __launch_bounds__(256) perm_apply_kernel(const PermApplyArgs a) {
+static __global__ void __launch_bounds__(256) perm_apply_kernel(const PermApplyArgs a) {
     __shared__ int labels[kPermMaxLen], old_next[kPermMaxLen];
     const PathView &pv = a.pv;
     const int c = blockIdx.x, N = a.N, M = pv.M;
@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(256) perm_apply_kernel(const PermApplyArgs a) 
 }
 
 /// next[c][p] = p: the unpermuted path.
-__global__ void perm_identity_kernel(int32_t *__restrict__ next, int C, int N) {
+static __global__ void perm_identity_kernel(int32_t *__restrict__ next, int C, int N) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < C * N) next[t] = t % N;
 }

@@ -119,7 +119,7 @@ __device__ __forceinline__ unsigned MirrorRow(int N, int q, int d) {
 
 /// R[c][row = particle * 3 + dim][slice (row length Ms)] -> R2[c][slice][row]: 32 x 32 tiles through shared
 /// memory, both sides coalesced.  grid (slice tiles, row tiles, clones), block (32, 8).
-__global__ void __launch_bounds__(256) slice_major_kernel(const double *__restrict__ R, int n_rows, int Mstore, int Ms, double *__restrict__ R2) {
+static __global__ void __launch_bounds__(256) slice_major_kernel(const double *__restrict__ R, int n_rows, int Mstore, int Ms, double *__restrict__ R2) {
     __shared__ double tile[32][33];
     const int c = blockIdx.z, s0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
     const double *src = R + (size_t)c * n_rows * Ms;
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) slice_major_kernel(const double *__restri
 /// IMAGES: the FreeSpline branches (periodic images of the free-particle density matrix) are compiled in; the
 /// n_images = 0 instantiation keeps the closed forms only (0.0750 vs 0.0790 ms per attempt at C3).
 template <bool IMAGES>
-__global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(const SweepFusedArgs a) {
+static __global__ void __launch_bounds__(kSweepThreads, 1) bisect_sweep_fused_kernel(const SweepFusedArgs a) {
     extern __shared__ __align__(16) unsigned char ssm[];
     __shared__ SweepShared sh;
     const int lane = threadIdx.x & 31;
