@@ -388,6 +388,8 @@ static __global__ void __launch_bounds__(128) perm_pair_fast_kernel(const PermPa
         double acc_o = 0., acc_n = 0.;
         const SpeciesView &M_old = a.moved_is_a ? a.A_old : a.B_old, &M_new = a.moved_is_a ? a.A_new : a.B_new;
         const SpeciesView &Q_old = a.moved_is_a ? a.B_old : a.A_old, &Q_new = a.moved_is_a ? a.B_new : a.A_new;
+        // an unlisted partner has no proposal: its two beads come straight from the committed array, once for both modes
+        const int s0 = WrapSlice(pv, bg) - pv.slice_lo, s1 = WrapSlice(pv, bg + 1) - pv.slice_lo;
         for (int i = 0; i < n_l; ++i) {
             const int m = la[i];
             double m0o[3], m1o[3], m0n[3], m1n[3];
@@ -396,18 +398,25 @@ static __global__ void __launch_bounds__(128) perm_pair_fast_kernel(const PermPa
             LoadPos(pv, M_new, c, m, bg, 1, m0n);
             LoadPos(pv, M_new, c, m, bg + 1, 1, m1n);
             for (int q = threadIdx.x; q < Q_old.N; q += blockDim.x) {
+                bool q_listed = false;
                 if (a.same) {
                     if (q == m) continue;
                     bool earlier = false;  // (listed_i, listed_j) once: only from the lower list index
-                    for (int i2 = 0; i2 < i; ++i2) earlier = earlier || la[i2] == q;
+                    for (int i2 = 0; i2 < n_l; ++i2) {
+                        earlier = earlier || (i2 < i && la[i2] == q);
+                        q_listed = q_listed || la[i2] == q;
+                    }
                     if (earlier) continue;
                 }
                 double q0[3], q1[3], r, rp, s;
-                LoadPos(pv, Q_old, c, q, bg, 0, q0);
-                LoadPos(pv, Q_old, c, q, bg + 1, 0, q1);
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    q0[d] = Q_old.R[PosIndex(pv, Q_old.N, c, q, d, s0)];
+                    q1[d] = Q_old.R[PosIndex(pv, Q_old.N, c, q, d, s1)];
+                }
                 DrDrpDrrpFast(m0o, q0, m1o, q1, pv.box, r, rp, s);
                 acc_o += FastIlkkaEval(tb, a.FT, r, rp, s);
-                if (a.same) {  // the partner may be a listed label itself
+                if (q_listed) {  // the partner is a listed label itself: its NEW beads come from its label window
                     LoadPos(pv, Q_new, c, q, bg, 1, q0);
                     LoadPos(pv, Q_new, c, q, bg + 1, 1, q1);
                 }
