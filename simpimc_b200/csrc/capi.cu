@@ -1105,6 +1105,12 @@ int pimc_ctx_destroy(pimc_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (pimc_action *a : ctx->actions) delete a;
+    for (cudaStream_t st : ctx->side_streams) {
+        cudaStreamSynchronize(st);
+        cudaStreamDestroy(st);
+    }
+    for (cudaEvent_t ev : ctx->side_events) cudaEventDestroy(ev);
+    if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return PIMC_OK;
@@ -2327,6 +2333,75 @@ int pimc_graph_destroy(pimc_graph *g) {
 }
 
 // ------------------------------------------------------------ internal.h (other translation units)
+int pimc_internal_evaluate_many(pimc_ctx *ctx, int which, pimc_action *const *actions, int n, double *d_out) {
+    if (!ctx || !actions || !d_out || n < 1) return Fail(PIMC_ERR_INVALID, "bad argument");
+    if (which != WHICH_U && which != WHICH_DU && which != WHICH_V) return Fail(PIMC_ERR_INVALID, "which must be 0 (action), 1 (dU/dbeta) or 2 (potential)");
+    for (int i = 0; i < n; ++i)
+        if (!actions[i] || actions[i]->ctx != ctx) return Fail(PIMC_ERR_INVALID, "action of another context");
+    PIMC_CUDA(cudaSetDevice(ctx->device));
+    if (n == 1 || ctx->timing) {  // per-kernel event pairs would time a kernel's wait for SMs as well: one after the other
+        for (int i = 0; i < n; ++i) {
+            const int rc = FullEvaluation(actions[i], which, d_out + (size_t)i * ctx->C);
+            if (rc != PIMC_OK) return rc;
+        }
+        return PIMC_OK;
+    }
+    while ((int)ctx->side_streams.size() < n - 1) {
+        cudaStream_t st = nullptr;
+        cudaEvent_t ev = nullptr;
+        PIMC_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        ctx->side_streams.push_back(st);
+        PIMC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->side_events.push_back(ev);
+    }
+    if (!ctx->fork_event) PIMC_CUDA(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
+    cudaStream_t main_stream = ctx->stream;
+    PIMC_CUDA(cudaEventRecord(ctx->fork_event, main_stream));
+    // an action evaluated beside others works in its own scratch and on its own stream: the launch helpers read both
+    // from the context, so they are swapped in for the duration of the call and restored on every path out
+    struct Swap {
+        pimc_ctx *ctx;
+        pimc_action *a;
+        cudaStream_t main_stream;
+        void Exchange() {
+            std::swap(ctx->partial.p, a->own_partial.p);
+            std::swap(ctx->partial.n, a->own_partial.n);
+            std::swap(ctx->lr_dev.p, a->own_lr.p);
+            std::swap(ctx->lr_dev.n, a->own_lr.n);
+        }
+        Swap(pimc_ctx *c, pimc_action *act, cudaStream_t s) : ctx(c), a(act), main_stream(c->stream) {
+            Exchange();
+            ctx->stream = s;
+        }
+        ~Swap() {
+            ctx->stream = main_stream;
+            Exchange();
+        }
+    };
+    int rc = PIMC_OK;
+    int forked = 0;
+    for (int i = 0; i < n && rc == PIMC_OK; ++i) {
+        cudaStream_t st = i == 0 ? main_stream : ctx->side_streams[(size_t)i - 1];
+        if (i > 0) {
+            PIMC_CUDA(cudaStreamWaitEvent(st, ctx->fork_event, 0));
+            forked = i;
+        }
+        {
+            Swap sw(ctx, actions[i], st);
+            rc = FullEvaluation(actions[i], which, d_out + (size_t)i * ctx->C);
+        }
+        if (i > 0) {  // joined even after a failure: a stream forked inside a capture must come back
+            const cudaError_t e = cudaEventRecord(ctx->side_events[(size_t)i - 1], st);
+            if (e != cudaSuccess && rc == PIMC_OK) rc = Fail(PIMC_ERR_CUDA, std::string("cudaEventRecord: ") + cudaGetErrorString(e));
+        }
+    }
+    for (int i = 1; i <= forked; ++i) {
+        const cudaError_t e = cudaStreamWaitEvent(main_stream, ctx->side_events[(size_t)i - 1], 0);
+        if (e != cudaSuccess && rc == PIMC_OK) rc = Fail(PIMC_ERR_CUDA, std::string("cudaStreamWaitEvent: ") + cudaGetErrorString(e));
+    }
+    return rc;
+}
+
 int pimc_internal_fail(int code, const char *msg) { return Fail(code, msg ? msg : ""); }
 int pimc_internal_device(const pimc_ctx *ctx) { return ctx->device; }
 int pimc_internal_n_clones(const pimc_ctx *ctx) { return ctx->C; }

@@ -236,17 +236,9 @@ int pimc_rotate(pimc_ctx *ctx, pimc_comm *cm, int32_t shift) {
 int pimc_sharded_evaluate(pimc_ctx *ctx, pimc_comm *cm, int32_t which, pimc_action *const *actions, int32_t n_actions, double *d_out) {
     if (!ctx || !cm || !actions || !d_out || n_actions < 1) return Fail(PIMC_ERR_INVALID, "bad argument");
     const int C = pimc_internal_n_clones(ctx);
-    for (int i = 0; i < n_actions; ++i) {
-        int rc;
-        double *dst = d_out + (size_t)i * C;
-        switch (which) {
-            case 0: rc = pimc_action_total_device(actions[i], dst); break;
-            case 1: rc = pimc_action_dbeta_device(actions[i], dst); break;
-            case 2: rc = pimc_action_potential_device(actions[i], dst); break;
-            default: return Fail(PIMC_ERR_INVALID, "which must be 0 (action), 1 (dU/dbeta) or 2 (potential)");
-        }
-        if (rc != PIMC_OK) return rc;
-    }
+    // the actions' whole-path kernels side by side (side streams forked from the context's and joined back), then ONE all-reduce
+    const int rc = pimc_internal_evaluate_many(ctx, which, actions, n_actions, d_out);
+    if (rc != PIMC_OK) return rc;
     return pimc_allreduce_sum(ctx, cm, d_out, (int64_t)n_actions * C);
 }
 

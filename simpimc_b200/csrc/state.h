@@ -134,6 +134,11 @@ struct pimc_ctx {
     DevBuf<double> perm_stage;     // [C][kPermMaxLen][3][M]
     DevBuf<long long> perm_counts; // attempted, accepted: 2 x [C][kPermMaxLen]
     std::vector<pimc_action *> actions;
+    // side streams of pimc_internal_evaluate_many: the whole-path evaluations of several actions forked off the
+    // context's stream and joined back into it (events), so that one action's CTAs fill the SMs another has left
+    std::vector<cudaStream_t> side_streams;
+    std::vector<cudaEvent_t> side_events;
+    cudaEvent_t fork_event = nullptr;
     int64_t launches = 0;
     bool force_general = false;  // tests: evaluate with the general kernels even where the fast path applies
     // optional per-kernel device timing (CUDA events on the context's stream)
@@ -203,6 +208,8 @@ struct pimc_action {
     std::vector<double> shell_k[3], shell_f[3];
     double k0[3] = {0, 0, 0}, r0[3] = {0, 0, 0};
     double ulong_scale = 1.;  // Bare CalcULong: level_tau
+    // the action's own partial-sum scratch for evaluations that run beside other actions' (pimc_internal_evaluate_many)
+    DevBuf<double> own_partial, own_lr;
     // Ilkka U / dU fast path (pair_fast.cuh): every table in one shared-memory block
     DevBuf<unsigned char> fast_tab[2];
     FastTable fast[2];
