@@ -482,6 +482,11 @@ struct LrWindowArgs {
     double2 *rho_commit;     // == rho_self, writable
     int32_t *accept;
     long long *n_accept;
+    // recompute_commit != 0 (with fuse_decide): drho is NOT stored; an accepted proposal rebuilds the phase tables and adds
+    // the same deltas (same arithmetic, same bits) to rho_k in the commit -- for a window that is the whole path
+    // (DisplaceParticle) this takes the rho_k traffic of an attempt from five passes over the array (read rho, write drho;
+    // read drho, read rho, write rho) to three
+    int recompute_commit = 0;
 };
 
 /// Species::UpdateRhoK for the proposal (species_class.h:406-425) fused with CalcULong over the
@@ -521,7 +526,7 @@ static __global__ void __launch_bounds__(256) lr_window_kernel(const LrWindowArg
             const double2 fo = CMul(CMul(to[i0], to[tl + i1]), to[2 * tl + i2]);
             const double2 fn = CMul(CMul(tn[i0], tn[tl + i1]), tn[2 * tl + i2]);
             const double2 d = make_double2(fn.x - fo.x, fn.y - fo.y);
-            a.drho[((size_t)c * a.n_window + j) * n_k + k] = d;
+            if (!a.recompute_commit) a.drho[((size_t)c * a.n_window + j) * n_k + k] = d;
             const size_t ri = ((size_t)RealClone(pv, c) * pv.Mloc + (bg - pv.slice_lo)) * n_k + k;
             const double2 rs = a.rho_self[ri];
             const double2 rn = make_double2(rs.x + d.x, rs.y + d.y);
@@ -585,12 +590,43 @@ static __global__ void __launch_bounds__(256) lr_window_kernel(const LrWindowArg
     // Move::Accept: the proposal's beads (n_prop beads from P_first: the window's interior for a bisection, the whole
     // path for a displacement) and rho_k += delta on the window (every read of rho_self is behind the barrier)
     const int n_prop = a.sv.n_prop, bead0 = a.b0[c], first = a.sv.P_first[c];
+    if (a.recompute_commit) {
+        // rho_k first, while the committed positions are still the OLD ones: the same tables, the same deltas as above
+        for (int j0 = 0; j0 < a.n_window; j0 += kLrChunk) {
+            const int nj = min(kLrChunk, a.n_window - j0);
+            __syncthreads();
+            for (int t = tid; t < nj * 6; t += blockDim.x) {
+                const int jj = t / 6, md = t - jj * 6;
+                const int mode = md / 3, d = md - mode * 3;
+                int bg = bead0 + j0 + jj;
+                bg = WrapSlice(pv, bg);
+                double r[3];
+                LoadPos(pv, a.sv, c, p, bg, mode, r);
+                PhaseTable(r[d], a.ks.kbox, a.ks.max_index, ptab + (size_t)t * tl);
+            }
+            __syncthreads();
+            for (int t = tid; t < nj * n_k; t += blockDim.x) {
+                const int jj = t / n_k, k = t - jj * n_k;
+                int bg = bead0 + j0 + jj;
+                bg = WrapSlice(pv, bg);
+                const int i0 = a.ks.kidx[3 * k], i1 = a.ks.kidx[3 * k + 1], i2 = a.ks.kidx[3 * k + 2];
+                const double2 *to = ptab + (size_t)jj * 6 * tl, *tn = to + 3 * tl;
+                const double2 fo = CMul(CMul(to[i0], to[tl + i1]), to[2 * tl + i2]);
+                const double2 fn = CMul(CMul(tn[i0], tn[tl + i1]), tn[2 * tl + i2]);
+                double2 *dst = a.rho_commit + ((size_t)RealClone(pv, c) * pv.Mloc + (bg - pv.slice_lo)) * n_k + k;
+                dst->x += fn.x - fo.x;
+                dst->y += fn.y - fo.y;
+            }
+        }
+        __syncthreads();  // every OLD position has been read
+    }
     for (int t = tid; t < n_prop * 3; t += blockDim.x) {
         const int j = t / 3, d = t - j * 3;
         int bg = first + j;
         bg = WrapSlice(pv, bg);
         a.R[PosIndex(pv, a.N, RealClone(pv, c), p, d, bg - pv.slice_lo)] = a.sv.P[((size_t)c * n_prop + j) * 3 + d];
     }
+    if (a.recompute_commit) return;
     for (int t = tid; t < a.n_window * n_k; t += blockDim.x) {
         const int j = t / n_k, k = t - j * n_k;
         int bg = bead0 + j;

@@ -760,6 +760,7 @@ int pimc_displace_sweep(pimc_ctx *ctx, int32_t s, double step_size, int32_t n_at
             l.lr_old = lr_old;
             l.lr_new = lr_new;
             l.fuse_decide = 1;  // decision and commit ride on this launch (the pair sums arrive per 32-link chunk)
+            l.recompute_commit = 1;  // the window is the whole path: no drho round trip through HBM
             l.alive = nullptr;
             l.partial = l.pair_old = l.pair_new = nullptr;
             l.logu0 = logu;
