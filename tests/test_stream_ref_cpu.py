@@ -126,8 +126,8 @@ def test_displace_mirror_follows_the_reference_program(name, oracle_mod):
     sim.close()
 
 
-@pytest.mark.parametrize("n_images_kin,n_level", [(0, 2), (1, 3)])
-def test_permuting_bisection_mirror_follows_the_reference_program(n_images_kin, n_level, oracle_mod):
+@pytest.mark.parametrize("n_images_kin,n_level,n_images_move", [(0, 2, 0), (1, 3, 0), (2, 3, 1)])
+def test_permuting_bisection_mirror_follows_the_reference_program(n_images_kin, n_level, n_images_move, oracle_mod):
     """PermBisectIterative (cycle selection from the permutation table, PermuteBeads, the members' Levy bridges,
     AssignParticleLabels; perm_bisect_iterative_class.h:10-222, perm_bisect_class.h:32-82) of the reference on injected
     Philox numbers against simpimc_b200.perm_moves.perm_bisect_attempt, which keeps positions by label plus the seam
@@ -142,7 +142,7 @@ def test_permuting_bisection_mirror_follows_the_reference_program(n_images_kin, 
     pair_cfg = S.egas_config(N=N, M=M, n_xy=40, n_r_long=200)      # theta = 0.1: exchange is frequent
     cfg = copy.copy(pair_cfg)
     cfg.actions = [S.ActionConfig("Kinetic", "Kinetic", "e", n_images=n_images_kin)] + list(pair_cfg.actions)
-    cfg.moves = [{"name": "PermE", "type": "PermBisectIterative", "species": "e", "n_level": n_level, "n_images": 0}]
+    cfg.moves = [{"name": "PermE", "type": "PermBisectIterative", "species": "e", "n_level": n_level, "n_images": n_images_move}]
     cfg.observables = []
     sim = refsim.RefSim(cfg, seed=1)
     if not hasattr(sim.lib, "ref_inject_random") or not hasattr(sim.lib, "ref_permutation"):
@@ -170,7 +170,8 @@ def test_permuting_bisection_mirror_follows_the_reference_program(n_images_kin, 
     n_acc = wrapped_on_permuted = 0
     for attempt in range(n_att):
         R_try, perm_try = R.copy(), perm_next.copy()
-        res = PM.perm_bisect_attempt(pair_cfg, 0, n_level, seed, attempt, 0, R_try, perm_try, action_old_new, n_images_kin=n_images_kin)
+        res = PM.perm_bisect_attempt(pair_cfg, 0, n_level, seed, attempt, 0, R_try, perm_try, action_old_new, n_images_kin=n_images_kin,
+                                     n_images_move=n_images_move)
         u, n = PM.perm_philox_numbers(pair_cfg, 0, n_level, seed, attempt, 0, res["steps"], max(res["n_perm"], 0))
         sim.inject_random(u, n)
         sim.move_do(0, 1)
@@ -194,5 +195,71 @@ def test_permuting_bisection_mirror_follows_the_reference_program(n_images_kin, 
     assert accepted[1:].sum() >= 3, accepted          # real permutations (two or more particles) were accepted
     assert wrapped_on_permuted >= 1                   # a window rolled over the seam of an already permuted path
     assert 0 < n_acc < n_att
+    o.close()
+    sim.close()
+
+
+def test_permuting_bisection_mirror_follows_the_reference_program_on_two_species(oracle_mod):
+    """The same pin for a two-species plasma: permuting moves of the electrons (species a of the e-p action) and of the
+    protons (species b of it, the (unlisted a, listed b) branch of GenerateParticlePairs, pair_action_class.h:95-112),
+    alternating; three pair actions with long range, every one of them evaluated for the listed labels."""
+    from oracle import refsim
+    from simpimc_b200 import perm_moves as PM
+    if not refsim.available():
+        pytest.skip("oracle/_ref not built")
+    n_level = 2
+    pair_cfg = S.plasma_config(Ne=5, Np=4, M=8, theta=0.25, n_xy=40, n_r_long=200, pp_action="IlkkaPairAction")
+    M = pair_cfg.n_bead
+    cfg = copy.copy(pair_cfg)
+    cfg.actions = [S.ActionConfig("KineticE", "Kinetic", "e", n_images=0), S.ActionConfig("KineticP", "Kinetic", "p", n_images=0)] + list(pair_cfg.actions)
+    cfg.moves = [{"name": "PermE", "type": "PermBisectIterative", "species": "e", "n_level": n_level, "n_images": 0},
+                 {"name": "PermP", "type": "PermBisectIterative", "species": "p", "n_level": n_level, "n_images": 0}]
+    cfg.observables = []
+    sim = refsim.RefSim(cfg, seed=1)
+    if not hasattr(sim.lib, "ref_inject_random") or not hasattr(sim.lib, "ref_permutation"):
+        pytest.skip("oracle/_ref predates the injection hooks")
+    o = oracle_mod.Oracle(pair_cfg)
+    R, nxt = [], []
+    for sp in range(2):
+        R.append(S.synthetic_paths(cfg, sp, 0, 5).copy())
+        nxt.append(np.arange(cfg.species[sp].n_part, dtype=np.int32))
+        sim.set_positions(sp, R[sp])
+        o.set_positions(sp, R[sp])
+    seed = 0x9E3700000000C1C1
+    n_acc = [0, 0]
+    n_done = [0, 0]
+    exchanged = 0
+    for attempt in range(160):
+        sp = attempt % 2
+        acts = [ai for ai, a in enumerate(pair_cfg.actions) if cfg.species[sp].name in (a.species_a, a.species_b)]
+
+        def action_old_new(labels, bead0, nb, windows):
+            for l in labels:
+                o.propose(sp, l, bead0, windows[l])
+            parts = [(sp, l) for l in labels]
+            old = sum(o.get_action(ai, 0, bead0, bead0 + nb, parts, 0) for ai in acts)
+            new = sum(o.get_action(ai, 1, bead0, bead0 + nb, parts, 0) for ai in acts)
+            for l in labels:
+                o.finish_move(sp, l, bead0, bead0 + nb, False)
+            return old, new
+
+        R_try, perm_try = R[sp].copy(), nxt[sp].copy()
+        res = PM.perm_bisect_attempt(pair_cfg, sp, n_level, seed, attempt, 0, R_try, perm_try, action_old_new)
+        u, n = PM.perm_philox_numbers(pair_cfg, sp, n_level, seed, attempt, 0, res["steps"], max(res["n_perm"], 0))
+        sim.inject_random(u, n)
+        sim.move_do(sp, 1)
+        left = sim.inject_pending(clear=True)
+        n_done[sp] += 1
+        if res["n_perm"] > 0 and res["accept"]:
+            n_acc[sp] += 1
+            assert left == (0, 0), (attempt, left)
+            exchanged += res["n_perm"] >= 2
+            R[sp], nxt[sp] = R_try, perm_try
+            o.set_positions(sp, R[sp])
+        assert sim.move_counts(sp) == (n_done[sp], n_acc[sp]), (attempt, sp, sim.move_counts(sp), n_done, n_acc)
+        assert np.array_equal(sim.permutation(sp)[1], nxt[sp]), (attempt, sp)
+        ref_R = sim.get_positions(sp, 0)
+        assert np.max(np.abs(ref_R - R[sp])) <= 1e-12 * max(1.0, np.max(np.abs(R[sp]))), (attempt, sp, res)
+    assert n_acc[0] > 0 and n_acc[1] > 0 and exchanged >= 1, (n_acc, exchanged)
     o.close()
     sim.close()
